@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: synthetic FDI foliation solve (BASELINE.json configs[1]).
+
+One step = one complete FDI solve of the synthetic 256^3-node problem of SURVEY.md section 8(d)
+(1e5 value + 1e4 gradient points, default weights, ridge 1e-8, column scaling, rtol 1e-5):
+constraint rows -> rhs/diagonal/scaling -> device CG to the reference's stopping rule.
+With N GPUs the grid is 256 x 256 x (256 N) nodes split into z-slabs (weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 256]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the meaning of every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fdi_cg_node_updates_per_second"
+UNIT = "dof-iter/s"
+BYTES_MATVEC_PER_DOF = 16.0      # read p, write q
+BYTES_ITERATION_PER_DOF = 96.0   # matvec 16 + x/r update 48 (+8 scaling) + p update 24 (+8 scaling) = 96 with scaling
+
+
+def synthetic_points(n_value, n_gradient, zscale=1.0, seed=0):
+    """f = z + 0.1 sin 2 pi x + 0.05 cos 2 pi y on the unit cube (z stretched for slabs)."""
+    rng = np.random.default_rng(seed)
+    pv = rng.uniform(0, 1, (n_value, 3))
+    pg = rng.uniform(0, 1, (n_gradient, 3))
+
+    def f(p):
+        return p[:, 2] + 0.1 * np.sin(2 * np.pi * p[:, 0]) + 0.05 * np.cos(2 * np.pi * p[:, 1])
+
+    def g(p):
+        return np.stack([0.2 * np.pi * np.cos(2 * np.pi * p[:, 0]), -0.1 * np.pi * np.sin(2 * np.pi * p[:, 1]),
+                         np.ones(p.shape[0]) / zscale], axis=1)
+
+    value = np.column_stack([pv * [1, 1, zscale], f(pv), np.ones(n_value)])
+    gradient = np.column_stack([pg * [1, 1, zscale], g(pg), np.ones(n_gradient)])
+    return value, gradient
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_step(n, n_value, n_gradient, seed=0):
+    """One solve of the scipy path (oracle port of the reference's default solve) on a bounded sample."""
+    from oracle import fdi_oracle as fo
+
+    grid, value, gradient = fo.synthetic_problem(n, n_value, n_gradient, seed=seed)
+    t0 = time.perf_counter()
+    fams = [fo.value_rows(grid, value, 1.0)] + fo.gradient_rows(grid, gradient, 1.0)
+    fams += fo.regularisation_families(grid, None)
+    timing = {}
+    c, res, S = fo.solve_reference_path(fams, grid.n_nodes, rtol=1e-5, atol=0.0, timing=timing)
+    dt = time.perf_counter() - t0
+    return grid.n_nodes, res.iterations, dt, timing
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = args.ref_n
+    nv, ng = max(100, int(1e5 * (n / 256.0) ** 3)), max(10, int(1e4 * (n / 256.0) ** 3))
+    for _ in range(args.warmup):
+        cpu_reference_step(n, nv, ng)
+    t0 = time.perf_counter()
+    units = 0
+    its = 0
+    solve_s = 0.0
+    for _ in range(args.steps):
+        dof, it, dt, timing = cpu_reference_step(n, nv, ng)
+        units += dof * it
+        its += it
+        solve_s += timing["solve_seconds"]
+    total = time.perf_counter() - t0
+    value = units / total
+    sample = (f"{n}^3-node sample of the 256^3 workload ({nv} value + {ng} gradient points), explicit A, ridge, "
+              f"column scaling, A^T A, scipy-equivalent CG rtol 1e-5; {its // max(args.steps,1)} iterations/solve")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic FDI foliation 256^3 nodes, 1e5 value + 1e4 gradient constraints (configs[1])",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "cg_only_value": units / solve_s if solve_s > 0 else None},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from loopstructural_b200 import Engine, build, engine as en, partition
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local)
+    build.build()
+    n = args.n
+    nz = n * world
+    zscale = float(world)
+    nsteps = np.array([n, n, nz])
+    step = np.array([1.0 / (n - 1), 1.0 / (n - 1), zscale / (nz - 1)])
+    bounds = partition.slab_bounds(nz, world)
+    eng = Engine(nsteps, np.zeros(3), step, slab=bounds[rank] if world > 1 else None, device=local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        ids = [Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0, device=torch.device("cuda", local))
+        eng.comm_init(ids[0], rank, world)
+    n_value, n_gradient = args.n_value * world, args.n_gradient * world
+    value, gradient = synthetic_points(n_value, n_gradient, zscale=zscale)
+    dof_global = int(n) * n * nz
+    eng.set_regularisation({})
+    eng.set_options(ridge_factor=1e-8, add_ridge=True, apply_scaling=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # pinned host staging, as a host caller of the C-ABI would hold it
+    value_h = torch.from_numpy(value).pin_memory().numpy()
+    gradient_h = torch.from_numpy(gradient).pin_memory().numpy()
+    c_host = torch.empty(eng.local_dof, dtype=torch.float64).pin_memory().numpy()
+
+    def step_resident():
+        """rows already on the device; timed: finalize-less CG solve (device-resident inputs)."""
+        c, res = eng.solve_cg(rtol=1e-5, atol=0.0, want_c=False)
+        return res
+
+    def step_e2e():
+        """public API with host buffers: H2D of the constraint arrays, setup, solve, D2H of c."""
+        eng.clear_rows()
+        eng.add_point_rows(en.ROWS_VALUE, value_h, 1.0)
+        eng.add_point_rows(en.ROWS_GRADIENT, gradient_h, 1.0)
+        c, res = eng.solve_cg(rtol=1e-5, atol=0.0, want_c=False)
+        from loopstructural_b200 import _native as nat
+        nat.check(eng._lib.lsb200_get_c(eng._h, nat.dptr(c_host)))
+        return res
+
+    # ---- device-resident arm
+    eng.add_point_rows(en.ROWS_VALUE, value_h, 1.0)
+    eng.add_point_rows(en.ROWS_GRADIENT, gradient_h, 1.0)
+    eng.finalize()
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    its = 0
+    launches = 0
+    dev_s = 0.0
+    for _ in range(args.steps):
+        res = step_resident()
+        its += res.iterations
+        launches += res.kernel_launches
+        dev_s += res.solve_seconds  # CUDA events on the engine's stream around the whole solve
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    iters_per_solve = its / max(args.steps, 1)
+
+    # ---- end-to-end arm (host buffers, copies inside the timed region)
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    its_e2e = 0
+    for _ in range(args.steps):
+        its_e2e += step_e2e().iterations
+    barrier()
+    wall_e2e = time.perf_counter() - t0
+
+    # max over ranks
+    t = torch.tensor([wall, dev_s, wall_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall, dev_s, wall_e2e = (float(v) for v in t.tolist())
+
+    # ---- roofline of the dominant operator kernel + whole iteration, CUDA events on the engine's stream
+    t_matvec = eng.time_kernel(0, reps=20)
+    t_iter = eng.time_kernel(1, reps=20)
+    peak, peak_src = measured_peak()
+    dof_local = eng.local_dof
+    ach = BYTES_MATVEC_PER_DOF * dof_local / t_matvec / 1e9
+    ach_it = BYTES_ITERATION_PER_DOF * dof_local / t_iter / 1e9
+
+    if rank == 0:
+        value_ = dof_global * its / wall
+        line = {
+            "metric": METRIC, "value": value_, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic FDI foliation {n}x{n}x{nz} nodes, {n_value} value + {n_gradient} gradient "
+                                   f"constraints, default weights, ridge 1e-8, column scaling, cg rtol 1e-5 (configs[1]"
+                                   f"{' x N z-slabs' if world > 1 else ''})",
+                       "parallelism": f"z-slabs x{world}", "l2": "node vectors (134 MB each) exceed the 126 MB L2",
+                       "dof": dof_global},
+            "solve_seconds": dev_s / max(args.steps, 1), "cg_iterations": iters_per_solve,
+            "cg_iterations_per_second": its / dev_s if dev_s > 0 else None,
+            "roofline": {"bound": "hbm", "kernel": "k_fdi_normal (regularisation normal matvec)", "achieved": ach,
+                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "seconds_per_launch": t_matvec, "bytes_per_dof": BYTES_MATVEC_PER_DOF},
+            "roofline_iteration": {"bound": "hbm", "achieved": ach_it, "peak": peak, "unit": "GB/s",
+                                   "frac": ach_it / peak, "seconds_per_iteration": t_iter,
+                                   "bytes_per_dof": BYTES_ITERATION_PER_DOF},
+            "e2e": {"value": dof_global * its_e2e / wall_e2e, "unit": UNIT,
+                    "h2d_bytes_per_step": int(value.nbytes + gradient.nbytes),
+                    "d2h_bytes_per_step": int(8 * dof_local), "ms_per_step": 1e3 * wall_e2e / max(args.steps, 1)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            t0 = time.perf_counter()
+            dof, it, dt, timing = cpu_reference_step(args.ref_n, max(100, int(1e5 * (args.ref_n / 256.0) ** 3)),
+                                                     max(10, int(1e4 * (args.ref_n / 256.0) ** 3)))
+            line["cpu_baseline"] = {
+                "value": dof * it / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"{args.ref_n}^3-node sample of the same workload, one full scipy-path solve "
+                          f"({it} iterations, {dt:.1f} s: assembly {timing['assembly_seconds']:.1f} s, preprocess "
+                          f"{timing['preprocess_seconds']:.1f} s, A^T A {timing['gram_seconds']:.1f} s, CG "
+                          f"{timing['solve_seconds']:.1f} s); scipy CG is single-threaded",
+            }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=256, help="nodes per axis per GPU")
+    ap.add_argument("--n-value", type=int, default=100_000)
+    ap.add_argument("--n-gradient", type=int, default=10_000)
+    ap.add_argument("--ref-n", type=int, default=64, help="nodes per axis of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,206 @@
+/*
+ * lsb200.h -- C ABI of the B200-native discrete implicit-interpolation engine.
+ *
+ * Drop-in boundary for LoopStructural's FiniteDifferenceInterpolator /
+ * P1Interpolator hot path (assemble -> solve -> evaluate).  The reference has
+ * no FFI of its own (pure Python); each entry point below names the reference
+ * interface it replaces, with the SURVEY.md prefixes
+ *   LI/ = /root/reference/packages/loop_interpolation/src/loop_interpolation/
+ *   LC/ = /root/reference/packages/loop_common/src/loop_common/
+ *
+ * Conventions
+ *   - plain C types only; every pointer argument is a HOST pointer unless the
+ *     name ends in _dev (then it is a device pointer on the handle's GPU);
+ *   - all functions return 0 on success, <0 on error; the message is then
+ *     available from lsb200_last_error() (thread-local);
+ *   - a handle is not re-entrant; independent handles may be used from
+ *     different threads;
+ *   - coordinates are the support's LOCAL coordinates (the reference projects
+ *     world->local before it reaches the support, LI/_geological_interpolator.py:249-286);
+ *   - node vectors (c, p, q, diag ...) are float64, length nx*ny*nz, flat index
+ *     gi = i + nx*j + nx*ny*k (LC/supports/_3d_base_structured.py:346-350).
+ *     On a z-slab handle they cover the owned planes [k0,k1) only.
+ *   - there is NO CPU fallback: every compute entry point fails with
+ *     LSB200_ERR_CUDA when no CUDA device is usable.
+ */
+#ifndef LSB200_H
+#define LSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSB200_OK 0
+#define LSB200_ERR_ARG (-1)
+#define LSB200_ERR_CUDA (-2)
+#define LSB200_ERR_STATE (-3)
+#define LSB200_ERR_COMM (-4)
+#define LSB200_ERR_ALLOC (-5)
+
+#define LSB200_ABI_VERSION 1
+
+typedef struct lsb200_ctx* lsb200_handle;
+
+/* index of the nine effective regularisation weights of lsb200_set_regularisation */
+enum {
+  LSB200_W_DXX = 0, LSB200_W_DYY = 1, LSB200_W_DZZ = 2,
+  LSB200_W_DXY = 3, LSB200_W_DXZ = 4, LSB200_W_DYZ = 5,
+  LSB200_W_DX = 6, LSB200_W_DY = 7, LSB200_W_DZ = 8
+};
+
+/* kinds of point-generated rows, lsb200_add_point_rows */
+enum {
+  LSB200_ROWS_VALUE = 0,    /* data (n,5): x y z value w        -> 1 row / point  */
+  LSB200_ROWS_GRADIENT = 1, /* data (n,7): x y z gx gy gz w     -> 2 rows / point */
+  LSB200_ROWS_NORMAL = 2,   /* data (n,7): x y z nx ny nz w     -> 3 rows / point */
+  LSB200_ROWS_TANGENT = 3   /* data (n,7): x y z tx ty tz b     -> 1 row / point  */
+};
+
+/* support kinds */
+enum { LSB200_SUPPORT_GRID = 0, LSB200_SUPPORT_TETMESH = 1 };
+
+int lsb200_abi_version(void);
+const char* lsb200_last_error(void);
+/* number of usable CUDA devices (0 without a GPU; never fails) */
+int lsb200_device_count(void);
+
+/* ---- supports --------------------------------------------------------- */
+
+/* StructuredGrid with nsteps = NODE counts (LC/supports/_3d_base_structured.py:66),
+ * owning the global z-planes [k0,k1) (k0=0,k1=nsteps[2] for a single-GPU handle).
+ * Replaces the role of StructuredGrid as the support of FiniteDifferenceInterpolator
+ * (LI/_finite_difference_interpolator.py:66-130). */
+int lsb200_create_grid(const int64_t nsteps[3], const double origin[3], const double step[3],
+                       int64_t k0, int64_t k1, int device, lsb200_handle* out);
+
+/* TetMesh on the same lattice: 5 tets per cell, parity masks
+ * (LC/supports/_3d_structured_tetra.py:28-34); nsteps = NODE counts.
+ * Support of P1Interpolator (LI/_p1interpolator.py:23-68). */
+int lsb200_create_tetmesh(const int64_t nsteps[3], const double origin[3], const double step[3],
+                          int device, lsb200_handle* out);
+
+int lsb200_destroy(lsb200_handle h);
+
+/* number of node values held by this handle (owned planes) and the support kind */
+int64_t lsb200_local_dof(lsb200_handle h);
+int lsb200_support_kind(lsb200_handle h);
+
+/* ---- regularisation ---------------------------------------------------- */
+
+/* FDI: the twelve stencil families of FiniteDifferenceInterpolator.setup_interpolator
+ * (assemble_inner LI/_finite_difference_interpolator.py:1146-1164, assemble_borders :1052-1144,
+ * _assemble_operator :643-692) are never materialised; only their EFFECTIVE row weights
+ * are given (mixed terms already divided by 4 as get_operators does,
+ * LC/supports/_3d_structured_grid.py:489-510).  Order: LSB200_W_*. */
+int lsb200_set_regularisation(lsb200_handle h, const double w[9]);
+
+/* P1: face gradient-jump regularisation, P1Interpolator.minimise_edge_jumps
+ * (LI/_p1interpolator.py:115-166) with row weight w (cgw), applied matrix-free. */
+int lsb200_set_p1_regularisation(lsb200_handle h, double w);
+
+/* ---- data rows --------------------------------------------------------- */
+
+/* Generic row ingestion = DiscreteInterpolator.add_constraints_to_least_squares
+ * (LI/_discrete_interpolator.py:316-389).  vals/cols are (n_rows,k) row-major; cols are GLOBAL
+ * node ids.  If normalise!=0 each row (and its b) is divided by the L2 norm of its listed
+ * entries (:361-366); w is the per-row weight (rows enter the normal equations with w^2).
+ * On a slab handle rows whose columns do not touch planes [k0-?]: rows are kept when every column lies in
+ * the owned+halo planes; the caller distributes rows (see loopstructural_b200.partition). */
+int lsb200_add_rows(lsb200_handle h, int64_t n_rows, int k, const double* vals, const int64_t* cols,
+                    const double* b, const double* w, int normalise);
+
+/* Device-side row generation from constraint points, replacing
+ * FDI.add_value_constraints (LI/_finite_difference_interpolator.py:236-269),
+ * add_gradient_constraints (:342-401), add_norm_constraints (:403-476),
+ * add_gradient_orthogonal_constraints (:478-539), and on a tet mesh
+ * P1Interpolator.add_value_constraints / add_norm_constraints /
+ * add_gradient_orthogonal_constraints (LI/_p1interpolator.py:73-113,248-296).
+ * data is (n,ncols) row-major as in GeologicalInterpolator.data (LI/_geological_interpolator.py:872-880);
+ * weight is the family weight (cpw / gpw / npw / tpw).  Points outside the support are dropped.
+ * n_rows_out (may be NULL) receives the number of rows created. */
+int lsb200_add_point_rows(lsb200_handle h, int kind, int64_t n, const double* data, int ncols,
+                          double weight, int64_t* n_rows_out);
+
+int lsb200_clear_rows(lsb200_handle h);
+int64_t lsb200_num_rows(lsb200_handle h);
+
+/* ---- solver ------------------------------------------------------------ */
+
+/* ridge_factor / add_ridge / apply_scaling_matrix of DiscreteInterpolator
+ * (LI/_discrete_interpolator.py:76-78; LI/_solver_pipeline.py:86-124).
+ * deterministic!=0 selects fixed-order reductions for the data rows. */
+int lsb200_set_options(lsb200_handle h, double ridge_factor, int add_ridge, int apply_scaling, int deterministic);
+
+/* Build rhs = A^T W b, diag(A^T W A + ridge^2 I) and the column scaling
+ * (preprocess_main_system, LI/_solver_pipeline.py:86-124; compute_column_scaling_matrix,
+ * LI/_discrete_interpolator.py:815-833) on the device.  Called implicitly by solve. */
+int lsb200_finalize_system(lsb200_handle h);
+
+/* Join an NCCL communicator (z-slab solve): nccl_id is the 128-byte ncclUniqueId
+ * created on rank 0 by lsb200_comm_unique_id and broadcast by the host (torch.distributed). */
+int lsb200_comm_unique_id(unsigned char id_out[128]);
+int lsb200_comm_init(lsb200_handle h, const unsigned char nccl_id[128], int rank, int nranks);
+
+typedef struct {
+  int32_t info;            /* scipy convention: 0 converged, >0 = maxiter reached */
+  int64_t iterations;      /* completed CG iterations (== number of scipy callbacks) */
+  double residual_norm;    /* ||r|| in the (column-scaled) variables the test is made in */
+  double threshold;        /* max(atol, rtol*||rhs||) in the same variables */
+  double rhs_norm;
+  double setup_seconds;    /* finalize_system: rhs, diagonal, scaling */
+  double solve_seconds;    /* CG loop, device time (CUDA events) */
+  double matvec_seconds;   /* device time inside the normal-operator kernels (profiled solves only) */
+  int64_t kernel_launches; /* kernels launched by this call */
+} lsb200_solve_info;
+
+/* Device-resident CG on (A^T W A + ridge^2 I) c = A^T W b, = solve_with_cg
+ * (LI/_solver_strategy.py:48-71) on the column-scaled system, i.e. scipy.sparse.linalg.cg
+ * with M=None on S N S, stopping when ||r|| < max(atol, rtol*||S A^T b||) tested at the top
+ * of every iteration; maxiter<=0 means 10*dof.  x0 (may be NULL) is in c-space (unscaled).
+ * c_out (may be NULL) receives the owned node values. */
+int lsb200_solve_cg(lsb200_handle h, double rtol, double atol, int64_t maxiter, const double* x0,
+                    double* c_out, lsb200_solve_info* info);
+
+/* q = (A^T W A + ridge^2 I) p (unscaled), for operator-level parity tests against
+ * LI/_finite_difference_interpolator.py:884-1050 and the explicit Gram matrix.
+ * parts: bit0 stencil/face regularisation, bit1 data rows, bit2 ridge. */
+int lsb200_apply_normal(lsb200_handle h, const double* p, double* q, int parts);
+
+int lsb200_get_rhs(lsb200_handle h, double* out);
+int lsb200_get_diagonal(lsb200_handle h, double* out);
+int lsb200_get_scaling(lsb200_handle h, double* out); /* S = diag^-1/2 (ones when scaling is off) */
+
+/* solved node values: DiscreteInterpolator.c (LI/_discrete_interpolator.py:1312-1318) */
+int lsb200_get_c(lsb200_handle h, double* out);
+int lsb200_set_c(lsb200_handle h, const double* c);
+
+/* ---- evaluation -------------------------------------------------------- */
+
+/* StructuredGrid.evaluate_value (LC/supports/_3d_structured_grid.py:295-322) +
+ * DiscreteInterpolator._evaluate_value_local (LI/_discrete_interpolator.py:1342-1362):
+ * NaN outside the support, 0.0 for rows holding NaN coordinates.  TetMesh.evaluate_value
+ * (LC/supports/_3d_structured_tetra.py:208-229) on a tet-mesh handle.  xyz is (n,3) row-major. */
+int lsb200_eval_value(lsb200_handle h, int64_t n, const double* xyz, double* out);
+
+/* StructuredGrid.evaluate_gradient (LC/supports/_3d_structured_grid.py:324-391): 0 outside;
+ * TetMesh.evaluate_gradient (LC/supports/_3d_structured_tetra.py:231-262): NaN outside.
+ * out is (n,3) row-major, local axes. */
+int lsb200_eval_gradient(lsb200_handle h, int64_t n, const double* xyz, double* out);
+
+/* same, device pointers, asynchronous on `stream` (a cudaStream_t passed as void*) */
+int lsb200_eval_value_dev(lsb200_handle h, int64_t n, const double* xyz_dev, double* out_dev, void* stream);
+int lsb200_eval_gradient_dev(lsb200_handle h, int64_t n, const double* xyz_dev, double* out_dev, void* stream);
+
+/* ---- measurement hooks (bench.py) -------------------------------------- */
+
+/* run `reps` applications of the dominant kernel on the device-resident vectors and return
+ * the average device time per launch in seconds (CUDA events on the launching stream).
+ * which: 0 = regularisation normal matvec, 1 = whole CG iteration, 2 = data-row matvec */
+int lsb200_time_kernel(lsb200_handle h, int which, int reps, double* seconds_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSB200_H */

@@ -1,0 +1,987 @@
+// C ABI of the lsb200 engine (include/lsb200.h): handle, device memory, solve driver.
+// Host code only orchestrates; all arithmetic on node vectors runs in the kernels of
+// fdi_stencil.cuh / rows.cuh / cg.cuh / eval.cuh / p1.cuh.  No CPU fallback anywhere.
+#include "../../include/lsb200.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "cg.cuh"
+#include "common.cuh"
+#include "eval.cuh"
+#include "fdi_stencil.cuh"
+#include "p1.cuh"
+#include "rows.cuh"
+
+using namespace lsb;
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      return fail(LSB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define CKL()                                                                                         \
+  do {                                                                                                \
+    cudaError_t e_ = cudaGetLastError();                                                              \
+    if (e_ != cudaSuccess)                                                                            \
+      return fail(LSB200_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------ NCCL (loaded at run time)
+// The library ships without a link-time NCCL dependency; libnccl.so.2 (the copy torch already
+// loaded, when the host process uses torch.distributed) is bound on first use.
+namespace nccl {
+typedef struct ncclComm* comm_t;
+typedef struct { char internal[128]; } unique_id;
+enum { Sum = 0 };
+enum { Float64 = 8 };
+static void* lib = nullptr;
+static int (*GetUniqueId)(unique_id*) = nullptr;
+static int (*CommInitRank)(comm_t*, int, unique_id, int) = nullptr;
+static int (*CommDestroy)(comm_t) = nullptr;
+static int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+static int (*Send)(const void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+static int (*Recv)(void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+static int (*GroupStart)() = nullptr;
+static int (*GroupEnd)() = nullptr;
+static const char* (*GetErrorString)(int) = nullptr;
+static int load() {
+  if (lib) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  if (!lib) return fail(LSB200_ERR_COMM, "cannot load libnccl.so.2: %s", dlerror());
+#define SYM(name)                                                                   \
+  *(void**)(&name) = dlsym(lib, "nccl" #name);                                      \
+  if (!name) return fail(LSB200_ERR_COMM, "libnccl lacks symbol nccl%s", #name);
+  SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(AllReduce) SYM(Send) SYM(Recv) SYM(GroupStart)
+      SYM(GroupEnd) SYM(GetErrorString)
+#undef SYM
+  return 0;
+}
+}  // namespace nccl
+#define NCK(call)                                                                                     \
+  do {                                                                                                \
+    int e_ = (call);                                                                                  \
+    if (e_ != 0) return fail(LSB200_ERR_COMM, "%s failed: %s", #call, nccl::GetErrorString(e_));       \
+  } while (0)
+
+// ------------------------------------------------------------------ context
+constexpr int MAX_PARTIALS = 1 << 16;
+constexpr int VEC_NT = 256;
+
+struct lsb200_ctx {
+  int kind = LSB200_SUPPORT_GRID;
+  int device = 0;
+  GridDesc g{};
+  double ew[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double p1_w = 0.0;
+  double ridge = 1e-8;
+  int add_ridge = 1, apply_scaling = 1, deterministic = 0;
+  cudaStream_t stream = nullptr;
+  double *x = nullptr, *r = nullptr, *p = nullptr, *q = nullptr, *rhs = nullptr, *diag = nullptr, *s2 = nullptr;
+  std::vector<RowBlock> pending;  // as added
+  std::vector<RowBlock> blocks;   // merged per width at finalize
+  long long rows_kept = 0;
+  CgScalars* sc = nullptr;
+  CgScalars* sc_host = nullptr;  // pinned
+  double* partials = nullptr;    // 3 * MAX_PARTIALS
+  unsigned int* counters = nullptr;
+  unsigned long long* status = nullptr;  // 2 words
+  bool finalized = false;
+  bool have_c = false;
+  nccl::comm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  int stencil_cfg = 0;
+  int cz = 0;
+  dim3 sgrid;
+  int sm_count = 148;
+  long long launches = 0;
+  double setup_seconds = 0.0;
+};
+
+static int vec_blocks(const lsb200_ctx* h, long long n, int per_thread = 4) {
+  long long b = (n + (long long)VEC_NT * per_thread - 1) / ((long long)VEC_NT * per_thread);
+  long long cap = (long long)h->sm_count * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+static StencilWeights make_weights(const lsb200_ctx* h) {
+  StencilWeights w;
+  const double* e = h->ew;
+  w.axx = e[LSB200_W_DXX] * e[LSB200_W_DXX];
+  w.ayy = e[LSB200_W_DYY] * e[LSB200_W_DYY];
+  w.azz = e[LSB200_W_DZZ] * e[LSB200_W_DZZ];
+  w.bxy = 0.25 * e[LSB200_W_DXY] * e[LSB200_W_DXY];
+  w.bxz = 0.25 * e[LSB200_W_DXZ] * e[LSB200_W_DXZ];
+  w.byz = 0.25 * e[LSB200_W_DYZ] * e[LSB200_W_DYZ];
+  w.dx = e[LSB200_W_DX] * e[LSB200_W_DX];
+  w.dy = e[LSB200_W_DY] * e[LSB200_W_DY];
+  w.dz = e[LSB200_W_DZ] * e[LSB200_W_DZ];
+  w.ridge2 = h->add_ridge ? h->ridge * h->ridge : 0.0;
+  return w;
+}
+
+static double* owned_ptr(const lsb200_ctx* h, double* v) { return v + (long long)HALO * h->g.plane; }
+
+// choose the z-chunk length of the stencil kernel: fill the SMs in whole waves
+template <int XB, int TXT, int TYT>
+static void plan_stencil(lsb200_ctx* h, int ctas_per_sm) {
+  using C = StencilCfg<XB, TXT, TYT>;
+  const int tiles_x = (h->g.nx + C::TX - 1) / C::TX, tiles_y = (h->g.ny + C::TY - 1) / C::TY;
+  const long long tiles = (long long)tiles_x * tiles_y;
+  const long long slots = (long long)h->sm_count * ctas_per_sm;
+  int best_nch = 1;
+  double best = -1.0;
+  const int max_nch = std::max(1, h->g.nzl / 4);
+  for (int nch = 1; nch <= max_nch && nch <= 4096; ++nch) {
+    const int cz = (h->g.nzl + nch - 1) / nch;
+    const int real = (h->g.nzl + cz - 1) / cz;
+    const long long ctas = tiles * real;
+    if (ctas > MAX_PARTIALS) break;
+    const long long waves = (ctas + slots - 1) / slots;
+    const double eff = (double)ctas / (double)(waves * slots) * (double)cz / (double)(cz + 2 * HALO);
+    if (eff > best + 1e-9) {
+      best = eff;
+      best_nch = real;
+      h->cz = cz;
+    }
+  }
+  (void)best_nch;
+  const int real = (h->g.nzl + h->cz - 1) / h->cz;
+  h->sgrid = dim3(tiles_x, tiles_y, real);
+}
+
+static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode) {
+  const StencilWeights w = make_weights(h);
+  double* part = h->partials;
+  unsigned int* cnt = h->counters + 0;
+  switch (h->stencil_cfg) {
+    case 1:
+      k_fdi_normal<2, 32, 16><<<h->sgrid, dim3(32, 16), 0, h->stream>>>(h->g, w, p, q, h->cz, part, cnt, h->sc, cg_mode);
+      break;
+    case 2:
+      k_fdi_normal<1, 32, 16><<<h->sgrid, dim3(32, 16), 0, h->stream>>>(h->g, w, p, q, h->cz, part, cnt, h->sc, cg_mode);
+      break;
+    case 3:
+      k_fdi_normal<4, 32, 8><<<h->sgrid, dim3(32, 8), 0, h->stream>>>(h->g, w, p, q, h->cz, part, cnt, h->sc, cg_mode);
+      break;
+    default:
+      k_fdi_normal<2, 32, 8><<<h->sgrid, dim3(32, 8), 0, h->stream>>>(h->g, w, p, q, h->cz, part, cnt, h->sc, cg_mode);
+  }
+  CKL();
+  h->launches++;
+  return 0;
+}
+
+static void plan(lsb200_ctx* h) {
+  const char* env = getenv("LSB200_STENCIL_CFG");
+  h->stencil_cfg = env ? atoi(env) : 0;
+  switch (h->stencil_cfg) {
+    case 1: plan_stencil<2, 32, 16>(h, 1); break;
+    case 2: plan_stencil<1, 32, 16>(h, 2); break;
+    case 3: plan_stencil<4, 32, 8>(h, 2); break;
+    default: h->stencil_cfg = 0; plan_stencil<2, 32, 8>(h, 2);
+  }
+  const char* cz = getenv("LSB200_STENCIL_CZ");
+  if (cz && atoi(cz) > 0) {
+    h->cz = atoi(cz);
+    h->sgrid.z = (h->g.nzl + h->cz - 1) / h->cz;
+  }
+}
+
+// the regularisation part of the normal operator (writes every owned entry of q, sets pq_part[0])
+static int launch_regularisation(lsb200_ctx* h, const double* p, double* q, int cg_mode) {
+  if (h->kind == LSB200_SUPPORT_GRID) return launch_stencil(h, p, q, cg_mode);
+  return p1_launch_face_normal(h->g, h->p1_w, h->add_ridge ? h->ridge * h->ridge : 0.0, p, q, h->partials,
+                               h->counters + 0, h->sc, cg_mode, h->sm_count, h->stream, &h->launches)
+             ? fail(LSB200_ERR_CUDA, "p1 face kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()))
+             : 0;
+}
+
+static int launch_rows(lsb200_ctx* h, const double* p, double* q, int cg_mode) {
+  bool first = true;
+  for (const RowBlock& rb : h->blocks) {
+    if (rb.n == 0) continue;
+    long long nb = (rb.n + VEC_NT - 1) / VEC_NT;
+    if (nb > h->sm_count * 16) nb = h->sm_count * 16;
+    k_rows_normal<VEC_NT><<<(int)nb, VEC_NT, 0, h->stream>>>(h->g, rb, p, q, h->partials + MAX_PARTIALS,
+                                                             h->counters + 1, h->sc, cg_mode, first ? 1 : 0);
+    CKL();
+    h->launches++;
+    first = false;
+  }
+  return 0;
+}
+
+static int halo_exchange(lsb200_ctx* h, double* v) {
+  if (h->nranks == 1) return 0;
+  const size_t cnt = (size_t)HALO * h->g.plane;
+  double* lo_halo = v;                                                  // planes k0-2,k0-1
+  double* lo_own = v + (long long)HALO * h->g.plane;                    // planes k0,k0+1
+  double* hi_own = v + (long long)h->g.nzl * h->g.plane;                // planes k1-2,k1-1
+  double* hi_halo = v + (long long)(h->g.nzl + HALO) * h->g.plane;      // planes k1,k1+1
+  NCK(nccl::GroupStart());
+  if (h->rank > 0) {
+    NCK(nccl::Send(lo_own, cnt, nccl::Float64, h->rank - 1, h->comm, h->stream));
+    NCK(nccl::Recv(lo_halo, cnt, nccl::Float64, h->rank - 1, h->comm, h->stream));
+  }
+  if (h->rank < h->nranks - 1) {
+    NCK(nccl::Send(hi_own, cnt, nccl::Float64, h->rank + 1, h->comm, h->stream));
+    NCK(nccl::Recv(hi_halo, cnt, nccl::Float64, h->rank + 1, h->comm, h->stream));
+  }
+  NCK(nccl::GroupEnd());
+  return 0;
+}
+
+static int allreduce_scalar(lsb200_ctx* h, double* dev) {
+  if (h->nranks == 1) return 0;
+  NCK(nccl::AllReduce(dev, dev, 1, nccl::Float64, nccl::Sum, h->comm, h->stream));
+  return 0;
+}
+
+static int free_block(RowBlock& rb) {
+  cudaFree(rb.vals);
+  cudaFree(rb.cols);
+  cudaFree(rb.w2);
+  cudaFree(rb.b);
+  rb = RowBlock{};
+  return 0;
+}
+
+static int alloc_block(RowBlock& rb, long long n, int k) {
+  rb.n = n;
+  rb.k = k;
+  const long long m = std::max<long long>(n, 1);
+  CK(cudaMalloc(&rb.vals, sizeof(double) * m * k));
+  CK(cudaMalloc(&rb.cols, sizeof(int) * m * k));
+  CK(cudaMalloc(&rb.w2, sizeof(double) * m));
+  CK(cudaMalloc(&rb.b, sizeof(double) * m));
+  return 0;
+}
+
+static int ensure_vectors(lsb200_ctx* h) {
+  if (h->x) return 0;
+  const size_t bytes = sizeof(double) * (size_t)h->g.nall;
+  double** v[] = {&h->x, &h->r, &h->p, &h->q, &h->rhs, &h->diag, &h->s2};
+  for (double** pv : v) {
+    cudaError_t e = cudaMalloc(pv, bytes);
+    if (e != cudaSuccess) return fail(LSB200_ERR_ALLOC, "cudaMalloc of a node vector (%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    CK(cudaMemsetAsync(*pv, 0, bytes, h->stream));
+  }
+  return 0;
+}
+
+// host (nx*ny*nzl, unpitched) <-> device (pitched, halo planes) copies of the owned planes
+static int copy_in(lsb200_ctx* h, double* dev, const double* host) {
+  CK(cudaMemcpy2DAsync(owned_ptr(h, dev), sizeof(double) * h->g.pitch, host, sizeof(double) * h->g.nx,
+                       sizeof(double) * h->g.nx, (size_t)h->g.ny * h->g.nzl, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+static int copy_out(lsb200_ctx* h, double* host, const double* dev) {
+  CK(cudaMemcpy2DAsync(host, sizeof(double) * h->g.nx, owned_ptr(h, const_cast<double*>(dev)), sizeof(double) * h->g.pitch,
+                       sizeof(double) * h->g.nx, (size_t)h->g.ny * h->g.nzl, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------ API
+extern "C" {
+
+int lsb200_abi_version(void) { return LSB200_ABI_VERSION; }
+const char* lsb200_last_error(void) { return g_err; }
+int lsb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+static int create_common(int kind, const int64_t nsteps[3], const double origin[3], const double step[3], int64_t k0,
+                         int64_t k1, int device, lsb200_handle* out) {
+  if (!out || !nsteps || !origin || !step) return fail(LSB200_ERR_ARG, "null argument");
+  *out = nullptr;
+  for (int a = 0; a < 3; ++a) {
+    if (nsteps[a] < 2) return fail(LSB200_ERR_ARG, "nsteps[%d]=%lld: need at least 2 nodes per axis", a, (long long)nsteps[a]);
+    if (!(step[a] > 0.0)) return fail(LSB200_ERR_ARG, "step[%d] must be positive", a);
+  }
+  if (k0 < 0 || k1 > nsteps[2] || k1 <= k0) return fail(LSB200_ERR_ARG, "bad slab [%lld,%lld) of %lld planes", (long long)k0, (long long)k1, (long long)nsteps[2]);
+  int ndev = lsb200_device_count();
+  if (ndev <= 0) return fail(LSB200_ERR_CUDA, "no CUDA device available (this engine has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(LSB200_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+  const long long plane = (long long)nsteps[0] * nsteps[1];
+  if (plane * (k1 - k0 + 2 * HALO) >= 2147483647LL)
+    return fail(LSB200_ERR_ARG, "local slab has %lld node slots; the limit per handle is 2^31-1 (use more z-slabs)", plane * (k1 - k0 + 2 * HALO));
+  CK(cudaSetDevice(device));
+  lsb200_ctx* h = new lsb200_ctx();
+  h->kind = kind;
+  h->device = device;
+  GridDesc& g = h->g;
+  g.nx = (int)nsteps[0]; g.ny = (int)nsteps[1]; g.nz = (int)nsteps[2];
+  g.k0 = (int)k0; g.k1 = (int)k1; g.nzl = (int)(k1 - k0);
+  g.pitch = g.nx;
+  g.plane = (long long)g.pitch * g.ny;
+  g.nloc = g.plane * g.nzl;
+  g.nall = g.plane * (g.nzl + 2 * HALO);
+  for (int a = 0; a < 3; ++a) { g.origin[a] = origin[a]; g.step[a] = step[a]; }
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  h->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaMalloc(&h->sc, sizeof(CgScalars)));
+  CK(cudaMemset(h->sc, 0, sizeof(CgScalars)));
+  CK(cudaMallocHost(&h->sc_host, sizeof(CgScalars)));
+  CK(cudaMalloc(&h->partials, sizeof(double) * 3 * MAX_PARTIALS));
+  CK(cudaMalloc(&h->counters, sizeof(unsigned int) * 8));
+  CK(cudaMemset(h->counters, 0, sizeof(unsigned int) * 8));
+  CK(cudaMalloc(&h->status, sizeof(unsigned long long) * 2));
+  plan(h);
+  *out = h;
+  return 0;
+}
+
+int lsb200_create_grid(const int64_t nsteps[3], const double origin[3], const double step[3], int64_t k0, int64_t k1,
+                       int device, lsb200_handle* out) {
+  return create_common(LSB200_SUPPORT_GRID, nsteps, origin, step, k0, k1, device, out);
+}
+
+int lsb200_create_tetmesh(const int64_t nsteps[3], const double origin[3], const double step[3], int device,
+                          lsb200_handle* out) {
+  if (!nsteps) return fail(LSB200_ERR_ARG, "null argument");
+  return create_common(LSB200_SUPPORT_TETMESH, nsteps, origin, step, 0, nsteps[2], device, out);
+}
+
+int lsb200_destroy(lsb200_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (RowBlock& rb : h->pending) free_block(rb);
+  for (RowBlock& rb : h->blocks) free_block(rb);
+  double* v[] = {h->x, h->r, h->p, h->q, h->rhs, h->diag, h->s2};
+  for (double* pv : v) cudaFree(pv);
+  cudaFree(h->sc);
+  cudaFreeHost(h->sc_host);
+  cudaFree(h->partials);
+  cudaFree(h->counters);
+  cudaFree(h->status);
+  if (h->comm) nccl::CommDestroy(h->comm);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+int64_t lsb200_local_dof(lsb200_handle h) { return h ? (int64_t)h->g.nx * h->g.ny * h->g.nzl : 0; }
+int lsb200_support_kind(lsb200_handle h) { return h ? h->kind : -1; }
+
+int lsb200_set_regularisation(lsb200_handle h, const double w[9]) {
+  if (!h || !w) return fail(LSB200_ERR_ARG, "null argument");
+  if (h->kind != LSB200_SUPPORT_GRID) return fail(LSB200_ERR_STATE, "stencil regularisation needs a grid handle");
+  for (int i = 0; i < 9; ++i) {
+    if (!(w[i] == w[i])) return fail(LSB200_ERR_ARG, "regularisation weight %d is NaN", i);
+    h->ew[i] = w[i];
+  }
+  h->finalized = false;
+  return 0;
+}
+
+int lsb200_set_p1_regularisation(lsb200_handle h, double w) {
+  if (!h) return fail(LSB200_ERR_ARG, "null argument");
+  if (h->kind != LSB200_SUPPORT_TETMESH) return fail(LSB200_ERR_STATE, "face-jump regularisation needs a tet-mesh handle");
+  h->p1_w = w;
+  h->finalized = false;
+  return 0;
+}
+
+int lsb200_set_options(lsb200_handle h, double ridge_factor, int add_ridge, int apply_scaling, int deterministic) {
+  if (!h) return fail(LSB200_ERR_ARG, "null argument");
+  h->ridge = ridge_factor;
+  h->add_ridge = add_ridge;
+  h->apply_scaling = apply_scaling;
+  h->deterministic = deterministic;
+  h->finalized = false;
+  return 0;
+}
+
+static int width_class(int k) {
+  int c = 4;
+  while (c < k) c <<= 1;
+  return c;
+}
+
+int lsb200_add_rows(lsb200_handle h, int64_t n_rows, int k, const double* vals, const int64_t* cols, const double* b,
+                    const double* w, int normalise) {
+  if (!h) return fail(LSB200_ERR_ARG, "null handle");
+  if (n_rows < 0 || k < 1 || k > 64) return fail(LSB200_ERR_ARG, "bad row block shape (%lld,%d)", (long long)n_rows, k);
+  if (n_rows == 0) return 0;
+  if (!vals || !cols || !b || !w) return fail(LSB200_ERR_ARG, "null row arrays");
+  const long long dof = (long long)h->g.nx * h->g.ny * h->g.nz;
+  for (long long t = 0; t < (long long)n_rows * k; ++t)
+    if (cols[t] < 0 || cols[t] >= dof) return fail(LSB200_ERR_ARG, "column id %lld outside [0,%lld)", (long long)cols[t], dof);
+  CK(cudaSetDevice(h->device));
+  double *dv = nullptr, *db = nullptr, *dw = nullptr;
+  long long* dc = nullptr;
+  CK(cudaMalloc(&dv, sizeof(double) * n_rows * k));
+  CK(cudaMalloc(&dc, sizeof(long long) * n_rows * k));
+  CK(cudaMalloc(&db, sizeof(double) * n_rows));
+  CK(cudaMalloc(&dw, sizeof(double) * n_rows));
+  CK(cudaMemcpyAsync(dv, vals, sizeof(double) * n_rows * k, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(dc, cols, sizeof(long long) * n_rows * k, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(db, b, sizeof(double) * n_rows, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(dw, w, sizeof(double) * n_rows, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * 2, h->stream));
+  RowBlock rb{};
+  int rc = alloc_block(rb, n_rows, width_class(k));
+  if (rc) return rc;
+  CK(cudaMemsetAsync(rb.cols, 0xff, sizeof(int) * rb.n * rb.k, h->stream));
+  CK(cudaMemsetAsync(rb.vals, 0, sizeof(double) * rb.n * rb.k, h->stream));
+  const int nb = (int)std::min<long long>((n_rows + 255) / 256, 4096);
+  k_rows_ingest<<<nb, 256, 0, h->stream>>>(h->g, n_rows, k, dv, dc, db, dw, normalise, rb, 0, h->status);
+  CKL();
+  h->launches++;
+  unsigned long long st[2];
+  CK(cudaMemcpyAsync(st, h->status, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(dv); cudaFree(dc); cudaFree(db); cudaFree(dw);
+  if (st[1]) {
+    free_block(rb);
+    return fail(LSB200_ERR_ARG, "a row touching the owned planes [%d,%d) has a column outside the halo planes", h->g.k0, h->g.k1);
+  }
+  h->rows_kept += (long long)st[0];
+  h->pending.push_back(rb);
+  h->finalized = false;
+  return 0;
+}
+
+int lsb200_add_point_rows(lsb200_handle h, int kind, int64_t n, const double* data, int ncols, double weight,
+                          int64_t* n_rows_out) {
+  if (!h) return fail(LSB200_ERR_ARG, "null handle");
+  if (n_rows_out) *n_rows_out = 0;
+  if (n < 0) return fail(LSB200_ERR_ARG, "negative point count");
+  const int need = kind == LSB200_ROWS_VALUE ? 5 : 7;
+  if (kind < LSB200_ROWS_VALUE || kind > LSB200_ROWS_TANGENT) return fail(LSB200_ERR_ARG, "unknown row kind %d", kind);
+  if (ncols < need) return fail(LSB200_ERR_ARG, "row kind %d needs %d data columns, got %d", kind, need, ncols);
+  if (n == 0) return 0;
+  if (!data) return fail(LSB200_ERR_ARG, "null data");
+  CK(cudaSetDevice(h->device));
+  const int mult = kind == LSB200_ROWS_GRADIENT ? 2 : (kind == LSB200_ROWS_NORMAL ? 3 : (kind == LSB200_ROWS_VALUE ? 1 : 1));
+  double* dd = nullptr;
+  CK(cudaMalloc(&dd, sizeof(double) * n * ncols));
+  CK(cudaMemcpyAsync(dd, data, sizeof(double) * n * ncols, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * 2, h->stream));
+  RowBlock rb{};
+  const int k = h->kind == LSB200_SUPPORT_GRID ? 8 : 4;
+  int rc = alloc_block(rb, n * mult, k);
+  if (rc) return rc;
+  const int nb = (int)std::min<long long>((n + 127) / 128, 4096);
+  if (h->kind == LSB200_SUPPORT_GRID) {
+    k_fdi_point_rows<<<nb, 128, 0, h->stream>>>(h->g, kind, n, dd, ncols, weight, rb, 0, h->status);
+  } else {
+    if (kind == LSB200_ROWS_GRADIENT) {
+      // P1Interpolator.add_gradient_constraints is a no-op (LI/_p1interpolator.py:70-71)
+      cudaFree(dd);
+      free_block(rb);
+      return 0;
+    }
+    k_p1_point_rows<<<nb, 128, 0, h->stream>>>(h->g, kind, n, dd, ncols, weight, rb, 0, h->status);
+  }
+  CKL();
+  h->launches++;
+  unsigned long long st[2];
+  CK(cudaMemcpyAsync(st, h->status, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(dd);
+  if (n_rows_out) *n_rows_out = (int64_t)st[0];
+  h->rows_kept += (long long)st[0];
+  h->pending.push_back(rb);
+  h->finalized = false;
+  return 0;
+}
+
+int lsb200_clear_rows(lsb200_handle h) {
+  if (!h) return fail(LSB200_ERR_ARG, "null handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  for (RowBlock& rb : h->pending) free_block(rb);
+  for (RowBlock& rb : h->blocks) free_block(rb);
+  h->pending.clear();
+  h->blocks.clear();
+  h->rows_kept = 0;
+  h->finalized = false;
+  return 0;
+}
+
+int64_t lsb200_num_rows(lsb200_handle h) { return h ? h->rows_kept : 0; }
+
+// merge pending blocks into one ELL block per width class
+static int merge_blocks(lsb200_ctx* h) {
+  if (h->pending.empty()) return 0;
+  std::vector<RowBlock> all = h->blocks;
+  all.insert(all.end(), h->pending.begin(), h->pending.end());
+  h->blocks.clear();
+  h->pending.clear();
+  std::vector<int> widths;
+  for (const RowBlock& rb : all)
+    if (std::find(widths.begin(), widths.end(), rb.k) == widths.end()) widths.push_back(rb.k);
+  std::sort(widths.begin(), widths.end());
+  for (int k : widths) {
+    long long n = 0;
+    int cnt = 0;
+    for (const RowBlock& rb : all)
+      if (rb.k == k) { n += rb.n; cnt++; }
+    if (cnt == 1) {
+      for (RowBlock& rb : all)
+        if (rb.k == k) { h->blocks.push_back(rb); rb = RowBlock{}; }
+      continue;
+    }
+    RowBlock m{};
+    int rc = alloc_block(m, n, k);
+    if (rc) return rc;
+    long long off = 0;
+    for (RowBlock& rb : all) {
+      if (rb.k != k) continue;
+      for (int j = 0; j < k; ++j) {
+        CK(cudaMemcpyAsync(m.vals + j * m.n + off, rb.vals + j * rb.n, sizeof(double) * rb.n, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(m.cols + j * m.n + off, rb.cols + j * rb.n, sizeof(int) * rb.n, cudaMemcpyDeviceToDevice, h->stream));
+      }
+      CK(cudaMemcpyAsync(m.w2 + off, rb.w2, sizeof(double) * rb.n, cudaMemcpyDeviceToDevice, h->stream));
+      CK(cudaMemcpyAsync(m.b + off, rb.b, sizeof(double) * rb.n, cudaMemcpyDeviceToDevice, h->stream));
+      off += rb.n;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    for (RowBlock& rb : all)
+      if (rb.k == k) free_block(rb);
+    h->blocks.push_back(m);
+  }
+  return 0;
+}
+
+int lsb200_finalize_system(lsb200_handle h) {
+  if (!h) return fail(LSB200_ERR_ARG, "null handle");
+  if (h->finalized) return 0;
+  CK(cudaSetDevice(h->device));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, h->stream));
+  int rc = ensure_vectors(h);
+  if (rc) return rc;
+  rc = merge_blocks(h);
+  if (rc) return rc;
+  const size_t bytes = sizeof(double) * (size_t)h->g.nall;
+  CK(cudaMemsetAsync(h->rhs, 0, bytes, h->stream));
+  CK(cudaMemsetAsync(h->diag, 0, bytes, h->stream));
+  // regularisation diagonal (+ ridge^2)
+  if (h->kind == LSB200_SUPPORT_GRID) {
+    k_fdi_diag<<<vec_blocks(h, h->g.nloc, 1), VEC_NT, 0, h->stream>>>(h->g, make_weights(h), h->diag);
+    CKL();
+    h->launches++;
+  } else {
+    if (p1_launch_face_diag(h->g, h->p1_w, h->add_ridge ? h->ridge * h->ridge : 0.0, h->diag, h->sm_count, h->stream, &h->launches))
+      return fail(LSB200_ERR_CUDA, "p1 diagonal kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  for (const RowBlock& rb : h->blocks) {
+    if (rb.n == 0) continue;
+    const int nb = (int)std::min<long long>((rb.n + 255) / 256, 8192);
+    k_rows_rhs<<<nb, 256, 0, h->stream>>>(h->g, rb, h->rhs);
+    CKL();
+    k_rows_diag<<<nb, 256, 0, h->stream>>>(h->g, rb, h->diag);
+    CKL();
+    h->launches += 2;
+  }
+  if (h->apply_scaling) {
+    k_scaling_from_diag<<<vec_blocks(h, h->g.nloc, 1), VEC_NT, 0, h->stream>>>(h->g.nloc, owned_ptr(h, h->diag), owned_ptr(h, h->s2));
+    CKL();
+    h->launches++;
+  }
+  CK(cudaEventRecord(e1, h->stream));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  h->setup_seconds = ms * 1e-3;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  h->finalized = true;
+  return 0;
+}
+
+int lsb200_comm_unique_id(unsigned char id_out[128]) {
+  if (!id_out) return fail(LSB200_ERR_ARG, "null argument");
+  int rc = nccl::load();
+  if (rc) return rc;
+  nccl::unique_id id;
+  NCK(nccl::GetUniqueId(&id));
+  memcpy(id_out, id.internal, 128);
+  return 0;
+}
+
+int lsb200_comm_init(lsb200_handle h, const unsigned char nccl_id[128], int rank, int nranks) {
+  if (!h || !nccl_id) return fail(LSB200_ERR_ARG, "null argument");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(LSB200_ERR_ARG, "bad rank %d of %d", rank, nranks);
+  if (nranks == 1) { h->rank = 0; h->nranks = 1; return 0; }
+  int rc = nccl::load();
+  if (rc) return rc;
+  CK(cudaSetDevice(h->device));
+  nccl::unique_id id;
+  memcpy(id.internal, nccl_id, 128);
+  NCK(nccl::CommInitRank(&h->comm, nranks, id, rank));
+  h->rank = rank;
+  h->nranks = nranks;
+  return 0;
+}
+
+// q = N p on device vectors (p must have its halo planes filled on slab handles)
+static int apply_normal_dev(lsb200_ctx* h, const double* p, double* q, int parts, int cg_mode) {
+  int rc;
+  if (parts & 1) {
+    if ((rc = launch_regularisation(h, p, q, cg_mode))) return rc;
+  } else if (!cg_mode) {
+    CK(cudaMemsetAsync(q, 0, sizeof(double) * (size_t)h->g.nall, h->stream));
+  }
+  if (parts & 2)
+    if ((rc = launch_rows(h, p, q, cg_mode))) return rc;
+  return 0;
+}
+
+int lsb200_apply_normal(lsb200_handle h, const double* p, double* q, int parts) {
+  if (!h || !p || !q) return fail(LSB200_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_vectors(h);
+  if (rc) return rc;
+  if ((rc = merge_blocks(h))) return rc;
+  if ((rc = copy_in(h, h->p, p))) return rc;
+  if ((rc = halo_exchange(h, h->p))) return rc;
+  // ridge is applied inside the regularisation kernel; switch it off unless asked for
+  if (!(parts & 1) && (parts & 4))
+    return fail(LSB200_ERR_ARG, "the ridge part is applied together with the regularisation part (parts bit0)");
+  const int keep = h->add_ridge;
+  if (!(parts & 4)) h->add_ridge = 0;
+  rc = apply_normal_dev(h, h->p, h->q, parts & 3, 0);
+  h->add_ridge = keep;
+  if (rc) return rc;
+  return copy_out(h, q, h->q);
+}
+
+int lsb200_get_rhs(lsb200_handle h, double* out) {
+  if (!h || !out) return fail(LSB200_ERR_ARG, "null argument");
+  int rc = lsb200_finalize_system(h);
+  if (rc) return rc;
+  return copy_out(h, out, h->rhs);
+}
+int lsb200_get_diagonal(lsb200_handle h, double* out) {
+  if (!h || !out) return fail(LSB200_ERR_ARG, "null argument");
+  int rc = lsb200_finalize_system(h);
+  if (rc) return rc;
+  return copy_out(h, out, h->diag);
+}
+int lsb200_get_scaling(lsb200_handle h, double* out) {
+  if (!h || !out) return fail(LSB200_ERR_ARG, "null argument");
+  int rc = lsb200_finalize_system(h);
+  if (rc) return rc;
+  if ((rc = copy_out(h, out, h->s2))) return rc;
+  const long long n = (long long)h->g.nx * h->g.ny * h->g.nzl;
+  for (long long i = 0; i < n; ++i) out[i] = h->apply_scaling ? sqrt(out[i]) : 1.0;
+  return 0;
+}
+
+int lsb200_get_c(lsb200_handle h, double* out) {
+  if (!h || !out) return fail(LSB200_ERR_ARG, "null argument");
+  if (!h->have_c) return fail(LSB200_ERR_STATE, "no solution on the device yet (solve or set_c first)");
+  CK(cudaSetDevice(h->device));
+  return copy_out(h, out, h->x);
+}
+int lsb200_set_c(lsb200_handle h, const double* c) {
+  if (!h || !c) return fail(LSB200_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_vectors(h);
+  if (rc) return rc;
+  if ((rc = copy_in(h, h->x, c))) return rc;
+  h->have_c = true;
+  return 0;
+}
+
+// one CG iteration enqueued on the stream (no host synchronisation)
+static int enqueue_iteration(lsb200_ctx* h) {
+  const long long n = h->g.nloc;
+  const double* s2 = h->apply_scaling ? owned_ptr(h, h->s2) : nullptr;
+  int rc;
+  k_cg_update_p<VEC_NT><<<vec_blocks(h, n), VEC_NT, 0, h->stream>>>(n, s2, owned_ptr(h, h->r), owned_ptr(h, h->p), h->sc);
+  CKL();
+  h->launches++;
+  if ((rc = halo_exchange(h, h->p))) return rc;
+  if ((rc = apply_normal_dev(h, h->p, h->q, 3, 1))) return rc;
+  if (h->nranks > 1) {
+    k_cg_pack_pq<<<1, 1, 0, h->stream>>>(h->sc);
+    CKL();
+    h->launches++;
+    if ((rc = allreduce_scalar(h, &h->sc->pq))) return rc;
+  }
+  k_cg_update_xr<VEC_NT><<<vec_blocks(h, n), VEC_NT, 0, h->stream>>>(n, owned_ptr(h, h->p), owned_ptr(h, h->q), owned_ptr(h, h->x),
+                                                                      owned_ptr(h, h->r), s2, h->partials + 2 * MAX_PARTIALS,
+                                                                      h->counters + 2, h->sc);
+  CKL();
+  h->launches++;
+  if (h->nranks > 1) {
+    if ((rc = allreduce_scalar(h, &h->sc->rho_new))) return rc;
+    k_cg_scalar_step<<<1, 1, 0, h->stream>>>(h->sc);
+    CKL();
+    h->launches++;
+  }
+  return 0;
+}
+
+int lsb200_solve_cg(lsb200_handle h, double rtol, double atol, int64_t maxiter, const double* x0, double* c_out,
+                    lsb200_solve_info* info) {
+  if (!h) return fail(LSB200_ERR_ARG, "null handle");
+  if (!(rtol >= 0.0) || !(atol >= 0.0)) return fail(LSB200_ERR_ARG, "rtol/atol must be non-negative");
+  CK(cudaSetDevice(h->device));
+  const long long launches0 = h->launches;
+  int rc = lsb200_finalize_system(h);
+  if (rc) return rc;
+  const long long n = h->g.nloc;
+  const size_t bytes = sizeof(double) * (size_t)h->g.nall;
+  const double* s2 = h->apply_scaling ? owned_ptr(h, h->s2) : nullptr;
+  if (!h->blocks.empty() || true) {
+    // pq_part[1] must read 0 when there are no data rows
+    CK(cudaMemsetAsync(h->sc, 0, sizeof(CgScalars), h->stream));
+  }
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, h->stream));
+
+  // ||S b||^2
+  CgScalars* sc = h->sc;
+  k_cg_residual<VEC_NT><<<vec_blocks(h, n), VEC_NT, 0, h->stream>>>(n, owned_ptr(h, h->rhs), nullptr, nullptr, s2,
+                                                                     h->partials + 2 * MAX_PARTIALS, h->counters + 2, &sc->rho_new);
+  CKL();
+  h->launches++;
+  if ((rc = allreduce_scalar(h, &sc->rho_new))) return rc;
+  CK(cudaMemcpyAsync(h->sc_host, sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const double bnorm = sqrt(h->sc_host->rho_new);
+  const double thr = std::max(atol, rtol * bnorm);
+  const long long dof_global = (long long)h->g.nx * h->g.ny * h->g.nz;
+  const long long maxit = maxiter > 0 ? (long long)maxiter : 10 * dof_global;
+
+  lsb200_solve_info res;
+  memset(&res, 0, sizeof(res));
+  res.rhs_norm = bnorm;
+  res.threshold = thr;
+  res.setup_seconds = h->setup_seconds;
+
+  CK(cudaMemsetAsync(h->p, 0, bytes, h->stream));
+  if (bnorm == 0.0) {
+    // scipy returns b (all zeros) immediately
+    CK(cudaMemsetAsync(h->x, 0, bytes, h->stream));
+  } else {
+    // x = x0 (or 0), r = b - N x0
+    if (x0) {
+      if ((rc = copy_in(h, h->x, x0))) return rc;
+      if ((rc = halo_exchange(h, h->x))) return rc;
+      if ((rc = apply_normal_dev(h, h->x, h->q, 3, 0))) return rc;
+    } else {
+      CK(cudaMemsetAsync(h->x, 0, bytes, h->stream));
+    }
+    k_cg_residual<VEC_NT><<<vec_blocks(h, n), VEC_NT, 0, h->stream>>>(n, owned_ptr(h, h->rhs), x0 ? owned_ptr(h, h->q) : nullptr,
+                                                                       owned_ptr(h, h->r), s2, h->partials + 2 * MAX_PARTIALS,
+                                                                       h->counters + 2, &sc->rho);
+    CKL();
+    h->launches++;
+    if ((rc = allreduce_scalar(h, &sc->rho))) return rc;
+    CK(cudaMemcpyAsync(h->sc_host, sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CgScalars init = *h->sc_host;
+    init.beta = 0.0;
+    init.thr2 = thr * thr;
+    init.iter = 0;
+    init.maxiter = maxit;
+    init.nranks = h->nranks;
+    init.info = 0;
+    init.pq_part[0] = init.pq_part[1] = 0.0;
+    init.done = (sqrt(init.rho) < thr) ? 1 : 0;
+    *h->sc_host = init;
+    CK(cudaMemcpyAsync(sc, h->sc_host, sizeof(CgScalars), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+
+    // enqueue batches of iterations; poll the device scalars once per batch, one batch behind
+    const int batch = 16;
+    cudaEvent_t ev[2];
+    CK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    CgScalars* snap = nullptr;
+    CK(cudaMallocHost(&snap, 2 * sizeof(CgScalars)));
+    bool done = init.done != 0;
+    long long enq = 0;
+    int slot = 0;
+    bool pending[2] = {false, false};
+    while (!done) {
+      const long long todo = std::min<long long>(batch, maxit - enq);
+      for (long long it = 0; it < todo; ++it)
+        if ((rc = enqueue_iteration(h))) return rc;
+      enq += todo;
+      CK(cudaMemcpyAsync(&snap[slot], sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaEventRecord(ev[slot], h->stream));
+      pending[slot] = true;
+      const int other = slot ^ 1;
+      if (pending[other]) {
+        CK(cudaEventSynchronize(ev[other]));
+        pending[other] = false;
+        if (snap[other].done) done = true;
+      }
+      if (!done && enq >= maxit) {
+        CK(cudaEventSynchronize(ev[slot]));
+        pending[slot] = false;
+        done = true;  // maxiter iterations enqueued: the device state says how it ended
+      }
+      slot ^= 1;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    cudaFreeHost(snap);
+  }
+  CK(cudaEventRecord(e1, h->stream));
+  CK(cudaMemcpyAsync(h->sc_host, sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  res.solve_seconds = ms * 1e-3;
+  if (bnorm != 0.0) {
+    res.info = h->sc_host->info;
+    res.iterations = h->sc_host->iter;
+    res.residual_norm = sqrt(h->sc_host->rho);
+  }
+  res.kernel_launches = h->launches - launches0;
+  h->have_c = true;
+  if (info) *info = res;
+  if (c_out) return copy_out(h, c_out, h->x);
+  return 0;
+}
+
+static int eval_common(lsb200_ctx* h, int64_t n, const double* xyz_dev, double* out_dev, cudaStream_t st, bool grad) {
+  if (h->g.k0 != 0 || h->g.k1 != h->g.nz) return fail(LSB200_ERR_STATE, "evaluation needs a handle that owns every plane (gather c first)");
+  if (!h->have_c) return fail(LSB200_ERR_STATE, "no solution on the device yet (solve or set_c first)");
+  if (n == 0) return 0;
+  const int nb = (int)std::min<long long>((n + 255) / 256, (long long)h->sm_count * 32);
+  if (h->kind == LSB200_SUPPORT_GRID) {
+    if (grad) k_eval_gradient_grid<<<nb, 256, 0, st>>>(h->g, h->x, n, xyz_dev, out_dev);
+    else k_eval_value_grid<<<nb, 256, 0, st>>>(h->g, h->x, n, xyz_dev, out_dev);
+  } else {
+    if (grad) k_eval_gradient_tet<<<nb, 256, 0, st>>>(h->g, h->x, n, xyz_dev, out_dev);
+    else k_eval_value_tet<<<nb, 256, 0, st>>>(h->g, h->x, n, xyz_dev, out_dev);
+  }
+  CKL();
+  h->launches++;
+  return 0;
+}
+
+int lsb200_eval_value_dev(lsb200_handle h, int64_t n, const double* xyz_dev, double* out_dev, void* stream) {
+  if (!h || (n > 0 && (!xyz_dev || !out_dev))) return fail(LSB200_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  return eval_common(h, n, xyz_dev, out_dev, (cudaStream_t)stream, false);
+}
+int lsb200_eval_gradient_dev(lsb200_handle h, int64_t n, const double* xyz_dev, double* out_dev, void* stream) {
+  if (!h || (n > 0 && (!xyz_dev || !out_dev))) return fail(LSB200_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  return eval_common(h, n, xyz_dev, out_dev, (cudaStream_t)stream, true);
+}
+
+static int eval_host(lsb200_ctx* h, int64_t n, const double* xyz, double* out, bool grad) {
+  if (n < 0) return fail(LSB200_ERR_ARG, "negative point count");
+  if (n == 0) return 0;
+  if (!xyz || !out) return fail(LSB200_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  // chunked so that arbitrarily large clouds fit beside the node vectors
+  const int64_t chunk = std::min<int64_t>(n, 1 << 24);
+  const int ow = grad ? 3 : 1;
+  double *dx = nullptr, *dout = nullptr;
+  CK(cudaMalloc(&dx, sizeof(double) * 3 * chunk));
+  CK(cudaMalloc(&dout, sizeof(double) * ow * chunk));
+  int rc = 0;
+  for (int64_t o = 0; o < n && !rc; o += chunk) {
+    const int64_t m = std::min<int64_t>(chunk, n - o);
+    CK(cudaMemcpyAsync(dx, xyz + 3 * o, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, h->stream));
+    rc = eval_common(h, m, dx, dout, h->stream, grad);
+    if (rc) break;
+    CK(cudaMemcpyAsync(out + ow * o, dout, sizeof(double) * ow * m, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  cudaFree(dx);
+  cudaFree(dout);
+  return rc;
+}
+
+int lsb200_eval_value(lsb200_handle h, int64_t n, const double* xyz, double* out) {
+  if (!h) return fail(LSB200_ERR_ARG, "null handle");
+  return eval_host(h, n, xyz, out, false);
+}
+int lsb200_eval_gradient(lsb200_handle h, int64_t n, const double* xyz, double* out) {
+  if (!h) return fail(LSB200_ERR_ARG, "null handle");
+  return eval_host(h, n, xyz, out, true);
+}
+
+int lsb200_time_kernel(lsb200_handle h, int which, int reps, double* seconds_per_launch) {
+  if (!h || !seconds_per_launch || reps < 1) return fail(LSB200_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(h->device));
+  int rc = lsb200_finalize_system(h);
+  if (rc) return rc;
+  // a state in which every kernel does its full work: done = 0, huge maxiter, rho = pq = 1
+  CgScalars s;
+  memset(&s, 0, sizeof(s));
+  s.rho = 1.0; s.pq = 1.0; s.pq_part[0] = 1.0; s.beta = 0.5; s.thr2 = 0.0; s.maxiter = 1LL << 60; s.nranks = h->nranks;
+  *h->sc_host = s;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  // p = rhs so that the vectors hold representative data
+  CK(cudaMemcpyAsync(h->p, h->rhs, sizeof(double) * (size_t)h->g.nall, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->r, h->rhs, sizeof(double) * (size_t)h->g.nall, cudaMemcpyDeviceToDevice, h->stream));
+  float total_ms = 0.f;
+  for (int rep = -3; rep < reps; ++rep) {
+    CK(cudaMemcpyAsync(h->sc, h->sc_host, sizeof(CgScalars), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(e0, h->stream));
+    if (which == 0) rc = launch_regularisation(h, h->p, h->q, 1);
+    else if (which == 1) rc = enqueue_iteration(h);
+    else rc = launch_rows(h, h->p, h->q, 1);
+    if (rc) return rc;
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep >= 0) total_ms += ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *seconds_per_launch = total_ms * 1e-3 / reps;
+  h->have_c = false;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// Shared device/host definitions of the lsb200 engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace lsb {
+
+// Regular lattice shared by StructuredGrid and TetMesh.  Node counts are GLOBAL; a handle
+// owns the z-planes [k0,k1).  Node vectors are stored with two halo planes on either side of
+// the owned planes: local plane l = k - k0 + 2, element (i,j,l) at i + pitch*j + plane*l.
+// Flat order follows the reference, gi = i + nx*j + nx*ny*k
+// (LC/supports/_3d_base_structured.py:346-350), so z-slabs are contiguous.
+struct GridDesc {
+  int nx, ny, nz;   // global node counts
+  int k0, k1;       // owned planes
+  int nzl;          // k1 - k0
+  int pitch;        // row pitch in elements (>= nx)
+  long long plane;  // pitch * ny
+  long long nloc;   // plane * nzl        (owned storage, halo excluded)
+  long long nall;   // plane * (nzl + 4)  (owned + halo)
+  double origin[3];
+  double step[3];
+};
+
+constexpr int HALO = 2;
+
+// Effective stencil weights squared, pre-multiplied by the constant factors of the
+// row-normalised masks (see fdi_stencil.cuh).
+struct StencilWeights {
+  double axx, ayy, azz;  // ew_xx^2, ew_yy^2, ew_zz^2      (rows [1,-2,1]/sqrt6)
+  double bxy, bxz, byz;  // ew_xy^2/4, ew_xz^2/4, ew_yz^2/4 (rows +-1/2 at the 4 corners)
+  double dx, dy, dz;     // border families ew_dx^2, ...     (rows [1,-2,1]/sqrt6 on planes 1 and n-2)
+  double ridge2;         // ridge_factor^2 (0 when the ridge is off)
+};
+
+// CG state kept on the device so that the loop never waits for the host.
+struct CgScalars {
+  double rho;       // r . S^2 r of the current residual (== ||r||^2 in the column-scaled variables)
+  double rho_new;   // reduction target of the x/r update
+  double pq;        // p . N p (sum of the parts below, all-reduced across ranks)
+  double pq_part[2];  // [0] stencil kernel, [1] data rows
+  double beta;
+  double thr2;      // threshold^2
+  long long iter;
+  long long maxiter;
+  int done;
+  int info;
+  int nranks;
+  int pad;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum, result valid in thread 0.  Fixed order => deterministic.
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double* red /* >= NT/32 doubles */) {
+  const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  v = warp_sum(v);
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (tid < 32) {
+    s = (tid < NT / 32) ? red[tid] : 0.0;
+    s = warp_sum(s);
+  }
+  __syncthreads();
+  return s;
+}
+
+// "last block done" reduction of per-block partials in a fixed order.  Returns true in
+// thread 0 of the last-arriving block, with *total holding the sum.
+template <int NT>
+__device__ __forceinline__ bool grid_sum_last_block(double block_val, double* partials, unsigned int* counter,
+                                                    unsigned int nblocks, unsigned int bid, double* red,
+                                                    double* total) {
+  __shared__ bool s_last;
+  const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  if (tid == 0) {
+    partials[bid] = block_val;
+    __threadfence();
+    unsigned int t = atomicInc(counter, nblocks - 1);
+    s_last = (t == nblocks - 1);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  double s = 0.0;
+  for (unsigned int i = tid; i < nblocks; i += NT) s += __ldcg(partials + i);
+  s = block_sum<NT>(s, red);
+  if (tid == 0) *total = s;
+  return tid == 0;
+}
+
+}  // namespace lsb

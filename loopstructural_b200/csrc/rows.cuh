@@ -1,0 +1,311 @@
+// K2/K3: scattered constraint rows (value, gradient, normal, tangent, interface, fold, orthogonality ...).
+//
+// K2 applies q += A_d^T W A_d p for ELL blocks of row-normalised rows -- the part of
+// A^T A (LI/_solver_strategy.py:64) that comes from DiscreteInterpolator.add_constraints_to_least_squares
+// (LI/_discrete_interpolator.py:316-389) families other than the regularisation.  Rows enter the
+// least-squares system multiplied by w (build_matrix, :684-755), so the normal operator carries w^2.
+// K3 generates the FDI point rows on the device (trilinear weights / trilinear gradient matrix,
+// LC/supports/_3d_structured_grid.py:90-146,393-454) instead of numpy temporaries.
+#pragma once
+#include "common.cuh"
+
+namespace lsb {
+
+// ELL block, column-major: entry j of row r at [j*n + r].
+struct RowBlock {
+  long long n;
+  int k;
+  double* vals;
+  int* cols;   // LOCAL storage index (halo planes included); -1 = padding
+  double* w2;  // w^2
+  double* b;
+};
+
+__device__ __forceinline__ bool owned(const GridDesc& g, int c) {
+  return c >= HALO * g.plane && c < (long long)(g.nzl + HALO) * g.plane;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+    k_rows_normal(const GridDesc g, const RowBlock rb, const double* __restrict__ p, double* __restrict__ q,
+                  double* __restrict__ partials, unsigned int* __restrict__ counter, CgScalars* __restrict__ sc,
+                  const int cg_mode, const int first) {
+  __shared__ double red[NT / 32];
+  if (cg_mode && sc->done) return;
+  double dot = 0.0;
+  for (long long r = blockIdx.x * (long long)NT + threadIdx.x; r < rb.n; r += (long long)gridDim.x * NT) {
+    double t = 0.0;
+    for (int j = 0; j < rb.k; ++j) {
+      const int c = rb.cols[j * rb.n + r];
+      if (c >= 0) t += rb.vals[j * rb.n + r] * p[c];
+    }
+    t *= rb.w2[r];
+    if (t != 0.0) {
+      for (int j = 0; j < rb.k; ++j) {
+        const int c = rb.cols[j * rb.n + r];
+        if (c >= 0 && owned(g, c)) {
+          const double a = rb.vals[j * rb.n + r];
+          atomicAdd(q + c, a * t);
+          dot += a * p[c] * t;
+        }
+      }
+    }
+  }
+  const double bsum = block_sum<NT>(dot, red);
+  double total;
+  if (grid_sum_last_block<NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total)) {
+    sc->pq_part[1] = first ? total : sc->pq_part[1] + total;
+  }
+}
+
+// rhs += A_d^T W b
+__global__ void k_rows_rhs(const GridDesc g, const RowBlock rb, double* __restrict__ rhs) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rb.n; r += (long long)gridDim.x * blockDim.x) {
+    const double t = rb.w2[r] * rb.b[r];
+    if (t == 0.0) continue;
+    for (int j = 0; j < rb.k; ++j) {
+      const int c = rb.cols[j * rb.n + r];
+      if (c >= 0 && owned(g, c)) atomicAdd(rhs + c, rb.vals[j * rb.n + r] * t);
+    }
+  }
+}
+
+// diag += diag(A_d^T W A_d).  Listed duplicate columns of one row are merged first, as the
+// reference's coo->csc conversion does (LI/_discrete_interpolator.py:384-386).
+__global__ void k_rows_diag(const GridDesc g, const RowBlock rb, double* __restrict__ diag) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rb.n; r += (long long)gridDim.x * blockDim.x) {
+    const double w2 = rb.w2[r];
+    if (w2 == 0.0) continue;
+    for (int j = 0; j < rb.k; ++j) {
+      const int c = rb.cols[j * rb.n + r];
+      if (c < 0 || !owned(g, c)) continue;
+      bool dup = false;
+      for (int jj = 0; jj < j; ++jj) dup |= (rb.cols[jj * rb.n + r] == c);
+      if (dup) continue;
+      double s = 0.0;
+      for (int jj = j; jj < rb.k; ++jj)
+        if (rb.cols[jj * rb.n + r] == c) s += rb.vals[jj * rb.n + r];
+      atomicAdd(diag + c, w2 * s * s);
+    }
+  }
+}
+
+// Ingest host-format rows (row-major vals/global cols) into an ELL block: optional row
+// normalisation (LI/_discrete_interpolator.py:361-366), global -> local column ids, w -> w^2.
+// status[0] counts rows kept, status[1] flags a kept row with a column outside owned+halo planes.
+__global__ void k_rows_ingest(const GridDesc g, const long long n, const int k, const double* __restrict__ vals,
+                              const long long* __restrict__ cols, const double* __restrict__ b,
+                              const double* __restrict__ w, const int normalise, RowBlock rb,
+                              const long long row0, unsigned long long* __restrict__ status) {
+  const long long nxny = (long long)g.nx * g.ny;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    double nrm2 = 0.0;
+    bool touches = false, bad = false, nan = false;
+    for (int j = 0; j < k; ++j) {
+      const double a = vals[r * k + j];
+      nrm2 += a * a;
+      nan |= (a != a);
+      const long long kz = cols[r * k + j] / nxny;
+      touches |= (kz >= g.k0 && kz < g.k1);
+      bad |= (kz < g.k0 - HALO || kz >= g.k1 + HALO);
+    }
+    double bb = b[r];
+    nan |= (bb != bb) || (w[r] != w[r]);
+    const double len = sqrt(nrm2);
+    const double inv = (normalise && len > 0.0) ? 1.0 / len : 1.0;
+    const bool keep = touches && !nan;
+    if (keep && bad) atomicExch(status + 1, 1ull);
+    const bool ok = keep && !bad;
+    if (ok) atomicAdd(status, 1ull);
+    const long long ro = row0 + r;
+    for (int j = 0; j < k; ++j) {
+      int lc = -1;
+      double a = 0.0;
+      if (ok) {
+        const long long gi = cols[r * k + j];
+        const long long kz = gi / nxny, rem = gi - kz * nxny;
+        const long long jy = rem / g.nx, ix = rem - jy * g.nx;
+        lc = (int)((kz - g.k0 + HALO) * g.plane + jy * g.pitch + ix);
+        // match numpy: a / len (division, not multiplication by the reciprocal)
+        a = (normalise && len > 0.0) ? vals[r * k + j] / len : vals[r * k + j];
+      }
+      rb.vals[j * rb.n + ro] = a;
+      rb.cols[j * rb.n + ro] = lc;
+    }
+    (void)inv;
+    rb.b[ro] = ok ? ((normalise && len > 0.0) ? bb / len : bb) : 0.0;
+    rb.w2[ro] = ok ? w[r] * w[r] : 0.0;
+  }
+}
+
+// ---- K3: FDI rows from constraint points ---------------------------------------------------
+
+struct CellLoc {
+  bool inside;
+  int ci[3];
+  double lc[3];  // local coordinates clipped to [0,1]
+};
+
+// position_to_cell_index / inside / position_to_local_coordinates
+// (LC/supports/_3d_base_structured.py:251-293; LC/supports/_3d_structured_grid.py:126-146)
+__device__ __forceinline__ CellLoc locate(const GridDesc& g, const double x[3]) {
+  CellLoc L;
+  L.inside = true;
+  const int nc[3] = {g.nx - 1, g.ny - 1, g.nz - 1};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double maxi = __dadd_rn(g.origin[a], __dmul_rn((double)nc[a], g.step[a]));
+    const double ext = fmax(fabs(maxi - g.origin[a]), 1.0);
+    const double tol = __dmul_rn(__dmul_rn(2.220446049250313e-16, 32.0), ext);
+    L.inside = L.inside && (x[a] >= g.origin[a] - tol) && (x[a] <= maxi + tol);
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    int c = 0;
+    double l = 0.0;
+    if (L.inside) {
+      const double f = floor((x[a] - g.origin[a]) / g.step[a]);
+      c = (int)fmin(fmax(f, 0.0), (double)(nc[a] - 1));
+      const double co = __dadd_rn(g.origin[a], __dmul_rn(g.step[a], (double)c));
+      l = fmin(fmax((x[a] - co) / g.step[a], 0.0), 1.0);
+    }
+    L.ci[a] = c;
+    L.lc[a] = l;
+  }
+  return L;
+}
+
+// trilinear shape functions, corner c has offsets (c&1,(c>>1)&1,(c>>2)&1)
+// (LC/supports/_3d_structured_grid.py:90-124)
+__device__ __forceinline__ void trilinear_w(const double l[3], double wgt[8]) {
+  const double x = l[0], y = l[1], z = l[2];
+  wgt[0] = (1 - x) * (1 - y) * (1 - z);
+  wgt[1] = x * (1 - y) * (1 - z);
+  wgt[2] = (1 - x) * y * (1 - z);
+  wgt[3] = x * y * (1 - z);
+  wgt[4] = (1 - x) * (1 - y) * z;
+  wgt[5] = x * (1 - y) * z;
+  wgt[6] = (1 - x) * y * z;
+  wgt[7] = x * y * z;
+}
+
+// derivative of the shape functions / step (LC/supports/_3d_structured_grid.py:393-454)
+__device__ __forceinline__ void trilinear_grad(const GridDesc& g, const double l[3], double T[3][8]) {
+  const double x = l[0], y = l[1], z = l[2];
+  T[0][0] = (1 - z) * (y - 1); T[0][1] = (1 - y) * (1 - z); T[0][2] = -y * (1 - z); T[0][3] = y * (1 - z);
+  T[0][4] = -(1 - y) * z;      T[0][5] = (1 - y) * z;       T[0][6] = -y * z;       T[0][7] = y * z;
+  T[1][0] = (x - 1) * (1 - z); T[1][1] = -x * (1 - z);      T[1][2] = (1 - x) * (1 - z); T[1][3] = x * (1 - z);
+  T[1][4] = -(1 - x) * z;      T[1][5] = -x * z;            T[1][6] = (1 - x) * z;  T[1][7] = x * z;
+  T[2][0] = -(1 - x) * (1 - y); T[2][1] = -x * (1 - y);     T[2][2] = -(1 - x) * y; T[2][3] = -x * y;
+  T[2][4] = (1 - x) * (1 - y); T[2][5] = x * (1 - y);       T[2][6] = (1 - x) * y;  T[2][7] = x * y;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) T[a][c] /= g.step[a];
+}
+
+__device__ __forceinline__ long long corner_local(const GridDesc& g, const int ci[3], int c) {
+  const int i = ci[0] + (c & 1), j = ci[1] + ((c >> 1) & 1), k = ci[2] + ((c >> 2) & 1);
+  return (long long)(k - g.k0 + HALO) * g.plane + (long long)j * g.pitch + i;
+}
+
+// get_vectors (LC/math/_maths.py:276-298): strike and dip vectors of a unit normal
+__device__ __forceinline__ void strike_dip(const double nrm[3], double strike[3], double dip[3]) {
+  const double len = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+  const double n[3] = {nrm[0] / len, nrm[1] / len, nrm[2] / len};
+  const double phi = atan2(n[1], n[0]);
+  const double deg = -phi * (180.0 / 3.14159265358979323846);
+  const double s = deg * (3.14159265358979323846 / 180.0);
+  double sv[3] = {sin(-s), -cos(-s), 0.0};
+  const double sl = sqrt(sv[0] * sv[0] + sv[1] * sv[1]);
+  sv[0] /= sl; sv[1] /= sl;
+  double dv[3] = {sv[1] * n[2] - sv[2] * n[1], sv[2] * n[0] - sv[0] * n[2], sv[0] * n[1] - sv[1] * n[0]};
+  const double dl = sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    strike[a] = sv[a] * len;
+    dip[a] = dv[a] / dl * len;
+  }
+}
+
+// One thread per constraint point; writes `mult` rows per point into rb at row0 + m*n + point.
+// Points outside the support (or on a slab: in cells that touch no owned plane) become empty rows.
+__global__ void k_fdi_point_rows(const GridDesc g, const int kind, const long long n, const double* __restrict__ data,
+                                 const int ncols, const double weight, RowBlock rb, const long long row0,
+                                 unsigned long long* __restrict__ status) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    const double* d = data + r * ncols;
+    const double x[3] = {d[0], d[1], d[2]};
+    CellLoc L = locate(g, x);
+    bool ok = L.inside;
+    for (int c = 0; c < ncols; ++c) ok = ok && (d[c] == d[c]);
+    // slab: keep the row when its cell touches an owned plane
+    ok = ok && (L.ci[2] + 1 >= g.k0) && (L.ci[2] < g.k1);
+    const int mult = kind == LSB200_ROWS_GRADIENT ? 2 : (kind == LSB200_ROWS_NORMAL ? 3 : 1);
+    double A[3][8];
+    double bb[3] = {0.0, 0.0, 0.0};
+    double ww = weight;
+    if (ok) {
+      if (kind == LSB200_ROWS_VALUE) {
+        trilinear_w(L.lc, A[0]);
+        bb[0] = d[3];
+        ww = weight * d[4];
+      } else {
+        double T[3][8];
+        trilinear_grad(g, L.lc, T);
+        if (kind == LSB200_ROWS_NORMAL) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) A[a][c] = T[a][c];
+            bb[a] = d[3 + a];
+          }
+          ww = weight / 3.0 * d[6];
+        } else {
+          const double len = sqrt(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
+          double v[3] = {d[3], d[4], d[5]};
+          if (len > 0.0 || kind == LSB200_ROWS_GRADIENT) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+              v[a] /= len;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) T[a][c] /= len;
+            }
+          }
+          if (kind == LSB200_ROWS_GRADIENT) {
+            double sv[3], dv[3];
+            strike_dip(v, sv, dv);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              A[0][c] = sv[0] * T[0][c] + sv[1] * T[1][c] + sv[2] * T[2][c];
+              A[1][c] = dv[0] * T[0][c] + dv[1] * T[1][c] + dv[2] * T[2][c];
+            }
+          } else {  // tangent / orthogonal
+#pragma unroll
+            for (int c = 0; c < 8; ++c) A[0][c] = v[0] * T[0][c] + v[1] * T[1][c] + v[2] * T[2][c];
+            bb[0] = d[6];
+          }
+        }
+      }
+      atomicAdd(status, (unsigned long long)mult);
+    }
+    for (int m = 0; m < mult; ++m) {
+      const long long ro = row0 + (long long)m * n + r;
+      double nrm2 = 0.0;
+      if (ok)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) nrm2 += A[m][c] * A[m][c];
+      const double len = sqrt(nrm2);
+      ok = ok && (len == len);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        rb.vals[c * rb.n + ro] = ok ? (len > 0.0 ? A[m][c] / len : A[m][c]) : 0.0;
+        rb.cols[c * rb.n + ro] = ok ? (int)corner_local(g, L.ci, c) : -1;
+      }
+      rb.b[ro] = ok ? (len > 0.0 ? bb[m] / len : bb[m]) : 0.0;
+      rb.w2[ro] = ok ? ww * ww : 0.0;
+    }
+  }
+}
+
+}  // namespace lsb

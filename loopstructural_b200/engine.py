@@ -1,0 +1,230 @@
+"""Thin Python owner of one ``lsb200`` device handle.
+
+``Engine`` is the host-side object the interpolator classes (``interpolators.py``) and the
+LoopStructural plug-in (``plugin.py``) drive.  It holds no numerics of its own: every method is one
+call through the C-ABI of ``include/lsb200.h`` into the CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _native as nat
+
+ROWS_VALUE, ROWS_GRADIENT, ROWS_NORMAL, ROWS_TANGENT = 0, 1, 2, 3
+PART_REGULARISATION, PART_ROWS, PART_RIDGE = 1, 2, 4
+
+# FDI weight defaults, LI/_finite_difference_interpolator.py:102-119
+FDI_DEFAULT_WEIGHTS = dict(dxy=1.0, dyz=1.0, dxz=1.0, dxx=1.0, dyy=1.0, dzz=1.0, dx=1.0, dy=1.0, dz=1.0,
+                           cpw=1.0, gpw=1.0, npw=10.0, tpw=1.0, ipw=1.0)
+
+
+def effective_stencil_weights(weights: dict) -> np.ndarray:
+    """Row weights the twelve stencil families actually get, in LSB200_W_* order.
+
+    get_operators divides the mixed-derivative weights by 4
+    (LC/supports/_3d_structured_grid.py:489-510); border families use dx/dy/dz
+    (LI/_finite_difference_interpolator.py:1102-1139)."""
+    w = dict(FDI_DEFAULT_WEIGHTS)
+    w.update({k: v for k, v in (weights or {}).items() if v is not None})
+    return np.array([w["dxx"], w["dyy"], w["dzz"], w["dxy"] / 4.0, w["dxz"] / 4.0, w["dyz"] / 4.0,
+                     w["dx"], w["dy"], w["dz"]], dtype=np.float64)
+
+
+@dataclass
+class SolveResult:
+    info: int
+    iterations: int
+    residual_norm: float
+    threshold: float
+    rhs_norm: float
+    setup_seconds: float
+    solve_seconds: float
+    kernel_launches: int
+
+
+class Engine:
+    """One support (regular grid or tet mesh on the same lattice) on one GPU.
+
+    ``nsteps`` are NODE counts per axis (LC/supports/_3d_base_structured.py:66); ``slab=(k0,k1)``
+    restricts the handle to the z-planes [k0,k1) of a multi-GPU solve."""
+
+    def __init__(self, nsteps, origin, step, kind: str = "grid", device: int = 0, slab=None):
+        self._lib = nat.load()
+        self._h = nat.Handle()
+        self.nsteps = np.asarray(nsteps, dtype=np.int64).reshape(3).copy()
+        self.origin = nat.as_f64(origin, (3,)).copy()
+        self.step = nat.as_f64(step, (3,)).copy()
+        self.kind = kind
+        self.device = int(device)
+        k0, k1 = (0, int(self.nsteps[2])) if slab is None else (int(slab[0]), int(slab[1]))
+        self.slab = (k0, k1)
+        if kind == "grid":
+            rc = self._lib.lsb200_create_grid(nat.iptr(self.nsteps), nat.dptr(self.origin), nat.dptr(self.step),
+                                              k0, k1, self.device, C.byref(self._h))
+        elif kind == "tetmesh":
+            if slab is not None:
+                raise ValueError("tet-mesh handles do not take a slab")
+            rc = self._lib.lsb200_create_tetmesh(nat.iptr(self.nsteps), nat.dptr(self.origin), nat.dptr(self.step),
+                                                 self.device, C.byref(self._h))
+        else:
+            raise ValueError(f"unknown support kind {kind!r}")
+        nat.check(rc)
+
+    # -- lifetime --------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.lsb200_destroy(self._h)
+            self._h = nat.Handle()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n_nodes(self) -> int:
+        return int(np.prod(self.nsteps))
+
+    @property
+    def local_dof(self) -> int:
+        return int(self._lib.lsb200_local_dof(self._h))
+
+    # -- system ----------------------------------------------------------------------------
+    def set_regularisation(self, weights: dict | None = None):
+        ew = effective_stencil_weights(weights or {})
+        nat.check(self._lib.lsb200_set_regularisation(self._h, nat.dptr(ew)))
+
+    def set_p1_regularisation(self, w: float):
+        nat.check(self._lib.lsb200_set_p1_regularisation(self._h, float(w)))
+
+    def set_options(self, ridge_factor: float = 1e-8, add_ridge: bool = True, apply_scaling: bool = True,
+                    deterministic: bool = False):
+        nat.check(self._lib.lsb200_set_options(self._h, float(ridge_factor), int(add_ridge), int(apply_scaling),
+                                               int(deterministic)))
+
+    def add_rows(self, A, idx, b, w, normalise: bool = True):
+        """add_constraints_to_least_squares (LI/_discrete_interpolator.py:316-389): rows (n,k),
+        global column ids (n,k), targets (n,), scalar or (n,) weights."""
+        A = nat.as_f64(A)
+        if A.ndim != 2:
+            raise ValueError("A must be (n_rows, k)")
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        if idx.shape != A.shape:
+            raise ValueError(f"idx shape {idx.shape} does not match A {A.shape}")
+        n = A.shape[0]
+        b = nat.as_f64(np.broadcast_to(np.asarray(b, dtype=np.float64), (n,)))
+        w = nat.as_f64(np.broadcast_to(np.asarray(w, dtype=np.float64), (n,)))
+        nat.check(self._lib.lsb200_add_rows(self._h, n, A.shape[1], nat.dptr(A), nat.iptr(idx), nat.dptr(b),
+                                            nat.dptr(w), int(normalise)))
+
+    def add_point_rows(self, kind: int, data, weight: float) -> int:
+        data = nat.as_f64(data)
+        if data.ndim != 2:
+            raise ValueError("data must be (n, ncols)")
+        out = C.c_int64(0)
+        nat.check(self._lib.lsb200_add_point_rows(self._h, int(kind), data.shape[0], nat.dptr(data), data.shape[1],
+                                                  float(weight), C.byref(out)))
+        return int(out.value)
+
+    def clear_rows(self):
+        nat.check(self._lib.lsb200_clear_rows(self._h))
+
+    @property
+    def num_rows(self) -> int:
+        return int(self._lib.lsb200_num_rows(self._h))
+
+    def finalize(self):
+        nat.check(self._lib.lsb200_finalize_system(self._h))
+
+    def comm_init(self, nccl_id: bytes, rank: int, nranks: int):
+        buf = (C.c_ubyte * 128).from_buffer_copy(nccl_id)
+        nat.check(self._lib.lsb200_comm_init(self._h, buf, int(rank), int(nranks)))
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_ubyte * 128)()
+        nat.check(nat.load().lsb200_comm_unique_id(buf))
+        return bytes(buf)
+
+    def _vec(self):
+        return np.empty(self.local_dof, dtype=np.float64)
+
+    def apply_normal(self, p, parts: int = PART_REGULARISATION | PART_ROWS | PART_RIDGE) -> np.ndarray:
+        p = nat.as_f64(p, (self.local_dof,))
+        q = self._vec()
+        nat.check(self._lib.lsb200_apply_normal(self._h, nat.dptr(p), nat.dptr(q), int(parts)))
+        return q
+
+    def rhs(self) -> np.ndarray:
+        out = self._vec()
+        nat.check(self._lib.lsb200_get_rhs(self._h, nat.dptr(out)))
+        return out
+
+    def diagonal(self) -> np.ndarray:
+        out = self._vec()
+        nat.check(self._lib.lsb200_get_diagonal(self._h, nat.dptr(out)))
+        return out
+
+    def scaling(self) -> np.ndarray:
+        out = self._vec()
+        nat.check(self._lib.lsb200_get_scaling(self._h, nat.dptr(out)))
+        return out
+
+    def solve_cg(self, rtol: float = 1e-5, atol: float = 0.0, maxiter: int | None = None, x0=None,
+                 want_c: bool = True):
+        info = nat.SolveInfo()
+        x0p = None
+        if x0 is not None:
+            x0 = nat.as_f64(x0, (self.local_dof,))
+            x0p = nat.dptr(x0)
+        c = self._vec() if want_c else None
+        nat.check(self._lib.lsb200_solve_cg(self._h, float(rtol), float(atol), int(maxiter or 0), x0p,
+                                            nat.dptr(c) if want_c else None, C.byref(info)))
+        res = SolveResult(int(info.info), int(info.iterations), float(info.residual_norm), float(info.threshold),
+                          float(info.rhs_norm), float(info.setup_seconds), float(info.solve_seconds),
+                          int(info.kernel_launches))
+        return c, res
+
+    # -- solution and evaluation -----------------------------------------------------------
+    def get_c(self) -> np.ndarray:
+        out = self._vec()
+        nat.check(self._lib.lsb200_get_c(self._h, nat.dptr(out)))
+        return out
+
+    def set_c(self, c):
+        c = nat.as_f64(c, (self.local_dof,))
+        nat.check(self._lib.lsb200_set_c(self._h, nat.dptr(c)))
+
+    def evaluate_value(self, xyz) -> np.ndarray:
+        xyz = nat.as_f64(xyz)
+        if xyz.ndim != 2 or xyz.shape[1] != 3:
+            raise ValueError("xyz must be (n,3)")
+        out = np.empty(xyz.shape[0], dtype=np.float64)
+        nat.check(self._lib.lsb200_eval_value(self._h, xyz.shape[0], nat.dptr(xyz), nat.dptr(out)))
+        return out
+
+    def evaluate_gradient(self, xyz) -> np.ndarray:
+        xyz = nat.as_f64(xyz)
+        if xyz.ndim != 2 or xyz.shape[1] != 3:
+            raise ValueError("xyz must be (n,3)")
+        out = np.empty((xyz.shape[0], 3), dtype=np.float64)
+        nat.check(self._lib.lsb200_eval_gradient(self._h, xyz.shape[0], nat.dptr(xyz), nat.dptr(out)))
+        return out
+
+    def evaluate_value_device(self, xyz_ptr: int, out_ptr: int, n: int, stream: int = 0):
+        """Device pointers (e.g. ``tensor.data_ptr()``), asynchronous on ``stream``."""
+        nat.check(self._lib.lsb200_eval_value_dev(self._h, int(n), C.c_void_p(xyz_ptr), C.c_void_p(out_ptr),
+                                                  C.c_void_p(stream)))
+
+    def evaluate_gradient_device(self, xyz_ptr: int, out_ptr: int, n: int, stream: int = 0):
+        nat.check(self._lib.lsb200_eval_gradient_dev(self._h, int(n), C.c_void_p(xyz_ptr), C.c_void_p(out_ptr),
+                                                     C.c_void_p(stream)))
+
+    def time_kernel(self, which: int, reps: int = 20) -> float:
+        out = C.c_double(0.0)
+        nat.check(self._lib.lsb200_time_kernel(self._h, int(which), int(reps), C.byref(out)))
+        return float(out.value)
