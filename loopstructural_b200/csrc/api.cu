@@ -178,19 +178,31 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
   const StencilWeights w = make_weights(h);
   double* part = h->partials;
   unsigned int* cnt = h->counters + 0;
-  switch (h->stencil_cfg) {
-    case 1:
-      k_fdi_normal<2, 32, 16><<<h->sgrid, dim3(32, 16), 0, h->stream>>>(h->g, w, p, q, h->cz, part, cnt, h->sc, cg_mode);
-      break;
-    case 2:
-      k_fdi_normal<1, 32, 16><<<h->sgrid, dim3(32, 16), 0, h->stream>>>(h->g, w, p, q, h->cz, part, cnt, h->sc, cg_mode);
-      break;
-    case 3:
-      k_fdi_normal<4, 32, 8><<<h->sgrid, dim3(32, 8), 0, h->stream>>>(h->g, w, p, q, h->cz, part, cnt, h->sc, cg_mode);
-      break;
-    default:
-      k_fdi_normal<2, 32, 8><<<h->sgrid, dim3(32, 8), 0, h->stream>>>(h->g, w, p, q, h->cz, part, cnt, h->sc, cg_mode);
+  const bool vec16 = (h->g.pitch % 2) == 0;
+#define LSB_LAUNCH(XB, TXT, TYT, MINB, ST)                                                                       \
+  {                                                                                                              \
+    const size_t smem = sizeof(double) * StencilCfg<XB, TXT, TYT, ST>::PLANE * ST;                               \
+    if (vec16) {                                                                                                 \
+      auto kern = k_fdi_normal<XB, TXT, TYT, MINB, ST, true>;                                                    \
+      if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      kern<<<h->sgrid, dim3(TXT, TYT), smem, h->stream>>>(h->g, w, p, q, h->cz, part, cnt, h->sc, cg_mode);      \
+    } else {                                                                                                     \
+      auto kern = k_fdi_normal<XB, TXT, TYT, MINB, ST, false>;                                                   \
+      if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      kern<<<h->sgrid, dim3(TXT, TYT), smem, h->stream>>>(h->g, w, p, q, h->cz, part, cnt, h->sc, cg_mode);      \
+    }                                                                                                            \
   }
+  switch (h->stencil_cfg) {
+    case 1: LSB_LAUNCH(2, 32, 16, 1, 4); break;
+    case 2: LSB_LAUNCH(1, 32, 16, 1, 4); break;
+    case 3: LSB_LAUNCH(2, 32, 8, 2, 6); break;
+    case 4: LSB_LAUNCH(2, 32, 12, 1, 4); break;
+    case 5: LSB_LAUNCH(2, 32, 8, 1, 4); break;
+    case 6: LSB_LAUNCH(1, 32, 8, 3, 4); break;
+    case 7: LSB_LAUNCH(1, 32, 8, 2, 6); break;
+    default: LSB_LAUNCH(2, 32, 8, 2, 4);
+  }
+#undef LSB_LAUNCH
   CKL();
   h->launches++;
   return 0;
@@ -201,8 +213,12 @@ static void plan(lsb200_ctx* h) {
   h->stencil_cfg = env ? atoi(env) : 0;
   switch (h->stencil_cfg) {
     case 1: plan_stencil<2, 32, 16>(h, 1); break;
-    case 2: plan_stencil<1, 32, 16>(h, 2); break;
-    case 3: plan_stencil<4, 32, 8>(h, 2); break;
+    case 2: plan_stencil<1, 32, 16>(h, 1); break;
+    case 3: plan_stencil<2, 32, 8>(h, 2); break;
+    case 4: plan_stencil<2, 32, 12>(h, 1); break;
+    case 5: plan_stencil<2, 32, 8>(h, 1); break;
+    case 6: plan_stencil<1, 32, 8>(h, 3); break;
+    case 7: plan_stencil<1, 32, 8>(h, 2); break;
     default: h->stencil_cfg = 0; plan_stencil<2, 32, 8>(h, 2);
   }
   const char* cz = getenv("LSB200_STENCIL_CZ");

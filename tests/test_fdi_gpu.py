@@ -21,7 +21,7 @@ def _built():
 
 # ---------------------------------------------------------------- K1: regularisation operator
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "fdi_operator_*.npz"))))
-@pytest.mark.parametrize("cfg", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("cfg", ["0", "1", "2", "3", "4", "5", "6", "7"])
 def test_stencil_operator_matches_reference_gram(path, cfg, monkeypatch):
     """R^T R p at EVERY dof incl. the boundary shell == the explicit Gram matrix of the reference
     (the bar of LIT/test_fdi_matrix_free_regularisation.py:468-493, 1e-10)."""
