@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "eval.cuh"
 #include "fdi_stencil.cuh"
+#include "fdi_main.cuh"
 #include "p1.cuh"
 #include "rows.cuh"
 
@@ -105,7 +106,7 @@ struct lsb200_ctx {
   long long rows_kept = 0;
   CgScalars* sc = nullptr;
   CgScalars* sc_host = nullptr;  // pinned
-  double* partials = nullptr;    // 3 * MAX_PARTIALS
+  double* partials = nullptr;    // 4 * MAX_PARTIALS: stencil, rows, x/r update, stencil y-shell
   unsigned int* counters = nullptr;
   unsigned long long* status = nullptr;  // 2 words
   bool finalized = false;
@@ -115,6 +116,10 @@ struct lsb200_ctx {
   int stencil_cfg = 0;
   int cz = 0;
   dim3 sgrid;
+  // main (register-tiled) kernel + y-shell launch of k_fdi_normal; main_cfg < 0: k_fdi_normal everywhere
+  int main_cfg = -1;
+  int main_cz = 0, shell_cz = 0;
+  dim3 main_grid, shell_grid;
   int sm_count = 148;
   long long launches = 0;
   double setup_seconds = 0.0;
@@ -174,23 +179,117 @@ static void plan_stencil(lsb200_ctx* h, int ctas_per_sm) {
   h->sgrid = dim3(tiles_x, tiles_y, real);
 }
 
+// z-chunk length that fills `slots` CTA slots in whole waves with the least halo re-staging
+static int pick_cz(const lsb200_ctx* h, long long tiles, long long slots) {
+  int best_cz = h->g.nzl;
+  double best = -1.0;
+  const int max_nch = std::max(1, h->g.nzl / 4);
+  for (int nch = 1; nch <= max_nch && nch <= 4096; ++nch) {
+    const int cz = (h->g.nzl + nch - 1) / nch;
+    const int real = (h->g.nzl + cz - 1) / cz;
+    const long long ctas = tiles * real;
+    if (ctas > MAX_PARTIALS) break;
+    const long long waves = (ctas + slots - 1) / slots;
+    const double eff = (double)ctas / (double)(waves * slots) * (double)cz / (double)(cz + 2 * HALO);
+    if (eff > best + 1e-9) {
+      best = eff;
+      best_cz = cz;
+    }
+  }
+  return best_cz;
+}
+
+// configurations of k_fdi_main: YB rows per thread, TYT warps, ST ring planes, MINB CTAs per SM
+#define LSB_MAIN_CFGS(X) \
+  X(0, 4, 8, 8, 1)       \
+  X(1, 4, 8, 6, 1)       \
+  X(2, 4, 4, 8, 2)       \
+  X(3, 2, 8, 8, 2)       \
+  X(4, 2, 16, 8, 1)      \
+  X(5, 4, 8, 10, 1)      \
+  X(6, 4, 4, 6, 3)       \
+  X(7, 2, 8, 6, 3)
+
+static void plan_main(lsb200_ctx* h) {
+  const char* env = getenv("LSB200_STENCIL_MAIN");
+  int cfg = env ? atoi(env) : 0;
+  h->main_cfg = -1;
+  if (cfg < 0 || h->kind != LSB200_SUPPORT_GRID) return;
+  if (h->g.ny < 16 || h->g.nx < 8) return;  // tiny grids: k_fdi_normal everywhere
+  int ty = 0, minb = 1;
+  switch (cfg) {
+#define X(ID, YB, TYT, ST, MINB) case ID: ty = YB * TYT; minb = MINB; break;
+    LSB_MAIN_CFGS(X)
+#undef X
+    default: cfg = 0; ty = 32; minb = 1;
+  }
+  const int tiles_x = (h->g.nx + 63) / 64, tiles_y = (h->g.ny - 6 + ty - 1) / ty;
+  h->main_cz = pick_cz(h, (long long)tiles_x * tiles_y, (long long)h->sm_count * minb);
+  const char* cz = getenv("LSB200_STENCIL_CZ");
+  if (cz && atoi(cz) > 0) h->main_cz = atoi(cz);
+  h->main_grid = dim3(tiles_x, tiles_y, (h->g.nzl + h->main_cz - 1) / h->main_cz);
+  // y shell: 2 strips of 3 rows, k_fdi_normal<2,32,4,...>
+  h->shell_cz = pick_cz(h, (long long)tiles_x * 2, (long long)h->sm_count * 2);
+  if (cz && atoi(cz) > 0) h->shell_cz = atoi(cz);
+  h->shell_grid = dim3(tiles_x, 2, (h->g.nzl + h->shell_cz - 1) / h->shell_cz);
+  if ((long long)h->main_grid.x * h->main_grid.y * h->main_grid.z > MAX_PARTIALS) return;
+  h->main_cfg = cfg;
+}
+
+static MainConsts make_main_consts(const StencilWeights& w) {
+  MainConsts K;
+  K.cy1 = w.ayy * (-2.0 / 3.0);
+  K.cy2 = w.ayy * (1.0 / 6.0) - 2.0 * w.byz;
+  K.bxy = w.bxy; K.bxz = w.bxz; K.byz = w.byz;
+  K.zt0 = w.azz * (1.0 / 6.0);
+  K.zt1 = w.azz * (-2.0 / 3.0);
+  return K;
+}
+
 static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode) {
   const StencilWeights w = make_weights(h);
   double* part = h->partials;
   unsigned int* cnt = h->counters + 0;
   const bool vec16 = (h->g.pitch % 2) == 0;
-#define LSB_LAUNCH(XB, TXT, TYT, MINB, ST)                                                                       \
+#define LSB_LAUNCH_AT(GRID, CZ, PART, CNT, YSHELL, XB, TXT, TYT, MINB, ST)                                       \
   {                                                                                                              \
     const size_t smem = sizeof(double) * StencilCfg<XB, TXT, TYT, ST>::PLANE * ST;                               \
     if (vec16) {                                                                                                 \
       auto kern = k_fdi_normal<XB, TXT, TYT, MINB, ST, true>;                                                    \
       if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-      kern<<<h->sgrid, dim3(TXT, TYT), smem, h->stream>>>(h->g, w, p, q, h->cz, part, cnt, h->sc, cg_mode);      \
+      kern<<<GRID, dim3(TXT, TYT), smem, h->stream>>>(h->g, w, p, q, CZ, PART, CNT, h->sc, cg_mode, YSHELL);      \
     } else {                                                                                                     \
       auto kern = k_fdi_normal<XB, TXT, TYT, MINB, ST, false>;                                                   \
       if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-      kern<<<h->sgrid, dim3(TXT, TYT), smem, h->stream>>>(h->g, w, p, q, h->cz, part, cnt, h->sc, cg_mode);      \
+      kern<<<GRID, dim3(TXT, TYT), smem, h->stream>>>(h->g, w, p, q, CZ, PART, CNT, h->sc, cg_mode, YSHELL);      \
     }                                                                                                            \
+  }
+#define LSB_LAUNCH(XB, TXT, TYT, MINB, ST) LSB_LAUNCH_AT(h->sgrid, h->cz, part, cnt, 0, XB, TXT, TYT, MINB, ST)
+  if (h->main_cfg >= 0) {
+    const MainConsts K = make_main_consts(w);
+    switch (h->main_cfg) {
+#define X(ID, YB, TYT, ST, MINB)                                                                                  \
+  case ID: {                                                                                                      \
+    const size_t smem = sizeof(double) * MainCfg<YB, TYT, ST>::PLANE * ST;                                        \
+    if (vec16) {                                                                                                  \
+      auto kern = k_fdi_main<YB, TYT, ST, MINB, true>;                                                            \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
+      kern<<<h->main_grid, dim3(32, TYT), smem, h->stream>>>(h->g, w, K, p, q, h->main_cz, part, cnt, h->sc, cg_mode); \
+    } else {                                                                                                      \
+      auto kern = k_fdi_main<YB, TYT, ST, MINB, false>;                                                           \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
+      kern<<<h->main_grid, dim3(32, TYT), smem, h->stream>>>(h->g, w, K, p, q, h->main_cz, part, cnt, h->sc, cg_mode); \
+    }                                                                                                             \
+  } break;
+      LSB_MAIN_CFGS(X)
+#undef X
+    }
+    CKL();
+    h->launches++;
+    LSB_LAUNCH_AT(h->shell_grid, h->shell_cz, h->partials + 3 * MAX_PARTIALS, h->counters + 3, 1, 2, 32, 4, 2, 4);
+    CKL();
+    h->launches++;
+    return 0;
   }
   switch (h->stencil_cfg) {
     case 1: LSB_LAUNCH(2, 32, 16, 1, 4); break;
@@ -203,6 +302,7 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
     default: LSB_LAUNCH(2, 32, 8, 2, 4);
   }
 #undef LSB_LAUNCH
+#undef LSB_LAUNCH_AT
   CKL();
   h->launches++;
   return 0;
@@ -226,6 +326,7 @@ static void plan(lsb200_ctx* h) {
     h->cz = atoi(cz);
     h->sgrid.z = (h->g.nzl + h->cz - 1) / h->cz;
   }
+  plan_main(h);
 }
 
 // the regularisation part of the normal operator (writes every owned entry of q, sets pq_part[0])
@@ -372,7 +473,7 @@ static int create_common(int kind, const int64_t nsteps[3], const double origin[
   CK(cudaMalloc(&h->sc, sizeof(CgScalars)));
   CK(cudaMemset(h->sc, 0, sizeof(CgScalars)));
   CK(cudaMallocHost(&h->sc_host, sizeof(CgScalars)));
-  CK(cudaMalloc(&h->partials, sizeof(double) * 3 * MAX_PARTIALS));
+  CK(cudaMalloc(&h->partials, sizeof(double) * 4 * MAX_PARTIALS));
   CK(cudaMalloc(&h->counters, sizeof(unsigned int) * 8));
   CK(cudaMemset(h->counters, 0, sizeof(unsigned int) * 8));
   CK(cudaMalloc(&h->status, sizeof(unsigned long long) * 2));
@@ -838,7 +939,7 @@ int lsb200_solve_cg(lsb200_handle h, double rtol, double atol, int64_t maxiter, 
     init.maxiter = maxit;
     init.nranks = h->nranks;
     init.info = 0;
-    init.pq_part[0] = init.pq_part[1] = 0.0;
+    init.pq_part[0] = init.pq_part[1] = init.pq_part[2] = 0.0;
     init.done = (sqrt(init.rho) < thr) ? 1 : 0;
     *h->sc_host = init;
     CK(cudaMemcpyAsync(sc, h->sc_host, sizeof(CgScalars), cudaMemcpyHostToDevice, h->stream));

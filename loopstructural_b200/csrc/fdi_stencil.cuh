@@ -271,7 +271,9 @@ template <int XB, int TXT, int TYT, int MINB, int ST, bool VEC16>
 __global__ void __launch_bounds__(TXT* TYT, MINB)
     k_fdi_normal(const GridDesc g, const StencilWeights w, const double* __restrict__ p, double* __restrict__ q,
                  const int cz, double* __restrict__ partials, unsigned int* __restrict__ counter,
-                 CgScalars* __restrict__ sc, const int cg_mode) {
+                 CgScalars* __restrict__ sc, const int cg_mode, const int yshell) {
+  // yshell != 0: only the three rows next to either y face are computed (blockIdx.y = 0: rows 0..2,
+  // 1: rows ny-3..ny-1); the rows in between belong to k_fdi_main (fdi_main.cuh).
   using C = StencilCfg<XB, TXT, TYT, ST>;
   extern __shared__ __align__(16) double S[];  // STAGES planes
   __shared__ double red[C::NT / 32];
@@ -280,7 +282,8 @@ __global__ void __launch_bounds__(TXT* TYT, MINB)
 
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int tid = tx + TXT * ty;
-  const int x0 = blockIdx.x * C::TX, y0 = blockIdx.y * C::TY;
+  const int x0 = blockIdx.x * C::TX;
+  const int y0 = yshell ? (blockIdx.y == 0 ? 0 : g.ny - 3) : blockIdx.y * C::TY;
   const int ka = g.k0 + blockIdx.z * cz;
   const int kb = min(ka + cz, g.k1);
 
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(TXT* TYT, MINB)
   const int j = y0 + ty;
   const int i0 = x0 + XB * tx;
   const bool ybnd = (j <= 2 || j >= g.ny - 3);
-  const bool row_ok = j < g.ny;
+  const bool row_ok = j < g.ny && (!yshell || ty < 3);
 
   // canonical accumulators: A[d] collects output plane kp-2+d of the next incoming plane kp;
   // P1/P2 are this thread's p at planes kp-1 / kp-2
@@ -459,7 +462,7 @@ __global__ void __launch_bounds__(TXT* TYT, MINB)
   const unsigned int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
   double total;
   if (grid_sum_last_block<C::NT>(bsum, partials, counter, nblocks, bid, red, &total)) {
-    sc->pq_part[0] = total;
+    sc->pq_part[yshell ? 2 : 0] = total;
   }
 }
 
