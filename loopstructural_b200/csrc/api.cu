@@ -88,7 +88,7 @@ static int load() {
   } while (0)
 
 // ------------------------------------------------------------------ context
-constexpr int MAX_PARTIALS = 1 << 16;
+constexpr int MAX_PARTIALS = 1 << 18;
 constexpr int VEC_NT = 256;
 
 struct lsb200_ctx {
@@ -106,7 +106,7 @@ struct lsb200_ctx {
   long long rows_kept = 0;
   CgScalars* sc = nullptr;
   CgScalars* sc_host = nullptr;  // pinned
-  double* partials = nullptr;    // 4 * MAX_PARTIALS: stencil, rows, x/r update, stencil y-shell
+  double* partials = nullptr;    // 6 * MAX_PARTIALS: stencil, rows, x/r update, stencil y-, x-, z-shell
   unsigned int* counters = nullptr;
   unsigned long long* status = nullptr;  // 2 words
   bool finalized = false;
@@ -118,8 +118,14 @@ struct lsb200_ctx {
   dim3 sgrid;
   // main (register-tiled) kernel + y-shell launch of k_fdi_normal; main_cfg < 0: k_fdi_normal everywhere
   int main_cfg = -1;
-  int main_cz = 0, shell_cz = 0;
-  dim3 main_grid, shell_grid;
+  bool main_uni = false;
+  int main_cz = 0;
+  int box_z0 = 0, box_z1 = 0;
+  dim3 main_grid;
+  // the shell launches run on side streams, overlapped with the box kernel (fork/join by events)
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  bool overlap_shells = true;
   int sm_count = 148;
   long long launches = 0;
   double setup_seconds = 0.0;
@@ -180,13 +186,15 @@ static void plan_stencil(lsb200_ctx* h, int ctas_per_sm) {
 }
 
 // z-chunk length that fills `slots` CTA slots in whole waves with the least halo re-staging
-static int pick_cz(const lsb200_ctx* h, long long tiles, long long slots) {
-  int best_cz = h->g.nzl;
+static int pick_cz(const lsb200_ctx* h, int nplanes, long long tiles, long long slots) {
+  (void)h;
+  if (nplanes < 1) return 1;
+  int best_cz = nplanes;
   double best = -1.0;
-  const int max_nch = std::max(1, h->g.nzl / 4);
+  const int max_nch = std::max(1, nplanes / 4);
   for (int nch = 1; nch <= max_nch && nch <= 4096; ++nch) {
-    const int cz = (h->g.nzl + nch - 1) / nch;
-    const int real = (h->g.nzl + cz - 1) / cz;
+    const int cz = (nplanes + nch - 1) / nch;
+    const int real = (nplanes + cz - 1) / cz;
     const long long ctas = tiles * real;
     if (ctas > MAX_PARTIALS) break;
     const long long waves = (ctas + slots - 1) / slots;
@@ -199,96 +207,143 @@ static int pick_cz(const lsb200_ctx* h, long long tiles, long long slots) {
   return best_cz;
 }
 
-// configurations of k_fdi_main: YB rows per thread, TYT warps, ST ring planes, MINB CTAs per SM
-#define LSB_MAIN_CFGS(X) \
-  X(0, 4, 8, 8, 1)       \
-  X(1, 4, 8, 6, 1)       \
-  X(2, 4, 4, 8, 2)       \
-  X(3, 2, 8, 8, 2)       \
-  X(4, 2, 16, 8, 1)      \
-  X(5, 4, 8, 10, 1)      \
-  X(6, 4, 4, 6, 3)       \
-  X(7, 2, 8, 6, 3)
+// Stencil launch plans.  IDs 0-7: k_fdi_box (interior box, uniform coefficients) beside k_fdi_shell (everything
+// else); -1: k_fdi_normal everywhere (always used on grids too small to have a box).
+// X(ID, YB rows per thread, TYT warps, ST ring planes, MINB CTAs per SM)
+#define LSB_BOX_CFGS(X) \
+  X(0, 4, 4, 8, 2)      \
+  X(1, 4, 8, 8, 1)      \
+  X(2, 2, 8, 8, 2)      \
+  X(3, 2, 16, 8, 1)     \
+  X(4, 4, 4, 6, 3)      \
+  X(5, 2, 8, 6, 3)      \
+  X(6, 3, 8, 8, 1)      \
+  X(7, 3, 4, 8, 2)
 
 static void plan_main(lsb200_ctx* h) {
   const char* env = getenv("LSB200_STENCIL_MAIN");
-  int cfg = env ? atoi(env) : 0;
+  int cfg = env ? atoi(env) : 4;
   h->main_cfg = -1;
+  const GridDesc& g = h->g;
   if (cfg < 0 || h->kind != LSB200_SUPPORT_GRID) return;
-  if (h->g.ny < 16 || h->g.nx < 8) return;  // tiny grids: k_fdi_normal everywhere
+  if (g.ny < 16 || g.nx < 16 || g.nz < 6) return;  // tiny grids: k_fdi_normal everywhere
   int ty = 0, minb = 1;
   switch (cfg) {
 #define X(ID, YB, TYT, ST, MINB) case ID: ty = YB * TYT; minb = MINB; break;
-    LSB_MAIN_CFGS(X)
+    LSB_BOX_CFGS(X)
 #undef X
-    default: cfg = 0; ty = 32; minb = 1;
+    default: cfg = 4; ty = 16; minb = 3;
   }
-  const int tiles_x = (h->g.nx + 63) / 64, tiles_y = (h->g.ny - 6 + ty - 1) / ty;
-  h->main_cz = pick_cz(h, (long long)tiles_x * tiles_y, (long long)h->sm_count * minb);
-  const char* cz = getenv("LSB200_STENCIL_CZ");
-  if (cz && atoi(cz) > 0) h->main_cz = atoi(cz);
-  h->main_grid = dim3(tiles_x, tiles_y, (h->g.nzl + h->main_cz - 1) / h->main_cz);
-  // y shell: 2 strips of 3 rows, k_fdi_normal<2,32,4,...>
-  h->shell_cz = pick_cz(h, (long long)tiles_x * 2, (long long)h->sm_count * 2);
-  if (cz && atoi(cz) > 0) h->shell_cz = atoi(cz);
-  h->shell_grid = dim3(tiles_x, 2, (h->g.nzl + h->shell_cz - 1) / h->shell_cz);
+  const bool box = true;
+  h->main_uni = box;
+  const char* czenv = getenv("LSB200_STENCIL_CZ");
+  const int czo = (czenv && atoi(czenv) > 0) ? atoi(czenv) : 0;
+  auto chunks = [&](int n, int cz) { return n > 0 ? (n + cz - 1) / cz : 0; };
+  // main / box
+  h->box_z0 = box ? std::max(g.k0, 3) : g.k0;
+  h->box_z1 = box ? std::min(g.k1, g.nz - 3) : g.k1;
+  const int nzm = std::max(0, h->box_z1 - h->box_z0);
+  const int tiles_x = ((box ? g.nx - 8 : g.nx) + 63) / 64, tiles_y = (g.ny - 6 + ty - 1) / ty;
+  h->main_cz = czo ? czo : pick_cz(h, nzm, (long long)tiles_x * tiles_y, (long long)h->sm_count * minb);
+  h->main_grid = dim3(tiles_x, tiles_y, chunks(nzm, h->main_cz));
   if ((long long)h->main_grid.x * h->main_grid.y * h->main_grid.z > MAX_PARTIALS) return;
   h->main_cfg = cfg;
 }
 
-static MainConsts make_main_consts(const StencilWeights& w) {
-  MainConsts K;
-  K.cy1 = w.ayy * (-2.0 / 3.0);
-  K.cy2 = w.ayy * (1.0 / 6.0) - 2.0 * w.byz;
-  K.bxy = w.bxy; K.bxz = w.bxz; K.byz = w.byz;
-  K.zt0 = w.azz * (1.0 / 6.0);
-  K.zt1 = w.azz * (-2.0 / 3.0);
-  return K;
+static UniConsts make_uni_consts(const StencilWeights& w) {
+  UniConsts U;
+  U.cc = w.axx + w.ayy + w.azz + 4.0 * (w.bxy + w.bxz + w.byz) + w.ridge2;
+  U.cx1 = w.axx * (-2.0 / 3.0);
+  U.cx2 = w.axx * (1.0 / 6.0) - 2.0 * (w.bxy + w.bxz);
+  U.cy1 = w.ayy * (-2.0 / 3.0);
+  U.cy2 = w.ayy * (1.0 / 6.0) - 2.0 * (w.bxy + w.byz);
+  U.bxy = w.bxy;
+  U.kz = w.azz * (1.0 / 6.0) - 2.0 * (w.bxz + w.byz);
+  U.bxz = w.bxz; U.byz = w.byz;
+  U.zt1 = w.azz * (-2.0 / 3.0);
+  return U;
 }
 
 static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode) {
   const StencilWeights w = make_weights(h);
+  const GridDesc& g = h->g;
   double* part = h->partials;
   unsigned int* cnt = h->counters + 0;
-  const bool vec16 = (h->g.pitch % 2) == 0;
-#define LSB_LAUNCH_AT(GRID, CZ, PART, CNT, YSHELL, XB, TXT, TYT, MINB, ST)                                       \
+  const bool vec16 = (g.pitch % 2) == 0;
+  Region full{0, 0, g.nx, 0, g.ny, g.k0, g.k1, 0, 0};
+#define LSB_LAUNCH_AT(STREAM, GRID, CZ, SLOT, RG, XB, TXT, TYT, MINB, ST)                                        \
   {                                                                                                              \
     const size_t smem = sizeof(double) * StencilCfg<XB, TXT, TYT, ST>::PLANE * ST;                               \
+    double* part_ = h->partials + (size_t)(SLOT) * MAX_PARTIALS;                                                 \
+    unsigned int* cnt_ = h->counters + (SLOT);                                                                   \
     if (vec16) {                                                                                                 \
       auto kern = k_fdi_normal<XB, TXT, TYT, MINB, ST, true>;                                                    \
       if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-      kern<<<GRID, dim3(TXT, TYT), smem, h->stream>>>(h->g, w, p, q, CZ, PART, CNT, h->sc, cg_mode, YSHELL);      \
+      kern<<<GRID, dim3(TXT, TYT), smem, STREAM>>>(g, w, p, q, CZ, part_, cnt_, h->sc, cg_mode, RG);              \
     } else {                                                                                                     \
       auto kern = k_fdi_normal<XB, TXT, TYT, MINB, ST, false>;                                                   \
       if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-      kern<<<GRID, dim3(TXT, TYT), smem, h->stream>>>(h->g, w, p, q, CZ, PART, CNT, h->sc, cg_mode, YSHELL);      \
+      kern<<<GRID, dim3(TXT, TYT), smem, STREAM>>>(g, w, p, q, CZ, part_, cnt_, h->sc, cg_mode, RG);              \
     }                                                                                                            \
+    CKL();                                                                                                       \
+    h->launches++;                                                                                               \
   }
-#define LSB_LAUNCH(XB, TXT, TYT, MINB, ST) LSB_LAUNCH_AT(h->sgrid, h->cz, part, cnt, 0, XB, TXT, TYT, MINB, ST)
+#define LSB_LAUNCH(XB, TXT, TYT, MINB, ST) LSB_LAUNCH_AT(h->stream, h->sgrid, h->cz, 0, full, XB, TXT, TYT, MINB, ST)
   if (h->main_cfg >= 0) {
-    const MainConsts K = make_main_consts(w);
-    switch (h->main_cfg) {
+    const bool box = h->main_uni;
+    const bool ov = h->overlap_shells;
+    // fork: the shell launches read p and write rows / columns / planes the box kernel never touches
+    if (ov) {
+      CK(cudaEventRecord(h->ev_fork, h->stream));
+      CK(cudaStreamWaitEvent(h->side[0], h->ev_fork, 0));
+    }
+    if (h->main_grid.z > 0) {
+      const UniConsts U = make_uni_consts(w);
+      switch (h->main_cfg) {
 #define X(ID, YB, TYT, ST, MINB)                                                                                  \
   case ID: {                                                                                                      \
     const size_t smem = sizeof(double) * MainCfg<YB, TYT, ST>::PLANE * ST;                                        \
     if (vec16) {                                                                                                  \
-      auto kern = k_fdi_main<YB, TYT, ST, MINB, true>;                                                            \
+      auto kern = k_fdi_box<YB, TYT, ST, MINB, true>;                                                             \
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
-      kern<<<h->main_grid, dim3(32, TYT), smem, h->stream>>>(h->g, w, K, p, q, h->main_cz, part, cnt, h->sc, cg_mode); \
+      kern<<<h->main_grid, dim3(32, TYT), smem, h->stream>>>(g, U, p, q, h->main_cz, h->box_z0, h->box_z1, part, cnt, h->sc, cg_mode); \
     } else {                                                                                                      \
-      auto kern = k_fdi_main<YB, TYT, ST, MINB, false>;                                                           \
+      auto kern = k_fdi_box<YB, TYT, ST, MINB, false>;                                                            \
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
-      kern<<<h->main_grid, dim3(32, TYT), smem, h->stream>>>(h->g, w, K, p, q, h->main_cz, part, cnt, h->sc, cg_mode); \
+      kern<<<h->main_grid, dim3(32, TYT), smem, h->stream>>>(g, U, p, q, h->main_cz, h->box_z0, h->box_z1, part, cnt, h->sc, cg_mode); \
     }                                                                                                             \
   } break;
-      LSB_MAIN_CFGS(X)
+        LSB_BOX_CFGS(X)
 #undef X
+      }
+      CKL();
+      h->launches++;
     }
-    CKL();
-    h->launches++;
-    LSB_LAUNCH_AT(h->shell_grid, h->shell_cz, h->partials + 3 * MAX_PARTIALS, h->counters + 3, 1, 2, 32, 4, 2, 4);
-    CKL();
-    h->launches++;
+    // everything outside the box: one gather launch on a side stream, overlapped with the box kernel
+    // (LSB200_SHELL=0 leaves it out: profiling of the box kernel alone, results are then incomplete)
+    static const bool with_shell = !(getenv("LSB200_SHELL") && atoi(getenv("LSB200_SHELL")) == 0);
+    if (with_shell) {
+      ShellBox sb;
+      sb.ilo = box ? 4 : 0; sb.ihi = box ? g.nx - 4 : g.nx;
+      sb.jlo = 3; sb.jhi = g.ny - 3;
+      sb.klo = h->box_z0; sb.khi = std::max(h->box_z0, h->box_z1);
+      const int nzm = sb.khi - sb.klo;
+      sb.n_full_planes = g.nzl - nzm;
+      sb.full_blocks = (g.nx * g.ny + 255) / 256;
+      sb.yrow_blocks = ((g.ny - (sb.jhi - sb.jlo)) * g.nx + 255) / 256;
+      sb.xcol_blocks = ((sb.jhi - sb.jlo) * (g.nx - (sb.ihi - sb.ilo)) + 255) / 256;
+      const long long nb = (long long)sb.n_full_planes * sb.full_blocks + (long long)nzm * (sb.yrow_blocks + sb.xcol_blocks);
+      if (nb > MAX_PARTIALS) return fail(LSB200_ERR_ARG, "shell launch needs %lld CTAs (limit %d)", nb, MAX_PARTIALS);
+      if (nb > 0)
+        k_fdi_shell<256><<<(int)nb, 256, 0, ov ? h->side[0] : h->stream>>>(g, w, sb, p, q, h->partials + 3 * (size_t)MAX_PARTIALS,
+                                                                          h->counters + 3, h->sc, cg_mode);
+      CKL();
+      h->launches++;
+    }
+    if (ov) {
+      CK(cudaEventRecord(h->ev_join[0], h->side[0]));
+      CK(cudaStreamWaitEvent(h->stream, h->ev_join[0], 0));
+    }
     return 0;
   }
   switch (h->stencil_cfg) {
@@ -303,8 +358,6 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
   }
 #undef LSB_LAUNCH
 #undef LSB_LAUNCH_AT
-  CKL();
-  h->launches++;
   return 0;
 }
 
@@ -470,10 +523,16 @@ static int create_common(int kind, const int64_t nsteps[3], const double origin[
   CK(cudaGetDeviceProperties(&prop, device));
   h->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (int t = 0; t < 3; ++t) {
+    CK(cudaStreamCreateWithFlags(&h->side[t], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_join[t], cudaEventDisableTiming));
+  }
+  CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  { const char* e = getenv("LSB200_OVERLAP"); h->overlap_shells = !(e && atoi(e) == 0); }
   CK(cudaMalloc(&h->sc, sizeof(CgScalars)));
   CK(cudaMemset(h->sc, 0, sizeof(CgScalars)));
   CK(cudaMallocHost(&h->sc_host, sizeof(CgScalars)));
-  CK(cudaMalloc(&h->partials, sizeof(double) * 4 * MAX_PARTIALS));
+  CK(cudaMalloc(&h->partials, sizeof(double) * 6 * MAX_PARTIALS));
   CK(cudaMalloc(&h->counters, sizeof(unsigned int) * 8));
   CK(cudaMemset(h->counters, 0, sizeof(unsigned int) * 8));
   CK(cudaMalloc(&h->status, sizeof(unsigned long long) * 2));
@@ -507,6 +566,11 @@ int lsb200_destroy(lsb200_handle h) {
   cudaFree(h->counters);
   cudaFree(h->status);
   if (h->comm) nccl::CommDestroy(h->comm);
+  for (int t = 0; t < 3; ++t) {
+    if (h->side[t]) cudaStreamDestroy(h->side[t]);
+    if (h->ev_join[t]) cudaEventDestroy(h->ev_join[t]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -939,7 +1003,7 @@ int lsb200_solve_cg(lsb200_handle h, double rtol, double atol, int64_t maxiter, 
     init.maxiter = maxit;
     init.nranks = h->nranks;
     init.info = 0;
-    init.pq_part[0] = init.pq_part[1] = init.pq_part[2] = 0.0;
+    for (int t = 0; t < 5; ++t) init.pq_part[t] = 0.0;
     init.done = (sqrt(init.rho) < thr) ? 1 : 0;
     *h->sc_host = init;
     CK(cudaMemcpyAsync(sc, h->sc_host, sizeof(CgScalars), cudaMemcpyHostToDevice, h->stream));

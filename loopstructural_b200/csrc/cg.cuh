@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(NT)
                    double* __restrict__ partials, unsigned int* __restrict__ counter, CgScalars* __restrict__ sc) {
   __shared__ double red[NT / 32];
   if (sc->done) return;
-  const double pq = sc->nranks == 1 ? (sc->pq_part[0] + sc->pq_part[2]) + sc->pq_part[1] : sc->pq;
+  const double pq = sc->nranks == 1 ? (((sc->pq_part[0] + sc->pq_part[2]) + sc->pq_part[3]) + sc->pq_part[4]) + sc->pq_part[1] : sc->pq;
   const double alpha = sc->rho / pq;
   const long long n2 = n >> 1;
   const double2* p2 = reinterpret_cast<const double2*>(p);
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(NT)
 // multi-rank: scalar steps run as tiny kernels after the all-reduce
 __global__ void k_cg_pack_pq(CgScalars* sc) {
   if (sc->done) return;
-  sc->pq = (sc->pq_part[0] + sc->pq_part[2]) + sc->pq_part[1];
+  sc->pq = (((sc->pq_part[0] + sc->pq_part[2]) + sc->pq_part[3]) + sc->pq_part[4]) + sc->pq_part[1];
 }
 __global__ void k_cg_scalar_step(CgScalars* sc) {
   if (sc->done) return;

@@ -39,7 +39,7 @@ struct CgScalars {
   double rho;       // r . S^2 r of the current residual (== ||r||^2 in the column-scaled variables)
   double rho_new;   // reduction target of the x/r update
   double pq;        // p . N p (sum of the parts below, all-reduced across ranks)
-  double pq_part[3];  // [0] stencil kernel, [1] data rows, [2] y-shell rows of the stencil (0 when unused)
+  double pq_part[5];  // [0] stencil kernel, [1] data rows, [2]/[3]/[4] y-/x-/z-shell launches of the stencil (0 when unused)
   double beta;
   double thr2;      // threshold^2
   long long iter;
