@@ -28,7 +28,10 @@ sys.path.insert(0, ROOT)
 METRIC = "fdi_cg_node_updates_per_second"
 UNIT = "dof-iter/s"
 BYTES_MATVEC_PER_DOF = 16.0      # read p, write q
-BYTES_ITERATION_PER_DOF = 96.0   # matvec 16 + x/r update 48 (+8 scaling) + p update 24 (+8 scaling) = 96 with scaling
+# dram__bytes_read.sum + dram__bytes_write.sum of one 256^3 matvec from ncu --set full (profiles/r01e_box_cfg0_full_details.csv:
+# 146.0 + 81.3 MB for k_fdi_box; profiles/r01j_shell_full_details.csv: 25.8 + 2.7 MB for k_fdi_shell)
+TRAFFIC_MATVEC_256 = (146.03 + 81.28 + 25.85 + 2.70) * 1e6
+BYTES_ITERATION_PER_DOF = 104.0  # matvec 16 + x/r update 48 (+8 scaling vector) + p update 24 (+8 scaling vector)
 
 
 def synthetic_points(n_value, n_gradient, zscale=1.0, seed=0):
@@ -211,15 +214,31 @@ def run_ours(args):
         c, res = eng.solve_cg(rtol=1e-5, atol=0.0, want_c=False)
         return res
 
+    interp = None
+    if world == 1:
+        # the public, reference-shaped API (loopstructural_b200.interpolators): what a LoopStructural user calls
+        from loopstructural_b200.interpolators import B200FiniteDifferenceInterpolator, Support
+
+        interp = B200FiniteDifferenceInterpolator(Support(np.zeros(3), nsteps - 1, step), device=local)
+        interp._engine = eng  # same device handle: the node vectors (7 x 134 MB) are allocated once
+
     def step_e2e():
-        """public API with host buffers: H2D of the constraint arrays, setup, solve, D2H of c."""
+        """public API with host buffers: H2D of the constraint arrays, row generation, rhs / diagonal /
+        scaling, CG solve, D2H of the solved node values."""
+        if interp is not None:
+            interp.set_value_constraints(value_h)
+            interp.set_gradient_constraints(gradient_h)
+            interp.setup_interpolator()
+            interp.solve_system("b200")
+            t = interp.get_last_solve_timing()
+            return t["iterations"]
         eng.clear_rows()
         eng.add_point_rows(en.ROWS_VALUE, value_h, 1.0)
         eng.add_point_rows(en.ROWS_GRADIENT, gradient_h, 1.0)
         c, res = eng.solve_cg(rtol=1e-5, atol=0.0, want_c=False)
         from loopstructural_b200 import _native as nat
         nat.check(eng._lib.lsb200_get_c(eng._h, nat.dptr(c_host)))
-        return res
+        return res.iterations
 
     # ---- device-resident arm
     eng.add_point_rows(en.ROWS_VALUE, value_h, 1.0)
@@ -253,7 +272,7 @@ def run_ours(args):
     t0 = time.perf_counter()
     its_e2e = 0
     for _ in range(args.steps):
-        its_e2e += step_e2e().iterations
+        its_e2e += step_e2e()
     barrier()
     wall_e2e = time.perf_counter() - t0
 
@@ -284,8 +303,10 @@ def run_ours(args):
                        "dof": dof_global},
             "solve_seconds": dev_s / max(args.steps, 1), "cg_iterations": iters_per_solve,
             "cg_iterations_per_second": its / dev_s if dev_s > 0 else None,
-            "roofline": {"bound": "hbm", "kernel": "k_fdi_normal (regularisation normal matvec)", "achieved": ach,
-                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": "FDI regularisation normal matvec = k_fdi_box + k_fdi_shell (one logical "
+                                                   "launch: interior box beside the boundary shell on a side stream)",
+                         "achieved": ach,
+                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": TRAFFIC_MATVEC_256 if n == 256 and world == 1 else None,
                          "seconds_per_launch": t_matvec, "bytes_per_dof": BYTES_MATVEC_PER_DOF},
             "roofline_iteration": {"bound": "hbm", "achieved": ach_it, "peak": peak, "unit": "GB/s",
                                    "frac": ach_it / peak, "seconds_per_iteration": t_iter,

@@ -123,6 +123,13 @@ int lsb200_add_rows(lsb200_handle h, int64_t n_rows, int k, const double* vals, 
 int lsb200_add_point_rows(lsb200_handle h, int kind, int64_t n, const double* data, int ncols,
                           double weight, int64_t* n_rows_out);
 
+/* Interface rows N(x_i) - N(x_j) = 0 for n point pairs (FDI.add_interface_constraints,
+ * LI/_finite_difference_interpolator.py:297-340): 16 listed entries per row, weight ipw.  The pairing per
+ * interface id (all / star / chain, :271-295) is done by the caller; pairs with a point outside the grid are
+ * dropped.  xyz_i, xyz_j are (n,3) row-major. */
+int lsb200_add_pair_rows(lsb200_handle h, int64_t n, const double* xyz_i, const double* xyz_j, double weight,
+                         int64_t* n_rows_out);
+
 int lsb200_clear_rows(lsb200_handle h);
 int64_t lsb200_num_rows(lsb200_handle h);
 

@@ -308,4 +308,44 @@ __global__ void k_fdi_point_rows(const GridDesc g, const int kind, const long lo
   }
 }
 
+// Interface rows N(x_i) - N(x_j) = 0 (FDI.add_interface_constraints,
+// LI/_finite_difference_interpolator.py:297-340): 16 listed entries per pair, normalised over the listed
+// entries (duplicate columns merge only later in the reference, LI/_discrete_interpolator.py:361-366,384-386).
+// The pairing itself (all / star / chain per interface id) is host logic, as in the reference (:271-295).
+__global__ void k_fdi_pair_rows(const GridDesc g, const long long n, const double* __restrict__ xi,
+                                const double* __restrict__ xj, const double weight, RowBlock rb,
+                                unsigned long long* __restrict__ status) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    const double a[3] = {xi[3 * r], xi[3 * r + 1], xi[3 * r + 2]};
+    const double b[3] = {xj[3 * r], xj[3 * r + 1], xj[3 * r + 2]};
+    const CellLoc La = locate(g, a), Lb = locate(g, b);
+    bool ok = La.inside && Lb.inside;
+    // a slab can only apply a row whose two cells both lie within its owned + halo planes
+    const bool touches = (La.ci[2] + 1 >= g.k0 && La.ci[2] < g.k1) || (Lb.ci[2] + 1 >= g.k0 && Lb.ci[2] < g.k1);
+    const bool reach = La.ci[2] >= g.k0 - HALO && La.ci[2] + 1 < g.k1 + HALO && Lb.ci[2] >= g.k0 - HALO &&
+                       Lb.ci[2] + 1 < g.k1 + HALO;
+    if (ok && touches && !reach) atomicExch(status + 1, 1ull);
+    ok = ok && touches && reach;
+    double wa[8], wb[8];
+    double nrm2 = 0.0;
+    if (ok) {
+      trilinear_w(La.lc, wa);
+      trilinear_w(Lb.lc, wb);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) nrm2 += wa[c] * wa[c] + wb[c] * wb[c];
+      atomicAdd(status, 1ull);
+    }
+    const double len = sqrt(nrm2);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      rb.vals[c * rb.n + r] = ok ? (len > 0.0 ? wa[c] / len : wa[c]) : 0.0;
+      rb.cols[c * rb.n + r] = ok ? (int)corner_local(g, La.ci, c) : -1;
+      rb.vals[(c + 8) * rb.n + r] = ok ? (len > 0.0 ? -wb[c] / len : -wb[c]) : 0.0;
+      rb.cols[(c + 8) * rb.n + r] = ok ? (int)corner_local(g, Lb.ci, c) : -1;
+    }
+    rb.b[r] = 0.0;
+    rb.w2[r] = ok ? weight * weight : 0.0;
+  }
+}
+
 }  // namespace lsb

@@ -33,6 +33,27 @@ def effective_stencil_weights(weights: dict) -> np.ndarray:
                      w["dx"], w["dy"], w["dz"]], dtype=np.float64)
 
 
+def interface_pair_indices(n: int, mode: str = "auto", threshold: int = 200, fallback: str = "star") -> np.ndarray:
+    """FiniteDifferenceInterpolator._interface_pair_indices (LI/_finite_difference_interpolator.py:271-295)."""
+    if n < 2:
+        return np.zeros((0, 2), dtype=np.int64)
+    mode = str(mode).lower()
+    threshold = max(2, int(threshold))
+    fallback = str(fallback).lower()
+    if fallback not in ("star", "chain"):
+        fallback = "star"
+    if mode == "auto":
+        mode = fallback if n > threshold else "all"
+    if mode == "all":
+        ii, jj = np.triu_indices(n, k=1)
+        return np.column_stack([ii, jj]).astype(np.int64)
+    if mode == "star":
+        return np.column_stack([np.zeros(n - 1, dtype=np.int64), np.arange(1, n, dtype=np.int64)])
+    if mode == "chain":
+        return np.column_stack([np.arange(0, n - 1, dtype=np.int64), np.arange(1, n, dtype=np.int64)])
+    raise ValueError(f"Unknown interface_pair_mode {mode!r}. Use one of: auto, all, star, chain")
+
+
 @dataclass
 class SolveResult:
     info: int
@@ -128,6 +149,40 @@ class Engine:
         out = C.c_int64(0)
         nat.check(self._lib.lsb200_add_point_rows(self._h, int(kind), data.shape[0], nat.dptr(data), data.shape[1],
                                                   float(weight), C.byref(out)))
+        return int(out.value)
+
+    def add_interface_rows(self, points, weight: float, mode: str = "auto", threshold: int = 200,
+                           fallback: str = "star") -> int:
+        """FDI.add_interface_constraints (LI/_finite_difference_interpolator.py:297-340).  ``points`` is (n,5):
+        x y z id w.  The pairing per interface id is host logic here as it is in the reference
+        (_interface_pair_indices, :271-295, over the points that lie inside the grid); the rows themselves are
+        generated on the device."""
+        pts = nat.as_f64(points)
+        if pts.ndim != 2 or pts.shape[1] < 4:
+            raise ValueError("interface points must be (n, >=4): x y z id")
+        if pts.shape[0] < 2:
+            return 0
+        # StructuredGrid.inside with its 32 eps tolerance (LC/supports/_3d_base_structured.py:287-293)
+        maximum = self.origin + (self.nsteps - 1) * self.step
+        tol = np.finfo(float).eps * 32.0 * np.maximum(np.abs(maximum - self.origin), 1.0)
+        xyz = pts[:, :3]
+        with np.errstate(invalid="ignore"):
+            inside = np.all((xyz >= self.origin - tol) & (xyz <= maximum + tol), axis=1)
+        ids = pts[inside, 3]
+        xin = xyz[inside]
+        pi, pj = [], []
+        for uid in np.unique(ids[~np.isnan(ids)]):
+            sel = np.flatnonzero(ids == uid)
+            pair = interface_pair_indices(len(sel), mode, threshold, fallback)
+            if pair.shape[0]:
+                pi.append(xin[sel[pair[:, 0]]])
+                pj.append(xin[sel[pair[:, 1]]])
+        if not pi:
+            return 0
+        xi, xj = nat.as_f64(np.vstack(pi)), nat.as_f64(np.vstack(pj))
+        out = C.c_int64(0)
+        nat.check(self._lib.lsb200_add_pair_rows(self._h, xi.shape[0], nat.dptr(xi), nat.dptr(xj), float(weight),
+                                                 C.byref(out)))
         return int(out.value)
 
     def clear_rows(self):

@@ -1,0 +1,209 @@
+"""Puts the B200 engine behind LoopStructural's own interpolator classes.
+
+``install()`` needs the reference packages (``loop_interpolation`` / ``loop_common``) importable.  It replaces
+``interpolator_map[InterpolatorType.FINITE_DIFFERENCE]`` -- the plain module-level dict that
+``InterpolatorFactory.create_interpolator`` consults at call time (LI/__init__.py:106-117,
+LI/_interpolator_factory.py:57-66) -- by a subclass of ``FiniteDifferenceInterpolator`` which
+
+* lets ``setup_interpolator(..., solver='b200')`` build every data family exactly as the reference does
+  (value, gradient, norm, tangent, interface, frame orthogonality, fold rows ... all end up row-normalised in
+  ``self.constraints[name] = {"matrix", "b", "w"}``, LI/_discrete_interpolator.py:316-389) but records only the
+  WEIGHTS of the twelve stencil families instead of materialising their rows (``assemble_inner`` /
+  ``assemble_borders``, LI/_finite_difference_interpolator.py:1052-1164);
+* serves ``solve_system(solver='b200')`` (LI/_discrete_interpolator.py:1221-1319) on the device: constraint
+  dict -> ELL rows through ``lsb200_add_rows``, ridge / column scaling / CG to the reference's stopping rule on
+  the GPU, ``self.c`` back as a host ndarray;
+* defers every other solver name to the reference (after re-assembling the stencil rows it had diverted).
+
+``GeologicalModel.create_and_add_foliation('strati', solver='b200')`` then uses the engine unchanged, because
+``solver`` rides in the builder's kwargs to both ``setup_interpolator`` and ``solve_system``
+(LoopStructural/modelling/features/builders/_geological_feature_builder.py:558-569).
+
+There is no CPU fallback: with ``solver='b200'`` and no usable CUDA device ``solve_system`` raises.
+"""
+from __future__ import annotations
+
+from time import perf_counter
+
+import numpy as np
+
+from .interpolators import B200_SOLVERS
+
+_STENCIL_NAMES = ("dxx", "dyy", "dzz", "dxy", "dxz", "dyz")
+_installed = {}
+
+
+def constraints_to_rows(constraints: dict):
+    """Turn the reference's constraint dict into ELL row blocks: a list of (name, vals (n,k), cols (n,k) int64,
+    b (n,), w (n,)).  Rows are already L2-normalised by add_constraints_to_least_squares; duplicate columns were
+    merged by its coo->csc conversion (LI/_discrete_interpolator.py:361-366,384-386).  Unused slots hold
+    value 0 on column 0."""
+    out = []
+    for name, c in constraints.items():
+        w = np.asarray(c["w"], dtype=np.float64).ravel()
+        if w.size == 0:
+            continue  # build_matrix skips families with empty w (LI/_discrete_interpolator.py:694-696)
+        m = c["matrix"].tocsr()
+        m.sort_indices()
+        n = m.shape[0]
+        counts = np.diff(m.indptr)
+        k = int(counts.max()) if n else 0
+        if n == 0 or k == 0:
+            continue
+        vals = np.zeros((n, k))
+        cols = np.zeros((n, k), dtype=np.int64)
+        slot = np.arange(m.nnz) - np.repeat(m.indptr[:-1], counts)
+        rows = np.repeat(np.arange(n), counts)
+        vals[rows, slot] = m.data
+        cols[rows, slot] = m.indices
+        out.append((name, vals, cols, np.asarray(c["b"], dtype=np.float64).ravel(), w))
+    return out
+
+
+def _make_fdi_class():
+    from loop_common.supports import StructuredGrid
+    from loop_interpolation import FiniteDifferenceInterpolator
+    from loop_interpolation._operator import Operator
+
+    default_masks = {"dxx": Operator.Dxx_mask, "dyy": Operator.Dyy_mask, "dzz": Operator.Dzz_mask,
+                     "dxy": Operator.Dxy_mask, "dxz": Operator.Dxz_mask, "dyz": Operator.Dyz_mask}
+
+    class B200FDI(FiniteDifferenceInterpolator):
+        """FiniteDifferenceInterpolator whose ``solver='b200'`` runs on the GPU engine."""
+
+        def __init__(self, grid, data=None):
+            super().__init__(grid, data=data)
+            self._b200_divert = False
+            self._b200_stencil = {}
+            self._b200_setup_kwargs = {}
+            self._b200_engine = None
+
+        # -- setup: divert the stencil families ---------------------------------------------------------
+        def _b200_can_divert(self, kwargs) -> bool:
+            sup = self.support
+            return (kwargs.get("solver") in B200_SOLVERS and isinstance(sup, StructuredGrid)
+                    and getattr(sup, "dimension", 3) == 3 and not getattr(sup, "is_rectilinear", False)
+                    and "operators" not in kwargs and not kwargs.get("use_regularisation_weight_scale", False))
+
+        def setup_interpolator(self, **kwargs):
+            self._b200_setup_kwargs = dict(kwargs)
+            self._b200_stencil = {}
+            self._b200_divert = self._b200_can_divert(kwargs)
+            return super().setup_interpolator(**kwargs)
+
+        def assemble_inner(self, operator, w, name="regularisation"):
+            if (self._b200_divert and name in default_masks and operator is not None
+                    and np.array_equal(operator, default_masks[name])):
+                # w is the effective row weight (mixed terms already / 4, LC/supports/_3d_structured_grid.py:502-509)
+                self._b200_stencil[name] = float(w)
+                return
+            return super().assemble_inner(operator, w, name=name)
+
+        def assemble_borders(self):
+            if self._b200_divert:
+                for k in ("dx", "dy", "dz"):
+                    self._b200_stencil[k] = float(self.interpolation_weights[k])
+                return
+            return super().assemble_borders()
+
+        # -- solve ---------------------------------------------------------------------------------------
+        def solve_system(self, solver=None, tol=None, solver_kwargs=None) -> bool:
+            if solver not in B200_SOLVERS:
+                if self._b200_divert:
+                    # the stencil rows were never assembled: redo the setup the stock way for this solver
+                    kw = dict(self._b200_setup_kwargs)
+                    kw["solver"] = solver
+                    self.setup_interpolator(**kw)
+                return super().solve_system(solver=solver, tol=tol, solver_kwargs=solver_kwargs)
+            if not self._b200_divert:
+                kw = dict(self._b200_setup_kwargs)
+                kw["solver"] = solver
+                if not self._b200_can_divert(kw):
+                    raise ValueError("solver='b200' needs a 3-D regular StructuredGrid with the default operator masks "
+                                     "and no per-node regularisation scale")
+                self.setup_interpolator(**kw)
+            if not self._pre_solve():
+                raise ValueError("Pre solve failed")
+            from .engine import Engine
+
+            started = perf_counter()
+            sup = self.support
+            kw = dict(solver_kwargs or {})
+            rtol = float(kw.get("rtol", 1e-5))
+            atol = float(kw.get("atol", 0.0))
+            if tol is not None and not ("atol" in kw and "rtol" in kw):
+                atol = float(tol)  # LI/_solver_strategy.py:59-60
+            if self._b200_engine is not None:
+                self._b200_engine.close()
+            eng = Engine(np.asarray(sup.nsteps), np.asarray(sup.origin, float), np.asarray(sup.step_vector, float))
+            self._b200_engine = eng
+            st = self._b200_stencil
+            # effective weights go in directly: the engine's dict API divides the mixed terms by 4 itself
+            eng.set_regularisation({"dxx": st.get("dxx", 0.0), "dyy": st.get("dyy", 0.0), "dzz": st.get("dzz", 0.0),
+                                    "dxy": 4.0 * st.get("dxy", 0.0), "dxz": 4.0 * st.get("dxz", 0.0),
+                                    "dyz": 4.0 * st.get("dyz", 0.0), "dx": st.get("dx", 0.0), "dy": st.get("dy", 0.0),
+                                    "dz": st.get("dz", 0.0)})
+            eng.set_options(ridge_factor=self.ridge_factor, add_ridge=self.add_ridge_regulatisation,
+                            apply_scaling=self.apply_scaling_matrix)
+            t_asm = perf_counter()
+            n_rows = 0
+            for _name, vals, cols, b, w in constraints_to_rows(self.constraints):
+                eng.add_rows(vals, cols, b, w, normalise=False)
+                n_rows += vals.shape[0]
+            assembly = perf_counter() - t_asm
+            c, res = eng.solve_cg(rtol=rtol, atol=atol, maxiter=kw.get("maxiter"), x0=kw.get("x0"))
+            self.c = c
+            self.up_to_date = True
+            self.latest_solve_timing = {
+                "solver": solver, "backend": "b200", "assembly_seconds": assembly,
+                "preprocess_seconds": res.setup_seconds, "solve_seconds": res.solve_seconds,
+                "total_seconds": perf_counter() - started, "iterations": res.iterations, "info": res.info,
+                "matrix_rows": n_rows, "matrix_cols": int(self.dof), "up_to_date": True,
+            }
+            return True
+
+        # -- evaluation: the device holds c after a b200 solve ---------------------------------------------
+        def _b200_engine_current(self):
+            eng = self._b200_engine
+            if eng is None or not self.up_to_date:
+                return None
+            return eng
+
+        def _evaluate_value_local(self, locations):
+            self.update()
+            eng = self._b200_engine_current()
+            if eng is None or self.latest_solve_timing.get("backend") != "b200":
+                return super()._evaluate_value_local(locations)
+            return eng.evaluate_value(np.asarray(locations, dtype=np.float64))
+
+        def _evaluate_gradient_local(self, locations):
+            self.update()
+            eng = self._b200_engine_current()
+            if eng is None or self.latest_solve_timing.get("backend") != "b200":
+                return super()._evaluate_gradient_local(locations)
+            locations = np.asarray(locations, dtype=np.float64)
+            if locations.shape[0] == 0:
+                return np.zeros((0, 3))
+            return eng.evaluate_gradient(locations)
+
+    B200FDI.__name__ = "B200FiniteDifferenceInterpolator"
+    return B200FDI
+
+
+def install():
+    """Register the B200 subclasses in the reference's ``interpolator_map`` (idempotent).  Returns the classes."""
+    import loop_interpolation as li
+
+    if "fdi" not in _installed:
+        _installed["fdi"] = _make_fdi_class()
+        _installed["fdi_stock"] = li.interpolator_map[li.InterpolatorType.FINITE_DIFFERENCE]
+    li.interpolator_map[li.InterpolatorType.FINITE_DIFFERENCE] = _installed["fdi"]
+    return {"FDI": _installed["fdi"]}
+
+
+def uninstall():
+    """Put the stock classes back."""
+    import loop_interpolation as li
+
+    if "fdi_stock" in _installed:
+        li.interpolator_map[li.InterpolatorType.FINITE_DIFFERENCE] = _installed["fdi_stock"]

@@ -289,3 +289,116 @@ def test_evaluate_large_cloud_against_oracle():
     face = np.array([[hi[0], 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])]])
     assert abs(e.evaluate_value(face)[0] - (grid.nsteps[0] - 1)) <= 1e-12
     e.close()
+
+
+# ---------------------------------------------------------------- host-side mirror of the reference API
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_interface_rows_generated_on_device_match_reference(tag):
+    """lsb200_add_pair_rows == the reference's interface_<id> families (16 listed entries, pairing on the host)."""
+    z = np.load(os.path.join(GOLDEN, f"fdi_rows_{tag}.npz"))
+    grid = fo.Grid.from_cells(z["ncells"], z["origin"], z["step"])
+    kw = H.weights_of(z, "kw_keys", "kw_vals")
+    e = H.engine_for(grid, dict.fromkeys(("dxx", "dyy", "dzz", "dxy", "dyz", "dxz", "dx", "dy", "dz"), 0.0))
+    e.set_options(add_ridge=False, apply_scaling=False)
+    n = e.add_interface_rows(z["interface"], kw["ipw"])
+    names = [str(s) for s in z["names"] if str(s).startswith("interface_")]
+    assert names
+    dof = grid.n_nodes
+    p = np.random.default_rng(8).standard_normal(dof)
+    q_ref, diag_ref, n_ref = np.zeros(dof), np.zeros(dof), 0
+    for name in names:
+        m, b, w = H.ref_family(z, name)
+        n_ref += m.shape[0]
+        q_ref += m.T @ (w * w * (m @ p))
+        diag_ref += np.asarray(m.multiply(m).T @ (w * w)).ravel()
+    assert n == n_ref
+    assert np.abs(e.apply_normal(p, parts=2) - q_ref).max() <= 1e-12 * np.abs(q_ref).max()
+    assert np.abs(e.diagonal() - diag_ref).max() <= 1e-12 * np.abs(diag_ref).max()
+    assert not e.rhs().any()
+    e.close()
+
+
+@pytest.mark.parametrize("tag", ["unit16", "aniso", "unit24_tight"])
+def test_interpolator_api_matches_reference(tag):
+    """B200FiniteDifferenceInterpolator driven like the reference's class (set_*_constraints, setup_interpolator,
+    solve_system, evaluate_*) reproduces the reference's coefficients and evaluations on the golden cases."""
+    from loopstructural_b200.interpolators import B200FiniteDifferenceInterpolator, Support
+
+    z = np.load(os.path.join(GOLDEN, f"fdi_solve_{tag}.npz"))
+    grid, weights, fams, rtol, atol = H.solve_case(z)
+    it = B200FiniteDifferenceInterpolator(Support(grid.origin, grid.nsteps - 1, grid.step))
+    it.apply_scaling_matrix = bool(z["scaling"])
+    for key in ("value", "gradient", "normal", "tangent"):
+        if f"data_{key}" in z:
+            getattr(it, f"set_{key}_constraints")(z[f"data_{key}"])
+    kw = H.weights_of(z, "kw_keys", "kw_vals")
+    counts = it.setup_interpolator(**kw)
+    assert counts["value"] > 0 and counts["regularisation"] == "matrix-free"
+    skw = {"rtol": rtol, "atol": atol}
+    assert it.solve_system("b200", solver_kwargs=skw) is True
+    t = it.get_last_solve_timing()
+    assert t["backend"] == "b200" and abs(t["iterations"] - int(z["iterations"])) <= 1
+    rng_ = float(z["c"].max() - z["c"].min())
+    assert np.linalg.norm(it.c - z["c"]) / np.sqrt(it.c.size) / rng_ <= 1e-6
+    q = z["query"]
+    v = it.evaluate_value(q)
+    np.testing.assert_array_equal(np.isnan(v), np.isnan(z["value_at"]))
+    fin = ~np.isnan(v)
+    assert np.abs(v[fin] - z["value_at"][fin]).max() <= 1e-5 * rng_
+    # assigning c from outside (the reference lets callers do that) re-syncs the device copy
+    it.set_c(z["c"])
+    np.testing.assert_allclose(it.evaluate_value(q), z["value_at"], rtol=0, atol=1e-13, equal_nan=True)
+    with pytest.raises(ValueError):
+        it.solve_system("cg")
+    it.close()
+
+
+def test_interpolator_api_tol_semantics_and_errors():
+    """tol -> atol unless both atol and rtol are given (LI/_solver_strategy.py:59-60); solve before setup fails."""
+    from loopstructural_b200.interpolators import B200FiniteDifferenceInterpolator, Support
+
+    grid, value, gradient = fo.synthetic_problem(12, 200, 20, seed=2)
+    it = B200FiniteDifferenceInterpolator(Support(grid.origin, grid.nsteps - 1, grid.step))
+    with pytest.raises(ValueError):
+        it.solve_system("b200")
+    with pytest.raises(ValueError):
+        it.set_value_constraints(np.zeros((3, 4)))
+    it.set_value_constraints(value)
+    it.set_gradient_constraints(gradient)
+    it.setup_interpolator()
+    it.solve_system("b200", tol=1e-3)
+    loose = it.get_last_solve_timing()
+    assert loose["threshold"] >= 1e-3  # atol = tol
+    it.solve_system("b200", tol=1e-3, solver_kwargs={"atol": 0.0, "rtol": 1e-9})
+    tight = it.get_last_solve_timing()
+    assert tight["iterations"] > loose["iterations"] and tight["threshold"] < loose["threshold"]
+    assert it.update() is True
+    it.close()
+
+
+def test_full_size_solve_properties():
+    """BASELINE configs[1] (256^3 nodes, 1e5 value + 1e4 gradient points) through the public class: the device
+    CG stops by the reference's rule, the final residual recomputed from the returned c through the operator
+    agrees with the recurrence, and the field honours the data."""
+    from loopstructural_b200.interpolators import B200FiniteDifferenceInterpolator, Support
+
+    n = 256
+    grid, value, gradient = fo.synthetic_problem(n, 100_000, 10_000, seed=0)
+    it = B200FiniteDifferenceInterpolator(Support(grid.origin, grid.nsteps - 1, grid.step))
+    it.set_value_constraints(value)
+    it.set_gradient_constraints(gradient)
+    it.setup_interpolator()
+    assert it.solve_system("b200") is True
+    t = it.get_last_solve_timing()
+    assert t["info"] == 0 and t["residual_norm"] < t["threshold"]
+    e = it.engine
+    S = e.scaling()
+    r = e.rhs() - e.apply_normal(it.c)
+    assert abs(np.linalg.norm(S * r) - t["residual_norm"]) <= 1e-6 * t["threshold"] + 1e-3 * t["residual_norm"]
+    # values at the data points are close to the data (cpw = 1 against unit regularisation)
+    v = it.evaluate_value(value[:, :3])
+    assert np.nanmax(np.abs(v - value[:, 3])) < 0.05
+    g = it.evaluate_gradient(gradient[:2000, :3])
+    cosang = np.sum(g * gradient[:2000, 3:6], axis=1) / (np.linalg.norm(g, axis=1) * np.linalg.norm(gradient[:2000, 3:6], axis=1))
+    assert np.median(cosang) > 0.95
+    it.close()
