@@ -1,0 +1,53 @@
+"""Worker of the multi-GPU parity test (one process per GPU, launched by torch.distributed.run):
+solves a golden FDI case on z-slabs and checks the gathered coefficients against the reference's."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+import golden_helpers as H  # noqa: E402
+from loopstructural_b200 import Engine, partition  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    for tag in sys.argv[1:] or ["unit24_tight", "aniso"]:
+        z = np.load(os.path.join(H.GOLDEN, f"fdi_solve_{tag}.npz"))
+        grid, weights, fams, rtol, atol = H.solve_case(z)
+        bounds = partition.slab_bounds(int(grid.nsteps[2]), world)
+        e = Engine(grid.nsteps, grid.origin, grid.step, slab=bounds[rank], device=local)
+        ids = [Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0, device=torch.device("cuda", local))
+        e.comm_init(ids[0], rank, world)
+        e.set_regularisation(weights)
+        e.set_options(apply_scaling=bool(z["scaling"]))
+        H.add_point_data(e, z, weights)
+        c_loc, res = e.solve_cg(rtol=rtol, atol=atol)
+        parts = [None] * world
+        dist.all_gather_object(parts, c_loc)
+        if rank == 0:
+            c = partition.gather_slabs(parts)
+            rng_ = float(z["c"].max() - z["c"].min())
+            rel = np.linalg.norm(c - z["c"]) / np.sqrt(c.size) / rng_
+            good = rel <= 1e-6 and abs(res.iterations - int(z["iterations"])) <= 1 and res.info == 0
+            print(f"slab solve {tag}: world={world} iterations={res.iterations} (reference {int(z['iterations'])}) rel_l2={rel:.2e} {'OK' if good else 'FAIL'}")
+            ok = ok and good
+        e.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
