@@ -96,9 +96,14 @@ int lsb200_support_kind(lsb200_handle h);
  * LC/supports/_3d_structured_grid.py:489-510).  Order: LSB200_W_*. */
 int lsb200_set_regularisation(lsb200_handle h, const double w[9]);
 
-/* P1: face gradient-jump regularisation, P1Interpolator.minimise_edge_jumps
- * (LI/_p1interpolator.py:115-166) with row weight w (cgw), applied matrix-free. */
+/* P1: face gradient-jump regularisation, P1Interpolator.minimise_edge_jumps (LI/_p1interpolator.py:115-166), with
+ * row weight w (cgw), applied matrix-free as a variable-coefficient node stencil (csrc/p1.cuh).  The stencil
+ * coefficients are the rows of R^T R assembled by the caller on a small mesh of m[a] cells per axis with the same
+ * step vector: m[a] = cells if cells <= 6, else 5 (odd cell count) or 6 (even).  table is
+ * [(m[2]+1)][(m[1]+1)][(m[0]+1)][125] row-major, tap (dz+2)*25 + (dy+2)*5 + (dx+2), for unit weight
+ * (loopstructural_b200/p1_tables.py builds it). */
 int lsb200_set_p1_regularisation(lsb200_handle h, double w);
+int lsb200_set_p1_tables(lsb200_handle h, const int64_t m[3], const double* table);
 
 /* ---- data rows --------------------------------------------------------- */
 

@@ -51,6 +51,7 @@ SIGNATURES = {
     "lsb200_support_kind": (C.c_int, [Handle]),
     "lsb200_set_regularisation": (C.c_int, [Handle, c_double_p]),
     "lsb200_set_p1_regularisation": (C.c_int, [Handle, C.c_double]),
+    "lsb200_set_p1_tables": (C.c_int, [Handle, c_int64_p, c_double_p]),
     "lsb200_add_rows": (C.c_int, [Handle, C.c_int64, C.c_int, c_double_p, c_int64_p, c_double_p, c_double_p, C.c_int]),
     "lsb200_add_point_rows": (C.c_int, [Handle, C.c_int, C.c_int64, c_double_p, C.c_int, C.c_double, c_int64_p]),
     "lsb200_add_pair_rows": (C.c_int, [Handle, C.c_int64, c_double_p, c_double_p, C.c_double, c_int64_p]),

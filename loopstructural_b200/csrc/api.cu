@@ -97,6 +97,8 @@ struct lsb200_ctx {
   GridDesc g{};
   double ew[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   double p1_w = 0.0;
+  double* p1_table = nullptr;  // rows of R^T R on the small mesh, see p1.cuh
+  int p1_m[3] = {0, 0, 0};
   double ridge = 1e-8;
   int add_ridge = 1, apply_scaling = 1, deterministic = 0;
   cudaStream_t stream = nullptr;
@@ -385,10 +387,15 @@ static void plan(lsb200_ctx* h) {
 // the regularisation part of the normal operator (writes every owned entry of q, sets pq_part[0])
 static int launch_regularisation(lsb200_ctx* h, const double* p, double* q, int cg_mode) {
   if (h->kind == LSB200_SUPPORT_GRID) return launch_stencil(h, p, q, cg_mode);
-  return p1_launch_face_normal(h->g, h->p1_w, h->add_ridge ? h->ridge * h->ridge : 0.0, p, q, h->partials,
-                               h->counters + 0, h->sc, cg_mode, h->sm_count, h->stream, &h->launches)
-             ? fail(LSB200_ERR_CUDA, "p1 face kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()))
-             : 0;
+  if (!h->p1_table) return fail(LSB200_ERR_STATE, "tet-mesh handle without regularisation tables (lsb200_set_p1_tables)");
+  const P1Tables tb{{h->p1_m[0], h->p1_m[1], h->p1_m[2]}, h->p1_table};
+  const long long n = (long long)h->g.nx * h->g.ny * h->g.nz;
+  const int nb = (int)std::min<long long>((n + VEC_NT - 1) / VEC_NT, (long long)h->sm_count * 16);
+  k_p1_normal<VEC_NT><<<nb, VEC_NT, 0, h->stream>>>(h->g, tb, h->p1_w * h->p1_w, h->add_ridge ? h->ridge * h->ridge : 0.0, p, q,
+                                                     h->partials, h->counters + 0, h->sc, cg_mode);
+  CKL();
+  h->launches++;
+  return 0;
 }
 
 static int launch_rows(lsb200_ctx* h, const double* p, double* q, int cg_mode) {
@@ -565,6 +572,7 @@ int lsb200_destroy(lsb200_handle h) {
   cudaFree(h->partials);
   cudaFree(h->counters);
   cudaFree(h->status);
+  cudaFree(h->p1_table);
   if (h->comm) nccl::CommDestroy(h->comm);
   for (int t = 0; t < 3; ++t) {
     if (h->side[t]) cudaStreamDestroy(h->side[t]);
@@ -594,6 +602,26 @@ int lsb200_set_p1_regularisation(lsb200_handle h, double w) {
   if (!h) return fail(LSB200_ERR_ARG, "null argument");
   if (h->kind != LSB200_SUPPORT_TETMESH) return fail(LSB200_ERR_STATE, "face-jump regularisation needs a tet-mesh handle");
   h->p1_w = w;
+  h->finalized = false;
+  return 0;
+}
+
+int lsb200_set_p1_tables(lsb200_handle h, const int64_t m[3], const double* table) {
+  if (!h || !m || !table) return fail(LSB200_ERR_ARG, "null argument");
+  if (h->kind != LSB200_SUPPORT_TETMESH) return fail(LSB200_ERR_STATE, "regularisation tables need a tet-mesh handle");
+  const int nc[3] = {h->g.nx - 1, h->g.ny - 1, h->g.nz - 1};
+  for (int a = 0; a < 3; ++a) {
+    const bool ok = (nc[a] <= 6) ? (m[a] == nc[a]) : ((m[a] == 5 || m[a] == 6) && ((m[a] - nc[a]) % 2 == 0));
+    if (!ok) return fail(LSB200_ERR_ARG, "axis %d: a small mesh of %lld cells cannot represent %d cells", a, (long long)m[a], nc[a]);
+  }
+  CK(cudaSetDevice(h->device));
+  const size_t n = (size_t)(m[0] + 1) * (m[1] + 1) * (m[2] + 1) * 125;
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(h->p1_table);
+  h->p1_table = nullptr;
+  CK(cudaMalloc(&h->p1_table, sizeof(double) * n));
+  CK(cudaMemcpy(h->p1_table, table, sizeof(double) * n, cudaMemcpyHostToDevice));
+  for (int a = 0; a < 3; ++a) h->p1_m[a] = (int)m[a];
   h->finalized = false;
   return 0;
 }
@@ -820,8 +848,12 @@ int lsb200_finalize_system(lsb200_handle h) {
     CKL();
     h->launches++;
   } else {
-    if (p1_launch_face_diag(h->g, h->p1_w, h->add_ridge ? h->ridge * h->ridge : 0.0, h->diag, h->sm_count, h->stream, &h->launches))
-      return fail(LSB200_ERR_CUDA, "p1 diagonal kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (!h->p1_table) return fail(LSB200_ERR_STATE, "tet-mesh handle without regularisation tables (lsb200_set_p1_tables)");
+    const P1Tables tb{{h->p1_m[0], h->p1_m[1], h->p1_m[2]}, h->p1_table};
+    k_p1_diag<<<vec_blocks(h, h->g.nloc, 1), VEC_NT, 0, h->stream>>>(h->g, tb, h->p1_w * h->p1_w,
+                                                                      h->add_ridge ? h->ridge * h->ridge : 0.0, h->diag);
+    CKL();
+    h->launches++;
   }
   for (const RowBlock& rb : h->blocks) {
     if (rb.n == 0) continue;

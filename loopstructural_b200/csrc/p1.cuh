@@ -1,18 +1,308 @@
-// P1 / TetMesh kernels (K4, K5, K8) -- placeholder while the FDI path is brought up.
+// P1 / TetMesh twin of the path (K4, K5, K8): P1Interpolator on the structured tetrahedral mesh.
+//
+// Mesh (LC/supports/_3d_structured_tetra.py): every cell of the lattice is cut into 5 tets, with the mask
+// depending on the cell parity (i+j+k)%2 (:28-34); tet id = local + 5 (cx + ncx cy + ncx ncy cz) (:401-419).
+//
+// K5, regularisation (P1Interpolator.minimise_edge_jumps, LI/_p1interpolator.py:115-166): one row
+// n . (grad phi_T1 - grad phi_T2) = 0 per interior shared face, row-normalised over its 8 listed entries,
+// weight cgw.  The reference stores ~10 rows per cell (15.9 M rows at 8 M tets).  Here the normal operator
+// R^T R is applied matrix-free as a variable-coefficient node stencil: on this lattice the row of R^T R of a
+// node depends only on (a) the node parity and (b) how many cells (0, 1, >= 2) lie on either side of it on
+// each axis, and it reaches +-2 nodes.  The host assembles R^T R explicitly ONCE on a tiny mesh (<= 6 cells per
+// axis, same step vector, same cell-count parity) that contains every such class (p1_tables.py) and uploads
+// its rows as a table; k_p1_normal maps each node to its representative (p1_rep) and gathers 125 taps.
+// 16 B/node of algorithmic traffic (read p, write q) instead of 96 B/row + 16 B/node.
 #pragma once
 #include "common.cuh"
 #include "rows.cuh"
 
 namespace lsb {
 
-static inline int p1_launch_face_normal(const GridDesc&, double, double, const double*, double*, double*, unsigned int*,
-                                        CgScalars*, int, int, cudaStream_t, long long*) {
-  return 1;
+struct P1Tables {
+  int m[3];             // cells per axis of the small mesh the table was assembled on
+  const double* table;  // [(m2+1)][(m1+1)][(m0+1)][125], tap t = (dz+2)*25 + (dy+2)*5 + (dx+2)
+};
+
+// representative node of the small mesh for node i of an axis with nc cells (m cells in the small mesh):
+// same count (0, 1, >= 2) of cells on either side, same parity
+__device__ __forceinline__ int p1_rep(int i, int nc, int m) {
+  if (nc == m) return i;
+  if (i < 2) return i;
+  if (i > nc - 2) return m - (nc - i);
+  return 2 + ((i - 2) & 1);
 }
-static inline int p1_launch_face_diag(const GridDesc&, double, double, double*, int, cudaStream_t, long long*) { return 1; }
-__global__ void k_p1_point_rows(const GridDesc, const int, const long long, const double*, const int, const double, RowBlock,
-                                const long long, unsigned long long*) {}
-__global__ void k_eval_value_tet(const GridDesc, const double*, const long long, const double*, double*) {}
-__global__ void k_eval_gradient_tet(const GridDesc, const double*, const long long, const double*, double*) {}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+    k_p1_normal(const GridDesc g, const P1Tables tb, const double w2, const double ridge2, const double* __restrict__ p,
+                double* __restrict__ q, double* __restrict__ partials, unsigned int* __restrict__ counter,
+                CgScalars* __restrict__ sc, const int cg_mode) {
+  __shared__ double red[NT / 32];
+  if (cg_mode && sc->done) return;
+  const long long n = (long long)g.nx * g.ny * g.nz;
+  double dot = 0.0;
+  for (long long t = blockIdx.x * (long long)NT + threadIdx.x; t < n; t += (long long)gridDim.x * NT) {
+    const int i = (int)(t % g.nx);
+    const long long r = t / g.nx;
+    const int j = (int)(r % g.ny), k = (int)(r / g.ny);
+    const int rx = p1_rep(i, g.nx - 1, tb.m[0]), ry = p1_rep(j, g.ny - 1, tb.m[1]), rz = p1_rep(k, g.nz - 1, tb.m[2]);
+    const double* T = tb.table + ((long long)(rz * (tb.m[1] + 1) + ry) * (tb.m[0] + 1) + rx) * 125;
+    const long long base = (long long)(k + HALO) * g.plane + (long long)j * g.pitch + i;
+    double acc = 0.0;
+#pragma unroll 1
+    for (int dz = -2; dz <= 2; ++dz)
+#pragma unroll
+      for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+        for (int dx = -2; dx <= 2; ++dx) {
+          const double c = __ldg(T + (dz + 2) * 25 + (dy + 2) * 5 + (dx + 2));
+          // a non-zero coefficient implies that the neighbour exists (same cell pattern as the representative)
+          if (c != 0.0) acc = fma(c, p[base + dz * g.plane + dy * g.pitch + dx], acc);
+        }
+    const double p0 = p[base];
+    const double v = fma(w2, acc, ridge2 * p0);
+    q[base] = v;
+    dot = fma(p0, v, dot);
+  }
+  const double bsum = block_sum<NT>(dot, red);
+  double total;
+  if (grid_sum_last_block<NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total)) sc->pq_part[0] = total;
+}
+
+// diag(R^T R) w^2 + ridge^2 (for the column scaling, LI/_discrete_interpolator.py:815-833)
+__global__ void k_p1_diag(const GridDesc g, const P1Tables tb, const double w2, const double ridge2,
+                          double* __restrict__ diag) {
+  const long long n = (long long)g.nx * g.ny * g.nz;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(t % g.nx);
+    const long long r = t / g.nx;
+    const int j = (int)(r % g.ny), k = (int)(r / g.ny);
+    const int rx = p1_rep(i, g.nx - 1, tb.m[0]), ry = p1_rep(j, g.ny - 1, tb.m[1]), rz = p1_rep(k, g.nz - 1, tb.m[2]);
+    const double* T = tb.table + ((long long)(rz * (tb.m[1] + 1) + ry) * (tb.m[0] + 1) + rx) * 125;
+    diag[(long long)(k + HALO) * g.plane + (long long)j * g.pitch + i] += fma(w2, T[62], ridge2);
+  }
+}
+
+// ---- point location ------------------------------------------------------------------------------------
+__constant__ int c_tet_even[5][4] = {{7, 1, 2, 4}, {6, 2, 4, 7}, {5, 1, 4, 7}, {0, 1, 2, 4}, {3, 1, 2, 7}};
+__constant__ int c_tet_odd[5][4] = {{0, 6, 5, 3}, {7, 3, 5, 6}, {4, 0, 5, 6}, {2, 0, 3, 6}, {1, 0, 3, 5}};
+
+struct TetLoc {
+  bool inside;
+  int node[4];     // storage indices of the tet's nodes
+  double c[4];     // barycentric coordinates (shape functions)
+  double v[4][3];  // vertex positions
+};
+
+// unfused arithmetic in numpy's order, so that points on tet faces take the same side as in the reference
+__device__ __forceinline__ void cross_rn(const double a[3], const double b[3], double o[3]) {
+  o[0] = __dsub_rn(__dmul_rn(a[1], b[2]), __dmul_rn(a[2], b[1]));
+  o[1] = __dsub_rn(__dmul_rn(a[2], b[0]), __dmul_rn(a[0], b[2]));
+  o[2] = __dsub_rn(__dmul_rn(a[0], b[1]), __dmul_rn(a[1], b[0]));
+}
+__device__ __forceinline__ double dot_rn(const double a[3], const double b[3]) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(a[0], b[0]), __dmul_rn(a[1], b[1])), __dmul_rn(a[2], b[2]));
+}
+
+// TetMesh.get_element_for_location (LC/supports/_3d_structured_tetra.py:274-365): cell by floor + clip, the five
+// tets of the cell, barycentrics by scalar triple products, the LAST tet with all c >= 0 wins; strict inside
+// (:264-272) on top of the tolerant one of position_to_cell_index (LC/supports/_3d_base_structured.py:255-293).
+__device__ __forceinline__ TetLoc locate_tet(const GridDesc& g, const double x[3]) {
+  TetLoc L;
+  const int nc[3] = {g.nx - 1, g.ny - 1, g.nz - 1};
+  bool ins_tol = true, ins_strict = true;
+  int cell[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double maxi = __dadd_rn(g.origin[a], __dmul_rn((double)nc[a], g.step[a]));
+    const double ext = fmax(fabs(maxi - g.origin[a]), 1.0);
+    const double tol = __dmul_rn(__dmul_rn(2.220446049250313e-16, 32.0), ext);
+    ins_tol = ins_tol && (x[a] >= g.origin[a] - tol) && (x[a] <= maxi + tol);
+    // TetMesh.inside: origin + step_vector * nsteps_cells
+    ins_strict = ins_strict && (x[a] > g.origin[a]) && (x[a] < __dadd_rn(g.origin[a], __dmul_rn(g.step[a], (double)nc[a])));
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    int c = 0;
+    if (ins_tol) {
+      const double f = floor((x[a] - g.origin[a]) / g.step[a]);
+      c = (int)fmin(fmax(f, 0.0), (double)(nc[a] - 1));
+    }
+    cell[a] = c;
+  }
+  const bool even = ((cell[0] + cell[1] + cell[2]) & 1) == 0;
+  int best = -1;
+  L.inside = false;
+#pragma unroll 1
+  for (int t = 0; t < 5; ++t) {
+    double v[4][3];
+    int corner[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      corner[s] = even ? c_tet_even[t][s] : c_tet_odd[t][s];
+      const int off[3] = {corner[s] & 1, (corner[s] >> 1) & 1, (corner[s] >> 2) & 1};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) v[s][a] = __dadd_rn(g.origin[a], __dmul_rn(g.step[a], (double)(cell[a] + off[a])));
+    }
+    double vap[3], vbp[3], vab[3], vac[3], vad[3], vbc[3], vbd[3], cr[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      vap[a] = x[a] - v[0][a]; vbp[a] = x[a] - v[1][a];
+      vab[a] = v[1][a] - v[0][a]; vac[a] = v[2][a] - v[0][a]; vad[a] = v[3][a] - v[0][a];
+      vbc[a] = v[2][a] - v[1][a]; vbd[a] = v[3][a] - v[1][a];
+    }
+    cross_rn(vbd, vbc, cr); const double va = dot_rn(vbp, cr) / 6.0;
+    cross_rn(vac, vad, cr); const double vb = dot_rn(vap, cr) / 6.0;
+    const double vol = dot_rn(vab, cr) / 6.0;
+    cross_rn(vad, vab, cr); const double vc = dot_rn(vap, cr) / 6.0;
+    cross_rn(vab, vac, cr); const double vd = dot_rn(vap, cr) / 6.0;
+    const double c0 = va / vol, c1 = vb / vol, c2 = vc / vol, c3 = vd / vol;
+    if (c0 >= 0.0 && c1 >= 0.0 && c2 >= 0.0 && c3 >= 0.0) {  // later tets overwrite earlier ones
+      best = t;
+      L.c[0] = c0; L.c[1] = c1; L.c[2] = c2; L.c[3] = c3;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int off[3] = {corner[s] & 1, (corner[s] >> 1) & 1, (corner[s] >> 2) & 1};
+        L.node[s] = (int)((long long)(cell[2] + off[2] + HALO) * g.plane + (long long)(cell[1] + off[1]) * g.pitch + cell[0] + off[0]);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) L.v[s][a] = v[s][a];
+      }
+    }
+  }
+  L.inside = ins_tol && ins_strict && best >= 0;
+  return L;
+}
+
+// shape-function gradients G = E^-1 [[-1,1,0,0],[-1,0,1,0],[-1,0,0,1]], E rows = v1-v0, v2-v0, v3-v0
+// (TetMesh.get_element_gradients, LC/supports/_3d_structured_tetra.py:421-486); returns |det E| / 6 (element_size)
+__device__ __forceinline__ double tet_gradients(const double v[4][3], double G[3][4]) {
+  double E[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) E[r][a] = v[r + 1][a] - v[0][a];
+  const double det = E[0][0] * (E[1][1] * E[2][2] - E[1][2] * E[2][1]) - E[0][1] * (E[1][0] * E[2][2] - E[1][2] * E[2][0]) +
+                     E[0][2] * (E[1][0] * E[2][1] - E[1][1] * E[2][0]);
+  const double id = 1.0 / det;
+  double inv[3][3];  // inverse of E
+  inv[0][0] = (E[1][1] * E[2][2] - E[1][2] * E[2][1]) * id;
+  inv[0][1] = (E[0][2] * E[2][1] - E[0][1] * E[2][2]) * id;
+  inv[0][2] = (E[0][1] * E[1][2] - E[0][2] * E[1][1]) * id;
+  inv[1][0] = (E[1][2] * E[2][0] - E[1][0] * E[2][2]) * id;
+  inv[1][1] = (E[0][0] * E[2][2] - E[0][2] * E[2][0]) * id;
+  inv[1][2] = (E[0][2] * E[1][0] - E[0][0] * E[1][2]) * id;
+  inv[2][0] = (E[1][0] * E[2][1] - E[1][1] * E[2][0]) * id;
+  inv[2][1] = (E[0][1] * E[2][0] - E[0][0] * E[2][1]) * id;
+  inv[2][2] = (E[0][0] * E[1][1] - E[0][1] * E[1][0]) * id;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    G[d][0] = -(inv[d][0] + inv[d][1] + inv[d][2]);
+    G[d][1] = inv[d][0];
+    G[d][2] = inv[d][1];
+    G[d][3] = inv[d][2];
+  }
+  return fabs(det) / 6.0;
+}
+
+// K4: P1 rows from constraint points (LI/_p1interpolator.py:73-113,248-296).  value: the 4 barycentrics, b = value,
+// w = cpw (the per-point weight column is not used); normal: three rows grad phi[d,:] with b = n_d, w = npw;
+// tangent / orthogonal: v_hat . grad phi = b, w = tpw * tet volume.  Rows are L2-normalised; mult rows per point at
+// row0 + 3*point + d for normals (the reference flattens the (n,3,4) block point-major), else row0 + point.
+__global__ void k_p1_point_rows(const GridDesc g, const int kind, const long long n, const double* __restrict__ data,
+                                const int ncols, const double weight, RowBlock rb, const long long row0,
+                                unsigned long long* __restrict__ status) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    const double* d = data + r * ncols;
+    const double x[3] = {d[0], d[1], d[2]};
+    const TetLoc L = locate_tet(g, x);
+    bool ok = L.inside;
+    const int used = kind == LSB200_ROWS_VALUE ? 4 : (kind == LSB200_ROWS_TANGENT ? 7 : 6);
+    for (int c = 0; c < used; ++c) ok = ok && (d[c] == d[c]);
+    const int mult = kind == LSB200_ROWS_NORMAL ? 3 : 1;
+    double A[3][4], bb[3] = {0.0, 0.0, 0.0};
+    double ww = weight;
+    if (ok) {
+      if (kind == LSB200_ROWS_VALUE) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) A[0][c] = L.c[c];
+        bb[0] = d[3];
+      } else {
+        double G[3][4];
+        const double vol = tet_gradients(L.v, G);
+        if (kind == LSB200_ROWS_NORMAL) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) A[a][c] = G[a][c];
+            bb[a] = d[3 + a];
+          }
+        } else {
+          const double len = sqrt(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
+          double vv[3] = {d[3], d[4], d[5]};
+          if (len > 0.0) { vv[0] /= len; vv[1] /= len; vv[2] /= len; }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) A[0][c] = vv[0] * G[0][c] + vv[1] * G[1][c] + vv[2] * G[2][c];
+          bb[0] = d[6];
+          ww = weight * vol;
+        }
+      }
+      atomicAdd(status, (unsigned long long)mult);
+    }
+    for (int m = 0; m < mult; ++m) {
+      const long long ro = row0 + (long long)mult * r + m;
+      double nrm2 = 0.0;
+      if (ok)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) nrm2 += A[m][c] * A[m][c];
+      const double len = sqrt(nrm2);
+      const bool good = ok && (len == len);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        rb.vals[c * rb.n + ro] = good ? (len > 0.0 ? A[m][c] / len : A[m][c]) : 0.0;
+        rb.cols[c * rb.n + ro] = good ? L.node[c] : -1;
+      }
+      rb.b[ro] = good ? (len > 0.0 ? bb[m] / len : bb[m]) : 0.0;
+      rb.w2[ro] = good ? ww * ww : 0.0;
+    }
+  }
+}
+
+// K8: TetMesh.evaluate_value (LC/supports/_3d_structured_tetra.py:208-229) behind _evaluate_value_local
+// (LI/_discrete_interpolator.py:1342-1362): NaN outside, 0.0 for rows holding a NaN coordinate.
+__global__ void k_eval_value_tet(const GridDesc g, const double* __restrict__ c, const long long n,
+                                 const double* __restrict__ xyz, double* __restrict__ out) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    const double x[3] = {xyz[3 * r], xyz[3 * r + 1], xyz[3 * r + 2]};
+    double v;
+    if (x[0] != x[0] || x[1] != x[1] || x[2] != x[2]) {
+      v = 0.0;
+    } else {
+      const TetLoc L = locate_tet(g, x);
+      if (!L.inside) v = nan("");
+      else v = L.c[0] * c[L.node[0]] + L.c[1] * c[L.node[1]] + L.c[2] * c[L.node[2]] + L.c[3] * c[L.node[3]];
+    }
+    out[r] = v;
+  }
+}
+
+// TetMesh.evaluate_gradient (:231-262): NaN outside
+__global__ void k_eval_gradient_tet(const GridDesc g, const double* __restrict__ c, const long long n,
+                                    const double* __restrict__ xyz, double* __restrict__ out) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    const double x[3] = {xyz[3 * r], xyz[3 * r + 1], xyz[3 * r + 2]};
+    const TetLoc L = locate_tet(g, x);
+    double gr[3] = {nan(""), nan(""), nan("")};
+    if (L.inside) {
+      double G[3][4];
+      tet_gradients(L.v, G);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        gr[a] = G[a][0] * c[L.node[0]] + G[a][1] * c[L.node[1]] + G[a][2] * c[L.node[2]] + G[a][3] * c[L.node[3]];
+    }
+    out[3 * r] = gr[0];
+    out[3 * r + 1] = gr[1];
+    out[3 * r + 2] = gr[2];
+  }
+}
 
 }  // namespace lsb

@@ -120,6 +120,15 @@ class Engine:
         nat.check(self._lib.lsb200_set_regularisation(self._h, nat.dptr(ew)))
 
     def set_p1_regularisation(self, w: float):
+        """Face gradient-jump regularisation of weight ``w`` (cgw).  The first call assembles the stencil table of
+        this support on a mesh of at most 6 cells per axis (p1_tables.py) and uploads it."""
+        if not getattr(self, "_p1_tables_set", False):
+            from . import p1_tables
+
+            m, table = p1_tables.regularisation_table(self.nsteps - 1, self.step)
+            m = np.ascontiguousarray(m, dtype=np.int64)
+            nat.check(self._lib.lsb200_set_p1_tables(self._h, nat.iptr(m), nat.dptr(table)))
+            self._p1_tables_set = True
         nat.check(self._lib.lsb200_set_p1_regularisation(self._h, float(w)))
 
     def set_options(self, ridge_factor: float = 1e-8, add_ridge: bool = True, apply_scaling: bool = True,

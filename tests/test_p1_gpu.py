@@ -1,0 +1,177 @@
+"""Parity of the CUDA P1 / TetMesh path (through the C-ABI) with the reference's golden outputs and the oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import fdi_oracle as fo
+from oracle import p1_oracle as po
+import golden_helpers as H
+
+pytestmark = pytest.mark.gpu
+GOLDEN = H.GOLDEN
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    from loopstructural_b200 import build
+
+    build.build()
+
+
+def _engine(grid, cgw=0.0, **opts):
+    from loopstructural_b200 import Engine
+
+    e = Engine(grid.nsteps, grid.origin, grid.step, kind="tetmesh")
+    e.set_p1_regularisation(cgw)
+    if opts:
+        e.set_options(**opts)
+    return e
+
+
+# ---------------------------------------------------------------- K5: face-jump regularisation operator
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "p1_operator_*.npz"))))
+def test_face_jump_operator_matches_reference_gram(path):
+    z = np.load(path)
+    grid = fo.Grid.from_cells(z["ncells"], np.zeros(3), z["step"])
+    e = _engine(grid, float(z["cgw"]), add_ridge=False)
+    scale = np.abs(z["y"]).max()
+    for x, y in zip(z["x"], z["y"]):
+        assert np.abs(e.apply_normal(x, parts=1) - y).max() <= 1e-12 * scale
+    assert np.abs(e.diagonal() - z["diag"]).max() <= 1e-12 * np.abs(z["diag"]).max()
+    e.set_options(ridge_factor=0.5)
+    q = e.apply_normal(z["x"][0], parts=1 | 4)
+    assert np.abs(q - (z["y"][0] + 0.25 * z["x"][0])).max() <= 1e-12 * scale
+    e.close()
+
+
+@pytest.mark.parametrize("ncells,step", [((9, 8, 7), (0.5, 1.25, 2.0)), ((12, 7, 10), (1.0, 1.0, 1.0)), ((7, 7, 8), (1, 1, 1)),
+                                         ((31, 22, 17), (0.1, 0.3, 0.2)), ((2, 9, 1), (1, 1, 1))])
+def test_face_jump_operator_matches_oracle_on_larger_meshes(ncells, step):
+    """Meshes larger than the 6-cell table mesh: the class lookup (p1_rep) against the oracle's explicit rows."""
+    grid = fo.Grid.from_cells(ncells, np.zeros(3), step)
+    fam = po.face_rows(grid, 0.3)
+    m = fam.matrix(grid.n_nodes)
+    e = _engine(grid, 0.3, add_ridge=False)
+    p = np.random.default_rng(sum(ncells)).standard_normal(grid.n_nodes)
+    ref = m.T @ (fam.w * fam.w * (m @ p))
+    assert np.abs(e.apply_normal(p, parts=1) - ref).max() <= 1e-12 * np.abs(ref).max()
+    assert np.abs(e.diagonal() - np.asarray(m.multiply(m).T @ (fam.w * fam.w)).ravel()).max() <= 1e-12 * np.abs(ref).max() + 1e-13
+    e.close()
+
+
+def test_face_jump_operator_full_size_properties():
+    """BASELINE config 3 size (117^3 cells = 8,008,065 tets, 1,643,032 nodes): constants and affine fields have
+    no gradient jumps, the operator is symmetric."""
+    grid = fo.Grid.from_cells([117, 117, 117], np.zeros(3), np.ones(3) / 117)
+    e = _engine(grid, 0.1, add_ridge=False)
+    n = grid.nsteps
+    i, j, k = np.meshgrid(np.arange(n[0]), np.arange(n[1]), np.arange(n[2]), indexing="ij")
+    lin = (0.3 * i - 1.7 * j + 0.9 * k + 4.0).ravel(order="F")
+    q = e.apply_normal(lin, parts=1)
+    assert np.abs(q).max() <= 1e-9 * np.abs(lin).max()
+    rng = np.random.default_rng(0)
+    a, b = rng.standard_normal(grid.n_nodes), rng.standard_normal(grid.n_nodes)
+    qa, qb = e.apply_normal(a, parts=1), e.apply_normal(b, parts=1)
+    assert abs(np.dot(b, qa) - np.dot(a, qb)) <= 1e-10 * abs(np.dot(b, qa))
+    assert np.dot(a, qa) > 0
+    e.close()
+
+
+# ---------------------------------------------------------------- K4: rows from points
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_point_rows_match_reference(tag):
+    from loopstructural_b200 import engine as en
+
+    z = np.load(os.path.join(GOLDEN, f"p1_rows_{tag}.npz"))
+    grid = fo.Grid.from_cells(z["ncells"], z["origin"], z["step"])
+    kw = H.weights_of(z, "kw_keys", "kw_vals")
+    dof = grid.n_nodes
+    p = np.random.default_rng(3).standard_normal(dof)
+    tang = np.column_stack([z["tangent"][:, :6], np.zeros(len(z["tangent"]))])
+    kinds = {"value": (en.ROWS_VALUE, z["value"], kw["cpw"]), "norm": (en.ROWS_NORMAL, z["normal"], kw["npw"]),
+             "undefined gradient orthogonal constraint": (en.ROWS_TANGENT, tang, kw["tpw"])}
+    for name, (kind, data, weight) in kinds.items():
+        e = _engine(grid, 0.0, add_ridge=False, apply_scaling=False)
+        nrows = e.add_point_rows(kind, data, weight)
+        m, b, w = H.ref_family(z, name)
+        assert nrows == m.shape[0], name
+        q_ref = m.T @ (w * w * (m @ p))
+        rhs_ref = m.T @ (w * w * b)
+        assert np.abs(e.apply_normal(p, parts=2) - q_ref).max() <= 1e-11 * np.abs(q_ref).max(), name
+        assert np.abs(e.rhs() - rhs_ref).max() <= 1e-11 * max(np.abs(rhs_ref).max(), 1.0), name
+        e.close()
+    # P1 ignores gradient constraints (LI/_p1interpolator.py:70-71)
+    e = _engine(grid, 0.0)
+    assert e.add_point_rows(en.ROWS_GRADIENT, z["normal"], 1.0) == 0
+    e.close()
+
+
+# ---------------------------------------------------------------- solve + K8: evaluation
+@pytest.mark.parametrize("tag", ["unit12", "aniso", "unit16_tight"])
+def test_solve_and_evaluation_match_reference(tag):
+    from loopstructural_b200.interpolators import B200P1Interpolator, Support
+
+    z = np.load(os.path.join(GOLDEN, f"p1_solve_{tag}.npz"))
+    grid = fo.Grid.from_cells(z["ncells"], z["origin"], z["step"])
+    it = B200P1Interpolator(Support(grid.origin, grid.nsteps - 1, grid.step))
+    it.apply_scaling_matrix = bool(z["scaling"])
+    for key in ("value", "normal", "tangent"):
+        if f"data_{key}" in z:
+            getattr(it, f"set_{key}_constraints")(z[f"data_{key}"])
+    it.setup_interpolator(**H.weights_of(z, "kw_keys", "kw_vals"))
+    rtol = 1e-5 if float(z["rtol"]) < 0 else float(z["rtol"])
+    atol = 0.0 if float(z["tol"]) < 0 else float(z["tol"])
+    assert it.solve_system("b200", solver_kwargs={"rtol": rtol, "atol": atol}) is True
+    t = it.get_last_solve_timing()
+    # same stopping rule => same iteration count, up to rounding in a 671-iteration run to rtol 1e-10 (1 %)
+    assert t["info"] == 0 and abs(t["iterations"] - int(z["iterations"])) <= max(1, int(z["iterations"]) // 100)
+    rng_ = float(z["c"].max() - z["c"].min())
+    # BASELINE bar: rel-L2 <= 1e-6 of the range, met whenever the tolerance is tight enough for the answer to be
+    # defined that sharply (aniso: 9e-16, unit16_tight: 5e-11).  unit12 runs at the DEFAULT rtol 1e-5 on an
+    # ill-conditioned system: the reference's residual at its last iteration is 0.98 of the threshold, CG
+    # trajectories that differ only by rounding (fp64 atomics, table vs explicit Gram) stop at 80 or 81
+    # iterations and land up to one CG step (2.7e-5 of the range, the reference's own distance from the converged
+    # field) apart.  There the bar is that one step, and the same system is solved again to rtol 1e-10 against
+    # the oracle's equally tight solve at the 1e-6 bar.
+    default_tol = float(z["rtol"]) < 0 and float(z["tol"]) < 0
+    rel = np.linalg.norm(it.c - z["c"]) / np.sqrt(it.c.size) / rng_
+    assert rel <= (5e-5 if default_tol else 1e-6), rel
+    if default_tol:
+        fams = [po.face_rows(grid, it.interpolation_weights["cgw"]), po.normal_rows(grid, z["data_normal"], it.interpolation_weights["npw"]),
+                po.value_rows(grid, z["data_value"], it.interpolation_weights["cpw"])]
+        c_ref, res_ref, _ = fo.solve_reference_path(fams, grid.n_nodes, rtol=1e-10, apply_scaling=bool(z["scaling"]))
+        assert it.solve_system("b200", solver_kwargs={"rtol": 1e-10, "atol": 0.0}) is True
+        assert abs(it.get_last_solve_timing()["iterations"] - res_ref.iterations) <= max(1, res_ref.iterations // 100)
+        assert np.linalg.norm(it.c - c_ref) / np.sqrt(it.c.size) / rng_ <= 1e-6
+    # evaluation of the REFERENCE's coefficients: value (NaN outside, 0 for NaN rows), gradient (NaN outside),
+    # incl. points on tet faces where the "last matching tet" tie-break decides the gradient
+    it.set_c(z["c"])
+    q = z["query"]
+    v = it.evaluate_value(q)
+    np.testing.assert_array_equal(np.isnan(v), np.isnan(z["value_at"]))
+    np.testing.assert_allclose(v, z["value_at"], rtol=0, atol=1e-12, equal_nan=True)
+    assert v[6] == 0.0
+    fin = np.all(np.isfinite(q), axis=1)
+    g = it.evaluate_gradient(q[fin])
+    np.testing.assert_array_equal(np.isnan(g), np.isnan(z["gradient_at"]))
+    np.testing.assert_allclose(g, z["gradient_at"], rtol=0, atol=1e-9, equal_nan=True)
+    it.close()
+
+
+def test_evaluate_large_cloud_against_oracle():
+    rng = np.random.default_rng(12)
+    grid = fo.Grid.from_cells([23, 19, 31], [1.0, -2.0, 0.5], [0.3, 0.2, 0.45])
+    c = rng.standard_normal(grid.n_nodes)
+    e = _engine(grid, 0.1)
+    e.set_c(c)
+    lo, hi = grid.origin, grid.maximum
+    pts = lo + rng.uniform(-0.02, 1.02, (200_000, 3)) * (hi - lo)
+    v, vo = e.evaluate_value(pts), po.evaluate_value(grid, pts, c)
+    np.testing.assert_array_equal(np.isnan(v), np.isnan(vo))
+    np.testing.assert_allclose(v, vo, rtol=0, atol=1e-12, equal_nan=True)
+    g, go = e.evaluate_gradient(pts), po.evaluate_gradient(grid, pts, c)
+    np.testing.assert_array_equal(np.isnan(g), np.isnan(go))
+    np.testing.assert_allclose(g, go, rtol=0, atol=1e-9, equal_nan=True)
+    e.close()
