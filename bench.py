@@ -182,8 +182,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     build.build()
     n = args.n
-    nz = n * world
-    zscale = float(world)
+    nz = (args.nz_per_gpu or n) * world
+    zscale = float(nz) / float(n)
     nsteps = np.array([n, n, nz])
     step = np.array([1.0 / (n - 1), 1.0 / (n - 1), zscale / (nz - 1)])
     bounds = partition.slab_bounds(nz, world)
@@ -341,6 +341,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=256, help="nodes per axis per GPU")
+    ap.add_argument("--nz-per-gpu", type=int, default=0, help="z planes per GPU (default: --n); e.g. --n 1024 --nz-per-gpu 128 "
+                                                              "on 8 GPUs is the 1024^3 grid of BASELINE configs[4]")
     ap.add_argument("--n-value", type=int, default=100_000)
     ap.add_argument("--n-gradient", type=int, default=10_000)
     ap.add_argument("--ref-n", type=int, default=64, help="nodes per axis of the bounded CPU sample")

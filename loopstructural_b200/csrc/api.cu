@@ -97,7 +97,9 @@ struct lsb200_ctx {
   GridDesc g{};
   double ew[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   double p1_w = 0.0;
-  double* p1_table = nullptr;  // rows of R^T R on the small mesh, see p1.cuh
+  double* p1_table = nullptr;  // compacted rows of R^T R on the small mesh, see p1.cuh: coefficients,
+  int* p1_off = nullptr;       //   tap offsets
+  double* p1_diag = nullptr;   //   and centre taps
   int p1_m[3] = {0, 0, 0};
   double ridge = 1e-8;
   int add_ridge = 1, apply_scaling = 1, deterministic = 0;
@@ -121,8 +123,9 @@ struct lsb200_ctx {
   // main (register-tiled) kernel + y-shell launch of k_fdi_normal; main_cfg < 0: k_fdi_normal everywhere
   int main_cfg = -1;
   bool main_uni = false;
-  int main_cz = 0;
+  int main_cz = 0, shell_cz = 0;  // shell_cz = 0: chosen per launch
   int box_z0 = 0, box_z1 = 0;
+  double* ztab = nullptr;  // per-plane z coefficients of k_fdi_shell (nz * SHELL_ZSTRIDE)
   dim3 main_grid;
   // the shell launches run on side streams, overlapped with the box kernel (fork/join by events)
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
@@ -249,6 +252,13 @@ static void plan_main(lsb200_ctx* h) {
   h->main_cz = czo ? czo : pick_cz(h, nzm, (long long)tiles_x * tiles_y, (long long)h->sm_count * minb);
   h->main_grid = dim3(tiles_x, tiles_y, chunks(nzm, h->main_cz));
   if ((long long)h->main_grid.x * h->main_grid.y * h->main_grid.z > MAX_PARTIALS) return;
+  { const char* e = getenv("LSB200_SHELL_CZ"); h->shell_cz = (e && atoi(e) > 0) ? atoi(e) : 0; }
+  if (!h->ztab) {
+    std::vector<double> zt((size_t)g.nz * SHELL_ZSTRIDE);
+    shell_fill_z_table(g.nz, zt.data());
+    if (cudaMalloc(&h->ztab, sizeof(double) * zt.size()) != cudaSuccess) return;
+    if (cudaMemcpy(h->ztab, zt.data(), sizeof(double) * zt.size(), cudaMemcpyHostToDevice) != cudaSuccess) return;
+  }
   h->main_cfg = cfg;
 }
 
@@ -330,14 +340,22 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
       sb.jlo = 3; sb.jhi = g.ny - 3;
       sb.klo = h->box_z0; sb.khi = std::max(h->box_z0, h->box_z1);
       const int nzm = sb.khi - sb.klo;
-      sb.n_full_planes = g.nzl - nzm;
-      sb.full_blocks = (g.nx * g.ny + 255) / 256;
-      sb.yrow_blocks = ((g.ny - (sb.jhi - sb.jlo)) * g.nx + 255) / 256;
-      sb.xcol_blocks = ((sb.jhi - sb.jlo) * (g.nx - (sb.ihi - sb.ilo)) + 255) / 256;
-      const long long nb = (long long)sb.n_full_planes * sb.full_blocks + (long long)nzm * (sb.yrow_blocks + sb.xcol_blocks);
+      constexpr int SNT = 128;
+      sb.ring_cols = (g.ny - (sb.jhi - sb.jlo)) * g.nx + (sb.jhi - sb.jlo) * (g.nx - (sb.ihi - sb.ilo));
+      sb.ring_blocks = (sb.ring_cols + SNT - 1) / SNT;
+      // z chunks of the ring: about 50 k marching threads in flight (measured: 16 planes at 256^3, 64 at 512^3, profiles/r01r)
+      int chunks = h->shell_cz > 0 ? (nzm + h->shell_cz - 1) / h->shell_cz : (int)(50000 / std::max(sb.ring_cols, 1));
+      chunks = std::max(1, std::min(chunks, std::max(1, nzm / 8)));
+      sb.ring_cz = nzm > 0 ? (nzm + chunks - 1) / chunks : 1;
+      sb.ring_chunks = nzm > 0 ? (nzm + sb.ring_cz - 1) / sb.ring_cz : 0;
+      sb.capA0 = g.k0; sb.capA1 = sb.klo;
+      sb.capB0 = sb.khi; sb.capB1 = g.k1;
+      sb.cap_blocks = (sb.capA1 > sb.capA0 || sb.capB1 > sb.capB0) ? (g.nx * g.ny + SNT - 1) / SNT : 0;
+      const long long nb = (long long)sb.ring_blocks * sb.ring_chunks + 2LL * sb.cap_blocks;
       if (nb > MAX_PARTIALS) return fail(LSB200_ERR_ARG, "shell launch needs %lld CTAs (limit %d)", nb, MAX_PARTIALS);
       if (nb > 0)
-        k_fdi_shell<256><<<(int)nb, 256, 0, ov ? h->side[0] : h->stream>>>(g, w, sb, p, q, h->partials + 3 * (size_t)MAX_PARTIALS,
+        k_fdi_shell<SNT><<<(int)nb, SNT, 0, ov ? h->side[0] : h->stream>>>(g, w, sb, h->ztab, p, q,
+                                                                          h->partials + 3 * (size_t)MAX_PARTIALS,
                                                                           h->counters + 3, h->sc, cg_mode);
       CKL();
       h->launches++;
@@ -388,7 +406,7 @@ static void plan(lsb200_ctx* h) {
 static int launch_regularisation(lsb200_ctx* h, const double* p, double* q, int cg_mode) {
   if (h->kind == LSB200_SUPPORT_GRID) return launch_stencil(h, p, q, cg_mode);
   if (!h->p1_table) return fail(LSB200_ERR_STATE, "tet-mesh handle without regularisation tables (lsb200_set_p1_tables)");
-  const P1Tables tb{{h->p1_m[0], h->p1_m[1], h->p1_m[2]}, h->p1_table};
+  const P1Tables tb{{h->p1_m[0], h->p1_m[1], h->p1_m[2]}, h->p1_table, h->p1_off, h->p1_diag};
   const long long n = (long long)h->g.nx * h->g.ny * h->g.nz;
   const int nb = (int)std::min<long long>((n + VEC_NT - 1) / VEC_NT, (long long)h->sm_count * 16);
   k_p1_normal<VEC_NT><<<nb, VEC_NT, 0, h->stream>>>(h->g, tb, h->p1_w * h->p1_w, h->add_ridge ? h->ridge * h->ridge : 0.0, p, q,
@@ -573,6 +591,9 @@ int lsb200_destroy(lsb200_handle h) {
   cudaFree(h->counters);
   cudaFree(h->status);
   cudaFree(h->p1_table);
+  cudaFree(h->p1_off);
+  cudaFree(h->p1_diag);
+  cudaFree(h->ztab);
   if (h->comm) nccl::CommDestroy(h->comm);
   for (int t = 0; t < 3; ++t) {
     if (h->side[t]) cudaStreamDestroy(h->side[t]);
@@ -615,12 +636,33 @@ int lsb200_set_p1_tables(lsb200_handle h, const int64_t m[3], const double* tabl
     if (!ok) return fail(LSB200_ERR_ARG, "axis %d: a small mesh of %lld cells cannot represent %d cells", a, (long long)m[a], nc[a]);
   }
   CK(cudaSetDevice(h->device));
-  const size_t n = (size_t)(m[0] + 1) * (m[1] + 1) * (m[2] + 1) * 125;
+  // compact the 125-tap rows into fixed-width (coefficient, storage offset) lists
+  const size_t rows = (size_t)(m[0] + 1) * (m[1] + 1) * (m[2] + 1);
+  std::vector<double> coef(rows * P1_TAPS, 0.0), diag(rows, 0.0);
+  std::vector<int> off(rows * P1_TAPS, 0);
+  for (size_t r = 0; r < rows; ++r) {
+    int cnt = 0;
+    for (int t = 0; t < 125; ++t) {
+      const double c = table[r * 125 + t];
+      if (!(c == c)) return fail(LSB200_ERR_ARG, "NaN in the regularisation table");
+      if (t == 62) diag[r] = c;
+      if (c == 0.0) continue;
+      if (cnt == P1_TAPS) return fail(LSB200_ERR_ARG, "table row %zu has more than %d non-zero taps", r, P1_TAPS);
+      const int dz = t / 25 - 2, dy = (t / 5) % 5 - 2, dx = t % 5 - 2;
+      coef[r * P1_TAPS + cnt] = c;
+      off[r * P1_TAPS + cnt] = (int)(dz * h->g.plane + dy * h->g.pitch + dx);
+      ++cnt;
+    }
+  }
   CK(cudaStreamSynchronize(h->stream));
-  cudaFree(h->p1_table);
-  h->p1_table = nullptr;
-  CK(cudaMalloc(&h->p1_table, sizeof(double) * n));
-  CK(cudaMemcpy(h->p1_table, table, sizeof(double) * n, cudaMemcpyHostToDevice));
+  cudaFree(h->p1_table); cudaFree(h->p1_off); cudaFree(h->p1_diag);
+  h->p1_table = nullptr; h->p1_off = nullptr; h->p1_diag = nullptr;
+  CK(cudaMalloc(&h->p1_table, sizeof(double) * coef.size()));
+  CK(cudaMalloc(&h->p1_off, sizeof(int) * off.size()));
+  CK(cudaMalloc(&h->p1_diag, sizeof(double) * diag.size()));
+  CK(cudaMemcpy(h->p1_table, coef.data(), sizeof(double) * coef.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->p1_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->p1_diag, diag.data(), sizeof(double) * diag.size(), cudaMemcpyHostToDevice));
   for (int a = 0; a < 3; ++a) h->p1_m[a] = (int)m[a];
   h->finalized = false;
   return 0;
@@ -849,7 +891,7 @@ int lsb200_finalize_system(lsb200_handle h) {
     h->launches++;
   } else {
     if (!h->p1_table) return fail(LSB200_ERR_STATE, "tet-mesh handle without regularisation tables (lsb200_set_p1_tables)");
-    const P1Tables tb{{h->p1_m[0], h->p1_m[1], h->p1_m[2]}, h->p1_table};
+    const P1Tables tb{{h->p1_m[0], h->p1_m[1], h->p1_m[2]}, h->p1_table, h->p1_off, h->p1_diag};
     k_p1_diag<<<vec_blocks(h, h->g.nloc, 1), VEC_NT, 0, h->stream>>>(h->g, tb, h->p1_w * h->p1_w,
                                                                       h->add_ridge ? h->ridge * h->ridge : 0.0, h->diag);
     CKL();

@@ -252,138 +252,191 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
 namespace lsb {
 
 // ---------------------------------------------------------------------------------------------
-// k_fdi_shell: every owned node OUTSIDE the interior box, one thread per node, gather form.
+// k_fdi_shell: every owned node OUTSIDE the interior box, in gather form with the true boundary operators
 //   q = ridge^2 p + sum_a (a_aa m_b m_c T_a + d_a B_a) p + sum_{a<b} b_ab m_c (C_a (x) C_b) p
-// with the true 1-D boundary operators (no ghost cells): T = D^T diag(m) D / 6, C = G^T diag(m) G,
-// B = sum_{r in {1,n-2}} d_r d_r^T / 6, m(r) = [1 <= r <= n-2] -- the row masks of
-// StructuredGrid.neighbour_global_indexes / FDI.assemble_borders (LC/supports/_3d_structured_grid.py:164-293,
-// LI/_finite_difference_interpolator.py:1052-1144) after row normalisation (LI/_discrete_interpolator.py:361-366).
-// 25 loads per node, all hitting L1/L2 beside the box kernel that streams the same planes.
+// (no ghost cells): T = D^T diag(m) D / 6, C = G^T diag(m) G, B = sum_{r in {1,n-2}} d_r d_r^T / 6,
+// m(r) = [1 <= r <= n-2] -- the row masks of StructuredGrid.neighbour_global_indexes / FDI.assemble_borders
+// (LC/supports/_3d_structured_grid.py:164-293, LI/_finite_difference_interpolator.py:1052-1144) after row
+// normalisation (LI/_discrete_interpolator.py:361-366).
+//
+// A thread owns one xy column and marches along z: its x and y coefficient sets are computed once, the z sets
+// come from a per-plane table (ShellZ), and of the 25 taps of an output plane only the 13 in-plane ones are
+// loaded -- the z neighbours are the per-plane scalars (p, C_x p, C_y p) kept in a five-deep register history.
+// ~100 instructions per node instead of the ~450 of the one-thread-per-node form it replaced (profiles/r01m).
+// Work items: the ring columns (outside [ilo,ihi) x [jlo,jhi)) over z chunks of the inner planes [klo,khi), and
+// every column over the planes next to the z faces.
 struct ShellBox {
   int ilo, ihi, jlo, jhi, klo, khi;  // the box that is NOT computed here (klo/khi clipped to the owned planes)
-  int n_full_planes;                 // owned planes outside [klo,khi): every node
-  int full_blocks;                   // CTAs per such plane: ceil(nx*ny / NT)
-  int yrow_blocks;                   // per plane inside [klo,khi): CTAs of the rows outside [jlo,jhi), every column
-  int xcol_blocks;                   //   and of the columns outside [ilo,ihi) of the rows [jlo,jhi)
+  int ring_cols;                     // columns outside [ilo,ihi) x [jlo,jhi)
+  int ring_blocks;                   // CTAs per z chunk of the ring: ceil(ring_cols / NT)
+  int ring_cz, ring_chunks;          // z chunking of [klo,khi)
+  int cap_blocks;                    // CTAs per cap: ceil(nx*ny / NT)
+  int capA0, capA1, capB0, capB1;    // owned planes below klo / from khi up (either may be empty)
 };
+
+// per-plane z coefficients, 16 doubles per GLOBAL plane k: [0..4] T_z taps -2..2 (1/6 included), [5..9] B_z taps
+// (1/6 included), [10..12] C_z taps -2,0,+2, [13] m_z(k)
+constexpr int SHELL_ZSTRIDE = 16;
 
 __device__ __forceinline__ double vrow(int r, int n) { return (r >= 1 && r <= n - 2) ? 1.0 : 0.0; }
-// 1-D data of one axis of a shell node: clamped tap offsets (a clamped tap always has coefficient 0), the
-// row-validity flags m(c-1), m(c), m(c+1) and whether border rows touch the node.  GEN = false: the axis is
-// known to be regular at this node (3 <= c <= n-4), everything is a constant.
-template <bool GEN>
-struct Axis1D {
-  int o[5];
-  double va, vb, vc;
-  bool border;
-  __device__ __forceinline__ Axis1D(int c, int n, int stride) {
-    if (GEN) {
-      va = vrow(c - 1, n); vb = vrow(c, n); vc = vrow(c + 1, n);
-      border = c <= 2 || c >= n - 3;
-#pragma unroll
-      for (int s = -2; s <= 2; ++s) o[s + 2] = (min(max(c + s, 0), n - 1) - c) * stride;
-    } else {
-      va = vb = vc = 1.0;
-      border = false;
-#pragma unroll
-      for (int s = -2; s <= 2; ++s) o[s + 2] = s * stride;
-    }
+// coefficient of p(i+s) in B = sum_{r in {1,n-2}} d_r d_r^T / 6 (both rows are counted when n = 3, as the
+// reference's lower and upper border families both exist then)
+__host__ __device__ inline double bline(int i, int n, int s) {
+  if (n < 3) return 0.0;
+  double c = 0.0;
+  const int t = i + s;
+  if (i <= 2 && t >= 0 && t <= 2) c += (i == 1 ? -2.0 : 1.0) * (t == 1 ? -2.0 : 1.0);
+  if (i >= n - 3 && t >= n - 3 && t <= n - 1) c += (i == n - 2 ? -2.0 : 1.0) * (t == n - 2 ? -2.0 : 1.0);
+  return c * (1.0 / 6.0);
+}
+// coefficient of p(i+s) in (T p)(i), T = D^T diag(m) D / 6
+__host__ __device__ inline double tline(int i, int n, int s) {
+  auto v = [n](int r) { return (r >= 1 && r <= n - 2) ? 1.0 : 0.0; };
+  const double a = v(i - 1), b = v(i), c = v(i + 1);
+  switch (s) {
+    case -2: return a * (1.0 / 6.0);
+    case -1: return (a + b) * (-2.0 / 6.0);
+    case 0: return (a + 4.0 * b + c) * (1.0 / 6.0);
+    case 1: return (b + c) * (-2.0 / 6.0);
+    default: return c * (1.0 / 6.0);
   }
-};
-
-template <bool GX, bool GY, bool GZ>
-__device__ __forceinline__ double shell_node(const GridDesc& g, const StencilWeights& w, const double* __restrict__ p,
-                                             double* __restrict__ q, const int cx, const int cy, const int cz) {
-  const Axis1D<GX> X(cx, g.nx, 1);
-  const Axis1D<GY> Y(cy, g.ny, g.pitch);
-  const Axis1D<GZ> Z(cz, g.nz, (int)g.plane);
-  const long long base = (long long)(cz - g.k0 + HALO) * g.plane + cy * g.pitch + cx;
-  const double* pb = p + base;
-  const double p0 = pb[0];
-  // the 24 neighbours first: independent loads, one round trip
-  const double x0 = pb[X.o[0]], x1 = pb[X.o[1]], x3 = pb[X.o[3]], x4 = pb[X.o[4]];
-  const double y0 = pb[Y.o[0]], y1 = pb[Y.o[1]], y3 = pb[Y.o[3]], y4 = pb[Y.o[4]];
-  const double z0 = pb[Z.o[0]], z1 = pb[Z.o[1]], z3 = pb[Z.o[3]], z4 = pb[Z.o[4]];
-  const double xy00 = pb[X.o[0] + Y.o[0]], xy04 = pb[X.o[0] + Y.o[4]], xy40 = pb[X.o[4] + Y.o[0]], xy44 = pb[X.o[4] + Y.o[4]];
-  const double xz00 = pb[X.o[0] + Z.o[0]], xz04 = pb[X.o[0] + Z.o[4]], xz40 = pb[X.o[4] + Z.o[0]], xz44 = pb[X.o[4] + Z.o[4]];
-  const double yz00 = pb[Y.o[0] + Z.o[0]], yz04 = pb[Y.o[0] + Z.o[4]], yz40 = pb[Y.o[4] + Z.o[0]], yz44 = pb[Y.o[4] + Z.o[4]];
-  double acc = w.ridge2 * p0;
-  // lines: a_aa m_b m_c T_a + d_a B_a,  T = D^T diag(m) D / 6
-  auto line = [&](const auto& A, const double a6, const double d, const int c, const int n, const double t0,
-                  const double t1, const double t3, const double t4) {
-    const double L0 = a6 * A.va, L1 = -2.0 * a6 * (A.va + A.vb), L2 = a6 * (A.va + 4.0 * A.vb + A.vc),
-                 L3 = -2.0 * a6 * (A.vb + A.vc), L4 = a6 * A.vc;
-    double v = L2 * p0;
-    v = fma(L0, t0, v); v = fma(L1, t1, v); v = fma(L3, t3, v); v = fma(L4, t4, v);
-    if (A.border && n >= 3) {
-      // border rows d_1 = [1,-2,1] on nodes 0..2 and d_{n-2} on nodes n-3..n-1: d(c) (d . p) / 6
-      if (c <= 2) {
-        const double e0 = c == 0 ? p0 : (c == 1 ? t1 : t0), e1 = c == 0 ? t3 : (c == 1 ? p0 : t1),
-                     e2 = c == 0 ? t4 : (c == 1 ? t3 : p0);
-        v = fma(d * (c == 1 ? -2.0 / 6.0 : 1.0 / 6.0), e0 - 2.0 * e1 + e2, v);
-      }
-      const int cu = n - 1 - c;
-      if (cu <= 2) {
-        const double e0 = cu == 0 ? p0 : (cu == 1 ? t3 : t4), e1 = cu == 0 ? t1 : (cu == 1 ? p0 : t3),
-                     e2 = cu == 0 ? t0 : (cu == 1 ? t1 : p0);
-        v = fma(d * (cu == 1 ? -2.0 / 6.0 : 1.0 / 6.0), e0 - 2.0 * e1 + e2, v);
-      }
+}
+// host: fill the per-plane table (nz * SHELL_ZSTRIDE doubles)
+inline void shell_fill_z_table(int nz, double* tab) {
+  for (int k = 0; k < nz; ++k) {
+    double* t = tab + (size_t)k * SHELL_ZSTRIDE;
+    auto v = [nz](int r) { return (r >= 1 && r <= nz - 2) ? 1.0 : 0.0; };
+    for (int s = -2; s <= 2; ++s) {
+      t[s + 2] = tline(k, nz, s);
+      t[5 + s + 2] = bline(k, nz, s);
     }
-    return v;
-  };
-  acc += line(X, w.axx * Y.vb * Z.vb * (1.0 / 6.0), w.dx, cx, g.nx, x0, x1, x3, x4);
-  acc += line(Y, w.ayy * X.vb * Z.vb * (1.0 / 6.0), w.dy, cy, g.ny, y0, y1, y3, y4);
-  acc += line(Z, w.azz * X.vb * Y.vb * (1.0 / 6.0), w.dz, cz, g.nz, z0, z1, z3, z4);
-  // mixed terms: b_ab m_c (C_a (x) C_b) p,  C = [-va, va+vc, -vc] at offsets -2, 0, +2
-  auto mixed = [&](const auto& A, const auto& B, const double bw, const double a0, const double a4, const double b0,
-                   const double b4, const double m00, const double m04, const double m40, const double m44) {
-    const double cb = B.va + B.vc;
-    const double rowm = fma(-B.vc, m04, fma(-B.va, m00, cb * a0));
-    const double row0 = fma(-B.vc, b4, fma(-B.va, b0, cb * p0));
-    const double rowp = fma(-B.vc, m44, fma(-B.va, m40, cb * a4));
-    return bw * fma(-A.vc, rowp, fma(-A.va, rowm, (A.va + A.vc) * row0));
-  };
-  acc += mixed(X, Y, w.bxy * Z.vb, x0, x4, y0, y4, xy00, xy04, xy40, xy44);
-  acc += mixed(X, Z, w.bxz * Y.vb, x0, x4, z0, z4, xz00, xz04, xz40, xz44);
-  acc += mixed(Y, Z, w.byz * X.vb, y0, y4, z0, z4, yz00, yz04, yz40, yz44);
-  q[base] = acc;
-  return p0 * acc;
+    t[10] = -v(k - 1);
+    t[11] = v(k - 1) + v(k + 1);
+    t[12] = -v(k + 1);
+    t[13] = v(k);
+    t[14] = t[15] = 0.0;
+  }
 }
 
-// One CTA = NT consecutive shell nodes of one plane: a full plane next to a z face (general on every axis),
-// the y rows of an inner plane (z regular), or the x columns of its remaining rows (y and z regular).
 template <int NT>
-__global__ void __launch_bounds__(NT, 3)
-    k_fdi_shell(const GridDesc g, const StencilWeights w, const ShellBox sb, const double* __restrict__ p,
-                double* __restrict__ q, double* __restrict__ partials, unsigned int* __restrict__ counter,
-                CgScalars* __restrict__ sc, const int cg_mode) {
+__global__ void __launch_bounds__(NT, 4)
+    k_fdi_shell(const GridDesc g, const StencilWeights w, const ShellBox sb, const double* __restrict__ ztab,
+                const double* __restrict__ p, double* __restrict__ q, double* __restrict__ partials,
+                unsigned int* __restrict__ counter, CgScalars* __restrict__ sc, const int cg_mode) {
   __shared__ double red[NT / 32];
   if (cg_mode && sc->done) return;
-  double dot = 0.0;
-  const int nfull = sb.n_full_planes * sb.full_blocks;
-  const int b = blockIdx.x;
-  if (b < nfull) {
-    const int zi = b / sb.full_blocks;
-    const int r = (b - zi * sb.full_blocks) * NT + threadIdx.x;
-    const int cz = zi < sb.klo - g.k0 ? g.k0 + zi : sb.khi + (zi - (sb.klo - g.k0));
-    const int cy = r / g.nx, cx = r - cy * g.nx;
-    if (cy < g.ny) dot = shell_node<true, true, true>(g, w, p, q, cx, cy, cz);
-  } else {
-    const int per = sb.yrow_blocks + sb.xcol_blocks;
-    const int b2 = b - nfull;
-    const int kz = b2 / per, bb = b2 - kz * per;
-    const int cz = sb.klo + kz;
-    if (bb < sb.yrow_blocks) {
-      const int r = bb * NT + threadIdx.x;
-      const int jj = r / g.nx, cx = r - jj * g.nx;
-      const int cy = jj < sb.jlo ? jj : sb.jhi + (jj - sb.jlo);
-      if (cy < g.ny) dot = shell_node<true, true, false>(g, w, p, q, cx, cy, cz);
+  // ---- which column and which output planes
+  int ci, cj, ka, kb;
+  bool active;
+  {
+    const int b = blockIdx.x;
+    const int nring = sb.ring_blocks * sb.ring_chunks;
+    if (b < nring) {
+      const int ch = b / sb.ring_blocks;
+      const int r = (b - ch * sb.ring_blocks) * NT + threadIdx.x;
+      active = r < sb.ring_cols;
+      ka = sb.klo + ch * sb.ring_cz;
+      kb = min(ka + sb.ring_cz, sb.khi);
+      const int ny_out = g.ny - (sb.jhi - sb.jlo);
+      if (r < ny_out * g.nx) {
+        const int jj = r / g.nx;
+        ci = r - jj * g.nx;
+        cj = jj < sb.jlo ? jj : sb.jhi + (jj - sb.jlo);
+      } else {
+        const int nx_out = max(g.nx - (sb.ihi - sb.ilo), 1);
+        const int r2 = r - ny_out * g.nx;
+        const int jr = r2 / nx_out, ii = r2 - jr * nx_out;
+        cj = sb.jlo + jr;
+        ci = ii < sb.ilo ? ii : sb.ihi + (ii - sb.ilo);
+      }
     } else {
-      const int nx_out = g.nx - (sb.ihi - sb.ilo);
-      const int r = (bb - sb.yrow_blocks) * NT + threadIdx.x;
-      const int jr = r / nx_out, ii = r - jr * nx_out;
-      const int cy = sb.jlo + jr, cx = ii < sb.ilo ? ii : sb.ihi + (ii - sb.ilo);
-      if (cy < sb.jhi) dot = shell_node<true, false, false>(g, w, p, q, cx, cy, cz);
+      const int b2 = b - nring;
+      const int cap = b2 / sb.cap_blocks;
+      const int r = (b2 - cap * sb.cap_blocks) * NT + threadIdx.x;
+      cj = r / g.nx;
+      ci = r - cj * g.nx;
+      active = cj < g.ny;
+      ka = cap == 0 ? sb.capA0 : sb.capB0;
+      kb = cap == 0 ? sb.capA1 : sb.capB1;
+    }
+    active = active && kb > ka;
+  }
+  double dot = 0.0;
+  if (active) {
+    // ---- x and y coefficient sets of the column
+    const double vax = vrow(ci - 1, g.nx), vbx = vrow(ci, g.nx), vcx = vrow(ci + 1, g.nx);
+    const double vay = vrow(cj - 1, g.ny), vby = vrow(cj, g.ny), vcy = vrow(cj + 1, g.ny);
+    const double ax6 = w.axx * vby * (1.0 / 6.0), ay6 = w.ayy * vbx * (1.0 / 6.0);
+    // T lines (to be multiplied by m_z of the plane) and border lines (unmasked); tap order -2,-1,0,+1,+2
+    const double tx0 = ax6 * vax, tx1 = -2.0 * ax6 * (vax + vbx), tx2 = ax6 * (vax + 4.0 * vbx + vcx),
+                 tx3 = -2.0 * ax6 * (vbx + vcx), tx4 = ax6 * vcx;
+    const double ty0 = ay6 * vay, ty1 = -2.0 * ay6 * (vay + vby), ty2 = ay6 * (vay + 4.0 * vby + vcy),
+                 ty3 = -2.0 * ay6 * (vby + vcy), ty4 = ay6 * vcy;
+    const bool bdx = (ci <= 2 || ci >= g.nx - 3), bdy = (cj <= 2 || cj >= g.ny - 3);
+    double bx[5] = {0, 0, 0, 0, 0}, by[5] = {0, 0, 0, 0, 0};
+    if (bdx)
+#pragma unroll
+      for (int s = 0; s < 5; ++s) bx[s] = w.dx * bline(ci, g.nx, s - 2);
+    if (bdy)
+#pragma unroll
+      for (int s = 0; s < 5; ++s) by[s] = w.dy * bline(cj, g.ny, s - 2);
+    const double cx0 = -vax, cx1 = vax + vcx, cx2 = -vcx;  // C_x taps -2, 0, +2
+    const double cy0 = -vay, cy1 = vay + vcy, cy2 = -vcy;
+    const double azm = w.azz * vbx * vby, bxzm = w.bxz * vby, byzm = w.byz * vbx;
+    // ---- march: history of (S, c, gx, gy) for planes kp-4 .. kp
+    double hS[5], hc[5], hgx[5], hgy[5];
+#pragma unroll
+    for (int t = 0; t < 5; ++t) hS[t] = hc[t] = hgx[t] = hgy[t] = 0.0;
+    const double* pc = p + ((long long)(ka - 2 - g.k0 + HALO) * g.plane + cj * g.pitch + ci);
+    double* qc = q + ((long long)(ka - g.k0 + HALO) * g.plane + cj * g.pitch + ci);
+    const int P = g.pitch;
+    // clamped in-plane offsets are not needed: a tap outside the grid has coefficient 0 and the address stays
+    // inside the vector's allocation (two halo planes on either side), whose contents are finite
+    for (int kp = ka - 2; kp < kb + 2; ++kp) {
+      double S = 0.0, c = 0.0, gx = 0.0, gy = 0.0;
+      if (kp >= 0 && kp < g.nz) {
+        c = pc[0];
+        const double xm2 = pc[-2], xm1 = pc[-1], xp1 = pc[1], xp2 = pc[2];
+        const double ym2 = pc[-2 * P], ym1 = pc[-P], yp1 = pc[P], yp2 = pc[2 * P];
+        gx = fma(cx2, xp2, fma(cx0, xm2, cx1 * c));
+        gy = fma(cy2, yp2, fma(cy0, ym2, cy1 * c));
+        if (kp >= ka && kp < kb) {  // in-plane part of an output plane
+          const double cmm = pc[-2 * P - 2], cpm = pc[-2 * P + 2], cmp = pc[2 * P - 2], cpp = pc[2 * P + 2];
+          const double mz = ztab[(long long)kp * SHELL_ZSTRIDE + 13];
+          double s1 = tx2 * c;
+          s1 = fma(tx0, xm2, s1); s1 = fma(tx1, xm1, s1); s1 = fma(tx3, xp1, s1); s1 = fma(tx4, xp2, s1);
+          s1 = fma(ty2, c, s1);
+          s1 = fma(ty0, ym2, s1); s1 = fma(ty1, ym1, s1); s1 = fma(ty3, yp1, s1); s1 = fma(ty4, yp2, s1);
+          // (C_x (x) C_y) p: C_y over the rows j-2, j, j+2 of (C_x p)
+          const double rm = fma(cx2, cpm, fma(cx0, cmm, cx1 * ym2));
+          const double rp = fma(cx2, cpp, fma(cx0, cmp, cx1 * yp2));
+          s1 = fma(w.bxy, fma(cy2, rp, fma(cy0, rm, cy1 * gx)), s1);
+          S = fma(mz, s1, w.ridge2 * c);
+          if (bdx) S += bx[0] * xm2 + bx[1] * xm1 + bx[2] * c + bx[3] * xp1 + bx[4] * xp2;
+          if (bdy) S += by[0] * ym2 + by[1] * ym1 + by[2] * c + by[3] * yp1 + by[4] * yp2;
+        }
+      }
+      // shift the history (registers) and append plane kp
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { hS[t] = hS[t + 1]; hc[t] = hc[t + 1]; hgx[t] = hgx[t + 1]; hgy[t] = hgy[t + 1]; }
+      hS[4] = S; hc[4] = c; hgx[4] = gx; hgy[4] = gy;
+      const int ko = kp - 2;  // output plane completed by plane kp: history index 2 is plane ko
+      if (ko >= ka) {
+        const double* z = ztab + (long long)ko * SHELL_ZSTRIDE;
+        double acc = hS[2];
+        // z line: a_zz m_x m_y T_z + d_z B_z
+        double lz = 0.0;
+#pragma unroll
+        for (int t = 0; t < 5; ++t) lz = fma(fma(azm, z[t], w.dz * z[5 + t]), hc[t], lz);
+        acc += lz;
+        // (C_x (x) C_z) p m_y and (C_y (x) C_z) p m_x
+        acc = fma(bxzm, fma(z[12], hgx[4], fma(z[10], hgx[0], z[11] * hgx[2])), acc);
+        acc = fma(byzm, fma(z[12], hgy[4], fma(z[10], hgy[0], z[11] * hgy[2])), acc);
+        qc[0] = acc;
+        dot = fma(hc[2], acc, dot);
+        qc += g.plane;
+      }
+      pc += g.plane;
     }
   }
   const double bsum = block_sum<NT>(dot, red);

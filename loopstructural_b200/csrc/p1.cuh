@@ -10,7 +10,7 @@
 // node depends only on (a) the node parity and (b) how many cells (0, 1, >= 2) lie on either side of it on
 // each axis, and it reaches +-2 nodes.  The host assembles R^T R explicitly ONCE on a tiny mesh (<= 6 cells per
 // axis, same step vector, same cell-count parity) that contains every such class (p1_tables.py) and uploads
-// its rows as a table; k_p1_normal maps each node to its representative (p1_rep) and gathers 125 taps.
+// its rows as a table; k_p1_normal maps each node to its representative (p1_rep) and gathers its <= 36 taps.
 // 16 B/node of algorithmic traffic (read p, write q) instead of 96 B/row + 16 B/node.
 #pragma once
 #include "common.cuh"
@@ -18,9 +18,14 @@
 
 namespace lsb {
 
+// The dense table rows (125 taps, at most 33 non-zero) are compacted on the host into fixed-width lists of
+// (coefficient, storage offset); `diag` keeps the centre tap for the column scaling.
+constexpr int P1_TAPS = 36;
 struct P1Tables {
   int m[3];             // cells per axis of the small mesh the table was assembled on
-  const double* table;  // [(m2+1)][(m1+1)][(m0+1)][125], tap t = (dz+2)*25 + (dy+2)*5 + (dx+2)
+  const double* coef;   // [rows][P1_TAPS], zero padded
+  const int* off;       // [rows][P1_TAPS], element offset of the tap in the node vector (0 for padding)
+  const double* diag;   // [rows] centre coefficient
 };
 
 // representative node of the small mesh for node i of an axis with nc cells (m cells in the small mesh):
@@ -30,6 +35,10 @@ __device__ __forceinline__ int p1_rep(int i, int nc, int m) {
   if (i < 2) return i;
   if (i > nc - 2) return m - (nc - i);
   return 2 + ((i - 2) & 1);
+}
+__device__ __forceinline__ int p1_row(const GridDesc& g, const P1Tables& tb, int i, int j, int k) {
+  const int rx = p1_rep(i, g.nx - 1, tb.m[0]), ry = p1_rep(j, g.ny - 1, tb.m[1]), rz = p1_rep(k, g.nz - 1, tb.m[2]);
+  return (rz * (tb.m[1] + 1) + ry) * (tb.m[0] + 1) + rx;
 }
 
 template <int NT>
@@ -45,23 +54,23 @@ __global__ void __launch_bounds__(NT)
     const int i = (int)(t % g.nx);
     const long long r = t / g.nx;
     const int j = (int)(r % g.ny), k = (int)(r / g.ny);
-    const int rx = p1_rep(i, g.nx - 1, tb.m[0]), ry = p1_rep(j, g.ny - 1, tb.m[1]), rz = p1_rep(k, g.nz - 1, tb.m[2]);
-    const double* T = tb.table + ((long long)(rz * (tb.m[1] + 1) + ry) * (tb.m[0] + 1) + rx) * 125;
-    const long long base = (long long)(k + HALO) * g.plane + (long long)j * g.pitch + i;
-    double acc = 0.0;
-#pragma unroll 1
-    for (int dz = -2; dz <= 2; ++dz)
+    const int row = p1_row(g, tb, i, j, k);
+    const double* __restrict__ C = tb.coef + (long long)row * P1_TAPS;
+    const int* __restrict__ O = tb.off + (long long)row * P1_TAPS;
+    const double* pb = p + ((long long)(k + HALO) * g.plane + (long long)j * g.pitch + i);
+    // a non-zero coefficient implies that the neighbour exists (same cell pattern as the representative);
+    // padding entries have coefficient 0 and offset 0
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-      for (int dy = -2; dy <= 2; ++dy)
-#pragma unroll
-        for (int dx = -2; dx <= 2; ++dx) {
-          const double c = __ldg(T + (dz + 2) * 25 + (dy + 2) * 5 + (dx + 2));
-          // a non-zero coefficient implies that the neighbour exists (same cell pattern as the representative)
-          if (c != 0.0) acc = fma(c, p[base + dz * g.plane + dy * g.pitch + dx], acc);
-        }
-    const double p0 = p[base];
-    const double v = fma(w2, acc, ridge2 * p0);
-    q[base] = v;
+    for (int e = 0; e < P1_TAPS; e += 4) {
+      a0 = fma(__ldg(C + e), pb[__ldg(O + e)], a0);
+      a1 = fma(__ldg(C + e + 1), pb[__ldg(O + e + 1)], a1);
+      a2 = fma(__ldg(C + e + 2), pb[__ldg(O + e + 2)], a2);
+      a3 = fma(__ldg(C + e + 3), pb[__ldg(O + e + 3)], a3);
+    }
+    const double p0 = pb[0];
+    const double v = fma(w2, (a0 + a1) + (a2 + a3), ridge2 * p0);
+    q[pb - p] = v;
     dot = fma(p0, v, dot);
   }
   const double bsum = block_sum<NT>(dot, red);
@@ -77,9 +86,7 @@ __global__ void k_p1_diag(const GridDesc g, const P1Tables tb, const double w2, 
     const int i = (int)(t % g.nx);
     const long long r = t / g.nx;
     const int j = (int)(r % g.ny), k = (int)(r / g.ny);
-    const int rx = p1_rep(i, g.nx - 1, tb.m[0]), ry = p1_rep(j, g.ny - 1, tb.m[1]), rz = p1_rep(k, g.nz - 1, tb.m[2]);
-    const double* T = tb.table + ((long long)(rz * (tb.m[1] + 1) + ry) * (tb.m[0] + 1) + rx) * 125;
-    diag[(long long)(k + HALO) * g.plane + (long long)j * g.pitch + i] += fma(w2, T[62], ridge2);
+    diag[(long long)(k + HALO) * g.plane + (long long)j * g.pitch + i] += fma(w2, tb.diag[p1_row(g, tb, i, j, k)], ridge2);
   }
 }
 

@@ -60,6 +60,98 @@ def constraints_to_rows(constraints: dict):
     return out
 
 
+def _resolve_tolerances(tol, solver_kwargs):
+    kw = dict(solver_kwargs or {})
+    rtol = float(kw.get("rtol", 1e-5))
+    atol = float(kw.get("atol", 0.0))
+    if tol is not None and not ("atol" in kw and "rtol" in kw):
+        atol = float(tol)  # LI/_solver_strategy.py:59-60
+    return rtol, atol, kw
+
+
+def _solve_on_engine(it, eng, solver, tol, solver_kwargs) -> bool:
+    """Common tail of solve_system(solver='b200'): constraint dict -> ELL rows -> device CG -> it.c."""
+    started = perf_counter()
+    rtol, atol, kw = _resolve_tolerances(tol, solver_kwargs)
+    eng.set_options(ridge_factor=it.ridge_factor, add_ridge=it.add_ridge_regulatisation,
+                    apply_scaling=it.apply_scaling_matrix)
+    t_asm = perf_counter()
+    n_rows = 0
+    for _name, vals, cols, b, w in constraints_to_rows(it.constraints):
+        eng.add_rows(vals, cols, b, w, normalise=False)
+        n_rows += vals.shape[0]
+    assembly = perf_counter() - t_asm
+    c, res = eng.solve_cg(rtol=rtol, atol=atol, maxiter=kw.get("maxiter"), x0=kw.get("x0"))
+    it.c = c
+    it.up_to_date = True  # non-convergence is a warning, never a failure (LI/_solver_strategy.py:66-71)
+    it.latest_solve_timing = {
+        "solver": solver, "backend": "b200", "assembly_seconds": assembly, "preprocess_seconds": res.setup_seconds,
+        "solve_seconds": res.solve_seconds, "total_seconds": perf_counter() - started, "iterations": res.iterations,
+        "info": res.info, "matrix_rows": n_rows, "matrix_cols": int(it.dof), "up_to_date": True,
+    }
+    return True
+
+
+class _B200Mixin:
+    """Shared by the FDI and P1 subclasses: set-up bookkeeping, solver dispatch, device evaluation."""
+
+    def _b200_init(self):
+        self._b200_divert = False
+        self._b200_reg = {}
+        self._b200_setup_kwargs = {}
+        self._b200_engine = None
+
+    def setup_interpolator(self, **kwargs):
+        self._b200_setup_kwargs = dict(kwargs)
+        self._b200_reg = {}
+        self._b200_divert = self._b200_can_divert(kwargs)
+        return super().setup_interpolator(**kwargs)
+
+    def solve_system(self, solver=None, tol=None, solver_kwargs=None) -> bool:
+        if solver not in B200_SOLVERS:
+            if self._b200_divert:
+                # the regularisation rows were never assembled: redo the setup the stock way for this solver
+                kw = dict(self._b200_setup_kwargs)
+                kw["solver"] = solver
+                self.setup_interpolator(**kw)
+            return super().solve_system(solver=solver, tol=tol, solver_kwargs=solver_kwargs)
+        if not self._b200_divert:
+            kw = dict(self._b200_setup_kwargs)
+            kw["solver"] = solver
+            if not self._b200_can_divert(kw):
+                raise ValueError(self._b200_unsupported)
+            self.setup_interpolator(**kw)
+        if not self._pre_solve():
+            raise ValueError("Pre solve failed")
+        if self._b200_engine is not None:
+            self._b200_engine.close()
+        self._b200_engine = self._b200_make_engine()
+        return _solve_on_engine(self, self._b200_engine, solver, tol, solver_kwargs)
+
+    # -- evaluation: the device holds c after a b200 solve -------------------------------------------------
+    def _b200_engine_current(self):
+        if self._b200_engine is None or not self.up_to_date or self.latest_solve_timing.get("backend") != "b200":
+            return None
+        return self._b200_engine
+
+    def _evaluate_value_local(self, locations):
+        self.update()
+        eng = self._b200_engine_current()
+        if eng is None:
+            return super()._evaluate_value_local(locations)
+        return eng.evaluate_value(np.asarray(locations, dtype=np.float64))
+
+    def _evaluate_gradient_local(self, locations):
+        self.update()
+        eng = self._b200_engine_current()
+        if eng is None:
+            return super()._evaluate_gradient_local(locations)
+        locations = np.asarray(locations, dtype=np.float64)
+        if locations.shape[0] == 0:
+            return np.zeros((0, 3))
+        return eng.evaluate_gradient(locations)
+
+
 def _make_fdi_class():
     from loop_common.supports import StructuredGrid
     from loop_interpolation import FiniteDifferenceInterpolator
@@ -68,142 +160,114 @@ def _make_fdi_class():
     default_masks = {"dxx": Operator.Dxx_mask, "dyy": Operator.Dyy_mask, "dzz": Operator.Dzz_mask,
                      "dxy": Operator.Dxy_mask, "dxz": Operator.Dxz_mask, "dyz": Operator.Dyz_mask}
 
-    class B200FDI(FiniteDifferenceInterpolator):
+    class B200FDI(_B200Mixin, FiniteDifferenceInterpolator):
         """FiniteDifferenceInterpolator whose ``solver='b200'`` runs on the GPU engine."""
+
+        _b200_unsupported = ("solver='b200' needs a 3-D regular StructuredGrid with the default operator masks and no "
+                             "per-node regularisation scale")
 
         def __init__(self, grid, data=None):
             super().__init__(grid, data=data)
-            self._b200_divert = False
-            self._b200_stencil = {}
-            self._b200_setup_kwargs = {}
-            self._b200_engine = None
+            self._b200_init()
 
-        # -- setup: divert the stencil families ---------------------------------------------------------
+        @property
+        def _b200_stencil(self):
+            return self._b200_reg
+
         def _b200_can_divert(self, kwargs) -> bool:
             sup = self.support
             return (kwargs.get("solver") in B200_SOLVERS and isinstance(sup, StructuredGrid)
                     and getattr(sup, "dimension", 3) == 3 and not getattr(sup, "is_rectilinear", False)
                     and "operators" not in kwargs and not kwargs.get("use_regularisation_weight_scale", False))
 
-        def setup_interpolator(self, **kwargs):
-            self._b200_setup_kwargs = dict(kwargs)
-            self._b200_stencil = {}
-            self._b200_divert = self._b200_can_divert(kwargs)
-            return super().setup_interpolator(**kwargs)
-
         def assemble_inner(self, operator, w, name="regularisation"):
             if (self._b200_divert and name in default_masks and operator is not None
                     and np.array_equal(operator, default_masks[name])):
                 # w is the effective row weight (mixed terms already / 4, LC/supports/_3d_structured_grid.py:502-509)
-                self._b200_stencil[name] = float(w)
+                self._b200_reg[name] = float(w)
                 return
             return super().assemble_inner(operator, w, name=name)
 
         def assemble_borders(self):
             if self._b200_divert:
                 for k in ("dx", "dy", "dz"):
-                    self._b200_stencil[k] = float(self.interpolation_weights[k])
+                    self._b200_reg[k] = float(self.interpolation_weights[k])
                 return
             return super().assemble_borders()
 
-        # -- solve ---------------------------------------------------------------------------------------
-        def solve_system(self, solver=None, tol=None, solver_kwargs=None) -> bool:
-            if solver not in B200_SOLVERS:
-                if self._b200_divert:
-                    # the stencil rows were never assembled: redo the setup the stock way for this solver
-                    kw = dict(self._b200_setup_kwargs)
-                    kw["solver"] = solver
-                    self.setup_interpolator(**kw)
-                return super().solve_system(solver=solver, tol=tol, solver_kwargs=solver_kwargs)
-            if not self._b200_divert:
-                kw = dict(self._b200_setup_kwargs)
-                kw["solver"] = solver
-                if not self._b200_can_divert(kw):
-                    raise ValueError("solver='b200' needs a 3-D regular StructuredGrid with the default operator masks "
-                                     "and no per-node regularisation scale")
-                self.setup_interpolator(**kw)
-            if not self._pre_solve():
-                raise ValueError("Pre solve failed")
+        def _b200_make_engine(self):
             from .engine import Engine
 
-            started = perf_counter()
             sup = self.support
-            kw = dict(solver_kwargs or {})
-            rtol = float(kw.get("rtol", 1e-5))
-            atol = float(kw.get("atol", 0.0))
-            if tol is not None and not ("atol" in kw and "rtol" in kw):
-                atol = float(tol)  # LI/_solver_strategy.py:59-60
-            if self._b200_engine is not None:
-                self._b200_engine.close()
             eng = Engine(np.asarray(sup.nsteps), np.asarray(sup.origin, float), np.asarray(sup.step_vector, float))
-            self._b200_engine = eng
-            st = self._b200_stencil
+            st = self._b200_reg
             # effective weights go in directly: the engine's dict API divides the mixed terms by 4 itself
             eng.set_regularisation({"dxx": st.get("dxx", 0.0), "dyy": st.get("dyy", 0.0), "dzz": st.get("dzz", 0.0),
                                     "dxy": 4.0 * st.get("dxy", 0.0), "dxz": 4.0 * st.get("dxz", 0.0),
                                     "dyz": 4.0 * st.get("dyz", 0.0), "dx": st.get("dx", 0.0), "dy": st.get("dy", 0.0),
                                     "dz": st.get("dz", 0.0)})
-            eng.set_options(ridge_factor=self.ridge_factor, add_ridge=self.add_ridge_regulatisation,
-                            apply_scaling=self.apply_scaling_matrix)
-            t_asm = perf_counter()
-            n_rows = 0
-            for _name, vals, cols, b, w in constraints_to_rows(self.constraints):
-                eng.add_rows(vals, cols, b, w, normalise=False)
-                n_rows += vals.shape[0]
-            assembly = perf_counter() - t_asm
-            c, res = eng.solve_cg(rtol=rtol, atol=atol, maxiter=kw.get("maxiter"), x0=kw.get("x0"))
-            self.c = c
-            self.up_to_date = True
-            self.latest_solve_timing = {
-                "solver": solver, "backend": "b200", "assembly_seconds": assembly,
-                "preprocess_seconds": res.setup_seconds, "solve_seconds": res.solve_seconds,
-                "total_seconds": perf_counter() - started, "iterations": res.iterations, "info": res.info,
-                "matrix_rows": n_rows, "matrix_cols": int(self.dof), "up_to_date": True,
-            }
-            return True
-
-        # -- evaluation: the device holds c after a b200 solve ---------------------------------------------
-        def _b200_engine_current(self):
-            eng = self._b200_engine
-            if eng is None or not self.up_to_date:
-                return None
             return eng
-
-        def _evaluate_value_local(self, locations):
-            self.update()
-            eng = self._b200_engine_current()
-            if eng is None or self.latest_solve_timing.get("backend") != "b200":
-                return super()._evaluate_value_local(locations)
-            return eng.evaluate_value(np.asarray(locations, dtype=np.float64))
-
-        def _evaluate_gradient_local(self, locations):
-            self.update()
-            eng = self._b200_engine_current()
-            if eng is None or self.latest_solve_timing.get("backend") != "b200":
-                return super()._evaluate_gradient_local(locations)
-            locations = np.asarray(locations, dtype=np.float64)
-            if locations.shape[0] == 0:
-                return np.zeros((0, 3))
-            return eng.evaluate_gradient(locations)
 
     B200FDI.__name__ = "B200FiniteDifferenceInterpolator"
     return B200FDI
+
+
+def _make_p1_class():
+    from loop_common.supports import TetMesh
+    from loop_interpolation import P1Interpolator
+
+    class B200P1(_B200Mixin, P1Interpolator):
+        """P1Interpolator whose ``solver='b200'`` runs on the GPU engine: the face gradient-jump rows of
+        minimise_edge_jumps (LI/_p1interpolator.py:115-166; 99 % of A) are applied matrix-free."""
+
+        _b200_unsupported = ("solver='b200' needs a 3-D structured TetMesh, the default (face-normal) edge-jump "
+                             "regularisation and no per-node regularisation scale")
+
+        def __init__(self, mesh):
+            super().__init__(mesh)
+            self._b200_init()
+
+        def _b200_can_divert(self, kwargs) -> bool:
+            return (kwargs.get("solver") in B200_SOLVERS and isinstance(self.support, TetMesh)
+                    and not kwargs.get("use_regularisation_weight_scale", False))
+
+        def minimise_edge_jumps(self, w=0.1, vector_func=None, vector=None, name="edge jump"):
+            if self._b200_divert and vector_func is None and vector is None and name == "edge jump" and "cgw" not in self._b200_reg:
+                self._b200_reg["cgw"] = float(w)
+                return
+            return super().minimise_edge_jumps(w=w, vector_func=vector_func, vector=vector, name=name)
+
+        def _b200_make_engine(self):
+            from .engine import Engine
+
+            sup = self.support
+            eng = Engine(np.asarray(sup.nsteps), np.asarray(sup.origin, float), np.asarray(sup.step_vector, float),
+                         kind="tetmesh")
+            eng.set_p1_regularisation(self._b200_reg.get("cgw", 0.0))
+            return eng
+
+    B200P1.__name__ = "B200P1Interpolator"
+    return B200P1
 
 
 def install():
     """Register the B200 subclasses in the reference's ``interpolator_map`` (idempotent).  Returns the classes."""
     import loop_interpolation as li
 
+    T = li.InterpolatorType
     if "fdi" not in _installed:
         _installed["fdi"] = _make_fdi_class()
-        _installed["fdi_stock"] = li.interpolator_map[li.InterpolatorType.FINITE_DIFFERENCE]
-    li.interpolator_map[li.InterpolatorType.FINITE_DIFFERENCE] = _installed["fdi"]
-    return {"FDI": _installed["fdi"]}
+        _installed["p1"] = _make_p1_class()
+        _installed["stock"] = {T.FINITE_DIFFERENCE: li.interpolator_map[T.FINITE_DIFFERENCE],
+                               T.PIECEWISE_LINEAR: li.interpolator_map[T.PIECEWISE_LINEAR]}
+    li.interpolator_map[T.FINITE_DIFFERENCE] = _installed["fdi"]
+    li.interpolator_map[T.PIECEWISE_LINEAR] = _installed["p1"]
+    return {"FDI": _installed["fdi"], "P1": _installed["p1"]}
 
 
 def uninstall():
     """Put the stock classes back."""
     import loop_interpolation as li
 
-    if "fdi_stock" in _installed:
-        li.interpolator_map[li.InterpolatorType.FINITE_DIFFERENCE] = _installed["fdi_stock"]
+    for key, cls in _installed.get("stock", {}).items():
+        li.interpolator_map[key] = cls

@@ -113,3 +113,37 @@ def test_b200_solve_fails_loudly_without_a_gpu(li):
     it.setup_interpolator(solver="b200")
     with pytest.raises(nat.Lsb200Error):
         it.solve_system(solver="b200")
+
+
+def test_p1_subclass_diverts_only_the_face_rows(li):
+    """P1: with solver='b200' the edge-jump family is reduced to its weight; every data family is the reference's;
+    any other solver re-assembles it and gives the stock answer."""
+    from loop_common.supports import TetMesh
+    from loopstructural_b200 import plugin
+    from oracle import fdi_oracle as fo
+
+    classes = plugin.install()
+    assert li.interpolator_map[li.InterpolatorType.PIECEWISE_LINEAR] is classes["P1"]
+    plugin.uninstall()
+    assert li.interpolator_map[li.InterpolatorType.PIECEWISE_LINEAR] is li.P1Interpolator
+    grid, value, gradient = fo.synthetic_problem(7, 40, 10, seed=4)
+    value[:, :3] = np.clip(value[:, :3], 0.01, 0.99)
+    gradient[:, :3] = np.clip(gradient[:, :3], 0.01, 0.99)
+    mesh = TetMesh(origin=grid.origin, nsteps_cells=grid.nsteps - 1, step_vector=grid.step)
+    it = classes["P1"](mesh)
+    it.set_value_constraints(value)
+    it.set_normal_constraints(gradient)
+    it.setup_interpolator(solver="b200", cgw=0.25)
+    assert it._b200_reg == {"cgw": 0.25} and sorted(it.constraints) == ["norm", "value"]
+    stock = li.P1Interpolator(mesh)
+    stock.set_value_constraints(value)
+    stock.set_normal_constraints(gradient)
+    stock.setup_interpolator(cgw=0.25)
+    for name, vals, cols, b, w in plugin.constraints_to_rows(it.constraints):
+        m = stock.constraints[name]["matrix"].toarray()
+        dense = np.zeros_like(m)
+        np.add.at(dense, (np.repeat(np.arange(vals.shape[0]), vals.shape[1]), cols.ravel()), vals.ravel())
+        assert np.array_equal(dense, m), name
+    assert it.solve_system(solver="cg", tol=1e-10) and stock.solve_system(solver="cg", tol=1e-10)
+    assert "edge jump" in it.constraints
+    assert np.allclose(it.c, stock.c, rtol=0, atol=1e-8)
