@@ -340,7 +340,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=256, help="nodes per axis per GPU")
+    ap.add_argument("--n", "--grid-n", dest="n", type=int, default=256,
+                    help="nodes per axis per GPU (use --grid-n under torchrun, whose own parser finds --n ambiguous)")
     ap.add_argument("--nz-per-gpu", type=int, default=0, help="z planes per GPU (default: --n); e.g. --n 1024 --nz-per-gpu 128 "
                                                               "on 8 GPUs is the 1024^3 grid of BASELINE configs[4]")
     ap.add_argument("--n-value", type=int, default=100_000)

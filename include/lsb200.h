@@ -205,6 +205,11 @@ int lsb200_eval_gradient(lsb200_handle h, int64_t n, const double* xyz, double* 
 int lsb200_eval_value_dev(lsb200_handle h, int64_t n, const double* xyz_dev, double* out_dev, void* stream);
 int lsb200_eval_gradient_dev(lsb200_handle h, int64_t n, const double* xyz_dev, double* out_dev, void* stream);
 
+/* Page-locked host memory for result buffers (c of a large grid is 134 MB - 1 GB: a pageable destination halves
+ * the device->host rate and pays its page faults inside every solve). */
+int lsb200_host_alloc(int64_t bytes, void** out);
+int lsb200_host_free(void* p);
+
 /* ---- measurement hooks (bench.py) -------------------------------------- */
 
 /* run `reps` applications of the dominant kernel on the device-resident vectors and return

@@ -1132,10 +1132,41 @@ int lsb200_solve_cg(lsb200_handle h, double rtol, double atol, int64_t maxiter, 
     long long enq = 0;
     int slot = 0;
     bool pending[2] = {false, false};
+    // After the first batch (which also sets every kernel attribute) a full batch is captured once into a CUDA
+    // graph and replayed: the iteration is 5-7 short launches plus the fork/join of the shell stream, and on
+    // small grids the per-launch latency, not the kernels, sets the pace (profiles/r01q: 39 us / iteration on the
+    // Claudius-size grid).  LSB200_GRAPH=0 keeps plain launches.
+    static const bool want_graph = !(getenv("LSB200_GRAPH") && atoi(getenv("LSB200_GRAPH")) == 0);
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    bool graph_tried = false;
+    long long launches_per_batch = 0;
     while (!done) {
       const long long todo = std::min<long long>(batch, maxit - enq);
-      for (long long it = 0; it < todo; ++it)
-        if ((rc = enqueue_iteration(h))) return rc;
+      if (want_graph && !graph_tried && enq >= batch && todo == batch) {
+        graph_tried = true;
+        const long long l0 = h->launches;
+        if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+          int crc = 0;
+          for (long long it = 0; it < batch && !crc; ++it) crc = enqueue_iteration(h);
+          const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+          if (crc || ce != cudaSuccess || !graph || cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
+            cudaGetLastError();
+            gexec = nullptr;
+          }
+        } else {
+          cudaGetLastError();
+        }
+        launches_per_batch = h->launches - l0;
+        h->launches = l0;  // nothing ran during the capture
+      }
+      if (gexec && todo == batch) {
+        CK(cudaGraphLaunch(gexec, h->stream));
+        h->launches += launches_per_batch;
+      } else {
+        for (long long it = 0; it < todo; ++it)
+          if ((rc = enqueue_iteration(h))) return rc;
+      }
       enq += todo;
       CK(cudaMemcpyAsync(&snap[slot], sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
       CK(cudaEventRecord(ev[slot], h->stream));
@@ -1154,6 +1185,8 @@ int lsb200_solve_cg(lsb200_handle h, double rtol, double atol, int64_t maxiter, 
       slot ^= 1;
     }
     CK(cudaStreamSynchronize(h->stream));
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
     cudaEventDestroy(ev[0]);
     cudaEventDestroy(ev[1]);
     cudaFreeHost(snap);
@@ -1238,6 +1271,19 @@ int lsb200_eval_value(lsb200_handle h, int64_t n, const double* xyz, double* out
 int lsb200_eval_gradient(lsb200_handle h, int64_t n, const double* xyz, double* out) {
   if (!h) return fail(LSB200_ERR_ARG, "null handle");
   return eval_host(h, n, xyz, out, true);
+}
+
+int lsb200_host_alloc(int64_t bytes, void** out) {
+  if (!out || bytes <= 0) return fail(LSB200_ERR_ARG, "bad argument");
+  *out = nullptr;
+  if (lsb200_device_count() <= 0) return fail(LSB200_ERR_CUDA, "no CUDA device available");
+  cudaError_t e = cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) return fail(LSB200_ERR_ALLOC, "cudaHostAlloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e));
+  return 0;
+}
+int lsb200_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+  return 0;
 }
 
 int lsb200_time_kernel(lsb200_handle h, int which, int reps, double* seconds_per_launch) {

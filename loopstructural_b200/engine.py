@@ -99,6 +99,9 @@ class Engine:
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.lsb200_destroy(self._h)
             self._h = nat.Handle()
+        if getattr(self, "_pinned", None) is not None:
+            self._pinned = None
+            self._lib.lsb200_host_free(self._pinned_ptr)
 
     def __del__(self):
         try:
@@ -238,14 +241,29 @@ class Engine:
         nat.check(self._lib.lsb200_get_scaling(self._h, nat.dptr(out)))
         return out
 
+    def pinned_vector(self) -> np.ndarray:
+        """A page-locked float64 array of local_dof entries owned by this engine (freed by close()); pass it as
+        ``out=`` to solve_cg / get_c to take the result without page faults or a pageable bounce."""
+        if getattr(self, "_pinned", None) is None:
+            ptr = C.c_void_p()
+            n = self.local_dof
+            nat.check(self._lib.lsb200_host_alloc(8 * n, C.byref(ptr)))
+            self._pinned_ptr = ptr
+            self._pinned = np.ctypeslib.as_array(C.cast(ptr, nat.c_double_p), shape=(n,))
+        return self._pinned
+
     def solve_cg(self, rtol: float = 1e-5, atol: float = 0.0, maxiter: int | None = None, x0=None,
-                 want_c: bool = True):
+                 want_c: bool = True, out: np.ndarray | None = None):
         info = nat.SolveInfo()
         x0p = None
         if x0 is not None:
             x0 = nat.as_f64(x0, (self.local_dof,))
             x0p = nat.dptr(x0)
-        c = self._vec() if want_c else None
+        if out is not None:
+            if out.dtype != np.float64 or out.shape != (self.local_dof,) or not out.flags.c_contiguous:
+                raise ValueError("out must be a contiguous float64 array of local_dof entries")
+            want_c = True
+        c = (out if out is not None else self._vec()) if want_c else None
         nat.check(self._lib.lsb200_solve_cg(self._h, float(rtol), float(atol), int(maxiter or 0), x0p,
                                             nat.dptr(c) if want_c else None, C.byref(info)))
         res = SolveResult(int(info.info), int(info.iterations), float(info.residual_norm), float(info.threshold),

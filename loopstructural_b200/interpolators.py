@@ -114,6 +114,8 @@ class _B200DiscreteInterpolator:
 
     def close(self):
         if self._engine is not None:
+            self.c = np.array(self.c, dtype=np.float64)  # detach from the engine's page-locked buffer
+            self._c_on_device = False
             self._engine.close()
             self._engine = None
 
@@ -143,7 +145,9 @@ class _B200DiscreteInterpolator:
         e = self.engine
         e.set_options(ridge_factor=self.ridge_factor, add_ridge=self.add_ridge_regulatisation,
                       apply_scaling=self.apply_scaling_matrix, deterministic=bool(kw.get("deterministic", False)))
-        c, res = e.solve_cg(rtol=rtol, atol=atol, maxiter=kw.get("maxiter"), x0=kw.get("x0"), want_c=True)
+        # the result lands in a page-locked buffer owned by the engine; like the reference's solve_system
+        # (which rebinds self.c on every solve) it is valid until the next solve of this interpolator
+        c, res = e.solve_cg(rtol=rtol, atol=atol, maxiter=kw.get("maxiter"), x0=kw.get("x0"), out=e.pinned_vector())
         self.c = c
         self._c_on_device = True
         self.up_to_date = True  # non-convergence is a warning, never a failure (LI/_solver_strategy.py:66-71)

@@ -24,6 +24,10 @@ def main():
     for tag in sys.argv[1:] or ["unit24_tight", "aniso"]:
         z = np.load(os.path.join(H.GOLDEN, f"fdi_solve_{tag}.npz"))
         grid, weights, fams, rtol, atol = H.solve_case(z)
+        if int(grid.nsteps[2]) < partition.HALO * world:
+            if rank == 0:
+                print(f"slab solve {tag}: skipped, {int(grid.nsteps[2])} planes cannot feed {world} slabs")
+            continue
         bounds = partition.slab_bounds(int(grid.nsteps[2]), world)
         e = Engine(grid.nsteps, grid.origin, grid.step, slab=bounds[rank], device=local)
         ids = [Engine.comm_unique_id() if rank == 0 else None]
