@@ -28,9 +28,9 @@ sys.path.insert(0, ROOT)
 METRIC = "fdi_cg_node_updates_per_second"
 UNIT = "dof-iter/s"
 BYTES_MATVEC_PER_DOF = 16.0      # read p, write q
-# dram__bytes_read.sum + dram__bytes_write.sum of one 256^3 matvec from ncu --set full (profiles/r01e_box_cfg0_full_details.csv:
-# 146.0 + 81.3 MB for k_fdi_box; profiles/r01j_shell_full_details.csv: 25.8 + 2.7 MB for k_fdi_shell)
-TRAFFIC_MATVEC_256 = (146.03 + 81.28 + 25.85 + 2.70) * 1e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one 256^3 matvec from ncu --set full
+# (profiles/r01y_matvec_full_details.csv: 143.4 + 80.2 MB for k_fdi_box, 25.8 + 0.4 MB for k_fdi_shell)
+TRAFFIC_MATVEC_256 = (143.39 + 80.18 + 25.84 + 0.41) * 1e6
 BYTES_ITERATION_PER_DOF = 104.0  # matvec 16 + x/r update 48 (+8 scaling vector) + p update 24 (+8 scaling vector)
 
 
@@ -106,6 +106,15 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_threads():
+    """Threads the CPU leg can use: the process affinity (scipy's CSR matvec is single-threaded, numpy's BLAS-backed
+    dot products use the rest)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -158,7 +167,7 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "synthetic FDI foliation 256^3 nodes, 1e5 value + 1e4 gradient constraints (configs[1])",
                    "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": sample,
                          "cg_only_value": units / solve_s if solve_s > 0 else None},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -285,6 +294,7 @@ def run_ours(args):
     # ---- roofline of the dominant operator kernel + whole iteration, CUDA events on the engine's stream
     t_matvec = eng.time_kernel(0, reps=20)
     t_iter = eng.time_kernel(1, reps=20)
+    t_rows, t_xr, t_p = eng.time_kernel(2, reps=20), eng.time_kernel(3, reps=20), eng.time_kernel(4, reps=20)
     peak, peak_src = measured_peak()
     dof_local = eng.local_dof
     ach = BYTES_MATVEC_PER_DOF * dof_local / t_matvec / 1e9
@@ -311,6 +321,11 @@ def run_ours(args):
             "roofline_iteration": {"bound": "hbm", "achieved": ach_it, "peak": peak, "unit": "GB/s",
                                    "frac": ach_it / peak, "seconds_per_iteration": t_iter,
                                    "bytes_per_dof": BYTES_ITERATION_PER_DOF},
+            "kernels": {  # every kernel of the iteration, CUDA events around 20 back-to-back launches each
+                "matvec k_fdi_box+k_fdi_shell": {"us": 1e6 * t_matvec, "bytes_per_dof": 16, "gbs": 16 * dof_local / t_matvec / 1e9},
+                "k_cg_update_xr": {"us": 1e6 * t_xr, "bytes_per_dof": 56, "gbs": 56 * dof_local / t_xr / 1e9},
+                "k_cg_update_p": {"us": 1e6 * t_p, "bytes_per_dof": 32, "gbs": 32 * dof_local / t_p / 1e9},
+                "k_rows_normal": {"us": 1e6 * t_rows, "rows": int(eng.num_rows)}},
             "e2e": {"value": dof_global * its_e2e / wall_e2e, "unit": UNIT,
                     "h2d_bytes_per_step": int(value.nbytes + gradient.nbytes),
                     "d2h_bytes_per_step": int(8 * dof_local), "ms_per_step": 1e3 * wall_e2e / max(args.steps, 1)},
@@ -322,11 +337,11 @@ def run_ours(args):
             dof, it, dt, timing = cpu_reference_step(args.ref_n, max(100, int(1e5 * (args.ref_n / 256.0) ** 3)),
                                                      max(10, int(1e4 * (args.ref_n / 256.0) ** 3)))
             line["cpu_baseline"] = {
-                "value": dof * it / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                "value": dof * it / dt, "unit": UNIT, "cores": host_threads(), "kind": "port",
                 "sample": f"{args.ref_n}^3-node sample of the same workload, one full scipy-path solve "
                           f"({it} iterations, {dt:.1f} s: assembly {timing['assembly_seconds']:.1f} s, preprocess "
                           f"{timing['preprocess_seconds']:.1f} s, A^T A {timing['gram_seconds']:.1f} s, CG "
-                          f"{timing['solve_seconds']:.1f} s); scipy CG is single-threaded",
+                          f"{timing['solve_seconds']:.1f} s); scipy's CSR matvec is single-threaded, numpy's BLAS dot products use the other threads",
             }
         print(json.dumps(line))
     if world > 1:

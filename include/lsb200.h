@@ -214,7 +214,8 @@ int lsb200_host_free(void* p);
 
 /* run `reps` applications of the dominant kernel on the device-resident vectors and return
  * the average device time per launch in seconds (CUDA events on the launching stream).
- * which: 0 = regularisation normal matvec, 1 = whole CG iteration, 2 = data-row matvec */
+ * which: 0 = regularisation normal matvec, 1 = whole CG iteration, 2 = data-row matvec, 3 = x/r update with the
+ * fused r.S^2 r reduction, 4 = p update */
 int lsb200_time_kernel(lsb200_handle h, int which, int reps, double* seconds_per_launch);
 
 #ifdef __cplusplus

@@ -10,6 +10,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cub/cub.cuh>
+
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -107,6 +109,7 @@ struct lsb200_ctx {
   double *x = nullptr, *r = nullptr, *p = nullptr, *q = nullptr, *rhs = nullptr, *diag = nullptr, *s2 = nullptr;
   std::vector<RowBlock> pending;  // as added
   std::vector<RowBlock> blocks;   // merged per width at finalize
+  std::vector<RowTranspose> transposes;  // node-major views of `blocks` (deterministic mode only)
   long long rows_kept = 0;
   CgScalars* sc = nullptr;
   CgScalars* sc_host = nullptr;  // pinned
@@ -135,6 +138,10 @@ struct lsb200_ctx {
   long long launches = 0;
   double setup_seconds = 0.0;
 };
+
+extern "C" {
+static void free_transposes(lsb200_ctx* h);  // defined beside lsb200_finalize_system
+}
 
 static int vec_blocks(const lsb200_ctx* h, long long n, int per_thread = 4) {
   long long b = (n + (long long)VEC_NT * per_thread - 1) / ((long long)VEC_NT * per_thread);
@@ -418,21 +425,35 @@ static int launch_regularisation(lsb200_ctx* h, const double* p, double* q, int 
 
 static int launch_rows(lsb200_ctx* h, const double* p, double* q, int cg_mode) {
   bool first = true;
-  for (const RowBlock& rb : h->blocks) {
+  const bool det = h->deterministic && h->transposes.size() == h->blocks.size();
+  for (size_t bi = 0; bi < h->blocks.size(); ++bi) {
+    const RowBlock& rb = h->blocks[bi];
     if (rb.n == 0) continue;
     long long nb = (rb.n + VEC_NT - 1) / VEC_NT;
     if (nb > h->sm_count * 16) nb = h->sm_count * 16;
-    k_rows_normal<VEC_NT><<<(int)nb, VEC_NT, 0, h->stream>>>(h->g, rb, p, q, h->partials + MAX_PARTIALS,
-                                                             h->counters + 1, h->sc, cg_mode, first ? 1 : 0);
-    CKL();
-    h->launches++;
+    if (det) {
+      const RowTranspose& tr = h->transposes[bi];
+      k_rows_t<VEC_NT><<<(int)nb, VEC_NT, 0, h->stream>>>(h->g, rb, tr, p, h->partials + MAX_PARTIALS, h->counters + 1, h->sc,
+                                                          cg_mode, first ? 1 : 0);
+      CKL();
+      const int ng = std::max(1, std::min((tr.n_nodes + 255) / 256, h->sm_count * 16));
+      k_rows_gather<<<ng, 256, 0, h->stream>>>(h->g, rb, tr, q, 0, h->sc, cg_mode);
+      CKL();
+      h->launches += 2;
+    } else {
+      k_rows_normal<VEC_NT><<<(int)nb, VEC_NT, 0, h->stream>>>(h->g, rb, p, q, h->partials + MAX_PARTIALS, h->counters + 1, h->sc,
+                                                               cg_mode, first ? 1 : 0);
+      CKL();
+      h->launches++;
+    }
     first = false;
   }
   return 0;
 }
 
-static int halo_exchange(lsb200_ctx* h, double* v) {
+static int halo_exchange(lsb200_ctx* h, double* v, cudaStream_t stream = nullptr) {
   if (h->nranks == 1) return 0;
+  if (!stream) stream = h->stream;
   const size_t cnt = (size_t)HALO * h->g.plane;
   double* lo_halo = v;                                                  // planes k0-2,k0-1
   double* lo_own = v + (long long)HALO * h->g.plane;                    // planes k0,k0+1
@@ -440,12 +461,12 @@ static int halo_exchange(lsb200_ctx* h, double* v) {
   double* hi_halo = v + (long long)(h->g.nzl + HALO) * h->g.plane;      // planes k1,k1+1
   NCK(nccl::GroupStart());
   if (h->rank > 0) {
-    NCK(nccl::Send(lo_own, cnt, nccl::Float64, h->rank - 1, h->comm, h->stream));
-    NCK(nccl::Recv(lo_halo, cnt, nccl::Float64, h->rank - 1, h->comm, h->stream));
+    NCK(nccl::Send(lo_own, cnt, nccl::Float64, h->rank - 1, h->comm, stream));
+    NCK(nccl::Recv(lo_halo, cnt, nccl::Float64, h->rank - 1, h->comm, stream));
   }
   if (h->rank < h->nranks - 1) {
-    NCK(nccl::Send(hi_own, cnt, nccl::Float64, h->rank + 1, h->comm, h->stream));
-    NCK(nccl::Recv(hi_halo, cnt, nccl::Float64, h->rank + 1, h->comm, h->stream));
+    NCK(nccl::Send(hi_own, cnt, nccl::Float64, h->rank + 1, h->comm, stream));
+    NCK(nccl::Recv(hi_halo, cnt, nccl::Float64, h->rank + 1, h->comm, stream));
   }
   NCK(nccl::GroupEnd());
   return 0;
@@ -457,23 +478,27 @@ static int allreduce_scalar(lsb200_ctx* h, double* dev) {
   return 0;
 }
 
-static int free_block(RowBlock& rb) {
-  cudaFree(rb.vals);
-  cudaFree(rb.cols);
-  cudaFree(rb.w2);
-  cudaFree(rb.b);
+static void pool_free(lsb200_ctx* h, void* p) {
+  if (p) cudaFreeAsync(p, h->stream);
+}
+
+static int free_block(lsb200_ctx* h, RowBlock& rb) {
+  pool_free(h, rb.vals);
+  pool_free(h, rb.cols);
+  pool_free(h, rb.w2);
+  pool_free(h, rb.b);
   rb = RowBlock{};
   return 0;
 }
 
-static int alloc_block(RowBlock& rb, long long n, int k) {
+static int alloc_block(lsb200_ctx* h, RowBlock& rb, long long n, int k) {
   rb.n = n;
   rb.k = k;
   const long long m = std::max<long long>(n, 1);
-  CK(cudaMalloc(&rb.vals, sizeof(double) * m * k));
-  CK(cudaMalloc(&rb.cols, sizeof(int) * m * k));
-  CK(cudaMalloc(&rb.w2, sizeof(double) * m));
-  CK(cudaMalloc(&rb.b, sizeof(double) * m));
+  CK(cudaMallocAsync(&rb.vals, sizeof(double) * m * k, h->stream));
+  CK(cudaMallocAsync(&rb.cols, sizeof(int) * m * k, h->stream));
+  CK(cudaMallocAsync(&rb.w2, sizeof(double) * m, h->stream));
+  CK(cudaMallocAsync(&rb.b, sizeof(double) * m, h->stream));
   return 0;
 }
 
@@ -548,6 +573,15 @@ static int create_common(int kind, const int64_t nsteps[3], const double origin[
   CK(cudaGetDeviceProperties(&prop, device));
   h->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  {
+    // transient buffers and row blocks come from the stream-ordered pool; keep what is freed (cudaMalloc / cudaFree
+    // cost 20-400 ms per set-up when they map and unmap memory, profiles/r01z)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   for (int t = 0; t < 3; ++t) {
     CK(cudaStreamCreateWithFlags(&h->side[t], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_join[t], cudaEventDisableTiming));
@@ -581,8 +615,9 @@ int lsb200_destroy(lsb200_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (RowBlock& rb : h->pending) free_block(rb);
-  for (RowBlock& rb : h->blocks) free_block(rb);
+  for (RowBlock& rb : h->pending) free_block(h, rb);
+  for (RowBlock& rb : h->blocks) free_block(h, rb);
+  free_transposes(h);
   double* v[] = {h->x, h->r, h->p, h->q, h->rhs, h->diag, h->s2};
   for (double* pv : v) cudaFree(pv);
   cudaFree(h->sc);
@@ -696,17 +731,17 @@ int lsb200_add_rows(lsb200_handle h, int64_t n_rows, int k, const double* vals, 
   CK(cudaSetDevice(h->device));
   double *dv = nullptr, *db = nullptr, *dw = nullptr;
   long long* dc = nullptr;
-  CK(cudaMalloc(&dv, sizeof(double) * n_rows * k));
-  CK(cudaMalloc(&dc, sizeof(long long) * n_rows * k));
-  CK(cudaMalloc(&db, sizeof(double) * n_rows));
-  CK(cudaMalloc(&dw, sizeof(double) * n_rows));
+  CK(cudaMallocAsync(&dv, sizeof(double) * n_rows * k, h->stream));
+  CK(cudaMallocAsync(&dc, sizeof(long long) * n_rows * k, h->stream));
+  CK(cudaMallocAsync(&db, sizeof(double) * n_rows, h->stream));
+  CK(cudaMallocAsync(&dw, sizeof(double) * n_rows, h->stream));
   CK(cudaMemcpyAsync(dv, vals, sizeof(double) * n_rows * k, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(dc, cols, sizeof(long long) * n_rows * k, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(db, b, sizeof(double) * n_rows, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(dw, w, sizeof(double) * n_rows, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * 2, h->stream));
   RowBlock rb{};
-  int rc = alloc_block(rb, n_rows, width_class(k));
+  int rc = alloc_block(h, rb, n_rows, width_class(k));
   if (rc) return rc;
   CK(cudaMemsetAsync(rb.cols, 0xff, sizeof(int) * rb.n * rb.k, h->stream));
   CK(cudaMemsetAsync(rb.vals, 0, sizeof(double) * rb.n * rb.k, h->stream));
@@ -717,9 +752,9 @@ int lsb200_add_rows(lsb200_handle h, int64_t n_rows, int k, const double* vals, 
   unsigned long long st[2];
   CK(cudaMemcpyAsync(st, h->status, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  cudaFree(dv); cudaFree(dc); cudaFree(db); cudaFree(dw);
+  pool_free(h, dv); pool_free(h, dc); pool_free(h, db); pool_free(h, dw);
   if (st[1]) {
-    free_block(rb);
+    free_block(h, rb);
     return fail(LSB200_ERR_ARG, "a row touching the owned planes [%d,%d) has a column outside the halo planes", h->g.k0, h->g.k1);
   }
   h->rows_kept += (long long)st[0];
@@ -741,12 +776,12 @@ int lsb200_add_point_rows(lsb200_handle h, int kind, int64_t n, const double* da
   CK(cudaSetDevice(h->device));
   const int mult = kind == LSB200_ROWS_GRADIENT ? 2 : (kind == LSB200_ROWS_NORMAL ? 3 : (kind == LSB200_ROWS_VALUE ? 1 : 1));
   double* dd = nullptr;
-  CK(cudaMalloc(&dd, sizeof(double) * n * ncols));
+  CK(cudaMallocAsync(&dd, sizeof(double) * n * ncols, h->stream));
   CK(cudaMemcpyAsync(dd, data, sizeof(double) * n * ncols, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * 2, h->stream));
   RowBlock rb{};
   const int k = h->kind == LSB200_SUPPORT_GRID ? 8 : 4;
-  int rc = alloc_block(rb, n * mult, k);
+  int rc = alloc_block(h, rb, n * mult, k);
   if (rc) return rc;
   const int nb = (int)std::min<long long>((n + 127) / 128, 4096);
   if (h->kind == LSB200_SUPPORT_GRID) {
@@ -754,8 +789,8 @@ int lsb200_add_point_rows(lsb200_handle h, int kind, int64_t n, const double* da
   } else {
     if (kind == LSB200_ROWS_GRADIENT) {
       // P1Interpolator.add_gradient_constraints is a no-op (LI/_p1interpolator.py:70-71)
-      cudaFree(dd);
-      free_block(rb);
+      pool_free(h, dd);
+      free_block(h, rb);
       return 0;
     }
     k_p1_point_rows<<<nb, 128, 0, h->stream>>>(h->g, kind, n, dd, ncols, weight, rb, 0, h->status);
@@ -765,7 +800,7 @@ int lsb200_add_point_rows(lsb200_handle h, int kind, int64_t n, const double* da
   unsigned long long st[2];
   CK(cudaMemcpyAsync(st, h->status, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  cudaFree(dd);
+  pool_free(h, dd);
   if (n_rows_out) *n_rows_out = (int64_t)st[0];
   h->rows_kept += (long long)st[0];
   h->pending.push_back(rb);
@@ -783,13 +818,13 @@ int lsb200_add_pair_rows(lsb200_handle h, int64_t n, const double* xyz_i, const 
   if (!xyz_i || !xyz_j) return fail(LSB200_ERR_ARG, "null coordinates");
   CK(cudaSetDevice(h->device));
   double *di = nullptr, *dj = nullptr;
-  CK(cudaMalloc(&di, sizeof(double) * 3 * n));
-  CK(cudaMalloc(&dj, sizeof(double) * 3 * n));
+  CK(cudaMallocAsync(&di, sizeof(double) * 3 * n, h->stream));
+  CK(cudaMallocAsync(&dj, sizeof(double) * 3 * n, h->stream));
   CK(cudaMemcpyAsync(di, xyz_i, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(dj, xyz_j, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * 2, h->stream));
   RowBlock rb{};
-  int rc = alloc_block(rb, n, 16);
+  int rc = alloc_block(h, rb, n, 16);
   if (rc) return rc;
   const int nb = (int)std::min<long long>((n + 127) / 128, 4096);
   k_fdi_pair_rows<<<nb, 128, 0, h->stream>>>(h->g, n, di, dj, weight, rb, h->status);
@@ -798,10 +833,10 @@ int lsb200_add_pair_rows(lsb200_handle h, int64_t n, const double* xyz_i, const 
   unsigned long long st[2];
   CK(cudaMemcpyAsync(st, h->status, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  cudaFree(di);
-  cudaFree(dj);
+  pool_free(h, di);
+  pool_free(h, dj);
   if (st[1]) {
-    free_block(rb);
+    free_block(h, rb);
     return fail(LSB200_ERR_ARG, "an interface pair spans planes outside the owned + halo planes [%d,%d) of this slab", h->g.k0 - HALO, h->g.k1 + HALO);
   }
   if (n_rows_out) *n_rows_out = (int64_t)st[0];
@@ -815,8 +850,9 @@ int lsb200_clear_rows(lsb200_handle h) {
   if (!h) return fail(LSB200_ERR_ARG, "null handle");
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
-  for (RowBlock& rb : h->pending) free_block(rb);
-  for (RowBlock& rb : h->blocks) free_block(rb);
+  for (RowBlock& rb : h->pending) free_block(h, rb);
+  for (RowBlock& rb : h->blocks) free_block(h, rb);
+  free_transposes(h);
   h->pending.clear();
   h->blocks.clear();
   h->rows_kept = 0;
@@ -848,7 +884,7 @@ static int merge_blocks(lsb200_ctx* h) {
       continue;
     }
     RowBlock m{};
-    int rc = alloc_block(m, n, k);
+    int rc = alloc_block(h, m, n, k);
     if (rc) return rc;
     long long off = 0;
     for (RowBlock& rb : all) {
@@ -863,8 +899,68 @@ static int merge_blocks(lsb200_ctx* h) {
     }
     CK(cudaStreamSynchronize(h->stream));
     for (RowBlock& rb : all)
-      if (rb.k == k) free_block(rb);
+      if (rb.k == k) free_block(h, rb);
     h->blocks.push_back(m);
+  }
+  return 0;
+}
+
+static void free_transposes(lsb200_ctx* h) {
+  for (RowTranspose& t : h->transposes) {
+    pool_free(h, t.node); pool_free(h, t.off); pool_free(h, t.entry); pool_free(h, t.t);
+  }
+  h->transposes.clear();
+}
+
+// node-major view of every block: stable radix sort of (node, row) keys, run-length encode, scan
+static int build_transposes(lsb200_ctx* h) {
+  free_transposes(h);
+  for (const RowBlock& rb : h->blocks) {
+    RowTranspose tr{};
+    const long long E = rb.n * rb.k;
+    if (E == 0) { h->transposes.push_back(tr); continue; }
+    if (E >= 2147483647LL) return fail(LSB200_ERR_ARG, "deterministic mode: block of %lld entries is too large", E);
+    unsigned long long *k_in = nullptr, *k_out = nullptr;
+    int *v_in = nullptr, *nodes = nullptr, *counts = nullptr, *nruns = nullptr;
+    CK(cudaMallocAsync(&k_in, sizeof(unsigned long long) * E, h->stream));
+    CK(cudaMallocAsync(&k_out, sizeof(unsigned long long) * E, h->stream));
+    CK(cudaMallocAsync(&v_in, sizeof(int) * E, h->stream));
+    CK(cudaMallocAsync(&tr.entry, sizeof(int) * E, h->stream));
+    CK(cudaMallocAsync(&nodes, sizeof(int) * E, h->stream));
+    CK(cudaMallocAsync(&tr.node, sizeof(int) * E, h->stream));
+    CK(cudaMallocAsync(&counts, sizeof(int) * (E + 1), h->stream));
+    CK(cudaMallocAsync(&tr.off, sizeof(int) * (E + 2), h->stream));
+    CK(cudaMallocAsync(&nruns, sizeof(int), h->stream));
+    CK(cudaMallocAsync(&tr.t, sizeof(double) * rb.n, h->stream));
+    const int nb = (int)std::min<long long>((E + 255) / 256, 4096);
+    k_rows_keys<<<nb, 256, 0, h->stream>>>(rb, k_in, v_in);
+    CKL();
+    size_t tmp_bytes = 0, need = 0;
+    void* tmp = nullptr;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, k_in, k_out, v_in, tr.entry, (int)E, 0, 64, h->stream);
+    tmp_bytes = need;
+    cub::DeviceRunLengthEncode::Encode(nullptr, need, nodes, tr.node, counts, nruns, (int)E, h->stream);
+    tmp_bytes = std::max(tmp_bytes, need);
+    cub::DeviceScan::ExclusiveSum(nullptr, need, counts, tr.off, (int)E + 1, h->stream);
+    tmp_bytes = std::max(tmp_bytes, need);
+    CK(cudaMallocAsync(&tmp, tmp_bytes, h->stream));
+    CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, tr.entry, (int)E, 0, 64, h->stream));
+    k_rows_node_of_key<<<nb, 256, 0, h->stream>>>(E, k_out, nodes);
+    CKL();
+    CK(cub::DeviceRunLengthEncode::Encode(tmp, tmp_bytes, nodes, tr.node, counts, nruns, (int)E, h->stream));
+    int runs = 0;
+    CK(cudaMemcpyAsync(&runs, nruns, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemsetAsync(counts + runs, 0, sizeof(int), h->stream));
+    CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, tr.off, runs + 1, h->stream));
+    // the padding run (node -1) sorts last: drop it
+    int last_node = 0;
+    if (runs > 0) CK(cudaMemcpyAsync(&last_node, tr.node + runs - 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    tr.n_nodes = (runs > 0 && last_node < 0) ? runs - 1 : runs;
+    h->launches += 5;
+    pool_free(h, k_in); pool_free(h, k_out); pool_free(h, v_in); pool_free(h, nodes); pool_free(h, counts); pool_free(h, nruns); pool_free(h, tmp);
+    h->transposes.push_back(tr);
   }
   return 0;
 }
@@ -897,13 +993,28 @@ int lsb200_finalize_system(lsb200_handle h) {
     CKL();
     h->launches++;
   }
-  for (const RowBlock& rb : h->blocks) {
+  if (h->deterministic) {
+    if ((rc = build_transposes(h))) return rc;
+  } else {
+    free_transposes(h);
+  }
+  for (size_t bi = 0; bi < h->blocks.size(); ++bi) {
+    const RowBlock& rb = h->blocks[bi];
     if (rb.n == 0) continue;
-    const int nb = (int)std::min<long long>((rb.n + 255) / 256, 8192);
-    k_rows_rhs<<<nb, 256, 0, h->stream>>>(h->g, rb, h->rhs);
-    CKL();
-    k_rows_diag<<<nb, 256, 0, h->stream>>>(h->g, rb, h->diag);
-    CKL();
+    if (h->deterministic) {
+      const RowTranspose& tr = h->transposes[bi];
+      const int ng = std::max(1, std::min((tr.n_nodes + 255) / 256, h->sm_count * 16));
+      k_rows_gather<<<ng, 256, 0, h->stream>>>(h->g, rb, tr, h->rhs, 1, h->sc, 0);
+      CKL();
+      k_rows_gather<<<ng, 256, 0, h->stream>>>(h->g, rb, tr, h->diag, 2, h->sc, 0);
+      CKL();
+    } else {
+      const int nb = (int)std::min<long long>((rb.n + 255) / 256, 8192);
+      k_rows_rhs<<<nb, 256, 0, h->stream>>>(h->g, rb, h->rhs);
+      CKL();
+      k_rows_diag<<<nb, 256, 0, h->stream>>>(h->g, rb, h->diag);
+      CKL();
+    }
     h->launches += 2;
   }
   if (h->apply_scaling) {
@@ -1022,10 +1133,31 @@ static int enqueue_iteration(lsb200_ctx* h) {
   const long long n = h->g.nloc;
   const double* s2 = h->apply_scaling ? owned_ptr(h, h->s2) : nullptr;
   int rc;
-  k_cg_update_p<VEC_NT><<<vec_blocks(h, n), VEC_NT, 0, h->stream>>>(n, s2, owned_ptr(h, h->r), owned_ptr(h, h->p), h->sc);
-  CKL();
-  h->launches++;
-  if ((rc = halo_exchange(h, h->p))) return rc;
+  const long long edge = (long long)HALO * h->g.plane;
+  if (h->nranks > 1 && h->overlap_shells && h->g.nzl >= 3 * HALO && h->g.plane % 2 == 0) {  // even: double2 alignment
+    // z slabs: update the two planes at either end first, ship them to the neighbours on the communication
+    // stream, and update the planes in between while they travel
+    auto upd = [&](long long off, long long cnt) {
+      k_cg_update_p<VEC_NT><<<vec_blocks(h, cnt), VEC_NT, 0, h->stream>>>(cnt, s2 ? s2 + off : nullptr, owned_ptr(h, h->r) + off,
+                                                                          owned_ptr(h, h->p) + off, h->sc);
+      h->launches++;
+    };
+    upd(0, edge);
+    upd(n - edge, edge);
+    CKL();
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    CK(cudaStreamWaitEvent(h->side[1], h->ev_fork, 0));
+    if ((rc = halo_exchange(h, h->p, h->side[1]))) return rc;
+    CK(cudaEventRecord(h->ev_join[1], h->side[1]));
+    upd(edge, n - 2 * edge);
+    CKL();
+    CK(cudaStreamWaitEvent(h->stream, h->ev_join[1], 0));
+  } else {
+    k_cg_update_p<VEC_NT><<<vec_blocks(h, n), VEC_NT, 0, h->stream>>>(n, s2, owned_ptr(h, h->r), owned_ptr(h, h->p), h->sc);
+    CKL();
+    h->launches++;
+    if ((rc = halo_exchange(h, h->p))) return rc;
+  }
   if ((rc = apply_normal_dev(h, h->p, h->q, 3, 1))) return rc;
   if (h->nranks > 1) {
     k_cg_pack_pq<<<1, 1, 0, h->stream>>>(h->sc);
@@ -1248,8 +1380,8 @@ static int eval_host(lsb200_ctx* h, int64_t n, const double* xyz, double* out, b
   const int64_t chunk = std::min<int64_t>(n, 1 << 24);
   const int ow = grad ? 3 : 1;
   double *dx = nullptr, *dout = nullptr;
-  CK(cudaMalloc(&dx, sizeof(double) * 3 * chunk));
-  CK(cudaMalloc(&dout, sizeof(double) * ow * chunk));
+  CK(cudaMallocAsync(&dx, sizeof(double) * 3 * chunk, h->stream));
+  CK(cudaMallocAsync(&dout, sizeof(double) * ow * chunk, h->stream));
   int rc = 0;
   for (int64_t o = 0; o < n && !rc; o += chunk) {
     const int64_t m = std::min<int64_t>(chunk, n - o);
@@ -1259,8 +1391,8 @@ static int eval_host(lsb200_ctx* h, int64_t n, const double* xyz, double* out, b
     CK(cudaMemcpyAsync(out + ow * o, dout, sizeof(double) * ow * m, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
-  cudaFree(dx);
-  cudaFree(dout);
+  pool_free(h, dx);
+  pool_free(h, dout);
   return rc;
 }
 
@@ -1309,7 +1441,19 @@ int lsb200_time_kernel(lsb200_handle h, int which, int reps, double* seconds_per
     CK(cudaMemcpyAsync(h->sc, h->sc_host, sizeof(CgScalars), cudaMemcpyHostToDevice, h->stream));
     if (which == 0) rc = launch_regularisation(h, h->p, h->q, 1);
     else if (which == 1) rc = enqueue_iteration(h);
-    else rc = launch_rows(h, h->p, h->q, 1);
+    else if (which == 2) rc = launch_rows(h, h->p, h->q, 1);
+    else if (which == 3 || which == 4) {
+      const long long n = h->g.nloc;
+      const double* s2 = h->apply_scaling ? owned_ptr(h, h->s2) : nullptr;
+      if (which == 3)
+        k_cg_update_xr<VEC_NT><<<vec_blocks(h, n), VEC_NT, 0, h->stream>>>(n, owned_ptr(h, h->p), owned_ptr(h, h->q), owned_ptr(h, h->x),
+                                                                            owned_ptr(h, h->r), s2, h->partials + 2 * MAX_PARTIALS,
+                                                                            h->counters + 2, h->sc);
+      else
+        k_cg_update_p<VEC_NT><<<vec_blocks(h, n), VEC_NT, 0, h->stream>>>(n, s2, owned_ptr(h, h->r), owned_ptr(h, h->p), h->sc);
+      CKL();
+      h->launches++;
+    } else return fail(LSB200_ERR_ARG, "unknown kernel selector %d", which);
     if (rc) return rc;
   }
   CK(cudaEventRecord(e1, h->stream));

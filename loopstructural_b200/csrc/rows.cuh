@@ -348,4 +348,96 @@ __global__ void k_fdi_pair_rows(const GridDesc g, const long long n, const doubl
   }
 }
 
+// ---- deterministic application of the data rows (lsb200_set_options(..., deterministic = 1)) -----------------
+// The atomics of k_rows_normal / k_rows_rhs / k_rows_diag add in arrival order, so two solves of the same system
+// differ in the last bits (and, on ill-conditioned systems, by an iteration).  RowTranspose is the node-major view
+// of one ELL block, built once per finalize by a stable radix sort of (node, row) keys: entries [off[u], off[u+1])
+// of `entry` belong to node `node[u]`, ordered by row.  Then  t = W A p  is one pass over the rows and
+// q += A^T t  one pass over the touched nodes, every sum in a fixed order and no atomics.
+struct RowTranspose {
+  int n_nodes;         // touched nodes
+  int* node;           // [n_nodes] storage index
+  int* off;            // [n_nodes + 1] segment offsets into entry
+  int* entry;          // [valid entries] ELL entry index e = j * n + r
+  double* t;           // [n rows] scratch: w^2 (a . p)
+};
+
+__global__ void k_rows_keys(const RowBlock rb, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+  const long long E = rb.n * rb.k;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
+    const int c = rb.cols[e];
+    const unsigned long long r = (unsigned long long)(e % rb.n);
+    keys[e] = c < 0 ? ~0ull : (((unsigned long long)(unsigned int)c << 32) | r);  // padding sorts to the end
+    vals[e] = (int)e;
+  }
+}
+__global__ void k_rows_node_of_key(const long long n, const unsigned long long* __restrict__ keys, int* __restrict__ nodes) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    nodes[e] = keys[e] == ~0ull ? -1 : (int)(keys[e] >> 32);
+}
+
+// t_r = w_r^2 (a_r . p); pq part = sum_r t_r (a_r . p) restricted to owned columns, as k_rows_normal counts it
+template <int NT>
+__global__ void __launch_bounds__(NT)
+    k_rows_t(const GridDesc g, const RowBlock rb, const RowTranspose tr, const double* __restrict__ p,
+             double* __restrict__ partials, unsigned int* __restrict__ counter, CgScalars* __restrict__ sc,
+             const int cg_mode, const int first) {
+  __shared__ double red[NT / 32];
+  if (cg_mode && sc->done) return;
+  double dot = 0.0;
+  for (long long r = blockIdx.x * (long long)NT + threadIdx.x; r < rb.n; r += (long long)gridDim.x * NT) {
+    double t = 0.0, town = 0.0;
+    for (int j = 0; j < rb.k; ++j) {
+      const int c = rb.cols[j * rb.n + r];
+      if (c >= 0) {
+        const double v = rb.vals[j * rb.n + r] * p[c];
+        t += v;
+        if (owned(g, c)) town += v;
+      }
+    }
+    t *= rb.w2[r];
+    tr.t[r] = t;
+    dot += town * t;
+  }
+  const double bsum = block_sum<NT>(dot, red);
+  double total;
+  if (grid_sum_last_block<NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total))
+    sc->pq_part[1] = first ? total : sc->pq_part[1] + total;
+}
+
+// mode 0: q[node] += sum_e a_e t_row(e);  mode 1: rhs[node] += sum_e a_e w_r^2 b_r;
+// mode 2: diag[node] += sum_rows w_r^2 (sum of the row's entries on this node)^2  (entries of a node are ordered by row)
+__global__ void k_rows_gather(const GridDesc g, const RowBlock rb, const RowTranspose tr, double* __restrict__ out,
+                              const int mode, const CgScalars* __restrict__ sc, const int cg_mode) {
+  if (cg_mode && sc->done) return;
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < tr.n_nodes; u += gridDim.x * blockDim.x) {
+    const int node = tr.node[u];
+    if (!owned(g, node)) continue;
+    double acc = 0.0;
+    if (mode == 2) {
+      long long prev = -1;
+      double s = 0.0, w2 = 0.0;
+      for (int t = tr.off[u]; t < tr.off[u + 1]; ++t) {
+        const int e = tr.entry[t];
+        const long long r = e % rb.n;
+        if (r != prev) {
+          acc += w2 * s * s;
+          s = 0.0;
+          w2 = rb.w2[r];
+          prev = r;
+        }
+        s += rb.vals[e];
+      }
+      acc += w2 * s * s;
+    } else {
+      for (int t = tr.off[u]; t < tr.off[u + 1]; ++t) {
+        const int e = tr.entry[t];
+        const long long r = e % rb.n;
+        acc += rb.vals[e] * (mode == 0 ? tr.t[r] : rb.w2[r] * rb.b[r]);
+      }
+    }
+    out[node] += acc;
+  }
+}
+
 }  // namespace lsb

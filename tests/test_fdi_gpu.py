@@ -402,3 +402,45 @@ def test_full_size_solve_properties():
     cosang = np.sum(g * gradient[:2000, 3:6], axis=1) / (np.linalg.norm(g, axis=1) * np.linalg.norm(gradient[:2000, 3:6], axis=1))
     assert np.median(cosang) > 0.95
     it.close()
+
+
+def test_deterministic_mode_is_bitwise_repeatable_and_matches():
+    """set_options(deterministic=True): the data rows are applied through the node-major transpose (stable sort,
+    fixed-order sums, no atomics).  Two solves give identical bits; the answer matches the reference like the
+    atomic path does; rhs / diagonal / operator agree with it to rounding."""
+    z = np.load(os.path.join(GOLDEN, "fdi_solve_aniso.npz"))
+    grid, weights, fams, rtol, atol = H.solve_case(z)
+    runs = []
+    for det in (True, True, False):
+        e = H.engine_for(grid, weights)
+        e.set_options(apply_scaling=bool(z["scaling"]), deterministic=det)
+        H.add_point_data(e, z, weights)
+        c, res = e.solve_cg(rtol=rtol, atol=atol)
+        runs.append((c, res.iterations, e.rhs(), e.diagonal(), e.apply_normal(z["c"], parts=2)))
+        e.close()
+    (c1, it1, rhs1, d1, q1), (c2, it2, rhs2, d2, q2), (c3, it3, rhs3, d3, q3) = runs
+    assert it1 == it2 and np.array_equal(c1, c2) and np.array_equal(rhs1, rhs2) and np.array_equal(d1, d2) and np.array_equal(q1, q2)
+    rng_ = float(z["c"].max() - z["c"].min())
+    assert np.linalg.norm(c1 - z["c"]) / np.sqrt(c1.size) / rng_ <= 1e-6 and abs(it1 - int(z["iterations"])) <= 1
+    for a, b in ((rhs1, rhs3), (d1, d3), (q1, q3)):
+        assert np.abs(a - b).max() <= 1e-13 * max(np.abs(b).max(), 1.0)
+
+
+def test_deterministic_mode_with_interface_and_generic_rows():
+    """Width-16 rows with duplicate columns (interface) through the transpose: diagonal merges duplicates per row."""
+    z = np.load(os.path.join(GOLDEN, "fdi_rows_a.npz"))
+    grid = fo.Grid.from_cells(z["ncells"], z["origin"], z["step"])
+    kw = H.weights_of(z, "kw_keys", "kw_vals")
+    out = []
+    for det in (True, False):
+        e = H.engine_for(grid, dict.fromkeys(("dxx", "dyy", "dzz", "dxy", "dyz", "dxz", "dx", "dy", "dz"), 0.0))
+        e.set_options(add_ridge=False, apply_scaling=False, deterministic=det)
+        from loopstructural_b200 import engine as en
+        e.add_interface_rows(z["interface"], kw["ipw"])
+        e.add_point_rows(en.ROWS_VALUE, z["value"], kw["cpw"])
+        e.add_point_rows(en.ROWS_NORMAL, z["normal"], kw["npw"])
+        p = np.random.default_rng(5).standard_normal(grid.n_nodes)
+        out.append((e.apply_normal(p, parts=2), e.diagonal(), e.rhs()))
+        e.close()
+    for a, b in zip(*out):
+        assert np.abs(a - b).max() <= 1e-12 * max(np.abs(b).max(), 1.0)
