@@ -251,13 +251,14 @@ static void plan_main(lsb200_ctx* h) {
   const char* czenv = getenv("LSB200_STENCIL_CZ");
   const int czo = (czenv && atoi(czenv) > 0) ? atoi(czenv) : 0;
   auto chunks = [&](int n, int cz) { return n > 0 ? (n + cz - 1) / cz : 0; };
-  // main / box
-  h->box_z0 = box ? std::max(g.k0, 3) : g.k0;
-  h->box_z1 = box ? std::min(g.k1, g.nz - 3) : g.k1;
-  const int nzm = std::max(0, h->box_z1 - h->box_z0);
-  const int tiles_x = ((box ? g.nx - 8 : g.nx) + 63) / 64, tiles_y = (g.ny - 6 + ty - 1) / ty;
-  h->main_cz = czo ? czo : pick_cz(h, nzm, (long long)tiles_x * tiles_y, (long long)h->sm_count * minb);
-  h->main_grid = dim3(tiles_x, tiles_y, chunks(nzm, h->main_cz));
+  // box: z chunks over ALL owned planes; a chunk that touches a z face (ka < 3 or kb > nz-3) runs the z-general
+  // variant (k_fdi_box<..., ZGEN>), the others the uniform one
+  h->box_z0 = g.k0;
+  h->box_z1 = g.k1;
+  const int tiles_x = (g.nx - 8 + 63) / 64, tiles_y = (g.ny - 6 + ty - 1) / ty;
+  h->main_cz = czo ? czo : pick_cz(h, g.nzl, (long long)tiles_x * tiles_y, (long long)h->sm_count * minb);
+  h->main_cz = std::min(std::max(h->main_cz, 3), BOX_ZGEN_MAX_STEPS - 2 * HALO);  // a face chunk covers planes 0..2 / nz-3..nz-1
+  h->main_grid = dim3(tiles_x, tiles_y, chunks(g.nzl, h->main_cz));
   if ((long long)h->main_grid.x * h->main_grid.y * h->main_grid.z > MAX_PARTIALS) return;
   { const char* e = getenv("LSB200_SHELL_CZ"); h->shell_cz = (e && atoi(e) > 0) ? atoi(e) : 0; }
   if (!h->ztab) {
@@ -280,6 +281,11 @@ static UniConsts make_uni_consts(const StencilWeights& w) {
   U.kz = w.azz * (1.0 / 6.0) - 2.0 * (w.bxz + w.byz);
   U.bxz = w.bxz; U.byz = w.byz;
   U.zt1 = w.azz * (-2.0 / 3.0);
+  U.cxy = w.axx + w.ayy + 4.0 * w.bxy;
+  U.cx2xy = w.axx * (1.0 / 6.0) - 2.0 * w.bxy;
+  U.cy2xy = w.ayy * (1.0 / 6.0) - 2.0 * w.bxy;
+  U.g0 = 2.0 * (w.bxz + w.byz);
+  U.azz = w.azz; U.dz = w.dz; U.ridge2 = w.ridge2;
   return U;
 }
 
@@ -316,27 +322,59 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
       CK(cudaEventRecord(h->ev_fork, h->stream));
       CK(cudaStreamWaitEvent(h->side[0], h->ev_fork, 0));
     }
-    if (h->main_grid.z > 0) {
+    {
       const UniConsts U = make_uni_consts(w);
+      const int cz = h->main_cz;
+      // output planes of the z-general launch (next to the z faces this handle owns) and of the uniform launch
+      const bool lo_face = g.k0 < 3, hi_face = g.k1 > g.nz - 3;
+      // short face ranges: the z-general variant is ~1.3x slower per plane, and 3 of its planes are needed anyway
+      static const int zface = (getenv("LSB200_ZFACE") && atoi(getenv("LSB200_ZFACE")) >= 3) ? atoi(getenv("LSB200_ZFACE")) : 8;
+      const int zc = std::min(cz, zface);
+      int zl = lo_face ? std::min(g.k1, g.k0 + zc) : g.k0;
+      int zh = hi_face ? std::max(zl, g.k1 - zc) : g.k1;
+      int za0 = 0, za1 = 0, zb0 = 0, zb1 = 0;
+      if (lo_face) { za0 = g.k0; za1 = zl; }
+      if (hi_face && zh < g.k1) { zb0 = zh; zb1 = g.k1; }
+      const int ulo = zl, uhi = std::max(zl, zh);
+      const bool zfirst = za1 > za0, zlast = zb1 > zb0;
+      const int nuni = (uhi - ulo + cz - 1) / cz;
+      const bool have_z = zfirst || zlast;
+      if (have_z && ov) CK(cudaStreamWaitEvent(h->side[2], h->ev_fork, 0));
+      cudaStream_t zs = (have_z && ov) ? h->side[2] : h->stream;
+      double* zpart = h->partials + 4 * (size_t)MAX_PARTIALS;
+      unsigned int* zcnt = h->counters + 4;
+      const dim3 ugrid(h->main_grid.x, h->main_grid.y, nuni), zgrid(h->main_grid.x, h->main_grid.y, 2);
       switch (h->main_cfg) {
 #define X(ID, YB, TYT, ST, MINB)                                                                                  \
   case ID: {                                                                                                      \
     const size_t smem = sizeof(double) * MainCfg<YB, TYT, ST>::PLANE * ST;                                        \
     if (vec16) {                                                                                                  \
-      auto kern = k_fdi_box<YB, TYT, ST, MINB, true>;                                                             \
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
-      kern<<<h->main_grid, dim3(32, TYT), smem, h->stream>>>(g, U, p, q, h->main_cz, h->box_z0, h->box_z1, part, cnt, h->sc, cg_mode); \
+      auto ku = k_fdi_box<YB, TYT, ST, MINB, true, false>;                                                        \
+      auto kz = k_fdi_box<YB, TYT, ST, MINB, true, true>;                                                         \
+      cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
+      cudaFuncSetAttribute(kz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
+      if (ugrid.z > 0) ku<<<ugrid, dim3(32, TYT), smem, h->stream>>>(g, U, p, q, cz, ulo, uhi, 0, 0, h->ztab, part, cnt, h->sc, cg_mode); \
+      if (have_z) kz<<<zgrid, dim3(32, TYT), smem, zs>>>(g, U, p, q, cz, za0, za1, zb0, zb1, h->ztab, zpart, zcnt, h->sc, cg_mode);      \
     } else {                                                                                                      \
-      auto kern = k_fdi_box<YB, TYT, ST, MINB, false>;                                                            \
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
-      kern<<<h->main_grid, dim3(32, TYT), smem, h->stream>>>(g, U, p, q, h->main_cz, h->box_z0, h->box_z1, part, cnt, h->sc, cg_mode); \
+      auto ku = k_fdi_box<YB, TYT, ST, MINB, false, false>;                                                       \
+      auto kz = k_fdi_box<YB, TYT, ST, MINB, false, true>;                                                        \
+      cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
+      cudaFuncSetAttribute(kz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
+      if (ugrid.z > 0) ku<<<ugrid, dim3(32, TYT), smem, h->stream>>>(g, U, p, q, cz, ulo, uhi, 0, 0, h->ztab, part, cnt, h->sc, cg_mode); \
+      if (have_z) kz<<<zgrid, dim3(32, TYT), smem, zs>>>(g, U, p, q, cz, za0, za1, zb0, zb1, h->ztab, zpart, zcnt, h->sc, cg_mode);      \
     }                                                                                                             \
   } break;
         LSB_BOX_CFGS(X)
 #undef X
       }
       CKL();
-      h->launches++;
+      h->launches += (ugrid.z > 0 ? 1 : 0) + (have_z ? 1 : 0);
+      if (ugrid.z == 0) CK(cudaMemsetAsync(&h->sc->pq_part[0], 0, sizeof(double), h->stream));
+      if (!have_z) CK(cudaMemsetAsync(&h->sc->pq_part[3], 0, sizeof(double), h->stream));
+      if (have_z && ov) {
+        CK(cudaEventRecord(h->ev_join[2], h->side[2]));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_join[2], 0));
+      }
     }
     // everything outside the box: one gather launch on a side stream, overlapped with the box kernel
     // (LSB200_SHELL=0 leaves it out: profiling of the box kernel alone, results are then incomplete)
@@ -345,7 +383,7 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
       ShellBox sb;
       sb.ilo = box ? 4 : 0; sb.ihi = box ? g.nx - 4 : g.nx;
       sb.jlo = 3; sb.jhi = g.ny - 3;
-      sb.klo = h->box_z0; sb.khi = std::max(h->box_z0, h->box_z1);
+      sb.klo = g.k0; sb.khi = g.k1;  // the ring columns over every owned plane; the z faces belong to k_fdi_box<ZGEN>
       const int nzm = sb.khi - sb.klo;
       constexpr int SNT = 128;
       sb.ring_cols = (g.ny - (sb.jhi - sb.jlo)) * g.nx + (sb.jhi - sb.jlo) * (g.nx - (sb.ihi - sb.ilo));

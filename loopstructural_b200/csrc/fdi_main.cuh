@@ -34,6 +34,25 @@ struct UniConsts {
   double bxy;        // the four (+-2, +-2, 0) corners
   double kz, bxz, byz;  // plane kp+-2: kz p + bxz (p(i-2)+p(i+2)) + byz (p(j-2)+p(j+2)),  kz = azz/6 - 2 (bxz + byz)
   double zt1;        // plane kp+-1: -2 azz/3
+  // z-general variant (chunks that touch a z face): the x/y part alone and the raw weights
+  double cxy;        // centre of the xy part: axx + ayy + 4 bxy
+  double cx2xy, cy2xy;  // x / y taps +-2 of the xy part: axx/6 - 2 bxy, ayy/6 - 2 bxy
+  double g0;         // 2 (bxz + byz): centre of G = bxz C_x p + byz C_y p
+  double azz, dz, ridge2;
+};
+
+// per-plane z coefficients (shell_fill_z_table), 16 doubles per GLOBAL plane k: [0..4] T_z taps -2..2 (1/6 included),
+// [5..9] B_z taps (1/6 included), [10..12] C_z taps -2,0,+2, [13] m_z(k)
+constexpr int SHELL_ZSTRIDE = 16;
+
+// z coefficients of one incoming plane kp in the z-general variant, from the per-plane table:
+// what plane kp contributes to the output planes kp-2 .. kp+2 through the z line L = azz T_z + dz B_z and C_z
+constexpr int BOX_ZGEN_MAX_STEPS = 160;  // a z-general chunk has at most 156 output planes (+ 4 halo steps)
+struct ZStep {
+  double mz;                      // m_z(kp): mask of the xy part of output plane kp
+  double l0, c0;                  // L(kp, 0), C_z(kp, 0)
+  double lm1, lp1;                // L(kp-1, +1), L(kp+1, -1)
+  double lm2, cm2, lp2, cp2;      // L(kp-2, +2), C_z(kp-2, +2), L(kp+2, -2), C_z(kp+2, -2)
 };
 
 template <int YB, int TYT, int ST>
@@ -104,6 +123,51 @@ __device__ __forceinline__ void uni_plane_fast(const double* __restrict__ Sc, co
   }
 }
 
+// z-general twin of uni_plane_fast for the chunks next to a z face: same x/y taps (columns and rows are interior),
+// z coefficients of this step in Z.  25 fp64 operations per node.
+template <int YB, int SX>
+__device__ __forceinline__ void zgen_plane_fast(const double* __restrict__ Sc, const UniConsts& K, const ZStep& Z,
+                                                double (&Am2)[YB][2], double (&Am1)[YB][2], double (&A0)[YB][2],
+                                                double (&Ap1)[YB][2], double (&Ap2)[YB][2]) {
+  constexpr int NR = YB + 4;
+  double pc[NR][2], h2[NR][2], xl[YB][2];
+#pragma unroll
+  for (int rr = 0; rr < NR; ++rr) {
+    const double2 a = lds2(Sc + rr * SX), b = lds2(Sc + rr * SX + 2), c = lds2(Sc + rr * SX + 4);
+    h2[rr][0] = a.x + c.x;
+    h2[rr][1] = a.y + c.y;
+    pc[rr][0] = b.x;
+    pc[rr][1] = b.y;
+    if (rr >= 2 && rr < YB + 2) {
+      xl[rr - 2][0] = fma(K.cx2xy, h2[rr][0], fma(K.cx1, a.y + b.y, K.cxy * b.x));
+      xl[rr - 2][1] = fma(K.cx2xy, h2[rr][1], fma(K.cx1, b.x + c.x, K.cxy * b.y));
+    }
+  }
+  const double cen = K.ridge2 + Z.l0;
+#pragma unroll
+  for (int r = 0; r < YB; ++r) {
+    const int rr = r + 2;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const double p0 = pc[rr][e];
+      const double sy1 = pc[rr - 1][e] + pc[rr + 1][e];
+      const double sy2 = pc[rr - 2][e] + pc[rr + 2][e];
+      const double cs = h2[rr - 2][e] + h2[rr + 2][e];
+      double xy = fma(K.cy1, sy1, xl[r][e]);
+      xy = fma(K.cy2xy, sy2, xy);
+      xy = fma(K.bxy, cs, xy);
+      const double G = fma(-K.byz, sy2, fma(-K.bxz, h2[rr][e], K.g0 * p0));  // (bxz C_x + byz C_y) p
+      double s = fma(Z.mz, xy, A0[r][e]);
+      s = fma(cen, p0, s);
+      A0[r][e] = fma(Z.c0, G, s);
+      Am1[r][e] = fma(Z.lm1, p0, Am1[r][e]);
+      Ap1[r][e] = fma(Z.lp1, p0, Ap1[r][e]);
+      Am2[r][e] = fma(Z.cm2, G, fma(Z.lm2, p0, Am2[r][e]));
+      Ap2[r][e] = fma(Z.cp2, G, fma(Z.lp2, p0, Ap2[r][e]));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_fdi_box: the interior box 4 <= i <= nx-5, 3 <= j <= ny-4, 3 <= k <= nz-4 only.  Every input plane is a
 // real plane, every coefficient a launch constant: no ghost mapping, no masks, no general path.  Everything
@@ -111,23 +175,28 @@ __device__ __forceinline__ void uni_plane_fast(const double* __restrict__ Sc, co
 // (A persistent-CTA variant with an equal split of the (tile, plane) list was measured and dropped: it loses the
 // L2 sharing of the tile halos between CTAs that march through the same planes together -- 573 us instead
 // of 375 us at 512^3, profiles/r01h.)
-template <int YB, int TYT, int ST, int MINB, bool VEC16>
+// ZGEN = true: the launch for the (at most two) chunks that touch a z face: blockIdx.z = 0 -> output planes [zlo,zhi),
+// 1 -> [zlo2,zhi2); z coefficients per plane from ztab, planes outside the grid are skipped.  Its p.q goes to
+// pq_part[3], its partial sums to its own slot.
+template <int YB, int TYT, int ST, int MINB, bool VEC16, bool ZGEN>
 __global__ void __launch_bounds__(32 * TYT, MINB)
     k_fdi_box(const GridDesc g, const UniConsts U, const double* __restrict__ p, double* __restrict__ q, const int cz,
-              const int zlo, const int zhi, double* __restrict__ partials, unsigned int* __restrict__ counter,
-              CgScalars* __restrict__ sc, const int cg_mode) {
+              const int zlo, const int zhi, const int zlo2, const int zhi2, const double* __restrict__ ztab,
+              double* __restrict__ partials, unsigned int* __restrict__ counter, CgScalars* __restrict__ sc,
+              const int cg_mode) {
   using C = MainCfg<YB, TYT, ST>;
   static_assert(ST >= 5, "ring needs planes kp-2..kp plus at least two in flight");
   extern __shared__ __align__(16) double S[];
   __shared__ double red[C::NT / 32];
+  __shared__ ZStep zsm[ZGEN ? BOX_ZGEN_MAX_STEPS : 1];  // z coefficients of every plane step of this CTA (ZGEN)
 
   if (cg_mode && sc->done) return;
 
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int tid = tx + 32 * ty;
   const int x0 = C::X_FIRST + blockIdx.x * C::TX, y0 = C::Y_FIRST + blockIdx.y * C::TY;
-  const int ka = zlo + blockIdx.z * cz;
-  const int kb = min(ka + cz, zhi);
+  const int ka = ZGEN ? (blockIdx.z == 0 ? zlo : zlo2) : zlo + blockIdx.z * cz;
+  const int kb = ZGEN ? (blockIdx.z == 0 ? zhi : zhi2) : min(ka + cz, zhi);
   const int i0 = x0 + 2 * tx;
   const int j0 = y0 + YB * ty;
   const int nrows = max(0, min(YB, (g.ny - 3) - j0));
@@ -149,9 +218,11 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
   }
   // next plane to stage (input planes ka-2 .. kb+1 of this handle's storage)
   const double* src = p + (long long)(ka - HALO - g.k0 + HALO) * g.plane;
+  int kstage = ka - HALO;  // global index of that plane
   auto issue_plane = [&](double* dstS) {
+    const bool exists = !ZGEN || (kstage >= 0 && kstage < g.nz);
 #pragma unroll
-    for (int t = 0; t < LD; ++t) {
+    for (int t = 0; t < LD && exists; ++t) {
       const int idx = tid + t * C::NT;
       if (idx < NSLOT) {
         const bool ok = off[t] >= 0;
@@ -160,6 +231,7 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
       }
     }
     src += g.plane;
+    ++kstage;
   };
 
   double A[5][YB][2];
@@ -217,12 +289,43 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
     qdst += g.plane;
   };
 
+  // z coefficients of incoming plane k (ZGEN): rows k-2..k+2 of the per-plane table; a row outside the grid gives 0
+  auto zstep = [&](const int k) {
+    auto row = [&](const int ko, const int col) {
+      return (ko >= 0 && ko < g.nz) ? ztab[(long long)ko * SHELL_ZSTRIDE + col] : 0.0;
+    };
+    // L(ko, s) = azz T_z(ko, s) + dz B_z(ko, s), tap s = k - ko at column 2 + s (T) / 7 + s (B); C_z taps at 10,11,12
+    auto L = [&](const int ko) { return fma(U.azz, row(ko, 2 + (k - ko)), U.dz * row(ko, 7 + (k - ko))); };
+    ZStep Z;
+    Z.mz = row(k, 13);
+    Z.l0 = L(k);
+    Z.c0 = row(k, 11);
+    Z.lm1 = L(k - 1);
+    Z.lp1 = L(k + 1);
+    Z.lm2 = L(k - 2);
+    Z.cm2 = row(k - 2, 12);   // C_z(k-2, +2)
+    Z.lp2 = L(k + 2);
+    Z.cp2 = row(k + 2, 10);   // C_z(k+2, -2)
+    return Z;
+  };
+  if (ZGEN) {
+    for (int t = tid; t < kend - kstart && t < BOX_ZGEN_MAX_STEPS; t += C::NT) zsm[t] = zstep(kstart + t);
+    // visible after the barrier of the first advance_pipeline()
+  }
 #define LSB_BOX_STEP(PH)                                                                                      \
   {                                                                                                           \
     if (kp >= kend) break;                                                                                    \
     advance_pipeline();                                                                                       \
-    uni_plane_fast<YB, C::SX>(S + slot * C::PLANE + my_off, U, A[(PH + 0) % 5], A[(PH + 1) % 5],              \
-                              A[(PH + 2) % 5], A[(PH + 3) % 5], A[(PH + 4) % 5]);                             \
+    if (ZGEN) {                                                                                               \
+      if (kp >= 0 && kp < g.nz) {                                                                             \
+        const ZStep Z = zsm[kp - kstart];                                                                     \
+        zgen_plane_fast<YB, C::SX>(S + slot * C::PLANE + my_off, U, Z, A[(PH + 0) % 5], A[(PH + 1) % 5],      \
+                                   A[(PH + 2) % 5], A[(PH + 3) % 5], A[(PH + 4) % 5]);                        \
+      }                                                                                                       \
+    } else {                                                                                                  \
+      uni_plane_fast<YB, C::SX>(S + slot * C::PLANE + my_off, U, A[(PH + 0) % 5], A[(PH + 1) % 5],            \
+                                A[(PH + 2) % 5], A[(PH + 3) % 5], A[(PH + 4) % 5]);                           \
+    }                                                                                                         \
     store_out(A[(PH + 0) % 5]);                                                                               \
     _Pragma("unroll") for (int r = 0; r < YB; ++r) A[(PH + 0) % 5][r][0] = A[(PH + 0) % 5][r][1] = 0.0;       \
     slot = (slot + 1 == ST) ? 0 : slot + 1;                                                                   \
@@ -244,7 +347,7 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
   const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
   const unsigned int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
   double total;
-  if (grid_sum_last_block<C::NT>(bsum, partials, counter, nblocks, bid, red, &total)) sc->pq_part[0] = total;
+  if (grid_sum_last_block<C::NT>(bsum, partials, counter, nblocks, bid, red, &total)) sc->pq_part[ZGEN ? 3 : 0] = total;
 }
 
 }  // namespace lsb
@@ -276,7 +379,6 @@ struct ShellBox {
 
 // per-plane z coefficients, 16 doubles per GLOBAL plane k: [0..4] T_z taps -2..2 (1/6 included), [5..9] B_z taps
 // (1/6 included), [10..12] C_z taps -2,0,+2, [13] m_z(k)
-constexpr int SHELL_ZSTRIDE = 16;
 
 __device__ __forceinline__ double vrow(int r, int n) { return (r >= 1 && r <= n - 2) ? 1.0 : 0.0; }
 // coefficient of p(i+s) in B = sum_{r in {1,n-2}} d_r d_r^T / 6 (both rows are counted when n = 3, as the
