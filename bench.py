@@ -28,9 +28,10 @@ sys.path.insert(0, ROOT)
 METRIC = "fdi_cg_node_updates_per_second"
 UNIT = "dof-iter/s"
 BYTES_MATVEC_PER_DOF = 16.0      # read p, write q
-# dram__bytes_read.sum + dram__bytes_write.sum of one 256^3 matvec from ncu --set full
-# (profiles/r01y_matvec_full_details.csv: 143.4 + 80.2 MB for k_fdi_box, 25.8 + 0.4 MB for k_fdi_shell)
-TRAFFIC_MATVEC_256 = (143.39 + 80.18 + 25.84 + 0.41) * 1e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one 256^3 matvec from ncu --set full (profiles/r02c_matvec_full_details.csv:
+# 138.3 + 75.3 MB for the uniform k_fdi_box, 10.5 + 0.0 MB for its z-general launch, 21.4 + 0.1 MB for k_fdi_shell; the
+# writes that are still in L2 when a kernel ends are not counted by ncu)
+TRAFFIC_MATVEC_256 = (138.34 + 75.32 + 10.49 + 0.0 + 21.43 + 0.06) * 1e6
 BYTES_ITERATION_PER_DOF = 104.0  # matvec 16 + x/r update 48 (+8 scaling vector) + p update 24 (+8 scaling vector)
 
 
@@ -313,8 +314,8 @@ def run_ours(args):
                        "dof": dof_global},
             "solve_seconds": dev_s / max(args.steps, 1), "cg_iterations": iters_per_solve,
             "cg_iterations_per_second": its / dev_s if dev_s > 0 else None,
-            "roofline": {"bound": "hbm", "kernel": "FDI regularisation normal matvec = k_fdi_box + k_fdi_shell (one logical "
-                                                   "launch: interior box beside the boundary shell on a side stream)",
+            "roofline": {"bound": "hbm", "kernel": "FDI regularisation normal matvec = k_fdi_box (uniform) + k_fdi_box (z faces) + k_fdi_shell "
+                                                   "(x/y ring): one logical launch on three streams",
                          "achieved": ach,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": TRAFFIC_MATVEC_256 if n == 256 and world == 1 else None,
                          "seconds_per_launch": t_matvec, "bytes_per_dof": BYTES_MATVEC_PER_DOF},
@@ -322,7 +323,7 @@ def run_ours(args):
                                    "frac": ach_it / peak, "seconds_per_iteration": t_iter,
                                    "bytes_per_dof": BYTES_ITERATION_PER_DOF},
             "kernels": {  # every kernel of the iteration, CUDA events around 20 back-to-back launches each
-                "matvec k_fdi_box+k_fdi_shell": {"us": 1e6 * t_matvec, "bytes_per_dof": 16, "gbs": 16 * dof_local / t_matvec / 1e9},
+                "matvec k_fdi_box(+zgen)+k_fdi_shell": {"us": 1e6 * t_matvec, "bytes_per_dof": 16, "gbs": 16 * dof_local / t_matvec / 1e9},
                 "k_cg_update_xr": {"us": 1e6 * t_xr, "bytes_per_dof": 56, "gbs": 56 * dof_local / t_xr / 1e9},
                 "k_cg_update_p": {"us": 1e6 * t_p, "bytes_per_dof": 32, "gbs": 32 * dof_local / t_p / 1e9},
                 "k_rows_normal": {"us": 1e6 * t_rows, "rows": int(eng.num_rows)}},

@@ -295,8 +295,7 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
   double* part = h->partials;
   unsigned int* cnt = h->counters + 0;
   const bool vec16 = (g.pitch % 2) == 0;
-  Region full{0, 0, g.nx, 0, g.ny, g.k0, g.k1, 0, 0};
-#define LSB_LAUNCH_AT(STREAM, GRID, CZ, SLOT, RG, XB, TXT, TYT, MINB, ST)                                        \
+#define LSB_LAUNCH_AT(STREAM, GRID, CZ, SLOT, XB, TXT, TYT, MINB, ST)                                            \
   {                                                                                                              \
     const size_t smem = sizeof(double) * StencilCfg<XB, TXT, TYT, ST>::PLANE * ST;                               \
     double* part_ = h->partials + (size_t)(SLOT) * MAX_PARTIALS;                                                 \
@@ -304,16 +303,16 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
     if (vec16) {                                                                                                 \
       auto kern = k_fdi_normal<XB, TXT, TYT, MINB, ST, true>;                                                    \
       if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-      kern<<<GRID, dim3(TXT, TYT), smem, STREAM>>>(g, w, p, q, CZ, part_, cnt_, h->sc, cg_mode, RG);              \
+      kern<<<GRID, dim3(TXT, TYT), smem, STREAM>>>(g, w, p, q, CZ, part_, cnt_, h->sc, cg_mode);                  \
     } else {                                                                                                     \
       auto kern = k_fdi_normal<XB, TXT, TYT, MINB, ST, false>;                                                   \
       if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-      kern<<<GRID, dim3(TXT, TYT), smem, STREAM>>>(g, w, p, q, CZ, part_, cnt_, h->sc, cg_mode, RG);              \
+      kern<<<GRID, dim3(TXT, TYT), smem, STREAM>>>(g, w, p, q, CZ, part_, cnt_, h->sc, cg_mode);                  \
     }                                                                                                            \
     CKL();                                                                                                       \
     h->launches++;                                                                                               \
   }
-#define LSB_LAUNCH(XB, TXT, TYT, MINB, ST) LSB_LAUNCH_AT(h->stream, h->sgrid, h->cz, 0, full, XB, TXT, TYT, MINB, ST)
+#define LSB_LAUNCH(XB, TXT, TYT, MINB, ST) LSB_LAUNCH_AT(h->stream, h->sgrid, h->cz, 0, XB, TXT, TYT, MINB, ST)
   if (h->main_cfg >= 0) {
     const bool box = h->main_uni;
     const bool ov = h->overlap_shells;

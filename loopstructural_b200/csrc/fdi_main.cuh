@@ -1,11 +1,15 @@
 // K1, large grids: the FDI regularisation normal operator q = (R^T R + ridge^2 I) p split by region.
-//   k_fdi_box    the interior box 4 <= i <= nx-5, 3 <= j <= ny-4, 3 <= k <= nz-4 (92 % of a 256^3 grid, 98 % of a
-//                1024^3 one), where R^T R is the constant 25-tap composite kernel of
-//                LI/_finite_difference_interpolator.py:884-1050;
-//   k_fdi_shell  every other node, one thread per node in gather form with the true boundary operators
-//                (row masks of LC/supports/_3d_structured_grid.py:164-293, border families of
-//                LI/_finite_difference_interpolator.py:1052-1144), on a side stream beside the box kernel.
-// k_fdi_normal (fdi_stencil.cuh) stays the single-kernel path for grids too small to have a box.
+//   k_fdi_box<.., ZGEN=false>  the interior columns 4 <= i <= nx-5 and rows 3 <= j <= ny-4 of the planes
+//                3 <= k <= nz-4 (92 % of a 256^3 grid, 98 % of a 1024^3 one), where R^T R is the constant 25-tap
+//                composite kernel of LI/_finite_difference_interpolator.py:884-1050;
+//   k_fdi_box<.., ZGEN=true>   the same columns and rows of the (<= 8) planes next to a z face: same tiling and x/y
+//                taps, z coefficients per plane from a table (true boundary operators along z);
+//   k_fdi_shell  the ring of columns outside that x/y range, every plane: one thread per column marching along z,
+//                gather form with the true boundary operators (row masks of LC/supports/_3d_structured_grid.py:
+//                164-293, border families of LI/_finite_difference_interpolator.py:1052-1144).
+// The three launches write disjoint nodes and run on three streams (fork/join by events); their p.q parts are
+// summed by the CG update.  k_fdi_normal (fdi_stencil.cuh) stays the single-kernel path for grids too small to
+// have a box.
 //
 // Why: ncu of k_fdi_normal at 256^3 (profiles/r01b) shows 103-168 warp instructions and 40 fp64 operations per
 // 32 nodes, two to five resident warps per scheduler, "wait" and "short scoreboard" as the top stalls: bound by
@@ -14,7 +18,8 @@
 //     (3.5 LDS.128 per node pair instead of 11);
 //   * the row sums p(i-2)+p(i+2) are formed once per staged row and serve the in-row tap, the xz tap and the xy
 //     corner taps of the rows two above and below;
-//   * 20 fp64 operations per node, every coefficient a launch constant, 2 YB independent chains per thread;
+//   * 20 fp64 operations per node (25 in the z-general variant), every coefficient a launch constant, 2 YB
+//     independent chains per thread, 162-167 registers, no spills;
 //   * the five output-plane accumulators rotate statically (five copies of the plane body);
 //   * planes are staged by 16-byte cp.async (LDGSTS) into a ring of ST planes, ST-3 of them in flight; the ring
 //     keeps planes kp-1 and kp-2 resident so that p(k) for the fused p.q reduction is re-read from shared
@@ -366,8 +371,8 @@ namespace lsb {
 // come from a per-plane table (ShellZ), and of the 25 taps of an output plane only the 13 in-plane ones are
 // loaded -- the z neighbours are the per-plane scalars (p, C_x p, C_y p) kept in a five-deep register history.
 // ~100 instructions per node instead of the ~450 of the one-thread-per-node form it replaced (profiles/r01m).
-// Work items: the ring columns (outside [ilo,ihi) x [jlo,jhi)) over z chunks of the inner planes [klo,khi), and
-// every column over the planes next to the z faces.
+// Work items: the ring columns (outside [ilo,ihi) x [jlo,jhi)) over z chunks of [klo,khi) -- every owned plane
+// in the current launch plan; the kernel can also take every column of the planes outside [klo,khi) ("caps").
 struct ShellBox {
   int ilo, ihi, jlo, jhi, klo, khi;  // the box that is NOT computed here (klo/khi clipped to the owned planes)
   int ring_cols;                     // columns outside [ilo,ihi) x [jlo,jhi)

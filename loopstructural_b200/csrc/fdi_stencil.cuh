@@ -43,18 +43,6 @@ __device__ __forceinline__ int ghost_map(int i, int n) {
   return -1;
 }
 
-// Output region of one launch of k_fdi_normal.  mode 0: every owned node, z-chunked over [zA0,zA1).
-// mode 1 (y shell): the three rows next to either y face (blockIdx.y = 0: rows 0..2, 1: rows ny-3..ny-1), every
-// column.  mode 2 (x shell; launched with TXT = 1, XB = 4): the four columns next to either x face (blockIdx.x = 0:
-// columns 0..3, 1: nx-4..nx-1) of the rows [jlo,jhi).  mode 3 (z shell): the planes [zA0,zA1) (blockIdx.z = 0) and
-// [zB0,zB1) (blockIdx.z = 1) next to the z faces, columns [ilo,ihi), rows [jlo,jhi).  What the shells leave out is
-// the interior box of k_fdi_box (fdi_main.cuh).
-struct Region {
-  int mode;
-  int ilo, ihi, jlo, jhi;  // stored columns / rows
-  int zA0, zA1, zB0, zB1;  // global output planes
-};
-
 template <int XB, int TXT, int TYT, int ST = 4>
 struct StencilCfg {
   static constexpr int NT = TXT * TYT;
@@ -259,18 +247,17 @@ __device__ __forceinline__ void plane_general(const GridDesc& g, const StencilWe
 }
 
 template <int XB>
-__device__ __forceinline__ double store_plane(const GridDesc& g, const Region& rg, double* __restrict__ q, const int ko,
-                                              const int j, const int i0, const double (&out)[XB],
-                                              const double (&pk)[XB]) {
+__device__ __forceinline__ double store_plane(const GridDesc& g, double* __restrict__ q, const int ko, const int j,
+                                              const int i0, const double (&out)[XB], const double (&pk)[XB]) {
   double dot = 0.0;
   double* dst = q + (long long)(ko - g.k0 + HALO) * g.plane + g.pitch * j + i0;
-  if (XB == 2 && (g.pitch & 1) == 0 && i0 >= rg.ilo && i0 + 1 < rg.ihi) {
+  if (XB == 2 && (g.pitch & 1) == 0 && i0 + 1 < g.nx) {
     *reinterpret_cast<double2*>(dst) = make_double2(out[0], out[XB - 1]);
     dot = fma(pk[0], out[0], pk[XB - 1] * out[XB - 1]);
   } else {
 #pragma unroll
     for (int e = 0; e < XB; ++e)
-      if (i0 + e >= rg.ilo && i0 + e < rg.ihi) {
+      if (i0 + e < g.nx) {
         dst[e] = out[e];
         dot = fma(pk[e], out[e], dot);
       }
@@ -284,9 +271,7 @@ template <int XB, int TXT, int TYT, int MINB, int ST, bool VEC16>
 __global__ void __launch_bounds__(TXT* TYT, MINB)
     k_fdi_normal(const GridDesc g, const StencilWeights w, const double* __restrict__ p, double* __restrict__ q,
                  const int cz, double* __restrict__ partials, unsigned int* __restrict__ counter,
-                 CgScalars* __restrict__ sc, const int cg_mode, const Region rg) {
-  const int mode = rg.mode;
-  const int yshell = mode == 1, xshell = mode == 2;
+                 CgScalars* __restrict__ sc, const int cg_mode) {
   using C = StencilCfg<XB, TXT, TYT, ST>;
   extern __shared__ __align__(16) double S[];  // STAGES planes
   __shared__ double red[C::NT / 32];
@@ -295,17 +280,9 @@ __global__ void __launch_bounds__(TXT* TYT, MINB)
 
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int tid = tx + TXT * ty;
-  const int x0 = xshell ? (blockIdx.x == 0 ? 0 : g.nx - 4) : blockIdx.x * C::TX;
-  const int y0 = yshell ? (blockIdx.y == 0 ? 0 : g.ny - 3) : blockIdx.y * C::TY;
-  int ka, kb;
-  if (mode == 3) {
-    ka = blockIdx.z == 0 ? rg.zA0 : rg.zB0;
-    kb = blockIdx.z == 0 ? rg.zA1 : rg.zB1;
-  } else {
-    ka = rg.zA0 + blockIdx.z * cz;
-    kb = min(ka + cz, rg.zA1);
-  }
-  const bool empty = kb <= ka;  // an empty z range still takes part in the grid reduction
+  const int x0 = blockIdx.x * C::TX, y0 = blockIdx.y * C::TY;
+  const int ka = g.k0 + blockIdx.z * cz;
+  const int kb = min(ka + cz, g.k1);
 
   // per-thread copy descriptors: staged slot -> in-plane global offset of its ghost-mapped source
   constexpr int LD = VEC16 ? C::LD16 : C::LD8;
@@ -339,7 +316,7 @@ __global__ void __launch_bounds__(TXT* TYT, MINB)
   const int j = y0 + ty;
   const int i0 = x0 + XB * tx;
   const bool ybnd = (j <= 2 || j >= g.ny - 3);
-  const bool row_ok = j >= rg.jlo && j < rg.jhi && (!yshell || ty < 3);
+  const bool row_ok = j < g.ny;
 
   // canonical accumulators: A[d] collects output plane kp-2+d of the next incoming plane kp;
   // P1/P2 are this thread's p at planes kp-1 / kp-2
@@ -352,7 +329,7 @@ __global__ void __launch_bounds__(TXT* TYT, MINB)
   }
   double dot = 0.0;
 
-  const int kend = empty ? ka - HALO : kb + HALO;
+  const int kend = kb + HALO;
   int kp = ka - HALO;
 
   // pipeline prologue: ST-1 planes in flight
@@ -381,7 +358,7 @@ __global__ void __launch_bounds__(TXT* TYT, MINB)
       double rc[XB + 4], rm2[XB + 4], rp2[XB + 4], rm1[XB], rp1[XB];
       load_rows<XB, C::SX>(S + slot * C::PLANE + my_off, rc, rm2, rp2, rm1, rp1);
       plane_general<XB>(g, w, kp, i0, j, rc, rm2, rp2, rm1, rp1, P1, P2, A[0], A[1], A[2], A[3], A[4]);
-      if (kp - HALO >= ka && row_ok) dot += store_plane<XB>(g, rg, q, kp - HALO, j, i0, A[0], P2);
+      if (kp - HALO >= ka && row_ok) dot += store_plane<XB>(g, q, kp - HALO, j, i0, A[0], P2);
 #pragma unroll
       for (int e = 0; e < XB; ++e) {
         A[0][e] = A[1][e]; A[1][e] = A[2][e]; A[2][e] = A[3][e]; A[3][e] = A[4][e]; A[4][e] = 0.0;
@@ -436,7 +413,7 @@ __global__ void __launch_bounds__(TXT* TYT, MINB)
     load_rows<XB, C::SX>(S + slot * C::PLANE + my_off, rc, rm2, rp2, rm1, rp1);                               \
     plane_fast<XB>(K, w, g, ybnd, j, rc, rm2, rp2, rm1, rp1, A[(PH + 0) % 5], A[(PH + 1) % 5], A[(PH + 2) % 5], \
                    A[(PH + 3) % 5], A[(PH + 4) % 5]);                                                         \
-    if (kp - HALO >= ka && row_ok) dot += store_plane<XB>(g, rg, q, kp - HALO, j, i0, A[(PH + 0) % 5], H[(PH + 3) % 5]); \
+    if (kp - HALO >= ka && row_ok) dot += store_plane<XB>(g, q, kp - HALO, j, i0, A[(PH + 0) % 5], H[(PH + 3) % 5]); \
     _Pragma("unroll") for (int e = 0; e < XB; ++e) {                                                          \
       A[(PH + 0) % 5][e] = 0.0;                                                                               \
       H[PH][e] = rc[e + 2];                                                                                   \
@@ -482,7 +459,7 @@ __global__ void __launch_bounds__(TXT* TYT, MINB)
   const unsigned int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
   double total;
   if (grid_sum_last_block<C::NT>(bsum, partials, counter, nblocks, bid, red, &total)) {
-    sc->pq_part[mode == 0 ? 0 : mode + 1] = total;
+    sc->pq_part[0] = total;
   }
 }
 

@@ -29,7 +29,6 @@ import numpy as np
 
 from .interpolators import B200_SOLVERS
 
-_STENCIL_NAMES = ("dxx", "dyy", "dzz", "dxy", "dxz", "dyz")
 _installed = {}
 
 
