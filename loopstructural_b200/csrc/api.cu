@@ -219,18 +219,15 @@ static int pick_cz(const lsb200_ctx* h, int nplanes, long long tiles, long long 
   return best_cz;
 }
 
-// Stencil launch plans.  IDs 0-7: k_fdi_box (interior box, uniform coefficients) beside k_fdi_shell (everything
+// Stencil launch plans.  IDs 0,1,2,4: k_fdi_box (interior box, uniform coefficients) beside k_fdi_shell (everything
 // else); -1: k_fdi_normal everywhere (always used on grids too small to have a box).
 // X(ID, YB rows per thread, TYT warps, ST ring planes, MINB CTAs per SM)
+// (measured and dropped, profiles/r01g: <2,16,8,1> <2,8,6,3> <3,8,8,1> <3,4,8,2>)
 #define LSB_BOX_CFGS(X) \
   X(0, 4, 4, 8, 2)      \
   X(1, 4, 8, 8, 1)      \
   X(2, 2, 8, 8, 2)      \
-  X(3, 2, 16, 8, 1)     \
-  X(4, 4, 4, 6, 3)      \
-  X(5, 2, 8, 6, 3)      \
-  X(6, 3, 8, 8, 1)      \
-  X(7, 3, 4, 8, 2)
+  X(4, 4, 4, 6, 3)
 
 static void plan_main(lsb200_ctx* h) {
   const char* env = getenv("LSB200_STENCIL_MAIN");
@@ -411,13 +408,8 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
     return 0;
   }
   switch (h->stencil_cfg) {
-    case 1: LSB_LAUNCH(2, 32, 16, 1, 4); break;
-    case 2: LSB_LAUNCH(1, 32, 16, 1, 4); break;
-    case 3: LSB_LAUNCH(2, 32, 8, 2, 6); break;
-    case 4: LSB_LAUNCH(2, 32, 12, 1, 4); break;
     case 5: LSB_LAUNCH(2, 32, 8, 1, 4); break;
     case 6: LSB_LAUNCH(1, 32, 8, 3, 4); break;
-    case 7: LSB_LAUNCH(1, 32, 8, 2, 6); break;
     default: LSB_LAUNCH(2, 32, 8, 2, 4);
   }
 #undef LSB_LAUNCH
@@ -429,13 +421,8 @@ static void plan(lsb200_ctx* h) {
   const char* env = getenv("LSB200_STENCIL_CFG");
   h->stencil_cfg = env ? atoi(env) : 0;
   switch (h->stencil_cfg) {
-    case 1: plan_stencil<2, 32, 16>(h, 1); break;
-    case 2: plan_stencil<1, 32, 16>(h, 1); break;
-    case 3: plan_stencil<2, 32, 8>(h, 2); break;
-    case 4: plan_stencil<2, 32, 12>(h, 1); break;
     case 5: plan_stencil<2, 32, 8>(h, 1); break;
     case 6: plan_stencil<1, 32, 8>(h, 3); break;
-    case 7: plan_stencil<1, 32, 8>(h, 2); break;
     default: h->stencil_cfg = 0; plan_stencil<2, 32, 8>(h, 2);
   }
   const char* cz = getenv("LSB200_STENCIL_CZ");
