@@ -331,6 +331,9 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
       int za0 = 0, za1 = 0, zb0 = 0, zb1 = 0;
       if (lo_face) { za0 = g.k0; za1 = zl; }
       if (hi_face && zh < g.k1) { zb0 = zh; zb1 = g.k1; }
+      if (za1 <= za0 && zb1 > zb0) {  // only the upper face: it becomes range A, the launch has one z block
+        za0 = zb0; za1 = zb1; zb0 = zb1 = 0;
+      }
       const int ulo = zl, uhi = std::max(zl, zh);
       const bool zfirst = za1 > za0, zlast = zb1 > zb0;
       const int nuni = (uhi - ulo + cz - 1) / cz;
@@ -339,7 +342,7 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
       cudaStream_t zs = (have_z && ov) ? h->side[2] : h->stream;
       double* zpart = h->partials + 4 * (size_t)MAX_PARTIALS;
       unsigned int* zcnt = h->counters + 4;
-      const dim3 ugrid(h->main_grid.x, h->main_grid.y, nuni), zgrid(h->main_grid.x, h->main_grid.y, 2);
+      const dim3 ugrid(h->main_grid.x, h->main_grid.y, nuni), zgrid(h->main_grid.x, h->main_grid.y, (zb1 > zb0) ? 2 : 1);
       switch (h->main_cfg) {
 #define X(ID, YB, TYT, ST, MINB)                                                                                  \
   case ID: {                                                                                                      \

@@ -246,7 +246,8 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
     for (int r = 0; r < YB; ++r) A[d][r][0] = A[d][r][1] = 0.0;
   double dot = 0.0;
 
-  const int kstart = ka - HALO, kend = kb + HALO;
+  // an empty range (ka >= kb) stages and computes nothing, but still takes part in the grid reduction
+  const int kstart = ka - HALO, kend = ka < kb ? kb + HALO : ka - HALO;
   int kp = kstart;
   int issued = kstart;  // next plane to stage
 #pragma unroll
