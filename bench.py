@@ -373,6 +373,22 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    if world > 1:
+        # one rank failing inside a solve leaves its peers waiting in NCCL for ever, and a process whose CUDA context has
+        # faulted can block in its own destructors: leave at once so that torchrun tears the job down, and never outlive
+        # the time limit
+        import traceback
+
+        limit = float(os.environ.get("LSB200_BENCH_TIMEOUT", "1500"))
+        threading.Timer(limit, lambda: os._exit(3)).start()
+        try:
+            rc = run_ours(args)
+        except BaseException:
+            traceback.print_exc()
+            sys.stderr.flush()
+            os._exit(1)
+        sys.stdout.flush()
+        os._exit(rc)
     return run_ours(args)
 
 

@@ -54,4 +54,17 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # a rank that fails must not leave its peers waiting in NCCL (see bench.py)
+    import threading
+    import traceback
+
+    threading.Timer(500.0, lambda: os._exit(3)).start()
+    try:
+        main()
+    except SystemExit as e:
+        sys.stdout.flush()
+        os._exit(int(e.code or 0))
+    except BaseException:
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
