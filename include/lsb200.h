@@ -205,6 +205,11 @@ int lsb200_eval_gradient(lsb200_handle h, int64_t n, const double* xyz, double* 
 int lsb200_eval_value_dev(lsb200_handle h, int64_t n, const double* xyz_dev, double* out_dev, void* stream);
 int lsb200_eval_gradient_dev(lsb200_handle h, int64_t n, const double* xyz_dev, double* out_dev, void* stream);
 
+/* Introspection (no device needed): the output planes of the three launches of the tiled FDI operator for a
+ * handle owning the planes [k0,k1) of nz: out = {A0,A1, B0,B1, U0,U1}, A/B = z-general ranges next to the z faces,
+ * U = uniform range; see plan_z_ranges in csrc/api.cu. */
+int lsb200_plan_z_ranges(int nz, int k0, int k1, int cz, int zface, int out[6]);
+
 /* Page-locked host memory for result buffers (c of a large grid is 134 MB - 1 GB: a pageable destination halves
  * the device->host rate and pays its page faults inside every solve). */
 int lsb200_host_alloc(int64_t bytes, void** out);

@@ -72,6 +72,7 @@ SIGNATURES = {
     "lsb200_eval_gradient": (C.c_int, [Handle, C.c_int64, c_double_p, c_double_p]),
     "lsb200_eval_value_dev": (C.c_int, [Handle, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lsb200_eval_gradient_dev": (C.c_int, [Handle, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lsb200_plan_z_ranges": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "lsb200_host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     "lsb200_host_free": (C.c_int, [C.c_void_p]),
     "lsb200_time_kernel": (C.c_int, [Handle, C.c_int, C.c_int, c_double_p]),

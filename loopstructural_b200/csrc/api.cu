@@ -128,6 +128,7 @@ struct lsb200_ctx {
   bool main_uni = false;
   int main_cz = 0, shell_cz = 0;  // shell_cz = 0: chosen per launch
   int box_z0 = 0, box_z1 = 0;
+  long long guard = 0;     // elements of the guard plane in front of every node vector (ensure_vectors)
   double* ztab = nullptr;  // per-plane z coefficients of k_fdi_shell (nz * SHELL_ZSTRIDE)
   dim3 main_grid;
   // the shell launches run on side streams, overlapped with the box kernel (fork/join by events)
@@ -267,6 +268,26 @@ static void plan_main(lsb200_ctx* h) {
   h->main_cfg = cfg;
 }
 
+// Output planes of the three box launches of a handle owning [k0,k1) of nz planes, z chunk cz:
+//   out[0..1] = A, out[2..3] = B: ranges of the z-general launch (k_fdi_box<ZGEN>), next to the z faces the handle owns;
+//               short (zface planes: that variant is ~1.3x slower per plane), A non-empty whenever B is;
+//   out[4..5] = U: range of the uniform launch, every plane of it satisfies 3 <= k <= nz-4.
+// A, U, B are disjoint and cover [k0,k1).  Exported as lsb200_plan_z_ranges for the CPU tests.
+static void plan_z_ranges(int nz, int k0, int k1, int cz, int zface, int out[6]) {
+  const bool lo_face = k0 < 3, hi_face = k1 > nz - 3;
+  const int zc = std::max(3, std::min(cz, zface));
+  const int zl = lo_face ? std::min(k1, k0 + zc) : k0;
+  const int zh = hi_face ? std::max(zl, k1 - zc) : k1;
+  int za0 = 0, za1 = 0, zb0 = 0, zb1 = 0;
+  if (lo_face) { za0 = k0; za1 = zl; }
+  if (hi_face && zh < k1) { zb0 = zh; zb1 = k1; }
+  if (za1 <= za0 && zb1 > zb0) {  // only the upper face: it becomes range A, the launch has one z block
+    za0 = zb0; za1 = zb1; zb0 = zb1 = 0;
+  }
+  out[0] = za0; out[1] = za1; out[2] = zb0; out[3] = zb1;
+  out[4] = zl; out[5] = std::max(zl, zh);
+}
+
 static UniConsts make_uni_consts(const StencilWeights& w) {
   UniConsts U;
   U.cc = w.axx + w.ayy + w.azz + 4.0 * (w.bxy + w.bxz + w.byz) + w.ridge2;
@@ -322,19 +343,10 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
       const UniConsts U = make_uni_consts(w);
       const int cz = h->main_cz;
       // output planes of the z-general launch (next to the z faces this handle owns) and of the uniform launch
-      const bool lo_face = g.k0 < 3, hi_face = g.k1 > g.nz - 3;
-      // short face ranges: the z-general variant is ~1.3x slower per plane, and 3 of its planes are needed anyway
       static const int zface = (getenv("LSB200_ZFACE") && atoi(getenv("LSB200_ZFACE")) >= 3) ? atoi(getenv("LSB200_ZFACE")) : 8;
-      const int zc = std::min(cz, zface);
-      int zl = lo_face ? std::min(g.k1, g.k0 + zc) : g.k0;
-      int zh = hi_face ? std::max(zl, g.k1 - zc) : g.k1;
-      int za0 = 0, za1 = 0, zb0 = 0, zb1 = 0;
-      if (lo_face) { za0 = g.k0; za1 = zl; }
-      if (hi_face && zh < g.k1) { zb0 = zh; zb1 = g.k1; }
-      if (za1 <= za0 && zb1 > zb0) {  // only the upper face: it becomes range A, the launch has one z block
-        za0 = zb0; za1 = zb1; zb0 = zb1 = 0;
-      }
-      const int ulo = zl, uhi = std::max(zl, zh);
+      int zr[6];
+      plan_z_ranges(g.nz, g.k0, g.k1, cz, zface, zr);
+      const int za0 = zr[0], za1 = zr[1], zb0 = zr[2], zb1 = zr[3], ulo = zr[4], uhi = zr[5];
       const bool zfirst = za1 > za0, zlast = zb1 > zb0;
       const int nuni = (uhi - ulo + cz - 1) / cz;
       const bool have_z = zfirst || zlast;
@@ -531,12 +543,20 @@ static int alloc_block(lsb200_ctx* h, RowBlock& rb, long long n, int k) {
 
 static int ensure_vectors(lsb200_ctx* h) {
   if (h->x) return 0;
-  const size_t bytes = sizeof(double) * (size_t)h->g.nall;
+  // One zeroed guard plane in front of and behind the nzl + 4 stored planes: the gather kernels (k_fdi_shell) read
+  // the in-plane taps of the first / last stored plane without clamping -- a tap outside the grid has coefficient
+  // 0 but is still loaded, up to 2 rows + 2 nodes away.  On a single-handle grid those loads fall into the halo
+  // planes; on a z slab the first / last stored plane IS a halo plane, and they would leave the allocation.
+  const size_t guard = ((size_t)h->g.plane + 31) & ~(size_t)31;  // keeps the 256-byte alignment of the base
+  h->guard = (long long)guard;
+  const size_t bytes = sizeof(double) * ((size_t)h->g.nall + 2 * guard);
   double** v[] = {&h->x, &h->r, &h->p, &h->q, &h->rhs, &h->diag, &h->s2};
   for (double** pv : v) {
-    cudaError_t e = cudaMalloc(pv, bytes);
+    double* raw = nullptr;
+    cudaError_t e = cudaMalloc(&raw, bytes);
     if (e != cudaSuccess) return fail(LSB200_ERR_ALLOC, "cudaMalloc of a node vector (%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
-    CK(cudaMemsetAsync(*pv, 0, bytes, h->stream));
+    CK(cudaMemsetAsync(raw, 0, bytes, h->stream));
+    *pv = raw + guard;
   }
   return 0;
 }
@@ -646,7 +666,8 @@ int lsb200_destroy(lsb200_handle h) {
   for (RowBlock& rb : h->blocks) free_block(h, rb);
   free_transposes(h);
   double* v[] = {h->x, h->r, h->p, h->q, h->rhs, h->diag, h->s2};
-  for (double* pv : v) cudaFree(pv);
+  for (double* pv : v)
+    if (pv) cudaFree(pv - h->guard);  // allocated with a guard plane in front, see ensure_vectors
   cudaFree(h->sc);
   cudaFreeHost(h->sc_host);
   cudaFree(h->partials);
@@ -1430,6 +1451,12 @@ int lsb200_eval_value(lsb200_handle h, int64_t n, const double* xyz, double* out
 int lsb200_eval_gradient(lsb200_handle h, int64_t n, const double* xyz, double* out) {
   if (!h) return fail(LSB200_ERR_ARG, "null handle");
   return eval_host(h, n, xyz, out, true);
+}
+
+int lsb200_plan_z_ranges(int nz, int k0, int k1, int cz, int zface, int out[6]) {
+  if (!out || nz < 1 || k0 < 0 || k1 > nz || k1 <= k0 || cz < 1) return fail(LSB200_ERR_ARG, "bad argument");
+  plan_z_ranges(nz, k0, k1, cz, zface, out);
+  return 0;
 }
 
 int lsb200_host_alloc(int64_t bytes, void** out) {
