@@ -125,7 +125,6 @@ struct lsb200_ctx {
   dim3 sgrid;
   // main (register-tiled) kernel + y-shell launch of k_fdi_normal; main_cfg < 0: k_fdi_normal everywhere
   int main_cfg = -1;
-  bool main_uni = false;
   int main_cz = 0, shell_cz = 0;  // shell_cz = 0: chosen per launch
   int box_z0 = 0, box_z1 = 0;
   long long guard = 0;     // elements of the guard plane in front of every node vector (ensure_vectors)
@@ -244,8 +243,6 @@ static void plan_main(lsb200_ctx* h) {
 #undef X
     default: cfg = 4; ty = 16; minb = 3;
   }
-  const bool box = true;
-  h->main_uni = box;
   const char* czenv = getenv("LSB200_STENCIL_CZ");
   const int czo = (czenv && atoi(czenv) > 0) ? atoi(czenv) : 0;
   auto chunks = [&](int n, int cz) { return n > 0 ? (n + cz - 1) / cz : 0; };
@@ -332,7 +329,6 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
   }
 #define LSB_LAUNCH(XB, TXT, TYT, MINB, ST) LSB_LAUNCH_AT(h->stream, h->sgrid, h->cz, 0, XB, TXT, TYT, MINB, ST)
   if (h->main_cfg >= 0) {
-    const bool box = h->main_uni;
     const bool ov = h->overlap_shells;
     // fork: the shell launches read p and write rows / columns / planes the box kernel never touches
     if (ov) {
@@ -392,7 +388,7 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
     static const bool with_shell = !(getenv("LSB200_SHELL") && atoi(getenv("LSB200_SHELL")) == 0);
     if (with_shell) {
       ShellBox sb;
-      sb.ilo = box ? 4 : 0; sb.ihi = box ? g.nx - 4 : g.nx;
+      sb.ilo = 4; sb.ihi = g.nx - 4;
       sb.jlo = 3; sb.jhi = g.ny - 3;
       sb.klo = g.k0; sb.khi = g.k1;  // the ring columns over every owned plane; the z faces belong to k_fdi_box<ZGEN>
       const int nzm = sb.khi - sb.klo;
