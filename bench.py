@@ -177,6 +177,39 @@ def run_reference(args):
     return 0
 
 
+def measure_eval(eng, local, npts=20_000_000, npts_host=2_000_000):
+    """evaluate_value / evaluate_gradient of the field the engine holds (StructuredGrid.evaluate_*,
+    LC/supports/_3d_structured_grid.py:295-454) on a uniform random cloud in the unit cube."""
+    import torch
+
+    dev = torch.device("cuda", local)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    cloud = torch.rand((npts, 3), dtype=torch.float64, device=dev, generator=gen)
+    out1 = torch.empty(npts, dtype=torch.float64, device=dev)
+    out3 = torch.empty((npts, 3), dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    res = {"points": npts, "layout": "uniform random cloud, device-resident", "bytes_per_point": {"value": 96, "gradient": 112}}
+    for what, fn, out in (("value", eng.evaluate_value_device, out1), ("gradient", eng.evaluate_gradient_device, out3)):
+        for _ in range(3):
+            fn(cloud.data_ptr(), out.data_ptr(), npts, st)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            fn(cloud.data_ptr(), out.data_ptr(), npts, st)
+        b.record()
+        torch.cuda.synchronize()
+        dt = a.elapsed_time(b) * 1e-3 / 5
+        res[f"{what}_points_per_second"] = npts / dt
+        res[f"{what}_gbs"] = res["bytes_per_point"][what] * npts / dt / 1e9
+    host = cloud[:npts_host].cpu().numpy()
+    eng.evaluate_value(host[:1000])
+    t0 = time.perf_counter()
+    v = eng.evaluate_value(host)
+    res["value_points_per_second_host_arrays"] = npts_host / (time.perf_counter() - t0)
+    res["finite_fraction"] = float(np.isfinite(v).mean())
+    return res
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -292,6 +325,15 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     wall, dev_s, wall_e2e = (float(v) for v in t.tolist())
 
+    # ---- "field evals/sec" (second half of the BASELINE metric): evaluation of the solved field on a random cloud,
+    # device-resident points (kernel rate) and host arrays through the public API.  Never allowed to break the line.
+    eval_info = None
+    if world == 1:
+        try:
+            eval_info = measure_eval(eng, local)
+        except Exception as exc:  # noqa: BLE001
+            eval_info = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ---- roofline of the dominant operator kernel + whole iteration, CUDA events on the engine's stream
     t_matvec = eng.time_kernel(0, reps=20)
     t_iter = eng.time_kernel(1, reps=20)
@@ -333,6 +375,8 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if eval_info is not None:
+            line["eval"] = eval_info
         if world == 1 and not args.no_cpu_baseline:
             t0 = time.perf_counter()
             dof, it, dt, timing = cpu_reference_step(args.ref_n, max(100, int(1e5 * (args.ref_n / 256.0) ** 3)),
