@@ -144,3 +144,24 @@ def test_cg_restatement_matches_scipy():
     np.testing.assert_allclose(res.x, x_ref, rtol=0, atol=1e-12 * np.abs(x_ref).max())
     # zero right-hand side returns immediately
     assert fo.cg(lambda v: N @ v, np.zeros(n)).iterations == 0
+
+
+def test_claudius_quickstart_matches_reference():
+    """BASELINE configs[0] (README quickstart: Claudius 'strati' foliation through GeologicalModel, FDI, scipy cg) at
+    nelements=2e4: the oracle fed with what reached the reference's interpolator reproduces its iteration count and
+    coefficients, and the evaluation of the reference's field."""
+    z = np.load(os.path.join(GOLDEN, "fdi_claudius_2e4.npz"))
+    grid = fo.Grid.from_cells(z["ncells"], z["origin"], z["step"])
+    kw = _weights(z, "kw_keys", "kw_vals")
+    w = dict(fo.DEFAULT_WEIGHTS)
+    w.update({k: v for k, v in kw.items() if k in w})
+    fams = fo.normal_rows(grid, z["data_normal"], w["npw"]) + [fo.value_rows(grid, z["data_value"], w["cpw"])]
+    fams += fo.regularisation_families(grid, w)
+    c, res, _ = fo.solve_reference_path(fams, grid.n_nodes, rtol=1e-5, atol=float(z["tol"]))
+    assert res.iterations == int(z["iterations"])
+    rng_ = float(z["c"].max() - z["c"].min())
+    assert np.linalg.norm(c - z["c"]) / np.sqrt(c.size) / rng_ <= 1e-9
+    v = fo.evaluate_value(grid, z["query"], z["c"])
+    np.testing.assert_array_equal(np.isnan(v), np.isnan(z["value_at"]))
+    np.testing.assert_allclose(v, z["value_at"], rtol=0, atol=1e-9, equal_nan=True)
+    np.testing.assert_allclose(fo.evaluate_gradient(grid, z["query"], z["c"]), z["gradient_at"], rtol=0, atol=1e-12)

@@ -1,0 +1,50 @@
+"""BASELINE configs[0] on the CUDA path: the Claudius 'strati' foliation of the reference's README quickstart
+(21,023 value + 25 normal points, real-world coordinates, weights as GeologicalModel's feature builder injects them)
+through B200FiniteDifferenceInterpolator, against the reference's own coefficients (tests/golden/fdi_claudius_2e4.npz,
+from tests/golden/make_golden_claudius.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import fdi_oracle as fo
+import golden_helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def test_claudius_quickstart_solve_and_evaluation():
+    from loopstructural_b200 import build
+    from loopstructural_b200.interpolators import B200FiniteDifferenceInterpolator, Support
+
+    build.build()
+    z = np.load(os.path.join(H.GOLDEN, "fdi_claudius_2e4.npz"))
+    grid = fo.Grid.from_cells(z["ncells"], z["origin"], z["step"])
+    kw = {k: v for k, v in H.weights_of(z, "kw_keys", "kw_vals").items() if k in fo.DEFAULT_WEIGHTS}
+    it = B200FiniteDifferenceInterpolator(Support(grid.origin, grid.nsteps - 1, grid.step))
+    it.set_value_constraints(z["data_value"])
+    it.set_normal_constraints(z["data_normal"])
+    counts = it.setup_interpolator(**kw)
+    assert counts["value"] == len(z["data_value"]) and counts["normal"] == 3 * len(z["data_normal"])
+    rng_ = float(z["c"].max() - z["c"].min())
+    # the model path: tol -> atol, rtol 1e-5 (LI/_solver_strategy.py:59-64).  The reference's last residual is 0.988 of the
+    # threshold, so rounding decides the stopping iteration: one CG step of slack on the field (see test_p1_gpu.py)
+    assert it.solve_system("b200", tol=float(z["tol"])) is True
+    t = it.get_last_solve_timing()
+    assert t["info"] == 0 and abs(t["iterations"] - int(z["iterations"])) <= max(2, int(z["iterations"]) // 50)
+    assert np.linalg.norm(it.c - z["c"]) / np.sqrt(it.c.size) / rng_ <= 5e-5
+    # the same system to rtol 1e-10 against the oracle's equally tight solve: the 1e-6 bar
+    w = dict(fo.DEFAULT_WEIGHTS)
+    w.update(kw)
+    fams = fo.normal_rows(grid, z["data_normal"], w["npw"]) + [fo.value_rows(grid, z["data_value"], w["cpw"])]
+    c_ref, res_ref, _ = fo.solve_reference_path(fams + fo.regularisation_families(grid, w), grid.n_nodes, rtol=1e-10)
+    assert it.solve_system("b200", solver_kwargs={"rtol": 1e-10, "atol": 0.0}) is True
+    assert abs(it.get_last_solve_timing()["iterations"] - res_ref.iterations) <= max(2, res_ref.iterations // 50)
+    assert np.linalg.norm(it.c - c_ref) / np.sqrt(c_ref.size) / rng_ <= 1e-6
+    # evaluation of the reference's field at the reference's query points (outside points: NaN / zero gradient)
+    it.set_c(z["c"])
+    v = it.evaluate_value(z["query"])
+    np.testing.assert_array_equal(np.isnan(v), np.isnan(z["value_at"]))
+    np.testing.assert_allclose(v, z["value_at"], rtol=0, atol=1e-9 * rng_, equal_nan=True)
+    np.testing.assert_allclose(it.evaluate_gradient(z["query"]), z["gradient_at"], rtol=0, atol=1e-10)
+    it.close()
