@@ -31,8 +31,10 @@ def test_claudius_quickstart_solve_and_evaluation():
     # threshold, so rounding decides the stopping iteration: one CG step of slack on the field (see test_p1_gpu.py)
     assert it.solve_system("b200", tol=float(z["tol"])) is True
     t = it.get_last_solve_timing()
-    assert t["info"] == 0 and abs(t["iterations"] - int(z["iterations"])) <= max(2, int(z["iterations"]) // 50)
-    assert np.linalg.norm(it.c - z["c"]) / np.sqrt(it.c.size) / rng_ <= 5e-5
+    d_its = abs(t["iterations"] - int(z["iterations"]))
+    assert t["info"] == 0 and d_its <= max(2, int(z["iterations"]) // 50)
+    # near the stopping point one CG step moves the field by 2.7e-5 .. 3.0e-5 of its range (measured with the oracle)
+    assert np.linalg.norm(it.c - z["c"]) / np.sqrt(it.c.size) / rng_ <= 3e-6 + 3.2e-5 * d_its
     # the same system to rtol 1e-10 against the oracle's equally tight solve: the 1e-6 bar
     w = dict(fo.DEFAULT_WEIGHTS)
     w.update(kw)
