@@ -1,0 +1,128 @@
+"""The plug-in inside the reference's real call chain on CPU: GeologicalModel.create_and_add_foliation(solver='b200')
+-> GeologicalFeatureBuilder -> interpolator_map -> B200FiniteDifferenceInterpolator.setup_interpolator / solve_system /
+evaluate.  The device engine is replaced BY THIS TEST with a stand-in that solves the same system with the oracle, so
+what is checked is the plumbing: which families reach the engine, the weight conventions, ridge / scaling / tolerance
+options, and that the model's answers equal the stock solver's.  (The engine itself is checked on the GPU.)"""
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "packages")), reason="reference not mounted")
+
+
+class OracleEngine:
+    """Same surface as loopstructural_b200.engine.Engine, numerics from oracle/ (test stand-in only)."""
+
+    instances = []
+
+    def __init__(self, nsteps, origin, step, kind="grid", device=0, slab=None):
+        from oracle import fdi_oracle as fo
+
+        self.fo = fo
+        self.kind = kind
+        self.grid = fo.Grid(np.asarray(nsteps), np.asarray(origin, float), np.asarray(step, float))
+        self.rows, self.weights, self.opts, self.c = [], None, {}, None
+        OracleEngine.instances.append(self)
+
+    def set_regularisation(self, weights):
+        self.weights = dict(weights)
+
+    def set_options(self, **kw):
+        self.opts = kw
+
+    def add_rows(self, A, idx, b, w, normalise=True):
+        assert normalise is False  # the reference has normalised them already
+        self.rows.append(self.fo.Family(f"rows{len(self.rows)}", np.array(A, float), np.array(idx), np.array(b, float), np.array(w, float)))
+
+    def solve_cg(self, rtol=1e-5, atol=0.0, maxiter=None, x0=None, want_c=True, out=None):
+        w = dict(self.fo.DEFAULT_WEIGHTS)
+        w.update(self.weights)
+        fams = self.rows + self.fo.regularisation_families(self.grid, w)
+        self.solve_args = dict(rtol=rtol, atol=atol)
+        c, res, _ = self.fo.solve_reference_path(fams, self.grid.n_nodes, rtol=rtol, atol=atol,
+                                                 ridge_factor=self.opts.get("ridge_factor", 1e-8),
+                                                 apply_scaling=self.opts.get("apply_scaling", True))
+        self.c = c
+        return c, SimpleNamespace(info=res.info, iterations=res.iterations, setup_seconds=0.0, solve_seconds=0.0,
+                                  residual_norm=res.residual_norm, threshold=res.threshold, kernel_launches=0)
+
+    def evaluate_value(self, xyz):
+        return self.fo.evaluate_value(self.grid, np.asarray(xyz, float), self.c)
+
+    def evaluate_gradient(self, xyz):
+        return self.fo.evaluate_gradient(self.grid, np.asarray(xyz, float), self.c)
+
+    def close(self):
+        pass
+
+
+@pytest.fixture()
+def ls(monkeypatch):
+    sys.dont_write_bytecode = True
+    for p in (os.path.join(HERE, "golden", "_stubs"), f"{REF}/packages/loop_common/src",
+              f"{REF}/packages/loop_interpolation/src", REF):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import logging
+
+    logging.disable(logging.CRITICAL)
+    import LoopStructural
+    from loopstructural_b200 import engine, plugin
+
+    monkeypatch.setattr(engine, "Engine", OracleEngine)
+    OracleEngine.instances.clear()
+    plugin.install()
+    yield LoopStructural
+    plugin.uninstall()
+
+
+def _model(ls, **kw):
+    from LoopStructural.datasets import load_claudius
+
+    data, bb = load_claudius()
+    model = ls.GeologicalModel(bb[0, :], bb[1, :])
+    model.data = data
+    model.create_and_add_foliation("strati", nelements=3e3, **kw)
+    model.update()
+    return model, bb
+
+
+def test_foliation_through_the_model_with_the_b200_solver_matches_the_stock_solver(ls):
+    model, bb = _model(ls, solver="b200")
+    it = model["strati"].interpolator
+    assert type(it).__name__ == "B200FiniteDifferenceInterpolator"
+    assert it.latest_solve_timing["backend"] == "b200" and it.up_to_date
+    eng = OracleEngine.instances[-1]
+    # only data families reached the engine as rows; the stencil families arrived as nine effective weights
+    assert sorted(it.constraints) == ["norm_0", "norm_1", "norm_2", "value"] and len(eng.rows) == 4
+    assert eng.weights == {"dxx": 1.0, "dyy": 1.0, "dzz": 1.0, "dxy": 1.0, "dxz": 1.0, "dyz": 1.0, "dx": 1.0, "dy": 1.0, "dz": 1.0}
+    assert eng.opts["ridge_factor"] == it.ridge_factor and eng.opts["apply_scaling"] is True
+    # the model passes tol (-> atol) and no rtol: rtol stays scipy's 1e-5 (LI/_solver_strategy.py:59-64)
+    assert eng.solve_args["rtol"] == 1e-5 and eng.solve_args["atol"] > 0
+    rng = np.random.default_rng(1)
+    pts = bb[0] + rng.uniform(0, 1, (50, 3)) * (bb[1] - bb[0])
+    val, grad = model.evaluate_feature_value("strati", pts), model.evaluate_feature_gradient("strati", pts)
+    c_b200 = np.array(it.c)
+
+    from loopstructural_b200 import plugin
+
+    plugin.uninstall()
+    stock, _ = _model(ls)  # stock class, stock 'cg'
+    its = stock["strati"].interpolator
+    assert type(its).__name__ == "FiniteDifferenceInterpolator" and its.latest_solve_timing["backend"] == "python"
+    rng_ = float(its.c.max() - its.c.min())
+    assert np.linalg.norm(c_b200 - its.c) / np.sqrt(its.c.size) / rng_ <= 1e-9
+    np.testing.assert_allclose(val, stock.evaluate_feature_value("strati", pts), rtol=0, atol=1e-9 * rng_)
+    np.testing.assert_allclose(grad, stock.evaluate_feature_gradient("strati", pts), rtol=0, atol=1e-12)
+
+
+def test_model_without_the_b200_solver_is_untouched_by_the_plugin(ls):
+    model, _ = _model(ls)  # plug-in installed, default solver
+    it = model["strati"].interpolator
+    assert type(it).__name__ == "B200FiniteDifferenceInterpolator"
+    assert it.latest_solve_timing["backend"] == "python" and "dxx" in it.constraints and not OracleEngine.instances
