@@ -66,3 +66,20 @@ def add_point_data(e, z, weights, prefix="data_"):
         t[:, 6] = 0.0  # column 6 is the row target b for tangent rows
         n += e.add_point_rows(en.ROWS_TANGENT, t, weights["tpw"])
     return n
+
+
+def fault_case(z):
+    """fields, profile, displacement, steps, fault_offset of a fault_*.npz fixture (oracle objects)."""
+    from oracle import fault_oracle as fa
+
+    fields = [fa.FrameField(fo.Grid.from_cells(z[f"f{i}_ncells"], z[f"f{i}_origin"], z[f"f{i}_step"]), z[f"f{i}_c"],
+                            z[f"f{i}_w2l"]) for i in range(3)]
+
+    def p1(row):
+        return fa.Profile1D(int(row[0]), tuple(row[1:5]), (row[5], row[6]), float(row[7]), float(row[8]))
+
+    axes = None
+    if int(z["has_function"]):
+        tab, comp = z["profile_table"], z["profile_composite"]
+        axes = tuple(fa.AxisProfile(p1(tab[a, 0]), p1(tab[a, 1]) if comp[a] else None) for a in range(3))
+    return fields, fa.FaultProfile(axes, float(z["profile_scale"])), float(z["displacement"]), int(z["steps"]), float(z["fault_offset"])

@@ -1,0 +1,47 @@
+"""oracle/fault_oracle.py against outputs of the unmodified reference (tests/golden/fault_*.npz,
+made by tests/golden/make_golden_fault.py): FaultSegment.apply_to_points / evaluate_displacement and the
+fault-frame gathers behind them."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from golden_helpers import GOLDEN, fault_case
+from oracle import fault_oracle as fa
+
+CASES = sorted(os.path.basename(p)[6:-4] for p in glob.glob(os.path.join(GOLDEN, "fault_*.npz")))
+
+
+def test_fixtures_present():
+    assert CASES == ["base", "base3d", "halfzero", "none", "wide"]
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_frame_gathers_match_the_reference(tag):
+    z = np.load(os.path.join(GOLDEN, f"fault_{tag}.npz"))
+    fields, *_ = fault_case(z)
+    vals, grad = fa.frame_eval(fields, z["points"])
+    np.testing.assert_array_equal(np.isnan(vals), np.isnan(z["frame_values"]))
+    np.testing.assert_allclose(vals, z["frame_values"], rtol=0, atol=1e-12, equal_nan=True)
+    # GeologicalFeature.evaluate_gradient leaves NaN only where a mask excludes the point: none here
+    np.testing.assert_allclose(grad, z["frame_gradient1"], rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_apply_to_points_matches_the_reference(tag):
+    z = np.load(os.path.join(GOLDEN, f"fault_{tag}.npz"))
+    fields, profile, disp, steps, _ = fault_case(z)
+    moved = fa.apply_to_points(fields, profile, disp, steps, z["points"])
+    np.testing.assert_array_equal(np.isnan(moved), np.isnan(z["moved"]))
+    np.testing.assert_allclose(moved, z["moved"], rtol=0, atol=1e-9, equal_nan=True)  # coordinates are O(1e4)
+    # `reverse` does not change the reference's result (the reversed d is overwritten inside the loop)
+    np.testing.assert_array_equal(z["moved"], z["moved_reverse"])
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_evaluate_displacement_matches_the_reference(tag):
+    z = np.load(os.path.join(GOLDEN, f"fault_{tag}.npz"))
+    fields, profile, disp, _, offset = fault_case(z)
+    d = fa.evaluate_displacement(fields, profile, disp, offset, z["points"])
+    np.testing.assert_allclose(d, z["displacement_at"], rtol=1e-13, atol=1e-13 * abs(disp))
