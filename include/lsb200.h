@@ -205,6 +205,68 @@ int lsb200_eval_gradient(lsb200_handle h, int64_t n, const double* xyz, double* 
 int lsb200_eval_value_dev(lsb200_handle h, int64_t n, const double* xyz_dev, double* out_dev, void* stream);
 int lsb200_eval_gradient_dev(lsb200_handle h, int64_t n, const double* xyz_dev, double* out_dev, void* stream);
 
+/* ---- fault-frame evaluation (the consumers of evaluate_value / evaluate_gradient) ------------------------- */
+
+/* One 1-D fault profile: the closed family of LoopStructural/modelling/features/fault/_fault_function.py --
+ * Zeros / Ones (:256-305), CubicFunction (:40-140: w0 v^3 + w1 v^2 + w2 v + w3, clamped to its value at lim[]
+ * outside the limits, then to [min_v, max_v]) and smooth_peak (:12-16). */
+enum { LSB200_PROFILE_ZEROS = 0, LSB200_PROFILE_ONES = 1, LSB200_PROFILE_CUBIC = 2, LSB200_PROFILE_SMOOTH_PEAK = 3 };
+typedef struct lsb200_profile1d {
+  int32_t kind;
+  int32_t reserved;
+  double w[4];
+  double lim[2];
+  double min_v, max_v;
+} lsb200_profile1d;
+
+/* FaultDisplacement (:308-369): d = scale * gx(v0) * gy(v1) * gz(v2) over the three fault-frame coordinates.
+ * composite[a] != 0: axis a is Composite(pos, neg) (:198-226; pos for v > 0, neg for v < 0, 0 at 0); otherwise
+ * pos[a] is used for every v.  has_function == 0: the segment has no fault function, d = [v0 > 0]. */
+typedef struct lsb200_fault_profile {
+  int32_t has_function;
+  int32_t composite[3];
+  double scale;
+  lsb200_profile1d pos[3];
+  lsb200_profile1d neg[3];
+} lsb200_fault_profile;
+
+/* The three solved fields of a fault frame (StructuralFrame, coordinates 0 / 1 / 2) are three grid handles on one
+ * device, each owning every plane and holding a solution.  xyz are WORLD coordinates; transforms (may be NULL =
+ * identity, i.e. xyz already local to all three supports) holds per field 21 doubles: the upper 3 x 4 of
+ * BoundingBox.world_to_local_matrix row-major (project, LC/geometry/_bounding_box.py:118-176,702-717) followed by the
+ * 3 x 3 rotation of local_to_world_matrix row-major (reproject_vectors, :750-761).
+ *
+ * lsb200_frame_eval: the gathers one integration step of a fault needs, in ONE pass over the points: values
+ * (n,3) = GeologicalInterpolator.evaluate_value of the three fields (LI/_geological_interpolator.py:723-730; NaN
+ * outside a support, 0.0 for NaN coordinates) and, when gradient != NULL, gradient (n,3) = evaluate_gradient of field
+ * `gradient_of` in world axes (:732-741; 0 outside). */
+int lsb200_frame_eval(const lsb200_handle fields[3], const double* transforms, int gradient_of, int64_t n,
+                      const double* xyz, double* values, double* gradient);
+
+/* FaultSegment.apply_to_points (LoopStructural/modelling/features/fault/_fault_segment.py:315-423): every point
+ * with a non-zero displacement is carried through `steps` steps of  x += (1/steps) d(x) g1(x)/|g1(x)|, d = profile of
+ * the three frame values * displacement, g1 = gradient of field 1 -- one thread per point, all steps on the device
+ * (the reference runs 4 gathers per step as separate numpy passes).  The reference's `reverse` flag does not
+ * change its result (the reversed d is overwritten inside the loop, :360-363 vs :403), so it has no counterpart
+ * here.  moved is (n,3) and must not alias xyz. */
+int lsb200_fault_displace(const lsb200_handle fields[3], const double* transforms, const lsb200_fault_profile* profile,
+                          double displacement, int steps, int64_t n, const double* xyz, double* moved);
+
+/* FaultSegment.evaluate_displacement (:283-313): d (n) = profile(v0 + fault_offset, v1, v2) * displacement. */
+int lsb200_fault_displacement(const lsb200_handle fields[3], const double* transforms,
+                              const lsb200_fault_profile* profile, double displacement, double fault_offset, int64_t n,
+                              const double* xyz, double* d);
+
+/* same three, device pointers on the handles' GPU, asynchronous on `stream` */
+int lsb200_frame_eval_dev(const lsb200_handle fields[3], const double* transforms, int gradient_of, int64_t n,
+                          const double* xyz_dev, double* values_dev, double* gradient_dev, void* stream);
+int lsb200_fault_displace_dev(const lsb200_handle fields[3], const double* transforms,
+                              const lsb200_fault_profile* profile, double displacement, int steps, int64_t n,
+                              const double* xyz_dev, double* moved_dev, void* stream);
+int lsb200_fault_displacement_dev(const lsb200_handle fields[3], const double* transforms,
+                                  const lsb200_fault_profile* profile, double displacement, double fault_offset,
+                                  int64_t n, const double* xyz_dev, double* d_dev, void* stream);
+
 /* Introspection (no device needed): the output planes of the three launches of the tiled FDI operator for a
  * handle owning the planes [k0,k1) of nz: out = {A0,A1, B0,B1, U0,U1}, A/B = z-general ranges next to the z faces,
  * U = uniform range; see plan_z_ranges in csrc/api.cu. */

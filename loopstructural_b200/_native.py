@@ -39,6 +39,23 @@ class SolveInfo(C.Structure):
     ]
 
 
+class Profile1D(C.Structure):
+    """lsb200_profile1d"""
+
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("w", C.c_double * 4), ("lim", C.c_double * 2),
+                ("min_v", C.c_double), ("max_v", C.c_double)]
+
+
+class FaultProfile(C.Structure):
+    """lsb200_fault_profile"""
+
+    _fields_ = [("has_function", C.c_int32), ("composite", C.c_int32 * 3), ("scale", C.c_double),
+                ("pos", Profile1D * 3), ("neg", Profile1D * 3)]
+
+
+_Handle3 = C.POINTER(Handle)
+_ProfileP = C.POINTER(FaultProfile)
+
 # every symbol include/lsb200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "lsb200_abi_version": (C.c_int, []),
@@ -72,6 +89,12 @@ SIGNATURES = {
     "lsb200_eval_gradient": (C.c_int, [Handle, C.c_int64, c_double_p, c_double_p]),
     "lsb200_eval_value_dev": (C.c_int, [Handle, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lsb200_eval_gradient_dev": (C.c_int, [Handle, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lsb200_frame_eval": (C.c_int, [_Handle3, c_double_p, C.c_int, C.c_int64, c_double_p, c_double_p, c_double_p]),
+    "lsb200_fault_displace": (C.c_int, [_Handle3, c_double_p, _ProfileP, C.c_double, C.c_int, C.c_int64, c_double_p, c_double_p]),
+    "lsb200_fault_displacement": (C.c_int, [_Handle3, c_double_p, _ProfileP, C.c_double, C.c_double, C.c_int64, c_double_p, c_double_p]),
+    "lsb200_frame_eval_dev": (C.c_int, [_Handle3, c_double_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lsb200_fault_displace_dev": (C.c_int, [_Handle3, c_double_p, _ProfileP, C.c_double, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lsb200_fault_displacement_dev": (C.c_int, [_Handle3, c_double_p, _ProfileP, C.c_double, C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lsb200_plan_z_ranges": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "lsb200_host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     "lsb200_host_free": (C.c_int, [C.c_void_p]),

@@ -21,6 +21,7 @@
 #include "eval.cuh"
 #include "fdi_stencil.cuh"
 #include "fdi_main.cuh"
+#include "frame.cuh"
 #include "p1.cuh"
 #include "rows.cuh"
 
@@ -1447,6 +1448,175 @@ int lsb200_eval_value(lsb200_handle h, int64_t n, const double* xyz, double* out
 int lsb200_eval_gradient(lsb200_handle h, int64_t n, const double* xyz, double* out) {
   if (!h) return fail(LSB200_ERR_ARG, "null handle");
   return eval_host(h, n, xyz, out, true);
+}
+
+// ------------------------------------------------------------------ fault-frame evaluation (frame.cuh)
+static_assert(sizeof(lsb200_profile1d) == sizeof(Profile1D), "profile layout");
+static_assert(sizeof(lsb200_fault_profile) == sizeof(FaultProfile), "fault profile layout");
+
+// the three handles of a frame -> kernel argument; every handle: grid kind, same device, all planes, a solution
+static int make_frame(const lsb200_handle fields[3], const double* transforms, FrameFields* FF) {
+  if (!fields) return fail(LSB200_ERR_ARG, "null field array");
+  for (int f = 0; f < 3; ++f) {
+    const lsb200_ctx* h = fields[f];
+    if (!h) return fail(LSB200_ERR_ARG, "fault-frame field %d: null handle", f);
+    if (h->kind != LSB200_SUPPORT_GRID) return fail(LSB200_ERR_ARG, "fault-frame field %d: only grid handles are supported", f);
+    if (h->device != fields[0]->device) return fail(LSB200_ERR_ARG, "fault-frame fields live on different devices");
+    if (h->g.k0 != 0 || h->g.k1 != h->g.nz) return fail(LSB200_ERR_STATE, "fault-frame field %d: the handle must own every plane", f);
+    if (!h->have_c) return fail(LSB200_ERR_STATE, "fault-frame field %d: no solution on the device yet (solve or set_c first)", f);
+    FrameField& F = FF->f[f];
+    F.g = h->g;
+    F.c = h->x;
+    if (transforms) {
+      const double* t = transforms + 21 * f;
+      for (int i = 0; i < 12; ++i) F.w2l[i] = t[i];
+      for (int i = 0; i < 9; ++i) F.l2w[i] = t[12 + i];
+    } else {
+      for (int i = 0; i < 12; ++i) F.w2l[i] = (i % 5 == 0) ? 1.0 : 0.0;  // [I | 0]
+      for (int i = 0; i < 9; ++i) F.l2w[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    }
+  }
+  return 0;
+}
+
+static int check_profile(const lsb200_fault_profile* p, FaultProfile* P) {
+  if (!p) return fail(LSB200_ERR_ARG, "null fault profile");
+  memcpy(P, p, sizeof(FaultProfile));
+  if (!p->has_function) return 0;
+  for (int a = 0; a < 3; ++a)
+    for (const lsb200_profile1d* q : {&p->pos[a], &p->neg[a]})
+      if (q->kind < LSB200_PROFILE_ZEROS || q->kind > LSB200_PROFILE_SMOOTH_PEAK)
+        return fail(LSB200_ERR_ARG, "fault profile axis %d: unknown kind %d", a, (int)q->kind);
+  return 0;
+}
+
+static int frame_blocks(const lsb200_ctx* h, int64_t n) {
+  return (int)std::min<long long>((n + 255) / 256, (long long)h->sm_count * 32);
+}
+
+enum { FRAME_EVAL = 0, FRAME_DISPLACE = 1, FRAME_DISPLACEMENT = 2 };
+struct FrameCall {
+  int what;
+  FrameFields FF;
+  FaultProfile P;
+  int gradient_of, steps;
+  double displacement, offset;
+};
+
+// launch on device buffers: out0 = values / moved / d, out1 = gradient (FRAME_EVAL only, may be null)
+static int frame_launch(lsb200_ctx* h, const FrameCall& fc, int64_t n, const double* xyz_dev, double* out0, double* out1,
+                        cudaStream_t st) {
+  if (n == 0) return 0;
+  const int nb = frame_blocks(h, n);
+  switch (fc.what) {
+    case FRAME_EVAL: k_frame_eval<<<nb, 256, 0, st>>>(fc.FF, fc.gradient_of, n, xyz_dev, out0, out1); break;
+    case FRAME_DISPLACE: k_fault_displace<<<nb, 256, 0, st>>>(fc.FF, fc.P, fc.displacement, fc.steps, n, xyz_dev, out0); break;
+    default: k_fault_displacement<<<nb, 256, 0, st>>>(fc.FF, fc.P, fc.displacement, fc.offset, n, xyz_dev, out0);
+  }
+  CKL();
+  h->launches++;
+  return 0;
+}
+
+// host buffers: chunked through a staging buffer on the first field's stream
+static int frame_host(lsb200_ctx* h, const FrameCall& fc, int64_t n, const double* xyz, double* out0, double* out1) {
+  if (n < 0) return fail(LSB200_ERR_ARG, "negative point count");
+  if (n == 0) return 0;
+  if (!xyz || !out0) return fail(LSB200_ERR_ARG, "null argument");
+  const int w0 = fc.what == FRAME_DISPLACEMENT ? 1 : 3;
+  const int64_t chunk = std::min<int64_t>(n, 1 << 24);
+  double *dx = nullptr, *d0 = nullptr, *d1 = nullptr;
+  CK(cudaMallocAsync(&dx, sizeof(double) * 3 * chunk, h->stream));
+  CK(cudaMallocAsync(&d0, sizeof(double) * w0 * chunk, h->stream));
+  if (out1) CK(cudaMallocAsync(&d1, sizeof(double) * 3 * chunk, h->stream));
+  int rc = 0;
+  for (int64_t o = 0; o < n && !rc; o += chunk) {
+    const int64_t m = std::min<int64_t>(chunk, n - o);
+    CK(cudaMemcpyAsync(dx, xyz + 3 * o, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, h->stream));
+    rc = frame_launch(h, fc, m, dx, d0, d1, h->stream);
+    if (rc) break;
+    CK(cudaMemcpyAsync(out0 + w0 * o, d0, sizeof(double) * w0 * m, cudaMemcpyDeviceToHost, h->stream));
+    if (out1) CK(cudaMemcpyAsync(out1 + 3 * o, d1, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  pool_free(h, dx);
+  pool_free(h, d0);
+  pool_free(h, d1);
+  return rc;
+}
+
+static int frame_prepare(const lsb200_handle fields[3], const double* transforms, const lsb200_fault_profile* profile,
+                         bool need_profile, FrameCall* fc) {
+  int rc = make_frame(fields, transforms, &fc->FF);
+  if (rc) return rc;
+  if (need_profile && (rc = check_profile(profile, &fc->P))) return rc;
+  CK(cudaSetDevice(fields[0]->device));
+  return 0;
+}
+
+int lsb200_frame_eval_dev(const lsb200_handle fields[3], const double* transforms, int gradient_of, int64_t n,
+                          const double* xyz_dev, double* values_dev, double* gradient_dev, void* stream) {
+  FrameCall fc{};
+  fc.what = FRAME_EVAL;
+  fc.gradient_of = gradient_of;
+  if (gradient_dev && (gradient_of < 0 || gradient_of > 2)) return fail(LSB200_ERR_ARG, "gradient_of must be 0, 1 or 2");
+  if (n < 0 || (n > 0 && (!xyz_dev || !values_dev))) return fail(LSB200_ERR_ARG, "bad argument");
+  const int rc = frame_prepare(fields, transforms, nullptr, false, &fc);
+  return rc ? rc : frame_launch(fields[0], fc, n, xyz_dev, values_dev, gradient_dev, (cudaStream_t)stream);
+}
+int lsb200_frame_eval(const lsb200_handle fields[3], const double* transforms, int gradient_of, int64_t n,
+                      const double* xyz, double* values, double* gradient) {
+  FrameCall fc{};
+  fc.what = FRAME_EVAL;
+  fc.gradient_of = gradient_of;
+  if (gradient && (gradient_of < 0 || gradient_of > 2)) return fail(LSB200_ERR_ARG, "gradient_of must be 0, 1 or 2");
+  const int rc = frame_prepare(fields, transforms, nullptr, false, &fc);
+  return rc ? rc : frame_host(fields[0], fc, n, xyz, values, gradient);
+}
+
+int lsb200_fault_displace_dev(const lsb200_handle fields[3], const double* transforms,
+                              const lsb200_fault_profile* profile, double displacement, int steps, int64_t n,
+                              const double* xyz_dev, double* moved_dev, void* stream) {
+  FrameCall fc{};
+  fc.what = FRAME_DISPLACE;
+  fc.displacement = displacement;
+  fc.steps = steps;
+  if (steps < 0) return fail(LSB200_ERR_ARG, "negative step count");
+  if (n < 0 || (n > 0 && (!xyz_dev || !moved_dev || xyz_dev == moved_dev))) return fail(LSB200_ERR_ARG, "bad argument");
+  const int rc = frame_prepare(fields, transforms, profile, true, &fc);
+  return rc ? rc : frame_launch(fields[0], fc, n, xyz_dev, moved_dev, nullptr, (cudaStream_t)stream);
+}
+int lsb200_fault_displace(const lsb200_handle fields[3], const double* transforms, const lsb200_fault_profile* profile,
+                          double displacement, int steps, int64_t n, const double* xyz, double* moved) {
+  FrameCall fc{};
+  fc.what = FRAME_DISPLACE;
+  fc.displacement = displacement;
+  fc.steps = steps;
+  if (steps < 0) return fail(LSB200_ERR_ARG, "negative step count");
+  const int rc = frame_prepare(fields, transforms, profile, true, &fc);
+  return rc ? rc : frame_host(fields[0], fc, n, xyz, moved, nullptr);
+}
+
+int lsb200_fault_displacement_dev(const lsb200_handle fields[3], const double* transforms,
+                                  const lsb200_fault_profile* profile, double displacement, double fault_offset,
+                                  int64_t n, const double* xyz_dev, double* d_dev, void* stream) {
+  FrameCall fc{};
+  fc.what = FRAME_DISPLACEMENT;
+  fc.displacement = displacement;
+  fc.offset = fault_offset;
+  if (n < 0 || (n > 0 && (!xyz_dev || !d_dev))) return fail(LSB200_ERR_ARG, "bad argument");
+  const int rc = frame_prepare(fields, transforms, profile, true, &fc);
+  return rc ? rc : frame_launch(fields[0], fc, n, xyz_dev, d_dev, nullptr, (cudaStream_t)stream);
+}
+int lsb200_fault_displacement(const lsb200_handle fields[3], const double* transforms,
+                              const lsb200_fault_profile* profile, double displacement, double fault_offset, int64_t n,
+                              const double* xyz, double* d) {
+  FrameCall fc{};
+  fc.what = FRAME_DISPLACEMENT;
+  fc.displacement = displacement;
+  fc.offset = fault_offset;
+  const int rc = frame_prepare(fields, transforms, profile, true, &fc);
+  return rc ? rc : frame_host(fields[0], fc, n, xyz, d, nullptr);
 }
 
 int lsb200_plan_z_ranges(int nz, int k0, int k1, int cz, int zface, int out[6]) {

@@ -25,6 +25,36 @@ struct GridDesc {
 
 constexpr int HALO = 2;
 
+// Per-point geometry (point location, shape functions) is written once for the device and the host: the host
+// instantiation exists for tests/hostsim only (a CPU harness that runs the very per-point code of a gather kernel
+// against the oracle when no GPU is at hand); nothing in liblsb200.so calls it.
+#define LSB_HD __host__ __device__ __forceinline__
+// single-rounding add / multiply (never contracted into an FMA), numpy's operation order
+LSB_HD double rn_add(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dadd_rn(a, b);
+#else
+  volatile double r = a + b;
+  return r;
+#endif
+}
+LSB_HD double rn_mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dmul_rn(a, b);
+#else
+  volatile double r = a * b;
+  return r;
+#endif
+}
+// read-only load of a node value
+LSB_HD double ld_node(const double* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
 // Effective stencil weights squared, pre-multiplied by the constant factors of the
 // row-normalised masks (see fdi_stencil.cuh).
 struct StencilWeights {

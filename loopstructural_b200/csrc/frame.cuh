@@ -1,0 +1,213 @@
+// K9: fault-frame evaluation -- the largest consumer of the solved fields (SURVEY.md section 8 f, rank 1).
+// A fault frame is three scalar fields solved one after the other (three handles, three c vectors).  The reference
+// moves a point cloud through a fault by gathering all three values and the gradient of the middle field at every
+// point, `steps` times, each gather a separate numpy pass over the cloud:
+//   FaultSegment.apply_to_points        LS/modelling/features/fault/_fault_segment.py:315-423
+//   FaultSegment.evaluate_displacement  LS/modelling/features/fault/_fault_segment.py:283-313
+//   profile functions                   LS/modelling/features/fault/_fault_function.py:12-16,40-140,198-226,308-369
+//   world <-> local transforms          LC/geometry/_bounding_box.py:118-176,702-761 behind
+//                                       GeologicalInterpolator.evaluate_value / evaluate_gradient
+//                                       (LI/_geological_interpolator.py:723-741)
+// Every step of that loop is independent per point, so here ONE thread carries one point through all steps:
+// xyz is read once (24 B), the moved point written once (24 B), the 3 x 8 corner values per step come from L2 / HBM
+// as random 8-byte gathers exactly as in k_eval_value_grid.  Grid supports only (the reference's default fault
+// interpolator is FDI); fault-frame features must carry no faults / regions of their own -- the host mirror checks
+// and otherwise leaves the call to the reference.
+//
+// The per-point code is LSB_HD: tests/hostsim runs the same functions on the CPU against the oracle.
+#pragma once
+#include "common.cuh"
+#include "rows.cuh"
+
+namespace lsb {
+
+// one solved field of the frame
+struct FrameField {
+  GridDesc g;
+  const double* c;  // node vector of the handle (halo planes included)
+  double w2l[12];   // world -> local, rows of the 3 x 4 affine: l_a = w2l[4a] x + w2l[4a+1] y + w2l[4a+2] z + w2l[4a+3]
+  double l2w[9];    // local -> world rotation for gradients (row-major 3 x 3)
+};
+struct FrameFields {
+  FrameField f[3];
+};
+
+// one 1-D profile: kinds of LS/modelling/features/fault/_fault_function.py
+struct Profile1D {
+  int kind;  // LSB200_PROFILE_ZEROS / ONES / CUBIC / SMOOTH_PEAK
+  int pad;
+  double w[4];    // CubicFunction.w: w0 v^3 + w1 v^2 + w2 v + w3
+  double lim[2];  // CubicFunction.lim: clamped to the value at the limit outside
+  double min_v, max_v;
+};
+struct FaultProfile {
+  int has_function;  // 0: FaultSegment.faultfunction is None, d = [gx > 0]
+  int composite[3];  // per axis: Composite(pos, neg) (0 at v == 0); else `pos` for every v
+  double scale;      // FaultDisplacement.scale
+  Profile1D pos[3], neg[3];
+};
+
+LSB_HD double cubic_at(const double w[4], const double v) {
+  // w0*v**3 + w1*v**2 + w2*v + w3, left to right, every product and sum rounded once
+  const double v2 = rn_mul(v, v);
+  return rn_add(rn_add(rn_add(rn_mul(w[0], rn_mul(v2, v)), rn_mul(w[1], v2)), rn_mul(w[2], v)), w[3]);
+}
+
+LSB_HD double profile1d(const Profile1D& P, const double v) {
+  switch (P.kind) {
+    case 0: return 0.0;
+    case 1: return 1.0;
+    case 3: {  // smooth_peak: x^4 - 2 x^2 + 1 on [-1, 1], 0 outside
+      if (!(v >= -1.0 && v <= 1.0)) return 0.0;
+      const double v2 = rn_mul(v, v);
+      return rn_add(rn_add(rn_mul(v2, v2), -rn_mul(2.0, v2)), 1.0);
+    }
+    default: {  // CubicFunction.__call__
+      double e = cubic_at(P.w, v);
+      if (v > P.lim[1]) e = cubic_at(P.w, P.lim[1]);
+      if (v < P.lim[0]) e = cubic_at(P.w, P.lim[0]);
+      if (e > P.max_v) e = P.max_v;
+      if (e < P.min_v) e = P.min_v;
+      return e;
+    }
+  }
+}
+
+LSB_HD double profile_axis(const FaultProfile& F, const int a, const double v) {
+  if (!F.composite[a]) return profile1d(F.pos[a], v);
+  if (v > 0.0) return profile1d(F.pos[a], v);
+  if (v < 0.0) return profile1d(F.neg[a], v);
+  return 0.0;
+}
+
+// d of one step before `* displacement` (_fault_segment.py:389-403); *ok = none of the three values is NaN
+LSB_HD double fault_step_d(const FaultProfile& F, const double gx, const double gy, const double gz, const double offset,
+                           bool* ok) {
+  *ok = (gx == gx) && (gy == gy) && (gz == gz);
+  if (!*ok) return 0.0;
+  if (!F.has_function) return gx > 0.0 ? 1.0 : 0.0;
+  return rn_mul(rn_mul(rn_mul(F.scale, profile_axis(F, 0, rn_add(gx, offset))), profile_axis(F, 1, gy)), profile_axis(F, 2, gz));
+}
+
+// value (and, when grad != nullptr, world-frame gradient) of one field at a WORLD point: project, locate, gather.
+// Value: 0.0 when a projected coordinate is NaN, NaN outside the support; gradient: 0 outside.
+LSB_HD double frame_field_at(const FrameField& F, const double xw[3], double* grad) {
+  double l[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    l[a] = rn_add(rn_add(rn_add(rn_mul(F.w2l[4 * a], xw[0]), rn_mul(F.w2l[4 * a + 1], xw[1])), rn_mul(F.w2l[4 * a + 2], xw[2])),
+                  F.w2l[4 * a + 3]);
+  const bool nanrow = (l[0] != l[0]) || (l[1] != l[1]) || (l[2] != l[2]);
+  const CellLoc L = locate(F.g, l);
+  double v = nanrow ? 0.0 : nan("");
+  double gl[3] = {0.0, 0.0, 0.0};
+  if (L.inside) {
+    double cv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cv[k] = ld_node(F.c + corner_local(F.g, L.ci, k));
+    double wgt[8];
+    trilinear_w(L.lc, wgt);
+    v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += wgt[k] * cv[k];
+    if (grad) {
+      double T[3][8];
+      trilinear_grad(F.g, L.lc, T);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        gl[0] += T[0][k] * cv[k];
+        gl[1] += T[1][k] * cv[k];
+        gl[2] += T[2][k] * cv[k];
+      }
+    }
+  }
+  if (grad) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      grad[a] = rn_add(rn_add(rn_mul(F.l2w[3 * a], gl[0]), rn_mul(F.l2w[3 * a + 1], gl[1])), rn_mul(F.l2w[3 * a + 2], gl[2]));
+  }
+  return v;
+}
+
+// FaultSegment.apply_to_points for one point: x is moved in place
+LSB_HD void fault_displace_point(const FrameFields& FF, const FaultProfile& P, const double displacement, const int steps,
+                                 double x[3]) {
+  double g[3];
+  double gx = frame_field_at(FF.f[0], x, nullptr);
+  double gy = frame_field_at(FF.f[1], x, g);
+  double gz = frame_field_at(FF.f[2], x, nullptr);
+  bool ok;
+  const double d0 = fault_step_d(P, gx, gy, gz, 0.0, &ok);
+  if (!(fabs(d0) > 0.0)) return;  // mask = |d| > 0: only these points enter the loop
+  const double inv_steps = 1.0 / (double)steps;
+  for (int i = 0; i < steps; ++i) {
+    if (i > 0) {
+      gx = frame_field_at(FF.f[0], x, nullptr);
+      gy = frame_field_at(FF.f[1], x, g);
+      gz = frame_field_at(FF.f[2], x, nullptr);
+    }
+    const double d = rn_mul(fault_step_d(P, gx, gy, gz, 0.0, &ok), displacement);
+    double gmag = 0.0;
+    if (ok) gmag = sqrt(rn_add(rn_add(rn_mul(g[0], g[0]), rn_mul(g[1], g[1])), rn_mul(g[2], g[2])));
+    if (gmag > 0.0) {
+      g[0] /= gmag;
+      g[1] /= gmag;
+      g[2] /= gmag;
+    }
+    const double s = rn_mul(inv_steps, d);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) x[a] = rn_add(x[a], rn_mul(g[a], s));
+  }
+}
+
+// FaultSegment.evaluate_displacement for one point
+LSB_HD double fault_displacement_point(const FrameFields& FF, const FaultProfile& P, const double displacement,
+                                       const double offset, const double x[3]) {
+  const double gx = frame_field_at(FF.f[0], x, nullptr);
+  const double gy = frame_field_at(FF.f[1], x, nullptr);
+  const double gz = frame_field_at(FF.f[2], x, nullptr);
+  bool ok;
+  return rn_mul(fault_step_d(P, gx, gy, gz, offset, &ok), displacement);
+}
+
+#ifdef __CUDACC__
+// the three values (n,3) and, when grad_out != nullptr, the gradient (n,3) of field `gfield`: one pass over xyz
+__global__ void __launch_bounds__(256)
+    k_frame_eval(const FrameFields FF, const int gfield, const long long n, const double* __restrict__ xyz,
+                 double* __restrict__ val_out, double* __restrict__ grad_out) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    const double x[3] = {xyz[3 * r], xyz[3 * r + 1], xyz[3 * r + 2]};
+    double g[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int f = 0; f < 3; ++f) val_out[3 * r + f] = frame_field_at(FF.f[f], x, (grad_out && f == gfield) ? g : nullptr);
+    if (grad_out) {
+      grad_out[3 * r] = g[0];
+      grad_out[3 * r + 1] = g[1];
+      grad_out[3 * r + 2] = g[2];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_fault_displace(const FrameFields FF, const FaultProfile P, const double displacement, const int steps,
+                     const long long n, const double* __restrict__ xyz, double* __restrict__ out) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    double x[3] = {xyz[3 * r], xyz[3 * r + 1], xyz[3 * r + 2]};
+    fault_displace_point(FF, P, displacement, steps, x);
+    out[3 * r] = x[0];
+    out[3 * r + 1] = x[1];
+    out[3 * r + 2] = x[2];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_fault_displacement(const FrameFields FF, const FaultProfile P, const double displacement, const double offset,
+                         const long long n, const double* __restrict__ xyz, double* __restrict__ out) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    const double x[3] = {xyz[3 * r], xyz[3 * r + 1], xyz[3 * r + 2]};
+    out[r] = fault_displacement_point(FF, P, displacement, offset, x);
+  }
+}
+#endif
+
+}  // namespace lsb

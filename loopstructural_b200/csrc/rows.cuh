@@ -148,15 +148,15 @@ struct CellLoc {
 
 // position_to_cell_index / inside / position_to_local_coordinates
 // (LC/supports/_3d_base_structured.py:251-293; LC/supports/_3d_structured_grid.py:126-146)
-__device__ __forceinline__ CellLoc locate(const GridDesc& g, const double x[3]) {
+LSB_HD CellLoc locate(const GridDesc& g, const double x[3]) {
   CellLoc L;
   L.inside = true;
   const int nc[3] = {g.nx - 1, g.ny - 1, g.nz - 1};
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    const double maxi = __dadd_rn(g.origin[a], __dmul_rn((double)nc[a], g.step[a]));
+    const double maxi = rn_add(g.origin[a], rn_mul((double)nc[a], g.step[a]));
     const double ext = fmax(fabs(maxi - g.origin[a]), 1.0);
-    const double tol = __dmul_rn(__dmul_rn(2.220446049250313e-16, 32.0), ext);
+    const double tol = rn_mul(rn_mul(2.220446049250313e-16, 32.0), ext);
     L.inside = L.inside && (x[a] >= g.origin[a] - tol) && (x[a] <= maxi + tol);
   }
 #pragma unroll
@@ -166,7 +166,7 @@ __device__ __forceinline__ CellLoc locate(const GridDesc& g, const double x[3]) 
     if (L.inside) {
       const double f = floor((x[a] - g.origin[a]) / g.step[a]);
       c = (int)fmin(fmax(f, 0.0), (double)(nc[a] - 1));
-      const double co = __dadd_rn(g.origin[a], __dmul_rn(g.step[a], (double)c));
+      const double co = rn_add(g.origin[a], rn_mul(g.step[a], (double)c));
       l = fmin(fmax((x[a] - co) / g.step[a], 0.0), 1.0);
     }
     L.ci[a] = c;
@@ -177,7 +177,7 @@ __device__ __forceinline__ CellLoc locate(const GridDesc& g, const double x[3]) 
 
 // trilinear shape functions, corner c has offsets (c&1,(c>>1)&1,(c>>2)&1)
 // (LC/supports/_3d_structured_grid.py:90-124)
-__device__ __forceinline__ void trilinear_w(const double l[3], double wgt[8]) {
+LSB_HD void trilinear_w(const double l[3], double wgt[8]) {
   const double x = l[0], y = l[1], z = l[2];
   wgt[0] = (1 - x) * (1 - y) * (1 - z);
   wgt[1] = x * (1 - y) * (1 - z);
@@ -190,7 +190,7 @@ __device__ __forceinline__ void trilinear_w(const double l[3], double wgt[8]) {
 }
 
 // derivative of the shape functions / step (LC/supports/_3d_structured_grid.py:393-454)
-__device__ __forceinline__ void trilinear_grad(const GridDesc& g, const double l[3], double T[3][8]) {
+LSB_HD void trilinear_grad(const GridDesc& g, const double l[3], double T[3][8]) {
   const double x = l[0], y = l[1], z = l[2];
   T[0][0] = (1 - z) * (y - 1); T[0][1] = (1 - y) * (1 - z); T[0][2] = -y * (1 - z); T[0][3] = y * (1 - z);
   T[0][4] = -(1 - y) * z;      T[0][5] = (1 - y) * z;       T[0][6] = -y * z;       T[0][7] = y * z;
@@ -204,7 +204,7 @@ __device__ __forceinline__ void trilinear_grad(const GridDesc& g, const double l
     for (int c = 0; c < 8; ++c) T[a][c] /= g.step[a];
 }
 
-__device__ __forceinline__ long long corner_local(const GridDesc& g, const int ci[3], int c) {
+LSB_HD long long corner_local(const GridDesc& g, const int ci[3], int c) {
   const int i = ci[0] + (c & 1), j = ci[1] + ((c >> 1) & 1), k = ci[2] + ((c >> 2) & 1);
   return (long long)(k - g.k0 + HALO) * g.plane + (long long)j * g.pitch + i;
 }

@@ -19,6 +19,11 @@ LI/_interpolator_factory.py:57-66) -- by a subclass of ``FiniteDifferenceInterpo
 ``solver`` rides in the builder's kwargs to both ``setup_interpolator`` and ``solve_system``
 (LoopStructural/modelling/features/builders/_geological_feature_builder.py:558-569).
 
+``install()`` also patches ``FaultSegment.apply_to_points`` / ``evaluate_displacement`` (the largest consumers of the
+solved fields, LoopStructural/modelling/features/fault/_fault_segment.py:283-423): when the three coordinates of a
+fault frame were solved by the engine and carry no faults / regions of their own, the whole integration runs in one
+device pass (``fault.FaultFrame``); any other case is left to the stock method.
+
 There is no CPU fallback: with ``solver='b200'`` and no usable CUDA device ``solve_system`` raises.
 """
 from __future__ import annotations
@@ -249,6 +254,77 @@ def _make_p1_class():
     return B200P1
 
 
+# -- fault frames: FaultSegment.apply_to_points / evaluate_displacement on the device -------------------------------
+def _frame_of(segment):
+    """FaultFrame over the three coordinate features of a FaultSegment, or None when the reference has to do the
+    work: a coordinate that is not a plain interpolated GeologicalFeature, that carries faults or regions of its
+    own, or whose interpolator was not solved by the grid engine."""
+    from . import fault as fl
+
+    engines, transforms = [], []
+    for i in range(3):
+        feat = segment[i]
+        if type(feat).__name__ != "GeologicalFeature":
+            return None
+        if len(getattr(feat, "regions", [])) > 0 or (getattr(feat, "faults_enabled", True) and len(getattr(feat, "faults", [])) > 0):
+            return None
+        if getattr(feat, "builder", None) is not None:
+            feat.builder.up_to_date()  # lazy solve, as GeologicalFeature.evaluate_value does (_geological_feature.py:139-140)
+        it = getattr(feat, "interpolator", None)
+        eng = it._b200_engine_current() if hasattr(it, "_b200_engine_current") else None
+        if eng is None or getattr(eng, "kind", "grid") != "grid":
+            return None
+        engines.append(eng)
+        bb = getattr(it, "bounding_box", None)
+        transforms.append(np.eye(4) if bb is None else np.asarray(bb.world_to_local_matrix, dtype=float))
+    key = tuple(id(e) for e in engines)
+    cached = getattr(segment, "_b200_frame", None)
+    if cached is None or cached[0] != key:
+        cached = (key, fl.FaultFrame(engines, transforms))
+        segment._b200_frame = cached
+    return cached[1]
+
+
+def _make_fault_methods(stock_apply, stock_displacement):
+    from . import fault as fl
+
+    def apply_to_points(self, points, reverse=False, precomputed_gx=None):
+        """FaultSegment.apply_to_points (LS/modelling/features/fault/_fault_segment.py:315-423) in one device pass when
+        the three frame coordinates were solved by the B200 engine; the stock method otherwise."""
+        frame = prof = None
+        if precomputed_gx is None:
+            prof = fl.profile_from_reference(self.faultfunction)
+            if prof is not None:
+                frame = _frame_of(self)
+        if frame is None:
+            return stock_apply(self, points, reverse=reverse, precomputed_gx=precomputed_gx)
+        return frame.apply_to_points(np.array(points, dtype=float), prof, float(self.displacement), int(self.steps))
+
+    def evaluate_displacement(self, points):
+        prof = fl.profile_from_reference(self.faultfunction)
+        frame = _frame_of(self) if prof is not None else None
+        if frame is None:
+            return stock_displacement(self, points)
+        return frame.evaluate_displacement(np.array(points, dtype=float), prof, float(self.displacement),
+                                           float(self.fault_offset))
+
+    return apply_to_points, evaluate_displacement
+
+
+def _install_fault_patch():
+    """Patch FaultSegment when LoopStructural itself is importable (the interpolation package alone is enough for
+    everything else in this module)."""
+    try:
+        from LoopStructural.modelling.features.fault import FaultSegment
+    except Exception:
+        return
+    if "fault_stock" in _installed:
+        stock = _installed["fault_stock"]
+    else:
+        stock = _installed["fault_stock"] = (FaultSegment, FaultSegment.apply_to_points, FaultSegment.evaluate_displacement)
+    FaultSegment.apply_to_points, FaultSegment.evaluate_displacement = _make_fault_methods(stock[1], stock[2])
+
+
 def install():
     """Register the B200 subclasses in the reference's ``interpolator_map`` (idempotent).  Returns the classes."""
     import loop_interpolation as li
@@ -261,6 +337,7 @@ def install():
                                T.PIECEWISE_LINEAR: li.interpolator_map[T.PIECEWISE_LINEAR]}
     li.interpolator_map[T.FINITE_DIFFERENCE] = _installed["fdi"]
     li.interpolator_map[T.PIECEWISE_LINEAR] = _installed["p1"]
+    _install_fault_patch()
     return {"FDI": _installed["fdi"], "P1": _installed["p1"]}
 
 
@@ -270,3 +347,6 @@ def uninstall():
 
     for key, cls in _installed.get("stock", {}).items():
         li.interpolator_map[key] = cls
+    if "fault_stock" in _installed:
+        cls, stock_apply, stock_displacement = _installed["fault_stock"]
+        cls.apply_to_points, cls.evaluate_displacement = stock_apply, stock_displacement

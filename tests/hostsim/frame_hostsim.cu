@@ -1,0 +1,100 @@
+// TEST INFRASTRUCTURE ONLY (not part of liblsb200.so, never loaded by the product): runs the per-point code of the
+// fault-frame kernels (loopstructural_b200/csrc/frame.cuh -- the very LSB_HD functions k_frame_eval /
+// k_fault_displace / k_fault_displacement call per thread) in a host loop, so that tests/ can compare it with the
+// oracle and the golden fixtures in a container that has no GPU.  The kernels' launch code is not exercised here;
+// tests/test_zz_fault_gpu.py does that on the device.
+//
+//   nvcc -O2 -std=c++17 -Xcompiler -fPIC -shared -o tests/hostsim/libframe_hostsim.so tests/hostsim/frame_hostsim.cu
+#include "../../include/lsb200.h"
+
+#include <string.h>
+
+#include <vector>
+
+#include "../../loopstructural_b200/csrc/frame.cuh"
+
+using namespace lsb;
+
+namespace {
+struct HostFrame {
+  FrameFields FF;
+  std::vector<double> store[3];  // node vectors in the handle's layout: two halo planes either side
+};
+
+void build(HostFrame& H, const int64_t* nsteps, const double* origin, const double* step, const double* const c[3],
+           const double* transforms) {
+  for (int f = 0; f < 3; ++f) {
+    FrameField& F = H.FF.f[f];
+    GridDesc& g = F.g;
+    g.nx = (int)nsteps[3 * f]; g.ny = (int)nsteps[3 * f + 1]; g.nz = (int)nsteps[3 * f + 2];
+    g.k0 = 0; g.k1 = g.nz; g.nzl = g.nz;
+    g.pitch = g.nx;
+    g.plane = (long long)g.pitch * g.ny;
+    g.nloc = g.plane * g.nzl;
+    g.nall = g.plane * (g.nzl + 2 * HALO);
+    for (int a = 0; a < 3; ++a) { g.origin[a] = origin[3 * f + a]; g.step[a] = step[3 * f + a]; }
+    H.store[f].assign((size_t)g.nall, 0.0);
+    memcpy(H.store[f].data() + (size_t)HALO * g.plane, c[f], sizeof(double) * (size_t)g.nloc);
+    F.c = H.store[f].data();
+    if (transforms) {
+      for (int i = 0; i < 12; ++i) F.w2l[i] = transforms[21 * f + i];
+      for (int i = 0; i < 9; ++i) F.l2w[i] = transforms[21 * f + 12 + i];
+    } else {
+      for (int i = 0; i < 12; ++i) F.w2l[i] = (i % 5 == 0) ? 1.0 : 0.0;
+      for (int i = 0; i < 9; ++i) F.l2w[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    }
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int hostsim_frame_eval(const int64_t* nsteps, const double* origin, const double* step, const double* c0, const double* c1,
+                       const double* c2, const double* transforms, int gradient_of, int64_t n, const double* xyz,
+                       double* values, double* gradient) {
+  HostFrame H;
+  const double* c[3] = {c0, c1, c2};
+  build(H, nsteps, origin, step, c, transforms);
+  for (int64_t r = 0; r < n; ++r) {  // body of k_frame_eval
+    const double x[3] = {xyz[3 * r], xyz[3 * r + 1], xyz[3 * r + 2]};
+    double g[3] = {0.0, 0.0, 0.0};
+    for (int f = 0; f < 3; ++f) values[3 * r + f] = frame_field_at(H.FF.f[f], x, (gradient && f == gradient_of) ? g : nullptr);
+    if (gradient) { gradient[3 * r] = g[0]; gradient[3 * r + 1] = g[1]; gradient[3 * r + 2] = g[2]; }
+  }
+  return 0;
+}
+
+int hostsim_fault_displace(const int64_t* nsteps, const double* origin, const double* step, const double* c0,
+                           const double* c1, const double* c2, const double* transforms,
+                           const lsb200_fault_profile* profile, double displacement, int steps, int64_t n,
+                           const double* xyz, double* moved) {
+  HostFrame H;
+  const double* c[3] = {c0, c1, c2};
+  build(H, nsteps, origin, step, c, transforms);
+  FaultProfile P;
+  memcpy(&P, profile, sizeof(P));
+  for (int64_t r = 0; r < n; ++r) {  // body of k_fault_displace
+    double x[3] = {xyz[3 * r], xyz[3 * r + 1], xyz[3 * r + 2]};
+    fault_displace_point(H.FF, P, displacement, steps, x);
+    moved[3 * r] = x[0]; moved[3 * r + 1] = x[1]; moved[3 * r + 2] = x[2];
+  }
+  return 0;
+}
+
+int hostsim_fault_displacement(const int64_t* nsteps, const double* origin, const double* step, const double* c0,
+                               const double* c1, const double* c2, const double* transforms,
+                               const lsb200_fault_profile* profile, double displacement, double offset, int64_t n,
+                               const double* xyz, double* d) {
+  HostFrame H;
+  const double* c[3] = {c0, c1, c2};
+  build(H, nsteps, origin, step, c, transforms);
+  FaultProfile P;
+  memcpy(&P, profile, sizeof(P));
+  for (int64_t r = 0; r < n; ++r) {  // body of k_fault_displacement
+    const double x[3] = {xyz[3 * r], xyz[3 * r + 1], xyz[3 * r + 2]};
+    d[r] = fault_displacement_point(H.FF, P, displacement, offset, x);
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -126,3 +126,93 @@ def test_model_without_the_b200_solver_is_untouched_by_the_plugin(ls):
     it = model["strati"].interpolator
     assert type(it).__name__ == "B200FiniteDifferenceInterpolator"
     assert it.latest_solve_timing["backend"] == "python" and "dxx" in it.constraints and not OracleEngine.instances
+
+
+class OracleFaultFrame:
+    """Same surface as loopstructural_b200.fault.FaultFrame, numerics from oracle/fault_oracle.py (test stand-in)."""
+
+    calls = []
+
+    def __init__(self, engines, world_to_local=None):
+        from oracle import fault_oracle as fa
+
+        self.fa = fa
+        self.fields = [fa.FrameField(e.grid, e.c, None if world_to_local is None else np.asarray(world_to_local[i]))
+                       for i, e in enumerate(engines)]
+
+    def _profile(self, p):
+        fa = self.fa
+        if not p.has_function:
+            return fa.FaultProfile(None, 0.0)
+
+        def one(q):
+            return fa.Profile1D(int(q.kind), tuple(q.w), tuple(q.lim), float(q.min_v), float(q.max_v))
+
+        return fa.FaultProfile(tuple(fa.AxisProfile(one(p.pos[a]), one(p.neg[a]) if p.composite[a] else None) for a in range(3)),
+                               float(p.scale))
+
+    def apply_to_points(self, xyz, profile, displacement, steps):
+        OracleFaultFrame.calls.append("apply")
+        return self.fa.apply_to_points(self.fields, self._profile(profile), displacement, steps, xyz)
+
+    def evaluate_displacement(self, xyz, profile, displacement, fault_offset=0.0):
+        OracleFaultFrame.calls.append("displacement")
+        return self.fa.evaluate_displacement(self.fields, self._profile(profile), displacement, fault_offset, xyz)
+
+
+def _fault_model(ls, **kw):
+    from LoopStructural.datasets import load_intrusion
+
+    data, bb = load_intrusion()
+    model = ls.GeologicalModel(bb[0, :], bb[1, :])
+    model.data = data
+    model.create_and_add_fault("fault", 500, nelements=2000, interpolatortype="FDI", buffer=0.3, **kw)
+    model.create_and_add_foliation("strati", nelements=2000, interpolatortype="FDI", **kw)
+    model.update()
+    return model, bb
+
+
+def test_fault_frame_and_faulted_foliation_through_the_model(ls, monkeypatch):
+    """BASELINE configs[3] in small: a fault frame (three coupled FDI solves with orthogonality rows) and a foliation
+    faulted by it, all with solver='b200'; FaultSegment.apply_to_points / evaluate_displacement go to the frame."""
+    from loopstructural_b200 import fault as fl, plugin
+
+    monkeypatch.setattr(fl, "FaultFrame", OracleFaultFrame)
+    OracleFaultFrame.calls.clear()
+    model, bb = _fault_model(ls, solver="b200")
+    fault = model["fault"]
+    for i in range(3):
+        it = fault[i].interpolator
+        assert type(it).__name__ == "B200FiniteDifferenceInterpolator" and it.latest_solve_timing["backend"] == "b200"
+    assert model["strati"].interpolator.latest_solve_timing["backend"] == "b200"
+    assert "apply" in OracleFaultFrame.calls  # the foliation's data were un-faulted through the frame during set-up
+    rng = np.random.default_rng(5)
+    pts = bb[0] + rng.uniform(-0.2, 1.2, (400, 3)) * (bb[1] - bb[0])
+    OracleFaultFrame.calls.clear()
+    moved = fault.apply_to_points(pts)
+    disp = fault.evaluate_displacement(pts)
+    strati = model.evaluate_feature_value("strati", pts)
+    assert OracleFaultFrame.calls.count("apply") >= 2 and "displacement" in OracleFaultFrame.calls
+    c_frame = [np.array(fault[i].interpolator.c) for i in range(3)]
+
+    # an unsupported profile goes back to the stock method
+    OracleFaultFrame.calls.clear()
+    keep = fault._faultfunction
+    fault._faultfunction = lambda gx, gy, gz: np.ones_like(gx)
+    fault.apply_to_points(pts[:5])
+    assert OracleFaultFrame.calls == []
+    fault._faultfunction = keep
+
+    plugin.uninstall()
+    stock, _ = _fault_model(ls)
+    sf = stock["fault"]
+    assert sf.apply_to_points.__func__.__qualname__.startswith("FaultSegment.")
+    for i in range(3):
+        cs = np.asarray(sf[i].interpolator.c)
+        assert np.linalg.norm(c_frame[i] - cs) / np.sqrt(cs.size) / float(cs.max() - cs.min()) <= 1e-6  # the bar of BASELINE.json's north star
+    ext = float(np.max(bb[1] - bb[0]))
+    np.testing.assert_allclose(moved, sf.apply_to_points(pts), rtol=0, atol=1e-6 * ext)
+    np.testing.assert_allclose(disp, sf.evaluate_displacement(pts), rtol=0, atol=1e-6 * abs(sf.displacement))
+    s_ref = stock.evaluate_feature_value("strati", pts)
+    np.testing.assert_array_equal(np.isnan(strati), np.isnan(s_ref))
+    np.testing.assert_allclose(strati, s_ref, rtol=0, atol=1e-6 * float(np.nanmax(s_ref) - np.nanmin(s_ref)), equal_nan=True)

@@ -1,0 +1,159 @@
+"""Fault-frame evaluation on the CUDA path (csrc/frame.cuh through lsb200_frame_eval / lsb200_fault_displace /
+lsb200_fault_displacement) against the golden fixtures of the unmodified reference (tests/golden/fault_*.npz:
+FaultSegment.apply_to_points / evaluate_displacement of a faulted GeologicalModel) and against the oracle.
+
+NOTE (round 1): these kernels were written after the round's GPU budget was spent.  Their per-point code is checked
+on the CPU by tests/test_frame_hostsim.py (same LSB_HD functions, host instantiation); the launches below have not
+run on a device yet, hence the file sorts last."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from golden_helpers import GOLDEN, fault_case
+from oracle import fault_oracle as fa
+from oracle import fdi_oracle as fo
+
+pytestmark = pytest.mark.gpu
+CASES = sorted(os.path.basename(p)[6:-4] for p in glob.glob(os.path.join(GOLDEN, "fault_*.npz")))
+
+
+def _frame(z):
+    from loopstructural_b200 import Engine, build
+    from loopstructural_b200.fault import FaultFrame
+
+    build.build()
+    engines = []
+    for i in range(3):
+        e = Engine(z[f"f{i}_ncells"] + 1, z[f"f{i}_origin"], z[f"f{i}_step"])
+        e.set_c(z[f"f{i}_c"])
+        engines.append(e)
+    return FaultFrame(engines, [z[f"f{i}_w2l"] for i in range(3)]), engines
+
+
+def _profile(z):
+    from test_frame_hostsim import native_profile
+
+    return native_profile(z)
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_frame_gathers_match_the_reference(tag):
+    z = np.load(os.path.join(GOLDEN, f"fault_{tag}.npz"))
+    frame, engines = _frame(z)
+    vals, grad = frame.evaluate(z["points"], gradient_of=1)
+    np.testing.assert_array_equal(np.isnan(vals), np.isnan(z["frame_values"]))
+    np.testing.assert_allclose(vals, z["frame_values"], rtol=0, atol=1e-11, equal_nan=True)
+    np.testing.assert_allclose(grad, z["frame_gradient1"], rtol=0, atol=1e-13)
+    vals2, none = frame.evaluate(z["points"], gradient_of=None)
+    assert none is None
+    np.testing.assert_array_equal(vals2, vals)
+    # the fused pass equals the three separate gathers of the existing evaluation entry points
+    w2l = z["f0_w2l"]
+    local = z["points"] @ w2l[:3, :3].T + w2l[:3, 3]
+    np.testing.assert_allclose(vals[:, 0], engines[0].evaluate_value(local), rtol=0, atol=1e-12, equal_nan=True)
+    for e in engines:
+        e.close()
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_apply_to_points_matches_the_reference(tag):
+    z = np.load(os.path.join(GOLDEN, f"fault_{tag}.npz"))
+    frame, engines = _frame(z)
+    pts = z["points"]
+    moved = frame.apply_to_points(pts, _profile(z), float(z["displacement"]), int(z["steps"]))
+    np.testing.assert_array_equal(np.isnan(moved), np.isnan(z["moved"]))
+    still = np.all((z["moved"] == pts) | np.isnan(pts), axis=1)
+    np.testing.assert_array_equal(moved[still], pts[still])
+    np.testing.assert_allclose(moved, z["moved"], rtol=0, atol=1e-9, equal_nan=True)  # coordinates are O(1e4)
+    for e in engines:
+        e.close()
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_evaluate_displacement_matches_the_reference(tag):
+    z = np.load(os.path.join(GOLDEN, f"fault_{tag}.npz"))
+    frame, engines = _frame(z)
+    disp = float(z["displacement"])
+    d = frame.evaluate_displacement(z["points"], _profile(z), disp, float(z["fault_offset"]))
+    np.testing.assert_allclose(d, z["displacement_at"], rtol=1e-12, atol=1e-12 * abs(disp))
+    for e in engines:
+        e.close()
+
+
+def test_large_cloud_device_pointers_and_properties():
+    """2e6 points on three 64^3 fields through the device-pointer entry point: zero displacement and zero steps are
+    the identity, the moved distance never exceeds |displacement| * max|profile|, and a sample equals the oracle."""
+    import torch
+
+    from loopstructural_b200 import Engine, build
+    from loopstructural_b200 import fault as fl
+
+    build.build()
+    rng = np.random.default_rng(11)
+    n_nodes = 64
+    grid = fo.Grid.from_cells(np.array([n_nodes - 1] * 3), np.zeros(3), np.full(3, 1.0 / (n_nodes - 1)))
+    ax = np.arange(n_nodes) / (n_nodes - 1)
+    X, Y, Z = np.meshgrid(ax, ax, ax, indexing="ij")
+    flat = lambda a: np.ascontiguousarray(a.transpose(2, 1, 0).ravel())  # noqa: E731  (i fastest)
+    cs = [flat(2.0 * (X - 0.5) + 0.2 * np.sin(3 * Y)), flat(Y + 0.3 * Z * Z + 0.1 * np.cos(4 * X)), flat(2.0 * (Z - 0.5) + 0.1 * X * Y)]
+    engines = []
+    for c in cs:
+        e = Engine(grid.nsteps, grid.origin, grid.step)
+        e.set_c(c)
+        engines.append(e)
+    frame = fl.FaultFrame(engines)
+    hw = fl.profile1d(fl.PROFILE_CUBIC, (2.0, -3.0, 0.0, 1.0), (0.0, 1.0))
+    fw = fl.profile1d(fl.PROFILE_CUBIC, (2.0, 3.0, 0.0, -1.0), (-1.0, 0.0))
+    prof = fl.fault_profile([(hw, fw), fl.profile1d(fl.PROFILE_ONES), fl.profile1d(fl.PROFILE_SMOOTH_PEAK)], 0.5)
+    n = 2_000_000
+    pts = rng.uniform(-0.1, 1.1, (n, 3))
+    x = torch.from_numpy(pts).cuda()
+    out = torch.empty_like(x)
+    st = torch.cuda.current_stream().cuda_stream
+    frame.apply_to_points_device(x.data_ptr(), out.data_ptr(), n, prof, 0.05, 10, stream=st)
+    moved = out.cpu().numpy()
+    frame.apply_to_points_device(x.data_ptr(), out.data_ptr(), n, prof, 0.0, 10, stream=st)
+    assert torch.equal(out, x)
+    frame.apply_to_points_device(x.data_ptr(), out.data_ptr(), n, prof, 0.05, 0, stream=st)
+    assert torch.equal(out, x)
+    shift = np.linalg.norm(moved - pts, axis=1)
+    assert shift.max() <= 0.05 * 0.5 * (1 + 1e-12) and np.sum(shift > 0) > n // 4
+    # the host-buffer entry point gives the same bits
+    np.testing.assert_array_equal(frame.apply_to_points(pts[:100000], prof, 0.05, 10), moved[:100000])
+    fields = [fa.FrameField(grid, c, None) for c in cs]
+    oprof = fa.FaultProfile((fa.AxisProfile(fa.Profile1D(fa.CUBIC, (2.0, -3.0, 0.0, 1.0), (0.0, 1.0)),
+                                            fa.Profile1D(fa.CUBIC, (2.0, 3.0, 0.0, -1.0), (-1.0, 0.0))),
+                             fa.AxisProfile(fa.Profile1D(fa.ONES)), fa.AxisProfile(fa.Profile1D(fa.SMOOTH_PEAK))), 0.5)
+    ref = fa.apply_to_points(fields, oprof, 0.05, 10, pts[:20000])
+    err = np.abs(moved[:20000] - ref).max(axis=1)
+    assert np.sum(err > 1e-13) <= 5 and err.max() < 0.05 / 10  # a cell-face crossing within rounding may differ for a step
+    vals = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+    grad = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+    frame.evaluate_device(x.data_ptr(), vals.data_ptr(), grad.data_ptr(), n, gradient_of=1, stream=st)
+    ov, og = fa.frame_eval(fields, pts[:20000], 1)
+    np.testing.assert_allclose(vals[:20000].cpu().numpy(), ov, rtol=0, atol=1e-13, equal_nan=True)
+    np.testing.assert_allclose(grad[:20000].cpu().numpy(), og, rtol=0, atol=1e-11)
+    for e in engines:
+        e.close()
+
+
+def test_argument_errors():
+    from loopstructural_b200 import Engine, build
+    from loopstructural_b200 import fault as fl
+    from loopstructural_b200._native import Lsb200Error
+
+    build.build()
+    engines = [Engine([5, 5, 5], [0, 0, 0], [1, 1, 1]) for _ in range(3)]
+    frame = fl.FaultFrame(engines)
+    with pytest.raises(Lsb200Error):  # no solution on the handles yet
+        frame.evaluate(np.zeros((4, 3)))
+    for e in engines:
+        e.set_c(np.zeros(125))
+    bad = fl.fault_profile([fl.profile1d(7)] * 3)
+    with pytest.raises(Lsb200Error):
+        frame.apply_to_points(np.zeros((4, 3)), bad, 1.0, 2)
+    assert frame.apply_to_points(np.zeros((0, 3)), fl.fault_profile(None), 1.0, 2).shape == (0, 3)
+    for e in engines:
+        e.close()
