@@ -210,6 +210,72 @@ def measure_eval(eng, local, npts=20_000_000, npts_host=2_000_000):
     return res
 
 
+def measure_fault(local, n_nodes=128, npts=10_000_000, steps=10, cpu_points=100_000):
+    """Fault-frame evaluation (SURVEY.md section 8 f rank 1; FaultSegment.apply_to_points,
+    LS/modelling/features/fault/_fault_segment.py:315-423): three synthetic 128^3 fields, a device-resident uniform
+    cloud, BaseFault-shaped profile, `steps` integration steps in ONE launch; beside it the numpy restatement of the
+    reference's loop (oracle/fault_oracle.py) on a sample of the same cloud."""
+    import torch
+
+    from loopstructural_b200 import Engine
+    from loopstructural_b200 import fault as fl
+    from oracle import fault_oracle as fa
+    from oracle import fdi_oracle as fo
+
+    dev = torch.device("cuda", local)
+    grid = fo.Grid.from_cells(np.array([n_nodes - 1] * 3), np.zeros(3), np.full(3, 1.0 / (n_nodes - 1)))
+    ax = np.arange(n_nodes) / (n_nodes - 1)
+    X, Y, Z = np.meshgrid(ax, ax, ax, indexing="ij")
+    flat = lambda a: np.ascontiguousarray(a.transpose(2, 1, 0).ravel())  # noqa: E731
+    cs = [flat(2.0 * (X - 0.5) + 0.2 * np.sin(3 * Y)), flat(Y + 0.3 * Z * Z + 0.1 * np.cos(4 * X)), flat(2.0 * (Z - 0.5) + 0.1 * X * Y)]
+    engines = []
+    for c in cs:
+        e = Engine(grid.nsteps, grid.origin, grid.step, device=local)
+        e.set_c(c)
+        engines.append(e)
+    frame = fl.FaultFrame(engines)
+    hw, fw = (2.0, -3.0, 0.0, 1.0), (2.0, 3.0, 0.0, -1.0)
+    prof = fl.fault_profile([(fl.profile1d(fl.PROFILE_CUBIC, hw, (0.0, 1.0)), fl.profile1d(fl.PROFILE_CUBIC, fw, (-1.0, 0.0))),
+                             fl.profile1d(fl.PROFILE_ONES), fl.profile1d(fl.PROFILE_SMOOTH_PEAK)], 0.5)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    cloud = torch.rand((npts, 3), dtype=torch.float64, device=dev, generator=gen)
+    out = torch.empty_like(cloud)
+    vals = torch.empty_like(cloud)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def timed(fn, reps=5):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e-3 / reps
+
+    t_move = timed(lambda: frame.apply_to_points_device(cloud.data_ptr(), out.data_ptr(), npts, prof, 0.05, steps, st))
+    t_eval = timed(lambda: frame.evaluate_device(cloud.data_ptr(), vals.data_ptr(), out.data_ptr(), npts, 1, st))
+    frame.apply_to_points_device(cloud.data_ptr(), out.data_ptr(), npts, prof, 0.05, steps, st)
+    torch.cuda.synchronize()
+    sample = cloud[:cpu_points].cpu().numpy()
+    moved = out[:cpu_points].cpu().numpy()
+    fields = [fa.FrameField(grid, c, None) for c in cs]
+    oprof = fa.FaultProfile((fa.AxisProfile(fa.Profile1D(fa.CUBIC, hw, (0.0, 1.0)), fa.Profile1D(fa.CUBIC, fw, (-1.0, 0.0))),
+                             fa.AxisProfile(fa.Profile1D(fa.ONES)), fa.AxisProfile(fa.Profile1D(fa.SMOOTH_PEAK))), 0.5)
+    t0 = time.perf_counter()
+    ref = fa.apply_to_points(fields, oprof, 0.05, steps, sample)
+    t_cpu = time.perf_counter() - t0
+    for e in engines:
+        e.close()
+    return {"workload": f"3 x {n_nodes}^3 fields, {npts} device-resident points, {steps} steps, cubic/ones/smooth_peak profile",
+            "displace_points_per_second": npts / t_move, "displace_seconds": t_move,
+            "frame_eval_points_per_second": npts / t_eval,
+            "moved_fraction": float((np.abs(moved - sample).max(axis=1) > 0).mean()),
+            "max_abs_diff_vs_oracle_sample": float(np.abs(moved - ref).max()),
+            "cpu_port_points_per_second": cpu_points / t_cpu, "cpu_sample_points": cpu_points}
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -388,6 +454,12 @@ def run_ours(args):
                           f"{timing['preprocess_seconds']:.1f} s, A^T A {timing['gram_seconds']:.1f} s, CG "
                           f"{timing['solve_seconds']:.1f} s); scipy's CSR matvec is single-threaded, numpy's BLAS dot products use the other threads",
             }
+        if world == 1 and not args.no_fault:
+            # last, after everything else has been measured: these kernels are the newest code in the library
+            try:
+                line["fault"] = measure_fault(local)
+            except Exception as exc:  # noqa: BLE001
+                line["fault"] = {"error": f"{type(exc).__name__}: {exc}"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -408,6 +480,7 @@ def main():
     ap.add_argument("--n-gradient", type=int, default=10_000)
     ap.add_argument("--ref-n", type=int, default=64, help="nodes per axis of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fault", action="store_true", help="skip the fault-frame evaluation measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
