@@ -267,6 +267,17 @@ int lsb200_fault_displacement_dev(const lsb200_handle fields[3], const double* t
                                   const lsb200_fault_profile* profile, double displacement, double fault_offset,
                                   int64_t n, const double* xyz_dev, double* d_dev, void* stream);
 
+/* Frame-orthogonality rows from a solved field (GeologicalFeatureBuilder.install_gradient_constraint,
+ * LoopStructural/modelling/features/builders/_geological_feature_builder.py:293-318 -> FDI
+ * add_gradient_orthogonal_constraints, LI/_finite_difference_interpolator.py:478-539): for every element_step-th cell e
+ * of h's support one row  v . grad(phi) = b  at the cell's barycentre, v = the normalised gradient of `other`
+ * (a solved grid handle on the same device owning every plane) there, row-normalised, weight `weight`.  The
+ * barycentres (h's LOCAL coordinates) are handed to `other` through other_transform (21 doubles as in
+ * lsb200_frame_eval, NULL = identity) exactly as the reference hands them to feature.evaluate_gradient.
+ * n_rows_out (may be NULL): rows this handle keeps (all ceil(n_cells / element_step) on a full handle). */
+int lsb200_add_field_orthogonal_rows(lsb200_handle h, lsb200_handle other, const double* other_transform,
+                                     int64_t element_step, double weight, double b, int64_t* n_rows_out);
+
 /* Introspection (no device needed): the output planes of the three launches of the tiled FDI operator for a
  * handle owning the planes [k0,k1) of nz: out = {A0,A1, B0,B1, U0,U1}, A/B = z-general ranges next to the z faces,
  * U = uniform range; see plan_z_ranges in csrc/api.cu. */

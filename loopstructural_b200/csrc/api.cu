@@ -891,6 +891,41 @@ int lsb200_add_pair_rows(lsb200_handle h, int64_t n, const double* xyz_i, const 
   return 0;
 }
 
+static int make_frame_field(const lsb200_ctx* h, const double* t, const char* what, int f, FrameField* F);  // below, frame section
+
+int lsb200_add_field_orthogonal_rows(lsb200_handle h, lsb200_handle other, const double* other_transform,
+                                     int64_t element_step, double weight, double b, int64_t* n_rows_out) {
+  if (!h) return fail(LSB200_ERR_ARG, "null handle");
+  if (n_rows_out) *n_rows_out = 0;
+  if (h->kind != LSB200_SUPPORT_GRID) return fail(LSB200_ERR_STATE, "field-orthogonality rows need a grid handle");
+  if (element_step < 1) return fail(LSB200_ERR_ARG, "element_step must be >= 1");
+  if (other == h) return fail(LSB200_ERR_ARG, "a field cannot be made orthogonal to itself");
+  FrameField F;
+  int rc = make_frame_field(other, other_transform, "other field", 0, &F);
+  if (rc) return rc;
+  if (other->device != h->device) return fail(LSB200_ERR_ARG, "the two handles live on different devices");
+  CK(cudaSetDevice(h->device));
+  const long long n_el = (long long)(h->g.nx - 1) * (h->g.ny - 1) * (h->g.nz - 1);
+  const long long n = (n_el + element_step - 1) / element_step;  // element_idx[::step]
+  if (n == 0) return 0;
+  CK(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * 2, h->stream));
+  RowBlock rb{};
+  rc = alloc_block(h, rb, n, 8);
+  if (rc) return rc;
+  const int nb = (int)std::min<long long>((n + 127) / 128, 4096);
+  k_fdi_field_orthogonal_rows<<<nb, 128, 0, h->stream>>>(h->g, F, (long long)element_step, n, weight, b, rb, 0, h->status);
+  CKL();
+  h->launches++;
+  unsigned long long st[2];
+  CK(cudaMemcpyAsync(st, h->status, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (n_rows_out) *n_rows_out = (int64_t)st[0];
+  h->rows_kept += (long long)st[0];
+  h->pending.push_back(rb);
+  h->finalized = false;
+  return 0;
+}
+
 int lsb200_clear_rows(lsb200_handle h) {
   if (!h) return fail(LSB200_ERR_ARG, "null handle");
   CK(cudaSetDevice(h->device));
@@ -1454,27 +1489,32 @@ int lsb200_eval_gradient(lsb200_handle h, int64_t n, const double* xyz, double* 
 static_assert(sizeof(lsb200_profile1d) == sizeof(Profile1D), "profile layout");
 static_assert(sizeof(lsb200_fault_profile) == sizeof(FaultProfile), "fault profile layout");
 
-// the three handles of a frame -> kernel argument; every handle: grid kind, same device, all planes, a solution
+// one solved field -> kernel argument: grid kind, all planes, a solution; t = 21 doubles (3 x 4 world -> local,
+// 3 x 3 local -> world rotation) or null = identity
+static int make_frame_field(const lsb200_ctx* h, const double* t, const char* what, int f, FrameField* F) {
+  if (!h) return fail(LSB200_ERR_ARG, "%s %d: null handle", what, f);
+  if (h->kind != LSB200_SUPPORT_GRID) return fail(LSB200_ERR_ARG, "%s %d: only grid handles are supported", what, f);
+  if (h->g.k0 != 0 || h->g.k1 != h->g.nz) return fail(LSB200_ERR_STATE, "%s %d: the handle must own every plane", what, f);
+  if (!h->have_c) return fail(LSB200_ERR_STATE, "%s %d: no solution on the device yet (solve or set_c first)", what, f);
+  F->g = h->g;
+  F->c = h->x;
+  if (t) {
+    for (int i = 0; i < 12; ++i) F->w2l[i] = t[i];
+    for (int i = 0; i < 9; ++i) F->l2w[i] = t[12 + i];
+  } else {
+    for (int i = 0; i < 12; ++i) F->w2l[i] = (i % 5 == 0) ? 1.0 : 0.0;  // [I | 0]
+    for (int i = 0; i < 9; ++i) F->l2w[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  }
+  return 0;
+}
+
+// the three handles of a frame -> kernel argument; all on one device
 static int make_frame(const lsb200_handle fields[3], const double* transforms, FrameFields* FF) {
   if (!fields) return fail(LSB200_ERR_ARG, "null field array");
   for (int f = 0; f < 3; ++f) {
-    const lsb200_ctx* h = fields[f];
-    if (!h) return fail(LSB200_ERR_ARG, "fault-frame field %d: null handle", f);
-    if (h->kind != LSB200_SUPPORT_GRID) return fail(LSB200_ERR_ARG, "fault-frame field %d: only grid handles are supported", f);
-    if (h->device != fields[0]->device) return fail(LSB200_ERR_ARG, "fault-frame fields live on different devices");
-    if (h->g.k0 != 0 || h->g.k1 != h->g.nz) return fail(LSB200_ERR_STATE, "fault-frame field %d: the handle must own every plane", f);
-    if (!h->have_c) return fail(LSB200_ERR_STATE, "fault-frame field %d: no solution on the device yet (solve or set_c first)", f);
-    FrameField& F = FF->f[f];
-    F.g = h->g;
-    F.c = h->x;
-    if (transforms) {
-      const double* t = transforms + 21 * f;
-      for (int i = 0; i < 12; ++i) F.w2l[i] = t[i];
-      for (int i = 0; i < 9; ++i) F.l2w[i] = t[12 + i];
-    } else {
-      for (int i = 0; i < 12; ++i) F.w2l[i] = (i % 5 == 0) ? 1.0 : 0.0;  // [I | 0]
-      for (int i = 0; i < 9; ++i) F.l2w[i] = (i % 4 == 0) ? 1.0 : 0.0;
-    }
+    const int rc = make_frame_field(fields[f], transforms ? transforms + 21 * f : nullptr, "fault-frame field", f, &FF->f[f]);
+    if (rc) return rc;
+    if (fields[f]->device != fields[0]->device) return fail(LSB200_ERR_ARG, "fault-frame fields live on different devices");
   }
   return 0;
 }

@@ -170,7 +170,86 @@ LSB_HD double fault_displacement_point(const FrameFields& FF, const FaultProfile
   return rn_mul(fault_step_d(P, gx, gy, gz, offset, &ok), displacement);
 }
 
+// ---- frame-orthogonality rows generated from a solved field (SURVEY.md section 8 f, rank 2) -------------------
+// GeologicalFeatureBuilder.install_gradient_constraint (LS/modelling/features/builders/_geological_feature_builder.py:
+// 293-318): the gradient of ANOTHER feature at the barycentre of every `estep`-th cell of this support, normalised,
+// becomes one row  v . grad(phi) = b  of FDI.add_gradient_orthogonal_constraints
+// (LI/_finite_difference_interpolator.py:478-539), row-normalised by add_constraints_to_least_squares
+// (LI/_discrete_interpolator.py:361-366).  O(N / estep) rows: the reference evaluates the other feature on the host
+// over ALL N barycentres, einsums and builds a COO matrix; here one thread makes one row from the device-resident
+// field.  The barycentres are this support's LOCAL coordinates and the reference passes them to the other feature's
+// evaluate_gradient, which projects them as world coordinates (rows come out empty where that lands outside the other
+// support): kept as is, pinned by tests/golden/orth_world.npz.
+// Row r <- cell e = r * estep.  Returns false when the row is empty on this handle (slab: cell touches no owned plane).
+LSB_HD bool field_orthogonal_row(const GridDesc& g, const FrameField& other, const long long e, const double bval,
+                                 double A[8], int ci[3], double* b_out) {
+  const int ncx = g.nx - 1, ncy = g.ny - 1;
+  const long long cxy = (long long)ncx * ncy;
+  const int cell[3] = {(int)(e % ncx), (int)((e / ncx) % ncy), (int)(e / cxy)};
+  double x[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)  // StructuredGrid.cell_centres: origin + step * cell + step * 0.5
+    x[a] = rn_add(rn_add(g.origin[a], rn_mul(g.step[a], (double)cell[a])), rn_mul(g.step[a], 0.5));
+  double v[3];
+  frame_field_at(other, x, v);
+  const double n1 = sqrt(rn_add(rn_add(rn_mul(v[0], v[0]), rn_mul(v[1], v[1])), rn_mul(v[2], v[2])));
+  if (n1 > 0.0) { v[0] /= n1; v[1] /= n1; v[2] /= n1; }
+  const CellLoc L = locate(g, x);
+  ci[0] = L.ci[0]; ci[1] = L.ci[1]; ci[2] = L.ci[2];
+  const bool ok = L.inside && (L.ci[2] + 1 >= g.k0) && (L.ci[2] < g.k1);
+  double T[3][8];
+  trilinear_grad(g, L.lc, T);
+  // add_gradient_orthogonal_constraints normalises the vector (and T) once more
+  const double n2 = sqrt(rn_add(rn_add(rn_mul(v[0], v[0]), rn_mul(v[1], v[1])), rn_mul(v[2], v[2])));
+  if (n2 > 0.0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      v[a] /= n2;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) T[a][c] /= n2;
+    }
+  }
+  double nrm2 = 0.0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    A[c] = v[0] * T[0][c] + v[1] * T[1][c] + v[2] * T[2][c];
+    nrm2 += A[c] * A[c];
+  }
+  const double len = sqrt(nrm2);
+  if (len > 0.0) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) A[c] /= len;
+  }
+  *b_out = len > 0.0 ? bval / len : bval;
+  return ok;
+}
+
+// body of k_fdi_field_orthogonal_rows for row r (shared with tests/hostsim)
+LSB_HD bool field_orthogonal_row_store(const GridDesc& g, const FrameField& other, const long long estep, const double weight,
+                                       const double bval, const RowBlock& rb, const long long row0, const long long r) {
+  double A[8], b;
+  int ci[3];
+  const bool ok = field_orthogonal_row(g, other, r * estep, bval, A, ci, &b);
+  const long long ro = row0 + r;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    rb.vals[c * rb.n + ro] = ok ? A[c] : 0.0;
+    rb.cols[c * rb.n + ro] = ok ? (int)corner_local(g, ci, c) : -1;
+  }
+  rb.b[ro] = ok ? b : 0.0;
+  rb.w2[ro] = ok ? weight * weight : 0.0;
+  return ok;
+}
+
 #ifdef __CUDACC__
+__global__ void __launch_bounds__(128)
+    k_fdi_field_orthogonal_rows(const GridDesc g, const FrameField other, const long long estep, const long long n_rows,
+                                const double weight, const double bval, const RowBlock rb, const long long row0,
+                                unsigned long long* __restrict__ status) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x)
+    if (field_orthogonal_row_store(g, other, estep, weight, bval, rb, row0, r)) atomicAdd(status, 1ull);
+}
+
 // the three values (n,3) and, when grad_out != nullptr, the gradient (n,3) of field `gfield`: one pass over xyz
 __global__ void __launch_bounds__(256)
     k_frame_eval(const FrameFields FF, const int gfield, const long long n, const double* __restrict__ xyz,

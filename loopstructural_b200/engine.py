@@ -197,6 +197,21 @@ class Engine:
                                                  C.byref(out)))
         return int(out.value)
 
+    def add_field_orthogonal_rows(self, other: "Engine", step: int = 10, weight: float = 1.0, b: float = 0.0,
+                                  other_world_to_local=None) -> int:
+        """GeologicalFeatureBuilder.install_gradient_constraint on the device
+        (LoopStructural/modelling/features/builders/_geological_feature_builder.py:293-318): rows that make this field's
+        gradient orthogonal to the gradient of ``other`` (a solved grid engine) at every ``step``-th cell barycentre."""
+        tr = None
+        if other_world_to_local is not None:
+            from .fault import transform_rows
+
+            tr = np.ascontiguousarray(transform_rows(other_world_to_local))
+        out = C.c_int64(0)
+        nat.check(self._lib.lsb200_add_field_orthogonal_rows(self._h, other._h, None if tr is None else nat.dptr(tr),
+                                                             int(step), float(weight), float(b), C.byref(out)))
+        return int(out.value)
+
     def clear_rows(self):
         nat.check(self._lib.lsb200_clear_rows(self._h))
 

@@ -167,3 +167,36 @@ def frame_eval(fields, points: np.ndarray, gradient_of: int = 1):
     """The gathers one step needs: the three values and the gradient of one field at the same points."""
     vals = np.stack([f.value(points) for f in fields], axis=1)
     return vals, fields[gradient_of].gradient(points)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Orthogonality rows of a structural frame (SURVEY.md section 8 f, rank 2)
+# ---------------------------------------------------------------------------------------------------------------
+
+
+def barycentres(grid: fo.Grid, elements: np.ndarray) -> np.ndarray:
+    """StructuredGrid.cell_centres (LC/supports/_3d_structured_grid.py:70-88): origin + step * cell + step * 0.5, cell
+    index = cx + ncx * (cy + ncy * cz) (global_index_to_cell_index, LC/supports/_3d_base_structured.py)."""
+    nc = grid.ncells
+    cx = elements % nc[0]
+    cy = (elements // nc[0]) % nc[1]
+    cz = elements // (nc[0] * nc[1])
+    cell = np.stack([cx, cy, cz], axis=1)
+    return grid.origin[None, :] + grid.step[None, :] * cell + grid.step[None, :] * 0.5
+
+
+def field_orthogonal_rows(grid: fo.Grid, other: FrameField, element_step: int, w: float, b: float = 0.0,
+                          name: str = "orthogonal"):
+    """GeologicalFeatureBuilder.install_gradient_constraint
+    (LS/modelling/features/builders/_geological_feature_builder.py:293-318) for a discrete interpolator on a
+    StructuredGrid: gradient of the OTHER feature at every barycentre of this support, normalised, every
+    `element_step`-th element -> FDI.add_gradient_orthogonal_constraints (LI/_finite_difference_interpolator.py:478-539).
+    The barycentres are this support's LOCAL coordinates and the reference hands them to the other feature's
+    evaluate_gradient, which projects them as if they were world coordinates: restated as is."""
+    n_el = int(np.prod(grid.ncells))
+    bary = barycentres(grid, np.arange(n_el))
+    vec = other.gradient(bary)
+    norm = np.linalg.norm(vec, axis=1)
+    vec[norm > 0] /= norm[norm > 0, None]
+    sel = np.arange(n_el)[::element_step]
+    return fo.orthogonal_rows(grid, bary[sel], vec[sel], w=w, b=b, name=name)

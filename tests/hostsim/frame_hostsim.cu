@@ -97,4 +97,33 @@ int hostsim_fault_displacement(const int64_t* nsteps, const double* origin, cons
   return 0;
 }
 
+// body of k_fdi_field_orthogonal_rows: rows of `target` (nsteps/origin/step at index 0 of the three-field arrays are the
+// TARGET support, index 1 the OTHER field whose c is c1 and whose transform is transforms[21..42)); outputs are
+// (n_rows, 8) row-major values / local column ids (-1 = empty), b and w^2.
+int hostsim_field_orthogonal_rows(const int64_t* nsteps, const double* origin, const double* step, const double* c_other,
+                                  const double* transforms, int64_t estep, double weight, double bval, int64_t n_rows,
+                                  double* vals, int64_t* cols, double* b, double* w2) {
+  HostFrame H;
+  std::vector<double> dummy((size_t)(nsteps[0] * nsteps[1] * nsteps[2]), 0.0), dummy2((size_t)(nsteps[6] * nsteps[7] * nsteps[8]), 0.0);
+  const double* c[3] = {dummy.data(), c_other, dummy2.data()};
+  build(H, nsteps, origin, step, c, transforms);
+  const GridDesc& g = H.FF.f[0].g;
+  std::vector<double> v((size_t)n_rows * 8), bb((size_t)n_rows), ww((size_t)n_rows);
+  std::vector<int> cc((size_t)n_rows * 8);
+  RowBlock rb{};
+  rb.n = n_rows; rb.k = 8; rb.vals = v.data(); rb.cols = cc.data(); rb.b = bb.data(); rb.w2 = ww.data();
+  int64_t kept = 0;
+  for (int64_t r = 0; r < n_rows; ++r) kept += field_orthogonal_row_store(g, H.FF.f[1], estep, weight, bval, rb, 0, r) ? 1 : 0;
+  for (int64_t r = 0; r < n_rows; ++r) {
+    for (int k = 0; k < 8; ++k) {
+      vals[r * 8 + k] = v[(size_t)k * n_rows + r];
+      const int lc = cc[(size_t)k * n_rows + r];
+      cols[r * 8 + k] = lc < 0 ? -1 : (int64_t)lc - (int64_t)HALO * g.plane;  // storage index -> global node id (full handle, pitch = nx)
+    }
+    b[r] = bb[r];
+    w2[r] = ww[r];
+  }
+  return (int)kept;
+}
+
 }  // extern "C"

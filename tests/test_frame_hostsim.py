@@ -160,3 +160,33 @@ def test_rotated_frames_and_distinct_supports_match_the_oracle(sim):
     assert sim.hostsim_fault_displacement(*args, C.byref(prof), C.c_double(0.35), C.c_double(0.2), C.c_int64(n),
                                           pts.ctypes.data_as(dp), d.ctypes.data_as(dp)) == 0
     np.testing.assert_allclose(d, fa.evaluate_displacement(fields, oprof, 0.35, 0.2, pts), rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("tag", ["world", "zero_origin"])
+def test_field_orthogonal_row_code_matches_the_reference(sim, tag):
+    """Body of k_fdi_field_orthogonal_rows against the '<feature>_orthogonal' families of the unmodified reference."""
+    from scipy import sparse
+
+    from loopstructural_b200.fault import transform_rows
+    from test_oracle_golden_orthogonal import orth_case
+
+    z = np.load(os.path.join(GOLDEN, f"orth_{tag}.npz"))
+    for key in z["families"]:
+        grid, other, step, w, B, (m_ref, b_ref, w_ref) = orth_case(z, str(key))
+        ns = np.ascontiguousarray(np.concatenate([grid.nsteps, other.grid.nsteps, [2, 2, 2]]), dtype=np.int64)
+        org = np.ascontiguousarray(np.concatenate([grid.origin, other.grid.origin, np.zeros(3)]))
+        stp = np.ascontiguousarray(np.concatenate([grid.step, other.grid.step, np.ones(3)]))
+        tr = np.ascontiguousarray(np.concatenate([transform_rows(None), transform_rows(other.world_to_local), transform_rows(None)]))
+        c_other = np.ascontiguousarray(other.c)
+        n_rows = m_ref.shape[0]
+        vals, cols = np.empty((n_rows, 8)), np.empty((n_rows, 8), dtype=np.int64)
+        b, w2 = np.empty(n_rows), np.empty(n_rows)
+        kept = sim.hostsim_field_orthogonal_rows(ns.ctypes.data_as(C.POINTER(C.c_int64)), org.ctypes.data_as(dp), stp.ctypes.data_as(dp),
+                                                 c_other.ctypes.data_as(dp), tr.ctypes.data_as(dp), C.c_int64(step), C.c_double(w),
+                                                 C.c_double(B), C.c_int64(n_rows), vals.ctypes.data_as(dp),
+                                                 cols.ctypes.data_as(C.POINTER(C.c_int64)), b.ctypes.data_as(dp), w2.ctypes.data_as(dp))
+        assert kept == n_rows and cols.min() >= 0
+        m = sparse.coo_matrix((vals.ravel(), (np.repeat(np.arange(n_rows), 8), cols.ravel())), shape=m_ref.shape).tocsr()
+        assert abs(m - m_ref).max() <= 1e-13
+        np.testing.assert_allclose(b, b_ref, rtol=0, atol=1e-14)
+        np.testing.assert_array_equal(w2, w_ref**2)

@@ -157,3 +157,37 @@ def test_argument_errors():
     assert frame.apply_to_points(np.zeros((0, 3)), fl.fault_profile(None), 1.0, 2).shape == (0, 3)
     for e in engines:
         e.close()
+
+
+@pytest.mark.parametrize("tag", ["world", "zero_origin"])
+def test_field_orthogonal_rows_match_the_reference(tag):
+    """lsb200_add_field_orthogonal_rows against the '<feature>_orthogonal' families of the unmodified reference
+    (tests/golden/orth_*.npz): the rows enter the normal operator and the right-hand side exactly as the reference's."""
+    from loopstructural_b200 import Engine, build
+    from loopstructural_b200 import engine as en
+    from test_oracle_golden_orthogonal import orth_case
+
+    build.build()
+    z = np.load(os.path.join(GOLDEN, f"orth_{tag}.npz"))
+    rng = np.random.default_rng(2)
+    for key in z["families"]:
+        grid, other, step, w, B, (m_ref, b_ref, w_ref) = orth_case(z, str(key))
+        B = 0.37  # the fixtures all have b = 0: a non-zero target also checks the scaling of b
+        fam = fa.field_orthogonal_rows(grid, other, step, w, B)
+        m_or = fam.matrix(grid.n_nodes)
+        assert abs(m_or - m_ref).max() <= 1e-13
+        eo = Engine(other.grid.nsteps, other.grid.origin, other.grid.step)
+        eo.set_c(other.c)
+        e = Engine(grid.nsteps, grid.origin, grid.step)
+        e.set_regularisation({})
+        kept = e.add_field_orthogonal_rows(eo, step=step, weight=w, b=B, other_world_to_local=other.world_to_local)
+        assert kept == m_ref.shape[0] == e.num_rows
+        e.finalize()
+        p = rng.normal(size=grid.n_nodes)
+        q = e.apply_normal(p, parts=en.PART_ROWS)
+        q_ref = m_or.T @ (fam.w**2 * (m_or @ p))
+        np.testing.assert_allclose(q, q_ref, rtol=0, atol=1e-12 * np.abs(q_ref).max())
+        rhs_rows = m_or.T @ (fam.w**2 * fam.b)
+        np.testing.assert_allclose(e.rhs(), rhs_rows, rtol=0, atol=1e-12 * max(np.abs(rhs_rows).max(), 1e-300))
+        e.close()
+        eo.close()
