@@ -278,6 +278,18 @@ int lsb200_fault_displacement_dev(const lsb200_handle fields[3], const double* t
 int lsb200_add_field_orthogonal_rows(lsb200_handle h, lsb200_handle other, const double* other_transform,
                                      int64_t element_step, double weight, double b, int64_t* n_rows_out);
 
+/* Evaluation on a regular lattice WITHOUT an xyz input: the points BoundingBox.regular_grid builds
+ * (LC/geometry/_bounding_box.py:532-573: np.linspace(start[a], stop[a], n[a]) per axis, meshgrid 'ij', flattened in
+ * order 'F' (order_f != 0, first axis fastest) or 'C') for BaseFeature.scalar_field / gradient_norm_scalar_field /
+ * GeologicalModel.evaluate_model (LoopStructural/modelling/features/_base_geological_feature.py:359-449), generated
+ * inside the kernel.  start/stop are WORLD coordinates, mapped through `transform` (21 doubles as in
+ * lsb200_frame_eval, NULL = identity).  gradient == 0: out is (N) values with the semantics of lsb200_eval_value;
+ * gradient != 0: out is (N,3) world-axis gradients (0 outside).  Grid handles owning every plane. */
+int lsb200_eval_lattice(lsb200_handle h, const double* transform, const double start[3], const double stop[3],
+                        const int64_t n[3], int order_f, int gradient, double* out);
+int lsb200_eval_lattice_dev(lsb200_handle h, const double* transform, const double start[3], const double stop[3],
+                            const int64_t n[3], int order_f, int gradient, double* out_dev, void* stream);
+
 /* Introspection (no device needed): the output planes of the three launches of the tiled FDI operator for a
  * handle owning the planes [k0,k1) of nz: out = {A0,A1, B0,B1, U0,U1}, A/B = z-general ranges next to the z faces,
  * U = uniform range; see plan_z_ranges in csrc/api.cu. */

@@ -1659,6 +1659,64 @@ int lsb200_fault_displacement(const lsb200_handle fields[3], const double* trans
   return rc ? rc : frame_host(fields[0], fc, n, xyz, d, nullptr);
 }
 
+// ---- lattice evaluation
+static int make_lattice(const double start[3], const double stop[3], const int64_t n[3], int order_f, Lattice* lat,
+                        long long* total) {
+  if (!start || !stop || !n) return fail(LSB200_ERR_ARG, "null lattice argument");
+  long long t = 1;
+  for (int a = 0; a < 3; ++a) {
+    if (n[a] < 1) return fail(LSB200_ERR_ARG, "lattice axis %d has %lld points", a, (long long)n[a]);
+    lat->start[a] = start[a];
+    lat->stop[a] = stop[a];
+    lat->n[a] = n[a];
+    lat->delta[a] = n[a] > 1 ? (stop[a] - start[a]) / (double)(n[a] - 1) : 0.0;  // np.linspace: step = delta / div
+    t *= n[a];
+  }
+  lat->order_f = order_f ? 1 : 0;
+  *total = t;
+  return 0;
+}
+
+int lsb200_eval_lattice_dev(lsb200_handle h, const double* transform, const double start[3], const double stop[3],
+                            const int64_t n[3], int order_f, int gradient, double* out_dev, void* stream) {
+  FrameField F;
+  Lattice lat;
+  long long total;
+  int rc = make_frame_field(h, transform, "lattice field", 0, &F);
+  if (rc || (rc = make_lattice(start, stop, n, order_f, &lat, &total))) return rc;
+  if (!out_dev) return fail(LSB200_ERR_ARG, "null output");
+  CK(cudaSetDevice(h->device));
+  k_eval_lattice<<<frame_blocks(h, total), 256, 0, (cudaStream_t)stream>>>(F, lat, 0, total, gradient ? 1 : 0, out_dev);
+  CKL();
+  h->launches++;
+  return 0;
+}
+
+int lsb200_eval_lattice(lsb200_handle h, const double* transform, const double start[3], const double stop[3],
+                        const int64_t n[3], int order_f, int gradient, double* out) {
+  FrameField F;
+  Lattice lat;
+  long long total;
+  int rc = make_frame_field(h, transform, "lattice field", 0, &F);
+  if (rc || (rc = make_lattice(start, stop, n, order_f, &lat, &total))) return rc;
+  if (!out) return fail(LSB200_ERR_ARG, "null output");
+  CK(cudaSetDevice(h->device));
+  const int ow = gradient ? 3 : 1;
+  const long long chunk = std::min<long long>(total, 1 << 24);
+  double* d = nullptr;
+  CK(cudaMallocAsync(&d, sizeof(double) * ow * chunk, h->stream));
+  for (long long o = 0; o < total; o += chunk) {
+    const long long m = std::min<long long>(chunk, total - o);
+    k_eval_lattice<<<frame_blocks(h, m), 256, 0, h->stream>>>(F, lat, o, m, gradient ? 1 : 0, d);
+    CKL();
+    h->launches++;
+    CK(cudaMemcpyAsync(out + ow * o, d, sizeof(double) * ow * m, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  pool_free(h, d);
+  return 0;
+}
+
 int lsb200_plan_z_ranges(int nz, int k0, int k1, int cz, int zface, int out[6]) {
   if (!out || nz < 1 || k0 < 0 || k1 > nz || k1 <= k0 || cz < 1) return fail(LSB200_ERR_ARG, "bad argument");
   plan_z_ranges(nz, k0, k1, cz, zface, out);

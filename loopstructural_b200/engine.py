@@ -321,6 +321,31 @@ class Engine:
         nat.check(self._lib.lsb200_eval_gradient_dev(self._h, int(n), C.c_void_p(xyz_ptr), C.c_void_p(out_ptr),
                                                      C.c_void_p(stream)))
 
+    def evaluate_lattice(self, start, stop, n, order: str = "F", gradient: bool = False, world_to_local=None,
+                         out_ptr: int | None = None, stream: int = 0):
+        """Value (N) or world gradient (N,3) of the field on np.linspace(start, stop, n) per axis, flattened in
+        ``order`` -- the points of BoundingBox.regular_grid(local=False) (LC/geometry/_bounding_box.py:532-573) --
+        without building or copying the coordinates.  ``out_ptr``: device pointer (asynchronous on ``stream``)."""
+        start, stop = nat.as_f64(start, (3,)), nat.as_f64(stop, (3,))
+        n = np.ascontiguousarray(n, dtype=np.int64).reshape(3)
+        if order not in ("F", "C"):
+            raise ValueError("order must be 'F' or 'C'")
+        tr = None
+        if world_to_local is not None:
+            from .fault import transform_rows
+
+            tr = np.ascontiguousarray(transform_rows(world_to_local))
+        trp = None if tr is None else nat.dptr(tr)
+        if out_ptr is not None:
+            nat.check(self._lib.lsb200_eval_lattice_dev(self._h, trp, nat.dptr(start), nat.dptr(stop), nat.iptr(n),
+                                                        int(order == "F"), int(gradient), C.c_void_p(out_ptr), C.c_void_p(stream)))
+            return None
+        total = int(np.prod(n))
+        out = np.empty((total, 3) if gradient else total, dtype=np.float64)
+        nat.check(self._lib.lsb200_eval_lattice(self._h, trp, nat.dptr(start), nat.dptr(stop), nat.iptr(n), int(order == "F"),
+                                                int(gradient), nat.dptr(out)))
+        return out
+
     def time_kernel(self, which: int, reps: int = 20) -> float:
         out = C.c_double(0.0)
         nat.check(self._lib.lsb200_time_kernel(self._h, int(which), int(reps), C.byref(out)))

@@ -22,7 +22,12 @@ LI/_interpolator_factory.py:57-66) -- by a subclass of ``FiniteDifferenceInterpo
 ``install()`` also patches ``FaultSegment.apply_to_points`` / ``evaluate_displacement`` (the largest consumers of the
 solved fields, LoopStructural/modelling/features/fault/_fault_segment.py:283-423): when the three coordinates of a
 fault frame were solved by the engine and carry no faults / regions of their own, the whole integration runs in one
-device pass (``fault.FaultFrame``); any other case is left to the stock method.
+device pass (``fault.FaultFrame``); any other case is left to the stock method.  Likewise
+``GeologicalFeatureBuilder.install_gradient_constraint`` (the frame-orthogonality families, :293-318 of
+builders/_geological_feature_builder.py): when the source feature was solved by the engine its rows are generated on
+the device from the resident field (``lsb200_add_field_orthogonal_rows``) instead of host evaluate -> einsum -> COO.
+``BaseFeature.scalar_field`` (regular-grid export) takes its node values from ``lsb200_eval_lattice``, which
+generates the lattice coordinates inside the kernel.
 
 There is no CPU fallback: with ``solver='b200'`` and no usable CUDA device ``solve_system`` raises.
 """
@@ -84,6 +89,9 @@ def _solve_on_engine(it, eng, solver, tol, solver_kwargs) -> bool:
     for _name, vals, cols, b, w in constraints_to_rows(it.constraints):
         eng.add_rows(vals, cols, b, w, normalise=False)
         n_rows += vals.shape[0]
+    for other, w2l, step, w, b in getattr(it, "_b200_device_rows", []):
+        # frame-orthogonality families diverted by the builder patch: generated on the device from the other field
+        n_rows += eng.add_field_orthogonal_rows(other, step=step, weight=w, b=b, other_world_to_local=w2l)
     assembly = perf_counter() - t_asm
     c, res = eng.solve_cg(rtol=rtol, atol=atol, maxiter=kw.get("maxiter"), x0=kw.get("x0"))
     it.c = c
@@ -104,10 +112,12 @@ class _B200Mixin:
         self._b200_reg = {}
         self._b200_setup_kwargs = {}
         self._b200_engine = None
+        self._b200_device_rows = []  # (other engine, its world_to_local, element step, weight, b) per diverted family
 
     def setup_interpolator(self, **kwargs):
         self._b200_setup_kwargs = dict(kwargs)
         self._b200_reg = {}
+        self._b200_device_rows = []
         self._b200_divert = self._b200_can_divert(kwargs)
         return super().setup_interpolator(**kwargs)
 
@@ -311,6 +321,103 @@ def _make_fault_methods(stock_apply, stock_displacement):
     return apply_to_points, evaluate_displacement
 
 
+def _solved_grid_field(feature):
+    """(engine, world_to_local) of a plain interpolated feature solved by the grid engine, else None."""
+    if type(feature).__name__ != "GeologicalFeature":
+        return None
+    if getattr(feature, "faults_enabled", True) and len(getattr(feature, "faults", [])) > 0:
+        return None
+    if getattr(feature, "builder", None) is not None:
+        feature.builder.up_to_date()
+    it = getattr(feature, "interpolator", None)
+    eng = it._b200_engine_current() if hasattr(it, "_b200_engine_current") else None
+    if eng is None or getattr(eng, "kind", "grid") != "grid":
+        return None
+    bb = getattr(it, "bounding_box", None)
+    return eng, (np.eye(4) if bb is None else np.asarray(bb.world_to_local_matrix, dtype=float))
+
+
+def _make_install_gradient_constraint(stock):
+    def install_gradient_constraint(self):
+        """GeologicalFeatureBuilder.install_gradient_constraint
+        (LS/modelling/features/builders/_geological_feature_builder.py:293-318): families whose source feature was
+        solved by the grid engine are recorded and generated on the device at solve time
+        (lsb200_add_field_orthogonal_rows); the others go through the stock method."""
+        it = self.interpolator
+        if not (getattr(it, "_b200_divert", False) and hasattr(it, "_b200_stencil")):
+            return stock(self)
+        rest = {}
+        for key, g in self._orthogonal_features.items():
+            feature, w, _region, step, b = g
+            if w == 0:
+                continue
+            src = _solved_grid_field(feature)
+            if src is None:
+                rest[key] = g
+            else:
+                it._b200_device_rows.append((src[0], src[1], int(step), float(w), float(b)))
+        if rest:
+            keep = self._orthogonal_features
+            self._orthogonal_features = rest
+            try:
+                stock(self)
+            finally:
+                self._orthogonal_features = keep
+
+    return install_gradient_constraint
+
+
+def _install_builder_patch():
+    try:
+        from LoopStructural.modelling.features.builders import GeologicalFeatureBuilder
+    except Exception:
+        return
+    if "builder_stock" not in _installed:
+        _installed["builder_stock"] = (GeologicalFeatureBuilder, GeologicalFeatureBuilder.install_gradient_constraint)
+    cls, stock = _installed["builder_stock"]
+    cls.install_gradient_constraint = _make_install_gradient_constraint(stock)
+
+
+def _make_scalar_field(stock):
+    def scalar_field(self, bounding_box=None):
+        """BaseFeature.scalar_field (LS/modelling/features/_base_geological_feature.py:359-388): node values on
+        BoundingBox.regular_grid(local=False, order='F') from lsb200_eval_lattice (coordinates generated in the
+        kernel) when the feature is a plain one solved by the grid engine; the stock method otherwise."""
+        src = None
+        if type(self).__name__ == "GeologicalFeature" and len(getattr(self, "regions", [])) == 0:
+            src = _solved_grid_field(self)
+        if src is None:
+            return stock(self, bounding_box)
+        from LoopStructural.geometry import StructuredGrid
+
+        if bounding_box is None:
+            if self.model is None:
+                raise ValueError("Must specify bounding box")
+            bounding_box = self.model.bounding_box
+        grid = StructuredGrid(origin=bounding_box.origin, step_vector=bounding_box.step_vector, nsteps=bounding_box.nsteps,
+                              name=self.name)
+        eng, w2l = src
+        grid.properties[self.name] = eng.evaluate_lattice(np.asarray(bounding_box.origin, dtype=float),
+                                                          np.asarray(bounding_box.maximum, dtype=float),
+                                                          np.asarray(bounding_box.nsteps), order="F", world_to_local=w2l)
+        # the cell-centre cloud is not a lattice to the bit (projected, shifted, reprojected): ordinary evaluation
+        grid.cell_properties[self.name] = self.evaluate_value(bounding_box.reproject(bounding_box.cell_centres(order="F")))
+        return grid
+
+    return scalar_field
+
+
+def _install_feature_patch():
+    try:
+        from LoopStructural.modelling.features._base_geological_feature import BaseFeature
+    except Exception:
+        return
+    if "feature_stock" not in _installed:
+        _installed["feature_stock"] = (BaseFeature, BaseFeature.scalar_field)
+    cls, stock = _installed["feature_stock"]
+    cls.scalar_field = _make_scalar_field(stock)
+
+
 def _install_fault_patch():
     """Patch FaultSegment when LoopStructural itself is importable (the interpolation package alone is enough for
     everything else in this module)."""
@@ -338,6 +445,8 @@ def install():
     li.interpolator_map[T.FINITE_DIFFERENCE] = _installed["fdi"]
     li.interpolator_map[T.PIECEWISE_LINEAR] = _installed["p1"]
     _install_fault_patch()
+    _install_builder_patch()
+    _install_feature_patch()
     return {"FDI": _installed["fdi"], "P1": _installed["p1"]}
 
 
@@ -350,3 +459,9 @@ def uninstall():
     if "fault_stock" in _installed:
         cls, stock_apply, stock_displacement = _installed["fault_stock"]
         cls.apply_to_points, cls.evaluate_displacement = stock_apply, stock_displacement
+    if "builder_stock" in _installed:
+        cls, stock = _installed["builder_stock"]
+        cls.install_gradient_constraint = stock
+    if "feature_stock" in _installed:
+        cls, stock = _installed["feature_stock"]
+        cls.scalar_field = stock

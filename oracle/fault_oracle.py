@@ -200,3 +200,23 @@ def field_orthogonal_rows(grid: fo.Grid, other: FrameField, element_step: int, w
     vec[norm > 0] /= norm[norm > 0, None]
     sel = np.arange(n_el)[::element_step]
     return fo.orthogonal_rows(grid, bary[sel], vec[sel], w=w, b=b, name=name)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Regular-grid export (SURVEY.md section 8 f, rank 4)
+# ---------------------------------------------------------------------------------------------------------------
+
+
+def lattice_points(start, stop, n, order: str = "F") -> np.ndarray:
+    """BoundingBox.regular_grid(local=False) (LC/geometry/_bounding_box.py:532-573): np.linspace per axis, meshgrid
+    'ij', flattened in `order`."""
+    coords = [np.linspace(start[i], stop[i], int(n[i])) for i in range(3)]
+    grid = np.meshgrid(*coords, indexing="ij")
+    return np.array([g.flatten(order=order) for g in grid]).T
+
+
+def evaluate_lattice(fld: FrameField, start, stop, n, order: str = "F", gradient: bool = False) -> np.ndarray:
+    """What BaseFeature.scalar_field stores in grid.properties (LS/modelling/features/_base_geological_feature.py:359-388)
+    for a feature without faults and regions: evaluate_value / evaluate_gradient on the lattice points."""
+    pts = lattice_points(start, stop, n, order)
+    return fld.gradient(pts) if gradient else fld.value(pts)

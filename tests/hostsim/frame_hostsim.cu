@@ -126,4 +126,30 @@ int hostsim_field_orthogonal_rows(const int64_t* nsteps, const double* origin, c
   return (int)kept;
 }
 
+// body of k_eval_lattice for the field at index 0 of the three-field arrays
+int hostsim_eval_lattice(const int64_t* nsteps, const double* origin, const double* step, const double* c0,
+                         const double* transforms, const double* start, const double* stop, const int64_t* n, int order_f,
+                         int gradient, double* out) {
+  HostFrame H;
+  std::vector<double> d1((size_t)(nsteps[3] * nsteps[4] * nsteps[5]), 0.0), d2((size_t)(nsteps[6] * nsteps[7] * nsteps[8]), 0.0);
+  const double* c[3] = {c0, d1.data(), d2.data()};
+  build(H, nsteps, origin, step, c, transforms);
+  Lattice lat;
+  long long total = 1;
+  for (int a = 0; a < 3; ++a) {  // make_lattice of csrc/api.cu
+    lat.start[a] = start[a]; lat.stop[a] = stop[a]; lat.n[a] = n[a];
+    lat.delta[a] = n[a] > 1 ? (stop[a] - start[a]) / (double)(n[a] - 1) : 0.0;
+    total *= n[a];
+  }
+  lat.order_f = order_f ? 1 : 0;
+  for (long long r = 0; r < total; ++r) {
+    double x[3], g[3];
+    lattice_point(lat, r, x);
+    const double v = frame_field_at(H.FF.f[0], x, gradient ? g : nullptr);
+    if (gradient) { out[3 * r] = g[0]; out[3 * r + 1] = g[1]; out[3 * r + 2] = g[2]; }
+    else out[r] = v;
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -190,3 +190,48 @@ def test_field_orthogonal_row_code_matches_the_reference(sim, tag):
         assert abs(m - m_ref).max() <= 1e-13
         np.testing.assert_allclose(b, b_ref, rtol=0, atol=1e-14)
         np.testing.assert_array_equal(w2, w_ref**2)
+
+
+def _lattice_call(sim, fld, start, stop, n, order, gradient):
+    from loopstructural_b200.fault import transform_rows
+
+    ns = np.ascontiguousarray(np.concatenate([fld.grid.nsteps, [2, 2, 2], [2, 2, 2]]), dtype=np.int64)
+    org = np.ascontiguousarray(np.concatenate([fld.grid.origin, np.zeros(6)]))
+    stp = np.ascontiguousarray(np.concatenate([fld.grid.step, np.ones(6)]))
+    tr = np.ascontiguousarray(np.concatenate([transform_rows(fld.world_to_local), transform_rows(None), transform_rows(None)]))
+    c = np.ascontiguousarray(fld.c)
+    start, stop = np.ascontiguousarray(start, dtype=np.float64), np.ascontiguousarray(stop, dtype=np.float64)
+    n = np.ascontiguousarray(n, dtype=np.int64)
+    total = int(np.prod(n))
+    out = np.empty((total, 3) if gradient else total)
+    ip = C.POINTER(C.c_int64)
+    rc = sim.hostsim_eval_lattice(ns.ctypes.data_as(ip), org.ctypes.data_as(dp), stp.ctypes.data_as(dp), c.ctypes.data_as(dp),
+                                  tr.ctypes.data_as(dp), start.ctypes.data_as(dp), stop.ctypes.data_as(dp), n.ctypes.data_as(ip),
+                                  C.c_int(order == "F"), C.c_int(int(gradient)), out.ctypes.data_as(dp))
+    assert rc == 0
+    return out
+
+
+def test_lattice_code_matches_the_reference_and_the_oracle(sim):
+    """Body of k_eval_lattice: BaseFeature.scalar_field of the unmodified reference (lattice_claudius.npz), then
+    lattices that reach outside the support, single-point axes and both flattening orders against the oracle."""
+    from oracle import fdi_oracle as fo
+
+    z = np.load(os.path.join(GOLDEN, "lattice_claudius.npz"))
+    fld = fa.FrameField(fo.Grid.from_cells(z["ncells"], z["origin"], z["step"]), z["c"], z["w2l"])
+    lo, hi, n = z["box_origin"], z["box_maximum"], z["box_nsteps"]
+    rng_ = float(np.nanmax(z["node_values_f"]) - np.nanmin(z["node_values_f"]))
+    np.testing.assert_allclose(_lattice_call(sim, fld, lo, hi, n, "F", False), z["node_values_f"], rtol=0, atol=1e-13 * rng_)
+    np.testing.assert_allclose(_lattice_call(sim, fld, lo, hi, n, "C", False), z["node_values_c"], rtol=0, atol=1e-13 * rng_)
+    np.testing.assert_allclose(_lattice_call(sim, fld, lo, hi, n, "F", True), z["node_gradient_f"], rtol=0, atol=1e-12)
+    ext = hi - lo
+    for start, stop, nn in ((lo - 0.7 * ext, hi + 0.7 * ext, (13, 9, 21)), (lo, hi, (1, 7, 5)), (hi, lo, (6, 1, 4)),
+                            (lo + 0.1 * ext, lo + 0.1 * ext, (3, 3, 3))):
+        for order in ("F", "C"):
+            v = _lattice_call(sim, fld, start, stop, nn, order, False)
+            ov = fa.evaluate_lattice(fld, start, stop, nn, order)
+            np.testing.assert_array_equal(np.isnan(v), np.isnan(ov))
+            np.testing.assert_allclose(v, ov, rtol=0, atol=1e-13 * rng_, equal_nan=True)
+            g = _lattice_call(sim, fld, start, stop, nn, order, True)
+            np.testing.assert_allclose(g, fa.evaluate_lattice(fld, start, stop, nn, order, gradient=True), rtol=0, atol=1e-12)
+    assert np.isnan(_lattice_call(sim, fld, lo - 0.7 * ext, hi + 0.7 * ext, (13, 9, 21), "F", False)).sum() > 500

@@ -45,3 +45,20 @@ def test_evaluate_displacement_matches_the_reference(tag):
     fields, profile, disp, _, offset = fault_case(z)
     d = fa.evaluate_displacement(fields, profile, disp, offset, z["points"])
     np.testing.assert_allclose(d, z["displacement_at"], rtol=1e-13, atol=1e-13 * abs(disp))
+
+
+def test_lattice_export_matches_the_reference():
+    """oracle evaluate_lattice against BaseFeature.scalar_field of the unmodified reference (lattice_claudius.npz)."""
+    from oracle import fdi_oracle as fo
+
+    z = np.load(os.path.join(GOLDEN, "lattice_claudius.npz"))
+    fld = fa.FrameField(fo.Grid.from_cells(z["ncells"], z["origin"], z["step"]), z["c"], z["w2l"])
+    pts = fa.lattice_points(z["box_origin"], z["box_maximum"], z["box_nsteps"], "F")
+    np.testing.assert_array_equal(pts[:50], z["points_f_head"])
+    np.testing.assert_array_equal(pts[-50:], z["points_f_tail"])
+    rng_ = float(np.nanmax(z["node_values_f"]) - np.nanmin(z["node_values_f"]))
+    for order, key in (("F", "node_values_f"), ("C", "node_values_c")):
+        v = fa.evaluate_lattice(fld, z["box_origin"], z["box_maximum"], z["box_nsteps"], order)
+        np.testing.assert_allclose(v, z[key], rtol=0, atol=1e-13 * rng_, equal_nan=True)
+    g = fa.evaluate_lattice(fld, z["box_origin"], z["box_maximum"], z["box_nsteps"], "F", gradient=True)
+    np.testing.assert_allclose(g, z["node_gradient_f"], rtol=0, atol=1e-13)

@@ -39,6 +39,15 @@ class OracleEngine:
         assert normalise is False  # the reference has normalised them already
         self.rows.append(self.fo.Family(f"rows{len(self.rows)}", np.array(A, float), np.array(idx), np.array(b, float), np.array(w, float)))
 
+    def add_field_orthogonal_rows(self, other, step=10, weight=1.0, b=0.0, other_world_to_local=None):
+        from oracle import fault_oracle as fa
+
+        fam = fa.field_orthogonal_rows(self.grid, fa.FrameField(other.grid, other.c, other_world_to_local), step, weight, b,
+                                       name=f"device_orthogonal{len(self.rows)}")
+        self.rows.append(fam)
+        self.device_families = getattr(self, "device_families", 0) + 1
+        return fam.A.shape[0]
+
     def solve_cg(self, rtol=1e-5, atol=0.0, maxiter=None, x0=None, want_c=True, out=None):
         w = dict(self.fo.DEFAULT_WEIGHTS)
         w.update(self.weights)
@@ -56,6 +65,12 @@ class OracleEngine:
 
     def evaluate_gradient(self, xyz):
         return self.fo.evaluate_gradient(self.grid, np.asarray(xyz, float), self.c)
+
+    def evaluate_lattice(self, start, stop, n, order="F", gradient=False, world_to_local=None, out_ptr=None, stream=0):
+        from oracle import fault_oracle as fa
+
+        self.lattice_calls = getattr(self, "lattice_calls", 0) + 1
+        return fa.evaluate_lattice(fa.FrameField(self.grid, self.c, world_to_local), start, stop, n, order, gradient)
 
     def close(self):
         pass
@@ -108,6 +123,8 @@ def test_foliation_through_the_model_with_the_b200_solver_matches_the_stock_solv
     pts = bb[0] + rng.uniform(0, 1, (50, 3)) * (bb[1] - bb[0])
     val, grad = model.evaluate_feature_value("strati", pts), model.evaluate_feature_gradient("strati", pts)
     c_b200 = np.array(it.c)
+    field = model["strati"].scalar_field()  # regular-grid export: node values from the lattice entry point
+    assert eng.lattice_calls == 1
 
     from loopstructural_b200 import plugin
 
@@ -119,6 +136,11 @@ def test_foliation_through_the_model_with_the_b200_solver_matches_the_stock_solv
     assert np.linalg.norm(c_b200 - its.c) / np.sqrt(its.c.size) / rng_ <= 1e-9
     np.testing.assert_allclose(val, stock.evaluate_feature_value("strati", pts), rtol=0, atol=1e-9 * rng_)
     np.testing.assert_allclose(grad, stock.evaluate_feature_gradient("strati", pts), rtol=0, atol=1e-12)
+    stock_field = stock["strati"].scalar_field()
+    assert type(stock["strati"]).scalar_field.__qualname__ == "BaseFeature.scalar_field"
+    for got, ref in ((field.properties, stock_field.properties), (field.cell_properties, stock_field.cell_properties)):
+        np.testing.assert_allclose(np.asarray(got["strati"], float), np.asarray(ref["strati"], float), rtol=0, atol=1e-9 * rng_,
+                                   equal_nan=True)
 
 
 def test_model_without_the_b200_solver_is_untouched_by_the_plugin(ls):
@@ -185,6 +207,9 @@ def test_fault_frame_and_faulted_foliation_through_the_model(ls, monkeypatch):
         it = fault[i].interpolator
         assert type(it).__name__ == "B200FiniteDifferenceInterpolator" and it.latest_solve_timing["backend"] == "b200"
     assert model["strati"].interpolator.latest_solve_timing["backend"] == "b200"
+    # the orthogonality families of coordinates 1 and 2 never existed on the host: generated from the resident fields
+    assert [getattr(fault[i].interpolator._b200_engine, "device_families", 0) for i in range(3)] == [0, 2, 1]
+    assert not any("orthogonal" in k for i in range(3) for k in fault[i].interpolator.constraints)
     assert "apply" in OracleFaultFrame.calls  # the foliation's data were un-faulted through the frame during set-up
     rng = np.random.default_rng(5)
     pts = bb[0] + rng.uniform(-0.2, 1.2, (400, 3)) * (bb[1] - bb[0])

@@ -191,3 +191,46 @@ def test_field_orthogonal_rows_match_the_reference(tag):
         np.testing.assert_allclose(e.rhs(), rhs_rows, rtol=0, atol=1e-12 * max(np.abs(rhs_rows).max(), 1e-300))
         e.close()
         eo.close()
+
+
+def test_lattice_export_matches_the_reference_and_the_oracle():
+    """lsb200_eval_lattice against BaseFeature.scalar_field of the unmodified reference (lattice_claudius.npz), then
+    lattices that reach outside the support, single-point axes, both flattening orders and the device-pointer entry."""
+    import torch
+
+    from loopstructural_b200 import Engine, build
+
+    build.build()
+    z = np.load(os.path.join(GOLDEN, "lattice_claudius.npz"))
+    grid = fo.Grid.from_cells(z["ncells"], z["origin"], z["step"])
+    fld = fa.FrameField(grid, z["c"], z["w2l"])
+    e = Engine(grid.nsteps, grid.origin, grid.step)
+    e.set_c(z["c"])
+    lo, hi, n = z["box_origin"], z["box_maximum"], z["box_nsteps"]
+    rng_ = float(np.nanmax(z["node_values_f"]) - np.nanmin(z["node_values_f"]))
+    kw = dict(world_to_local=z["w2l"])
+    np.testing.assert_allclose(e.evaluate_lattice(lo, hi, n, "F", **kw), z["node_values_f"], rtol=0, atol=1e-13 * rng_)
+    np.testing.assert_allclose(e.evaluate_lattice(lo, hi, n, "C", **kw), z["node_values_c"], rtol=0, atol=1e-13 * rng_)
+    np.testing.assert_allclose(e.evaluate_lattice(lo, hi, n, "F", gradient=True, **kw), z["node_gradient_f"], rtol=0, atol=1e-12)
+    ext = hi - lo
+    for start, stop, nn in ((lo - 0.7 * ext, hi + 0.7 * ext, (13, 9, 21)), (lo, hi, (1, 7, 5)), (hi, lo, (6, 1, 4))):
+        for order in ("F", "C"):
+            v = e.evaluate_lattice(start, stop, nn, order, **kw)
+            ov = fa.evaluate_lattice(fld, start, stop, nn, order)
+            np.testing.assert_array_equal(np.isnan(v), np.isnan(ov))
+            np.testing.assert_allclose(v, ov, rtol=0, atol=1e-13 * rng_, equal_nan=True)
+            g = e.evaluate_lattice(start, stop, nn, order, gradient=True, **kw)
+            np.testing.assert_allclose(g, fa.evaluate_lattice(fld, start, stop, nn, order, gradient=True), rtol=0, atol=1e-12)
+    # device-pointer entry point, a lattice of 2.1e7 points (more than one staging chunk on the host path)
+    nn = (300, 280, 250)
+    total = int(np.prod(nn))
+    out = torch.empty(total, dtype=torch.float64, device="cuda")
+    e.evaluate_lattice(lo, hi, nn, "F", out_ptr=out.data_ptr(), stream=torch.cuda.current_stream().cuda_stream, **kw)
+    torch.cuda.synchronize()
+    host = e.evaluate_lattice(lo, hi, nn, "F", **kw)
+    np.testing.assert_array_equal(out.cpu().numpy(), host)
+    # against the ordinary gather on explicitly built coordinates (every 997-th point)
+    pts = fa.lattice_points(lo, hi, nn, "F")[::997]
+    local = pts @ z["w2l"][:3, :3].T + z["w2l"][:3, 3]
+    np.testing.assert_allclose(host[::997], e.evaluate_value(local), rtol=0, atol=1e-12 * rng_, equal_nan=True)
+    e.close()
