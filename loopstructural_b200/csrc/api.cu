@@ -336,82 +336,100 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
       CK(cudaEventRecord(h->ev_fork, h->stream));
       CK(cudaStreamWaitEvent(h->side[0], h->ev_fork, 0));
     }
+    // Launch order decides which kernel's CTAs reach the SMs first.  Default: box first (the gather shell then only
+    // finds room on the SMs the box leaves one slot short, profiles/r01r).  LSB200_SHELL_FIRST=1 enqueues the
+    // latency-bound shell first so that the box fills in around it -- an experiment for the next GPU session, off by
+    // default because it has not been measured.
+    static const bool shell_first = getenv("LSB200_SHELL_FIRST") && atoi(getenv("LSB200_SHELL_FIRST")) == 1;
+    auto launch_box = [&]() -> int {
     {
-      const UniConsts U = make_uni_consts(w);
-      const int cz = h->main_cz;
-      // output planes of the z-general launch (next to the z faces this handle owns) and of the uniform launch
-      static const int zface = (getenv("LSB200_ZFACE") && atoi(getenv("LSB200_ZFACE")) >= 3) ? atoi(getenv("LSB200_ZFACE")) : 8;
-      int zr[6];
-      plan_z_ranges(g.nz, g.k0, g.k1, cz, zface, zr);
-      const int za0 = zr[0], za1 = zr[1], zb0 = zr[2], zb1 = zr[3], ulo = zr[4], uhi = zr[5];
-      const bool zfirst = za1 > za0, zlast = zb1 > zb0;
-      const int nuni = (uhi - ulo + cz - 1) / cz;
-      const bool have_z = zfirst || zlast;
-      if (have_z && ov) CK(cudaStreamWaitEvent(h->side[2], h->ev_fork, 0));
-      cudaStream_t zs = (have_z && ov) ? h->side[2] : h->stream;
-      double* zpart = h->partials + 4 * (size_t)MAX_PARTIALS;
-      unsigned int* zcnt = h->counters + 4;
-      const dim3 ugrid(h->main_grid.x, h->main_grid.y, nuni), zgrid(h->main_grid.x, h->main_grid.y, (zb1 > zb0) ? 2 : 1);
-      switch (h->main_cfg) {
+        const UniConsts U = make_uni_consts(w);
+        const int cz = h->main_cz;
+        // output planes of the z-general launch (next to the z faces this handle owns) and of the uniform launch
+        static const int zface = (getenv("LSB200_ZFACE") && atoi(getenv("LSB200_ZFACE")) >= 3) ? atoi(getenv("LSB200_ZFACE")) : 8;
+        int zr[6];
+        plan_z_ranges(g.nz, g.k0, g.k1, cz, zface, zr);
+        const int za0 = zr[0], za1 = zr[1], zb0 = zr[2], zb1 = zr[3], ulo = zr[4], uhi = zr[5];
+        const bool zfirst = za1 > za0, zlast = zb1 > zb0;
+        const int nuni = (uhi - ulo + cz - 1) / cz;
+        const bool have_z = zfirst || zlast;
+        if (have_z && ov) CK(cudaStreamWaitEvent(h->side[2], h->ev_fork, 0));
+        cudaStream_t zs = (have_z && ov) ? h->side[2] : h->stream;
+        double* zpart = h->partials + 4 * (size_t)MAX_PARTIALS;
+        unsigned int* zcnt = h->counters + 4;
+        const dim3 ugrid(h->main_grid.x, h->main_grid.y, nuni), zgrid(h->main_grid.x, h->main_grid.y, (zb1 > zb0) ? 2 : 1);
+        switch (h->main_cfg) {
 #define X(ID, YB, TYT, ST, MINB)                                                                                  \
   case ID: {                                                                                                      \
-    const size_t smem = sizeof(double) * MainCfg<YB, TYT, ST>::PLANE * ST;                                        \
-    if (vec16) {                                                                                                  \
-      auto ku = k_fdi_box<YB, TYT, ST, MINB, true, false>;                                                        \
-      auto kz = k_fdi_box<YB, TYT, ST, MINB, true, true>;                                                         \
-      cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
-      cudaFuncSetAttribute(kz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
-      if (ugrid.z > 0) ku<<<ugrid, dim3(32, TYT), smem, h->stream>>>(g, U, p, q, cz, ulo, uhi, 0, 0, h->ztab, part, cnt, h->sc, cg_mode); \
-      if (have_z) kz<<<zgrid, dim3(32, TYT), smem, zs>>>(g, U, p, q, cz, za0, za1, zb0, zb1, h->ztab, zpart, zcnt, h->sc, cg_mode);      \
-    } else {                                                                                                      \
-      auto ku = k_fdi_box<YB, TYT, ST, MINB, false, false>;                                                       \
-      auto kz = k_fdi_box<YB, TYT, ST, MINB, false, true>;                                                        \
-      cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
-      cudaFuncSetAttribute(kz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
-      if (ugrid.z > 0) ku<<<ugrid, dim3(32, TYT), smem, h->stream>>>(g, U, p, q, cz, ulo, uhi, 0, 0, h->ztab, part, cnt, h->sc, cg_mode); \
-      if (have_z) kz<<<zgrid, dim3(32, TYT), smem, zs>>>(g, U, p, q, cz, za0, za1, zb0, zb1, h->ztab, zpart, zcnt, h->sc, cg_mode);      \
-    }                                                                                                             \
+      const size_t smem = sizeof(double) * MainCfg<YB, TYT, ST>::PLANE * ST;                                        \
+      if (vec16) {                                                                                                  \
+        auto ku = k_fdi_box<YB, TYT, ST, MINB, true, false>;                                                        \
+        auto kz = k_fdi_box<YB, TYT, ST, MINB, true, true>;                                                         \
+        cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
+        cudaFuncSetAttribute(kz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
+        if (ugrid.z > 0) ku<<<ugrid, dim3(32, TYT), smem, h->stream>>>(g, U, p, q, cz, ulo, uhi, 0, 0, h->ztab, part, cnt, h->sc, cg_mode); \
+        if (have_z) kz<<<zgrid, dim3(32, TYT), smem, zs>>>(g, U, p, q, cz, za0, za1, zb0, zb1, h->ztab, zpart, zcnt, h->sc, cg_mode);      \
+      } else {                                                                                                      \
+        auto ku = k_fdi_box<YB, TYT, ST, MINB, false, false>;                                                       \
+        auto kz = k_fdi_box<YB, TYT, ST, MINB, false, true>;                                                        \
+        cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
+        cudaFuncSetAttribute(kz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
+        if (ugrid.z > 0) ku<<<ugrid, dim3(32, TYT), smem, h->stream>>>(g, U, p, q, cz, ulo, uhi, 0, 0, h->ztab, part, cnt, h->sc, cg_mode); \
+        if (have_z) kz<<<zgrid, dim3(32, TYT), smem, zs>>>(g, U, p, q, cz, za0, za1, zb0, zb1, h->ztab, zpart, zcnt, h->sc, cg_mode);      \
+      }                                                                                                             \
   } break;
-        LSB_BOX_CFGS(X)
+          LSB_BOX_CFGS(X)
 #undef X
+        }
+        CKL();
+        h->launches += (ugrid.z > 0 ? 1 : 0) + (have_z ? 1 : 0);
+        if (ugrid.z == 0) CK(cudaMemsetAsync(&h->sc->pq_part[0], 0, sizeof(double), h->stream));
+        if (!have_z) CK(cudaMemsetAsync(&h->sc->pq_part[3], 0, sizeof(double), h->stream));
+        if (have_z && ov) {
+          CK(cudaEventRecord(h->ev_join[2], h->side[2]));
+          CK(cudaStreamWaitEvent(h->stream, h->ev_join[2], 0));
+        }
       }
-      CKL();
-      h->launches += (ugrid.z > 0 ? 1 : 0) + (have_z ? 1 : 0);
-      if (ugrid.z == 0) CK(cudaMemsetAsync(&h->sc->pq_part[0], 0, sizeof(double), h->stream));
-      if (!have_z) CK(cudaMemsetAsync(&h->sc->pq_part[3], 0, sizeof(double), h->stream));
-      if (have_z && ov) {
-        CK(cudaEventRecord(h->ev_join[2], h->side[2]));
-        CK(cudaStreamWaitEvent(h->stream, h->ev_join[2], 0));
-      }
-    }
+      return 0;
+    };
+    auto launch_shell = [&]() -> int {
     // everything outside the box: one gather launch on a side stream, overlapped with the box kernel
-    // (LSB200_SHELL=0 leaves it out: profiling of the box kernel alone, results are then incomplete)
-    static const bool with_shell = !(getenv("LSB200_SHELL") && atoi(getenv("LSB200_SHELL")) == 0);
-    if (with_shell) {
-      ShellBox sb;
-      sb.ilo = 4; sb.ihi = g.nx - 4;
-      sb.jlo = 3; sb.jhi = g.ny - 3;
-      sb.klo = g.k0; sb.khi = g.k1;  // the ring columns over every owned plane; the z faces belong to k_fdi_box<ZGEN>
-      const int nzm = sb.khi - sb.klo;
-      constexpr int SNT = 128;
-      sb.ring_cols = (g.ny - (sb.jhi - sb.jlo)) * g.nx + (sb.jhi - sb.jlo) * (g.nx - (sb.ihi - sb.ilo));
-      sb.ring_blocks = (sb.ring_cols + SNT - 1) / SNT;
-      // z chunks of the ring: about 50 k marching threads in flight (measured: 16 planes at 256^3, 64 at 512^3, profiles/r01r)
-      int chunks = h->shell_cz > 0 ? (nzm + h->shell_cz - 1) / h->shell_cz : (int)(50000 / std::max(sb.ring_cols, 1));
-      chunks = std::max(1, std::min(chunks, std::max(1, nzm / 8)));
-      sb.ring_cz = nzm > 0 ? (nzm + chunks - 1) / chunks : 1;
-      sb.ring_chunks = nzm > 0 ? (nzm + sb.ring_cz - 1) / sb.ring_cz : 0;
-      sb.capA0 = g.k0; sb.capA1 = sb.klo;
-      sb.capB0 = sb.khi; sb.capB1 = g.k1;
-      sb.cap_blocks = (sb.capA1 > sb.capA0 || sb.capB1 > sb.capB0) ? (g.nx * g.ny + SNT - 1) / SNT : 0;
-      const long long nb = (long long)sb.ring_blocks * sb.ring_chunks + 2LL * sb.cap_blocks;
-      if (nb > MAX_PARTIALS) return fail(LSB200_ERR_ARG, "shell launch needs %lld CTAs (limit %d)", nb, MAX_PARTIALS);
-      if (nb > 0)
-        k_fdi_shell<SNT><<<(int)nb, SNT, 0, ov ? h->side[0] : h->stream>>>(g, w, sb, h->ztab, p, q,
-                                                                          h->partials + 3 * (size_t)MAX_PARTIALS,
-                                                                          h->counters + 3, h->sc, cg_mode);
-      CKL();
-      h->launches++;
+      // (LSB200_SHELL=0 leaves it out: profiling of the box kernel alone, results are then incomplete)
+      static const bool with_shell = !(getenv("LSB200_SHELL") && atoi(getenv("LSB200_SHELL")) == 0);
+      if (with_shell) {
+        ShellBox sb;
+        sb.ilo = 4; sb.ihi = g.nx - 4;
+        sb.jlo = 3; sb.jhi = g.ny - 3;
+        sb.klo = g.k0; sb.khi = g.k1;  // the ring columns over every owned plane; the z faces belong to k_fdi_box<ZGEN>
+        const int nzm = sb.khi - sb.klo;
+        constexpr int SNT = 128;
+        sb.ring_cols = (g.ny - (sb.jhi - sb.jlo)) * g.nx + (sb.jhi - sb.jlo) * (g.nx - (sb.ihi - sb.ilo));
+        sb.ring_blocks = (sb.ring_cols + SNT - 1) / SNT;
+        // z chunks of the ring: about 50 k marching threads in flight (measured: 16 planes at 256^3, 64 at 512^3, profiles/r01r)
+        int chunks = h->shell_cz > 0 ? (nzm + h->shell_cz - 1) / h->shell_cz : (int)(50000 / std::max(sb.ring_cols, 1));
+        chunks = std::max(1, std::min(chunks, std::max(1, nzm / 8)));
+        sb.ring_cz = nzm > 0 ? (nzm + chunks - 1) / chunks : 1;
+        sb.ring_chunks = nzm > 0 ? (nzm + sb.ring_cz - 1) / sb.ring_cz : 0;
+        sb.capA0 = g.k0; sb.capA1 = sb.klo;
+        sb.capB0 = sb.khi; sb.capB1 = g.k1;
+        sb.cap_blocks = (sb.capA1 > sb.capA0 || sb.capB1 > sb.capB0) ? (g.nx * g.ny + SNT - 1) / SNT : 0;
+        const long long nb = (long long)sb.ring_blocks * sb.ring_chunks + 2LL * sb.cap_blocks;
+        if (nb > MAX_PARTIALS) return fail(LSB200_ERR_ARG, "shell launch needs %lld CTAs (limit %d)", nb, MAX_PARTIALS);
+        if (nb > 0)
+          k_fdi_shell<SNT><<<(int)nb, SNT, 0, ov ? h->side[0] : h->stream>>>(g, w, sb, h->ztab, p, q,
+                                                                            h->partials + 3 * (size_t)MAX_PARTIALS,
+                                                                            h->counters + 3, h->sc, cg_mode);
+        CKL();
+        h->launches++;
+      }
+      return 0;
+    };
+    if (shell_first) {
+      if (int rc = launch_shell()) return rc;
+      if (int rc = launch_box()) return rc;
+    } else {
+      if (int rc = launch_box()) return rc;
+      if (int rc = launch_shell()) return rc;
     }
     if (ov) {
       CK(cudaEventRecord(h->ev_join[0], h->side[0]));
