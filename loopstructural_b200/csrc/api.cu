@@ -21,6 +21,7 @@
 #include "eval.cuh"
 #include "fdi_stencil.cuh"
 #include "fdi_main.cuh"
+#include "fdi_plan.cuh"
 #include "frame.cuh"
 #include "p1.cuh"
 #include "rows.cuh"
@@ -198,64 +199,21 @@ static void plan_stencil(lsb200_ctx* h, int ctas_per_sm) {
   h->sgrid = dim3(tiles_x, tiles_y, real);
 }
 
-// z-chunk length that fills `slots` CTA slots in whole waves with the least halo re-staging
-static int pick_cz(const lsb200_ctx* h, int nplanes, long long tiles, long long slots) {
-  (void)h;
-  if (nplanes < 1) return 1;
-  int best_cz = nplanes;
-  double best = -1.0;
-  const int max_nch = std::max(1, nplanes / 4);
-  for (int nch = 1; nch <= max_nch && nch <= 4096; ++nch) {
-    const int cz = (nplanes + nch - 1) / nch;
-    const int real = (nplanes + cz - 1) / cz;
-    const long long ctas = tiles * real;
-    if (ctas > MAX_PARTIALS) break;
-    const long long waves = (ctas + slots - 1) / slots;
-    const double eff = (double)ctas / (double)(waves * slots) * (double)cz / (double)(cz + 2 * HALO);
-    if (eff > best + 1e-9) {
-      best = eff;
-      best_cz = cz;
-    }
-  }
-  return best_cz;
-}
-
-// Stencil launch plans.  IDs 0,1,2,4: k_fdi_box (interior box, uniform coefficients) beside k_fdi_shell (everything
-// else); -1: k_fdi_normal everywhere (always used on grids too small to have a box).
-// X(ID, YB rows per thread, TYT warps, ST ring planes, MINB CTAs per SM)
-// (measured and dropped, profiles/r01g: <2,16,8,1> <2,8,6,3> <3,8,8,1> <3,4,8,2>)
-#define LSB_BOX_CFGS(X) \
-  X(0, 4, 4, 8, 2)      \
-  X(1, 4, 8, 8, 1)      \
-  X(2, 2, 8, 8, 2)      \
-  X(4, 4, 4, 6, 3)
-
 static void plan_main(lsb200_ctx* h) {
   const char* env = getenv("LSB200_STENCIL_MAIN");
   int cfg = env ? atoi(env) : 4;
   h->main_cfg = -1;
   const GridDesc& g = h->g;
   if (cfg < 0 || h->kind != LSB200_SUPPORT_GRID) return;
-  if (g.ny < 16 || g.nx < 16 || g.nz < 6) return;  // tiny grids: k_fdi_normal everywhere
-  int ty = 0, minb = 1;
-  switch (cfg) {
-#define X(ID, YB, TYT, ST, MINB) case ID: ty = YB * TYT; minb = MINB; break;
-    LSB_BOX_CFGS(X)
-#undef X
-    default: cfg = 4; ty = 16; minb = 3;
-  }
   const char* czenv = getenv("LSB200_STENCIL_CZ");
   const int czo = (czenv && atoi(czenv) > 0) ? atoi(czenv) : 0;
-  auto chunks = [&](int n, int cz) { return n > 0 ? (n + cz - 1) / cz : 0; };
-  // box: z chunks over ALL owned planes; a chunk that touches a z face (ka < 3 or kb > nz-3) runs the z-general
-  // variant (k_fdi_box<..., ZGEN>), the others the uniform one
+  BoxTiles bt;
+  if (!plan_box_tiles(g, cfg, czo, h->sm_count, MAX_PARTIALS, &bt)) return;  // no box: k_fdi_normal everywhere
+  cfg = bt.cfg;
   h->box_z0 = g.k0;
   h->box_z1 = g.k1;
-  const int tiles_x = (g.nx - 8 + 63) / 64, tiles_y = (g.ny - 6 + ty - 1) / ty;
-  h->main_cz = czo ? czo : pick_cz(h, g.nzl, (long long)tiles_x * tiles_y, (long long)h->sm_count * minb);
-  h->main_cz = std::min(std::max(h->main_cz, 3), BOX_ZGEN_MAX_STEPS - 2 * HALO);  // a face chunk covers planes 0..2 / nz-3..nz-1
-  h->main_grid = dim3(tiles_x, tiles_y, chunks(g.nzl, h->main_cz));
-  if ((long long)h->main_grid.x * h->main_grid.y * h->main_grid.z > MAX_PARTIALS) return;
+  h->main_cz = bt.cz;
+  h->main_grid = dim3(bt.tiles_x, bt.tiles_y, bt.chunks);
   { const char* e = getenv("LSB200_SHELL_CZ"); h->shell_cz = (e && atoi(e) > 0) ? atoi(e) : 0; }
   if (!h->ztab) {
     std::vector<double> zt((size_t)g.nz * SHELL_ZSTRIDE);
@@ -264,45 +222,6 @@ static void plan_main(lsb200_ctx* h) {
     if (cudaMemcpy(h->ztab, zt.data(), sizeof(double) * zt.size(), cudaMemcpyHostToDevice) != cudaSuccess) return;
   }
   h->main_cfg = cfg;
-}
-
-// Output planes of the three box launches of a handle owning [k0,k1) of nz planes, z chunk cz:
-//   out[0..1] = A, out[2..3] = B: ranges of the z-general launch (k_fdi_box<ZGEN>), next to the z faces the handle owns;
-//               short (zface planes: that variant is ~1.3x slower per plane), A non-empty whenever B is;
-//   out[4..5] = U: range of the uniform launch, every plane of it satisfies 3 <= k <= nz-4.
-// A, U, B are disjoint and cover [k0,k1).  Exported as lsb200_plan_z_ranges for the CPU tests.
-static void plan_z_ranges(int nz, int k0, int k1, int cz, int zface, int out[6]) {
-  const bool lo_face = k0 < 3, hi_face = k1 > nz - 3;
-  const int zc = std::max(3, std::min(cz, zface));
-  const int zl = lo_face ? std::min(k1, k0 + zc) : k0;
-  const int zh = hi_face ? std::max(zl, k1 - zc) : k1;
-  int za0 = 0, za1 = 0, zb0 = 0, zb1 = 0;
-  if (lo_face) { za0 = k0; za1 = zl; }
-  if (hi_face && zh < k1) { zb0 = zh; zb1 = k1; }
-  if (za1 <= za0 && zb1 > zb0) {  // only the upper face: it becomes range A, the launch has one z block
-    za0 = zb0; za1 = zb1; zb0 = zb1 = 0;
-  }
-  out[0] = za0; out[1] = za1; out[2] = zb0; out[3] = zb1;
-  out[4] = zl; out[5] = std::max(zl, zh);
-}
-
-static UniConsts make_uni_consts(const StencilWeights& w) {
-  UniConsts U;
-  U.cc = w.axx + w.ayy + w.azz + 4.0 * (w.bxy + w.bxz + w.byz) + w.ridge2;
-  U.cx1 = w.axx * (-2.0 / 3.0);
-  U.cx2 = w.axx * (1.0 / 6.0) - 2.0 * (w.bxy + w.bxz);
-  U.cy1 = w.ayy * (-2.0 / 3.0);
-  U.cy2 = w.ayy * (1.0 / 6.0) - 2.0 * (w.bxy + w.byz);
-  U.bxy = w.bxy;
-  U.kz = w.azz * (1.0 / 6.0) - 2.0 * (w.bxz + w.byz);
-  U.bxz = w.bxz; U.byz = w.byz;
-  U.zt1 = w.azz * (-2.0 / 3.0);
-  U.cxy = w.axx + w.ayy + 4.0 * w.bxy;
-  U.cx2xy = w.axx * (1.0 / 6.0) - 2.0 * w.bxy;
-  U.cy2xy = w.ayy * (1.0 / 6.0) - 2.0 * w.bxy;
-  U.g0 = 2.0 * (w.bxz + w.byz);
-  U.azz = w.azz; U.dz = w.dz; U.ridge2 = w.ridge2;
-  return U;
 }
 
 static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode) {
@@ -397,23 +316,9 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
       // (LSB200_SHELL=0 leaves it out: profiling of the box kernel alone, results are then incomplete)
       static const bool with_shell = !(getenv("LSB200_SHELL") && atoi(getenv("LSB200_SHELL")) == 0);
       if (with_shell) {
-        ShellBox sb;
-        sb.ilo = 4; sb.ihi = g.nx - 4;
-        sb.jlo = 3; sb.jhi = g.ny - 3;
-        sb.klo = g.k0; sb.khi = g.k1;  // the ring columns over every owned plane; the z faces belong to k_fdi_box<ZGEN>
-        const int nzm = sb.khi - sb.klo;
         constexpr int SNT = 128;
-        sb.ring_cols = (g.ny - (sb.jhi - sb.jlo)) * g.nx + (sb.jhi - sb.jlo) * (g.nx - (sb.ihi - sb.ilo));
-        sb.ring_blocks = (sb.ring_cols + SNT - 1) / SNT;
-        // z chunks of the ring: about 50 k marching threads in flight (measured: 16 planes at 256^3, 64 at 512^3, profiles/r01r)
-        int chunks = h->shell_cz > 0 ? (nzm + h->shell_cz - 1) / h->shell_cz : (int)(50000 / std::max(sb.ring_cols, 1));
-        chunks = std::max(1, std::min(chunks, std::max(1, nzm / 8)));
-        sb.ring_cz = nzm > 0 ? (nzm + chunks - 1) / chunks : 1;
-        sb.ring_chunks = nzm > 0 ? (nzm + sb.ring_cz - 1) / sb.ring_cz : 0;
-        sb.capA0 = g.k0; sb.capA1 = sb.klo;
-        sb.capB0 = sb.khi; sb.capB1 = g.k1;
-        sb.cap_blocks = (sb.capA1 > sb.capA0 || sb.capB1 > sb.capB0) ? (g.nx * g.ny + SNT - 1) / SNT : 0;
-        const long long nb = (long long)sb.ring_blocks * sb.ring_chunks + 2LL * sb.cap_blocks;
+        ShellBox sb;
+        const long long nb = make_shell_box(g, h->shell_cz, SNT, &sb);
         if (nb > MAX_PARTIALS) return fail(LSB200_ERR_ARG, "shell launch needs %lld CTAs (limit %d)", nb, MAX_PARTIALS);
         if (nb > 0)
           k_fdi_shell<SNT><<<(int)nb, SNT, 0, ov ? h->side[0] : h->stream>>>(g, w, sb, h->ztab, p, q,

@@ -80,6 +80,15 @@ struct CgScalars {
   int pad;
 };
 
+// Dynamic shared memory of a kernel.  (LSB_EMU: tests/hostsim/cuda_emu.h runs the block-level kernels on the CPU, one
+// OS thread per CUDA thread, to check launch plans and kernels without a device; it is never defined in the library.)
+#ifdef LSB_EMU
+#define LSB_DYN_SMEM(name) double* name = lsb_emu::dyn_smem()
+#else
+#define LSB_DYN_SMEM(name) extern __shared__ __align__(16) double name[]
+#endif
+
+#ifndef LSB_EMU
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -101,6 +110,21 @@ __device__ __forceinline__ double block_sum(double v, double* red /* >= NT/32 do
   __syncthreads();
   return s;
 }
+#else
+// emulation: same contract (sum valid in thread 0), plain sum through a CTA-wide scratch array
+template <int NT>
+inline double block_sum(double v, double* /*red*/) {
+  static double scratch[NT];
+  const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  scratch[tid] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (tid == 0)
+    for (int i = 0; i < NT; ++i) s += scratch[i];
+  __syncthreads();
+  return s;
+}
+#endif
 
 // "last block done" reduction of per-block partials in a fixed order.  Returns true in
 // thread 0 of the last-arriving block, with *total holding the sum.

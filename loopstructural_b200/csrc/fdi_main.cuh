@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
               const int cg_mode) {
   using C = MainCfg<YB, TYT, ST>;
   static_assert(ST >= 5, "ring needs planes kp-2..kp plus at least two in flight");
-  extern __shared__ __align__(16) double S[];
+  LSB_DYN_SMEM(S);
   __shared__ double red[C::NT / 32];
   __shared__ ZStep zsm[ZGEN ? BOX_ZGEN_MAX_STEPS : 1];  // z coefficients of every plane step of this CTA (ZGEN)
 

@@ -57,6 +57,16 @@ struct StencilCfg {
 };
 
 // cp.async (LDGSTS): global -> shared without a register round trip, zero-filled when !valid
+#ifdef LSB_EMU
+inline void cp_async_8(double* smem_dst, const double* gsrc, bool valid) { smem_dst[0] = valid ? gsrc[0] : 0.0; }
+inline void cp_async_16(double* smem_dst, const double* gsrc, bool valid) {
+  smem_dst[0] = valid ? gsrc[0] : 0.0;
+  smem_dst[1] = valid ? gsrc[1] : 0.0;
+}
+inline void cp_async_commit() {}
+template <int N>
+inline void cp_async_wait() {}
+#else
 __device__ __forceinline__ void cp_async_8(double* smem_dst, const double* gsrc, bool valid) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   const int n = valid ? 8 : 0;
@@ -70,6 +80,7 @@ __device__ __forceinline__ void cp_async_16(double* smem_dst, const double* gsrc
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+#endif
 
 // the five staged rows a thread needs for its XB outputs: rc/rm2/rp2 hold columns i0-2..i0+XB+1 of
 // rows j, j-2, j+2; rm1/rp1 hold columns i0..i0+XB-1 of rows j-1, j+1
@@ -273,7 +284,7 @@ __global__ void __launch_bounds__(TXT* TYT, MINB)
                  const int cz, double* __restrict__ partials, unsigned int* __restrict__ counter,
                  CgScalars* __restrict__ sc, const int cg_mode) {
   using C = StencilCfg<XB, TXT, TYT, ST>;
-  extern __shared__ __align__(16) double S[];  // STAGES planes
+  LSB_DYN_SMEM(S);  // STAGES planes
   __shared__ double red[C::NT / 32];
 
   if (cg_mode && sc->done) return;

@@ -1,0 +1,131 @@
+// TEST INFRASTRUCTURE ONLY: runs the three launches of the tiled FDI regularisation operator (k_fdi_box uniform,
+// k_fdi_box<ZGEN>, k_fdi_shell -- loopstructural_b200/csrc/fdi_main.cuh, unmodified) and the single-kernel form
+// (k_fdi_normal) on the CPU through tests/hostsim/cuda_emu.h, with the launch plan of csrc/fdi_plan.cuh that
+// csrc/api.cu's launch_stencil uses, for ONE handle: a full grid or a z slab [k0,k1) whose halo planes are filled
+// from the global vector as the NCCL halo exchange would.  tests/test_stencil_emu.py compares it with the oracle.
+//
+//   g++ -O1 -std=c++20 -pthread -mfma -DLSB_EMU -I/usr/local/cuda/include -fPIC -shared \
+//       -o tests/hostsim/libstencil_emu.so tests/hostsim/stencil_emu.cpp
+#include "cuda_emu.h"
+
+#include <string.h>
+
+#include "../../loopstructural_b200/csrc/fdi_plan.cuh"
+
+using namespace lsb;
+
+namespace {
+constexpr int MAX_PARTIALS = 1 << 18;  // as in csrc/api.cu
+
+StencilWeights weights_from(const double* ew, double ridge2) {  // make_weights of csrc/api.cu
+  StencilWeights w;
+  w.axx = ew[0] * ew[0]; w.ayy = ew[1] * ew[1]; w.azz = ew[2] * ew[2];
+  w.bxy = 0.25 * ew[3] * ew[3]; w.bxz = 0.25 * ew[4] * ew[4]; w.byz = 0.25 * ew[5] * ew[5];
+  w.dx = ew[6] * ew[6]; w.dy = ew[7] * ew[7]; w.dz = ew[8] * ew[8];
+  w.ridge2 = ridge2;
+  return w;
+}
+}  // namespace
+
+extern "C" {
+
+// dims = {nx, ny, nz, k0, k1}; ew = the nine effective row weights (LSB200_W_* order: mixed terms as given to
+// lsb200_set_regularisation, i.e. already divided by 4 ... see weights_from); p_global: nx*ny*nz; q_owned: nx*ny*(k1-k0).
+// cfg >= 0: box + shell launches (as LSB200_STENCIL_MAIN), cfg < 0: k_fdi_normal.  info[0..5] = z ranges, info[6] = cz,
+// info[7] = CTAs launched, info[8] = 1 if the box plan was used.  pq_out = p.q over the owned planes as the kernels sum it.
+int emu_fdi_matvec(const int* dims, const double* ew, double ridge2, int cfg, int cz_override, int zface, int shell_cz,
+                   const double* p_global, double* q_owned, double* pq_out, int* info) {
+  GridDesc g{};
+  g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
+  g.k0 = dims[3]; g.k1 = dims[4]; g.nzl = g.k1 - g.k0;
+  g.pitch = g.nx;
+  g.plane = (long long)g.pitch * g.ny;
+  g.nloc = g.plane * g.nzl;
+  g.nall = g.plane * (g.nzl + 2 * HALO);
+  for (int a = 0; a < 3; ++a) { g.origin[a] = 0.0; g.step[a] = 1.0; }
+  const StencilWeights w = weights_from(ew, ridge2);
+  // node vectors as ensure_vectors lays them out: zeroed guard plane, nzl + 4 planes, guard plane
+  const size_t guard = ((size_t)g.plane + 31) & ~(size_t)31;
+  std::vector<double> pst((size_t)g.nall + 2 * guard, 0.0), qst((size_t)g.nall + 2 * guard, nan(""));
+  double* p = pst.data() + guard;
+  double* q = qst.data() + guard;
+  for (int k = g.k0 - HALO; k < g.k1 + HALO; ++k)  // owned planes + what the halo exchange delivers
+    if (k >= 0 && k < g.nz)
+      memcpy(p + (size_t)(k - g.k0 + HALO) * g.plane, p_global + (size_t)k * g.plane, sizeof(double) * g.plane);
+  std::vector<double> ztab((size_t)g.nz * SHELL_ZSTRIDE);
+  shell_fill_z_table(g.nz, ztab.data());
+  std::vector<double> partials((size_t)6 * MAX_PARTIALS, 0.0);
+  unsigned int counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  CgScalars sc{};
+  const bool vec16 = (g.pitch % 2) == 0;
+  int ctas = 0;
+  BoxTiles bt{};
+  const bool box = cfg >= 0 && plan_box_tiles(g, cfg, cz_override, 148, MAX_PARTIALS, &bt);
+  for (int i = 0; i < 9; ++i) info[i] = 0;
+  if (box) {
+    const UniConsts U = make_uni_consts(w);
+    int zr[6];
+    plan_z_ranges(g.nz, g.k0, g.k1, bt.cz, zface, zr);
+    const int za0 = zr[0], za1 = zr[1], zb0 = zr[2], zb1 = zr[3], ulo = zr[4], uhi = zr[5];
+    const int nuni = (uhi - ulo + bt.cz - 1) / bt.cz;
+    const bool have_z = za1 > za0 || zb1 > zb0;
+    const dim3 ugrid(bt.tiles_x, bt.tiles_y, nuni), zgrid(bt.tiles_x, bt.tiles_y, (zb1 > zb0) ? 2 : 1);
+    double* part = partials.data();
+    double* zpart = partials.data() + 4 * (size_t)MAX_PARTIALS;
+    const int cz = bt.cz;
+    switch (bt.cfg) {  // the dispatch of launch_stencil, launches through the emulator
+#define X(ID, YB, TYT, ST, MINB)                                                                                     \
+  case ID: {                                                                                                         \
+    const size_t smem = sizeof(double) * MainCfg<YB, TYT, ST>::PLANE * ST;                                           \
+    if (vec16) {                                                                                                     \
+      if (ugrid.z > 0) lsb_emu::launch(ugrid, dim3(32, TYT), smem, [&] { k_fdi_box<YB, TYT, ST, MINB, true, false>(g, U, p, q, cz, ulo, uhi, 0, 0, ztab.data(), part, counters + 0, &sc, 0); }); \
+      if (have_z) lsb_emu::launch(zgrid, dim3(32, TYT), smem, [&] { k_fdi_box<YB, TYT, ST, MINB, true, true>(g, U, p, q, cz, za0, za1, zb0, zb1, ztab.data(), zpart, counters + 4, &sc, 0); }); \
+    } else {                                                                                                         \
+      if (ugrid.z > 0) lsb_emu::launch(ugrid, dim3(32, TYT), smem, [&] { k_fdi_box<YB, TYT, ST, MINB, false, false>(g, U, p, q, cz, ulo, uhi, 0, 0, ztab.data(), part, counters + 0, &sc, 0); }); \
+      if (have_z) lsb_emu::launch(zgrid, dim3(32, TYT), smem, [&] { k_fdi_box<YB, TYT, ST, MINB, false, true>(g, U, p, q, cz, za0, za1, zb0, zb1, ztab.data(), zpart, counters + 4, &sc, 0); }); \
+    }                                                                                                                \
+  } break;
+      LSB_BOX_CFGS(X)
+#undef X
+    }
+    ctas += (ugrid.z > 0 ? ugrid.x * ugrid.y * ugrid.z : 0) + (have_z ? zgrid.x * zgrid.y * zgrid.z : 0);
+    if (ugrid.z == 0) sc.pq_part[0] = 0.0;
+    if (!have_z) sc.pq_part[3] = 0.0;
+    constexpr int SNT = 128;
+    ShellBox sb;
+    const long long nb = make_shell_box(g, shell_cz, SNT, &sb);
+    if (nb > MAX_PARTIALS) return -1;
+    if (nb > 0)
+      lsb_emu::launch(dim3((unsigned)nb), dim3(SNT), 0, [&] {
+        k_fdi_shell<SNT>(g, w, sb, ztab.data(), p, q, partials.data() + 3 * (size_t)MAX_PARTIALS, counters + 3, &sc, 0);
+      });
+    ctas += (int)nb;
+    for (int i = 0; i < 6; ++i) info[i] = zr[i];
+    info[6] = cz;
+    info[8] = 1;
+    *pq_out = sc.pq_part[0] + sc.pq_part[2] + sc.pq_part[3];
+  } else {
+    // k_fdi_normal everywhere: plan_stencil<2,32,8>(h, 2) of csrc/api.cu with one z chunk per 16 planes
+    using C = StencilCfg<2, 32, 8, 4>;
+    const int tiles_x = (g.nx + C::TX - 1) / C::TX, tiles_y = (g.ny + C::TY - 1) / C::TY;
+    const int cz = cz_override > 0 ? cz_override : std::max(4, std::min(g.nzl, 16));
+    const dim3 grid(tiles_x, tiles_y, (g.nzl + cz - 1) / cz);
+    const size_t smem = sizeof(double) * C::PLANE * 4;
+    if (vec16) lsb_emu::launch(grid, dim3(32, 8), smem, [&] { k_fdi_normal<2, 32, 8, 2, 4, true>(g, w, p, q, cz, partials.data(), counters + 0, &sc, 0); });
+    else lsb_emu::launch(grid, dim3(32, 8), smem, [&] { k_fdi_normal<2, 32, 8, 2, 4, false>(g, w, p, q, cz, partials.data(), counters + 0, &sc, 0); });
+    ctas += grid.x * grid.y * grid.z;
+    info[6] = cz;
+    *pq_out = sc.pq_part[0];
+  }
+  info[7] = ctas;
+  for (int k = 0; k < g.nzl; ++k)
+    memcpy(q_owned + (size_t)k * g.plane, q + (size_t)(k + HALO) * g.plane, sizeof(double) * g.plane);
+  // nothing may be written outside the owned planes (halo and guard planes keep their sentinel)
+  for (size_t i = 0; i < qst.size(); ++i) {
+    const bool owned = i >= guard + (size_t)HALO * g.plane && i < guard + (size_t)(HALO + g.nzl) * g.plane;
+    if (!owned && qst[i] == qst[i]) return -2;
+  }
+  return 0;
+}
+
+}  // extern "C"
