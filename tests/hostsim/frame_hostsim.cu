@@ -47,9 +47,10 @@ void build(HostFrame& H, const int64_t* nsteps, const double* origin, const doub
 }
 }  // namespace
 
+#define HOSTSIM_API __attribute__((visibility("default")))
 extern "C" {
 
-int hostsim_frame_eval(const int64_t* nsteps, const double* origin, const double* step, const double* c0, const double* c1,
+HOSTSIM_API int hostsim_frame_eval(const int64_t* nsteps, const double* origin, const double* step, const double* c0, const double* c1,
                        const double* c2, const double* transforms, int gradient_of, int64_t n, const double* xyz,
                        double* values, double* gradient) {
   HostFrame H;
@@ -64,7 +65,7 @@ int hostsim_frame_eval(const int64_t* nsteps, const double* origin, const double
   return 0;
 }
 
-int hostsim_fault_displace(const int64_t* nsteps, const double* origin, const double* step, const double* c0,
+HOSTSIM_API int hostsim_fault_displace(const int64_t* nsteps, const double* origin, const double* step, const double* c0,
                            const double* c1, const double* c2, const double* transforms,
                            const lsb200_fault_profile* profile, double displacement, int steps, int64_t n,
                            const double* xyz, double* moved) {
@@ -81,7 +82,7 @@ int hostsim_fault_displace(const int64_t* nsteps, const double* origin, const do
   return 0;
 }
 
-int hostsim_fault_displacement(const int64_t* nsteps, const double* origin, const double* step, const double* c0,
+HOSTSIM_API int hostsim_fault_displacement(const int64_t* nsteps, const double* origin, const double* step, const double* c0,
                                const double* c1, const double* c2, const double* transforms,
                                const lsb200_fault_profile* profile, double displacement, double offset, int64_t n,
                                const double* xyz, double* d) {
@@ -100,7 +101,7 @@ int hostsim_fault_displacement(const int64_t* nsteps, const double* origin, cons
 // body of k_fdi_field_orthogonal_rows: rows of `target` (nsteps/origin/step at index 0 of the three-field arrays are the
 // TARGET support, index 1 the OTHER field whose c is c1 and whose transform is transforms[21..42)); outputs are
 // (n_rows, 8) row-major values / local column ids (-1 = empty), b and w^2.
-int hostsim_field_orthogonal_rows(const int64_t* nsteps, const double* origin, const double* step, const double* c_other,
+HOSTSIM_API int hostsim_field_orthogonal_rows(const int64_t* nsteps, const double* origin, const double* step, const double* c_other,
                                   const double* transforms, int64_t estep, double weight, double bval, int64_t n_rows,
                                   double* vals, int64_t* cols, double* b, double* w2) {
   HostFrame H;
@@ -127,7 +128,7 @@ int hostsim_field_orthogonal_rows(const int64_t* nsteps, const double* origin, c
 }
 
 // body of k_eval_lattice for the field at index 0 of the three-field arrays
-int hostsim_eval_lattice(const int64_t* nsteps, const double* origin, const double* step, const double* c0,
+HOSTSIM_API int hostsim_eval_lattice(const int64_t* nsteps, const double* origin, const double* step, const double* c0,
                          const double* transforms, const double* start, const double* stop, const int64_t* n, int order_f,
                          int gradient, double* out) {
   HostFrame H;

@@ -4,7 +4,7 @@
 // csrc/api.cu's launch_stencil uses, for ONE handle: a full grid or a z slab [k0,k1) whose halo planes are filled
 // from the global vector as the NCCL halo exchange would.  tests/test_stencil_emu.py compares it with the oracle.
 //
-//   g++ -O1 -std=c++20 -pthread -mfma -DLSB_EMU -I/usr/local/cuda/include -fPIC -shared \
+//   g++ -O1 -std=c++20 -pthread -mfma -DLSB_EMU -I/usr/local/cuda/include -fPIC -fvisibility=hidden -Wl,-Bsymbolic -shared \
 //       -o tests/hostsim/libstencil_emu.so tests/hostsim/stencil_emu.cpp
 #include "cuda_emu.h"
 
@@ -27,13 +27,14 @@ StencilWeights weights_from(const double* ew, double ridge2) {  // make_weights 
 }
 }  // namespace
 
+#define HOSTSIM_API __attribute__((visibility("default")))
 extern "C" {
 
 // dims = {nx, ny, nz, k0, k1}; ew = the nine effective row weights (LSB200_W_* order: mixed terms as given to
 // lsb200_set_regularisation, i.e. already divided by 4 ... see weights_from); p_global: nx*ny*nz; q_owned: nx*ny*(k1-k0).
 // cfg >= 0: box + shell launches (as LSB200_STENCIL_MAIN), cfg < 0: k_fdi_normal.  info[0..5] = z ranges, info[6] = cz,
 // info[7] = CTAs launched, info[8] = 1 if the box plan was used.  pq_out = p.q over the owned planes as the kernels sum it.
-int emu_fdi_matvec(const int* dims, const double* ew, double ridge2, int cfg, int cz_override, int zface, int shell_cz,
+HOSTSIM_API int emu_fdi_matvec(const int* dims, const double* ew, double ridge2, int cfg, int cz_override, int zface, int shell_cz,
                    const double* p_global, double* q_owned, double* pq_out, int* info) {
   GridDesc g{};
   g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];

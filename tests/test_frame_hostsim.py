@@ -28,7 +28,7 @@ def sim():
         pytest.skip("nvcc not available")
     deps = [SRC] + glob.glob(os.path.join(CSRC, "*.cuh"))
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
-        subprocess.run([nvcc, "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-gencode",
+        subprocess.run([nvcc, "-O2", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xlinker", "-Bsymbolic", "-shared", "-gencode",
                         "arch=compute_100a,code=sm_100a", "-o", LIB, SRC], check=True, capture_output=True)
     return C.CDLL(LIB)
 

@@ -33,7 +33,8 @@ def emu():
     deps = [SRC, os.path.join(HERE, "hostsim", "cuda_emu.h")] + glob.glob(os.path.join(CSRC, "*.cuh"))
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.run([gxx, "-O1", "-std=c++20", "-pthread", "-mfma", "-w", "-DLSB_EMU", "-I/usr/local/cuda/include", "-fPIC",
-                        "-shared", "-o", LIB, SRC], check=True, capture_output=True)
+                        # its own instantiations of the kernels, not the device stubs of liblsb200.so (RTLD_GLOBAL)
+                        "-fvisibility=hidden", "-Wl,-Bsymbolic", "-shared", "-o", LIB, SRC], check=True, capture_output=True)
     return C.CDLL(LIB)
 
 
