@@ -81,6 +81,11 @@ int lsb200_create_grid(const int64_t nsteps[3], const double origin[3], const do
 int lsb200_create_tetmesh(const int64_t nsteps[3], const double origin[3], const double step[3],
                           int device, lsb200_handle* out);
 
+/* the same support owning the node planes [k0,k1) only (z-slab of a multi-GPU P1 solve; evaluation needs a handle
+ * that owns every plane) */
+int lsb200_create_tetmesh_slab(const int64_t nsteps[3], const double origin[3], const double step[3],
+                               int64_t k0, int64_t k1, int device, lsb200_handle* out);
+
 int lsb200_destroy(lsb200_handle h);
 
 /* number of node values held by this handle (owned planes) and the support kind */

@@ -63,6 +63,7 @@ SIGNATURES = {
     "lsb200_device_count": (C.c_int, []),
     "lsb200_create_grid": (C.c_int, [c_int64_p, c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_int, C.POINTER(Handle)]),
     "lsb200_create_tetmesh": (C.c_int, [c_int64_p, c_double_p, c_double_p, C.c_int, C.POINTER(Handle)]),
+    "lsb200_create_tetmesh_slab": (C.c_int, [c_int64_p, c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_int, C.POINTER(Handle)]),
     "lsb200_destroy": (C.c_int, [Handle]),
     "lsb200_local_dof": (C.c_int64, [Handle]),
     "lsb200_support_kind": (C.c_int, [Handle]),

@@ -373,8 +373,8 @@ static int launch_regularisation(lsb200_ctx* h, const double* p, double* q, int 
   if (h->kind == LSB200_SUPPORT_GRID) return launch_stencil(h, p, q, cg_mode);
   if (!h->p1_table) return fail(LSB200_ERR_STATE, "tet-mesh handle without regularisation tables (lsb200_set_p1_tables)");
   const P1Tables tb{{h->p1_m[0], h->p1_m[1], h->p1_m[2]}, h->p1_table, h->p1_off, h->p1_diag};
-  const long long n = (long long)h->g.nx * h->g.ny * h->g.nz;
-  const int nb = (int)std::min<long long>((n + VEC_NT - 1) / VEC_NT, (long long)h->sm_count * 16);
+  const long long n = (long long)h->g.nx * h->g.ny * h->g.nzl;
+  const int nb = (int)std::max<long long>(1, std::min<long long>((n + VEC_NT - 1) / VEC_NT, (long long)h->sm_count * 16));
   k_p1_normal<VEC_NT><<<nb, VEC_NT, 0, h->stream>>>(h->g, tb, h->p1_w * h->p1_w, h->add_ridge ? h->ridge * h->ridge : 0.0, p, q,
                                                      h->partials, h->counters + 0, h->sc, cg_mode);
   CKL();
@@ -578,6 +578,12 @@ int lsb200_create_tetmesh(const int64_t nsteps[3], const double origin[3], const
   return create_common(LSB200_SUPPORT_TETMESH, nsteps, origin, step, 0, nsteps[2], device, out);
 }
 
+int lsb200_create_tetmesh_slab(const int64_t nsteps[3], const double origin[3], const double step[3], int64_t k0,
+                               int64_t k1, int device, lsb200_handle* out) {
+  if (!nsteps) return fail(LSB200_ERR_ARG, "null argument");
+  return create_common(LSB200_SUPPORT_TETMESH, nsteps, origin, step, k0, k1, device, out);
+}
+
 int lsb200_destroy(lsb200_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
@@ -639,24 +645,13 @@ int lsb200_set_p1_tables(lsb200_handle h, const int64_t m[3], const double* tabl
     if (!ok) return fail(LSB200_ERR_ARG, "axis %d: a small mesh of %lld cells cannot represent %d cells", a, (long long)m[a], nc[a]);
   }
   CK(cudaSetDevice(h->device));
-  // compact the 125-tap rows into fixed-width (coefficient, storage offset) lists
-  const size_t rows = (size_t)(m[0] + 1) * (m[1] + 1) * (m[2] + 1);
-  std::vector<double> coef(rows * P1_TAPS, 0.0), diag(rows, 0.0);
-  std::vector<int> off(rows * P1_TAPS, 0);
-  for (size_t r = 0; r < rows; ++r) {
-    int cnt = 0;
-    for (int t = 0; t < 125; ++t) {
-      const double c = table[r * 125 + t];
-      if (!(c == c)) return fail(LSB200_ERR_ARG, "NaN in the regularisation table");
-      if (t == 62) diag[r] = c;
-      if (c == 0.0) continue;
-      if (cnt == P1_TAPS) return fail(LSB200_ERR_ARG, "table row %zu has more than %d non-zero taps", r, P1_TAPS);
-      const int dz = t / 25 - 2, dy = (t / 5) % 5 - 2, dx = t % 5 - 2;
-      coef[r * P1_TAPS + cnt] = c;
-      off[r * P1_TAPS + cnt] = (int)(dz * h->g.plane + dy * h->g.pitch + dx);
-      ++cnt;
-    }
-  }
+  std::vector<double> coef, diag;
+  std::vector<int> off;
+  size_t bad = 0;
+  const long long mm[3] = {(long long)m[0], (long long)m[1], (long long)m[2]};
+  const int crc = p1_compact_tables(h->g, mm, table, coef, off, diag, &bad);
+  if (crc == 1) return fail(LSB200_ERR_ARG, "NaN in the regularisation table");
+  if (crc == 2) return fail(LSB200_ERR_ARG, "table row %zu has more than %d non-zero taps", bad, P1_TAPS);
   CK(cudaStreamSynchronize(h->stream));
   cudaFree(h->p1_table); cudaFree(h->p1_off); cudaFree(h->p1_diag);
   h->p1_table = nullptr; h->p1_off = nullptr; h->p1_diag = nullptr;

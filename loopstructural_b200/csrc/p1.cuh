@@ -13,6 +13,8 @@
 // its rows as a table; k_p1_normal maps each node to its representative (p1_rep) and gathers its <= 36 taps.
 // 16 B/node of algorithmic traffic (read p, write q) instead of 96 B/row + 16 B/node.
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 #include "rows.cuh"
 
@@ -27,6 +29,32 @@ struct P1Tables {
   const int* off;       // [rows][P1_TAPS], element offset of the tap in the node vector (0 for padding)
   const double* diag;   // [rows] centre coefficient
 };
+
+// host: compact the dense table (rows of 125 taps, tap (dz+2)*25 + (dy+2)*5 + (dx+2)) into fixed-width
+// (coefficient, storage offset) lists for a handle with the layout g.  Returns 0, 1 = NaN in the table, 2 = a row has
+// more than P1_TAPS non-zero taps (*bad_row).  Shared by lsb200_set_p1_tables and tests/hostsim.
+inline int p1_compact_tables(const GridDesc& g, const long long m[3], const double* table, std::vector<double>& coef,
+                             std::vector<int>& off, std::vector<double>& diag, size_t* bad_row) {
+  const size_t rows = (size_t)(m[0] + 1) * (m[1] + 1) * (m[2] + 1);
+  coef.assign(rows * P1_TAPS, 0.0);
+  diag.assign(rows, 0.0);
+  off.assign(rows * P1_TAPS, 0);
+  for (size_t r = 0; r < rows; ++r) {
+    int cnt = 0;
+    for (int t = 0; t < 125; ++t) {
+      const double c = table[r * 125 + t];
+      if (!(c == c)) return 1;
+      if (t == 62) diag[r] = c;
+      if (c == 0.0) continue;
+      if (cnt == P1_TAPS) { *bad_row = r; return 2; }
+      const int dz = t / 25 - 2, dy = (t / 5) % 5 - 2, dx = t % 5 - 2;
+      coef[r * P1_TAPS + cnt] = c;
+      off[r * P1_TAPS + cnt] = (int)(dz * g.plane + dy * g.pitch + dx);
+      ++cnt;
+    }
+  }
+  return 0;
+}
 
 // representative node of the small mesh for node i of an axis with nc cells (m cells in the small mesh):
 // same count (0, 1, >= 2) of cells on either side, same parity
@@ -48,16 +76,16 @@ __global__ void __launch_bounds__(NT)
                 CgScalars* __restrict__ sc, const int cg_mode) {
   __shared__ double red[NT / 32];
   if (cg_mode && sc->done) return;
-  const long long n = (long long)g.nx * g.ny * g.nz;
+  const long long n = (long long)g.nx * g.ny * g.nzl;  // the owned planes [k0,k1); the taps reach into the halo planes
   double dot = 0.0;
   for (long long t = blockIdx.x * (long long)NT + threadIdx.x; t < n; t += (long long)gridDim.x * NT) {
     const int i = (int)(t % g.nx);
     const long long r = t / g.nx;
-    const int j = (int)(r % g.ny), k = (int)(r / g.ny);
-    const int row = p1_row(g, tb, i, j, k);
+    const int j = (int)(r % g.ny), kl = (int)(r / g.ny);
+    const int row = p1_row(g, tb, i, j, g.k0 + kl);  // the class of a node depends on its GLOBAL plane
     const double* __restrict__ C = tb.coef + (long long)row * P1_TAPS;
     const int* __restrict__ O = tb.off + (long long)row * P1_TAPS;
-    const double* pb = p + ((long long)(k + HALO) * g.plane + (long long)j * g.pitch + i);
+    const double* pb = p + ((long long)(kl + HALO) * g.plane + (long long)j * g.pitch + i);
     // a non-zero coefficient implies that the neighbour exists (same cell pattern as the representative);
     // padding entries have coefficient 0 and offset 0
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -81,12 +109,12 @@ __global__ void __launch_bounds__(NT)
 // diag(R^T R) w^2 + ridge^2 (for the column scaling, LI/_discrete_interpolator.py:815-833)
 __global__ void k_p1_diag(const GridDesc g, const P1Tables tb, const double w2, const double ridge2,
                           double* __restrict__ diag) {
-  const long long n = (long long)g.nx * g.ny * g.nz;
+  const long long n = (long long)g.nx * g.ny * g.nzl;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(t % g.nx);
     const long long r = t / g.nx;
-    const int j = (int)(r % g.ny), k = (int)(r / g.ny);
-    diag[(long long)(k + HALO) * g.plane + (long long)j * g.pitch + i] += fma(w2, tb.diag[p1_row(g, tb, i, j, k)], ridge2);
+    const int j = (int)(r % g.ny), kl = (int)(r / g.ny);
+    diag[(long long)(kl + HALO) * g.plane + (long long)j * g.pitch + i] += fma(w2, tb.diag[p1_row(g, tb, i, j, g.k0 + kl)], ridge2);
   }
 }
 
@@ -96,7 +124,8 @@ __constant__ int c_tet_odd[5][4] = {{0, 6, 5, 3}, {7, 3, 5, 6}, {4, 0, 5, 6}, {2
 
 struct TetLoc {
   bool inside;
-  int node[4];     // storage indices of the tet's nodes
+  int cz;          // z index of the cell (global)
+  int node[4];     // storage indices of the tet's nodes (relative to the handle's planes)
   double c[4];     // barycentric coordinates (shape functions)
   double v[4][3];  // vertex positions
 };
@@ -170,13 +199,14 @@ __device__ __forceinline__ TetLoc locate_tet(const GridDesc& g, const double x[3
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
         const int off[3] = {corner[s] & 1, (corner[s] >> 1) & 1, (corner[s] >> 2) & 1};
-        L.node[s] = (int)((long long)(cell[2] + off[2] + HALO) * g.plane + (long long)(cell[1] + off[1]) * g.pitch + cell[0] + off[0]);
+        L.node[s] = (int)((long long)(cell[2] + off[2] - g.k0 + HALO) * g.plane + (long long)(cell[1] + off[1]) * g.pitch + cell[0] + off[0]);
 #pragma unroll
         for (int a = 0; a < 3; ++a) L.v[s][a] = v[s][a];
       }
     }
   }
   L.inside = ins_tol && ins_strict && best >= 0;
+  L.cz = cell[2];
   return L;
 }
 
@@ -225,6 +255,8 @@ __global__ void k_p1_point_rows(const GridDesc g, const int kind, const long lon
     bool ok = L.inside;
     const int used = kind == LSB200_ROWS_VALUE ? 4 : (kind == LSB200_ROWS_TANGENT ? 7 : 6);
     for (int c = 0; c < used; ++c) ok = ok && (d[c] == d[c]);
+    // slab: keep the row when its cell touches an owned plane (as k_fdi_point_rows does)
+    ok = ok && (L.cz + 1 >= g.k0) && (L.cz < g.k1);
     const int mult = kind == LSB200_ROWS_NORMAL ? 3 : 1;
     double A[3][4], bb[3] = {0.0, 0.0, 0.0};
     double ww = weight;

@@ -86,10 +86,12 @@ class Engine:
             rc = self._lib.lsb200_create_grid(nat.iptr(self.nsteps), nat.dptr(self.origin), nat.dptr(self.step),
                                               k0, k1, self.device, C.byref(self._h))
         elif kind == "tetmesh":
-            if slab is not None:
-                raise ValueError("tet-mesh handles do not take a slab")
-            rc = self._lib.lsb200_create_tetmesh(nat.iptr(self.nsteps), nat.dptr(self.origin), nat.dptr(self.step),
-                                                 self.device, C.byref(self._h))
+            if slab is None:
+                rc = self._lib.lsb200_create_tetmesh(nat.iptr(self.nsteps), nat.dptr(self.origin), nat.dptr(self.step),
+                                                     self.device, C.byref(self._h))
+            else:
+                rc = self._lib.lsb200_create_tetmesh_slab(nat.iptr(self.nsteps), nat.dptr(self.origin), nat.dptr(self.step),
+                                                          k0, k1, self.device, C.byref(self._h))
         else:
             raise ValueError(f"unknown support kind {kind!r}")
         nat.check(rc)

@@ -61,7 +61,8 @@ using std::max;
 using std::min;
 inline void __syncthreads() { lsb_emu::cta_barrier->arrive_and_wait(); }
 inline void __threadfence() {}
-inline double __ldg(const double* p) { return *p; }
+template <class T>
+inline T __ldg(const T* p) { return *p; }
 inline double __ldcg(const double* p) { return *p; }
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }

@@ -1,0 +1,122 @@
+// TEST INFRASTRUCTURE ONLY: the P1 / TetMesh kernels (loopstructural_b200/csrc/p1.cuh, unmodified) on the CPU through
+// tests/hostsim/cuda_emu.h, for ONE handle -- the full mesh or a z slab [k0,k1) with its halo planes filled as the NCCL
+// exchange would.  tests/test_p1_emu.py compares with the oracle (explicit face-jump rows, point rows).
+//
+//   g++ -O1 -std=c++20 -pthread -mfma -w -DLSB_EMU -I/usr/local/cuda/include -fPIC -fvisibility=hidden -Wl,-Bsymbolic \
+//       -shared -o tests/hostsim/libp1_emu.so tests/hostsim/p1_emu.cpp
+#include "cuda_emu.h"
+
+#include <string.h>
+
+#include <mutex>
+
+#include "../../include/lsb200.h"
+
+// atomics of the row kernels: the emulated threads of a CTA run concurrently
+namespace { std::mutex g_atomic; }
+inline unsigned long long atomicAdd(unsigned long long* a, unsigned long long v) {
+  std::lock_guard<std::mutex> l(g_atomic);
+  const unsigned long long old = *a;
+  *a = old + v;
+  return old;
+}
+inline double atomicAdd(double* a, double v) {
+  std::lock_guard<std::mutex> l(g_atomic);
+  const double old = *a;
+  *a = old + v;
+  return old;
+}
+inline unsigned long long atomicExch(unsigned long long* a, unsigned long long v) {
+  std::lock_guard<std::mutex> l(g_atomic);
+  const unsigned long long old = *a;
+  *a = v;
+  return old;
+}
+inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
+
+#include "../../loopstructural_b200/csrc/p1.cuh"
+
+using namespace lsb;
+
+namespace {
+constexpr int MAX_PARTIALS = 1 << 18;
+GridDesc make_grid(const int* dims, const double* origin, const double* step) {
+  GridDesc g{};
+  g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
+  g.k0 = dims[3]; g.k1 = dims[4]; g.nzl = g.k1 - g.k0;
+  g.pitch = g.nx;
+  g.plane = (long long)g.pitch * g.ny;
+  g.nloc = g.plane * g.nzl;
+  g.nall = g.plane * (g.nzl + 2 * HALO);
+  for (int a = 0; a < 3; ++a) { g.origin[a] = origin[a]; g.step[a] = step[a]; }
+  return g;
+}
+}  // namespace
+
+#define HOSTSIM_API __attribute__((visibility("default")))
+extern "C" {
+
+// q = (w2 R^T R + ridge2 I) p on the owned planes and diag of the same; dims = {nx, ny, nz, k0, k1}
+HOSTSIM_API int emu_p1_normal(const int* dims, const double* step, const long long* m, const double* table, double w2,
+                              double ridge2, const double* p_global, double* q_owned, double* diag_owned, double* pq_out) {
+  const double origin[3] = {0.0, 0.0, 0.0};
+  const GridDesc g = make_grid(dims, origin, step);
+  std::vector<double> coef, dg;
+  std::vector<int> off;
+  size_t bad = 0;
+  if (p1_compact_tables(g, m, table, coef, off, dg, &bad)) return -1;
+  const P1Tables tb{{(int)m[0], (int)m[1], (int)m[2]}, coef.data(), off.data(), dg.data()};
+  const size_t guard = ((size_t)g.plane + 31) & ~(size_t)31;
+  std::vector<double> pst((size_t)g.nall + 2 * guard, 0.0), qst((size_t)g.nall + 2 * guard, nan("")), dst((size_t)g.nall + 2 * guard, 0.0);
+  double* p = pst.data() + guard;
+  double* q = qst.data() + guard;
+  double* d = dst.data() + guard;
+  for (int k = g.k0 - HALO; k < g.k1 + HALO; ++k)
+    if (k >= 0 && k < g.nz)
+      memcpy(p + (size_t)(k - g.k0 + HALO) * g.plane, p_global + (size_t)k * g.plane, sizeof(double) * g.plane);
+  std::vector<double> partials((size_t)MAX_PARTIALS, 0.0);
+  unsigned int counter = 0;
+  CgScalars sc{};
+  constexpr int NT = 256;
+  const long long n = (long long)g.nx * g.ny * g.nzl;
+  const int nb = (int)std::max<long long>(1, std::min<long long>((n + NT - 1) / NT, 5));
+  lsb_emu::launch(dim3(nb), dim3(NT), 0, [&] { k_p1_normal<NT>(g, tb, w2, ridge2, p, q, partials.data(), &counter, &sc, 0); });
+  lsb_emu::launch(dim3(nb), dim3(NT), 0, [&] { k_p1_diag(g, tb, w2, ridge2, d); });
+  for (int k = 0; k < g.nzl; ++k) {
+    memcpy(q_owned + (size_t)k * g.plane, q + (size_t)(k + HALO) * g.plane, sizeof(double) * g.plane);
+    memcpy(diag_owned + (size_t)k * g.plane, d + (size_t)(k + HALO) * g.plane, sizeof(double) * g.plane);
+  }
+  *pq_out = sc.pq_part[0];
+  for (size_t i = 0; i < qst.size(); ++i) {
+    const bool owned = i >= guard + (size_t)HALO * g.plane && i < guard + (size_t)(HALO + g.nzl) * g.plane;
+    if (!owned && (qst[i] == qst[i] || dst[i] != 0.0)) return -2;
+  }
+  return 0;
+}
+
+// k_p1_point_rows on a slab: rows as (n_out, 4) values, GLOBAL node ids (-1 = empty row), b, w^2; returns rows kept
+HOSTSIM_API long long emu_p1_point_rows(const int* dims, const double* origin, const double* step, int kind, long long n,
+                                        const double* data, int ncols, double weight, double* vals, long long* cols, double* b,
+                                        double* w2) {
+  const GridDesc g = make_grid(dims, origin, step);
+  const int mult = kind == LSB200_ROWS_NORMAL ? 3 : 1;
+  const long long nr = n * mult;
+  std::vector<double> v((size_t)nr * 4), bb((size_t)nr), ww((size_t)nr);
+  std::vector<int> cc((size_t)nr * 4);
+  RowBlock rb{};
+  rb.n = nr; rb.k = 4; rb.vals = v.data(); rb.cols = cc.data(); rb.b = bb.data(); rb.w2 = ww.data();
+  unsigned long long status[2] = {0, 0};
+  lsb_emu::launch(dim3(2), dim3(128), 0, [&] { k_p1_point_rows(g, kind, n, data, ncols, weight, rb, 0, status); });
+  for (long long r = 0; r < nr; ++r) {
+    for (int k = 0; k < 4; ++k) {
+      vals[r * 4 + k] = v[(size_t)k * nr + r];
+      const int lc = cc[(size_t)k * nr + r];
+      cols[r * 4 + k] = lc < 0 ? -1 : (long long)lc + (long long)(g.k0 - HALO) * g.plane;  // storage index -> global node id
+    }
+    b[r] = bb[r];
+    w2[r] = ww[r];
+  }
+  return (long long)status[0];
+}
+
+}  // extern "C"

@@ -47,6 +47,47 @@ def main():
             print(f"slab solve {tag}: world={world} iterations={res.iterations} (reference {int(z['iterations'])}) rel_l2={rel:.2e} {'OK' if good else 'FAIL'}")
             ok = ok and good
         e.close()
+    # the P1 / TetMesh twin on the same partition (k_p1_normal / k_p1_diag / k_p1_point_rows on slab handles)
+    from loopstructural_b200 import engine as en
+    from loopstructural_b200.interpolators import P1_DEFAULT_WEIGHTS
+
+    for tag in (["aniso", "unit16_tight"] if not sys.argv[1:] else []):
+        z = np.load(os.path.join(H.GOLDEN, f"p1_solve_{tag}.npz"))
+        grid = H.fo.Grid.from_cells(z["ncells"], z["origin"], z["step"])
+        if int(grid.nsteps[2]) < partition.HALO * world:
+            continue
+        w = dict(P1_DEFAULT_WEIGHTS)
+        kw = H.weights_of(z, "kw_keys", "kw_vals")
+        if "regularisation" in kw:
+            w["cgw"] = kw["regularisation"]
+        w.update({k: v for k, v in kw.items() if k in w})
+        bounds = partition.slab_bounds(int(grid.nsteps[2]), world)
+        e = Engine(grid.nsteps, grid.origin, grid.step, kind="tetmesh", slab=bounds[rank], device=local)
+        ids = [Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0, device=torch.device("cuda", local))
+        e.comm_init(ids[0], rank, world)
+        e.set_p1_regularisation(w["cgw"])
+        e.set_options(apply_scaling=bool(z["scaling"]))
+        if "data_normal" in z:
+            e.add_point_rows(en.ROWS_NORMAL, z["data_normal"], w["npw"])
+        e.add_point_rows(en.ROWS_VALUE, z["data_value"], w["cpw"])
+        if "data_tangent" in z:
+            t = np.array(z["data_tangent"], dtype=float)
+            t[:, 6] = 0.0
+            e.add_point_rows(en.ROWS_TANGENT, t, w["tpw"])
+        rtol = 1e-5 if float(z["rtol"]) < 0 else float(z["rtol"])
+        atol = 0.0 if float(z["tol"]) < 0 else float(z["tol"])
+        c_loc, res = e.solve_cg(rtol=rtol, atol=atol)
+        parts = [None] * world
+        dist.all_gather_object(parts, c_loc)
+        if rank == 0:
+            c = partition.gather_slabs(parts)
+            rng_ = float(z["c"].max() - z["c"].min())
+            rel = np.linalg.norm(c - z["c"]) / np.sqrt(c.size) / rng_
+            good = rel <= 1e-6 and abs(res.iterations - int(z["iterations"])) <= max(1, int(z["iterations"]) // 100) and res.info == 0
+            print(f"P1 slab solve {tag}: world={world} iterations={res.iterations} (reference {int(z['iterations'])}) rel_l2={rel:.2e} {'OK' if good else 'FAIL'}")
+            ok = ok and good
+        e.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()
