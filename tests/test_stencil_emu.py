@@ -101,3 +101,27 @@ def test_single_kernel_operator_on_every_slab_matches_the_oracle(emu, nsteps, wo
         assert info[8] == 0
         assert np.abs(q - ref[sl]).max() <= 1e-12 * max(np.abs(ref).max(), 1.0)
         assert abs(pq - float(p[sl] @ ref[sl])) <= 1e-10 * abs(float(p @ ref))
+
+
+def test_random_small_grids_slabs_and_launch_parameters(emu):
+    """Seeded sweep over edge sizes (16 = the smallest grid that has a box, odd pitches, 6-plane grids), partitions down
+    to 2 planes per rank, all tile configurations, forced z chunks, z-face ranges and shell chunking."""
+    rng = np.random.default_rng(2026)
+    cases = [(nx, ny, nz) for nx in (16, 17, 19, 66, 71, 131) for ny in (16, 18, 19, 33) for nz in (6, 7, 8, 11, 17, 23)]
+    rng.shuffle(cases)
+    runs = 0
+    for nx, ny, nz in cases[:14]:
+        grid = fo.Grid(np.array([nx, ny, nz]), np.zeros(3), np.ones(3))
+        p = rng.standard_normal(grid.n_nodes)
+        w = ANISO if rng.random() < 0.7 else {}
+        ref = fo.regularisation_normal_matvec(grid, w, p) + 0.05 * p
+        world = min(int(rng.integers(1, max(2, nz // 2))), nz // 2)
+        cfg, cz = int(rng.choice([0, 1, 2, 4])), int(rng.choice([0, 3, 4, 7]))
+        zface, scz = int(rng.choice([3, 5, 8])), int(rng.choice([0, 2, 8]))
+        for k0, k1 in (partition.slab_bounds(nz, world) if world > 1 else [(0, nz)]):
+            q, _pq, info = run(emu, (nx, ny, nz), (k0, k1), w, 0.05, p, cfg=cfg, cz=cz, zface=zface, shell_cz=scz)
+            sl = slice(k0 * nx * ny, k1 * nx * ny)
+            assert not np.isnan(q).any(), ((nx, ny, nz), (k0, k1), info)
+            assert np.abs(q - ref[sl]).max() <= 1e-12 * max(np.abs(ref).max(), 1.0), ((nx, ny, nz), (k0, k1), cfg, cz, zface, info)
+            runs += 1
+    assert runs >= 20
