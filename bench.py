@@ -258,6 +258,11 @@ def measure_fault(local, n_nodes=128, npts=10_000_000, steps=10, cpu_points=100_
     t_eval = timed(lambda: frame.evaluate_device(cloud.data_ptr(), vals.data_ptr(), out.data_ptr(), npts, 1, st))
     frame.apply_to_points_device(cloud.data_ptr(), out.data_ptr(), npts, prof, 0.05, steps, st)
     torch.cuda.synchronize()
+    # regular-grid export (section 8 f rank 4): 512^3 lattice values of field 0 straight into a device buffer
+    nl = 512
+    lat = torch.empty(nl ** 3, dtype=torch.float64, device=dev)
+    t_lat = timed(lambda: engines[0].evaluate_lattice(np.zeros(3), np.ones(3), (nl, nl, nl), "F", out_ptr=lat.data_ptr(), stream=st), reps=3)
+    del lat
     sample = cloud[:cpu_points].cpu().numpy()
     moved = out[:cpu_points].cpu().numpy()
     fields = [fa.FrameField(grid, c, None) for c in cs]
@@ -271,6 +276,7 @@ def measure_fault(local, n_nodes=128, npts=10_000_000, steps=10, cpu_points=100_
     return {"workload": f"3 x {n_nodes}^3 fields, {npts} device-resident points, {steps} steps, cubic/ones/smooth_peak profile",
             "displace_points_per_second": npts / t_move, "displace_seconds": t_move,
             "frame_eval_points_per_second": npts / t_eval,
+            "lattice_points_per_second": nl ** 3 / t_lat, "lattice_gbs_written": 8 * nl ** 3 / t_lat / 1e9,
             "moved_fraction": float((np.abs(moved - sample).max(axis=1) > 0).mean()),
             "max_abs_diff_vs_oracle_sample": float(np.abs(moved - ref).max()),
             "cpu_port_points_per_second": cpu_points / t_cpu, "cpu_sample_points": cpu_points}
