@@ -406,6 +406,34 @@ def run_ours(args):
         except Exception as exc:  # noqa: BLE001
             eval_info = {"error": f"{type(exc).__name__}: {exc}"}
 
+    # ---- evaluation after a z-slab solve (BASELINE configs[4]): replicate c on every GPU (device-side
+    # all-gather), each rank evaluates its share of the cloud.  Opt-in (--multi-gpu-eval): written after the round's GPU
+    # budget was spent, so it stays out of the default multi-rank run until it has been seen on a multi-GPU box.
+    if world > 1 and args.multi_gpu_eval:
+        npts = args.eval_points
+        a, b = partition.split_points(npts, world)[rank]
+        full = partition.replicate_solution(eng, bounds, local)
+        gen = torch.Generator(device="cuda").manual_seed(rank)
+        cloud = torch.rand((b - a, 3), dtype=torch.float64, device="cuda", generator=gen)
+        cloud[:, 2] *= zscale
+        out1 = torch.empty(b - a, dtype=torch.float64, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        for _ in range(2):
+            full.evaluate_value_device(cloud.data_ptr(), out1.data_ptr(), b - a, st)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            full.evaluate_value_device(cloud.data_ptr(), out1.data_ptr(), b - a, st)
+        e1.record()
+        torch.cuda.synchronize()
+        te = torch.tensor([e0.elapsed_time(e1) * 1e-3 / 3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        eval_info = {"points": npts, "layout": f"uniform random cloud split over {world} ranks, c replicated by all-gather",
+                     "value_points_per_second": npts / float(te.item()),
+                     "finite_fraction_rank0": float(torch.isfinite(out1).double().mean().item())}
+        full.close()
+
     # ---- roofline of the dominant operator kernel + whole iteration, CUDA events on the engine's stream
     t_matvec = eng.time_kernel(0, reps=20)
     t_iter = eng.time_kernel(1, reps=20)
@@ -486,6 +514,8 @@ def main():
     ap.add_argument("--n-gradient", type=int, default=10_000)
     ap.add_argument("--ref-n", type=int, default=64, help="nodes per axis of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multi-gpu-eval", action="store_true", help="N > 1: replicate c and evaluate a cloud split over the ranks")
+    ap.add_argument("--eval-points", type=int, default=100_000_000)
     ap.add_argument("--no-fault", action="store_true", help="skip the fault-frame evaluation measurement")
     args = ap.parse_args()
     if args.impl == "reference":

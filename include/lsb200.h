@@ -193,6 +193,13 @@ int lsb200_get_scaling(lsb200_handle h, double* out); /* S = diag^-1/2 (ones whe
 int lsb200_get_c(lsb200_handle h, double* out);
 int lsb200_set_c(lsb200_handle h, const double* c);
 
+/* the same with a device buffer on the handle's GPU holding the owned planes contiguously (nx*ny*nzl doubles);
+ * get is asynchronous on `stream`, set returns when the copy has completed.  For replicating the solution of a
+ * z-slab solve on every GPU (all-gather of the slabs, then lsb200_set_c_dev on a handle that owns every plane)
+ * before evaluation. */
+int lsb200_get_c_dev(lsb200_handle h, double* c_dev, void* stream);
+int lsb200_set_c_dev(lsb200_handle h, const double* c_dev, void* stream);
+
 /* ---- evaluation -------------------------------------------------------- */
 
 /* StructuredGrid.evaluate_value (LC/supports/_3d_structured_grid.py:295-322) +

@@ -86,6 +86,8 @@ SIGNATURES = {
     "lsb200_get_scaling": (C.c_int, [Handle, c_double_p]),
     "lsb200_get_c": (C.c_int, [Handle, c_double_p]),
     "lsb200_set_c": (C.c_int, [Handle, c_double_p]),
+    "lsb200_get_c_dev": (C.c_int, [Handle, C.c_void_p, C.c_void_p]),
+    "lsb200_set_c_dev": (C.c_int, [Handle, C.c_void_p, C.c_void_p]),
     "lsb200_eval_value": (C.c_int, [Handle, C.c_int64, c_double_p, c_double_p]),
     "lsb200_eval_gradient": (C.c_int, [Handle, C.c_int64, c_double_p, c_double_p]),
     "lsb200_eval_value_dev": (C.c_int, [Handle, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

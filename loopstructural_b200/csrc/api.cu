@@ -1126,6 +1126,30 @@ int lsb200_set_c(lsb200_handle h, const double* c) {
   return 0;
 }
 
+// device <-> device variants: `c_dev` holds the owned planes contiguously (nx * ny * nzl doubles) on the handle's GPU.
+// Asynchronous on `stream`, ordered after the handle's own work (the solve / set_c that produced x has completed: both
+// synchronise before they return).  Used to replicate a z-slab solution on every GPU before evaluation.
+int lsb200_get_c_dev(lsb200_handle h, double* c_dev, void* stream) {
+  if (!h || !c_dev) return fail(LSB200_ERR_ARG, "null argument");
+  if (!h->have_c) return fail(LSB200_ERR_STATE, "no solution on the device yet (solve or set_c first)");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy2DAsync(c_dev, sizeof(double) * h->g.nx, owned_ptr(h, h->x), sizeof(double) * h->g.pitch, sizeof(double) * h->g.nx,
+                       (size_t)h->g.ny * h->g.nzl, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+int lsb200_set_c_dev(lsb200_handle h, const double* c_dev, void* stream) {
+  if (!h || !c_dev) return fail(LSB200_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_vectors(h);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));  // ensure_vectors zeroes the vectors on the handle's stream
+  CK(cudaMemcpy2DAsync(owned_ptr(h, h->x), sizeof(double) * h->g.pitch, c_dev, sizeof(double) * h->g.nx, sizeof(double) * h->g.nx,
+                       (size_t)h->g.ny * h->g.nzl, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  h->have_c = true;
+  return 0;
+}
+
 // one CG iteration enqueued on the stream (no host synchronisation)
 static int enqueue_iteration(lsb200_ctx* h) {
   const long long n = h->g.nloc;

@@ -298,6 +298,13 @@ class Engine:
         c = nat.as_f64(c, (self.local_dof,))
         nat.check(self._lib.lsb200_set_c(self._h, nat.dptr(c)))
 
+    def get_c_device(self, out_ptr: int, stream: int = 0):
+        """Owned planes of the solution into a device buffer of local_dof doubles (asynchronous on ``stream``)."""
+        nat.check(self._lib.lsb200_get_c_dev(self._h, C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+    def set_c_device(self, c_ptr: int, stream: int = 0):
+        nat.check(self._lib.lsb200_set_c_dev(self._h, C.c_void_p(c_ptr), C.c_void_p(stream)))
+
     def evaluate_value(self, xyz) -> np.ndarray:
         xyz = nat.as_f64(xyz)
         if xyz.ndim != 2 or xyz.shape[1] != 3:

@@ -46,6 +46,22 @@ def main():
             good = rel <= 1e-6 and abs(res.iterations - int(z["iterations"])) <= 1 and res.info == 0
             print(f"slab solve {tag}: world={world} iterations={res.iterations} (reference {int(z['iterations'])}) rel_l2={rel:.2e} {'OK' if good else 'FAIL'}")
             ok = ok and good
+        # evaluation after a slab solve: replicate c on every GPU, each rank evaluates its share
+        full = partition.replicate_solution(e, bounds, local)
+        q = np.ascontiguousarray(z["query"][np.all(np.isfinite(z["query"]), axis=1)])
+        a, b = partition.split_points(len(q), world)[rank]
+        mine = (full.evaluate_value(q[a:b]), full.evaluate_gradient(q[a:b]))
+        shares = [None] * world
+        dist.all_gather_object(shares, (a, mine))
+        if rank == 0:
+            shares.sort(key=lambda t: t[0])
+            val = np.concatenate([m[0] for _a, m in shares])
+            grad = np.concatenate([m[1] for _a, m in shares])
+            good = (np.allclose(val, H.fo.evaluate_value(grid, q, c), rtol=0, atol=1e-12, equal_nan=True)
+                    and np.allclose(grad, H.fo.evaluate_gradient(grid, q, c), rtol=0, atol=1e-10))
+            print(f"slab evaluate {tag}: world={world} {len(q)} points split over the ranks {'OK' if good else 'FAIL'}")
+            ok = ok and good
+        full.close()
         e.close()
     # the P1 / TetMesh twin on the same partition (k_p1_normal / k_p1_diag / k_p1_point_rows on slab handles)
     from loopstructural_b200 import engine as en

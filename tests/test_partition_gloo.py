@@ -89,3 +89,44 @@ def test_slab_operator_is_partition_independent_gloo(world):
         assert pr.exitcode == 0
     assert err <= 1e-12
     assert abs(pq - pq_ref) <= 1e-10 * abs(pq_ref)
+
+
+def _gather_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nx, ny, nz = 5, 4, 11  # 11 planes over 3 ranks: slabs of 4, 4, 3 planes
+    nxny = nx * ny
+    c = np.random.default_rng(9).standard_normal(nxny * nz)
+    bounds = partition.slab_bounds(nz, world)
+    k0, k1 = bounds[rank]
+    full = partition.allgather_slabs(torch.from_numpy(c[k0 * nxny:k1 * nxny].copy()), bounds, nxny)
+    # every rank evaluates its share of the query points on the replicated field (the oracle stands in for the kernel)
+    grid = fo.Grid(np.array([nx, ny, nz]), np.zeros(3), np.ones(3))
+    pts = np.random.default_rng(3).uniform(-0.5, 10.5, (1001, 3)) * np.array([0.4, 0.3, 1.0])
+    a, b = partition.split_points(len(pts), world)[rank]
+    mine = fo.evaluate_value(grid, pts[a:b], full.numpy())
+    parts = [None] * world
+    dist.all_gather_object(parts, (a, b, mine))
+    if rank == 0:
+        got = np.concatenate([m for _a, _b, m in sorted(parts, key=lambda t: t[0])])
+        ref = fo.evaluate_value(grid, pts, c)
+        out.put((bool(np.array_equal(full.numpy(), c)), bool(np.array_equal(got, ref, equal_nan=True)), [p[:2] for p in parts]))
+    dist.destroy_process_group()
+
+
+def test_allgather_of_unequal_slabs_and_point_split_gloo():
+    """Replicating the solution of a slab solve on every rank (padded all-gather of unequal slabs) and splitting the
+    query points: the path partition.replicate_solution drives with CUDA tensors over NCCL."""
+    assert partition.split_points(10, 3) == [(0, 4), (4, 7), (7, 10)] and partition.split_points(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    world = 3
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, 29731, out)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    same_c, same_eval, spans = out.get(timeout=120)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert same_c and same_eval and sorted(spans) == [(0, 334), (334, 668), (668, 1001)]
