@@ -174,6 +174,211 @@ __device__ __forceinline__ void zgen_plane_fast(const double* __restrict__ Sc, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_fdi_shell: every owned node OUTSIDE the interior box, in gather form with the true boundary operators
+//   q = ridge^2 p + sum_a (a_aa m_b m_c T_a + d_a B_a) p + sum_{a<b} b_ab m_c (C_a (x) C_b) p
+// (no ghost cells): T = D^T diag(m) D / 6, C = G^T diag(m) G, B = sum_{r in {1,n-2}} d_r d_r^T / 6,
+// m(r) = [1 <= r <= n-2] -- the row masks of StructuredGrid.neighbour_global_indexes / FDI.assemble_borders
+// (LC/supports/_3d_structured_grid.py:164-293, LI/_finite_difference_interpolator.py:1052-1144) after row
+// normalisation (LI/_discrete_interpolator.py:361-366).
+//
+// A thread owns one xy column and marches along z: its x and y coefficient sets are computed once, the z sets
+// come from a per-plane table (ShellZ), and of the 25 taps of an output plane only the 13 in-plane ones are
+// loaded -- the z neighbours are the per-plane scalars (p, C_x p, C_y p) kept in a five-deep register history.
+// ~100 instructions per node instead of the ~450 of the one-thread-per-node form it replaced (profiles/r01m).
+// Work items: the ring columns (outside [ilo,ihi) x [jlo,jhi)) over z chunks of [klo,khi) -- every owned plane
+// in the current launch plan; the kernel can also take every column of the planes outside [klo,khi) ("caps").
+struct ShellBox {
+  int ilo, ihi, jlo, jhi, klo, khi;  // the box that is NOT computed here (klo/khi clipped to the owned planes)
+  int ring_cols;                     // columns outside [ilo,ihi) x [jlo,jhi)
+  int ring_blocks;                   // CTAs per z chunk of the ring: ceil(ring_cols / NT)
+  int ring_cz, ring_chunks;          // z chunking of [klo,khi)
+  int cap_blocks;                    // CTAs per cap: ceil(nx*ny / NT)
+  int capA0, capA1, capB0, capB1;    // owned planes below klo / from khi up (either may be empty)
+};
+
+// per-plane z coefficients, 16 doubles per GLOBAL plane k: [0..4] T_z taps -2..2 (1/6 included), [5..9] B_z taps
+// (1/6 included), [10..12] C_z taps -2,0,+2, [13] m_z(k)
+
+__device__ __forceinline__ double vrow(int r, int n) { return (r >= 1 && r <= n - 2) ? 1.0 : 0.0; }
+// coefficient of p(i+s) in B = sum_{r in {1,n-2}} d_r d_r^T / 6 (both rows are counted when n = 3, as the
+// reference's lower and upper border families both exist then)
+__host__ __device__ inline double bline(int i, int n, int s) {
+  if (n < 3) return 0.0;
+  double c = 0.0;
+  const int t = i + s;
+  if (i <= 2 && t >= 0 && t <= 2) c += (i == 1 ? -2.0 : 1.0) * (t == 1 ? -2.0 : 1.0);
+  if (i >= n - 3 && t >= n - 3 && t <= n - 1) c += (i == n - 2 ? -2.0 : 1.0) * (t == n - 2 ? -2.0 : 1.0);
+  return c * (1.0 / 6.0);
+}
+// coefficient of p(i+s) in (T p)(i), T = D^T diag(m) D / 6
+__host__ __device__ inline double tline(int i, int n, int s) {
+  auto v = [n](int r) { return (r >= 1 && r <= n - 2) ? 1.0 : 0.0; };
+  const double a = v(i - 1), b = v(i), c = v(i + 1);
+  switch (s) {
+    case -2: return a * (1.0 / 6.0);
+    case -1: return (a + b) * (-2.0 / 6.0);
+    case 0: return (a + 4.0 * b + c) * (1.0 / 6.0);
+    case 1: return (b + c) * (-2.0 / 6.0);
+    default: return c * (1.0 / 6.0);
+  }
+}
+// host: fill the per-plane table (nz * SHELL_ZSTRIDE doubles)
+inline void shell_fill_z_table(int nz, double* tab) {
+  for (int k = 0; k < nz; ++k) {
+    double* t = tab + (size_t)k * SHELL_ZSTRIDE;
+    auto v = [nz](int r) { return (r >= 1 && r <= nz - 2) ? 1.0 : 0.0; };
+    for (int s = -2; s <= 2; ++s) {
+      t[s + 2] = tline(k, nz, s);
+      t[5 + s + 2] = bline(k, nz, s);
+    }
+    t[10] = -v(k - 1);
+    t[11] = v(k - 1) + v(k + 1);
+    t[12] = -v(k + 1);
+    t[13] = v(k);
+    t[14] = t[15] = 0.0;
+  }
+}
+
+// column number r of the ring (outside [ilo,ihi) x [jlo,jhi)): first the full rows below / above the box, then the
+// left / right column stubs of the rows in between
+__device__ __forceinline__ void ring_column(const GridDesc& g, const ShellBox& sb, const int r, int* ci, int* cj) {
+  const int ny_out = g.ny - (sb.jhi - sb.jlo);
+  if (r < ny_out * g.nx) {
+    const int jj = r / g.nx;
+    *ci = r - jj * g.nx;
+    *cj = jj < sb.jlo ? jj : sb.jhi + (jj - sb.jlo);
+  } else {
+    const int nx_out = max(g.nx - (sb.ihi - sb.ilo), 1);
+    const int r2 = r - ny_out * g.nx;
+    const int jr = r2 / nx_out, ii = r2 - jr * nx_out;
+    *cj = sb.jlo + jr;
+    *ci = ii < sb.ilo ? ii : sb.ihi + (ii - sb.ilo);
+  }
+}
+
+// One thread, one xy column (ci, cj), output planes [ka, kb): the march described above.  Returns its part of p.q.
+__device__ __forceinline__ double shell_march(const GridDesc& g, const StencilWeights& w, const double* __restrict__ ztab,
+                                              const double* __restrict__ p, double* __restrict__ q, const int ci,
+                                              const int cj, const int ka, const int kb) {
+  double dot = 0.0;
+  // ---- x and y coefficient sets of the column
+  const double vax = vrow(ci - 1, g.nx), vbx = vrow(ci, g.nx), vcx = vrow(ci + 1, g.nx);
+  const double vay = vrow(cj - 1, g.ny), vby = vrow(cj, g.ny), vcy = vrow(cj + 1, g.ny);
+  const double ax6 = w.axx * vby * (1.0 / 6.0), ay6 = w.ayy * vbx * (1.0 / 6.0);
+  // T lines (to be multiplied by m_z of the plane) and border lines (unmasked); tap order -2,-1,0,+1,+2
+  const double tx0 = ax6 * vax, tx1 = -2.0 * ax6 * (vax + vbx), tx2 = ax6 * (vax + 4.0 * vbx + vcx),
+               tx3 = -2.0 * ax6 * (vbx + vcx), tx4 = ax6 * vcx;
+  const double ty0 = ay6 * vay, ty1 = -2.0 * ay6 * (vay + vby), ty2 = ay6 * (vay + 4.0 * vby + vcy),
+               ty3 = -2.0 * ay6 * (vby + vcy), ty4 = ay6 * vcy;
+  const bool bdx = (ci <= 2 || ci >= g.nx - 3), bdy = (cj <= 2 || cj >= g.ny - 3);
+  double bx[5] = {0, 0, 0, 0, 0}, by[5] = {0, 0, 0, 0, 0};
+  if (bdx)
+#pragma unroll
+    for (int s = 0; s < 5; ++s) bx[s] = w.dx * bline(ci, g.nx, s - 2);
+  if (bdy)
+#pragma unroll
+    for (int s = 0; s < 5; ++s) by[s] = w.dy * bline(cj, g.ny, s - 2);
+  const double cx0 = -vax, cx1 = vax + vcx, cx2 = -vcx;  // C_x taps -2, 0, +2
+  const double cy0 = -vay, cy1 = vay + vcy, cy2 = -vcy;
+  const double azm = w.azz * vbx * vby, bxzm = w.bxz * vby, byzm = w.byz * vbx;
+  // ---- march: history of (S, c, gx, gy) for planes kp-4 .. kp
+  double hS[5], hc[5], hgx[5], hgy[5];
+#pragma unroll
+  for (int t = 0; t < 5; ++t) hS[t] = hc[t] = hgx[t] = hgy[t] = 0.0;
+  const double* pc = p + ((long long)(ka - 2 - g.k0 + HALO) * g.plane + cj * g.pitch + ci);
+  double* qc = q + ((long long)(ka - g.k0 + HALO) * g.plane + cj * g.pitch + ci);
+  const int P = g.pitch;
+  // clamped in-plane offsets are not needed: a tap outside the grid has coefficient 0 and the address stays
+  // inside the vector's allocation (two halo planes on either side), whose contents are finite
+  for (int kp = ka - 2; kp < kb + 2; ++kp) {
+    double S = 0.0, c = 0.0, gx = 0.0, gy = 0.0;
+    if (kp >= 0 && kp < g.nz) {
+      c = pc[0];
+      const double xm2 = pc[-2], xm1 = pc[-1], xp1 = pc[1], xp2 = pc[2];
+      const double ym2 = pc[-2 * P], ym1 = pc[-P], yp1 = pc[P], yp2 = pc[2 * P];
+      gx = fma(cx2, xp2, fma(cx0, xm2, cx1 * c));
+      gy = fma(cy2, yp2, fma(cy0, ym2, cy1 * c));
+      if (kp >= ka && kp < kb) {  // in-plane part of an output plane
+        const double cmm = pc[-2 * P - 2], cpm = pc[-2 * P + 2], cmp = pc[2 * P - 2], cpp = pc[2 * P + 2];
+        const double mz = ztab[(long long)kp * SHELL_ZSTRIDE + 13];
+        double s1 = tx2 * c;
+        s1 = fma(tx0, xm2, s1); s1 = fma(tx1, xm1, s1); s1 = fma(tx3, xp1, s1); s1 = fma(tx4, xp2, s1);
+        s1 = fma(ty2, c, s1);
+        s1 = fma(ty0, ym2, s1); s1 = fma(ty1, ym1, s1); s1 = fma(ty3, yp1, s1); s1 = fma(ty4, yp2, s1);
+        // (C_x (x) C_y) p: C_y over the rows j-2, j, j+2 of (C_x p)
+        const double rm = fma(cx2, cpm, fma(cx0, cmm, cx1 * ym2));
+        const double rp = fma(cx2, cpp, fma(cx0, cmp, cx1 * yp2));
+        s1 = fma(w.bxy, fma(cy2, rp, fma(cy0, rm, cy1 * gx)), s1);
+        S = fma(mz, s1, w.ridge2 * c);
+        if (bdx) S += bx[0] * xm2 + bx[1] * xm1 + bx[2] * c + bx[3] * xp1 + bx[4] * xp2;
+        if (bdy) S += by[0] * ym2 + by[1] * ym1 + by[2] * c + by[3] * yp1 + by[4] * yp2;
+      }
+    }
+    // shift the history (registers) and append plane kp
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { hS[t] = hS[t + 1]; hc[t] = hc[t + 1]; hgx[t] = hgx[t + 1]; hgy[t] = hgy[t + 1]; }
+    hS[4] = S; hc[4] = c; hgx[4] = gx; hgy[4] = gy;
+    const int ko = kp - 2;  // output plane completed by plane kp: history index 2 is plane ko
+    if (ko >= ka) {
+      const double* z = ztab + (long long)ko * SHELL_ZSTRIDE;
+      double acc = hS[2];
+      // z line: a_zz m_x m_y T_z + d_z B_z
+      double lz = 0.0;
+#pragma unroll
+      for (int t = 0; t < 5; ++t) lz = fma(fma(azm, z[t], w.dz * z[5 + t]), hc[t], lz);
+      acc += lz;
+      // (C_x (x) C_z) p m_y and (C_y (x) C_z) p m_x
+      acc = fma(bxzm, fma(z[12], hgx[4], fma(z[10], hgx[0], z[11] * hgx[2])), acc);
+      acc = fma(byzm, fma(z[12], hgy[4], fma(z[10], hgy[0], z[11] * hgy[2])), acc);
+      qc[0] = acc;
+      dot = fma(hc[2], acc, dot);
+      qc += g.plane;
+    }
+    pc += g.plane;
+  }
+  return dot;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 4)
+    k_fdi_shell(const GridDesc g, const StencilWeights w, const ShellBox sb, const double* __restrict__ ztab,
+                const double* __restrict__ p, double* __restrict__ q, double* __restrict__ partials,
+                unsigned int* __restrict__ counter, CgScalars* __restrict__ sc, const int cg_mode) {
+  __shared__ double red[NT / 32];
+  if (cg_mode && sc->done) return;
+  // ---- which column and which output planes
+  int ci = 0, cj = 0, ka, kb;
+  bool active;
+  {
+    const int b = blockIdx.x;
+    const int nring = sb.ring_blocks * sb.ring_chunks;
+    if (b < nring) {
+      const int ch = b / sb.ring_blocks;
+      const int r = (b - ch * sb.ring_blocks) * NT + threadIdx.x;
+      active = r < sb.ring_cols;
+      ka = sb.klo + ch * sb.ring_cz;
+      kb = min(ka + sb.ring_cz, sb.khi);
+      if (active) ring_column(g, sb, r, &ci, &cj);
+    } else {
+      const int b2 = b - nring;
+      const int cap = b2 / sb.cap_blocks;
+      const int r = (b2 - cap * sb.cap_blocks) * NT + threadIdx.x;
+      cj = r / g.nx;
+      ci = r - cj * g.nx;
+      active = cj < g.ny;
+      ka = cap == 0 ? sb.capA0 : sb.capB0;
+      kb = cap == 0 ? sb.capA1 : sb.capB1;
+    }
+    active = active && kb > ka;
+  }
+  double dot = 0.0;
+  if (active) dot = shell_march(g, w, ztab, p, q, ci, cj, ka, kb);
+  const double bsum = block_sum<NT>(dot, red);
+  double total;
+  if (grid_sum_last_block<NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total)) sc->pq_part[2] = total;
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_fdi_box: the interior box 4 <= i <= nx-5, 3 <= j <= ny-4, 3 <= k <= nz-4 only.  Every input plane is a
 // real plane, every coefficient a launch constant: no ghost mapping, no masks, no general path.  Everything
 // outside the box is k_fdi_shell's.  Output planes [zlo, zhi) of this handle, z-chunks of cz planes.
@@ -356,200 +561,6 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
   if (grid_sum_last_block<C::NT>(bsum, partials, counter, nblocks, bid, red, &total)) sc->pq_part[ZGEN ? 3 : 0] = total;
 }
 
-}  // namespace lsb
 
-namespace lsb {
-
-// ---------------------------------------------------------------------------------------------
-// k_fdi_shell: every owned node OUTSIDE the interior box, in gather form with the true boundary operators
-//   q = ridge^2 p + sum_a (a_aa m_b m_c T_a + d_a B_a) p + sum_{a<b} b_ab m_c (C_a (x) C_b) p
-// (no ghost cells): T = D^T diag(m) D / 6, C = G^T diag(m) G, B = sum_{r in {1,n-2}} d_r d_r^T / 6,
-// m(r) = [1 <= r <= n-2] -- the row masks of StructuredGrid.neighbour_global_indexes / FDI.assemble_borders
-// (LC/supports/_3d_structured_grid.py:164-293, LI/_finite_difference_interpolator.py:1052-1144) after row
-// normalisation (LI/_discrete_interpolator.py:361-366).
-//
-// A thread owns one xy column and marches along z: its x and y coefficient sets are computed once, the z sets
-// come from a per-plane table (ShellZ), and of the 25 taps of an output plane only the 13 in-plane ones are
-// loaded -- the z neighbours are the per-plane scalars (p, C_x p, C_y p) kept in a five-deep register history.
-// ~100 instructions per node instead of the ~450 of the one-thread-per-node form it replaced (profiles/r01m).
-// Work items: the ring columns (outside [ilo,ihi) x [jlo,jhi)) over z chunks of [klo,khi) -- every owned plane
-// in the current launch plan; the kernel can also take every column of the planes outside [klo,khi) ("caps").
-struct ShellBox {
-  int ilo, ihi, jlo, jhi, klo, khi;  // the box that is NOT computed here (klo/khi clipped to the owned planes)
-  int ring_cols;                     // columns outside [ilo,ihi) x [jlo,jhi)
-  int ring_blocks;                   // CTAs per z chunk of the ring: ceil(ring_cols / NT)
-  int ring_cz, ring_chunks;          // z chunking of [klo,khi)
-  int cap_blocks;                    // CTAs per cap: ceil(nx*ny / NT)
-  int capA0, capA1, capB0, capB1;    // owned planes below klo / from khi up (either may be empty)
-};
-
-// per-plane z coefficients, 16 doubles per GLOBAL plane k: [0..4] T_z taps -2..2 (1/6 included), [5..9] B_z taps
-// (1/6 included), [10..12] C_z taps -2,0,+2, [13] m_z(k)
-
-__device__ __forceinline__ double vrow(int r, int n) { return (r >= 1 && r <= n - 2) ? 1.0 : 0.0; }
-// coefficient of p(i+s) in B = sum_{r in {1,n-2}} d_r d_r^T / 6 (both rows are counted when n = 3, as the
-// reference's lower and upper border families both exist then)
-__host__ __device__ inline double bline(int i, int n, int s) {
-  if (n < 3) return 0.0;
-  double c = 0.0;
-  const int t = i + s;
-  if (i <= 2 && t >= 0 && t <= 2) c += (i == 1 ? -2.0 : 1.0) * (t == 1 ? -2.0 : 1.0);
-  if (i >= n - 3 && t >= n - 3 && t <= n - 1) c += (i == n - 2 ? -2.0 : 1.0) * (t == n - 2 ? -2.0 : 1.0);
-  return c * (1.0 / 6.0);
-}
-// coefficient of p(i+s) in (T p)(i), T = D^T diag(m) D / 6
-__host__ __device__ inline double tline(int i, int n, int s) {
-  auto v = [n](int r) { return (r >= 1 && r <= n - 2) ? 1.0 : 0.0; };
-  const double a = v(i - 1), b = v(i), c = v(i + 1);
-  switch (s) {
-    case -2: return a * (1.0 / 6.0);
-    case -1: return (a + b) * (-2.0 / 6.0);
-    case 0: return (a + 4.0 * b + c) * (1.0 / 6.0);
-    case 1: return (b + c) * (-2.0 / 6.0);
-    default: return c * (1.0 / 6.0);
-  }
-}
-// host: fill the per-plane table (nz * SHELL_ZSTRIDE doubles)
-inline void shell_fill_z_table(int nz, double* tab) {
-  for (int k = 0; k < nz; ++k) {
-    double* t = tab + (size_t)k * SHELL_ZSTRIDE;
-    auto v = [nz](int r) { return (r >= 1 && r <= nz - 2) ? 1.0 : 0.0; };
-    for (int s = -2; s <= 2; ++s) {
-      t[s + 2] = tline(k, nz, s);
-      t[5 + s + 2] = bline(k, nz, s);
-    }
-    t[10] = -v(k - 1);
-    t[11] = v(k - 1) + v(k + 1);
-    t[12] = -v(k + 1);
-    t[13] = v(k);
-    t[14] = t[15] = 0.0;
-  }
-}
-
-template <int NT>
-__global__ void __launch_bounds__(NT, 4)
-    k_fdi_shell(const GridDesc g, const StencilWeights w, const ShellBox sb, const double* __restrict__ ztab,
-                const double* __restrict__ p, double* __restrict__ q, double* __restrict__ partials,
-                unsigned int* __restrict__ counter, CgScalars* __restrict__ sc, const int cg_mode) {
-  __shared__ double red[NT / 32];
-  if (cg_mode && sc->done) return;
-  // ---- which column and which output planes
-  int ci, cj, ka, kb;
-  bool active;
-  {
-    const int b = blockIdx.x;
-    const int nring = sb.ring_blocks * sb.ring_chunks;
-    if (b < nring) {
-      const int ch = b / sb.ring_blocks;
-      const int r = (b - ch * sb.ring_blocks) * NT + threadIdx.x;
-      active = r < sb.ring_cols;
-      ka = sb.klo + ch * sb.ring_cz;
-      kb = min(ka + sb.ring_cz, sb.khi);
-      const int ny_out = g.ny - (sb.jhi - sb.jlo);
-      if (r < ny_out * g.nx) {
-        const int jj = r / g.nx;
-        ci = r - jj * g.nx;
-        cj = jj < sb.jlo ? jj : sb.jhi + (jj - sb.jlo);
-      } else {
-        const int nx_out = max(g.nx - (sb.ihi - sb.ilo), 1);
-        const int r2 = r - ny_out * g.nx;
-        const int jr = r2 / nx_out, ii = r2 - jr * nx_out;
-        cj = sb.jlo + jr;
-        ci = ii < sb.ilo ? ii : sb.ihi + (ii - sb.ilo);
-      }
-    } else {
-      const int b2 = b - nring;
-      const int cap = b2 / sb.cap_blocks;
-      const int r = (b2 - cap * sb.cap_blocks) * NT + threadIdx.x;
-      cj = r / g.nx;
-      ci = r - cj * g.nx;
-      active = cj < g.ny;
-      ka = cap == 0 ? sb.capA0 : sb.capB0;
-      kb = cap == 0 ? sb.capA1 : sb.capB1;
-    }
-    active = active && kb > ka;
-  }
-  double dot = 0.0;
-  if (active) {
-    // ---- x and y coefficient sets of the column
-    const double vax = vrow(ci - 1, g.nx), vbx = vrow(ci, g.nx), vcx = vrow(ci + 1, g.nx);
-    const double vay = vrow(cj - 1, g.ny), vby = vrow(cj, g.ny), vcy = vrow(cj + 1, g.ny);
-    const double ax6 = w.axx * vby * (1.0 / 6.0), ay6 = w.ayy * vbx * (1.0 / 6.0);
-    // T lines (to be multiplied by m_z of the plane) and border lines (unmasked); tap order -2,-1,0,+1,+2
-    const double tx0 = ax6 * vax, tx1 = -2.0 * ax6 * (vax + vbx), tx2 = ax6 * (vax + 4.0 * vbx + vcx),
-                 tx3 = -2.0 * ax6 * (vbx + vcx), tx4 = ax6 * vcx;
-    const double ty0 = ay6 * vay, ty1 = -2.0 * ay6 * (vay + vby), ty2 = ay6 * (vay + 4.0 * vby + vcy),
-                 ty3 = -2.0 * ay6 * (vby + vcy), ty4 = ay6 * vcy;
-    const bool bdx = (ci <= 2 || ci >= g.nx - 3), bdy = (cj <= 2 || cj >= g.ny - 3);
-    double bx[5] = {0, 0, 0, 0, 0}, by[5] = {0, 0, 0, 0, 0};
-    if (bdx)
-#pragma unroll
-      for (int s = 0; s < 5; ++s) bx[s] = w.dx * bline(ci, g.nx, s - 2);
-    if (bdy)
-#pragma unroll
-      for (int s = 0; s < 5; ++s) by[s] = w.dy * bline(cj, g.ny, s - 2);
-    const double cx0 = -vax, cx1 = vax + vcx, cx2 = -vcx;  // C_x taps -2, 0, +2
-    const double cy0 = -vay, cy1 = vay + vcy, cy2 = -vcy;
-    const double azm = w.azz * vbx * vby, bxzm = w.bxz * vby, byzm = w.byz * vbx;
-    // ---- march: history of (S, c, gx, gy) for planes kp-4 .. kp
-    double hS[5], hc[5], hgx[5], hgy[5];
-#pragma unroll
-    for (int t = 0; t < 5; ++t) hS[t] = hc[t] = hgx[t] = hgy[t] = 0.0;
-    const double* pc = p + ((long long)(ka - 2 - g.k0 + HALO) * g.plane + cj * g.pitch + ci);
-    double* qc = q + ((long long)(ka - g.k0 + HALO) * g.plane + cj * g.pitch + ci);
-    const int P = g.pitch;
-    // clamped in-plane offsets are not needed: a tap outside the grid has coefficient 0 and the address stays
-    // inside the vector's allocation (two halo planes on either side), whose contents are finite
-    for (int kp = ka - 2; kp < kb + 2; ++kp) {
-      double S = 0.0, c = 0.0, gx = 0.0, gy = 0.0;
-      if (kp >= 0 && kp < g.nz) {
-        c = pc[0];
-        const double xm2 = pc[-2], xm1 = pc[-1], xp1 = pc[1], xp2 = pc[2];
-        const double ym2 = pc[-2 * P], ym1 = pc[-P], yp1 = pc[P], yp2 = pc[2 * P];
-        gx = fma(cx2, xp2, fma(cx0, xm2, cx1 * c));
-        gy = fma(cy2, yp2, fma(cy0, ym2, cy1 * c));
-        if (kp >= ka && kp < kb) {  // in-plane part of an output plane
-          const double cmm = pc[-2 * P - 2], cpm = pc[-2 * P + 2], cmp = pc[2 * P - 2], cpp = pc[2 * P + 2];
-          const double mz = ztab[(long long)kp * SHELL_ZSTRIDE + 13];
-          double s1 = tx2 * c;
-          s1 = fma(tx0, xm2, s1); s1 = fma(tx1, xm1, s1); s1 = fma(tx3, xp1, s1); s1 = fma(tx4, xp2, s1);
-          s1 = fma(ty2, c, s1);
-          s1 = fma(ty0, ym2, s1); s1 = fma(ty1, ym1, s1); s1 = fma(ty3, yp1, s1); s1 = fma(ty4, yp2, s1);
-          // (C_x (x) C_y) p: C_y over the rows j-2, j, j+2 of (C_x p)
-          const double rm = fma(cx2, cpm, fma(cx0, cmm, cx1 * ym2));
-          const double rp = fma(cx2, cpp, fma(cx0, cmp, cx1 * yp2));
-          s1 = fma(w.bxy, fma(cy2, rp, fma(cy0, rm, cy1 * gx)), s1);
-          S = fma(mz, s1, w.ridge2 * c);
-          if (bdx) S += bx[0] * xm2 + bx[1] * xm1 + bx[2] * c + bx[3] * xp1 + bx[4] * xp2;
-          if (bdy) S += by[0] * ym2 + by[1] * ym1 + by[2] * c + by[3] * yp1 + by[4] * yp2;
-        }
-      }
-      // shift the history (registers) and append plane kp
-#pragma unroll
-      for (int t = 0; t < 4; ++t) { hS[t] = hS[t + 1]; hc[t] = hc[t + 1]; hgx[t] = hgx[t + 1]; hgy[t] = hgy[t + 1]; }
-      hS[4] = S; hc[4] = c; hgx[4] = gx; hgy[4] = gy;
-      const int ko = kp - 2;  // output plane completed by plane kp: history index 2 is plane ko
-      if (ko >= ka) {
-        const double* z = ztab + (long long)ko * SHELL_ZSTRIDE;
-        double acc = hS[2];
-        // z line: a_zz m_x m_y T_z + d_z B_z
-        double lz = 0.0;
-#pragma unroll
-        for (int t = 0; t < 5; ++t) lz = fma(fma(azm, z[t], w.dz * z[5 + t]), hc[t], lz);
-        acc += lz;
-        // (C_x (x) C_z) p m_y and (C_y (x) C_z) p m_x
-        acc = fma(bxzm, fma(z[12], hgx[4], fma(z[10], hgx[0], z[11] * hgx[2])), acc);
-        acc = fma(byzm, fma(z[12], hgy[4], fma(z[10], hgy[0], z[11] * hgy[2])), acc);
-        qc[0] = acc;
-        dot = fma(hc[2], acc, dot);
-        qc += g.plane;
-      }
-      pc += g.plane;
-    }
-  }
-  const double bsum = block_sum<NT>(dot, red);
-  double total;
-  if (grid_sum_last_block<NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total)) sc->pq_part[2] = total;
-}
 
 }  // namespace lsb
