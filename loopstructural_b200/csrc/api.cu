@@ -260,6 +260,10 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
     // latency-bound shell first so that the box fills in around it -- an experiment for the next GPU session, off by
     // default because it has not been measured.
     static const bool shell_first = getenv("LSB200_SHELL_FIRST") && atoi(getenv("LSB200_SHELL_FIRST")) == 1;
+    // LSB200_RING=1: the ring columns are computed by the box CTAs themselves (k_fdi_box<..., RING>), no shell launch
+    static const bool ring = getenv("LSB200_RING") && atoi(getenv("LSB200_RING")) == 1;
+    ShellBox sb;
+    const long long shell_ctas = make_shell_box(g, h->shell_cz, 128, &sb);
     auto launch_box = [&]() -> int {
     {
         const UniConsts U = make_uni_consts(w);
@@ -278,27 +282,26 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
         unsigned int* zcnt = h->counters + 4;
         const dim3 ugrid(h->main_grid.x, h->main_grid.y, nuni), zgrid(h->main_grid.x, h->main_grid.y, (zb1 > zb0) ? 2 : 1);
         switch (h->main_cfg) {
+#define LSB_BOX_LAUNCH(YB, TYT, ST, MINB, V16, RING)                                                                 \
+  {                                                                                                               \
+    auto ku = k_fdi_box<YB, TYT, ST, MINB, V16, false, RING>;                                                     \
+    auto kz = k_fdi_box<YB, TYT, ST, MINB, V16, true, RING>;                                                      \
+    cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                             \
+    cudaFuncSetAttribute(kz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                             \
+    if (ugrid.z > 0) ku<<<ugrid, dim3(32, TYT), smem, h->stream>>>(g, U, p, q, cz, ulo, uhi, 0, 0, h->ztab, part, cnt, h->sc, cg_mode, w, sb); \
+    if (have_z) kz<<<zgrid, dim3(32, TYT), smem, zs>>>(g, U, p, q, cz, za0, za1, zb0, zb1, h->ztab, zpart, zcnt, h->sc, cg_mode, w, sb);      \
+  }
 #define X(ID, YB, TYT, ST, MINB)                                                                                  \
   case ID: {                                                                                                      \
-      const size_t smem = sizeof(double) * MainCfg<YB, TYT, ST>::PLANE * ST;                                        \
-      if (vec16) {                                                                                                  \
-        auto ku = k_fdi_box<YB, TYT, ST, MINB, true, false>;                                                        \
-        auto kz = k_fdi_box<YB, TYT, ST, MINB, true, true>;                                                         \
-        cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
-        cudaFuncSetAttribute(kz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
-        if (ugrid.z > 0) ku<<<ugrid, dim3(32, TYT), smem, h->stream>>>(g, U, p, q, cz, ulo, uhi, 0, 0, h->ztab, part, cnt, h->sc, cg_mode); \
-        if (have_z) kz<<<zgrid, dim3(32, TYT), smem, zs>>>(g, U, p, q, cz, za0, za1, zb0, zb1, h->ztab, zpart, zcnt, h->sc, cg_mode);      \
-      } else {                                                                                                      \
-        auto ku = k_fdi_box<YB, TYT, ST, MINB, false, false>;                                                       \
-        auto kz = k_fdi_box<YB, TYT, ST, MINB, false, true>;                                                        \
-        cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
-        cudaFuncSetAttribute(kz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
-        if (ugrid.z > 0) ku<<<ugrid, dim3(32, TYT), smem, h->stream>>>(g, U, p, q, cz, ulo, uhi, 0, 0, h->ztab, part, cnt, h->sc, cg_mode); \
-        if (have_z) kz<<<zgrid, dim3(32, TYT), smem, zs>>>(g, U, p, q, cz, za0, za1, zb0, zb1, h->ztab, zpart, zcnt, h->sc, cg_mode);      \
-      }                                                                                                             \
+    const size_t smem = sizeof(double) * MainCfg<YB, TYT, ST>::PLANE * ST;                                        \
+    if (vec16 && ring) LSB_BOX_LAUNCH(YB, TYT, ST, MINB, true, true)                                              \
+    else if (vec16) LSB_BOX_LAUNCH(YB, TYT, ST, MINB, true, false)                                                \
+    else if (ring) LSB_BOX_LAUNCH(YB, TYT, ST, MINB, false, true)                                                 \
+    else LSB_BOX_LAUNCH(YB, TYT, ST, MINB, false, false)                                                          \
   } break;
           LSB_BOX_CFGS(X)
 #undef X
+#undef LSB_BOX_LAUNCH
         }
         CKL();
         h->launches += (ugrid.z > 0 ? 1 : 0) + (have_z ? 1 : 0);
@@ -315,10 +318,11 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
     // everything outside the box: one gather launch on a side stream, overlapped with the box kernel
       // (LSB200_SHELL=0 leaves it out: profiling of the box kernel alone, results are then incomplete)
       static const bool with_shell = !(getenv("LSB200_SHELL") && atoi(getenv("LSB200_SHELL")) == 0);
-      if (with_shell) {
+      if (ring) {
+        CK(cudaMemsetAsync(&h->sc->pq_part[2], 0, sizeof(double), h->stream));
+      } else if (with_shell) {
         constexpr int SNT = 128;
-        ShellBox sb;
-        const long long nb = make_shell_box(g, h->shell_cz, SNT, &sb);
+        const long long nb = shell_ctas;
         if (nb > MAX_PARTIALS) return fail(LSB200_ERR_ARG, "shell launch needs %lld CTAs (limit %d)", nb, MAX_PARTIALS);
         if (nb > 0)
           k_fdi_shell<SNT><<<(int)nb, SNT, 0, ov ? h->side[0] : h->stream>>>(g, w, sb, h->ztab, p, q,

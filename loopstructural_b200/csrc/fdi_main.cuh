@@ -388,12 +388,19 @@ __global__ void __launch_bounds__(NT, 4)
 // ZGEN = true: the launch for the (at most two) chunks that touch a z face: blockIdx.z = 0 -> output planes [zlo,zhi),
 // 1 -> [zlo2,zhi2); z coefficients per plane from ztab, planes outside the grid are skipped.  Its p.q goes to
 // pq_part[3], its partial sums to its own slot.
-template <int YB, int TYT, int ST, int MINB, bool VEC16, bool ZGEN>
+// RING = true (LSB200_RING=1): no k_fdi_shell launch.  After its box work every CTA also computes an equal share of
+// the ring columns over its own planes [ka,kb) with shell_march -- the columns of a z chunk are dealt out over the
+// tiles of that chunk, each column's planes split into sub-ranges so that all threads of the CTA march at once.
+// The march gathers from global memory (L2: the planes were just streamed by this chunk's CTAs), needs no shared
+// memory and fewer registers than the box part, and its latency hides behind the other CTAs resident on the SM --
+// which a separate shell kernel cannot do, because the box CTAs leave it no registers to become resident
+// (profiles/r01r).  Its p.q goes into this launch's sum.
+template <int YB, int TYT, int ST, int MINB, bool VEC16, bool ZGEN, bool RING = false>
 __global__ void __launch_bounds__(32 * TYT, MINB)
     k_fdi_box(const GridDesc g, const UniConsts U, const double* __restrict__ p, double* __restrict__ q, const int cz,
               const int zlo, const int zhi, const int zlo2, const int zhi2, const double* __restrict__ ztab,
               double* __restrict__ partials, unsigned int* __restrict__ counter, CgScalars* __restrict__ sc,
-              const int cg_mode) {
+              const int cg_mode, const StencilWeights w, const ShellBox sb) {
   using C = MainCfg<YB, TYT, ST>;
   static_assert(ST >= 5, "ring needs planes kp-2..kp plus at least two in flight");
   LSB_DYN_SMEM(S);
@@ -553,6 +560,28 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
   }
 #undef LSB_BOX_STEP
   cp_async_wait<0>();
+
+  if (RING) {
+    const int ntiles = gridDim.x * gridDim.y;
+    const int tile = blockIdx.x + gridDim.x * blockIdx.y;
+    const int per = (sb.ring_cols + ntiles - 1) / ntiles;
+    const int c0 = tile * per, ncol = min(c0 + per, sb.ring_cols) - c0;
+    const int nplanes = kb - ka;
+    if (ncol > 0 && nplanes > 0) {
+      // sub-ranges of at least RING_MIN_PLANES planes (each re-reads 4 halo planes), enough of them to occupy the CTA
+      constexpr int RING_MIN_PLANES = 6;
+      int nsub = max(1, min(C::NT / ncol, nplanes / RING_MIN_PLANES));
+      const int sub = (nplanes + nsub - 1) / nsub;
+      nsub = (nplanes + sub - 1) / sub;
+      for (int it = tid; it < ncol * nsub; it += C::NT) {
+        const int sidx = it / ncol;
+        int ci, cj;
+        ring_column(g, sb, c0 + (it - sidx * ncol), &ci, &cj);  // consecutive threads take consecutive columns
+        const int za = ka + sidx * sub;
+        dot += shell_march(g, w, ztab, p, q, ci, cj, za, min(za + sub, kb));
+      }
+    }
+  }
 
   const double bsum = block_sum<C::NT>(dot, red);
   const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;

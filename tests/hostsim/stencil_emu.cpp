@@ -34,7 +34,7 @@ extern "C" {
 // lsb200_set_regularisation, i.e. already divided by 4 ... see weights_from); p_global: nx*ny*nz; q_owned: nx*ny*(k1-k0).
 // cfg >= 0: box + shell launches (as LSB200_STENCIL_MAIN), cfg < 0: k_fdi_normal.  info[0..5] = z ranges, info[6] = cz,
 // info[7] = CTAs launched, info[8] = 1 if the box plan was used.  pq_out = p.q over the owned planes as the kernels sum it.
-HOSTSIM_API int emu_fdi_matvec(const int* dims, const double* ew, double ridge2, int cfg, int cz_override, int zface, int shell_cz,
+HOSTSIM_API int emu_fdi_matvec(const int* dims, const double* ew, double ridge2, int cfg, int cz_override, int zface, int shell_cz, int ring,
                    const double* p_global, double* q_owned, double* pq_out, int* info) {
   GridDesc g{};
   g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
@@ -74,17 +74,22 @@ HOSTSIM_API int emu_fdi_matvec(const int* dims, const double* ew, double ridge2,
     double* part = partials.data();
     double* zpart = partials.data() + 4 * (size_t)MAX_PARTIALS;
     const int cz = bt.cz;
+    constexpr int SNT = 128;
+    ShellBox sb;
+    const long long nb = make_shell_box(g, shell_cz, SNT, &sb);
     switch (bt.cfg) {  // the dispatch of launch_stencil, launches through the emulator
+#define EMU_BOX_LAUNCH(YB, TYT, ST, MINB, V16, RING)                                                                  \
+  {                                                                                                                  \
+    if (ugrid.z > 0) lsb_emu::launch(ugrid, dim3(32, TYT), smem, [&] { k_fdi_box<YB, TYT, ST, MINB, V16, false, RING>(g, U, p, q, cz, ulo, uhi, 0, 0, ztab.data(), part, counters + 0, &sc, 0, w, sb); }); \
+    if (have_z) lsb_emu::launch(zgrid, dim3(32, TYT), smem, [&] { k_fdi_box<YB, TYT, ST, MINB, V16, true, RING>(g, U, p, q, cz, za0, za1, zb0, zb1, ztab.data(), zpart, counters + 4, &sc, 0, w, sb); }); \
+  }
 #define X(ID, YB, TYT, ST, MINB)                                                                                     \
   case ID: {                                                                                                         \
     const size_t smem = sizeof(double) * MainCfg<YB, TYT, ST>::PLANE * ST;                                           \
-    if (vec16) {                                                                                                     \
-      if (ugrid.z > 0) lsb_emu::launch(ugrid, dim3(32, TYT), smem, [&] { k_fdi_box<YB, TYT, ST, MINB, true, false>(g, U, p, q, cz, ulo, uhi, 0, 0, ztab.data(), part, counters + 0, &sc, 0); }); \
-      if (have_z) lsb_emu::launch(zgrid, dim3(32, TYT), smem, [&] { k_fdi_box<YB, TYT, ST, MINB, true, true>(g, U, p, q, cz, za0, za1, zb0, zb1, ztab.data(), zpart, counters + 4, &sc, 0); }); \
-    } else {                                                                                                         \
-      if (ugrid.z > 0) lsb_emu::launch(ugrid, dim3(32, TYT), smem, [&] { k_fdi_box<YB, TYT, ST, MINB, false, false>(g, U, p, q, cz, ulo, uhi, 0, 0, ztab.data(), part, counters + 0, &sc, 0); }); \
-      if (have_z) lsb_emu::launch(zgrid, dim3(32, TYT), smem, [&] { k_fdi_box<YB, TYT, ST, MINB, false, true>(g, U, p, q, cz, za0, za1, zb0, zb1, ztab.data(), zpart, counters + 4, &sc, 0); }); \
-    }                                                                                                                \
+    if (vec16 && ring) EMU_BOX_LAUNCH(YB, TYT, ST, MINB, true, true)                                                 \
+    else if (vec16) EMU_BOX_LAUNCH(YB, TYT, ST, MINB, true, false)                                                   \
+    else if (ring) EMU_BOX_LAUNCH(YB, TYT, ST, MINB, false, true)                                                    \
+    else EMU_BOX_LAUNCH(YB, TYT, ST, MINB, false, false)                                                             \
   } break;
       LSB_BOX_CFGS(X)
 #undef X
@@ -92,15 +97,13 @@ HOSTSIM_API int emu_fdi_matvec(const int* dims, const double* ew, double ridge2,
     ctas += (ugrid.z > 0 ? ugrid.x * ugrid.y * ugrid.z : 0) + (have_z ? zgrid.x * zgrid.y * zgrid.z : 0);
     if (ugrid.z == 0) sc.pq_part[0] = 0.0;
     if (!have_z) sc.pq_part[3] = 0.0;
-    constexpr int SNT = 128;
-    ShellBox sb;
-    const long long nb = make_shell_box(g, shell_cz, SNT, &sb);
     if (nb > MAX_PARTIALS) return -1;
-    if (nb > 0)
+    if (ring) sc.pq_part[2] = 0.0;  // as launch_stencil: no shell launch
+    else if (nb > 0)
       lsb_emu::launch(dim3((unsigned)nb), dim3(SNT), 0, [&] {
         k_fdi_shell<SNT>(g, w, sb, ztab.data(), p, q, partials.data() + 3 * (size_t)MAX_PARTIALS, counters + 3, &sc, 0);
       });
-    ctas += (int)nb;
+    if (!ring) ctas += (int)nb;
     for (int i = 0; i < 6; ++i) info[i] = zr[i];
     info[6] = cz;
     info[8] = 1;

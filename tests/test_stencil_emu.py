@@ -38,7 +38,7 @@ def emu():
     return C.CDLL(LIB)
 
 
-def run(emu, nsteps, slab, weights, ridge2, p, cfg=4, cz=0, zface=8, shell_cz=0):
+def run(emu, nsteps, slab, weights, ridge2, p, cfg=4, cz=0, zface=8, shell_cz=0, ring=0):
     nx, ny, nz = (int(v) for v in nsteps)
     k0, k1 = slab
     dims = (C.c_int * 5)(nx, ny, nz, k0, k1)
@@ -46,7 +46,7 @@ def run(emu, nsteps, slab, weights, ridge2, p, cfg=4, cz=0, zface=8, shell_cz=0)
     q = np.empty(nx * ny * (k1 - k0))
     pq = C.c_double(0.0)
     info = (C.c_int * 9)()
-    rc = emu.emu_fdi_matvec(dims, ew.ctypes.data_as(dp), C.c_double(ridge2), cfg, cz, zface, shell_cz,
+    rc = emu.emu_fdi_matvec(dims, ew.ctypes.data_as(dp), C.c_double(ridge2), cfg, cz, zface, shell_cz, ring,
                             np.ascontiguousarray(p).ctypes.data_as(dp), q.ctypes.data_as(dp), C.byref(pq), info)
     assert rc == 0, f"emulated launch failed ({rc}): -2 = a kernel wrote outside the owned planes"
     return q, pq.value, list(info)
@@ -65,7 +65,9 @@ ANISO = dict(dxx=1.3, dyy=0.7, dzz=2.1, dxy=0.9, dxz=1.7, dyz=0.4, dx=1.9, dy=0.
     ((70, 20, 9), 1, ANISO, 1, 0, 8),      # both z-face ranges overlap: one z-general range, no uniform launch
     ((70, 20, 9), 2, ANISO, 4, 0, 8),
 ])
-def test_tiled_operator_on_every_slab_matches_the_oracle(emu, nsteps, world, weights, cfg, cz, zface):
+@pytest.mark.parametrize("ring", [0, 1])
+def test_tiled_operator_on_every_slab_matches_the_oracle(emu, nsteps, world, weights, cfg, cz, zface, ring):
+    """ring = 1: the fused form (k_fdi_box<..., RING>: the box CTAs also compute the ring columns, no shell launch)."""
     grid = fo.Grid(np.array(nsteps), np.zeros(3), np.ones(3))
     rng = np.random.default_rng(sum(nsteps) + world)
     p = rng.standard_normal(grid.n_nodes)
@@ -76,7 +78,7 @@ def test_tiled_operator_on_every_slab_matches_the_oracle(emu, nsteps, world, wei
     scale = max(np.abs(ref).max(), 1.0)
     total_pq = 0.0
     for k0, k1 in bounds:
-        q, pq, info = run(emu, nsteps, (k0, k1), weights, ridge2, p, cfg=cfg, cz=cz, zface=zface)
+        q, pq, info = run(emu, nsteps, (k0, k1), weights, ridge2, p, cfg=cfg, cz=cz, zface=zface, ring=ring)
         assert info[8] == 1  # the box plan, not the small-grid kernel
         sl = slice(k0 * plane, k1 * plane)
         assert not np.isnan(q).any(), f"slab {k0, k1}: {int(np.isnan(q).sum())} owned nodes were never written (plan {info})"
@@ -118,8 +120,9 @@ def test_random_small_grids_slabs_and_launch_parameters(emu):
         world = min(int(rng.integers(1, max(2, nz // 2))), nz // 2)
         cfg, cz = int(rng.choice([0, 1, 2, 4])), int(rng.choice([0, 3, 4, 7]))
         zface, scz = int(rng.choice([3, 5, 8])), int(rng.choice([0, 2, 8]))
+        ring = int(rng.integers(0, 2))
         for k0, k1 in (partition.slab_bounds(nz, world) if world > 1 else [(0, nz)]):
-            q, _pq, info = run(emu, (nx, ny, nz), (k0, k1), w, 0.05, p, cfg=cfg, cz=cz, zface=zface, shell_cz=scz)
+            q, _pq, info = run(emu, (nx, ny, nz), (k0, k1), w, 0.05, p, cfg=cfg, cz=cz, zface=zface, shell_cz=scz, ring=ring)
             sl = slice(k0 * nx * ny, k1 * nx * ny)
             assert not np.isnan(q).any(), ((nx, ny, nz), (k0, k1), info)
             assert np.abs(q - ref[sl]).max() <= 1e-12 * max(np.abs(ref).max(), 1.0), ((nx, ny, nz), (k0, k1), cfg, cz, zface, info)
