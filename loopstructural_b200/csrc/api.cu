@@ -261,9 +261,12 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
     // default because it has not been measured.
     static const bool shell_first = getenv("LSB200_SHELL_FIRST") && atoi(getenv("LSB200_SHELL_FIRST")) == 1;
     // LSB200_RING=1: the ring columns are computed by the box CTAs themselves (k_fdi_box<..., RING>), no shell launch
-    static const bool ring = getenv("LSB200_RING") && atoi(getenv("LSB200_RING")) == 1;
+    // (LSB200_RING=2: the same with the ring phase of every other CTA in front of its box work, see fdi_main.cuh)
+    static const int ring_mode = getenv("LSB200_RING") ? atoi(getenv("LSB200_RING")) : 0;
+    const bool ring = ring_mode == 1 || ring_mode == 2;
     ShellBox sb;
     const long long shell_ctas = make_shell_box(g, h->shell_cz, 128, &sb);
+    sb.ring_stagger = ring_mode == 2 ? 1 : 0;
     auto launch_box = [&]() -> int {
     {
         const UniConsts U = make_uni_consts(w);

@@ -194,6 +194,7 @@ struct ShellBox {
   int ring_cz, ring_chunks;          // z chunking of [klo,khi)
   int cap_blocks;                    // CTAs per cap: ceil(nx*ny / NT)
   int capA0, capA1, capB0, capB1;    // owned planes below klo / from khi up (either may be empty)
+  int ring_stagger;                  // k_fdi_box<RING>: 1 = CTAs of odd parity do their ring share BEFORE the box work
 };
 
 // per-plane z coefficients, 16 doubles per GLOBAL plane k: [0..4] T_z taps -2..2 (1/6 included), [5..9] B_z taps
@@ -458,6 +459,34 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
     for (int r = 0; r < YB; ++r) A[d][r][0] = A[d][r][1] = 0.0;
   double dot = 0.0;
 
+  // this CTA's share of the ring columns over its planes [ka,kb) (RING only)
+  auto ring_phase = [&]() {
+    const int ntiles = gridDim.x * gridDim.y;
+    const int tile = blockIdx.x + gridDim.x * blockIdx.y;
+    const int per = (sb.ring_cols + ntiles - 1) / ntiles;
+    const int c0 = tile * per, ncol = min(c0 + per, sb.ring_cols) - c0;
+    const int nplanes = kb - ka;
+    if (ncol > 0 && nplanes > 0) {
+      // sub-ranges of at least RING_MIN_PLANES planes (each re-reads 4 halo planes), enough of them to occupy the CTA
+      constexpr int RING_MIN_PLANES = 6;
+      int nsub = max(1, min(C::NT / ncol, nplanes / RING_MIN_PLANES));
+      const int sub = (nplanes + nsub - 1) / nsub;
+      nsub = (nplanes + sub - 1) / sub;
+      for (int it = tid; it < ncol * nsub; it += C::NT) {
+        const int sidx = it / ncol;
+        int ci, cj;
+        ring_column(g, sb, c0 + (it - sidx * ncol), &ci, &cj);  // consecutive threads take consecutive columns
+        const int za = ka + sidx * sub;
+        dot += shell_march(g, w, ztab, p, q, ci, cj, za, min(za + sub, kb));
+      }
+    }
+  };
+  // In a launch of a single wave every CTA would reach a trailing ring phase at the same time, with nothing left to
+  // hide its latency behind: with ring_stagger the CTAs of odd parity march first and stream afterwards, so that at any
+  // time about half of the resident CTAs keep HBM busy.
+  const bool ring_first = RING && sb.ring_stagger && ((blockIdx.x + blockIdx.y + blockIdx.z) & 1);
+  if (RING && ring_first) ring_phase();
+
   // an empty range (ka >= kb) stages and computes nothing, but still takes part in the grid reduction
   const int kstart = ka - HALO, kend = ka < kb ? kb + HALO : ka - HALO;
   int kp = kstart;
@@ -561,27 +590,7 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
 #undef LSB_BOX_STEP
   cp_async_wait<0>();
 
-  if (RING) {
-    const int ntiles = gridDim.x * gridDim.y;
-    const int tile = blockIdx.x + gridDim.x * blockIdx.y;
-    const int per = (sb.ring_cols + ntiles - 1) / ntiles;
-    const int c0 = tile * per, ncol = min(c0 + per, sb.ring_cols) - c0;
-    const int nplanes = kb - ka;
-    if (ncol > 0 && nplanes > 0) {
-      // sub-ranges of at least RING_MIN_PLANES planes (each re-reads 4 halo planes), enough of them to occupy the CTA
-      constexpr int RING_MIN_PLANES = 6;
-      int nsub = max(1, min(C::NT / ncol, nplanes / RING_MIN_PLANES));
-      const int sub = (nplanes + nsub - 1) / nsub;
-      nsub = (nplanes + sub - 1) / sub;
-      for (int it = tid; it < ncol * nsub; it += C::NT) {
-        const int sidx = it / ncol;
-        int ci, cj;
-        ring_column(g, sb, c0 + (it - sidx * ncol), &ci, &cj);  // consecutive threads take consecutive columns
-        const int za = ka + sidx * sub;
-        dot += shell_march(g, w, ztab, p, q, ci, cj, za, min(za + sub, kb));
-      }
-    }
-  }
+  if (RING && !ring_first) ring_phase();
 
   const double bsum = block_sum<C::NT>(dot, red);
   const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;

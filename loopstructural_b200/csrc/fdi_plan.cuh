@@ -126,6 +126,7 @@ inline long long make_shell_box(const GridDesc& g, const int shell_cz, const int
   sb.capA0 = g.k0; sb.capA1 = sb.klo;
   sb.capB0 = sb.khi; sb.capB1 = g.k1;
   sb.cap_blocks = (sb.capA1 > sb.capA0 || sb.capB1 > sb.capB0) ? (g.nx * g.ny + SNT - 1) / SNT : 0;
+  sb.ring_stagger = 0;
   *out = sb;
   return (long long)sb.ring_blocks * sb.ring_chunks + 2LL * sb.cap_blocks;
 }

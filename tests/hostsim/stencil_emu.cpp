@@ -77,6 +77,7 @@ HOSTSIM_API int emu_fdi_matvec(const int* dims, const double* ew, double ridge2,
     constexpr int SNT = 128;
     ShellBox sb;
     const long long nb = make_shell_box(g, shell_cz, SNT, &sb);
+    sb.ring_stagger = ring == 2 ? 1 : 0;
     switch (bt.cfg) {  // the dispatch of launch_stencil, launches through the emulator
 #define EMU_BOX_LAUNCH(YB, TYT, ST, MINB, V16, RING)                                                                  \
   {                                                                                                                  \

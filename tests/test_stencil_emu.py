@@ -65,9 +65,10 @@ ANISO = dict(dxx=1.3, dyy=0.7, dzz=2.1, dxy=0.9, dxz=1.7, dyz=0.4, dx=1.9, dy=0.
     ((70, 20, 9), 1, ANISO, 1, 0, 8),      # both z-face ranges overlap: one z-general range, no uniform launch
     ((70, 20, 9), 2, ANISO, 4, 0, 8),
 ])
-@pytest.mark.parametrize("ring", [0, 1])
+@pytest.mark.parametrize("ring", [0, 1, 2])
 def test_tiled_operator_on_every_slab_matches_the_oracle(emu, nsteps, world, weights, cfg, cz, zface, ring):
-    """ring = 1: the fused form (k_fdi_box<..., RING>: the box CTAs also compute the ring columns, no shell launch)."""
+    """ring = 1: the fused form (k_fdi_box<..., RING>: the box CTAs also compute the ring columns, no shell launch);
+    ring = 2: the same with every other CTA doing its ring share before its box work."""
     grid = fo.Grid(np.array(nsteps), np.zeros(3), np.ones(3))
     rng = np.random.default_rng(sum(nsteps) + world)
     p = rng.standard_normal(grid.n_nodes)
@@ -120,7 +121,7 @@ def test_random_small_grids_slabs_and_launch_parameters(emu):
         world = min(int(rng.integers(1, max(2, nz // 2))), nz // 2)
         cfg, cz = int(rng.choice([0, 1, 2, 4])), int(rng.choice([0, 3, 4, 7]))
         zface, scz = int(rng.choice([3, 5, 8])), int(rng.choice([0, 2, 8]))
-        ring = int(rng.integers(0, 2))
+        ring = int(rng.integers(0, 3))
         for k0, k1 in (partition.slab_bounds(nz, world) if world > 1 else [(0, nz)]):
             q, _pq, info = run(emu, (nx, ny, nz), (k0, k1), w, 0.05, p, cfg=cfg, cz=cz, zface=zface, shell_cz=scz, ring=ring)
             sl = slice(k0 * nx * ny, k1 * nx * ny)
