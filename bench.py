@@ -282,6 +282,41 @@ def measure_fault(local, n_nodes=128, npts=10_000_000, steps=10, cpu_points=100_
             "cpu_port_points_per_second": cpu_points / t_cpu, "cpu_sample_points": cpu_points}
 
 
+def measure_launch_plans(local, sizes=(256, 512), timeout=150):
+    """The matvec under the launch-plan switches that are built but have not been measured yet,
+    each in a process of its own (scripts/matvec_experiment.py): fused ring (LSB200_RING=1 / 2) and shell-first launch
+    order, beside the default plan.  Reports times and whether q = N p agrees with the default plan's."""
+    import subprocess
+
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "matvec_experiment.py")
+    plans = {"default": {}, "shell_first": {"LSB200_SHELL_FIRST": "1"}, "ring": {"LSB200_RING": "1"},
+             "ring_staggered": {"LSB200_RING": "2"}}
+    out = {}
+    for n in sizes:
+        ref = None
+        for name, env in plans.items():
+            if n > 256 and name == "shell_first":
+                continue
+            key = f"{name}_{n}"
+            try:
+                e = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local)), **env)
+                res = subprocess.run([sys.executable, script, str(n)], capture_output=True, text=True, timeout=timeout, env=e)
+                if res.returncode != 0:
+                    out[key] = {"error": (res.stderr or res.stdout)[-300:]}
+                    continue
+                r = json.loads(res.stdout.strip().splitlines()[-1])
+                if name == "default":
+                    ref = r
+                agree = None
+                if ref is not None:
+                    agree = max(abs(r[k] - ref[k]) / max(abs(ref[k]), 1e-300) for k in ("q_dot_probe", "q_norm", "p_dot_q"))
+                out[key] = {"matvec_us": r["matvec_us"], "matvec_gbs": r["matvec_gbs"], "iteration_us": r["iteration_us"],
+                            "max_rel_checksum_diff_vs_default": agree}
+            except Exception as exc:  # noqa: BLE001
+                out[key] = {"error": f"{type(exc).__name__}: {exc}"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -494,6 +529,14 @@ def run_ours(args):
                 line["fault"] = measure_fault(local)
             except Exception as exc:  # noqa: BLE001
                 line["fault"] = {"error": f"{type(exc).__name__}: {exc}"}
+        if world == 1 and not args.no_experiments:
+            # processes of their own, after this one has released the device memory it no longer needs
+            try:
+                eng.close()
+                torch.cuda.empty_cache()
+                line["launch_plan_experiments"] = measure_launch_plans(local)
+            except Exception as exc:  # noqa: BLE001
+                line["launch_plan_experiments"] = {"error": f"{type(exc).__name__}: {exc}"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -516,6 +559,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--multi-gpu-eval", action="store_true", help="N > 1: replicate c and evaluate a cloud split over the ranks")
     ap.add_argument("--eval-points", type=int, default=100_000_000)
+    ap.add_argument("--no-experiments", action="store_true", help="skip the unmeasured launch-plan experiments (subprocesses)")
     ap.add_argument("--no-fault", action="store_true", help="skip the fault-frame evaluation measurement")
     args = ap.parse_args()
     if args.impl == "reference":
