@@ -1,0 +1,51 @@
+"""The opt-in launch plans of the FDI matvec on the device (LSB200_RING=1 / 2: ring columns computed by the box CTAs,
+no shell launch; LSB200_SHELL_FIRST=1: shell enqueued before the box), each in a process of its own because the
+switches are read once per process: q = (R^T R + ridge^2 I) p and p.q against the oracle's explicit operator, and a
+whole solve against the reference's golden coefficients.  Parity of these kernels on the CPU emulator:
+tests/test_stencil_emu.py.  (Written after the round's GPU budget was spent: not yet run on a device, hence last.)"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+SCRIPT = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import golden_helpers as H
+from oracle import fdi_oracle as fo
+from loopstructural_b200 import engine as en
+W = dict(dxx=1.3, dyy=0.7, dzz=2.1, dxy=0.9, dxz=1.7, dyz=0.4, dx=1.9, dy=0.6, dz=1.1)
+for nsteps, w in (((40, 36, 30), {}), ((131, 70, 50), W), ((33, 18, 48), W), ((70, 20, 9), W)):
+    grid = fo.Grid(np.array(nsteps), np.zeros(3), np.ones(3))
+    e = H.engine_for(grid, w, ridge_factor=0.3)
+    p = np.random.default_rng(1).standard_normal(grid.n_nodes)
+    ref = fo.regularisation_normal_matvec(grid, w, p) + 0.09 * p
+    q = e.apply_normal(p, parts=en.PART_REGULARISATION | en.PART_RIDGE)
+    err = np.abs(q - ref).max() / max(np.abs(ref).max(), 1.0)
+    assert err <= 1e-12, (nsteps, err)
+    e.close()
+z = np.load(os.path.join(H.GOLDEN, "fdi_solve_unit24_tight.npz"))
+grid, weights, fams, rtol, atol = H.solve_case(z)
+e = H.engine_for(grid, weights, apply_scaling=bool(z["scaling"]))
+H.add_point_data(e, z, weights)
+c, res = e.solve_cg(rtol=rtol, atol=atol)
+rel = np.linalg.norm(c - z["c"]) / np.sqrt(c.size) / float(z["c"].max() - z["c"].min())
+assert rel <= 1e-6 and abs(res.iterations - int(z["iterations"])) <= 1 and res.info == 0, (rel, res.iterations)
+print("OK", os.environ.get("LSB200_RING"), os.environ.get("LSB200_SHELL_FIRST"), rel)
+"""
+
+
+@pytest.mark.parametrize("env", [{"LSB200_RING": "1"}, {"LSB200_RING": "2"}, {"LSB200_SHELL_FIRST": "1"},
+                                 {"LSB200_RING": "1", "LSB200_GRAPH": "0"}])
+def test_opt_in_launch_plans_match_the_oracle(env):
+    from loopstructural_b200 import build
+
+    build.build()
+    res = subprocess.run([sys.executable, "-c", SCRIPT, os.path.dirname(HERE)], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, **env))
+    assert res.returncode == 0 and "OK" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]
