@@ -232,6 +232,8 @@ def test_fault_frame_and_faulted_foliation_through_the_model(ls, monkeypatch):
     stock, _ = _fault_model(ls)
     sf = stock["fault"]
     assert sf.apply_to_points.__func__.__qualname__.startswith("FaultSegment.")
+    assert type(sf[1].builder).install_gradient_constraint.__qualname__ == "GeologicalFeatureBuilder.install_gradient_constraint"
+    assert any("orthogonal" in k for k in sf[1].interpolator.constraints)  # the stock build has the families on the host
     for i in range(3):
         cs = np.asarray(sf[i].interpolator.c)
         assert np.linalg.norm(c_frame[i] - cs) / np.sqrt(cs.size) / float(cs.max() - cs.min()) <= 1e-6  # the bar of BASELINE.json's north star
