@@ -226,19 +226,16 @@ def _make_fdi_class():
     return B200FDI
 
 
-def _make_p1_class():
+def _make_tet_class(base, name, doc):
+    """B200 subclass of a TetMesh interpolator (P1Interpolator or a class derived from it)."""
     from loop_common.supports import TetMesh
-    from loop_interpolation import P1Interpolator
 
-    class B200P1(_B200Mixin, P1Interpolator):
-        """P1Interpolator whose ``solver='b200'`` runs on the GPU engine: the face gradient-jump rows of
-        minimise_edge_jumps (LI/_p1interpolator.py:115-166; 99 % of A) are applied matrix-free."""
-
+    class B200Tet(_B200Mixin, base):
         _b200_unsupported = ("solver='b200' needs a 3-D structured TetMesh, the default (face-normal) edge-jump "
                              "regularisation and no per-node regularisation scale")
 
-        def __init__(self, mesh):
-            super().__init__(mesh)
+        def __init__(self, *args, **kwargs):
+            super().__init__(*args, **kwargs)
             self._b200_init()
 
         def _b200_can_divert(self, kwargs) -> bool:
@@ -260,8 +257,29 @@ def _make_p1_class():
             eng.set_p1_regularisation(self._b200_reg.get("cgw", 0.0))
             return eng
 
-    B200P1.__name__ = "B200P1Interpolator"
-    return B200P1
+    B200Tet.__name__ = B200Tet.__qualname__ = name
+    B200Tet.__doc__ = doc
+    return B200Tet
+
+
+def _make_p1_class():
+    from loop_interpolation import P1Interpolator
+
+    return _make_tet_class(P1Interpolator, "B200P1Interpolator",
+                           "P1Interpolator whose ``solver='b200'`` runs on the GPU engine: the face gradient-jump rows of "
+                           "minimise_edge_jumps (LI/_p1interpolator.py:115-166; 99 % of A) are applied matrix-free.")
+
+
+def _make_dfi_class():
+    """DiscreteFoldInterpolator (LI/_discrete_fold_interpolator.py:21-242; every folded foliation / folded fold frame is
+    built with it, LoopStructural/modelling/core/_model_feature_factory.py:248-250) on the same engine path as P1: its
+    fold orientation / axis / normalisation rows and its direction-weighted face rows ('fold regularisation n',
+    minimise_edge_jumps with a vector_func) stay explicit families and reach the device through lsb200_add_rows; a
+    plain 'edge jump' family, when the builder asks for one, is applied matrix-free like P1's."""
+    from loop_interpolation._discrete_fold_interpolator import DiscreteFoldInterpolator
+
+    return _make_tet_class(DiscreteFoldInterpolator, "B200DiscreteFoldInterpolator",
+                           "DiscreteFoldInterpolator whose ``solver='b200'`` runs on the GPU engine.")
 
 
 # -- fault frames: FaultSegment.apply_to_points / evaluate_displacement on the device -------------------------------
@@ -440,14 +458,17 @@ def install():
     if "fdi" not in _installed:
         _installed["fdi"] = _make_fdi_class()
         _installed["p1"] = _make_p1_class()
+        _installed["dfi"] = _make_dfi_class()
         _installed["stock"] = {T.FINITE_DIFFERENCE: li.interpolator_map[T.FINITE_DIFFERENCE],
-                               T.PIECEWISE_LINEAR: li.interpolator_map[T.PIECEWISE_LINEAR]}
+                               T.PIECEWISE_LINEAR: li.interpolator_map[T.PIECEWISE_LINEAR],
+                               T.DISCRETE_FOLD: li.interpolator_map[T.DISCRETE_FOLD]}
     li.interpolator_map[T.FINITE_DIFFERENCE] = _installed["fdi"]
     li.interpolator_map[T.PIECEWISE_LINEAR] = _installed["p1"]
+    li.interpolator_map[T.DISCRETE_FOLD] = _installed["dfi"]
     _install_fault_patch()
     _install_builder_patch()
     _install_feature_patch()
-    return {"FDI": _installed["fdi"], "P1": _installed["p1"]}
+    return {"FDI": _installed["fdi"], "P1": _installed["p1"], "DFI": _installed["dfi"]}
 
 
 def uninstall():

@@ -32,6 +32,9 @@ class OracleEngine:
     def set_regularisation(self, weights):
         self.weights = dict(weights)
 
+    def set_p1_regularisation(self, w):
+        self.cgw = float(w)
+
     def set_options(self, **kw):
         self.opts = kw
 
@@ -49,9 +52,14 @@ class OracleEngine:
         return fam.A.shape[0]
 
     def solve_cg(self, rtol=1e-5, atol=0.0, maxiter=None, x0=None, want_c=True, out=None):
-        w = dict(self.fo.DEFAULT_WEIGHTS)
-        w.update(self.weights)
-        fams = self.rows + self.fo.regularisation_families(self.grid, w)
+        if self.kind == "tetmesh":
+            from oracle import p1_oracle as po
+
+            fams = self.rows + ([po.face_rows(self.grid, self.cgw)] if self.cgw else [])
+        else:
+            w = dict(self.fo.DEFAULT_WEIGHTS)
+            w.update(self.weights)
+            fams = self.rows + self.fo.regularisation_families(self.grid, w)
         self.solve_args = dict(rtol=rtol, atol=atol)
         c, res, _ = self.fo.solve_reference_path(fams, self.grid.n_nodes, rtol=rtol, atol=atol,
                                                  ridge_factor=self.opts.get("ridge_factor", 1e-8),
@@ -61,9 +69,21 @@ class OracleEngine:
                                   residual_norm=res.residual_norm, threshold=res.threshold, kernel_launches=0)
 
     def evaluate_value(self, xyz):
+        if self.kind == "tetmesh":
+            from oracle import p1_oracle as po
+
+            xyz = np.asarray(xyz, float)
+            out = np.zeros(len(xyz))  # rows with NaN coordinates give 0.0 (LI/_discrete_interpolator.py:1357-1361)
+            good = ~np.any(np.isnan(xyz), axis=1)
+            out[good] = po.evaluate_value(self.grid, xyz[good], self.c)
+            return out
         return self.fo.evaluate_value(self.grid, np.asarray(xyz, float), self.c)
 
     def evaluate_gradient(self, xyz):
+        if self.kind == "tetmesh":
+            from oracle import p1_oracle as po
+
+            return po.evaluate_gradient(self.grid, np.asarray(xyz, float), self.c)
         return self.fo.evaluate_gradient(self.grid, np.asarray(xyz, float), self.c)
 
     def evaluate_lattice(self, start, stop, n, order="F", gradient=False, world_to_local=None, out_ptr=None, stream=0):
@@ -243,3 +263,55 @@ def test_fault_frame_and_faulted_foliation_through_the_model(ls, monkeypatch):
     s_ref = stock.evaluate_feature_value("strati", pts)
     np.testing.assert_array_equal(np.isnan(strati), np.isnan(s_ref))
     np.testing.assert_allclose(strati, s_ref, rtol=0, atol=1e-6 * float(np.nanmax(s_ref) - np.nanmin(s_ref)), equal_nan=True)
+
+
+def _fold_model(ls, **kw):
+    from loop_common.math import rng
+    from LoopStructural.datasets import load_laurent2016
+
+    # DiscreteFoldInterpolator shuffles the elements it puts fold constraints on with this module-level, unseeded
+    # generator (LI/_discrete_fold_interpolator.py:116-176): same state for the two builds that are compared
+    rng.bit_generator.state = np.random.default_rng(123).bit_generator.state
+    data, bb = load_laurent2016()
+    model = ls.GeologicalModel(bb[0, :], bb[1, :])
+    model.data = data
+    s2 = model.create_and_add_fold_frame("s2", nelements=1500, buffer=0.3, **kw)
+    s1 = model.create_and_add_folded_fold_frame("s1", fold_frame=s2, limb_wl=4, av_fold_axis=True, nelements=1500, buffer=0.3, **kw)
+    model.create_and_add_folded_foliation("s0", fold_frame=s1, limb_wl=1.0, av_fold_axis=True, nelements=1500, buffer=0.3, **kw)
+    model.update()
+    return model, bb
+
+
+def test_refolded_model_through_the_b200_solver_matches_the_stock_solver(ls):
+    """BASELINE configs[3], fold half (load_laurent2016 style): a fold frame (FDI), a folded fold frame and a folded
+    foliation (DiscreteFoldInterpolator on a TetMesh: fold orientation / axis / normalisation rows and direction-weighted
+    face rows as explicit families) all solved with solver='b200'."""
+    from loopstructural_b200 import plugin
+
+    model, bb = _fold_model(ls, solver="b200")
+    it0 = model["s0"].interpolator
+    assert type(it0).__name__ == "B200DiscreteFoldInterpolator" and it0.latest_solve_timing["backend"] == "b200"
+    assert {"fold orientation", "fold axis", "fold normalisation", "fold regularisation 1"} <= set(it0.constraints)
+    assert model["s1"][0].interpolator.latest_solve_timing["backend"] == "b200"   # DFI coordinate of the folded frame
+    assert model["s2"][0].interpolator.latest_solve_timing["backend"] == "b200"   # FDI
+    # Every stage against the stock solver ON THE SAME SYSTEM: the fold rows of s1 / s0 are functions of the previous
+    # field (rotation angles fitted to its gradient) and the systems take thousands of CG iterations, so two separately
+    # built models drift apart by far more than any solver difference -- the reference against itself under a one-ulp
+    # change of s2 does the same.  Nothing of a fold interpolator is diverted here (cgw = 0: no plain edge-jump family),
+    # so its constraint dict is the whole system and the stock solve_system can run on it directly.
+    for it in (model["s1"][0].interpolator, it0):
+        assert it._b200_reg == {} and it.interpolation_weights["cgw"] == 0.0
+        c_b200 = np.array(it.c)
+        tol = it.interpolation_weights.get("tol")
+        it._b200_divert = False  # keep the assembled families: the mixin would otherwise redo the (shuffled) set-up
+        assert it.solve_system("cg", tol=tol) is True and it.latest_solve_timing["backend"] == "python"
+        rng_ = float(it.c.max() - it.c.min())
+        assert np.linalg.norm(c_b200 - it.c) / np.sqrt(it.c.size) / rng_ <= 1e-9
+    c_frame = np.array(model["s2"][0].interpolator.c)
+
+    plugin.uninstall()
+    stock, _ = _fold_model(ls)
+    its = stock["s0"].interpolator
+    assert type(its).__name__ == "DiscreteFoldInterpolator" and its.latest_solve_timing["backend"] == "python"
+    cs2 = np.asarray(stock["s2"][0].interpolator.c)
+    assert np.linalg.norm(c_frame - cs2) / np.sqrt(cs2.size) / float(cs2.max() - cs2.min()) <= 1e-9  # the unfolded frame
