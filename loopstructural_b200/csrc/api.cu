@@ -838,7 +838,10 @@ int lsb200_add_field_orthogonal_rows(lsb200_handle h, lsb200_handle other, const
   rc = alloc_block(h, rb, n, 8);
   if (rc) return rc;
   const int nb = (int)std::min<long long>((n + 127) / 128, 4096);
-  k_fdi_field_orthogonal_rows<<<nb, 128, 0, h->stream>>>(h->g, F, (long long)element_step, n, weight, b, rb, 0, h->status);
+  if (F.kind == LSB200_SUPPORT_TETMESH)
+    k_fdi_field_orthogonal_rows<true><<<nb, 128, 0, h->stream>>>(h->g, F, (long long)element_step, n, weight, b, rb, 0, h->status);
+  else
+    k_fdi_field_orthogonal_rows<false><<<nb, 128, 0, h->stream>>>(h->g, F, (long long)element_step, n, weight, b, rb, 0, h->status);
   CKL();
   h->launches++;
   unsigned long long st[2];
@@ -1442,9 +1445,10 @@ static_assert(sizeof(lsb200_fault_profile) == sizeof(FaultProfile), "fault profi
 // 3 x 3 local -> world rotation) or null = identity
 static int make_frame_field(const lsb200_ctx* h, const double* t, const char* what, int f, FrameField* F) {
   if (!h) return fail(LSB200_ERR_ARG, "%s %d: null handle", what, f);
-  if (h->kind != LSB200_SUPPORT_GRID) return fail(LSB200_ERR_ARG, "%s %d: only grid handles are supported", what, f);
   if (h->g.k0 != 0 || h->g.k1 != h->g.nz) return fail(LSB200_ERR_STATE, "%s %d: the handle must own every plane", what, f);
   if (!h->have_c) return fail(LSB200_ERR_STATE, "%s %d: no solution on the device yet (solve or set_c first)", what, f);
+  F->kind = h->kind;
+  F->pad = 0;
   F->g = h->g;
   F->c = h->x;
   if (t) {
@@ -1497,10 +1501,20 @@ static int frame_launch(lsb200_ctx* h, const FrameCall& fc, int64_t n, const dou
                         cudaStream_t st) {
   if (n == 0) return 0;
   const int nb = frame_blocks(h, n);
+  bool tet = false;  // any tet-mesh field: the kernels that carry the (register-hungry) tet branch
+  for (int f = 0; f < 3; ++f) tet = tet || fc.FF.f[f].kind == LSB200_SUPPORT_TETMESH;
   switch (fc.what) {
-    case FRAME_EVAL: k_frame_eval<<<nb, 256, 0, st>>>(fc.FF, fc.gradient_of, n, xyz_dev, out0, out1); break;
-    case FRAME_DISPLACE: k_fault_displace<<<nb, 256, 0, st>>>(fc.FF, fc.P, fc.displacement, fc.steps, n, xyz_dev, out0); break;
-    default: k_fault_displacement<<<nb, 256, 0, st>>>(fc.FF, fc.P, fc.displacement, fc.offset, n, xyz_dev, out0);
+    case FRAME_EVAL:
+      if (tet) k_frame_eval<true><<<nb, 256, 0, st>>>(fc.FF, fc.gradient_of, n, xyz_dev, out0, out1);
+      else k_frame_eval<false><<<nb, 256, 0, st>>>(fc.FF, fc.gradient_of, n, xyz_dev, out0, out1);
+      break;
+    case FRAME_DISPLACE:
+      if (tet) k_fault_displace<true><<<nb, 256, 0, st>>>(fc.FF, fc.P, fc.displacement, fc.steps, n, xyz_dev, out0);
+      else k_fault_displace<false><<<nb, 256, 0, st>>>(fc.FF, fc.P, fc.displacement, fc.steps, n, xyz_dev, out0);
+      break;
+    default:
+      if (tet) k_fault_displacement<true><<<nb, 256, 0, st>>>(fc.FF, fc.P, fc.displacement, fc.offset, n, xyz_dev, out0);
+      else k_fault_displacement<false><<<nb, 256, 0, st>>>(fc.FF, fc.P, fc.displacement, fc.offset, n, xyz_dev, out0);
   }
   CKL();
   h->launches++;
@@ -1635,7 +1649,10 @@ int lsb200_eval_lattice_dev(lsb200_handle h, const double* transform, const doub
   if (rc || (rc = make_lattice(start, stop, n, order_f, &lat, &total))) return rc;
   if (!out_dev) return fail(LSB200_ERR_ARG, "null output");
   CK(cudaSetDevice(h->device));
-  k_eval_lattice<<<frame_blocks(h, total), 256, 0, (cudaStream_t)stream>>>(F, lat, 0, total, gradient ? 1 : 0, out_dev);
+  if (F.kind == LSB200_SUPPORT_TETMESH)
+    k_eval_lattice<true><<<frame_blocks(h, total), 256, 0, (cudaStream_t)stream>>>(F, lat, 0, total, gradient ? 1 : 0, out_dev);
+  else
+    k_eval_lattice<false><<<frame_blocks(h, total), 256, 0, (cudaStream_t)stream>>>(F, lat, 0, total, gradient ? 1 : 0, out_dev);
   CKL();
   h->launches++;
   return 0;
@@ -1656,7 +1673,8 @@ int lsb200_eval_lattice(lsb200_handle h, const double* transform, const double s
   CK(cudaMallocAsync(&d, sizeof(double) * ow * chunk, h->stream));
   for (long long o = 0; o < total; o += chunk) {
     const long long m = std::min<long long>(chunk, total - o);
-    k_eval_lattice<<<frame_blocks(h, m), 256, 0, h->stream>>>(F, lat, o, m, gradient ? 1 : 0, d);
+    if (F.kind == LSB200_SUPPORT_TETMESH) k_eval_lattice<true><<<frame_blocks(h, m), 256, 0, h->stream>>>(F, lat, o, m, gradient ? 1 : 0, d);
+    else k_eval_lattice<false><<<frame_blocks(h, m), 256, 0, h->stream>>>(F, lat, o, m, gradient ? 1 : 0, d);
     CKL();
     h->launches++;
     CK(cudaMemcpyAsync(out + ow * o, d, sizeof(double) * ow * m, cudaMemcpyDeviceToHost, h->stream));

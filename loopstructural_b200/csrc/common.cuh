@@ -38,6 +38,14 @@ LSB_HD double rn_add(double a, double b) {
   return r;
 #endif
 }
+LSB_HD double rn_sub(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dsub_rn(a, b);
+#else
+  volatile double r = a - b;
+  return r;
+#endif
+}
 LSB_HD double rn_mul(double a, double b) {
 #ifdef __CUDA_ARCH__
   return __dmul_rn(a, b);

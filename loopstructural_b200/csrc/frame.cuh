@@ -10,19 +10,22 @@
 //                                       (LI/_geological_interpolator.py:723-741)
 // Every step of that loop is independent per point, so here ONE thread carries one point through all steps:
 // xyz is read once (24 B), the moved point written once (24 B), the 3 x 8 corner values per step come from L2 / HBM
-// as random 8-byte gathers exactly as in k_eval_value_grid.  Grid supports only (the reference's default fault
-// interpolator is FDI); fault-frame features must carry no faults / regions of their own -- the host mirror checks
-// and otherwise leaves the call to the reference.
+// as random 8-byte gathers exactly as in k_eval_value_grid.  Each field is a grid (FDI, the reference's default for
+// faults) or a tet mesh (PLI / fold interpolators); fault-frame features must carry no faults / regions of their own
+// -- the host mirror checks and otherwise leaves the call to the reference.
 //
 // The per-point code is LSB_HD: tests/hostsim runs the same functions on the CPU against the oracle.
 #pragma once
 #include "common.cuh"
+#include "p1.cuh"
 #include "rows.cuh"
 
 namespace lsb {
 
 // one solved field of the frame
 struct FrameField {
+  int kind;  // LSB200_SUPPORT_GRID: trilinear cells; LSB200_SUPPORT_TETMESH: P1 on the 5-tet decomposition
+  int pad;
   GridDesc g;
   const double* c;  // node vector of the handle (halo planes included)
   double w2l[12];   // world -> local, rows of the 3 x 4 affine: l_a = w2l[4a] x + w2l[4a+1] y + w2l[4a+2] z + w2l[4a+3]
@@ -90,7 +93,11 @@ LSB_HD double fault_step_d(const FaultProfile& F, const double gx, const double 
 }
 
 // value (and, when grad != nullptr, world-frame gradient) of one field at a WORLD point: project, locate, gather.
-// Value: 0.0 when a projected coordinate is NaN, NaN outside the support; gradient: 0 outside.
+// Value: 0.0 when a projected coordinate is NaN, NaN outside the support; gradient: 0 outside a grid, NaN outside a
+// tet mesh (StructuredGrid.evaluate_gradient vs TetMesh.evaluate_gradient, LC/supports/_3d_structured_grid.py:356-357,
+// LC/supports/_3d_structured_tetra.py:247-248).
+// TET = false: every field of the call is a grid (the tet branch is not compiled: 124 instead of 252 registers).
+template <bool TET = true>
 LSB_HD double frame_field_at(const FrameField& F, const double xw[3], double* grad) {
   double l[3];
 #pragma unroll
@@ -98,9 +105,32 @@ LSB_HD double frame_field_at(const FrameField& F, const double xw[3], double* gr
     l[a] = rn_add(rn_add(rn_add(rn_mul(F.w2l[4 * a], xw[0]), rn_mul(F.w2l[4 * a + 1], xw[1])), rn_mul(F.w2l[4 * a + 2], xw[2])),
                   F.w2l[4 * a + 3]);
   const bool nanrow = (l[0] != l[0]) || (l[1] != l[1]) || (l[2] != l[2]);
-  const CellLoc L = locate(F.g, l);
   double v = nanrow ? 0.0 : nan("");
   double gl[3] = {0.0, 0.0, 0.0};
+  if (TET && F.kind == LSB200_SUPPORT_TETMESH) {
+    const TetLoc T = locate_tet(F.g, l);
+    double cv[4] = {0.0, 0.0, 0.0, 0.0};
+    if (T.inside) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cv[k] = ld_node(F.c + T.node[k]);
+      v = T.c[0] * cv[0] + T.c[1] * cv[1] + T.c[2] * cv[2] + T.c[3] * cv[3];
+    }
+    if (grad) {
+      if (T.inside) {
+        double G[3][4];
+        tet_gradients(T.v, G);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) gl[a] = G[a][0] * cv[0] + G[a][1] * cv[1] + G[a][2] * cv[2] + G[a][3] * cv[3];
+      } else {
+        gl[0] = gl[1] = gl[2] = nan("");
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        grad[a] = rn_add(rn_add(rn_mul(F.l2w[3 * a], gl[0]), rn_mul(F.l2w[3 * a + 1], gl[1])), rn_mul(F.l2w[3 * a + 2], gl[2]));
+    }
+    return v;
+  }
+  const CellLoc L = locate(F.g, l);
   if (L.inside) {
     double cv[8];
 #pragma unroll
@@ -130,21 +160,22 @@ LSB_HD double frame_field_at(const FrameField& F, const double xw[3], double* gr
 }
 
 // FaultSegment.apply_to_points for one point: x is moved in place
+template <bool TET = true>
 LSB_HD void fault_displace_point(const FrameFields& FF, const FaultProfile& P, const double displacement, const int steps,
                                  double x[3]) {
   double g[3];
-  double gx = frame_field_at(FF.f[0], x, nullptr);
-  double gy = frame_field_at(FF.f[1], x, g);
-  double gz = frame_field_at(FF.f[2], x, nullptr);
+  double gx = frame_field_at<TET>(FF.f[0], x, nullptr);
+  double gy = frame_field_at<TET>(FF.f[1], x, g);
+  double gz = frame_field_at<TET>(FF.f[2], x, nullptr);
   bool ok;
   const double d0 = fault_step_d(P, gx, gy, gz, 0.0, &ok);
   if (!(fabs(d0) > 0.0)) return;  // mask = |d| > 0: only these points enter the loop
   const double inv_steps = 1.0 / (double)steps;
   for (int i = 0; i < steps; ++i) {
     if (i > 0) {
-      gx = frame_field_at(FF.f[0], x, nullptr);
-      gy = frame_field_at(FF.f[1], x, g);
-      gz = frame_field_at(FF.f[2], x, nullptr);
+      gx = frame_field_at<TET>(FF.f[0], x, nullptr);
+      gy = frame_field_at<TET>(FF.f[1], x, g);
+      gz = frame_field_at<TET>(FF.f[2], x, nullptr);
     }
     const double d = rn_mul(fault_step_d(P, gx, gy, gz, 0.0, &ok), displacement);
     double gmag = 0.0;
@@ -161,11 +192,12 @@ LSB_HD void fault_displace_point(const FrameFields& FF, const FaultProfile& P, c
 }
 
 // FaultSegment.evaluate_displacement for one point
+template <bool TET = true>
 LSB_HD double fault_displacement_point(const FrameFields& FF, const FaultProfile& P, const double displacement,
                                        const double offset, const double x[3]) {
-  const double gx = frame_field_at(FF.f[0], x, nullptr);
-  const double gy = frame_field_at(FF.f[1], x, nullptr);
-  const double gz = frame_field_at(FF.f[2], x, nullptr);
+  const double gx = frame_field_at<TET>(FF.f[0], x, nullptr);
+  const double gy = frame_field_at<TET>(FF.f[1], x, nullptr);
+  const double gz = frame_field_at<TET>(FF.f[2], x, nullptr);
   bool ok;
   return rn_mul(fault_step_d(P, gx, gy, gz, offset, &ok), displacement);
 }
@@ -181,6 +213,7 @@ LSB_HD double fault_displacement_point(const FrameFields& FF, const FaultProfile
 // evaluate_gradient, which projects them as world coordinates (rows come out empty where that lands outside the other
 // support): kept as is, pinned by tests/golden/orth_world.npz.
 // Row r <- cell e = r * estep.  Returns false when the row is empty on this handle (slab: cell touches no owned plane).
+template <bool TET = true>
 LSB_HD bool field_orthogonal_row(const GridDesc& g, const FrameField& other, const long long e, const double bval,
                                  double A[8], int ci[3], double* b_out) {
   const int ncx = g.nx - 1, ncy = g.ny - 1;
@@ -191,7 +224,7 @@ LSB_HD bool field_orthogonal_row(const GridDesc& g, const FrameField& other, con
   for (int a = 0; a < 3; ++a)  // StructuredGrid.cell_centres: origin + step * cell + step * 0.5
     x[a] = rn_add(rn_add(g.origin[a], rn_mul(g.step[a], (double)cell[a])), rn_mul(g.step[a], 0.5));
   double v[3];
-  frame_field_at(other, x, v);
+  frame_field_at<TET>(other, x, v);
   const double n1 = sqrt(rn_add(rn_add(rn_mul(v[0], v[0]), rn_mul(v[1], v[1])), rn_mul(v[2], v[2])));
   if (n1 > 0.0) { v[0] /= n1; v[1] /= n1; v[2] /= n1; }
   const CellLoc L = locate(g, x);
@@ -225,11 +258,12 @@ LSB_HD bool field_orthogonal_row(const GridDesc& g, const FrameField& other, con
 }
 
 // body of k_fdi_field_orthogonal_rows for row r (shared with tests/hostsim)
+template <bool TET = true>
 LSB_HD bool field_orthogonal_row_store(const GridDesc& g, const FrameField& other, const long long estep, const double weight,
                                        const double bval, const RowBlock& rb, const long long row0, const long long r) {
   double A[8], b;
   int ci[3];
-  const bool ok = field_orthogonal_row(g, other, r * estep, bval, A, ci, &b);
+  const bool ok = field_orthogonal_row<TET>(g, other, r * estep, bval, A, ci, &b);
   const long long ro = row0 + r;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
@@ -275,13 +309,14 @@ LSB_HD void lattice_point(const Lattice& lat, const long long idx, double x[3]) 
 
 #ifdef __CUDACC__
 // points [first, first + m) of the lattice: value (m) or world gradient (m,3) of one field
+template <bool TET>
 __global__ void __launch_bounds__(256)
     k_eval_lattice(const FrameField F, const Lattice lat, const long long first, const long long m, const int gradient,
                    double* __restrict__ out) {
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < m; r += (long long)gridDim.x * blockDim.x) {
     double x[3], g[3];
     lattice_point(lat, first + r, x);
-    const double v = frame_field_at(F, x, gradient ? g : nullptr);
+    const double v = frame_field_at<TET>(F, x, gradient ? g : nullptr);
     if (gradient) {
       out[3 * r] = g[0];
       out[3 * r + 1] = g[1];
@@ -292,15 +327,17 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+template <bool TET>
 __global__ void __launch_bounds__(128)
     k_fdi_field_orthogonal_rows(const GridDesc g, const FrameField other, const long long estep, const long long n_rows,
                                 const double weight, const double bval, const RowBlock rb, const long long row0,
                                 unsigned long long* __restrict__ status) {
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x)
-    if (field_orthogonal_row_store(g, other, estep, weight, bval, rb, row0, r)) atomicAdd(status, 1ull);
+    if (field_orthogonal_row_store<TET>(g, other, estep, weight, bval, rb, row0, r)) atomicAdd(status, 1ull);
 }
 
 // the three values (n,3) and, when grad_out != nullptr, the gradient (n,3) of field `gfield`: one pass over xyz
+template <bool TET>
 __global__ void __launch_bounds__(256)
     k_frame_eval(const FrameFields FF, const int gfield, const long long n, const double* __restrict__ xyz,
                  double* __restrict__ val_out, double* __restrict__ grad_out) {
@@ -308,7 +345,7 @@ __global__ void __launch_bounds__(256)
     const double x[3] = {xyz[3 * r], xyz[3 * r + 1], xyz[3 * r + 2]};
     double g[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-    for (int f = 0; f < 3; ++f) val_out[3 * r + f] = frame_field_at(FF.f[f], x, (grad_out && f == gfield) ? g : nullptr);
+    for (int f = 0; f < 3; ++f) val_out[3 * r + f] = frame_field_at<TET>(FF.f[f], x, (grad_out && f == gfield) ? g : nullptr);
     if (grad_out) {
       grad_out[3 * r] = g[0];
       grad_out[3 * r + 1] = g[1];
@@ -317,24 +354,26 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+template <bool TET>
 __global__ void __launch_bounds__(256)
     k_fault_displace(const FrameFields FF, const FaultProfile P, const double displacement, const int steps,
                      const long long n, const double* __restrict__ xyz, double* __restrict__ out) {
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
     double x[3] = {xyz[3 * r], xyz[3 * r + 1], xyz[3 * r + 2]};
-    fault_displace_point(FF, P, displacement, steps, x);
+    fault_displace_point<TET>(FF, P, displacement, steps, x);
     out[3 * r] = x[0];
     out[3 * r + 1] = x[1];
     out[3 * r + 2] = x[2];
   }
 }
 
+template <bool TET>
 __global__ void __launch_bounds__(256)
     k_fault_displacement(const FrameFields FF, const FaultProfile P, const double displacement, const double offset,
                          const long long n, const double* __restrict__ xyz, double* __restrict__ out) {
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
     const double x[3] = {xyz[3 * r], xyz[3 * r + 1], xyz[3 * r + 2]};
-    out[r] = fault_displacement_point(FF, P, displacement, offset, x);
+    out[r] = fault_displacement_point<TET>(FF, P, displacement, offset, x);
   }
 }
 #endif

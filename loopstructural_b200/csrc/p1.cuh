@@ -121,6 +121,16 @@ __global__ void k_p1_diag(const GridDesc g, const P1Tables tb, const double w2, 
 // ---- point location ------------------------------------------------------------------------------------
 __constant__ int c_tet_even[5][4] = {{7, 1, 2, 4}, {6, 2, 4, 7}, {5, 1, 4, 7}, {0, 1, 2, 4}, {3, 1, 2, 7}};
 __constant__ int c_tet_odd[5][4] = {{0, 6, 5, 3}, {7, 3, 5, 6}, {4, 0, 5, 6}, {2, 0, 3, 6}, {1, 0, 3, 5}};
+// corner s of tet t of a cell (LC/supports/_3d_structured_tetra.py:28-34); the host copy serves tests/hostsim only
+LSB_HD int tet_corner(const bool even, const int t, const int s) {
+#ifdef __CUDA_ARCH__
+  return even ? c_tet_even[t][s] : c_tet_odd[t][s];
+#else
+  constexpr int ev[5][4] = {{7, 1, 2, 4}, {6, 2, 4, 7}, {5, 1, 4, 7}, {0, 1, 2, 4}, {3, 1, 2, 7}};
+  constexpr int od[5][4] = {{0, 6, 5, 3}, {7, 3, 5, 6}, {4, 0, 5, 6}, {2, 0, 3, 6}, {1, 0, 3, 5}};
+  return even ? ev[t][s] : od[t][s];
+#endif
+}
 
 struct TetLoc {
   bool inside;
@@ -131,31 +141,31 @@ struct TetLoc {
 };
 
 // unfused arithmetic in numpy's order, so that points on tet faces take the same side as in the reference
-__device__ __forceinline__ void cross_rn(const double a[3], const double b[3], double o[3]) {
-  o[0] = __dsub_rn(__dmul_rn(a[1], b[2]), __dmul_rn(a[2], b[1]));
-  o[1] = __dsub_rn(__dmul_rn(a[2], b[0]), __dmul_rn(a[0], b[2]));
-  o[2] = __dsub_rn(__dmul_rn(a[0], b[1]), __dmul_rn(a[1], b[0]));
+LSB_HD void cross_rn(const double a[3], const double b[3], double o[3]) {
+  o[0] = rn_sub(rn_mul(a[1], b[2]), rn_mul(a[2], b[1]));
+  o[1] = rn_sub(rn_mul(a[2], b[0]), rn_mul(a[0], b[2]));
+  o[2] = rn_sub(rn_mul(a[0], b[1]), rn_mul(a[1], b[0]));
 }
-__device__ __forceinline__ double dot_rn(const double a[3], const double b[3]) {
-  return __dadd_rn(__dadd_rn(__dmul_rn(a[0], b[0]), __dmul_rn(a[1], b[1])), __dmul_rn(a[2], b[2]));
+LSB_HD double dot_rn(const double a[3], const double b[3]) {
+  return rn_add(rn_add(rn_mul(a[0], b[0]), rn_mul(a[1], b[1])), rn_mul(a[2], b[2]));
 }
 
 // TetMesh.get_element_for_location (LC/supports/_3d_structured_tetra.py:274-365): cell by floor + clip, the five
 // tets of the cell, barycentrics by scalar triple products, the LAST tet with all c >= 0 wins; strict inside
 // (:264-272) on top of the tolerant one of position_to_cell_index (LC/supports/_3d_base_structured.py:255-293).
-__device__ __forceinline__ TetLoc locate_tet(const GridDesc& g, const double x[3]) {
+LSB_HD TetLoc locate_tet(const GridDesc& g, const double x[3]) {
   TetLoc L;
   const int nc[3] = {g.nx - 1, g.ny - 1, g.nz - 1};
   bool ins_tol = true, ins_strict = true;
   int cell[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    const double maxi = __dadd_rn(g.origin[a], __dmul_rn((double)nc[a], g.step[a]));
+    const double maxi = rn_add(g.origin[a], rn_mul((double)nc[a], g.step[a]));
     const double ext = fmax(fabs(maxi - g.origin[a]), 1.0);
-    const double tol = __dmul_rn(__dmul_rn(2.220446049250313e-16, 32.0), ext);
+    const double tol = rn_mul(rn_mul(2.220446049250313e-16, 32.0), ext);
     ins_tol = ins_tol && (x[a] >= g.origin[a] - tol) && (x[a] <= maxi + tol);
     // TetMesh.inside: origin + step_vector * nsteps_cells
-    ins_strict = ins_strict && (x[a] > g.origin[a]) && (x[a] < __dadd_rn(g.origin[a], __dmul_rn(g.step[a], (double)nc[a])));
+    ins_strict = ins_strict && (x[a] > g.origin[a]) && (x[a] < rn_add(g.origin[a], rn_mul(g.step[a], (double)nc[a])));
   }
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
@@ -175,10 +185,10 @@ __device__ __forceinline__ TetLoc locate_tet(const GridDesc& g, const double x[3
     int corner[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-      corner[s] = even ? c_tet_even[t][s] : c_tet_odd[t][s];
+      corner[s] = tet_corner(even, t, s);
       const int off[3] = {corner[s] & 1, (corner[s] >> 1) & 1, (corner[s] >> 2) & 1};
 #pragma unroll
-      for (int a = 0; a < 3; ++a) v[s][a] = __dadd_rn(g.origin[a], __dmul_rn(g.step[a], (double)(cell[a] + off[a])));
+      for (int a = 0; a < 3; ++a) v[s][a] = rn_add(g.origin[a], rn_mul(g.step[a], (double)(cell[a] + off[a])));
     }
     double vap[3], vbp[3], vab[3], vac[3], vad[3], vbc[3], vbd[3], cr[3];
 #pragma unroll
@@ -212,7 +222,7 @@ __device__ __forceinline__ TetLoc locate_tet(const GridDesc& g, const double x[3
 
 // shape-function gradients G = E^-1 [[-1,1,0,0],[-1,0,1,0],[-1,0,0,1]], E rows = v1-v0, v2-v0, v3-v0
 // (TetMesh.get_element_gradients, LC/supports/_3d_structured_tetra.py:421-486); returns |det E| / 6 (element_size)
-__device__ __forceinline__ double tet_gradients(const double v[4][3], double G[3][4]) {
+LSB_HD double tet_gradients(const double v[4][3], double G[3][4]) {
   double E[3][3];
 #pragma unroll
   for (int r = 0; r < 3; ++r)

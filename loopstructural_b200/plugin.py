@@ -300,7 +300,7 @@ def _frame_of(segment):
             feat.builder.up_to_date()  # lazy solve, as GeologicalFeature.evaluate_value does (_geological_feature.py:139-140)
         it = getattr(feat, "interpolator", None)
         eng = it._b200_engine_current() if hasattr(it, "_b200_engine_current") else None
-        if eng is None or getattr(eng, "kind", "grid") != "grid":
+        if eng is None or getattr(eng, "kind", "grid") not in ("grid", "tetmesh"):
             return None
         engines.append(eng)
         bb = getattr(it, "bounding_box", None)
@@ -339,8 +339,10 @@ def _make_fault_methods(stock_apply, stock_displacement):
     return apply_to_points, evaluate_displacement
 
 
-def _solved_grid_field(feature):
-    """(engine, world_to_local) of a plain interpolated feature solved by the grid engine, else None."""
+def _solved_grid_field(feature, kinds=("grid",)):
+    """(engine, world_to_local) of a plain interpolated feature solved by the engine on one of ``kinds``, else None.
+    (Orthogonality rows take grid sources only: outside a tet mesh the gradient is NaN and the reference then drops the
+    WHOLE family, LI/_discrete_interpolator.py:357-359 -- left to the stock method.)"""
     if type(feature).__name__ != "GeologicalFeature":
         return None
     if getattr(feature, "faults_enabled", True) and len(getattr(feature, "faults", [])) > 0:
@@ -349,7 +351,7 @@ def _solved_grid_field(feature):
         feature.builder.up_to_date()
     it = getattr(feature, "interpolator", None)
     eng = it._b200_engine_current() if hasattr(it, "_b200_engine_current") else None
-    if eng is None or getattr(eng, "kind", "grid") != "grid":
+    if eng is None or getattr(eng, "kind", "grid") not in kinds:
         return None
     bb = getattr(it, "bounding_box", None)
     return eng, (np.eye(4) if bb is None else np.asarray(bb.world_to_local_matrix, dtype=float))
@@ -403,7 +405,7 @@ def _make_scalar_field(stock):
         kernel) when the feature is a plain one solved by the grid engine; the stock method otherwise."""
         src = None
         if type(self).__name__ == "GeologicalFeature" and len(getattr(self, "regions", [])) == 0:
-            src = _solved_grid_field(self)
+            src = _solved_grid_field(self, kinds=("grid", "tetmesh"))
         if src is None:
             return stock(self, bounding_box)
         from LoopStructural.geometry import StructuredGrid

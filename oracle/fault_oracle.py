@@ -94,6 +94,7 @@ class FrameField:
     grid: fo.Grid
     c: np.ndarray
     world_to_local: np.ndarray | None = None  # 4 x 4; None = points are already local
+    kind: str = "grid"  # "grid": StructuredGrid (FDI); "tetmesh": TetMesh on the same lattice (P1 / fold interpolators)
 
     def project(self, pts):
         if self.world_to_local is None:
@@ -103,10 +104,24 @@ class FrameField:
         return (self.world_to_local @ hom.T).T[:, :3]
 
     def value(self, pts):
-        return fo.evaluate_value(self.grid, self.project(pts), self.c)
+        loc = self.project(pts)
+        if self.kind == "tetmesh":
+            from . import p1_oracle as po
+
+            out = np.zeros(loc.shape[0])  # rows with NaN coordinates: 0.0 (LI/_discrete_interpolator.py:1357-1361)
+            good = ~np.any(np.isnan(loc), axis=1)
+            if good.any():
+                out[good] = po.evaluate_value(self.grid, loc[good], self.c)
+            return out
+        return fo.evaluate_value(self.grid, loc, self.c)
 
     def gradient(self, pts):
-        g = fo.evaluate_gradient(self.grid, self.project(pts), self.c)
+        if self.kind == "tetmesh":
+            from . import p1_oracle as po
+
+            g = po.evaluate_gradient(self.grid, self.project(pts), self.c)  # NaN outside the mesh
+        else:
+            g = fo.evaluate_gradient(self.grid, self.project(pts), self.c)
         if self.world_to_local is None:
             return g
         rot = np.linalg.inv(self.world_to_local)[:3, :3]  # reproject_vectors, _bounding_box.py:750-761

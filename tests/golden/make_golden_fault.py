@@ -53,11 +53,11 @@ def profile_table(fd):
     return tab, comp
 
 
-def main():
+def main(interpolatortype="FDI", prefix="fault_", only=None):
     data, bb = load_intrusion()
     model = GeologicalModel(bb[0, :], bb[1, :])
     model.data = data
-    model.create_and_add_fault("fault", 500, nelements=2000, interpolatortype="FDI", buffer=0.3)
+    model.create_and_add_fault("fault", 500, nelements=2000, interpolatortype=interpolatortype, buffer=0.3)
     model.update()
     fault = model["fault"]
     fields = {}
@@ -71,6 +71,7 @@ def main():
         fields[f"f{i}_step"] = np.asarray(sup.step_vector, float)
         fields[f"f{i}_c"] = np.array(it.c)
         fields[f"f{i}_w2l"] = np.array(it.bounding_box.world_to_local_matrix, float)
+        fields[f"f{i}_kind"] = np.array(1 if type(sup).__name__ == "TetMesh" else 0)
     rng = np.random.default_rng(7)
     ext = bb[1] - bb[0]
     pts = bb[0] + rng.uniform(-0.6, 1.6, (2000, 3)) * ext  # well beyond the buffered supports on every side
@@ -108,6 +109,8 @@ def main():
         "none": (None, 120.0, 5, 0.0),
     }
     for tag, (fd, disp, steps, offset) in cases.items():
+        if only is not None and tag not in only:
+            continue
         fault._faultfunction = fd
         fault.displacement = disp
         fault.steps = steps
@@ -124,7 +127,7 @@ def main():
                        has_function=0)
         vals = np.stack([fault[i].evaluate_value(pts) for i in range(3)], axis=1)
         grad1 = fault[1].evaluate_gradient(pts, ignore_regions=True)
-        np.savez_compressed(os.path.join(HERE, f"fault_{tag}.npz"), points=pts, moved=moved, moved_reverse=moved_rev,
+        np.savez_compressed(os.path.join(HERE, f"{prefix}{tag}.npz"), points=pts, moved=moved, moved_reverse=moved_rev,
                             displacement_at=dsp, frame_values=vals, frame_gradient1=grad1, displacement=disp, steps=steps,
                             fault_offset=offset, **out)
         n_moved = int(np.sum(np.any(moved != pts, axis=1) & ~np.any(np.isnan(pts), axis=1)))
@@ -134,3 +137,5 @@ def main():
 
 if __name__ == "__main__":
     main()
+    # the same frame on a TetMesh (P1): evaluation is NaN outside for value AND gradient
+    main("PLI", "faultp1_", only=("base", "wide", "none"))

@@ -73,7 +73,8 @@ def fault_case(z):
     from oracle import fault_oracle as fa
 
     fields = [fa.FrameField(fo.Grid.from_cells(z[f"f{i}_ncells"], z[f"f{i}_origin"], z[f"f{i}_step"]), z[f"f{i}_c"],
-                            z[f"f{i}_w2l"]) for i in range(3)]
+                            z[f"f{i}_w2l"], "tetmesh" if f"f{i}_kind" in z and int(z[f"f{i}_kind"]) == 1 else "grid")
+              for i in range(3)]
 
     def p1(row):
         return fa.Profile1D(int(row[0]), tuple(row[1:5]), (row[5], row[6]), float(row[7]), float(row[8]))

@@ -21,10 +21,14 @@ struct HostFrame {
   std::vector<double> store[3];  // node vectors in the handle's layout: two halo planes either side
 };
 
+int g_kinds[3] = {LSB200_SUPPORT_GRID, LSB200_SUPPORT_GRID, LSB200_SUPPORT_GRID};  // set by hostsim_set_kinds
+
 void build(HostFrame& H, const int64_t* nsteps, const double* origin, const double* step, const double* const c[3],
            const double* transforms) {
   for (int f = 0; f < 3; ++f) {
     FrameField& F = H.FF.f[f];
+    F.kind = g_kinds[f];
+    F.pad = 0;
     GridDesc& g = F.g;
     g.nx = (int)nsteps[3 * f]; g.ny = (int)nsteps[3 * f + 1]; g.nz = (int)nsteps[3 * f + 2];
     g.k0 = 0; g.k1 = g.nz; g.nzl = g.nz;
@@ -49,6 +53,9 @@ void build(HostFrame& H, const int64_t* nsteps, const double* origin, const doub
 
 #define HOSTSIM_API __attribute__((visibility("default")))
 extern "C" {
+
+// support kind of the three fields of the following calls (LSB200_SUPPORT_GRID / LSB200_SUPPORT_TETMESH)
+HOSTSIM_API void hostsim_set_kinds(int k0, int k1, int k2) { g_kinds[0] = k0; g_kinds[1] = k1; g_kinds[2] = k2; }
 
 HOSTSIM_API int hostsim_frame_eval(const int64_t* nsteps, const double* origin, const double* step, const double* c0, const double* c1,
                        const double* c2, const double* transforms, int gradient_of, int64_t n, const double* xyz,

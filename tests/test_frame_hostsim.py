@@ -235,3 +235,37 @@ def test_lattice_code_matches_the_reference_and_the_oracle(sim):
             g = _lattice_call(sim, fld, start, stop, nn, order, True)
             np.testing.assert_allclose(g, fa.evaluate_lattice(fld, start, stop, nn, order, gradient=True), rtol=0, atol=1e-12)
     assert np.isnan(_lattice_call(sim, fld, lo - 0.7 * ext, hi + 0.7 * ext, (13, 9, 21), "F", False)).sum() > 500
+
+
+P1_CASES = sorted(os.path.basename(p)[8:-4] for p in glob.glob(os.path.join(GOLDEN, "faultp1_*.npz")))
+
+
+@pytest.mark.parametrize("tag", P1_CASES)
+def test_tet_mesh_frame_code_matches_the_reference(sim, tag):
+    """The tet-mesh branch of the frame kernels (P1 barycentrics / tet gradients, NaN outside for value and gradient)
+    against the reference's FaultSegment on a frame solved with interpolatortype='PLI'."""
+    z = np.load(os.path.join(GOLDEN, f"faultp1_{tag}.npz"))
+    keep, args = _frame_args(z)
+    prof = native_profile(z)
+    pts = np.ascontiguousarray(z["points"])
+    n = pts.shape[0]
+    sim.hostsim_set_kinds(1, 1, 1)
+    try:
+        vals, grad = np.empty((n, 3)), np.empty((n, 3))
+        assert sim.hostsim_frame_eval(*args, 1, C.c_int64(n), pts.ctypes.data_as(dp), vals.ctypes.data_as(dp), grad.ctypes.data_as(dp)) == 0
+        np.testing.assert_array_equal(np.isnan(vals), np.isnan(z["frame_values"]))
+        np.testing.assert_allclose(vals, z["frame_values"], rtol=0, atol=1e-11, equal_nan=True)
+        np.testing.assert_array_equal(np.isnan(grad), np.isnan(z["frame_gradient1"]))
+        np.testing.assert_allclose(grad, z["frame_gradient1"], rtol=0, atol=1e-12, equal_nan=True)
+        moved = np.empty((n, 3))
+        assert sim.hostsim_fault_displace(*args, C.byref(prof), C.c_double(float(z["displacement"])), C.c_int(int(z["steps"])),
+                                          C.c_int64(n), pts.ctypes.data_as(dp), moved.ctypes.data_as(dp)) == 0
+        np.testing.assert_array_equal(np.isnan(moved), np.isnan(z["moved"]))
+        np.testing.assert_allclose(moved, z["moved"], rtol=0, atol=1e-9, equal_nan=True)
+        d = np.empty(n)
+        disp = float(z["displacement"])
+        assert sim.hostsim_fault_displacement(*args, C.byref(prof), C.c_double(disp), C.c_double(float(z["fault_offset"])),
+                                              C.c_int64(n), pts.ctypes.data_as(dp), d.ctypes.data_as(dp)) == 0
+        np.testing.assert_allclose(d, z["displacement_at"], rtol=1e-12, atol=1e-12 * abs(disp))
+    finally:
+        sim.hostsim_set_kinds(0, 0, 0)

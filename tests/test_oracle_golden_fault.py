@@ -11,6 +11,7 @@ from golden_helpers import GOLDEN, fault_case
 from oracle import fault_oracle as fa
 
 CASES = sorted(os.path.basename(p)[6:-4] for p in glob.glob(os.path.join(GOLDEN, "fault_*.npz")))
+P1_CASES = sorted(os.path.basename(p)[8:-4] for p in glob.glob(os.path.join(GOLDEN, "faultp1_*.npz")))
 
 
 def test_fixtures_present():
@@ -62,3 +63,22 @@ def test_lattice_export_matches_the_reference():
         np.testing.assert_allclose(v, z[key], rtol=0, atol=1e-13 * rng_, equal_nan=True)
     g = fa.evaluate_lattice(fld, z["box_origin"], z["box_maximum"], z["box_nsteps"], "F", gradient=True)
     np.testing.assert_allclose(g, z["node_gradient_f"], rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("tag", P1_CASES)
+def test_fault_frame_on_a_tet_mesh_matches_the_reference(tag):
+    """The same frame solved with interpolatortype='PLI' (TetMesh): value AND gradient are NaN outside the mesh, so a
+    point that leaves it becomes NaN (faultp1_none: 7 NaN coordinates in the reference's output)."""
+    z = np.load(os.path.join(GOLDEN, f"faultp1_{tag}.npz"))
+    assert P1_CASES == ["base", "none", "wide"] and int(z["f1_kind"]) == 1
+    fields, profile, disp, steps, offset = fault_case(z)
+    vals, grad = fa.frame_eval(fields, z["points"])
+    np.testing.assert_array_equal(np.isnan(vals), np.isnan(z["frame_values"]))
+    np.testing.assert_allclose(vals, z["frame_values"], rtol=0, atol=1e-11, equal_nan=True)
+    np.testing.assert_array_equal(np.isnan(grad), np.isnan(z["frame_gradient1"]))
+    np.testing.assert_allclose(grad, z["frame_gradient1"], rtol=0, atol=1e-13, equal_nan=True)
+    moved = fa.apply_to_points(fields, profile, disp, steps, z["points"])
+    np.testing.assert_array_equal(np.isnan(moved), np.isnan(z["moved"]))
+    np.testing.assert_allclose(moved, z["moved"], rtol=0, atol=1e-9, equal_nan=True)
+    d = fa.evaluate_displacement(fields, profile, disp, offset, z["points"])
+    np.testing.assert_allclose(d, z["displacement_at"], rtol=1e-13, atol=1e-13 * abs(disp))

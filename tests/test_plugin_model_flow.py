@@ -90,7 +90,7 @@ class OracleEngine:
         from oracle import fault_oracle as fa
 
         self.lattice_calls = getattr(self, "lattice_calls", 0) + 1
-        return fa.evaluate_lattice(fa.FrameField(self.grid, self.c, world_to_local), start, stop, n, order, gradient)
+        return fa.evaluate_lattice(fa.FrameField(self.grid, self.c, world_to_local, self.kind), start, stop, n, order, gradient)
 
     def close(self):
         pass
@@ -179,7 +179,7 @@ class OracleFaultFrame:
         from oracle import fault_oracle as fa
 
         self.fa = fa
-        self.fields = [fa.FrameField(e.grid, e.c, None if world_to_local is None else np.asarray(world_to_local[i]))
+        self.fields = [fa.FrameField(e.grid, e.c, None if world_to_local is None else np.asarray(world_to_local[i]), e.kind)
                        for i, e in enumerate(engines)]
 
     def _profile(self, p):

@@ -234,3 +234,32 @@ def test_lattice_export_matches_the_reference_and_the_oracle():
     local = pts @ z["w2l"][:3, :3].T + z["w2l"][:3, 3]
     np.testing.assert_allclose(host[::997], e.evaluate_value(local), rtol=0, atol=1e-12 * rng_, equal_nan=True)
     e.close()
+
+
+@pytest.mark.parametrize("tag", ["base", "none", "wide"])
+def test_fault_frame_on_a_tet_mesh_matches_the_reference(tag):
+    """Frame solved with interpolatortype='PLI' (tests/golden/faultp1_*.npz): the tet-mesh branch of the frame kernels."""
+    from loopstructural_b200 import Engine, build
+    from loopstructural_b200.fault import FaultFrame
+
+    build.build()
+    z = np.load(os.path.join(GOLDEN, f"faultp1_{tag}.npz"))
+    engines = []
+    for i in range(3):
+        e = Engine(z[f"f{i}_ncells"] + 1, z[f"f{i}_origin"], z[f"f{i}_step"], kind="tetmesh")
+        e.set_c(z[f"f{i}_c"])
+        engines.append(e)
+    frame = FaultFrame(engines, [z[f"f{i}_w2l"] for i in range(3)])
+    vals, grad = frame.evaluate(z["points"], gradient_of=1)
+    np.testing.assert_array_equal(np.isnan(vals), np.isnan(z["frame_values"]))
+    np.testing.assert_allclose(vals, z["frame_values"], rtol=0, atol=1e-11, equal_nan=True)
+    np.testing.assert_array_equal(np.isnan(grad), np.isnan(z["frame_gradient1"]))
+    np.testing.assert_allclose(grad, z["frame_gradient1"], rtol=0, atol=1e-12, equal_nan=True)
+    moved = frame.apply_to_points(z["points"], _profile(z), float(z["displacement"]), int(z["steps"]))
+    np.testing.assert_array_equal(np.isnan(moved), np.isnan(z["moved"]))
+    np.testing.assert_allclose(moved, z["moved"], rtol=0, atol=1e-9, equal_nan=True)
+    disp = float(z["displacement"])
+    d = frame.evaluate_displacement(z["points"], _profile(z), disp, float(z["fault_offset"]))
+    np.testing.assert_allclose(d, z["displacement_at"], rtol=1e-12, atol=1e-12 * abs(disp))
+    for e in engines:
+        e.close()
