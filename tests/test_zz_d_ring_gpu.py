@@ -1,7 +1,8 @@
 """The opt-in launch plans of the FDI matvec on the device (LSB200_RING=1 / 2: ring columns computed by the box CTAs,
 no shell launch; LSB200_SHELL_FIRST=1: shell enqueued before the box), each in a process of its own because the
 switches are read once per process: q = (R^T R + ridge^2 I) p and p.q against the oracle's explicit operator, and a
-whole solve against the reference's golden coefficients.  Parity of these kernels on the CPU emulator:
+whole solve against the reference's golden coefficients; also (first case: the default plan) z-slab handles on one
+device -- halo planes zero -- among them the rank that owns only the upper z face, whose launch faulted on the 8-GPU box.  Parity of these kernels on the CPU emulator:
 tests/test_stencil_emu.py.  (Written after the round's GPU budget was spent: not yet run on a device, hence last.)"""
 import os
 import subprocess
@@ -29,6 +30,24 @@ for nsteps, w in (((40, 36, 30), {}), ((131, 70, 50), W), ((33, 18, 48), W), ((7
     err = np.abs(q - ref).max() / max(np.abs(ref).max(), 1.0)
     assert err <= 1e-12, (nsteps, err)
     e.close()
+# z slabs on ONE device: without neighbours the halo planes stay zero, i.e. the slab applies the global operator to
+# p extended by zero -- every rank of a 3-way split, among them the one that owns only the upper face
+from loopstructural_b200 import Engine, partition
+nsteps = (40, 36, 30)
+grid = fo.Grid(np.array(nsteps), np.zeros(3), np.ones(3))
+plane = nsteps[0] * nsteps[1]
+for k0, k1 in partition.slab_bounds(nsteps[2], 3):
+    e = Engine(grid.nsteps, grid.origin, grid.step, slab=(k0, k1))
+    e.set_regularisation(W)
+    e.set_options(ridge_factor=0.3)
+    p_loc = np.random.default_rng(k0).standard_normal(plane * (k1 - k0))
+    p_ext = np.zeros(grid.n_nodes)
+    p_ext[k0 * plane:k1 * plane] = p_loc
+    ref = (fo.regularisation_normal_matvec(grid, W, p_ext) + 0.09 * p_ext)[k0 * plane:k1 * plane]
+    q = e.apply_normal(p_loc, parts=en.PART_REGULARISATION | en.PART_RIDGE)
+    err = np.abs(q - ref).max() / max(np.abs(ref).max(), 1.0)
+    assert err <= 1e-12, ("slab", (k0, k1), err)
+    e.close()
 z = np.load(os.path.join(H.GOLDEN, "fdi_solve_unit24_tight.npz"))
 grid, weights, fams, rtol, atol = H.solve_case(z)
 e = H.engine_for(grid, weights, apply_scaling=bool(z["scaling"]))
@@ -40,7 +59,7 @@ print("OK", os.environ.get("LSB200_RING"), os.environ.get("LSB200_SHELL_FIRST"),
 """
 
 
-@pytest.mark.parametrize("env", [{"LSB200_RING": "1"}, {"LSB200_RING": "2"}, {"LSB200_SHELL_FIRST": "1"},
+@pytest.mark.parametrize("env", [{}, {"LSB200_RING": "1"}, {"LSB200_RING": "2"}, {"LSB200_SHELL_FIRST": "1"},
                                  {"LSB200_RING": "1", "LSB200_GRAPH": "0"}])
 def test_opt_in_launch_plans_match_the_oracle(env):
     from loopstructural_b200 import build
