@@ -119,6 +119,31 @@ class _B200DiscreteInterpolator:
             self._engine.close()
             self._engine = None
 
+    def _inside(self, xyz: np.ndarray) -> np.ndarray:
+        """StructuredGrid.inside with its 32-eps tolerance (LC/supports/_3d_base_structured.py:287-293); TetMesh.inside is
+        strict on top of it (LC/supports/_3d_structured_tetra.py:264-272)."""
+        lo, hi = self.support.origin, self.support.maximum
+        with np.errstate(invalid="ignore"):
+            if self.kind == "tetmesh":
+                return np.all((xyz > lo) & (xyz < hi), axis=1)
+            tol = np.finfo(float).eps * 32.0 * np.maximum(np.abs(hi - lo), 1.0)
+            return np.all((xyz >= lo - tol) & (xyz <= hi + tol), axis=1)
+
+    def _family(self, key: str, used_cols) -> np.ndarray | None:
+        """Constraint points of one family, or None when the reference would add nothing: it drops the WHOLE family when
+        any row that reaches add_constraints_to_least_squares holds a NaN (LI/_discrete_interpolator.py:355-359); points
+        outside the support never get that far.  (The C-ABI itself drops single rows.)"""
+        pts = self.data[key]
+        if len(pts) == 0:
+            return None
+        inside = self._inside(pts[:, :3])
+        if inside.any() and np.isnan(pts[inside][:, used_cols]).any():
+            import warnings
+
+            warnings.warn(f"Constraints contain nan not adding constraints: {key}", stacklevel=3)
+            return None
+        return pts
+
     def _apply_weight_kwargs(self, kwargs):
         # every unknown key lands in interpolation_weights (LI/_discrete_interpolator.py:172-177)
         for k, v in kwargs.items():
@@ -219,13 +244,16 @@ class B200FiniteDifferenceInterpolator(_B200DiscreteInterpolator):
         e.clear_rows()
         e.set_regularisation(w)
         rc = {}
-        rc["normal"] = e.add_point_rows(en.ROWS_NORMAL, self.data["normal"], w["npw"]) if len(self.data["normal"]) else 0
-        rc["gradient"] = e.add_point_rows(en.ROWS_GRADIENT, self.data["gradient"], w["gpw"]) if len(self.data["gradient"]) else 0
-        rc["value"] = e.add_point_rows(en.ROWS_VALUE, self.data["value"], w["cpw"]) if len(self.data["value"]) else 0
-        if len(self.data["tangent"]):
+        vec = [3, 4, 5]
+        normal, gradient, value, tangent = (self._family("normal", vec), self._family("gradient", vec),
+                                            self._family("value", [3]), self._family("tangent", vec))
+        rc["normal"] = e.add_point_rows(en.ROWS_NORMAL, normal, w["npw"]) if normal is not None else 0
+        rc["gradient"] = e.add_point_rows(en.ROWS_GRADIENT, gradient, w["gpw"]) if gradient is not None else 0
+        rc["value"] = e.add_point_rows(en.ROWS_VALUE, value, w["cpw"]) if value is not None else 0
+        if tangent is not None:
             # add_tangent_constraints -> add_gradient_orthogonal_constraints(points, vectors, w, b=0)
             # (LI/_discrete_interpolator.py:668-682): column 6 of the point array is the row target b
-            t = self.data["tangent"].copy()
+            t = tangent.copy()
             t[:, 6] = 0.0
             rc["tangent"] = e.add_point_rows(en.ROWS_TANGENT, t, w["tpw"])
         else:
@@ -272,10 +300,11 @@ class B200P1Interpolator(_B200DiscreteInterpolator):
         e.clear_rows()
         e.set_p1_regularisation(w["cgw"])
         rc = {"regularisation": "matrix-free"}
-        rc["normal"] = e.add_point_rows(en.ROWS_NORMAL, self.data["normal"], w["npw"]) if len(self.data["normal"]) else 0
-        rc["value"] = e.add_point_rows(en.ROWS_VALUE, self.data["value"], w["cpw"]) if len(self.data["value"]) else 0
-        if len(self.data["tangent"]):
-            t = self.data["tangent"].copy()
+        normal, value, tangent = self._family("normal", [3, 4, 5]), self._family("value", [3]), self._family("tangent", [3, 4, 5])
+        rc["normal"] = e.add_point_rows(en.ROWS_NORMAL, normal, w["npw"]) if normal is not None else 0
+        rc["value"] = e.add_point_rows(en.ROWS_VALUE, value, w["cpw"]) if value is not None else 0
+        if tangent is not None:
+            t = tangent.copy()
             t[:, 6] = 0.0
             rc["tangent"] = e.add_point_rows(en.ROWS_TANGENT, t, w["tpw"])
         else:

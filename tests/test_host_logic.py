@@ -108,3 +108,56 @@ def test_z_ranges_of_the_box_launches_partition_every_slab():
                         if a1 > a0 and b1 > b0:
                             assert a1 <= b0
     assert lib.lsb200_plan_z_ranges(10, 5, 3, 4, 8, out) != 0
+
+
+def test_mirror_drops_a_whole_family_that_holds_a_nan_like_the_reference(monkeypatch):
+    """add_constraints_to_least_squares returns without adding anything when A, B or the indices of a family contain a
+    NaN (LI/_discrete_interpolator.py:355-359) -- a NaN value constraint inside the support silences ALL value
+    constraints; one outside the support never reaches the check.  The mirror classes follow that rule."""
+    import warnings
+
+    from loopstructural_b200 import interpolators as ip
+
+    calls = []
+
+    class FakeEngine:
+        def __init__(self, *a, **k):
+            self.kind = k.get("kind", "grid")
+
+        def clear_rows(self):
+            calls.clear()
+
+        def set_regularisation(self, w):
+            pass
+
+        def set_p1_regularisation(self, w):
+            pass
+
+        def add_point_rows(self, kind, data, weight):
+            calls.append((kind, len(data)))
+            return len(data)
+
+        def add_interface_rows(self, data, weight):
+            return 0
+
+    monkeypatch.setattr(ip, "Engine", FakeEngine)
+    sup = ip.Support(np.zeros(3), np.array([4, 4, 4]), np.ones(3))
+    good = np.array([[0.5, 0.5, 0.5, 1.0, 1.0], [1.5, 2.5, 0.5, 2.0, 1.0]])
+    nan_inside = np.vstack([good, [[2.5, 2.5, 2.5, np.nan, 1.0]]])
+    nan_outside = np.vstack([good, [[9.0, 2.5, 2.5, np.nan, 1.0]]])
+    for cls in (ip.B200FiniteDifferenceInterpolator, ip.B200P1Interpolator):
+        it = cls(sup)
+        it.set_value_constraints(nan_outside)
+        assert it.setup_interpolator()["value"] == 3 and calls == [(ip.en.ROWS_VALUE, 3)]  # the engine drops the outside row itself
+        it.set_value_constraints(nan_inside)
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            assert it.setup_interpolator()["value"] == 0 and calls == []
+        assert any("contain nan" in str(x.message) for x in w)
+        nrm = np.array([[0.5, 0.5, 0.5, 0.0, np.nan, 1.0, 1.0]])
+        it.set_value_constraints(good)
+        it.set_normal_constraints(nrm)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            rc = it.setup_interpolator()
+        assert rc["normal"] == 0 and rc["value"] == 2
