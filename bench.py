@@ -314,6 +314,23 @@ def measure_launch_plans(local, sizes=(256, 512), timeout=150):
                             "max_rel_checksum_diff_vs_default": agree}
             except Exception as exc:  # noqa: BLE001
                 out[key] = {"error": f"{type(exc).__name__}: {exc}"}
+    # the P1 face-jump operator at BASELINE configs[2] size: generic kernel against the class-coherent interior kernel
+    script = os.path.join(os.path.dirname(script), "p1_experiment.py")
+    ref = None
+    for name, env in (("p1_default_117", {}), ("p1_fast_117", {"LSB200_P1_FAST": "1"})):
+        try:
+            e = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local)), **env)
+            res = subprocess.run([sys.executable, script, "117"], capture_output=True, text=True, timeout=timeout, env=e)
+            if res.returncode != 0:
+                out[name] = {"error": (res.stderr or res.stdout)[-300:]}
+                continue
+            r = json.loads(res.stdout.strip().splitlines()[-1])
+            ref = ref or r
+            out[name] = {"matvec_us": r["matvec_us"], "iteration_us": r["iteration_us"],
+                         "max_rel_checksum_diff_vs_default": max(abs(r[k] - ref[k]) / max(abs(ref[k]), 1e-300)
+                                                                 for k in ("q_dot_probe", "q_norm", "p_dot_q"))}
+        except Exception as exc:  # noqa: BLE001
+            out[name] = {"error": f"{type(exc).__name__}: {exc}"}
     return out
 
 

@@ -382,8 +382,22 @@ static int launch_regularisation(lsb200_ctx* h, const double* p, double* q, int 
   const P1Tables tb{{h->p1_m[0], h->p1_m[1], h->p1_m[2]}, h->p1_table, h->p1_off, h->p1_diag};
   const long long n = (long long)h->g.nx * h->g.ny * h->g.nzl;
   const int nb = (int)std::max<long long>(1, std::min<long long>((n + VEC_NT - 1) / VEC_NT, (long long)h->sm_count * 16));
-  k_p1_normal<VEC_NT><<<nb, VEC_NT, 0, h->stream>>>(h->g, tb, h->p1_w * h->p1_w, h->add_ridge ? h->ridge * h->ridge : 0.0, p, q,
-                                                     h->partials, h->counters + 0, h->sc, cg_mode);
+  const double w2 = h->p1_w * h->p1_w, ridge2 = h->add_ridge ? h->ridge * h->ridge : 0.0;
+  // LSB200_P1_FAST=1: interior nodes by the class-coherent kernel (table rows in registers), the rest by the generic
+  // one; off by default until it has been measured
+  static const bool fast = getenv("LSB200_P1_FAST") && atoi(getenv("LSB200_P1_FAST")) == 1;
+  P1InteriorPlan pl;
+  if (fast && p1_plan_interior(h->g, h->p1_m, 128, MAX_PARTIALS, &pl)) {
+    k_p1_normal_interior<128><<<dim3(pl.gx, pl.gy, pl.gz), 128, 0, h->stream>>>(h->g, tb, w2, ridge2, pl.jchunk, pl.kchunk, p, q,
+                                                                              h->partials, h->counters + 0, h->sc, cg_mode);
+    CKL();
+    k_p1_normal<VEC_NT, true><<<nb, VEC_NT, 0, h->stream>>>(h->g, tb, w2, ridge2, p, q, h->partials + 3 * (size_t)MAX_PARTIALS,
+                                                            h->counters + 3, h->sc, cg_mode);
+    CKL();
+    h->launches += 2;
+    return 0;
+  }
+  k_p1_normal<VEC_NT, false><<<nb, VEC_NT, 0, h->stream>>>(h->g, tb, w2, ridge2, p, q, h->partials, h->counters + 0, h->sc, cg_mode);
   CKL();
   h->launches++;
   return 0;

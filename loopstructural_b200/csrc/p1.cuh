@@ -69,7 +69,15 @@ __device__ __forceinline__ int p1_row(const GridDesc& g, const P1Tables& tb, int
   return (rz * (tb.m[1] + 1) + ry) * (tb.m[0] + 1) + rx;
 }
 
-template <int NT>
+// a node whose class is one of the eight interior ones on every axis (p1_rep: 2 + parity): 2 <= i <= nc - 2, on a
+// mesh with more cells than the small mesh of the table (nc > m)
+__device__ __forceinline__ bool p1_interior_axis(int i, int nc, int m) { return nc != m && i >= 2 && i <= nc - 2; }
+__device__ __forceinline__ bool p1_interior(const GridDesc& g, const P1Tables& tb, int i, int j, int k) {
+  return p1_interior_axis(i, g.nx - 1, tb.m[0]) && p1_interior_axis(j, g.ny - 1, tb.m[1]) && p1_interior_axis(k, g.nz - 1, tb.m[2]);
+}
+
+// BOUNDARY_ONLY = true: the companion of k_p1_normal_interior -- only the nodes that kernel leaves out, p.q into pq_part[2]
+template <int NT, bool BOUNDARY_ONLY = false>
 __global__ void __launch_bounds__(NT)
     k_p1_normal(const GridDesc g, const P1Tables tb, const double w2, const double ridge2, const double* __restrict__ p,
                 double* __restrict__ q, double* __restrict__ partials, unsigned int* __restrict__ counter,
@@ -82,6 +90,7 @@ __global__ void __launch_bounds__(NT)
     const int i = (int)(t % g.nx);
     const long long r = t / g.nx;
     const int j = (int)(r % g.ny), kl = (int)(r / g.ny);
+    if (BOUNDARY_ONLY && p1_interior(g, tb, i, j, g.k0 + kl)) continue;
     const int row = p1_row(g, tb, i, j, g.k0 + kl);  // the class of a node depends on its GLOBAL plane
     const double* __restrict__ C = tb.coef + (long long)row * P1_TAPS;
     const int* __restrict__ O = tb.off + (long long)row * P1_TAPS;
@@ -103,7 +112,99 @@ __global__ void __launch_bounds__(NT)
   }
   const double bsum = block_sum<NT>(dot, red);
   double total;
-  if (grid_sum_last_block<NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total)) sc->pq_part[0] = total;
+  if (grid_sum_last_block<NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total)) sc->pq_part[BOUNDARY_ONLY ? 2 : 0] = total;
+}
+
+// The interior nodes of the same operator (LSB200_P1_FAST=1, beside k_p1_normal<NT, true> for the rest).  In
+// k_p1_normal every node costs 36 x (coefficient + offset + p) = 108 loads, two thirds of them table reads that
+// depend only on the node's CLASS, and on the interior there are just eight classes (the parities of i, j, k).  Here a
+// thread keeps i fixed and walks j and k in steps of two, so its class is constant: the 36 (coefficient, offset) pairs
+// are loaded into registers once per parity pair and a node costs its 36 gathers of p.  Thread x <-> consecutive i
+// (coalesced rows); blockIdx.y / .z: chunks of j / of the owned planes.
+template <int NT>
+__global__ void __launch_bounds__(NT)
+    k_p1_normal_interior(const GridDesc g, const P1Tables tb, const double w2, const double ridge2, const int jchunk,
+                         const int kchunk, const double* __restrict__ p, double* __restrict__ q,
+                         double* __restrict__ partials, unsigned int* __restrict__ counter, CgScalars* __restrict__ sc,
+                         const int cg_mode) {
+  __shared__ double red[NT / 32];
+  if (cg_mode && sc->done) return;
+  const int ncx = g.nx - 1, ncy = g.ny - 1, ncz = g.nz - 1;
+  const int i = 2 + blockIdx.x * NT + threadIdx.x;
+  // interior ranges of j and of the owned planes (global k), cut into this block's chunks
+  const int j0 = 2 + blockIdx.y * jchunk, j1 = min(j0 + jchunk, ncy - 1);
+  const int kfirst = max(g.k0, 2), klast = min(g.k1, ncz - 1);  // [kfirst, klast)
+  const int k0 = kfirst + blockIdx.z * kchunk, k1 = min(k0 + kchunk, klast);
+  double dot = 0.0;
+  if (i <= ncx - 2) {
+    const int rx = 2 + ((i - 2) & 1);
+#pragma unroll 1
+    for (int par = 0; par < 4; ++par) {
+      const int pj = par & 1, pk = par >> 1;
+      // first j / k of the chunk with (j - 2) & 1 == pj, (k - 2) & 1 == pk
+      const int ja = j0 + (((j0 - 2) & 1) == pj ? 0 : 1), ka = k0 + (((k0 - 2) & 1) == pk ? 0 : 1);
+      if (ja >= j1 || ka >= k1) continue;
+      const int row = ((2 + pk) * (tb.m[1] + 1) + (2 + pj)) * (tb.m[0] + 1) + rx;
+      double C[P1_TAPS];
+      int O[P1_TAPS];
+#pragma unroll
+      for (int e = 0; e < P1_TAPS; ++e) {
+        C[e] = __ldg(tb.coef + (long long)row * P1_TAPS + e);
+        O[e] = __ldg(tb.off + (long long)row * P1_TAPS + e);
+      }
+      for (int k = ka; k < k1; k += 2) {
+        const double* pr = p + ((long long)(k - g.k0 + HALO) * g.plane + i);
+        for (int j = ja; j < j1; j += 2) {
+          const double* pb = pr + (long long)j * g.pitch;
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+          for (int e = 0; e < P1_TAPS; e += 4) {
+            a0 = fma(C[e], pb[O[e]], a0);
+            a1 = fma(C[e + 1], pb[O[e + 1]], a1);
+            a2 = fma(C[e + 2], pb[O[e + 2]], a2);
+            a3 = fma(C[e + 3], pb[O[e + 3]], a3);
+          }
+          const double p0 = pb[0];
+          const double v = fma(w2, (a0 + a1) + (a2 + a3), ridge2 * p0);
+          q[pb - p] = v;
+          dot = fma(p0, v, dot);
+        }
+      }
+    }
+  }
+  const double bsum = block_sum<NT>(dot, red);
+  const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
+  const unsigned int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  double total;
+  if (grid_sum_last_block<NT>(bsum, partials, counter, nblocks, bid, red, &total)) sc->pq_part[0] = total;
+}
+
+// launch shape of k_p1_normal_interior for a handle (host); returns false when there is no interior to speak of (a
+// small-mesh axis, or no owned interior plane): k_p1_normal then does everything
+struct P1InteriorPlan {
+  int gx, gy, gz, jchunk, kchunk;
+};
+inline bool p1_plan_interior(const GridDesc& g, const int m[3], const int NT, const long long max_blocks, P1InteriorPlan* out) {
+  const int nc[3] = {g.nx - 1, g.ny - 1, g.nz - 1};
+  for (int a = 0; a < 3; ++a)
+    if (nc[a] == m[a] || nc[a] < 4) return false;
+  const int ni = nc[0] - 3, nj = nc[1] - 3;
+  const int kfirst = g.k0 > 2 ? g.k0 : 2, klast = g.k1 < nc[2] - 1 ? g.k1 : nc[2] - 1;
+  const int nk = klast - kfirst;
+  if (ni < 1 || nj < 1 || nk < 1) return false;
+  P1InteriorPlan pl;
+  pl.jchunk = 8;
+  pl.kchunk = 4;
+  pl.gx = (ni + NT - 1) / NT;
+  for (;;) {
+    pl.gy = (nj + pl.jchunk - 1) / pl.jchunk;
+    pl.gz = (nk + pl.kchunk - 1) / pl.kchunk;
+    if ((long long)pl.gx * pl.gy * pl.gz <= max_blocks) break;
+    pl.jchunk *= 2;
+    pl.kchunk *= 2;
+  }
+  *out = pl;
+  return true;
 }
 
 // diag(R^T R) w^2 + ridge^2 (for the column scaling, LI/_discrete_interpolator.py:815-833)

@@ -17,6 +17,7 @@ for env in "" "LSB200_RING=1" "LSB200_RING=2"; do
   env $env python scripts/prof_slab.py 1024 128 >> gpurun_out/n_slab_1024.txt 2>&1
 done
 # 2. the device tests that have never run: opt-in plans + slab handles on one device, P1 slabs, fault frames / lattice / rows
+for env in "" "LSB200_P1_FAST=1"; do env $env python scripts/p1_experiment.py 117 >> gpurun_out/n_launch_plans.jsonl 2>> gpurun_out/n_launch_plans.err; done
 python -m pytest tests/test_zz_d_ring_gpu.py tests/test_zz_e_p1_slab_gpu.py tests/test_zz_fault_gpu.py -q > gpurun_out/n_pytest_new.txt 2>&1
 # 3. the whole device suite and the bench line (with the "fault" and "launch_plan_experiments" keys)
 python -m pytest tests -q -m gpu > gpurun_out/n_pytest_gpu.txt 2>&1
