@@ -45,7 +45,7 @@ def test_frame_gathers_match_the_reference(tag):
     vals, grad = frame.evaluate(z["points"], gradient_of=1)
     np.testing.assert_array_equal(np.isnan(vals), np.isnan(z["frame_values"]))
     np.testing.assert_allclose(vals, z["frame_values"], rtol=0, atol=1e-11, equal_nan=True)
-    np.testing.assert_allclose(grad, z["frame_gradient1"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(grad, z["frame_gradient1"], rtol=0, atol=1e-12)  # FMA-contracted sums on the device
     vals2, none = frame.evaluate(z["points"], gradient_of=None)
     assert none is None
     np.testing.assert_array_equal(vals2, vals)
