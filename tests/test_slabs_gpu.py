@@ -16,12 +16,25 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_slab_solve_matches_reference(world):
+def _run(world, extras):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
-           "127.0.0.1", "--master-port", str(29600 + world), os.path.join(HERE, "slab_worker.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "127.0.0.1", "--master-port", str(29600 + world + (20 if extras else 0)), os.path.join(HERE, "slab_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, LSB200_SLAB_EXTRAS="1" if extras else "0"))
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "FAIL" not in res.stdout
+    return res.stdout
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_slab_solve_matches_reference(world):
+    _run(world, extras=False)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_slab_evaluation_and_p1_slabs(world):
+    """Replicated-solution evaluation after the slab solve and the P1 / TetMesh twin on slabs (not yet run on GPUs)."""
+    out = _run(world, extras=True)
+    assert "slab evaluate" in out and "P1 slab solve" in out
