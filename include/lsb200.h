@@ -264,6 +264,14 @@ int lsb200_frame_eval(const lsb200_handle fields[3], const double* transforms, i
 int lsb200_fault_displace(const lsb200_handle fields[3], const double* transforms, const lsb200_fault_profile* profile,
                           double displacement, int steps, int64_t n, const double* xyz, double* moved);
 
+/* n_faults faults applied one after the other to the same points (BaseFeature._apply_faults,
+ * LoopStructural/modelling/features/_base_geological_feature.py:252-270): fields holds 3 handles per fault, transforms
+ * 63 doubles per fault (or NULL for all), one profile / displacement / step count per fault.  The points cross the
+ * bus once in each direction, whatever the number of faults. */
+int lsb200_fault_displace_chain(int n_faults, const lsb200_handle* fields, const double* transforms,
+                                const lsb200_fault_profile* profiles, const double* displacements, const int* steps,
+                                int64_t n, const double* xyz, double* moved);
+
 /* FaultSegment.evaluate_displacement (:283-313): d (n) = profile(v0 + fault_offset, v1, v2) * displacement. */
 int lsb200_fault_displacement(const lsb200_handle fields[3], const double* transforms,
                               const lsb200_fault_profile* profile, double displacement, double fault_offset, int64_t n,

@@ -1614,6 +1614,56 @@ int lsb200_fault_displace(const lsb200_handle fields[3], const double* transform
   return rc ? rc : frame_host(fields[0], fc, n, xyz, moved, nullptr);
 }
 
+// A sequence of faults applied one after the other (BaseFeature._apply_faults,
+// LoopStructural/modelling/features/_base_geological_feature.py:252-270): the points go to the device once, every fault
+// is one k_fault_displace launch between two device buffers, the result comes back once.
+int lsb200_fault_displace_chain(int n_faults, const lsb200_handle* fields, const double* transforms,
+                                const lsb200_fault_profile* profiles, const double* displacements, const int* steps, int64_t n,
+                                const double* xyz, double* moved) {
+  if (n_faults < 0 || (n_faults > 0 && (!fields || !profiles || !displacements || !steps))) return fail(LSB200_ERR_ARG, "bad argument");
+  if (n < 0) return fail(LSB200_ERR_ARG, "negative point count");
+  if (n == 0) return 0;
+  if (!xyz || !moved) return fail(LSB200_ERR_ARG, "null argument");
+  if (n_faults == 0) {
+    memcpy(moved, xyz, sizeof(double) * 3 * (size_t)n);
+    return 0;
+  }
+  std::vector<FrameCall> calls((size_t)n_faults);
+  for (int f = 0; f < n_faults; ++f) {
+    FrameCall& fc = calls[f];
+    fc = FrameCall{};
+    fc.what = FRAME_DISPLACE;
+    fc.displacement = displacements[f];
+    fc.steps = steps[f];
+    if (steps[f] < 0) return fail(LSB200_ERR_ARG, "fault %d: negative step count", f);
+    const int rc = frame_prepare(fields + 3 * f, transforms ? transforms + 63 * f : nullptr, profiles + f, true, &fc);
+    if (rc) return rc;
+    if (fields[3 * f]->device != fields[0]->device) return fail(LSB200_ERR_ARG, "the faults of a chain must live on one device");
+  }
+  lsb200_ctx* h = fields[0];
+  CK(cudaSetDevice(h->device));
+  const int64_t chunk = std::min<int64_t>(n, 1 << 24);
+  double* buf[2] = {nullptr, nullptr};
+  CK(cudaMallocAsync(&buf[0], sizeof(double) * 3 * chunk, h->stream));
+  CK(cudaMallocAsync(&buf[1], sizeof(double) * 3 * chunk, h->stream));
+  int rc = 0;
+  for (int64_t o = 0; o < n && !rc; o += chunk) {
+    const int64_t m = std::min<int64_t>(chunk, n - o);
+    CK(cudaMemcpyAsync(buf[0], xyz + 3 * o, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, h->stream));
+    int cur = 0;
+    for (int f = 0; f < n_faults && !rc; ++f) {
+      rc = frame_launch(h, calls[f], m, buf[cur], buf[1 - cur], nullptr, h->stream);
+      cur = 1 - cur;
+    }
+    if (rc) break;
+    CK(cudaMemcpyAsync(moved + 3 * o, buf[cur], sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  pool_free(h, buf[0]);
+  pool_free(h, buf[1]);
+  return rc;
+}
+
 int lsb200_fault_displacement_dev(const lsb200_handle fields[3], const double* transforms,
                                   const lsb200_fault_profile* profile, double displacement, double fault_offset,
                                   int64_t n, const double* xyz_dev, double* d_dev, void* stream) {

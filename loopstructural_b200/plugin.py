@@ -427,6 +427,30 @@ def _make_scalar_field(stock):
     return scalar_field
 
 
+def _make_apply_faults(stock):
+    def _apply_faults(self, evaluation_points, reverse=False):
+        """BaseFeature._apply_faults (LS/modelling/features/_base_geological_feature.py:252-270): two or more faults
+        whose frames were all solved by the engine are applied in one call (lsb200_fault_displace_chain: the points
+        cross the bus once); anything else goes fault by fault through FaultSegment.apply_to_points as before."""
+        from . import fault as fl
+
+        faults = list(getattr(self, "faults", [])) if getattr(self, "faults_enabled", True) else []
+        if len(faults) < 2:
+            return stock(self, evaluation_points, reverse=reverse)
+        frames, profiles = [], []
+        for f in faults:
+            prof = fl.profile_from_reference(getattr(f, "faultfunction", None)) if type(f).__name__ == "FaultSegment" else None
+            frame = _frame_of(f) if prof is not None else None
+            if frame is None:
+                return stock(self, evaluation_points, reverse=reverse)
+            frames.append(frame)
+            profiles.append(prof)
+        return fl.apply_fault_chain(frames, profiles, [float(f.displacement) for f in faults], [int(f.steps) for f in faults],
+                                    np.array(evaluation_points, dtype=float))
+
+    return _apply_faults
+
+
 def _install_feature_patch():
     try:
         from LoopStructural.modelling.features._base_geological_feature import BaseFeature
@@ -434,8 +458,10 @@ def _install_feature_patch():
         return
     if "feature_stock" not in _installed:
         _installed["feature_stock"] = (BaseFeature, BaseFeature.scalar_field)
+        _installed["apply_faults_stock"] = BaseFeature._apply_faults
     cls, stock = _installed["feature_stock"]
     cls.scalar_field = _make_scalar_field(stock)
+    cls._apply_faults = _make_apply_faults(_installed["apply_faults_stock"])
 
 
 def _install_fault_patch():
@@ -488,3 +514,4 @@ def uninstall():
     if "feature_stock" in _installed:
         cls, stock = _installed["feature_stock"]
         cls.scalar_field = stock
+        cls._apply_faults = _installed["apply_faults_stock"]

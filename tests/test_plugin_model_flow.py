@@ -315,3 +315,53 @@ def test_refolded_model_through_the_b200_solver_matches_the_stock_solver(ls):
     assert type(its).__name__ == "DiscreteFoldInterpolator" and its.latest_solve_timing["backend"] == "python"
     cs2 = np.asarray(stock["s2"][0].interpolator.c)
     assert np.linalg.norm(c_frame - cs2) / np.sqrt(cs2.size) / float(cs2.max() - cs2.min()) <= 1e-9  # the unfolded frame
+
+
+def test_two_faults_are_applied_as_one_chain(ls, monkeypatch):
+    """A feature cut by two faults: BaseFeature._apply_faults hands both frames to lsb200_fault_displace_chain in one
+    call (here an oracle stand-in composing the two displacements) and the model's answers equal the stock solver's."""
+    from LoopStructural.datasets import load_intrusion
+
+    from loopstructural_b200 import fault as fl, plugin
+
+    chain_calls = []
+
+    def oracle_chain(frames, profiles, displacements, steps, xyz):
+        chain_calls.append(len(frames))
+        pts = np.array(xyz, dtype=float)
+        for fr, pr, d, s in zip(frames, profiles, displacements, steps):
+            pts = fr.apply_to_points(pts, pr, d, s)
+        return pts
+
+    monkeypatch.setattr(fl, "FaultFrame", OracleFaultFrame)
+    monkeypatch.setattr(fl, "apply_fault_chain", oracle_chain)
+
+    def build(**kw):
+        data, bb = load_intrusion()
+        second = data[data["feature_name"] == "fault"].copy()
+        second["feature_name"] = "fault_b"
+        second["X"] = second["X"] + 0.35 * (bb[1, 0] - bb[0, 0])
+        import pandas as pd
+
+        model = ls.GeologicalModel(bb[0, :], bb[1, :])
+        model.data = pd.concat([data, second], ignore_index=True)
+        model.create_and_add_fault("fault", 300, nelements=1500, interpolatortype="FDI", buffer=0.3, **kw)
+        model.create_and_add_fault("fault_b", -200, nelements=1500, interpolatortype="FDI", buffer=0.3, **kw)
+        model.create_and_add_foliation("strati", nelements=1500, interpolatortype="FDI", **kw)
+        model.update()
+        return model, bb
+
+    model, bb = build(solver="b200")
+    assert len(model["strati"].faults) == 2
+    rng = np.random.default_rng(6)
+    pts = bb[0] + rng.uniform(0, 1, (300, 3)) * (bb[1] - bb[0])
+    val = model.evaluate_feature_value("strati", pts)
+    assert chain_calls and set(chain_calls) == {2}  # (the builder un-faults its data fault by fault; evaluation chains)
+    plugin.uninstall()
+    stock, _ = build()
+    assert type(stock["strati"])._apply_faults.__qualname__ == "BaseFeature._apply_faults"
+    ref = stock.evaluate_feature_value("strati", pts)
+    np.testing.assert_array_equal(np.isnan(val), np.isnan(ref))
+    # seven coupled solves (two fault frames, then the foliation on data moved through both), each stopped at the
+    # default tolerance: the fields agree to a few 1e-6 of the range
+    np.testing.assert_allclose(val, ref, rtol=0, atol=2e-5 * float(np.nanmax(ref) - np.nanmin(ref)), equal_nan=True)

@@ -263,3 +263,24 @@ def test_fault_frame_on_a_tet_mesh_matches_the_reference(tag):
     np.testing.assert_allclose(d, z["displacement_at"], rtol=1e-12, atol=1e-12 * abs(disp))
     for e in engines:
         e.close()
+
+
+def test_fault_chain_equals_the_faults_applied_one_by_one():
+    """lsb200_fault_displace_chain (two frames from the golden fixtures, different profiles) against two separate
+    lsb200_fault_displace calls: same bits, one transfer."""
+    from loopstructural_b200 import fault as fl
+
+    za = np.load(os.path.join(GOLDEN, "fault_base.npz"))
+    zb = np.load(os.path.join(GOLDEN, "fault_wide.npz"))
+    fa_, ea = _frame(za)
+    fb_, eb = _frame(zb)
+    pa, pb = _profile(za), _profile(zb)
+    pts = za["points"]
+    one = fa_.apply_to_points(pts, pa, float(za["displacement"]), int(za["steps"]))
+    two = fb_.apply_to_points(one, pb, float(zb["displacement"]), int(zb["steps"]))
+    chain = fl.apply_fault_chain([fa_, fb_], [pa, pb], [float(za["displacement"]), float(zb["displacement"])],
+                                 [int(za["steps"]), int(zb["steps"])], pts)
+    np.testing.assert_array_equal(chain, two)
+    np.testing.assert_array_equal(fl.apply_fault_chain([], [], [], [], pts), pts)
+    for e in ea + eb:
+        e.close()
