@@ -272,6 +272,16 @@ int lsb200_fault_displace_chain(int n_faults, const lsb200_handle* fields, const
                                 const lsb200_fault_profile* profiles, const double* displacements, const int* steps,
                                 int64_t n, const double* xyz, double* moved);
 
+/* Evaluation of a faulted feature in one call: the chain above, then the value (gradient == 0: out is (n)) or the
+ * world-axis gradient (gradient != 0: out is (n,3)) of `field` at the moved points, which never leave the device
+ * (GeologicalFeature.evaluate_value: _apply_faults then interpolator.evaluate_value,
+ * LoopStructural/modelling/features/_geological_feature.py:116-157; evaluate_gradient of an unfaulted interpolator at
+ * faulted points, :231-236).  field_transform: 21 doubles as in lsb200_frame_eval or NULL.  n_faults may be 0. */
+int lsb200_faulted_eval(int n_faults, const lsb200_handle* fields, const double* transforms,
+                        const lsb200_fault_profile* profiles, const double* displacements, const int* steps,
+                        lsb200_handle field, const double* field_transform, int gradient, int64_t n, const double* xyz,
+                        double* out);
+
 /* FaultSegment.evaluate_displacement (:283-313): d (n) = profile(v0 + fault_offset, v1, v2) * displacement. */
 int lsb200_fault_displacement(const lsb200_handle fields[3], const double* transforms,
                               const lsb200_fault_profile* profile, double displacement, double fault_offset, int64_t n,

@@ -96,6 +96,8 @@ SIGNATURES = {
     "lsb200_fault_displace": (C.c_int, [_Handle3, c_double_p, _ProfileP, C.c_double, C.c_int, C.c_int64, c_double_p, c_double_p]),
     "lsb200_fault_displace_chain": (C.c_int, [C.c_int, _Handle3, c_double_p, _ProfileP, c_double_p, C.POINTER(C.c_int), C.c_int64,
                                              c_double_p, c_double_p]),
+    "lsb200_faulted_eval": (C.c_int, [C.c_int, _Handle3, c_double_p, _ProfileP, c_double_p, C.POINTER(C.c_int), Handle, c_double_p,
+                                     C.c_int, C.c_int64, c_double_p, c_double_p]),
     "lsb200_fault_displacement": (C.c_int, [_Handle3, c_double_p, _ProfileP, C.c_double, C.c_double, C.c_int64, c_double_p, c_double_p]),
     "lsb200_frame_eval_dev": (C.c_int, [_Handle3, c_double_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lsb200_fault_displace_dev": (C.c_int, [_Handle3, c_double_p, _ProfileP, C.c_double, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

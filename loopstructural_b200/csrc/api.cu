@@ -1616,16 +1616,19 @@ int lsb200_fault_displace(const lsb200_handle fields[3], const double* transform
 
 // A sequence of faults applied one after the other (BaseFeature._apply_faults,
 // LoopStructural/modelling/features/_base_geological_feature.py:252-270): the points go to the device once, every fault
-// is one k_fault_displace launch between two device buffers, the result comes back once.
-int lsb200_fault_displace_chain(int n_faults, const lsb200_handle* fields, const double* transforms,
-                                const lsb200_fault_profile* profiles, const double* displacements, const int* steps, int64_t n,
-                                const double* xyz, double* moved) {
+// is one k_fault_displace launch between two device buffers, the result comes back once.  With `field` != NULL the moved
+// points never come back: the field is evaluated at them on the device (GeologicalFeature.evaluate_value /
+// evaluate_gradient of a faulted feature, LS/modelling/features/_geological_feature.py:116-157,231-236) and only the
+// values (n) or world gradients (n,3) are returned.
+static int fault_chain(int n_faults, const lsb200_handle* fields, const double* transforms, const lsb200_fault_profile* profiles,
+                       const double* displacements, const int* steps, lsb200_handle field, const double* field_transform,
+                       int gradient, int64_t n, const double* xyz, double* out) {
   if (n_faults < 0 || (n_faults > 0 && (!fields || !profiles || !displacements || !steps))) return fail(LSB200_ERR_ARG, "bad argument");
   if (n < 0) return fail(LSB200_ERR_ARG, "negative point count");
   if (n == 0) return 0;
-  if (!xyz || !moved) return fail(LSB200_ERR_ARG, "null argument");
-  if (n_faults == 0) {
-    memcpy(moved, xyz, sizeof(double) * 3 * (size_t)n);
+  if (!xyz || !out) return fail(LSB200_ERR_ARG, "null argument");
+  if (n_faults == 0 && !field) {
+    memcpy(out, xyz, sizeof(double) * 3 * (size_t)n);
     return 0;
   }
   std::vector<FrameCall> calls((size_t)n_faults);
@@ -1638,14 +1641,24 @@ int lsb200_fault_displace_chain(int n_faults, const lsb200_handle* fields, const
     if (steps[f] < 0) return fail(LSB200_ERR_ARG, "fault %d: negative step count", f);
     const int rc = frame_prepare(fields + 3 * f, transforms ? transforms + 63 * f : nullptr, profiles + f, true, &fc);
     if (rc) return rc;
-    if (fields[3 * f]->device != fields[0]->device) return fail(LSB200_ERR_ARG, "the faults of a chain must live on one device");
   }
-  lsb200_ctx* h = fields[0];
+  FrameField F{};
+  if (field) {
+    const int rc = make_frame_field(field, field_transform, "evaluated field", 0, &F);
+    if (rc) return rc;
+  }
+  lsb200_ctx* h = n_faults > 0 ? fields[0] : field;
+  for (int f = 0; f < n_faults; ++f)
+    if (fields[3 * f]->device != h->device) return fail(LSB200_ERR_ARG, "the faults of a chain must live on one device");
+  if (field && field->device != h->device) return fail(LSB200_ERR_ARG, "the evaluated field lives on another device than the faults");
   CK(cudaSetDevice(h->device));
   const int64_t chunk = std::min<int64_t>(n, 1 << 24);
+  const int ow = field ? (gradient ? 3 : 1) : 3;
   double* buf[2] = {nullptr, nullptr};
+  double* res = nullptr;
   CK(cudaMallocAsync(&buf[0], sizeof(double) * 3 * chunk, h->stream));
   CK(cudaMallocAsync(&buf[1], sizeof(double) * 3 * chunk, h->stream));
+  if (field) CK(cudaMallocAsync(&res, sizeof(double) * ow * chunk, h->stream));
   int rc = 0;
   for (int64_t o = 0; o < n && !rc; o += chunk) {
     const int64_t m = std::min<int64_t>(chunk, n - o);
@@ -1656,12 +1669,35 @@ int lsb200_fault_displace_chain(int n_faults, const lsb200_handle* fields, const
       cur = 1 - cur;
     }
     if (rc) break;
-    CK(cudaMemcpyAsync(moved + 3 * o, buf[cur], sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, h->stream));
+    const double* src = buf[cur];
+    if (field) {
+      const int nb = frame_blocks(h, m);
+      if (F.kind == LSB200_SUPPORT_TETMESH) k_field_eval<true><<<nb, 256, 0, h->stream>>>(F, gradient ? 1 : 0, m, buf[cur], res);
+      else k_field_eval<false><<<nb, 256, 0, h->stream>>>(F, gradient ? 1 : 0, m, buf[cur], res);
+      CKL();
+      h->launches++;
+      src = res;
+    }
+    CK(cudaMemcpyAsync(out + ow * o, src, sizeof(double) * ow * m, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
   pool_free(h, buf[0]);
   pool_free(h, buf[1]);
+  pool_free(h, res);
   return rc;
+}
+
+int lsb200_fault_displace_chain(int n_faults, const lsb200_handle* fields, const double* transforms,
+                                const lsb200_fault_profile* profiles, const double* displacements, const int* steps, int64_t n,
+                                const double* xyz, double* moved) {
+  return fault_chain(n_faults, fields, transforms, profiles, displacements, steps, nullptr, nullptr, 0, n, xyz, moved);
+}
+
+int lsb200_faulted_eval(int n_faults, const lsb200_handle* fields, const double* transforms, const lsb200_fault_profile* profiles,
+                        const double* displacements, const int* steps, lsb200_handle field, const double* field_transform,
+                        int gradient, int64_t n, const double* xyz, double* out) {
+  if (!field) return fail(LSB200_ERR_ARG, "null field handle");
+  return fault_chain(n_faults, fields, transforms, profiles, displacements, steps, field, field_transform, gradient, n, xyz, out);
 }
 
 int lsb200_fault_displacement_dev(const lsb200_handle fields[3], const double* transforms,

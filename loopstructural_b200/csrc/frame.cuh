@@ -354,6 +354,26 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// value (n) or world gradient (n,3) of ONE field at world points that are already on the device (the tail of a fault
+// chain: GeologicalFeature.evaluate_value / evaluate_gradient after _apply_faults)
+template <bool TET>
+__global__ void __launch_bounds__(256)
+    k_field_eval(const FrameField F, const int gradient, const long long n, const double* __restrict__ xyz,
+                 double* __restrict__ out) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    const double x[3] = {xyz[3 * r], xyz[3 * r + 1], xyz[3 * r + 2]};
+    double g[3];
+    const double v = frame_field_at<TET>(F, x, gradient ? g : nullptr);
+    if (gradient) {
+      out[3 * r] = g[0];
+      out[3 * r + 1] = g[1];
+      out[3 * r + 2] = g[2];
+    } else {
+      out[r] = v;
+    }
+  }
+}
+
 template <bool TET>
 __global__ void __launch_bounds__(256)
     k_fault_displace(const FrameFields FF, const FaultProfile P, const double displacement, const int steps,

@@ -169,6 +169,36 @@ class FaultFrame:
                                                           C.c_void_p(out_ptr), C.c_void_p(stream)))
 
 
+def _chain_args(frames, profiles, displacements, steps):
+    nf = len(frames)
+    if not (len(profiles) == len(displacements) == len(steps) == nf):
+        raise ValueError("one profile, displacement and step count per fault")
+    handles = (nat.Handle * max(3 * nf, 1))(*[h for fr in frames for h in fr._handles])
+    if any(fr._transforms is not None for fr in frames):
+        tr = np.ascontiguousarray(np.concatenate([fr._transforms if fr._transforms is not None else
+                                                  np.concatenate([transform_rows(None)] * 3) for fr in frames]))
+    else:
+        tr = None
+    profs = (nat.FaultProfile * max(nf, 1))(*profiles)
+    disp = np.ascontiguousarray(list(displacements) or [0.0], dtype=np.float64)
+    st = (C.c_int * max(nf, 1))(*[int(s) for s in steps])
+    return nf, handles, tr, profs, disp, st
+
+
+def faulted_evaluate(frames, profiles, displacements, steps, engine, xyz, gradient: bool = False, world_to_local=None):
+    """GeologicalFeature.evaluate_value / evaluate_gradient of a faulted feature in one call: the fault chain, then
+    ``engine``'s field at the moved points, which stay on the device (lsb200_faulted_eval)."""
+    frames = list(frames)
+    xyz = FaultFrame._points(xyz)
+    nf, handles, tr, profs, disp, st = _chain_args(frames, profiles, displacements, steps)
+    ftr = None if world_to_local is None else np.ascontiguousarray(transform_rows(world_to_local))
+    out = np.empty((xyz.shape[0], 3) if gradient else xyz.shape[0])
+    nat.check(nat.load().lsb200_faulted_eval(nf, handles, None if tr is None else nat.dptr(tr), profs, nat.dptr(disp), st, engine._h,
+                                             None if ftr is None else nat.dptr(ftr), int(gradient), xyz.shape[0], nat.dptr(xyz),
+                                             nat.dptr(out)))
+    return out
+
+
 def apply_fault_chain(frames, profiles, displacements, steps, xyz) -> np.ndarray:
     """Several faults one after the other on the same points (BaseFeature._apply_faults,
     LoopStructural/modelling/features/_base_geological_feature.py:252-270) with one transfer of the points in each

@@ -339,13 +339,13 @@ def _make_fault_methods(stock_apply, stock_displacement):
     return apply_to_points, evaluate_displacement
 
 
-def _solved_grid_field(feature, kinds=("grid",)):
+def _solved_grid_field(feature, kinds=("grid",), allow_faults=False):
     """(engine, world_to_local) of a plain interpolated feature solved by the engine on one of ``kinds``, else None.
     (Orthogonality rows take grid sources only: outside a tet mesh the gradient is NaN and the reference then drops the
     WHOLE family, LI/_discrete_interpolator.py:357-359 -- left to the stock method.)"""
     if type(feature).__name__ != "GeologicalFeature":
         return None
-    if getattr(feature, "faults_enabled", True) and len(getattr(feature, "faults", [])) > 0:
+    if not allow_faults and getattr(feature, "faults_enabled", True) and len(getattr(feature, "faults", [])) > 0:
         return None
     if getattr(feature, "builder", None) is not None:
         feature.builder.up_to_date()
@@ -427,6 +427,52 @@ def _make_scalar_field(stock):
     return scalar_field
 
 
+def _fault_chain_of(feature):
+    """(frames, profiles, displacements, steps) of the faults that cut ``feature`` when every one of them can run on the
+    engine, else None."""
+    from . import fault as fl
+
+    faults = list(getattr(feature, "faults", [])) if getattr(feature, "faults_enabled", True) else []
+    frames, profiles = [], []
+    for f in faults:
+        prof = fl.profile_from_reference(getattr(f, "faultfunction", None)) if type(f).__name__ == "FaultSegment" else None
+        frame = _frame_of(f) if prof is not None else None
+        if frame is None:
+            return None
+        frames.append(frame)
+        profiles.append(prof)
+    return frames, profiles, [float(f.displacement) for f in faults], [int(f.steps) for f in faults]
+
+
+def _make_evaluate_value(stock):
+    def evaluate_value(self, pos, ignore_regions=False, fillnan=None):
+        """GeologicalFeature.evaluate_value (LS/modelling/features/_geological_feature.py:116-157) of a FAULTED feature
+        in one device call (lsb200_faulted_eval: fault chain, then the field at the moved points, which never come back
+        to the host) when the feature and the frames of all its faults were solved by the engine; the stock method in
+        every other case (no faults, fillnan, other feature types)."""
+        if fillnan is not None or type(self).__name__ != "GeologicalFeature" or np.ndim(pos) != 2 or np.shape(pos)[1] != 3:
+            return stock(self, pos, ignore_regions=ignore_regions, fillnan=fillnan)
+        if not (getattr(self, "faults_enabled", True) and len(getattr(self, "faults", [])) > 0):
+            return stock(self, pos, ignore_regions=ignore_regions, fillnan=fillnan)
+        src = _solved_grid_field(self, kinds=("grid", "tetmesh"), allow_faults=True)
+        chain = _fault_chain_of(self) if src is not None else None
+        if chain is None:
+            return stock(self, pos, ignore_regions=ignore_regions, fillnan=fillnan)
+        from . import fault as fl
+
+        pts = np.array(pos, dtype=float)
+        mask = self._calculate_mask(pos, ignore_regions=ignore_regions)
+        v = np.full(pts.shape[0], np.nan)
+        if mask.dtype not in [int, bool]:
+            return v  # the reference logs an error and returns NaN (:146-147)
+        val = fl.faulted_evaluate(*chain, src[0], pts, gradient=False, world_to_local=src[1])
+        keep = mask.astype(bool)
+        v[keep] = val[keep]
+        return v
+
+    return evaluate_value
+
+
 def _make_apply_faults(stock):
     def _apply_faults(self, evaluation_points, reverse=False):
         """BaseFeature._apply_faults (LS/modelling/features/_base_geological_feature.py:252-270): two or more faults
@@ -434,19 +480,12 @@ def _make_apply_faults(stock):
         cross the bus once); anything else goes fault by fault through FaultSegment.apply_to_points as before."""
         from . import fault as fl
 
-        faults = list(getattr(self, "faults", [])) if getattr(self, "faults_enabled", True) else []
-        if len(faults) < 2:
+        if not getattr(self, "faults_enabled", True) or len(getattr(self, "faults", [])) < 2:
             return stock(self, evaluation_points, reverse=reverse)
-        frames, profiles = [], []
-        for f in faults:
-            prof = fl.profile_from_reference(getattr(f, "faultfunction", None)) if type(f).__name__ == "FaultSegment" else None
-            frame = _frame_of(f) if prof is not None else None
-            if frame is None:
-                return stock(self, evaluation_points, reverse=reverse)
-            frames.append(frame)
-            profiles.append(prof)
-        return fl.apply_fault_chain(frames, profiles, [float(f.displacement) for f in faults], [int(f.steps) for f in faults],
-                                    np.array(evaluation_points, dtype=float))
+        chain = _fault_chain_of(self)
+        if chain is None:
+            return stock(self, evaluation_points, reverse=reverse)
+        return fl.apply_fault_chain(*chain, np.array(evaluation_points, dtype=float))
 
     return _apply_faults
 
@@ -462,6 +501,14 @@ def _install_feature_patch():
     cls, stock = _installed["feature_stock"]
     cls.scalar_field = _make_scalar_field(stock)
     cls._apply_faults = _make_apply_faults(_installed["apply_faults_stock"])
+    try:
+        from LoopStructural.modelling.features._geological_feature import GeologicalFeature
+    except Exception:
+        return
+    if "evaluate_value_stock" not in _installed:
+        _installed["evaluate_value_stock"] = (GeologicalFeature, GeologicalFeature.evaluate_value)
+    gcls, gstock = _installed["evaluate_value_stock"]
+    gcls.evaluate_value = _make_evaluate_value(gstock)
 
 
 def _install_fault_patch():
@@ -515,3 +562,6 @@ def uninstall():
         cls, stock = _installed["feature_stock"]
         cls.scalar_field = stock
         cls._apply_faults = _installed["apply_faults_stock"]
+    if "evaluate_value_stock" in _installed:
+        gcls, gstock = _installed["evaluate_value_stock"]
+        gcls.evaluate_value = gstock

@@ -202,6 +202,21 @@ class OracleFaultFrame:
         return self.fa.evaluate_displacement(self.fields, self._profile(profile), displacement, fault_offset, xyz)
 
 
+eval_calls = []
+
+
+def oracle_faulted_evaluate(frames, profiles, displacements, steps, engine, xyz, gradient=False, world_to_local=None):
+    """Stand-in for loopstructural_b200.fault.faulted_evaluate (fault chain, then the field at the moved points)."""
+    from oracle import fault_oracle as fa
+
+    eval_calls.append(len(frames))
+    pts = np.array(xyz, dtype=float)
+    for fr, pr, d, s in zip(frames, profiles, displacements, steps):
+        pts = fa.apply_to_points(fr.fields, fr._profile(pr), d, s, pts)
+    fld = fa.FrameField(engine.grid, engine.c, world_to_local, engine.kind)
+    return fld.gradient(pts) if gradient else fld.value(pts)
+
+
 def _fault_model(ls, **kw):
     from LoopStructural.datasets import load_intrusion
 
@@ -220,7 +235,9 @@ def test_fault_frame_and_faulted_foliation_through_the_model(ls, monkeypatch):
     from loopstructural_b200 import fault as fl, plugin
 
     monkeypatch.setattr(fl, "FaultFrame", OracleFaultFrame)
+    monkeypatch.setattr(fl, "faulted_evaluate", oracle_faulted_evaluate)
     OracleFaultFrame.calls.clear()
+    eval_calls.clear()
     model, bb = _fault_model(ls, solver="b200")
     fault = model["fault"]
     for i in range(3):
@@ -237,7 +254,8 @@ def test_fault_frame_and_faulted_foliation_through_the_model(ls, monkeypatch):
     moved = fault.apply_to_points(pts)
     disp = fault.evaluate_displacement(pts)
     strati = model.evaluate_feature_value("strati", pts)
-    assert OracleFaultFrame.calls.count("apply") >= 2 and "displacement" in OracleFaultFrame.calls
+    assert OracleFaultFrame.calls.count("apply") >= 1 and "displacement" in OracleFaultFrame.calls
+    assert eval_calls == [1]  # the faulted foliation: fault + field in one call
     c_frame = [np.array(fault[i].interpolator.c) for i in range(3)]
 
     # an unsupported profile goes back to the stock method
@@ -335,6 +353,8 @@ def test_two_faults_are_applied_as_one_chain(ls, monkeypatch):
 
     monkeypatch.setattr(fl, "FaultFrame", OracleFaultFrame)
     monkeypatch.setattr(fl, "apply_fault_chain", oracle_chain)
+    monkeypatch.setattr(fl, "faulted_evaluate", oracle_faulted_evaluate)
+    eval_calls.clear()
 
     def build(**kw):
         data, bb = load_intrusion()
@@ -356,10 +376,14 @@ def test_two_faults_are_applied_as_one_chain(ls, monkeypatch):
     rng = np.random.default_rng(6)
     pts = bb[0] + rng.uniform(0, 1, (300, 3)) * (bb[1] - bb[0])
     val = model.evaluate_feature_value("strati", pts)
-    assert chain_calls and set(chain_calls) == {2}  # (the builder un-faults its data fault by fault; evaluation chains)
+    # evaluate_value of the faulted foliation: fault chain + field in ONE call; the chain alone serves _apply_faults
+    assert eval_calls == [2]
+    moved = model["strati"]._apply_faults(pts)
+    assert chain_calls == [2] and np.abs(moved - pts).max() > 1.0
     plugin.uninstall()
     stock, _ = build()
     assert type(stock["strati"])._apply_faults.__qualname__ == "BaseFeature._apply_faults"
+    assert type(stock["strati"]).evaluate_value.__qualname__ == "GeologicalFeature.evaluate_value"
     ref = stock.evaluate_feature_value("strati", pts)
     np.testing.assert_array_equal(np.isnan(val), np.isnan(ref))
     # seven coupled solves (two fault frames, then the foliation on data moved through both), each stopped at the

@@ -284,3 +284,28 @@ def test_fault_chain_equals_the_faults_applied_one_by_one():
     np.testing.assert_array_equal(fl.apply_fault_chain([], [], [], [], pts), pts)
     for e in ea + eb:
         e.close()
+
+
+def test_faulted_evaluation_in_one_call():
+    """lsb200_faulted_eval (fault chain, then a field at the moved points, all on the device) against the same thing done
+    in pieces through the entry points checked above, for 0, 1 and 2 faults, value and gradient."""
+    from loopstructural_b200 import fault as fl
+
+    za = np.load(os.path.join(GOLDEN, "fault_base.npz"))
+    zb = np.load(os.path.join(GOLDEN, "fault_wide.npz"))
+    fa_, ea = _frame(za)
+    fb_, eb = _frame(zb)
+    pa, pb = _profile(za), _profile(zb)
+    pts = za["points"]
+    field, w2l = ea[2], za["f2_w2l"]  # any solved handle serves as the evaluated feature
+    args = ([fa_, fb_], [pa, pb], [float(za["displacement"]), float(zb["displacement"])], [int(za["steps"]), int(zb["steps"])])
+    for nf in (0, 1, 2):
+        sub = tuple(a[:nf] for a in args)
+        moved = fl.apply_fault_chain(*sub, pts)
+        local = moved @ w2l[:3, :3].T + w2l[:3, 3]
+        v = fl.faulted_evaluate(*sub, field, pts, gradient=False, world_to_local=w2l)
+        np.testing.assert_array_equal(v, field.evaluate_value(local))
+        g = fl.faulted_evaluate(*sub, field, pts, gradient=True, world_to_local=w2l)
+        np.testing.assert_array_equal(g, field.evaluate_gradient(local))  # identity rotation: local axes = world axes
+    for e in ea + eb:
+        e.close()
