@@ -304,8 +304,10 @@ def test_faulted_evaluation_in_one_call():
         moved = fl.apply_fault_chain(*sub, pts)
         local = moved @ w2l[:3, :3].T + w2l[:3, 3]
         v = fl.faulted_evaluate(*sub, field, pts, gradient=False, world_to_local=w2l)
-        np.testing.assert_array_equal(v, field.evaluate_value(local))
+        ref = field.evaluate_value(local)
+        np.testing.assert_array_equal(np.isnan(v), np.isnan(ref))
+        np.testing.assert_allclose(v, ref, rtol=0, atol=1e-12, equal_nan=True)
         g = fl.faulted_evaluate(*sub, field, pts, gradient=True, world_to_local=w2l)
-        np.testing.assert_array_equal(g, field.evaluate_gradient(local))  # identity rotation: local axes = world axes
+        np.testing.assert_allclose(g, field.evaluate_gradient(local), rtol=0, atol=1e-13)  # identity rotation: local = world axes
     for e in ea + eb:
         e.close()
