@@ -263,6 +263,12 @@ def measure_fault(local, n_nodes=128, npts=10_000_000, steps=10, cpu_points=100_
     lat = torch.empty(nl ** 3, dtype=torch.float64, device=dev)
     t_lat = timed(lambda: engines[0].evaluate_lattice(np.zeros(3), np.ones(3), (nl, nl, nl), "F", out_ptr=lat.data_ptr(), stream=st), reps=3)
     del lat
+    # a faulted feature evaluated through the host-array entry point (fault + field in one call, 24 B/pt in, 8 B/pt out)
+    host_pts = cloud[:2_000_000].cpu().numpy()
+    fl.faulted_evaluate([frame], [prof], [0.05], [steps], engines[2], host_pts[:1000])
+    t0 = time.perf_counter()
+    fl.faulted_evaluate([frame], [prof], [0.05], [steps], engines[2], host_pts)
+    t_feval = time.perf_counter() - t0
     sample = cloud[:cpu_points].cpu().numpy()
     moved = out[:cpu_points].cpu().numpy()
     fields = [fa.FrameField(grid, c, None) for c in cs]
@@ -276,6 +282,7 @@ def measure_fault(local, n_nodes=128, npts=10_000_000, steps=10, cpu_points=100_
     return {"workload": f"3 x {n_nodes}^3 fields, {npts} device-resident points, {steps} steps, cubic/ones/smooth_peak profile",
             "displace_points_per_second": npts / t_move, "displace_seconds": t_move,
             "frame_eval_points_per_second": npts / t_eval,
+            "faulted_eval_points_per_second_host_arrays": len(host_pts) / t_feval,
             "lattice_points_per_second": nl ** 3 / t_lat, "lattice_gbs_written": 8 * nl ** 3 / t_lat / 1e9,
             "moved_fraction": float((np.abs(moved - sample).max(axis=1) > 0).mean()),
             "max_abs_diff_vs_oracle_sample": float(np.abs(moved - ref).max()),
