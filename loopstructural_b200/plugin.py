@@ -148,6 +148,38 @@ class _B200Mixin:
             return None
         return self._b200_engine
 
+    def _b200_world_to_local(self):
+        bb = getattr(self, "bounding_box", None)
+        return None if bb is None else np.asarray(bb.world_to_local_matrix, dtype=float)
+
+    def evaluate_value(self, locations):
+        """GeologicalInterpolator.evaluate_value (LI/_geological_interpolator.py:723-730) with the world -> local
+        projection on the device: the reference builds an (N,4) homogeneous copy of the points and multiplies it by
+        the 4 x 4 matrix on the host (BoundingBox._apply_affine, LC/geometry/_bounding_box.py:154-176) before every
+        evaluation; lsb200_faulted_eval with no faults takes the world points and the matrix."""
+        self.update()
+        eng = self._b200_engine_current()
+        locations = np.asarray(locations, dtype=np.float64)
+        if eng is None or locations.ndim != 2 or locations.shape[1] != 3:
+            return super().evaluate_value(locations)
+        from . import fault as fl
+
+        return fl.faulted_evaluate([], [], [], [], eng, locations, gradient=False, world_to_local=self._b200_world_to_local())
+
+    def evaluate_gradient(self, locations):
+        """GeologicalInterpolator.evaluate_gradient (:732-741): projection, gather and the rotation of the gradients back
+        to world axes (reproject_vectors) in one device call."""
+        self.update()
+        eng = self._b200_engine_current()
+        locations = np.asarray(locations, dtype=np.float64)
+        if eng is None or locations.ndim != 2 or locations.shape[1] != 3:
+            return super().evaluate_gradient(locations)
+        if locations.shape[0] == 0:
+            return np.zeros((0, 3))
+        from . import fault as fl
+
+        return fl.faulted_evaluate([], [], [], [], eng, locations, gradient=True, world_to_local=self._b200_world_to_local())
+
     def _evaluate_value_local(self, locations):
         self.update()
         eng = self._b200_engine_current()
