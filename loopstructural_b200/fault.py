@@ -207,21 +207,8 @@ def apply_fault_chain(frames, profiles, displacements, steps, xyz) -> np.ndarray
     xyz = FaultFrame._points(xyz)
     if not frames:
         return xyz.copy()
-    nf = len(frames)
-    if not (len(profiles) == len(displacements) == len(steps) == nf):
-        raise ValueError("one profile, displacement and step count per fault")
-    handles = (nat.Handle * (3 * nf))(*[h for fr in frames for h in fr._handles])
-    have_tr = [fr._transforms is not None for fr in frames]
-    if any(have_tr):
-        tr = np.ascontiguousarray(np.concatenate([fr._transforms if fr._transforms is not None else
-                                                  np.concatenate([transform_rows(None)] * 3) for fr in frames]))
-        trp = nat.dptr(tr)
-    else:
-        trp = None
-    profs = (nat.FaultProfile * nf)(*profiles)
-    disp = np.ascontiguousarray(displacements, dtype=np.float64)
-    st = (C.c_int * nf)(*[int(s) for s in steps])
+    nf, handles, tr, profs, disp, st = _chain_args(frames, profiles, displacements, steps)
     out = np.empty_like(xyz)
-    nat.check(nat.load().lsb200_fault_displace_chain(nf, handles, trp, profs, nat.dptr(disp), st, xyz.shape[0], nat.dptr(xyz),
-                                                     nat.dptr(out)))
+    nat.check(nat.load().lsb200_fault_displace_chain(nf, handles, None if tr is None else nat.dptr(tr), profs, nat.dptr(disp), st,
+                                                     xyz.shape[0], nat.dptr(xyz), nat.dptr(out)))
     return out

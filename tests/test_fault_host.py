@@ -77,3 +77,27 @@ def test_profiles_of_the_reference_objects_translate_and_evaluate_alike():
     assert fl.profile_from_reference(lambda gx, gy, gz: gx) is None
     assert fl.profile_from_reference(ff.FaultDisplacement(gx=ff.Ones(), gy=np.tanh, gz=ff.Ones())) is None
     assert fl.profile_from_reference(ff.FaultDisplacement(hw=ff.Ones(), fw=np.tanh)) is None
+
+
+def test_chain_argument_packing():
+    """Host packing for lsb200_fault_displace_chain / lsb200_faulted_eval: 3 handles and 63 transform doubles per fault in
+    fault order, identity rows for a frame without transforms when another one has them, placeholders for no faults."""
+    class Frame:
+        def __init__(self, base, transforms):
+            self._handles = (nat.Handle * 3)(nat.Handle(base), nat.Handle(base + 1), nat.Handle(base + 2))
+            self._transforms = transforms
+
+    w2l = np.eye(4)
+    w2l[:3, 3] = [1.0, 2.0, 3.0]
+    t = np.concatenate([fl.transform_rows(w2l)] * 3)
+    frames = [Frame(10, None), Frame(20, t)]
+    profs = [fl.fault_profile(None), fl.fault_profile([fl.profile1d(fl.PROFILE_ONES)] * 3, 0.25)]
+    nf, handles, tr, parr, disp, st = fl._chain_args(frames, profs, [1.5, -2.0], [4, 7])
+    assert nf == 2 and [handles[i] for i in range(6)] == [10, 11, 12, 20, 21, 22]
+    assert tr.shape == (126,) and np.array_equal(tr[63:], t)
+    np.testing.assert_array_equal(tr[:21], fl.transform_rows(None))
+    assert parr[0].has_function == 0 and parr[1].scale == 0.25 and list(disp) == [1.5, -2.0] and list(st) == [4, 7]
+    nf, handles, tr, parr, disp, st = fl._chain_args([], [], [], [])
+    assert nf == 0 and tr is None and len(handles) == 1 and len(parr) == 1 and len(st) == 1
+    with pytest.raises(ValueError):
+        fl._chain_args(frames, profs, [1.0], [4, 7])
