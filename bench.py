@@ -128,7 +128,8 @@ def measured_peak():
 
 # ------------------------------------------------------------------------------------------ reference arm
 def cpu_reference_step(n, n_value, n_gradient, seed=0):
-    """One solve of the scipy path (oracle port of the reference's default solve) on a bounded sample."""
+    """One solve of the scipy path (oracle port of the reference's default solve) on a bounded sample.  Only used when
+    the reference itself is not installed under baseline/_ref (kind "port")."""
     from oracle import fdi_oracle as fo
 
     grid, value, gradient = fo.synthetic_problem(n, n_value, n_gradient, seed=seed)
@@ -141,35 +142,152 @@ def cpu_reference_step(n, n_value, n_gradient, seed=0):
     return grid.n_nodes, res.iterations, dt, timing
 
 
+def reference_step(n, n_value, n_gradient, seed=0):
+    """One step of the workload through the UNMODIFIED reference (baseline/_ref, see baseline/install_reference.sh):
+    StructuredGrid + FiniteDifferenceInterpolator.setup_interpolator() + solve_system('cg') -- the stock code path of
+    LI/_discrete_interpolator.py:1221-1319 / LI/_solver_strategy.py:48-71 -- on an n^3-node sample of the synthetic
+    problem.  Returns (dof, iterations, seconds, timing dict of the reference)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refenv
+
+    if refenv.activate() is None:
+        raise RuntimeError("reference not installed")
+    from loop_common.supports import StructuredGrid
+    from loop_interpolation import FiniteDifferenceInterpolator
+
+    value, gradient = synthetic_points(n_value, n_gradient, seed=seed)
+    t0 = time.perf_counter()
+    sg = StructuredGrid(origin=np.zeros(3), nsteps_cells=np.array([n - 1] * 3), step_vector=np.full(3, 1.0 / (n - 1)))
+    it = FiniteDifferenceInterpolator(sg)
+    it.set_value_constraints(value)
+    it.set_gradient_constraints(gradient)
+    it.setup_interpolator()
+    setup_s = time.perf_counter() - t0
+    count = [0]
+
+    def callback(_x):
+        count[0] += 1
+
+    ok = it.solve_system("cg", solver_kwargs={"callback": callback})
+    dt = time.perf_counter() - t0
+    if not ok or it.latest_solve_timing.get("backend") != "python" or not np.all(np.isfinite(it.c)):
+        raise RuntimeError("reference solve failed")
+    timing = dict(it.latest_solve_timing)
+    timing["setup_seconds"] = setup_s
+    return int(it.dof), int(count[0]), dt, timing
+
+
+def _sample_counts(n):
+    return max(100, int(1e5 * (n / 256.0) ** 3)), max(10, int(1e4 * (n / 256.0) ** 3))
+
+
+def _reference_worker(args):
+    n, kind, blas_threads = args
+    nv, ng = _sample_counts(n)
+    fn = reference_step if kind == "reference" else cpu_reference_step
+    if blas_threads:
+        # one of several solves at once: numpy's BLAS (the dot products of scipy's CG) keeps to its own core
+        from threadpoolctl import threadpool_limits
+
+        with threadpool_limits(limits=blas_threads):
+            dof, its, dt, timing = fn(n, nv, ng)
+    else:
+        dof, its, dt, timing = fn(n, nv, ng)
+    return dof, its, dt, float(timing.get("solve_seconds", 0.0))
+
+
+def _fit_procs(procs, n):
+    """Keep the batch inside half of the free host memory: a solve holds A, its column-scaled copy and A^T A, about
+    4 kB per node with the COO/CSR temporaries of the assembly (6 GB at 128^3, measured)."""
+    try:
+        import psutil
+
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 32 << 30
+    return max(1, min(procs, int(0.5 * avail / (4000.0 * n ** 3))))
+
+
+def reference_available():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import refenv
+
+        return refenv.available()
+    except Exception:
+        return False
+
+
+def run_reference_batch(n, kind, procs):
+    """`procs` independent solves of the n^3 sample at once, one process each (scipy's CG and CSR matvec are single
+    threaded: independent problems are the only way the reference uses more than one core).  Returns the summed
+    dof x iterations, the wall time of the batch and the CG-only seconds of one solve."""
+    if procs <= 1:
+        dof, its, dt, solve_s = _reference_worker((n, kind, 0))
+        return dof * its, dt, its, solve_s
+    from concurrent.futures import ProcessPoolExecutor
+
+    t0 = time.perf_counter()
+    with ProcessPoolExecutor(max_workers=procs) as pool:
+        res = list(pool.map(_reference_worker, [(n, kind, 1)] * procs))
+    wall = time.perf_counter() - t0
+    return sum(d * i for d, i, _t, _s in res), wall, res[0][1], res[0][3]
+
+
 def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of the path on the box's host cores.  A step is one
+    batch of independent solves of a bounded sample of the workload (every host thread busy); the sample size is chosen
+    from a calibration solve so that warm-up + steps end within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    n = args.ref_n
-    nv, ng = max(100, int(1e5 * (n / 256.0) ** 3)), max(10, int(1e4 * (n / 256.0) ** 3))
+    kind = "reference" if reference_available() else "port"
+    threads = host_threads()
+    procs = max(1, min(threads, 32)) if not args.ref_procs else args.ref_procs
+    budget = float(args.ref_budget)
+    total_steps = args.steps + args.warmup
+    # calibration: one single solve of the smallest sample (also the first import of the reference)
+    t0 = time.perf_counter()
+    dof0, its0, dt0, _ = _reference_worker((64, kind, 0))
+    calib = time.perf_counter() - t0
+    n = args.ref_n or 64
+    procs = _fit_procs(procs, max(n, 96))
+    if not args.ref_n:
+        # one batch at 64^3 shows what the host's memory system makes of `procs` solves at once; fewer processes when
+        # warm-up + steps would not fit the budget, the 96^3 sample (3.6 x the work per solve, measured) when they would
+        _u, tb, _i, _s = run_reference_batch(64, kind, procs)
+        while procs > 1 and tb * max(total_steps, 1) > budget:
+            procs = max(1, procs // 2)
+            _u, tb, _i, _s = run_reference_batch(64, kind, procs)
+        if tb * 3.6 * 1.3 * max(total_steps, 1) <= budget:
+            n = 96
     for _ in range(args.warmup):
-        cpu_reference_step(n, nv, ng)
+        run_reference_batch(n, kind, procs)
     t0 = time.perf_counter()
     units = 0
     its = 0
     solve_s = 0.0
     for _ in range(args.steps):
-        dof, it, dt, timing = cpu_reference_step(n, nv, ng)
-        units += dof * it
+        u, _wall, it, ss = run_reference_batch(n, kind, procs)
+        units += u
         its += it
-        solve_s += timing["solve_seconds"]
+        solve_s += ss
     total = time.perf_counter() - t0
     value = units / total
-    sample = (f"{n}^3-node sample of the 256^3 workload ({nv} value + {ng} gradient points), explicit A, ridge, "
-              f"column scaling, A^T A, scipy-equivalent CG rtol 1e-5; {its // max(args.steps,1)} iterations/solve")
+    nv, ng = _sample_counts(n)
+    what = ("unmodified reference (baseline/_ref): StructuredGrid + FiniteDifferenceInterpolator.setup_interpolator + "
+            "solve_system('cg')" if kind == "reference" else "oracle port of the reference's default solve")
+    sample = (f"{procs} independent solves at once (one process each; scipy's CG is single-threaded) of a {n}^3-node sample of "
+              f"the 256^3 workload ({nv} value + {ng} gradient points), {what}; {its // max(args.steps, 1)} iterations/solve; "
+              f"single-solve calibration at 64^3: {dof0 * its0 / dt0:.3g} dof-iter/s")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "synthetic FDI foliation 256^3 nodes, 1e5 value + 1e4 gradient constraints (configs[1])",
                    "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": sample,
-                         "cg_only_value": units / solve_s if solve_s > 0 else None},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample,
+                         "single_solve_value": dof0 * its0 / dt0, "host_threads": threads},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -537,15 +655,19 @@ def run_ours(args):
         if eval_info is not None:
             line["eval"] = eval_info
         if world == 1 and not args.no_cpu_baseline:
-            t0 = time.perf_counter()
-            dof, it, dt, timing = cpu_reference_step(args.ref_n, max(100, int(1e5 * (args.ref_n / 256.0) ** 3)),
-                                                     max(10, int(1e4 * (args.ref_n / 256.0) ** 3)))
+            # bounded sample on the host cores: the unmodified reference when baseline/_ref travelled with the snapshot
+            # (kind "reference"), else the oracle port; one batch of independent solves, one per host thread
+            kind = "reference" if reference_available() else "port"
+            n_ref = args.ref_n or 64
+            procs = _fit_procs(args.ref_procs or max(1, min(host_threads(), 32)), n_ref)
+            units, wall_ref, it_ref, solve_ref = run_reference_batch(n_ref, kind, procs)
+            nv_ref, ng_ref = _sample_counts(n_ref)
             line["cpu_baseline"] = {
-                "value": dof * it / dt, "unit": UNIT, "cores": host_threads(), "kind": "port",
-                "sample": f"{args.ref_n}^3-node sample of the same workload, one full scipy-path solve "
-                          f"({it} iterations, {dt:.1f} s: assembly {timing['assembly_seconds']:.1f} s, preprocess "
-                          f"{timing['preprocess_seconds']:.1f} s, A^T A {timing['gram_seconds']:.1f} s, CG "
-                          f"{timing['solve_seconds']:.1f} s); scipy's CSR matvec is single-threaded, numpy's BLAS dot products use the other threads",
+                "value": units / wall_ref, "unit": UNIT, "cores": procs, "kind": kind,
+                "sample": f"{procs} independent solves at once (one process each; scipy's CG is single-threaded) of a {n_ref}^3-node "
+                          f"sample of the same workload ({nv_ref} value + {ng_ref} gradient points): "
+                          + ("unmodified reference, setup_interpolator + solve_system('cg')" if kind == "reference" else "oracle port of the scipy path")
+                          + f", {it_ref} iterations, {wall_ref:.1f} s per batch (CG alone {solve_ref:.1f} s)",
             }
         if world == 1 and not args.no_fault:
             # last, after everything else has been measured: these kernels are the newest code in the library
@@ -579,7 +701,9 @@ def main():
                                                               "on 8 GPUs is the 1024^3 grid of BASELINE configs[4]")
     ap.add_argument("--n-value", type=int, default=100_000)
     ap.add_argument("--n-gradient", type=int, default=10_000)
-    ap.add_argument("--ref-n", type=int, default=64, help="nodes per axis of the bounded CPU sample")
+    ap.add_argument("--ref-n", type=int, default=0, help="nodes per axis of the bounded CPU sample (0: chosen from a calibration solve)")
+    ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: independent solves at once (0: one per host thread, at most 32)")
+    ap.add_argument("--ref-budget", type=float, default=240.0, help="reference arm: seconds that warm-up + steps may take")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--multi-gpu-eval", action="store_true", help="N > 1: replicate c and evaluate a cloud split over the ranks")
     ap.add_argument("--eval-points", type=int, default=100_000_000)

@@ -7,6 +7,7 @@ call through the C-ABI of ``include/lsb200.h`` into the CUDA kernels.
 from __future__ import annotations
 
 import ctypes as C
+import sys
 from dataclasses import dataclass
 
 import numpy as np
@@ -66,6 +67,22 @@ class SolveResult:
     kernel_launches: int
 
 
+class _PinnedBlock:
+    """Owner of one cudaHostAlloc block (lsb200_host_alloc / lsb200_host_free)."""
+
+    def __init__(self, lib, nbytes: int):
+        self.lib = lib
+        self.ptr = C.c_void_p()
+        nat.check(lib.lsb200_host_alloc(int(nbytes), C.byref(self.ptr)))
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.lsb200_host_free(self.ptr)
+        except Exception:
+            pass
+
+
 class Engine:
     """One support (regular grid or tet mesh on the same lattice) on one GPU.
 
@@ -101,9 +118,7 @@ class Engine:
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.lsb200_destroy(self._h)
             self._h = nat.Handle()
-        if getattr(self, "_pinned", None) is not None:
-            self._pinned = None
-            self._lib.lsb200_host_free(self._pinned_ptr)
+        self._pinned_buf = None  # the block itself lives as long as any array over it (see pinned_vector)
 
     def __del__(self):
         try:
@@ -259,15 +274,20 @@ class Engine:
         return out
 
     def pinned_vector(self) -> np.ndarray:
-        """A page-locked float64 array of local_dof entries owned by this engine (freed by close()); pass it as
-        ``out=`` to solve_cg / get_c to take the result without page faults or a pageable bounce."""
-        if getattr(self, "_pinned", None) is None:
-            ptr = C.c_void_p()
-            n = self.local_dof
-            nat.check(self._lib.lsb200_host_alloc(8 * n, C.byref(ptr)))
-            self._pinned_ptr = ptr
-            self._pinned = np.ctypeslib.as_array(C.cast(ptr, nat.c_double_p), shape=(n,))
-        return self._pinned
+        """A page-locked float64 array of local_dof entries; pass it as ``out=`` to solve_cg / get_c to take the result
+        without page faults or a pageable bounce.  The block belongs to the ARRAY (array -> ctypes buffer -> _PinnedBlock),
+        not to the engine: it is freed when the last array or view over it dies, so a caller may keep the result past
+        ``close()``.  The engine reuses its block only while nobody else holds an array over it; otherwise the next call
+        hands out a fresh one and the caller's data stay untouched."""
+        n = self.local_dof
+        buf = getattr(self, "_pinned_buf", None)
+        # references to buf: this attribute, the local name, getrefcount's argument; every live array adds one (its base)
+        if buf is None or len(buf) != n or sys.getrefcount(buf) > 3:
+            owner = _PinnedBlock(self._lib, 8 * n)
+            buf = (C.c_double * n).from_address(owner.ptr.value)
+            buf._owner = owner
+            self._pinned_buf = buf
+        return np.frombuffer(buf, dtype=np.float64)
 
     def solve_cg(self, rtol: float = 1e-5, atol: float = 0.0, maxiter: int | None = None, x0=None,
                  want_c: bool = True, out: np.ndarray | None = None):

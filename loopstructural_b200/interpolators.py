@@ -114,8 +114,7 @@ class _B200DiscreteInterpolator:
 
     def close(self):
         if self._engine is not None:
-            self.c = np.array(self.c, dtype=np.float64)  # detach from the engine's page-locked buffer
-            self._c_on_device = False
+            self._c_on_device = False  # self.c stays valid: it owns its (page-locked) block
             self._engine.close()
             self._engine = None
 
@@ -170,9 +169,18 @@ class _B200DiscreteInterpolator:
         e = self.engine
         e.set_options(ridge_factor=self.ridge_factor, add_ridge=self.add_ridge_regulatisation,
                       apply_scaling=self.apply_scaling_matrix, deterministic=bool(kw.get("deterministic", False)))
-        # the result lands in a page-locked buffer owned by the engine; like the reference's solve_system
-        # (which rebinds self.c on every solve) it is valid until the next solve of this interpolator
-        c, res = e.solve_cg(rtol=rtol, atol=atol, maxiter=kw.get("maxiter"), x0=kw.get("x0"), out=e.pinned_vector())
+        # The result lands in a page-locked array that owns its block (Engine.pinned_vector).  Like the reference's
+        # solve_system this rebinds self.c; an array the caller still holds from an earlier solve keeps its data (the
+        # engine reuses a block only when nobody else refers to it) and outlives close().
+        x0 = kw.get("x0")
+        x0 = None if x0 is None else np.array(x0, dtype=np.float64)
+        self.c = None  # drop our reference to the previous result so that its block can be reused
+        try:
+            c, res = e.solve_cg(rtol=rtol, atol=atol, maxiter=kw.get("maxiter"), x0=x0, out=e.pinned_vector())
+        except Exception:
+            self.c = np.full(self.dof, np.nan)
+            self._c_on_device = False
+            raise
         self.c = c
         self._c_on_device = True
         self.up_to_date = True  # non-convergence is a warning, never a failure (LI/_solver_strategy.py:66-71)

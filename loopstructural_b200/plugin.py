@@ -78,23 +78,26 @@ def _resolve_tolerances(tol, solver_kwargs):
     return rtol, atol, kw
 
 
-def _solve_on_engine(it, eng, solver, tol, solver_kwargs) -> bool:
-    """Common tail of solve_system(solver='b200'): constraint dict -> ELL rows -> device CG -> it.c."""
+def _solve_on_engine(it, eng, solver, tol, solver_kwargs, skip=()) -> bool:
+    """Common tail of solve_system(solver='b200'): constraint dict -> ELL rows -> device CG -> it.c.  ``skip``: keys of
+    ``it.constraints`` that reach the engine as stencil weights instead of rows."""
     started = perf_counter()
     rtol, atol, kw = _resolve_tolerances(tol, solver_kwargs)
     eng.set_options(ridge_factor=it.ridge_factor, add_ridge=it.add_ridge_regulatisation,
-                    apply_scaling=it.apply_scaling_matrix)
+                    apply_scaling=it.apply_scaling_matrix, deterministic=bool(kw.get("deterministic", False)))
     t_asm = perf_counter()
     n_rows = 0
-    for _name, vals, cols, b, w in constraints_to_rows(it.constraints):
+    eng.clear_rows()
+    rows = {k: c for k, c in it.constraints.items() if k not in skip}
+    for _name, vals, cols, b, w in constraints_to_rows(rows):
         eng.add_rows(vals, cols, b, w, normalise=False)
         n_rows += vals.shape[0]
-    for other, w2l, step, w, b in getattr(it, "_b200_device_rows", []):
+    for other, w2l, step, w, b, _stock, _pos in getattr(it, "_b200_device_rows", []):
         # frame-orthogonality families diverted by the builder patch: generated on the device from the other field
         n_rows += eng.add_field_orthogonal_rows(other, step=step, weight=w, b=b, other_world_to_local=w2l)
     assembly = perf_counter() - t_asm
     c, res = eng.solve_cg(rtol=rtol, atol=atol, maxiter=kw.get("maxiter"), x0=kw.get("x0"))
-    it.c = c
+    it.c = c  # an ndarray that owns its memory: callers may keep it across solves and past the interpolator's life
     it.up_to_date = True  # non-convergence is a warning, never a failure (LI/_solver_strategy.py:66-71)
     it.latest_solve_timing = {
         "solver": solver, "backend": "b200", "assembly_seconds": assembly, "preprocess_seconds": res.setup_seconds,
@@ -105,42 +108,96 @@ def _solve_on_engine(it, eng, solver, tol, solver_kwargs) -> bool:
 
 
 class _B200Mixin:
-    """Shared by the FDI and P1 subclasses: set-up bookkeeping, solver dispatch, device evaluation."""
+    """Shared by the FDI and P1 subclasses: set-up bookkeeping, solver dispatch, device evaluation.
+
+    Two set-up states serve ``solver='b200'``:
+      * *diverted* (``setup_interpolator(..., solver='b200')``, the GeologicalModel flow): the O(N) regularisation
+        families were recorded as weights and never assembled;
+      * *explicit* (any other set-up, e.g. loop_interpolation's InterpolatorBuilder, which pops ``solver`` from its kwargs
+        before it calls ``setup``): the families are in ``self.constraints``; those recognised as default stencil
+        families at assembly time are still applied matrix-free, everything else goes to the engine as rows.
+    Neither direction re-runs the set-up, so constraints added after it (orthogonal rows, equality constraints, the
+    builder's gradient constraints) are kept, exactly as with the stock class."""
 
     def _b200_init(self):
         self._b200_divert = False
-        self._b200_reg = {}
+        self._b200_reg = {}        # diverted families: name -> effective weight
+        self._b200_reg_ops = {}    # diverted families: name -> what the stock assembly needs to materialise them
+        self._b200_explicit = {}   # explicit set-up: constraints key -> (stencil name, weight) of a default family
         self._b200_setup_kwargs = {}
         self._b200_engine = None
-        self._b200_device_rows = []  # (other engine, its world_to_local, element step, weight, b) per diverted family
+        # (other engine, its world_to_local, element step, weight, b, stock, position) per diverted orthogonality
+        # family; stock() assembles the same family on the host (used when a stock solver is asked for after all)
+        self._b200_device_rows = []
 
     def setup_interpolator(self, **kwargs):
         self._b200_setup_kwargs = dict(kwargs)
-        self._b200_reg = {}
+        self._b200_reg, self._b200_reg_ops, self._b200_explicit = {}, {}, {}
         self._b200_device_rows = []
-        self._b200_divert = self._b200_can_divert(kwargs)
+        self._b200_divert = (self._b200_supported(kwargs) and kwargs.get("solver") in B200_SOLVERS
+                             and not kwargs.get("use_regularisation_weight_scale", False))
         return super().setup_interpolator(**kwargs)
+
+    def reset(self):
+        super().reset()
+        if getattr(self, "_b200_divert", False):
+            # DiscreteInterpolator.reset allocates np.ones(dof) (LI/_discrete_interpolator.py:313); only the explicit
+            # stencil assembly with use_regularisation_weight_scale reads it, and that case is never diverted
+            ones = np.broadcast_to(np.float64(1.0), (int(self.dof),))
+            self.regularisation_scale = ones
+
+    def _b200_record(self, name, payload):
+        """A family that is not assembled now: remember where it would have stood in self.constraints."""
+        self._b200_reg_ops[name] = (len(self.constraints), payload)
+
+    def _b200_assemble_recorded(self, name, payload):
+        raise NotImplementedError
+
+    def _b200_materialise(self):
+        """Assemble on the host what a diverted set-up only recorded (a stock solver was asked for after all), each
+        family at the place the stock set-up would have put it, so that the stock solver sees the stock matrix."""
+        self._b200_divert = False  # from here on the assembly methods take the stock path
+        self.regularisation_scale = np.ones(self.dof)
+        todo = [(pos, lambda n=name, p=payload: self._b200_assemble_recorded(n, p)) for name, (pos, payload) in self._b200_reg_ops.items()]
+        todo += [(entry[6], entry[5]) for entry in self._b200_device_rows]
+        placed = []
+        for pos, run in todo:
+            before = set(self.constraints)
+            run()
+            placed.append((pos, [k for k in self.constraints if k not in before]))
+        moved = {k for _pos, keys in placed for k in keys}
+        order = [k for k in self.constraints if k not in moved]
+        shift = 0
+        for pos, keys in sorted(placed, key=lambda t: t[0]):  # stable: equal positions keep their recording order
+            order[pos + shift:pos + shift] = keys
+            shift += len(keys)
+        self.constraints = {k: self.constraints[k] for k in order}
+        self._b200_reg, self._b200_reg_ops, self._b200_device_rows = {}, {}, []
+
+    def _b200_get_engine(self):
+        """One engine per interpolator, kept across solves (7 node vectors of device memory)."""
+        sup = self.support
+        key = (tuple(int(v) for v in sup.nsteps), tuple(float(v) for v in sup.origin), tuple(float(v) for v in sup.step_vector))
+        if self._b200_engine is not None and getattr(self, "_b200_engine_key", None) != key:
+            self._b200_engine.close()
+            self._b200_engine = None
+        if self._b200_engine is None:
+            self._b200_engine = self._b200_make_engine()
+            self._b200_engine_key = key
+        return self._b200_engine
 
     def solve_system(self, solver=None, tol=None, solver_kwargs=None) -> bool:
         if solver not in B200_SOLVERS:
             if self._b200_divert:
-                # the regularisation rows were never assembled: redo the setup the stock way for this solver
-                kw = dict(self._b200_setup_kwargs)
-                kw["solver"] = solver
-                self.setup_interpolator(**kw)
+                self._b200_materialise()
             return super().solve_system(solver=solver, tol=tol, solver_kwargs=solver_kwargs)
-        if not self._b200_divert:
-            kw = dict(self._b200_setup_kwargs)
-            kw["solver"] = solver
-            if not self._b200_can_divert(kw):
-                raise ValueError(self._b200_unsupported)
-            self.setup_interpolator(**kw)
+        if not self._b200_supported(self._b200_setup_kwargs):
+            raise ValueError(self._b200_unsupported)
         if not self._pre_solve():
             raise ValueError("Pre solve failed")
-        if self._b200_engine is not None:
-            self._b200_engine.close()
-        self._b200_engine = self._b200_make_engine()
-        return _solve_on_engine(self, self._b200_engine, solver, tol, solver_kwargs)
+        eng = self._b200_get_engine()
+        skip = self._b200_set_regularisation(eng)
+        return _solve_on_engine(self, eng, solver, tol, solver_kwargs, skip=skip)
 
     # -- evaluation: the device holds c after a b200 solve -------------------------------------------------
     def _b200_engine_current(self):
@@ -198,6 +255,11 @@ class _B200Mixin:
         return eng.evaluate_gradient(locations)
 
 
+def _uniform_weight(c, w) -> bool:
+    ww = np.asarray(c["w"], dtype=np.float64).ravel()
+    return ww.size > 0 and bool(np.all(ww == w))
+
+
 def _make_fdi_class():
     from loop_common.supports import StructuredGrid
     from loop_interpolation import FiniteDifferenceInterpolator
@@ -205,12 +267,13 @@ def _make_fdi_class():
 
     default_masks = {"dxx": Operator.Dxx_mask, "dyy": Operator.Dyy_mask, "dzz": Operator.Dzz_mask,
                      "dxy": Operator.Dxy_mask, "dxz": Operator.Dxz_mask, "dyz": Operator.Dyz_mask}
+    border_axis = {"dx_lower": "dx", "dx_upper": "dx", "dy_lower": "dy", "dy_upper": "dy", "dz_lower": "dz", "dz_upper": "dz"}
 
     class B200FDI(_B200Mixin, FiniteDifferenceInterpolator):
         """FiniteDifferenceInterpolator whose ``solver='b200'`` runs on the GPU engine."""
 
-        _b200_unsupported = ("solver='b200' needs a 3-D regular StructuredGrid with the default operator masks and no "
-                             "per-node regularisation scale")
+        _b200_unsupported = ("solver='b200' needs a 3-D regular StructuredGrid (RectilinearGrid and 2-D grids stay on "
+                             "the stock solvers)")
 
         def __init__(self, grid, data=None):
             super().__init__(grid, data=data)
@@ -220,39 +283,106 @@ def _make_fdi_class():
         def _b200_stencil(self):
             return self._b200_reg
 
-        def _b200_can_divert(self, kwargs) -> bool:
+        def _b200_supported(self, kwargs) -> bool:
+            # the exact class: RectilinearGrid subclasses StructuredGrid (LC/supports/_3d_rectilinear_grid.py:18) but its
+            # node spacing is not uniform, and the engine gathers with uniform-cell trilinear weights
             sup = self.support
-            return (kwargs.get("solver") in B200_SOLVERS and isinstance(sup, StructuredGrid)
-                    and getattr(sup, "dimension", 3) == 3 and not getattr(sup, "is_rectilinear", False)
-                    and "operators" not in kwargs and not kwargs.get("use_regularisation_weight_scale", False))
+            return type(sup) is StructuredGrid and getattr(sup, "dimension", 3) == 3
+
+        def _b200_matrix_free_family(self, operator, w, name) -> bool:
+            """A default second-derivative family with one scalar weight: what the engine applies matrix-free."""
+            return (name in default_masks and operator is not None and np.ndim(w) == 0
+                    and np.shape(operator) == np.shape(default_masks[name]) and np.array_equal(operator, default_masks[name])
+                    and self._b200_supported(self._b200_setup_kwargs) and not self.use_regularisation_weight_scale
+                    and not getattr(self, "regularisation_matrix_free", False))
 
         def assemble_inner(self, operator, w, name="regularisation"):
-            if (self._b200_divert and name in default_masks and operator is not None
-                    and np.array_equal(operator, default_masks[name])):
+            ok = self._b200_matrix_free_family(operator, w, name)
+            if self._b200_divert and ok and name not in self._b200_reg:
                 # w is the effective row weight (mixed terms already / 4, LC/supports/_3d_structured_grid.py:502-509)
                 self._b200_reg[name] = float(w)
+                self._b200_record(name, (operator, w))
                 return
-            return super().assemble_inner(operator, w, name=name)
+            before = set(self.constraints)
+            out = super().assemble_inner(operator, w, name=name)
+            new = set(self.constraints) - before
+            if ok and len(new) == 1 and name not in {v[0] for v in self._b200_explicit.values()}:
+                self._b200_explicit[new.pop()] = (name, float(w))
+            return out
 
         def assemble_borders(self):
-            if self._b200_divert:
+            ok = self._b200_supported(self._b200_setup_kwargs) and not self.use_regularisation_weight_scale and \
+                not getattr(self, "regularisation_matrix_free", False)
+            if self._b200_divert and ok:
                 for k in ("dx", "dy", "dz"):
                     self._b200_reg[k] = float(self.interpolation_weights[k])
+                self._b200_record("borders", None)
                 return
-            return super().assemble_borders()
+            before = set(self.constraints)
+            out = super().assemble_borders()
+            if ok:
+                for key in set(self.constraints) - before:
+                    if key in border_axis:
+                        self._b200_explicit[key] = (border_axis[key], float(self.interpolation_weights[border_axis[key]]))
+            return out
+
+        def add_norm_constraints(self, w=1.0):
+            """FDI.add_norm_constraints (LI/_finite_difference_interpolator.py:403-476) without its KD-tree pass over ALL
+            nodes (compute_weighting over support.nodes, :436-444: O(N log n) time and a 24 B/node table) -- that pass only
+            feeds regularisation_scale, which nothing reads unless use_regularisation_weight_scale is set."""
+            if not self._b200_divert or self.use_regularisation_weight_scale:
+                return super().add_norm_constraints(w)
+            pts = self.get_norm_constraints()
+            if pts.shape[0] == 0:
+                return
+            dim = self.support.dimension
+            corners, inside = self.support.position_to_cell_corners(pts[:, :dim])
+            corners = np.asarray(corners, dtype=int)[inside, :]
+            T = self.support.get_element_gradient_for_location(pts[inside, :dim])[1]
+            per_point = pts[inside, 2 * dim] if pts.shape[1] > 2 * dim else np.ones(int(inside.sum()))
+            share = w / dim  # one row per axis: the point's weight is shared between them (:455-460)
+            weights = (share[inside] if isinstance(share, np.ndarray) else float(share)) * per_point
+            for d in range(dim):
+                self.add_constraints_to_least_squares(T[:, d, :], pts[inside, dim + d], corners, w=weights, name=f"norm_{d}")
+            self.up_to_date = False
+
+        def _b200_assemble_recorded(self, name, payload):
+            if name == "borders":
+                self.assemble_borders()
+            else:
+                self.assemble_inner(payload[0], payload[1], name=name)
 
         def _b200_make_engine(self):
             from .engine import Engine
 
             sup = self.support
-            eng = Engine(np.asarray(sup.nsteps), np.asarray(sup.origin, float), np.asarray(sup.step_vector, float))
-            st = self._b200_reg
+            return Engine(np.asarray(sup.nsteps), np.asarray(sup.origin, float), np.asarray(sup.step_vector, float))
+
+        def _b200_set_regularisation(self, eng):
+            """Stencil weights of this solve; returns the keys of self.constraints they replace."""
+            st, skip = dict(self._b200_reg), set()
+            if not self._b200_divert:
+                st = {}
+                borders = {}
+                for key, (name, w) in self._b200_explicit.items():
+                    c = self.constraints.get(key)
+                    if c is None or not _uniform_weight(c, w):
+                        continue
+                    if name in ("dx", "dy", "dz"):
+                        borders.setdefault(name, []).append(key)
+                    elif name not in st:
+                        st[name] = w
+                        skip.add(key)
+                for name, keys in borders.items():
+                    if len(keys) == 2:  # the lower and the upper plane: the engine applies both or neither
+                        st[name] = self._b200_explicit[keys[0]][1]
+                        skip.update(keys)
             # effective weights go in directly: the engine's dict API divides the mixed terms by 4 itself
             eng.set_regularisation({"dxx": st.get("dxx", 0.0), "dyy": st.get("dyy", 0.0), "dzz": st.get("dzz", 0.0),
                                     "dxy": 4.0 * st.get("dxy", 0.0), "dxz": 4.0 * st.get("dxz", 0.0),
                                     "dyz": 4.0 * st.get("dyz", 0.0), "dx": st.get("dx", 0.0), "dy": st.get("dy", 0.0),
                                     "dz": st.get("dz", 0.0)})
-            return eng
+            return skip
 
     B200FDI.__name__ = "B200FiniteDifferenceInterpolator"
     return B200FDI
@@ -263,31 +393,52 @@ def _make_tet_class(base, name, doc):
     from loop_common.supports import TetMesh
 
     class B200Tet(_B200Mixin, base):
-        _b200_unsupported = ("solver='b200' needs a 3-D structured TetMesh, the default (face-normal) edge-jump "
-                             "regularisation and no per-node regularisation scale")
+        _b200_unsupported = "solver='b200' needs a 3-D structured TetMesh"
 
         def __init__(self, *args, **kwargs):
             super().__init__(*args, **kwargs)
             self._b200_init()
 
-        def _b200_can_divert(self, kwargs) -> bool:
-            return (kwargs.get("solver") in B200_SOLVERS and isinstance(self.support, TetMesh)
-                    and not kwargs.get("use_regularisation_weight_scale", False))
+        def _b200_supported(self, kwargs) -> bool:
+            return type(self.support) is TetMesh
 
         def minimise_edge_jumps(self, w=0.1, vector_func=None, vector=None, name="edge jump"):
-            if self._b200_divert and vector_func is None and vector is None and name == "edge jump" and "cgw" not in self._b200_reg:
+            plain = (vector_func is None and vector is None and name == "edge jump" and np.ndim(w) == 0
+                     and self._b200_supported(self._b200_setup_kwargs)
+                     and not self._b200_setup_kwargs.get("use_regularisation_weight_scale", False))
+            if self._b200_divert and plain and "cgw" not in self._b200_reg:
                 self._b200_reg["cgw"] = float(w)
+                self._b200_record("cgw", w)
                 return
-            return super().minimise_edge_jumps(w=w, vector_func=vector_func, vector=vector, name=name)
+            before = set(self.constraints)
+            out = super().minimise_edge_jumps(w=w, vector_func=vector_func, vector=vector, name=name)
+            new = set(self.constraints) - before
+            if plain and len(new) == 1 and not self._b200_explicit:
+                self._b200_explicit[new.pop()] = ("cgw", float(w))
+            return out
+
+        def _b200_assemble_recorded(self, name, payload):
+            self.minimise_edge_jumps(w=payload)
 
         def _b200_make_engine(self):
             from .engine import Engine
 
             sup = self.support
-            eng = Engine(np.asarray(sup.nsteps), np.asarray(sup.origin, float), np.asarray(sup.step_vector, float),
-                         kind="tetmesh")
-            eng.set_p1_regularisation(self._b200_reg.get("cgw", 0.0))
-            return eng
+            return Engine(np.asarray(sup.nsteps), np.asarray(sup.origin, float), np.asarray(sup.step_vector, float),
+                          kind="tetmesh")
+
+        def _b200_set_regularisation(self, eng):
+            skip = set()
+            cgw = self._b200_reg.get("cgw", 0.0)
+            if not self._b200_divert:
+                cgw = 0.0
+                for key, (_n, w) in self._b200_explicit.items():
+                    c = self.constraints.get(key)
+                    if c is not None and _uniform_weight(c, w):
+                        cgw = w
+                        skip.add(key)
+            eng.set_p1_regularisation(cgw)
+            return skip
 
     B200Tet.__name__ = B200Tet.__qualname__ = name
     B200Tet.__doc__ = doc
@@ -399,6 +550,17 @@ def _make_install_gradient_constraint(stock):
         if not (getattr(it, "_b200_divert", False) and hasattr(it, "_b200_stencil")):
             return stock(self)
         rest = {}
+
+        def only(key, g):
+            def run():  # the same family through the stock method (a stock solver was asked for after a diverted set-up)
+                keep = self._orthogonal_features
+                self._orthogonal_features = {key: g}
+                try:
+                    stock(self)
+                finally:
+                    self._orthogonal_features = keep
+            return run
+
         for key, g in self._orthogonal_features.items():
             feature, w, _region, step, b = g
             if w == 0:
@@ -407,7 +569,7 @@ def _make_install_gradient_constraint(stock):
             if src is None:
                 rest[key] = g
             else:
-                it._b200_device_rows.append((src[0], src[1], int(step), float(w), float(b)))
+                it._b200_device_rows.append((src[0], src[1], int(step), float(w), float(b), only(key, g), len(it.constraints)))
         if rest:
             keep = self._orthogonal_features
             self._orthogonal_features = rest

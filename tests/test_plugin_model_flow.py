@@ -38,6 +38,10 @@ class OracleEngine:
     def set_options(self, **kw):
         self.opts = kw
 
+    def clear_rows(self):
+        self.rows = []
+        self.device_families = 0
+
     def add_rows(self, A, idx, b, w, normalise=True):
         assert normalise is False  # the reference has normalised them already
         self.rows.append(self.fo.Family(f"rows{len(self.rows)}", np.array(A, float), np.array(idx), np.array(b, float), np.array(w, float)))
@@ -392,3 +396,108 @@ def test_two_faults_are_applied_as_one_chain(ls, monkeypatch):
     # seven coupled solves (two fault frames, then the foliation on data moved through both), each stopped at the
     # default tolerance: the fields agree to a few 1e-6 of the range
     np.testing.assert_allclose(val, ref, rtol=0, atol=2e-5 * float(np.nanmax(ref) - np.nanmin(ref)), equal_nan=True)
+
+
+# ---- set-up / solver bookkeeping of the plug-in classes ----------------------------------------------
+def _raw_fdi(ls, n=9, seed=2):
+    from loop_common.supports import StructuredGrid
+    from oracle import fdi_oracle as fo
+
+    grid, value, gradient = fo.synthetic_problem(n, 80, 16, seed=seed)
+    sg = StructuredGrid(origin=grid.origin, nsteps_cells=grid.nsteps - 1, step_vector=grid.step)
+    return grid, sg, value, gradient
+
+
+def _orth(grid, seed=7, n=25):
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(0.05, 0.95, (n, 3)) * (grid.nsteps - 1) * grid.step + grid.origin
+    vec = rng.normal(size=(n, 3))
+    return pts, vec
+
+
+def test_constraints_added_after_the_setup_survive_either_solver_direction(ls):
+    """InterpolatorBuilder-style flow: setup WITHOUT solver='b200', constraints added afterwards, solve_system('b200') --
+    and the opposite direction (diverted set-up, stock solver).  Neither re-runs the set-up; both equal the stock class."""
+    import loop_interpolation as li
+
+    grid, sg, value, gradient = _raw_fdi(ls)
+    pts, vec = _orth(grid)
+
+    def prepare(cls, **kw):
+        it = cls(sg)
+        it.set_value_constraints(value)
+        it.set_normal_constraints(gradient)
+        it.setup_interpolator(**kw)
+        it.add_gradient_orthogonal_constraints(pts.copy(), vec.copy(), w=0.7, b=0.0, name="after_setup")  # it normalises vec in place
+        return it
+
+    cls = li.interpolator_map[li.InterpolatorType.FINITE_DIFFERENCE]
+    assert cls.__name__ == "B200FiniteDifferenceInterpolator"
+    stock = prepare(li.FiniteDifferenceInterpolator)
+    assert stock.solve_system("cg", tol=1e-12)
+
+    # explicit set-up -> b200: every family is in self.constraints; the twelve stencil families reach the engine as weights
+    it = prepare(cls)
+    assert not it._b200_divert and "dxx" in it.constraints and "after_setup" in it.constraints
+    n_before = len(OracleEngine.instances)
+    assert it.solve_system("b200", tol=1e-12) and it.latest_solve_timing["backend"] == "b200"
+    eng = OracleEngine.instances[-1]
+    assert len(OracleEngine.instances) == n_before + 1
+    assert eng.weights == {k: 1.0 for k in ("dxx", "dyy", "dzz", "dxy", "dxz", "dyz", "dx", "dy", "dz")}
+    assert len(eng.rows) == 5  # norm_0..2, value, after_setup: none of the 12 stencil families travelled as rows
+    assert "after_setup" in it.constraints and "dxx" in it.constraints  # nothing was reset
+    rng_ = float(stock.c.max() - stock.c.min())
+    assert np.linalg.norm(it.c - stock.c) / np.sqrt(stock.c.size) / rng_ <= 1e-7  # family order differs: other rounding
+    # a second solve reuses the engine (seven node vectors of device memory) instead of re-creating it
+    assert it.solve_system("b200", tol=1e-12) and len(OracleEngine.instances) == n_before + 1 and len(eng.rows) == 5
+    # c is an ordinary ndarray that owns its memory
+    assert it.c.flags.owndata or it.c.base is None or isinstance(it.c.base, np.ndarray)
+
+    # diverted set-up -> stock solver: the recorded families are assembled where the stock set-up puts them
+    it2 = prepare(cls, solver="b200")
+    assert it2._b200_divert and "dxx" not in it2.constraints and "after_setup" in it2.constraints
+    assert it2.solve_system("cg", tol=1e-12) and it2.latest_solve_timing["backend"] == "python"
+    assert list(it2.constraints) == list(stock.constraints)
+    np.testing.assert_array_equal(it2.c, stock.c)  # same matrix, same order: the same bits
+
+
+def test_rectilinear_grids_are_refused_by_the_b200_solver(ls):
+    import loop_interpolation as li
+    from loop_common.supports import RectilinearGrid
+
+    cls = li.interpolator_map[li.InterpolatorType.FINITE_DIFFERENCE]
+    x = np.array([0.0, 0.1, 0.3, 0.6, 1.0])
+    rg = RectilinearGrid(x, x, x)
+    it = cls(rg)
+    rng = np.random.default_rng(0)
+    it.set_value_constraints(np.column_stack([rng.uniform(0.1, 0.9, (20, 3)), rng.normal(size=20), np.ones(20)]))
+    it.setup_interpolator(solver="b200")
+    assert not it._b200_divert
+    with pytest.raises(ValueError, match="regular StructuredGrid"):
+        it.solve_system("b200")
+    assert it.solve_system("cg") and not OracleEngine.instances
+
+
+def test_diverted_setup_never_touches_the_node_table(ls, monkeypatch):
+    """with solver='b200' neither support.nodes (24 B/node) nor the all-node KD-tree of
+    add_norm_constraints is built; the norm families are still the stock ones bit for bit."""
+    import loop_interpolation as li
+    from loop_common.supports import StructuredGrid
+
+    grid, sg, value, gradient = _raw_fdi(ls, n=10, seed=5)
+    stock = li.FiniteDifferenceInterpolator(sg)
+    stock.set_value_constraints(value)
+    stock.set_normal_constraints(gradient)
+    stock.setup_interpolator()
+    monkeypatch.setattr(StructuredGrid, "nodes", property(lambda self: (_ for _ in ()).throw(AssertionError("support.nodes built"))))
+    cls = li.interpolator_map[li.InterpolatorType.FINITE_DIFFERENCE]
+    it = cls(sg)
+    it.set_value_constraints(value)
+    it.set_normal_constraints(gradient)
+    it.setup_interpolator(solver="b200")
+    assert it.regularisation_scale.strides == (0,)  # a broadcast view, not dof doubles
+    for k in ("norm_0", "norm_1", "norm_2", "value"):
+        assert (it.constraints[k]["matrix"] != stock.constraints[k]["matrix"]).nnz == 0
+        np.testing.assert_array_equal(it.constraints[k]["b"], stock.constraints[k]["b"])
+        np.testing.assert_array_equal(it.constraints[k]["w"], stock.constraints[k]["w"])
+    assert it.solve_system("b200")
