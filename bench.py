@@ -248,7 +248,8 @@ def run_reference(args):
     total_steps = args.steps + args.warmup
     # calibration: one single solve of the smallest sample (also the first import of the reference)
     t0 = time.perf_counter()
-    dof0, its0, dt0, _ = _reference_worker((64, kind, 0))
+    n_cal = args.ref_n or 64
+    dof0, its0, dt0, _ = _reference_worker((n_cal, kind, 0))
     calib = time.perf_counter() - t0
     n = args.ref_n or 64
     procs = _fit_procs(procs, max(n, 96))
@@ -279,7 +280,7 @@ def run_reference(args):
             "solve_system('cg')" if kind == "reference" else "oracle port of the reference's default solve")
     sample = (f"{procs} independent solves at once (one process each; scipy's CG is single-threaded) of a {n}^3-node sample of "
               f"the 256^3 workload ({nv} value + {ng} gradient points), {what}; {its // max(args.steps, 1)} iterations/solve; "
-              f"single-solve calibration at 64^3: {dof0 * its0 / dt0:.3g} dof-iter/s")
+              f"one solve alone at {n_cal}^3: {dof0 * its0 / dt0:.3g} dof-iter/s")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True,

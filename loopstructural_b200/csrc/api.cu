@@ -23,6 +23,7 @@
 #include "fdi_main.cuh"
 #include "fdi_plan.cuh"
 #include "frame.cuh"
+#include "hostpipe.cuh"
 #include "p1.cuh"
 #include "rows.cuh"
 
@@ -117,7 +118,7 @@ struct lsb200_ctx {
   CgScalars* sc_host = nullptr;  // pinned
   double* partials = nullptr;    // 6 * MAX_PARTIALS: stencil, rows, x/r update, stencil y-, x-, z-shell
   unsigned int* counters = nullptr;
-  unsigned long long* status = nullptr;  // 2 words
+  unsigned long long* status = nullptr;  // 4 words
   bool finalized = false;
   bool have_c = false;
   nccl::comm_t comm = nullptr;
@@ -139,7 +140,14 @@ struct lsb200_ctx {
   int sm_count = 148;
   long long launches = 0;
   double setup_seconds = 0.0;
+  HostPipe pipe;  // staging of the host-array entry points (hostpipe.cuh)
 };
+
+constexpr long long PIPE_CHUNK = 1 << 20;  // points per staged chunk (24 MB in, 8-48 MB out)
+static int pipe_result(int rc, cudaError_t e, const char* what) {
+  if (e != cudaSuccess) return fail(LSB200_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return rc;
+}
 
 extern "C" {
 static void free_transposes(lsb200_ctx* h);  // defined beside lsb200_finalize_system
@@ -421,8 +429,18 @@ static int launch_rows(lsb200_ctx* h, const double* p, double* q, int cg_mode) {
       CKL();
       h->launches += 2;
     } else {
-      k_rows_normal<VEC_NT><<<(int)nb, VEC_NT, 0, h->stream>>>(h->g, rb, p, q, h->partials + MAX_PARTIALS, h->counters + 1, h->sc,
-                                                               cg_mode, first ? 1 : 0);
+      double* part = h->partials + MAX_PARTIALS;
+      unsigned int* cnt = h->counters + 1;
+      const int f = first ? 1 : 0;
+      constexpr int RNT = 128;  // one row per thread, 2 K + 10 live values: small CTAs spread a short launch over every SM
+      long long rnb = (rb.n + RNT - 1) / RNT;
+      if (rnb > h->sm_count * 16) rnb = h->sm_count * 16;
+      switch (rb.k) {
+        case 4: k_rows_normal<RNT, 4><<<(int)rnb, RNT, 0, h->stream>>>(h->g, rb, p, q, part, cnt, h->sc, cg_mode, f); break;
+        case 8: k_rows_normal<RNT, 8><<<(int)rnb, RNT, 0, h->stream>>>(h->g, rb, p, q, part, cnt, h->sc, cg_mode, f); break;
+        case 16: k_rows_normal<RNT, 16><<<(int)rnb, RNT, 0, h->stream>>>(h->g, rb, p, q, part, cnt, h->sc, cg_mode, f); break;
+        default: k_rows_normal_wide<VEC_NT><<<(int)nb, VEC_NT, 0, h->stream>>>(h->g, rb, p, q, part, cnt, h->sc, cg_mode, f);
+      }
       CKL();
       h->launches++;
     }
@@ -582,7 +600,7 @@ static int create_common(int kind, const int64_t nsteps[3], const double origin[
   CK(cudaMalloc(&h->partials, sizeof(double) * 6 * MAX_PARTIALS));
   CK(cudaMalloc(&h->counters, sizeof(unsigned int) * 8));
   CK(cudaMemset(h->counters, 0, sizeof(unsigned int) * 8));
-  CK(cudaMalloc(&h->status, sizeof(unsigned long long) * 2));
+  CK(cudaMalloc(&h->status, sizeof(unsigned long long) * 4));
   plan(h);
   *out = h;
   return 0;
@@ -625,6 +643,7 @@ int lsb200_destroy(lsb200_handle h) {
   cudaFree(h->p1_diag);
   cudaFree(h->ztab);
   if (h->comm) nccl::CommDestroy(h->comm);
+  h->pipe.destroy();
   for (int t = 0; t < 3; ++t) {
     if (h->side[t]) cudaStreamDestroy(h->side[t]);
     if (h->ev_join[t]) cudaEventDestroy(h->ev_join[t]);
@@ -709,34 +728,47 @@ int lsb200_add_rows(lsb200_handle h, int64_t n_rows, int k, const double* vals, 
   if (n_rows < 0 || k < 1 || k > 64) return fail(LSB200_ERR_ARG, "bad row block shape (%lld,%d)", (long long)n_rows, k);
   if (n_rows == 0) return 0;
   if (!vals || !cols || !b || !w) return fail(LSB200_ERR_ARG, "null row arrays");
-  const long long dof = (long long)h->g.nx * h->g.ny * h->g.nz;
-  for (long long t = 0; t < (long long)n_rows * k; ++t)
-    if (cols[t] < 0 || cols[t] >= dof) return fail(LSB200_ERR_ARG, "column id %lld outside [0,%lld)", (long long)cols[t], dof);
   CK(cudaSetDevice(h->device));
   double *dv = nullptr, *db = nullptr, *dw = nullptr;
   long long* dc = nullptr;
-  CK(cudaMallocAsync(&dv, sizeof(double) * n_rows * k, h->stream));
-  CK(cudaMallocAsync(&dc, sizeof(long long) * n_rows * k, h->stream));
-  CK(cudaMallocAsync(&db, sizeof(double) * n_rows, h->stream));
-  CK(cudaMallocAsync(&dw, sizeof(double) * n_rows, h->stream));
-  CK(cudaMemcpyAsync(dv, vals, sizeof(double) * n_rows * k, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(dc, cols, sizeof(long long) * n_rows * k, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(db, b, sizeof(double) * n_rows, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(dw, w, sizeof(double) * n_rows, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * 2, h->stream));
   RowBlock rb{};
-  int rc = alloc_block(h, rb, n_rows, width_class(k));
-  if (rc) return rc;
-  CK(cudaMemsetAsync(rb.cols, 0xff, sizeof(int) * rb.n * rb.k, h->stream));
-  CK(cudaMemsetAsync(rb.vals, 0, sizeof(double) * rb.n * rb.k, h->stream));
-  const int nb = (int)std::min<long long>((n_rows + 255) / 256, 4096);
-  k_rows_ingest<<<nb, 256, 0, h->stream>>>(h->g, n_rows, k, dv, dc, db, dw, normalise, rb, 0, h->status);
-  CKL();
-  h->launches++;
-  unsigned long long st[2];
-  CK(cudaMemcpyAsync(st, h->status, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  pool_free(h, dv); pool_free(h, dc); pool_free(h, db); pool_free(h, dw);
+  auto release = [&]() { pool_free(h, dv); pool_free(h, dc); pool_free(h, db); pool_free(h, dw); };
+  auto stage = [&]() -> int {
+    CK(cudaMallocAsync(&dv, sizeof(double) * n_rows * k, h->stream));
+    CK(cudaMallocAsync(&dc, sizeof(long long) * n_rows * k, h->stream));
+    CK(cudaMallocAsync(&db, sizeof(double) * n_rows, h->stream));
+    CK(cudaMallocAsync(&dw, sizeof(double) * n_rows, h->stream));
+    CK(cudaMemcpyAsync(dv, vals, sizeof(double) * n_rows * k, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dc, cols, sizeof(long long) * n_rows * k, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(db, b, sizeof(double) * n_rows, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dw, w, sizeof(double) * n_rows, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * 4, h->stream));
+    int rc = alloc_block(h, rb, n_rows, width_class(k));
+    if (rc) return rc;
+    CK(cudaMemsetAsync(rb.cols, 0xff, sizeof(int) * rb.n * rb.k, h->stream));
+    CK(cudaMemsetAsync(rb.vals, 0, sizeof(double) * rb.n * rb.k, h->stream));
+    const int nb = (int)std::min<long long>((n_rows + 255) / 256, 4096);
+    k_rows_ingest<<<nb, 256, 0, h->stream>>>(h->g, n_rows, k, dv, dc, db, dw, normalise, rb, 0, h->status);
+    CKL();
+    h->launches++;
+    return 0;
+  };
+  unsigned long long st[4] = {0, 0, 0, 0};
+  int rc = stage();
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(st, h->status, sizeof(st), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) rc = fail(LSB200_ERR_CUDA, "row ingestion failed: %s", cudaGetErrorString(e));
+  }
+  release();
+  if (rc) {
+    free_block(h, rb);
+    return rc;
+  }
+  if (st[2]) {
+    free_block(h, rb);
+    return fail(LSB200_ERR_ARG, "column id %lld outside [0,%lld)", (long long)st[3], (long long)h->g.nx * h->g.ny * h->g.nz);
+  }
   if (st[1]) {
     free_block(h, rb);
     return fail(LSB200_ERR_ARG, "a row touching the owned planes [%d,%d) has a column outside the halo planes", h->g.k0, h->g.k1);
@@ -762,7 +794,7 @@ int lsb200_add_point_rows(lsb200_handle h, int kind, int64_t n, const double* da
   double* dd = nullptr;
   CK(cudaMallocAsync(&dd, sizeof(double) * n * ncols, h->stream));
   CK(cudaMemcpyAsync(dd, data, sizeof(double) * n * ncols, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * 2, h->stream));
+  CK(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * 4, h->stream));
   RowBlock rb{};
   const int k = h->kind == LSB200_SUPPORT_GRID ? 8 : 4;
   int rc = alloc_block(h, rb, n * mult, k);
@@ -806,7 +838,7 @@ int lsb200_add_pair_rows(lsb200_handle h, int64_t n, const double* xyz_i, const 
   CK(cudaMallocAsync(&dj, sizeof(double) * 3 * n, h->stream));
   CK(cudaMemcpyAsync(di, xyz_i, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(dj, xyz_j, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * 2, h->stream));
+  CK(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * 4, h->stream));
   RowBlock rb{};
   int rc = alloc_block(h, rb, n, 16);
   if (rc) return rc;
@@ -847,7 +879,7 @@ int lsb200_add_field_orthogonal_rows(lsb200_handle h, lsb200_handle other, const
   const long long n_el = (long long)(h->g.nx - 1) * (h->g.ny - 1) * (h->g.nz - 1);
   const long long n = (n_el + element_step - 1) / element_step;  // element_idx[::step]
   if (n == 0) return 0;
-  CK(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * 2, h->stream));
+  CK(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * 4, h->stream));
   RowBlock rb{};
   rc = alloc_block(h, rb, n, 8);
   if (rc) return rc;
@@ -927,6 +959,48 @@ static int merge_blocks(lsb200_ctx* h) {
   return 0;
 }
 
+// Drop the dead rows of a merged block and sort the rest by first column (k_rows_sort_keys / k_rows_permute): the block
+// k_rows_normal streams every iteration then holds live rows only -- on a z slab every rank is handed all the points
+// and keeps the few whose cell touches its planes -- in an order that keeps a warp's gathers and adds close together
+// and the rows of one constraint point in adjacent lanes.
+static int compact_and_order(lsb200_ctx* h, RowBlock& rb) {
+  if (rb.ordered || rb.n == 0) return 0;
+  if (rb.n >= 2147483647LL) return fail(LSB200_ERR_ARG, "a row block of %lld rows is too large", rb.n);
+  const int n = (int)rb.n;
+  unsigned int *k_in = nullptr, *k_out = nullptr;
+  int *i_in = nullptr, *i_out = nullptr;
+  void* tmp = nullptr;
+  CK(cudaMallocAsync(&k_in, sizeof(unsigned int) * n, h->stream));
+  CK(cudaMallocAsync(&k_out, sizeof(unsigned int) * n, h->stream));
+  CK(cudaMallocAsync(&i_in, sizeof(int) * n, h->stream));
+  CK(cudaMallocAsync(&i_out, sizeof(int) * n, h->stream));
+  CK(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * 4, h->stream));
+  const int nb = std::min((n + 255) / 256, 4096);
+  k_rows_sort_keys<<<nb, 256, 0, h->stream>>>(rb, k_in, i_in, h->status);
+  CKL();
+  size_t tmp_bytes = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, i_in, i_out, n, 0, 32, h->stream));
+  CK(cudaMallocAsync(&tmp, tmp_bytes, h->stream));
+  CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, i_in, i_out, n, 0, 32, h->stream));  // stable
+  unsigned long long live = 0;
+  CK(cudaMemcpyAsync(&live, h->status, sizeof(live), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  RowBlock out{};
+  if (live > 0) {
+    int rc = alloc_block(h, out, (long long)live, rb.k);
+    if (rc) return rc;
+    k_rows_permute<<<std::min(((int)live + 255) / 256, 4096), 256, 0, h->stream>>>(rb, i_out, out);
+    CKL();
+  }
+  h->launches += 3;
+  out.ordered = 1;
+  out.k = rb.k;
+  pool_free(h, k_in); pool_free(h, k_out); pool_free(h, i_in); pool_free(h, i_out); pool_free(h, tmp);
+  free_block(h, rb);
+  rb = out;
+  return 0;
+}
+
 static void free_transposes(lsb200_ctx* h) {
   for (RowTranspose& t : h->transposes) {
     pool_free(h, t.node); pool_free(h, t.off); pool_free(h, t.entry); pool_free(h, t.t);
@@ -999,6 +1073,8 @@ int lsb200_finalize_system(lsb200_handle h) {
   if (rc) return rc;
   rc = merge_blocks(h);
   if (rc) return rc;
+  for (RowBlock& rb : h->blocks)
+    if ((rc = compact_and_order(h, rb))) return rc;
   const size_t bytes = sizeof(double) * (size_t)h->g.nall;
   CK(cudaMemsetAsync(h->rhs, 0, bytes, h->stream));
   CK(cudaMemsetAsync(h->diag, 0, bytes, h->stream));
@@ -1422,24 +1498,13 @@ static int eval_host(lsb200_ctx* h, int64_t n, const double* xyz, double* out, b
   if (n == 0) return 0;
   if (!xyz || !out) return fail(LSB200_ERR_ARG, "null argument");
   CK(cudaSetDevice(h->device));
-  // chunked so that arbitrarily large clouds fit beside the node vectors
-  const int64_t chunk = std::min<int64_t>(n, 1 << 24);
   const int ow = grad ? 3 : 1;
-  double *dx = nullptr, *dout = nullptr;
-  CK(cudaMallocAsync(&dx, sizeof(double) * 3 * chunk, h->stream));
-  CK(cudaMallocAsync(&dout, sizeof(double) * ow * chunk, h->stream));
-  int rc = 0;
-  for (int64_t o = 0; o < n && !rc; o += chunk) {
-    const int64_t m = std::min<int64_t>(chunk, n - o);
-    CK(cudaMemcpyAsync(dx, xyz + 3 * o, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, h->stream));
-    rc = eval_common(h, m, dx, dout, h->stream, grad);
-    if (rc) break;
-    CK(cudaMemcpyAsync(out + ow * o, dout, sizeof(double) * ow * m, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-  }
-  pool_free(h, dx);
-  pool_free(h, dout);
-  return rc;
+  cudaError_t ce;
+  const int rc = h->pipe.run(n, PIPE_CHUNK, 3 * sizeof(double), xyz, ow * sizeof(double), out, 0, nullptr, 0,
+                             [&](cudaStream_t st, long long, long long m, double* dx, double* d0, double*, double*) {
+                               return eval_common(h, m, dx, d0, st, grad);
+                             }, &ce);
+  return pipe_result(rc, ce, "staged evaluation");
 }
 
 int lsb200_eval_value(lsb200_handle h, int64_t n, const double* xyz, double* out) {
@@ -1541,25 +1606,12 @@ static int frame_host(lsb200_ctx* h, const FrameCall& fc, int64_t n, const doubl
   if (n == 0) return 0;
   if (!xyz || !out0) return fail(LSB200_ERR_ARG, "null argument");
   const int w0 = fc.what == FRAME_DISPLACEMENT ? 1 : 3;
-  const int64_t chunk = std::min<int64_t>(n, 1 << 24);
-  double *dx = nullptr, *d0 = nullptr, *d1 = nullptr;
-  CK(cudaMallocAsync(&dx, sizeof(double) * 3 * chunk, h->stream));
-  CK(cudaMallocAsync(&d0, sizeof(double) * w0 * chunk, h->stream));
-  if (out1) CK(cudaMallocAsync(&d1, sizeof(double) * 3 * chunk, h->stream));
-  int rc = 0;
-  for (int64_t o = 0; o < n && !rc; o += chunk) {
-    const int64_t m = std::min<int64_t>(chunk, n - o);
-    CK(cudaMemcpyAsync(dx, xyz + 3 * o, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, h->stream));
-    rc = frame_launch(h, fc, m, dx, d0, d1, h->stream);
-    if (rc) break;
-    CK(cudaMemcpyAsync(out0 + w0 * o, d0, sizeof(double) * w0 * m, cudaMemcpyDeviceToHost, h->stream));
-    if (out1) CK(cudaMemcpyAsync(out1 + 3 * o, d1, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-  }
-  pool_free(h, dx);
-  pool_free(h, d0);
-  pool_free(h, d1);
-  return rc;
+  cudaError_t ce;
+  const int rc = h->pipe.run(n, PIPE_CHUNK, 3 * sizeof(double), xyz, w0 * sizeof(double), out0, out1 ? 3 * sizeof(double) : 0, out1, 0,
+                             [&](cudaStream_t st, long long, long long m, double* dx, double* d0, double* d1, double*) {
+                               return frame_launch(h, fc, m, dx, d0, d1, st);
+                             }, &ce);
+  return pipe_result(rc, ce, "staged frame evaluation");
 }
 
 static int frame_prepare(const lsb200_handle fields[3], const double* transforms, const lsb200_fault_profile* profile,
@@ -1652,39 +1704,32 @@ static int fault_chain(int n_faults, const lsb200_handle* fields, const double* 
     if (fields[3 * f]->device != h->device) return fail(LSB200_ERR_ARG, "the faults of a chain must live on one device");
   if (field && field->device != h->device) return fail(LSB200_ERR_ARG, "the evaluated field lives on another device than the faults");
   CK(cudaSetDevice(h->device));
-  const int64_t chunk = std::min<int64_t>(n, 1 << 24);
   const int ow = field ? (gradient ? 3 : 1) : 3;
-  double* buf[2] = {nullptr, nullptr};
-  double* res = nullptr;
-  CK(cudaMallocAsync(&buf[0], sizeof(double) * 3 * chunk, h->stream));
-  CK(cudaMallocAsync(&buf[1], sizeof(double) * 3 * chunk, h->stream));
-  if (field) CK(cudaMallocAsync(&res, sizeof(double) * ow * chunk, h->stream));
-  int rc = 0;
-  for (int64_t o = 0; o < n && !rc; o += chunk) {
-    const int64_t m = std::min<int64_t>(chunk, n - o);
-    CK(cudaMemcpyAsync(buf[0], xyz + 3 * o, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, h->stream));
-    int cur = 0;
-    for (int f = 0; f < n_faults && !rc; ++f) {
-      rc = frame_launch(h, calls[f], m, buf[cur], buf[1 - cur], nullptr, h->stream);
-      cur = 1 - cur;
-    }
-    if (rc) break;
-    const double* src = buf[cur];
-    if (field) {
-      const int nb = frame_blocks(h, m);
-      if (F.kind == LSB200_SUPPORT_TETMESH) k_field_eval<true><<<nb, 256, 0, h->stream>>>(F, gradient ? 1 : 0, m, buf[cur], res);
-      else k_field_eval<false><<<nb, 256, 0, h->stream>>>(F, gradient ? 1 : 0, m, buf[cur], res);
-      CKL();
-      h->launches++;
-      src = res;
-    }
-    CK(cudaMemcpyAsync(out + ow * o, src, sizeof(double) * ow * m, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-  }
-  pool_free(h, buf[0]);
-  pool_free(h, buf[1]);
-  pool_free(h, res);
-  return rc;
+  // per chunk: the points go up once, every fault is one k_fault_displace launch between the chunk's two device buffers
+  // (input buffer and scratch), the field is evaluated at the moved points, one result comes back
+  cudaError_t ce;
+  const int rc = h->pipe.run(
+      n, PIPE_CHUNK, 3 * sizeof(double), xyz, ow * sizeof(double), out, 0, nullptr, 3 * sizeof(double),
+      [&](cudaStream_t st, long long, long long m, double* dx, double* d0, double*, double* tmp) -> int {
+        double* buf[2] = {dx, tmp};
+        int cur = 0;
+        for (int f = 0; f < n_faults; ++f) {
+          // the last displacement writes straight into the output buffer when no field follows
+          double* dst = (!field && f == n_faults - 1) ? d0 : buf[1 - cur];
+          const int r = frame_launch(h, calls[f], m, buf[cur], dst, nullptr, st);
+          if (r) return r;
+          if (dst != d0) cur = 1 - cur;
+        }
+        if (field) {
+          const int nb = frame_blocks(h, m);
+          if (F.kind == LSB200_SUPPORT_TETMESH) k_field_eval<true><<<nb, 256, 0, st>>>(F, gradient ? 1 : 0, m, buf[cur], d0);
+          else k_field_eval<false><<<nb, 256, 0, st>>>(F, gradient ? 1 : 0, m, buf[cur], d0);
+          CKL();
+          h->launches++;
+        }
+        return 0;
+      }, &ce);
+  return pipe_result(rc, ce, "staged fault chain");
 }
 
 int lsb200_fault_displace_chain(int n_faults, const lsb200_handle* fields, const double* transforms,
@@ -1768,20 +1813,17 @@ int lsb200_eval_lattice(lsb200_handle h, const double* transform, const double s
   if (!out) return fail(LSB200_ERR_ARG, "null output");
   CK(cudaSetDevice(h->device));
   const int ow = gradient ? 3 : 1;
-  const long long chunk = std::min<long long>(total, 1 << 24);
-  double* d = nullptr;
-  CK(cudaMallocAsync(&d, sizeof(double) * ow * chunk, h->stream));
-  for (long long o = 0; o < total; o += chunk) {
-    const long long m = std::min<long long>(chunk, total - o);
-    if (F.kind == LSB200_SUPPORT_TETMESH) k_eval_lattice<true><<<frame_blocks(h, m), 256, 0, h->stream>>>(F, lat, o, m, gradient ? 1 : 0, d);
-    else k_eval_lattice<false><<<frame_blocks(h, m), 256, 0, h->stream>>>(F, lat, o, m, gradient ? 1 : 0, d);
-    CKL();
-    h->launches++;
-    CK(cudaMemcpyAsync(out + ow * o, d, sizeof(double) * ow * m, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-  }
-  pool_free(h, d);
-  return 0;
+  cudaError_t ce;
+  const bool tet = F.kind == LSB200_SUPPORT_TETMESH;
+  rc = h->pipe.run(total, 4 * PIPE_CHUNK, 0, nullptr, ow * sizeof(double), out, 0, nullptr, 0,
+                   [&](cudaStream_t st, long long o, long long m, double*, double* d0, double*, double*) -> int {
+                     if (tet) k_eval_lattice<true><<<frame_blocks(h, m), 256, 0, st>>>(F, lat, o, m, gradient ? 1 : 0, d0);
+                     else k_eval_lattice<false><<<frame_blocks(h, m), 256, 0, st>>>(F, lat, o, m, gradient ? 1 : 0, d0);
+                     CKL();
+                     h->launches++;
+                     return 0;
+                   }, &ce);
+  return pipe_result(rc, ce, "staged lattice evaluation");
 }
 
 int lsb200_plan_z_ranges(int nz, int k0, int k1, int cz, int zface, int out[6]) {

@@ -19,13 +19,32 @@ struct RowBlock {
   int* cols;   // LOCAL storage index (halo planes included); -1 = padding
   double* w2;  // w^2
   double* b;
+  int ordered;  // host bookkeeping: compacted and sorted by lsb200_finalize_system
 };
 
 __device__ __forceinline__ bool owned(const GridDesc& g, int c) {
   return c >= HALO * g.plane && c < (long long)(g.nzl + HALO) * g.plane;
 }
 
-template <int NT>
+// non-returning fp64 add (RED.E.ADD.F64): the issuing thread does not wait for the L2 round trip, unlike atomicAdd,
+// whose return value the compiler keeps alive through ATOMG
+__device__ __forceinline__ void red_add(double* addr, double v) {
+#ifdef LSB_EMU
+  *addr += v;
+#else
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+#endif
+}
+
+#ifndef LSB_EMU  // warp-level kernels: not part of the CPU emulation of the stencil / P1 operators
+// q += A_d^T W A_d p over one ELL block whose rows lsb200_finalize_system has compacted (no dead rows) and sorted by
+// their first column, so that (a) a warp's gathers and adds fall into neighbouring sectors and (b) the rows one
+// constraint point produces (2 gradient rows, 3 normal rows, several points of one cell) sit in adjacent lanes.  One
+// thread per row: K independent gathers, t = w^2 (a . p); then lanes whose K columns all equal those of the lane below
+// form a segment, the per-column products a_j t are summed over the segment with shuffles, and the segment's first lane
+// issues ONE non-returning add per column -- the warp-aggregated scatter.  p . q part: sum_r t_r (a_r . p) over owned
+// columns, fixed-order block / grid reduction.
+template <int NT, int K>
 __global__ void __launch_bounds__(NT)
     k_rows_normal(const GridDesc g, const RowBlock rb, const double* __restrict__ p, double* __restrict__ q,
                   double* __restrict__ partials, unsigned int* __restrict__ counter, CgScalars* __restrict__ sc,
@@ -33,21 +52,82 @@ __global__ void __launch_bounds__(NT)
   __shared__ double red[NT / 32];
   if (cg_mode && sc->done) return;
   double dot = 0.0;
+  const unsigned lane = threadIdx.x & 31u;
+  const long long stride = (long long)gridDim.x * NT;
+  for (long long base = blockIdx.x * (long long)NT; base < rb.n; base += stride) {  // block-uniform trip count
+    const long long r = base + threadIdx.x;
+    const bool active = r < rb.n;
+    int c[K];
+    double a[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      c[j] = active ? rb.cols[j * rb.n + r] : -1;
+      a[j] = active ? rb.vals[j * rb.n + r] : 0.0;
+    }
+    double t = 0.0, town = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      if (c[j] >= 0) {
+        const double v = a[j] * p[c[j]];
+        t += v;
+        if (owned(g, c[j])) town += v;
+      }
+    }
+    t *= active ? rb.w2[r] : 0.0;
+    dot = fma(town, t, dot);
+    // segments of lanes with identical column lists
+    bool same = active && lane > 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int below = __shfl_up_sync(0xffffffffu, c[j], 1);
+      same = same && (below == c[j]);
+    }
+    const unsigned heads = __ballot_sync(0xffffffffu, !same);
+    const unsigned above = lane == 31u ? 0u : (heads >> (lane + 1u));
+    const int len = same ? 0 : (above ? __ffs(above) : (int)(32u - lane));  // head lanes: lanes in my segment
+    const int maxlen = __reduce_max_sync(0xffffffffu, len);
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      double v = a[j] * t;
+      for (int s = 1; s < maxlen; ++s) {
+        const double x = __shfl_down_sync(0xffffffffu, a[j] * t, s);
+        if (s < len) v += x;
+      }
+      if (!same && c[j] >= 0 && v != 0.0 && owned(g, c[j])) red_add(q + c[j], v);
+    }
+  }
+  const double bsum = block_sum<NT>(dot, red);
+  double total;
+  if (grid_sum_last_block<NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total)) {
+    sc->pq_part[1] = first ? total : sc->pq_part[1] + total;
+  }
+}
+
+// generic width (blocks wider than 16): one thread per row, one non-returning add per entry
+template <int NT>
+__global__ void __launch_bounds__(NT)
+    k_rows_normal_wide(const GridDesc g, const RowBlock rb, const double* __restrict__ p, double* __restrict__ q,
+                       double* __restrict__ partials, unsigned int* __restrict__ counter, CgScalars* __restrict__ sc,
+                       const int cg_mode, const int first) {
+  __shared__ double red[NT / 32];
+  if (cg_mode && sc->done) return;
+  double dot = 0.0;
   for (long long r = blockIdx.x * (long long)NT + threadIdx.x; r < rb.n; r += (long long)gridDim.x * NT) {
-    double t = 0.0;
+    double t = 0.0, town = 0.0;
     for (int j = 0; j < rb.k; ++j) {
       const int c = rb.cols[j * rb.n + r];
-      if (c >= 0) t += rb.vals[j * rb.n + r] * p[c];
+      if (c >= 0) {
+        const double v = rb.vals[j * rb.n + r] * p[c];
+        t += v;
+        if (owned(g, c)) town += v;
+      }
     }
     t *= rb.w2[r];
+    dot = fma(town, t, dot);
     if (t != 0.0) {
       for (int j = 0; j < rb.k; ++j) {
         const int c = rb.cols[j * rb.n + r];
-        if (c >= 0 && owned(g, c)) {
-          const double a = rb.vals[j * rb.n + r];
-          atomicAdd(q + c, a * t);
-          dot += a * p[c] * t;
-        }
+        if (c >= 0 && owned(g, c)) red_add(q + c, rb.vals[j * rb.n + r] * t);
       }
     }
   }
@@ -57,6 +137,39 @@ __global__ void __launch_bounds__(NT)
     sc->pq_part[1] = first ? total : sc->pq_part[1] + total;
   }
 }
+
+// ---- compaction and ordering of a block at finalize -------------------------------------------------------------
+// key of a row: its first column (the lowest corner of its cell for point rows; the smallest column of an ingested row);
+// dead rows -- weight 0 (points outside the support or, on a z slab, in cells that touch no owned plane) or no column --
+// get the largest key and are cut off after the sort.  status[0] counts the live rows.
+__global__ void k_rows_sort_keys(const RowBlock rb, unsigned int* __restrict__ keys, int* __restrict__ index,
+                                 unsigned long long* __restrict__ status) {
+  unsigned long long live = 0;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rb.n; r += (long long)gridDim.x * blockDim.x) {
+    const int c0 = rb.cols[r];
+    const bool ok = c0 >= 0 && rb.w2[r] != 0.0;
+    keys[r] = ok ? (unsigned int)c0 : 0xffffffffu;
+    index[r] = (int)r;
+    live += ok ? 1ull : 0ull;
+  }
+  live = __reduce_add_sync(0xffffffffu, (unsigned)live);
+  if ((threadIdx.x & 31) == 0 && live) atomicAdd(status, live);
+}
+
+// dst row r = src row order[r], r < dst.n
+__global__ void k_rows_permute(const RowBlock src, const int* __restrict__ order, RowBlock dst) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < dst.n; r += (long long)gridDim.x * blockDim.x) {
+    const long long o = order[r];
+    for (int j = 0; j < src.k; ++j) {
+      dst.vals[j * dst.n + r] = src.vals[j * src.n + o];
+      dst.cols[j * dst.n + r] = src.cols[j * src.n + o];
+    }
+    dst.w2[r] = src.w2[o];
+    dst.b[r] = src.b[o];
+  }
+}
+
+#endif  // LSB_EMU
 
 // rhs += A_d^T W b
 __global__ void k_rows_rhs(const GridDesc g, const RowBlock rb, double* __restrict__ rhs) {
@@ -92,7 +205,8 @@ __global__ void k_rows_diag(const GridDesc g, const RowBlock rb, double* __restr
 
 // Ingest host-format rows (row-major vals/global cols) into an ELL block: optional row
 // normalisation (LI/_discrete_interpolator.py:361-366), global -> local column ids, w -> w^2.
-// status[0] counts rows kept, status[1] flags a kept row with a column outside owned+halo planes.
+// status[0] counts rows kept, status[1] flags a kept row with a column outside owned+halo planes, status[2] a column id
+// outside [0, nx*ny*nz) (status[3]: one such id).
 __global__ void k_rows_ingest(const GridDesc g, const long long n, const int k, const double* __restrict__ vals,
                               const long long* __restrict__ cols, const double* __restrict__ b,
                               const double* __restrict__ w, const int normalise, RowBlock rb,
@@ -105,7 +219,12 @@ __global__ void k_rows_ingest(const GridDesc g, const long long n, const int k, 
       const double a = vals[r * k + j];
       nrm2 += a * a;
       nan |= (a != a);
-      const long long kz = cols[r * k + j] / nxny;
+      const long long gc = cols[r * k + j];
+      if (gc < 0 || gc >= nxny * g.nz) {
+        if (atomicExch(status + 2, 1ull) == 0ull) status[3] = (unsigned long long)gc;
+        bad = true;
+      }
+      const long long kz = gc < 0 ? -1 - HALO + g.k0 : gc / nxny;
       touches |= (kz >= g.k0 && kz < g.k1);
       bad |= (kz < g.k0 - HALO || kz >= g.k1 + HALO);
     }

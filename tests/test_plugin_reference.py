@@ -6,21 +6,16 @@ import sys
 import numpy as np
 import pytest
 
-REF = "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "packages")), reason="reference not mounted")
+sys.path.insert(0, HERE)
+import refenv  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not refenv.available(), reason="reference neither installed (baseline/_ref) nor mounted")
 
 
 @pytest.fixture(scope="module")
 def li():
-    sys.dont_write_bytecode = True
-    for p in (os.path.join(HERE, "golden", "_stubs"), f"{REF}/packages/loop_common/src",
-              f"{REF}/packages/loop_interpolation/src", REF):
-        if p not in sys.path:
-            sys.path.insert(0, p)
-    import logging
-
-    logging.disable(logging.CRITICAL)
+    refenv.activate()
     import loop_interpolation
 
     return loop_interpolation
