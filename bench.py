@@ -296,7 +296,7 @@ def run_reference(args):
     return 0
 
 
-def measure_eval(eng, local, npts=20_000_000, npts_host=2_000_000):
+def measure_eval(eng, local, npts=20_000_000, npts_host=10_000_000):
     """evaluate_value / evaluate_gradient of the field the engine holds (StructuredGrid.evaluate_*,
     LC/supports/_3d_structured_grid.py:295-454) on a uniform random cloud in the unit cube."""
     import torch
@@ -320,11 +320,19 @@ def measure_eval(eng, local, npts=20_000_000, npts_host=2_000_000):
         dt = a.elapsed_time(b) * 1e-3 / 5
         res[f"{what}_points_per_second"] = npts / dt
         res[f"{what}_gbs"] = res["bytes_per_point"][what] * npts / dt / 1e9
+    # host arrays through the C-ABI (pageable numpy arrays in and out, as a LoopStructural caller holds them): staged in
+    # chunks through page-locked buffers, copies and kernel overlapped (csrc/hostpipe.cuh).  The first call sizes the
+    # staging buffers; the second is timed.
     host = cloud[:npts_host].cpu().numpy()
-    eng.evaluate_value(host[:1000])
+    eng.evaluate_value(host)
     t0 = time.perf_counter()
     v = eng.evaluate_value(host)
-    res["value_points_per_second_host_arrays"] = npts_host / (time.perf_counter() - t0)
+    dt = time.perf_counter() - t0
+    res["value_points_per_second_host_arrays"] = npts_host / dt
+    res["host_arrays"] = {"points": npts_host, "seconds": dt, "gbs_over_pcie": 32.0 * npts_host / dt / 1e9}
+    t0 = time.perf_counter()
+    eng.evaluate_gradient(host)
+    res["gradient_points_per_second_host_arrays"] = npts_host / (time.perf_counter() - t0)
     res["finite_fraction"] = float(np.isfinite(v).mean())
     return res
 
@@ -383,8 +391,8 @@ def measure_fault(local, n_nodes=128, npts=10_000_000, steps=10, cpu_points=100_
     t_lat = timed(lambda: engines[0].evaluate_lattice(np.zeros(3), np.ones(3), (nl, nl, nl), "F", out_ptr=lat.data_ptr(), stream=st), reps=3)
     del lat
     # a faulted feature evaluated through the host-array entry point (fault + field in one call, 24 B/pt in, 8 B/pt out)
-    host_pts = cloud[:2_000_000].cpu().numpy()
-    fl.faulted_evaluate([frame], [prof], [0.05], [steps], engines[2], host_pts[:1000])
+    host_pts = cloud[:5_000_000].cpu().numpy()
+    fl.faulted_evaluate([frame], [prof], [0.05], [steps], engines[2], host_pts)  # sizes the staging buffers
     t0 = time.perf_counter()
     fl.faulted_evaluate([frame], [prof], [0.05], [steps], engines[2], host_pts)
     t_feval = time.perf_counter() - t0

@@ -128,6 +128,8 @@ struct lsb200_ctx {
   dim3 sgrid;
   // main (register-tiled) kernel + y-shell launch of k_fdi_normal; main_cfg < 0: k_fdi_normal everywhere
   int main_cfg = -1;
+  bool fused = false;      // the single-launch plan (k_fdi_fused): default whenever the grid is large enough
+  FusedChoice fz{};
   int main_cz = 0, shell_cz = 0;  // shell_cz = 0: chosen per launch
   int box_z0 = 0, box_z1 = 0;
   long long guard = 0;     // elements of the guard plane in front of every node vector (ensure_vectors)
@@ -230,6 +232,11 @@ static void plan_main(lsb200_ctx* h) {
     if (cudaMemcpy(h->ztab, zt.data(), sizeof(double) * zt.size(), cudaMemcpyHostToDevice) != cudaSuccess) return;
   }
   h->main_cfg = cfg;
+  // the single-launch plan; LSB200_FUSED=0 keeps the three-launch plan of round 1 (for comparison measurements)
+  static const bool want_fused = !(getenv("LSB200_FUSED") && atoi(getenv("LSB200_FUSED")) == 0);
+  auto env_int = [](const char* name) { const char* e = getenv(name); return (e && atoi(e) > 0) ? atoi(e) : 0; };
+  h->fused = want_fused && plan_fused(g, h->sm_count, MAX_PARTIALS, env_int("LSB200_FUSED_CFG"), env_int("LSB200_FUSED_CZ"),
+                                      env_int("LSB200_FUSED_SCZ"), &h->fz);
 }
 
 static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode) {
@@ -256,6 +263,33 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
     h->launches++;                                                                                               \
   }
 #define LSB_LAUNCH(XB, TXT, TYT, MINB, ST) LSB_LAUNCH_AT(h->stream, h->sgrid, h->cz, 0, XB, TXT, TYT, MINB, ST)
+  if (h->main_cfg >= 0 && h->fused) {
+    // one launch: box tiles (y edges and z faces included) and x strips, sized by plan_fused to one even wave
+    const UniConsts U = make_uni_consts(w);
+    const FusedPlan& pl = h->fz.pl;
+    const unsigned int ctas = (unsigned int)(pl.n_box + pl.n_strip);
+    switch (h->fz.tyt) {
+#define X(TYT, ST, MINB)                                                                                          \
+  case TYT: {                                                                                                     \
+    const size_t smem = sizeof(double) * MainCfg<4, TYT, ST>::PLANE * ST;                                         \
+    if (vec16) {                                                                                                  \
+      auto kern = k_fdi_fused<TYT, ST, MINB, true>;                                                               \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
+      kern<<<ctas, dim3(32, TYT), smem, h->stream>>>(g, U, w, pl, p, q, h->ztab, part, cnt, h->sc, cg_mode);       \
+    } else {                                                                                                      \
+      auto kern = k_fdi_fused<TYT, ST, MINB, false>;                                                              \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
+      kern<<<ctas, dim3(32, TYT), smem, h->stream>>>(g, U, w, pl, p, q, h->ztab, part, cnt, h->sc, cg_mode);       \
+    }                                                                                                             \
+  } break;
+      LSB_FUSED_CFGS(X)
+#undef X
+      default: return fail(LSB200_ERR_STATE, "no fused stencil configuration %d", h->fz.tyt);
+    }
+    CKL();
+    h->launches++;
+    return 0;
+  }
   if (h->main_cfg >= 0) {
     const bool ov = h->overlap_shells;
     // fork: the shell launches read p and write rows / columns / planes the box kernel never touches

@@ -5,6 +5,7 @@
 #include <algorithm>
 
 #include "fdi_main.cuh"
+#include "fdi_fused.cuh"
 
 namespace lsb {
 
@@ -129,6 +130,73 @@ inline long long make_shell_box(const GridDesc& g, const int shell_cz, const int
   sb.ring_stagger = 0;
   *out = sb;
   return (long long)sb.ring_blocks * sb.ring_chunks + 2LL * sb.cap_blocks;
+}
+
+// ---- the single-launch plan (k_fdi_fused, csrc/fdi_fused.cuh) ------------------------------------------------------
+// X(TYT warps per CTA, ST ring planes, MINB CTAs per SM): tiles of 64 x 4 TYT nodes
+#define LSB_FUSED_CFGS(X) \
+  X(4, 6, 3)              \
+  X(3, 6, 4)
+
+struct FusedChoice {
+  int tyt, minb;
+  FusedPlan pl;
+  long long ctas;
+  double cost;  // plane steps on the critical path (waves x steps per CTA), the quantity the planner minimises
+};
+
+// One candidate: box CTAs of `nch` z chunks; the strip CTAs get chunks long enough to cost about `strip_rel` of a box CTA
+// (a strip step moves a quarter of the nodes of a box step with general coefficients: measured guess, LSB200_FUSED_SCZ
+// overrides) so that they are never the last to finish.
+inline FusedChoice fused_candidate(const GridDesc& g, const int tyt, const int minb, const int nch, const int sm_count,
+                                   const int scz_override) {
+  FusedChoice c;
+  c.tyt = tyt;
+  c.minb = minb;
+  FusedPlan& pl = c.pl;
+  const int ty = 4 * tyt, nt = 32 * tyt;
+  pl.tiles_x = (g.nx - 8 + 63) / 64;
+  pl.tiles_y = (g.ny + ty - 1) / ty;
+  pl.cz = std::max(1, (g.nzl + nch - 1) / nch);
+  pl.chunks = (g.nzl + pl.cz - 1) / pl.cz;
+  pl.n_box = pl.tiles_x * pl.tiles_y * pl.chunks;
+  pl.strips_y = (g.ny + nt - 1) / nt;
+  constexpr double strip_rel = 0.6;
+  int scz = scz_override > 0 ? scz_override : (int)((pl.cz + 2 * HALO) / strip_rel) - 2 * HALO;
+  scz = std::max(4, std::min(scz, g.nzl));
+  pl.schunks = (g.nzl + scz - 1) / scz;
+  pl.scz = (g.nzl + pl.schunks - 1) / pl.schunks;
+  pl.schunks = (g.nzl + pl.scz - 1) / pl.scz;
+  pl.n_strip = 2 * pl.strips_y * pl.schunks;
+  c.ctas = (long long)pl.n_box + pl.n_strip;
+  const long long slots = (long long)sm_count * minb;
+  const long long waves = (c.ctas + slots - 1) / slots;
+  c.cost = (double)waves * (pl.cz + 2 * HALO);
+  return c;
+}
+
+// The plan of a handle, or false when the grid is too small for it (k_fdi_normal is used everywhere then).
+// cfg_override: TYT (3 or 4), 0 = choose; cz_override / scz_override: chunk lengths, 0 = choose.
+inline bool plan_fused(const GridDesc& g, const int sm_count, const long long max_partials, const int cfg_override,
+                       const int cz_override, const int scz_override, FusedChoice* out) {
+  if (g.nx < 16 || g.ny < 16 || g.nz < 6 || g.nzl < 1) return false;
+  bool have = false;
+  FusedChoice best{};
+#define X(TYT, ST, MINB)                                                                                \
+  if (cfg_override == 0 || cfg_override == TYT) {                                                       \
+    const int max_nch = cz_override > 0 ? 1 : std::max(1, g.nzl / 4);                                   \
+    for (int nch = 1; nch <= max_nch && nch <= 4096; ++nch) {                                           \
+      const int n = cz_override > 0 ? std::max(1, (g.nzl + cz_override - 1) / cz_override) : nch;       \
+      const FusedChoice c = fused_candidate(g, TYT, MINB, n, sm_count, scz_override);                   \
+      if (c.ctas > max_partials) break;                                                                 \
+      if (!have || c.cost < best.cost - 1e-9) { best = c; have = true; }                                \
+    }                                                                                                   \
+  }
+  LSB_FUSED_CFGS(X)
+#undef X
+  if (!have) return false;
+  *out = best;
+  return true;
 }
 
 }  // namespace lsb

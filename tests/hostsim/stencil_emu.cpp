@@ -133,4 +133,60 @@ HOSTSIM_API int emu_fdi_matvec(const int* dims, const double* ew, double ridge2,
   return 0;
 }
 
+// The single-launch plan (k_fdi_fused + plan_fused, csrc/fdi_fused.cuh / fdi_plan.cuh), same conventions as
+// emu_fdi_matvec.  cfg: TYT (3 or 4), 0 = the planner's choice; cz / scz: forced chunk lengths of the box / strip CTAs.
+// info[0] = TYT, [1] = cz, [2] = chunks, [3] = box CTAs, [4] = scz, [5] = strip CTAs, [6] = tiles_x, [7] = tiles_y.
+HOSTSIM_API int emu_fdi_fused(const int* dims, const double* ew, double ridge2, int cfg, int cz_override, int scz_override, int sm_count,
+                              const double* p_global, double* q_owned, double* pq_out, int* info) {
+  GridDesc g{};
+  g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
+  g.k0 = dims[3]; g.k1 = dims[4]; g.nzl = g.k1 - g.k0;
+  g.pitch = g.nx;
+  g.plane = (long long)g.pitch * g.ny;
+  g.nloc = g.plane * g.nzl;
+  g.nall = g.plane * (g.nzl + 2 * HALO);
+  for (int a = 0; a < 3; ++a) { g.origin[a] = 0.0; g.step[a] = 1.0; }
+  const StencilWeights w = weights_from(ew, ridge2);
+  const size_t guard = ((size_t)g.plane + 31) & ~(size_t)31;
+  std::vector<double> pst((size_t)g.nall + 2 * guard, 0.0), qst((size_t)g.nall + 2 * guard, nan(""));
+  double* p = pst.data() + guard;
+  double* q = qst.data() + guard;
+  for (int k = g.k0 - HALO; k < g.k1 + HALO; ++k)
+    if (k >= 0 && k < g.nz)
+      memcpy(p + (size_t)(k - g.k0 + HALO) * g.plane, p_global + (size_t)k * g.plane, sizeof(double) * g.plane);
+    else  // planes outside the grid are never read: poison them
+      for (long long t = 0; t < g.plane; ++t) p[(size_t)(k - g.k0 + HALO) * g.plane + t] = nan("");
+  std::vector<double> ztab((size_t)g.nz * SHELL_ZSTRIDE);
+  shell_fill_z_table(g.nz, ztab.data());
+  std::vector<double> partials((size_t)MAX_PARTIALS, 0.0);
+  unsigned int counter = 0;
+  CgScalars sc{};
+  FusedChoice fc;
+  if (!plan_fused(g, sm_count, MAX_PARTIALS, cfg, cz_override, scz_override, &fc)) return -3;
+  const UniConsts U = make_uni_consts(w);
+  const bool vec16 = (g.pitch % 2) == 0;
+  const unsigned ctas = (unsigned)(fc.pl.n_box + fc.pl.n_strip);
+  switch (fc.tyt) {
+#define X(TYT, ST, MINB)                                                                                             \
+  case TYT: {                                                                                                        \
+    const size_t smem = sizeof(double) * MainCfg<4, TYT, ST>::PLANE * ST;                                            \
+    if (vec16) lsb_emu::launch(dim3(ctas), dim3(32, TYT), smem, [&] { k_fdi_fused<TYT, ST, MINB, true>(g, U, w, fc.pl, p, q, ztab.data(), partials.data(), &counter, &sc, 0); }); \
+    else lsb_emu::launch(dim3(ctas), dim3(32, TYT), smem, [&] { k_fdi_fused<TYT, ST, MINB, false>(g, U, w, fc.pl, p, q, ztab.data(), partials.data(), &counter, &sc, 0); }); \
+  } break;
+    LSB_FUSED_CFGS(X)
+#undef X
+    default: return -4;
+  }
+  info[0] = fc.tyt; info[1] = fc.pl.cz; info[2] = fc.pl.chunks; info[3] = fc.pl.n_box; info[4] = fc.pl.scz; info[5] = fc.pl.n_strip;
+  info[6] = fc.pl.tiles_x; info[7] = fc.pl.tiles_y; info[8] = 2;
+  *pq_out = sc.pq_part[0];
+  for (int k = 0; k < g.nzl; ++k)
+    memcpy(q_owned + (size_t)k * g.plane, q + (size_t)(k + HALO) * g.plane, sizeof(double) * g.plane);
+  for (size_t i = 0; i < qst.size(); ++i) {
+    const bool owned = i >= guard + (size_t)HALO * g.plane && i < guard + (size_t)(HALO + g.nzl) * g.plane;
+    if (!owned && qst[i] == qst[i]) return -2;
+  }
+  return 0;
+}
+
 }  // extern "C"

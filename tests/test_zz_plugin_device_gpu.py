@@ -87,7 +87,8 @@ def test_fault_frame_and_faulted_foliation_on_the_device(ls):
     moved = fault.apply_to_points(pts)
     disp = fault.evaluate_displacement(pts)
     strati = model.evaluate_feature_value("strati", pts)
-    sgrad = model.evaluate_feature_gradient("strati", pts)
+    # (the gradient of a FAULTED feature is not compared: the stock GeologicalFeature.evaluate_gradient itself fails on
+    # it -- it reuses `v` for the (n,4) fault values and then assigns the (n,3) gradient, _geological_feature.py:211-228)
     c_frame = [np.array(fault[i].interpolator.c) for i in range(3)]
     plugin.uninstall()
     stock, _ = _fault_model(ls)
@@ -102,8 +103,11 @@ def test_fault_frame_and_faulted_foliation_on_the_device(ls):
     s_ref = stock.evaluate_feature_value("strati", pts)
     np.testing.assert_array_equal(np.isnan(strati), np.isnan(s_ref))
     np.testing.assert_allclose(strati, s_ref, rtol=0, atol=5e-5 * float(np.nanmax(s_ref) - np.nanmin(s_ref)), equal_nan=True)
-    g_ref = stock.evaluate_feature_gradient("strati", pts)
-    np.testing.assert_allclose(sgrad, g_ref, rtol=0, atol=1e-3 * float(np.nanmax(np.abs(g_ref))), equal_nan=True)
+    # unfaulted gradients: the fault frame's own coordinates
+    g_b200 = [np.asarray(f.evaluate_gradient(pts)) for f in (fault[0], fault[1])]
+    for gb, f in zip(g_b200, (sf[0], sf[1])):
+        g_ref = np.asarray(f.evaluate_gradient(pts))
+        np.testing.assert_allclose(gb, g_ref, rtol=0, atol=1e-3 * float(np.nanmax(np.abs(g_ref))), equal_nan=True)
 
 
 def test_refolded_model_on_the_device(ls):
