@@ -468,6 +468,119 @@ def measure_launch_plans(local, sizes=(256, 512), timeout=150):
     return out
 
 
+def multi_gpu_check(eng, res, nsteps, step, bounds, rank, world, local, value_h, gradient_h, dist, torch):
+    """N > 1: is the answer right?  (a) the residual recomputed through the operator (halo exchange + the same kernels,
+    all-reduced) against the stopping threshold; (b) checksums of c over all ranks; (c) for N <= 2, rank 0 solves the
+    WHOLE grid alone on its GPU and compares its slab of the slab solve node by node."""
+    from loopstructural_b200 import Engine, engine as en
+
+    c_loc, res = eng.solve_cg(rtol=1e-5, atol=0.0)
+    scaled, plain = eng.residual_norm()
+    sums = torch.tensor([float(c_loc.sum()), float(np.dot(c_loc, c_loc)), float(c_loc.min()), float(-c_loc.max())],
+                        dtype=torch.float64, device="cuda")
+    tot = sums[:2].clone()
+    dist.all_reduce(tot)
+    ext = sums[2:].clone()
+    dist.all_reduce(ext, op=dist.ReduceOp.MIN)
+    out = {"residual_norm_recomputed": scaled, "residual_norm_recurrence": res.residual_norm, "threshold": res.threshold,
+           "residual_ok": bool(scaled <= 1.05 * res.threshold), "plain_residual_norm": plain,
+           "iterations": res.iterations, "c_sum": float(tot[0]), "c_l2": float(tot[1]) ** 0.5,
+           "c_range": float(-ext[1] - ext[0]), "peer_memory_scalars": bool(eng.uses_peer_memory)}
+    if world <= 2:
+        verdict = torch.zeros(3, dtype=torch.float64, device="cuda")
+        if rank == 0:
+            full = Engine(nsteps, np.zeros(3), step, device=local)
+            full.set_regularisation({})
+            full.set_options(ridge_factor=1e-8, add_ridge=True, apply_scaling=True)
+            full.add_point_rows(en.ROWS_VALUE, value_h, 1.0)
+            full.add_point_rows(en.ROWS_GRADIENT, gradient_h, 1.0)
+            c_full, res_full = full.solve_cg(rtol=1e-5, atol=0.0)
+            plane = int(nsteps[0]) * int(nsteps[1])
+            mine = c_full[bounds[0][0] * plane:bounds[0][1] * plane]
+            rng_ = float(c_full.max() - c_full.min())
+            verdict[0] = float(np.linalg.norm(mine - c_loc) / np.sqrt(mine.size) / rng_)
+            verdict[1] = float(res_full.iterations)
+            verdict[2] = float(np.abs(mine - c_loc).max() / rng_)
+            full.close()
+        dist.broadcast(verdict, src=0)
+        out["vs_single_gpu_solve"] = {"rel_l2_rank0_slab": float(verdict[0]), "max_abs_over_range": float(verdict[2]),
+                                      "iterations_single_gpu": int(verdict[1])}
+    return out
+
+
+def measure_c5(args, rank, world, local, dist, torch):
+    """BASELINE configs[4]: synthetic FDI 1024^3 nodes (1.07e9 dofs, fp64) on z slabs over all ranks, 1e6 value + 1e5
+    gradient points, solved to the reference tolerance; then c replicated on every GPU (device all-gather) and 1e8 points
+    evaluated (value and gradient), each rank its share."""
+    from loopstructural_b200 import Engine, engine as en, partition
+
+    n = args.c5_n
+    nsteps = np.array([n, n, n])
+    step = np.full(3, 1.0 / (n - 1))
+    bounds = partition.slab_bounds(n, world)
+    eng = Engine(nsteps, np.zeros(3), step, slab=bounds[rank], device=local)
+    ids = [Engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0, device=torch.device("cuda", local))
+    eng.comm_init(ids[0], rank, world)
+    scale = (n / 256.0) ** 3
+    value, gradient = synthetic_points(int(1e5 * scale / 6.4), int(1e4 * scale / 6.4))  # 1e6 + 1e5 at 1024^3 (SURVEY 8d)
+    eng.set_regularisation({})
+    eng.set_options(ridge_factor=1e-8, add_ridge=True, apply_scaling=True)
+    eng.add_point_rows(en.ROWS_VALUE, value, 1.0)
+    eng.add_point_rows(en.ROWS_GRADIENT, gradient, 1.0)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    c_loc, res = eng.solve_cg(rtol=1e-5, atol=0.0, want_c=False)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    scaled, _plain = eng.residual_norm()
+    t_matvec, t_iter = eng.time_kernel(0, reps=10), eng.time_kernel(1, reps=10)
+    peak, _ = measured_peak()
+    tt = torch.tensor([wall, res.solve_seconds, t_matvec, t_iter], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    wall, solve_s, t_matvec, t_iter = (float(v) for v in tt.tolist())
+    # the solve again for a solution to evaluate (time_kernel left the vectors in a timing state)
+    eng.solve_cg(rtol=1e-5, atol=0.0, want_c=False)
+    out = {"grid": f"{n}^3 nodes on {world} z slabs", "value_points": len(value), "gradient_points": len(gradient),
+           "iterations": res.iterations, "solve_seconds": solve_s, "wall_seconds": wall,
+           "residual_norm_recomputed": scaled, "threshold": res.threshold, "residual_ok": bool(scaled <= 1.05 * res.threshold),
+           "matvec_us_max_over_ranks": 1e6 * t_matvec, "iteration_us_max_over_ranks": 1e6 * t_iter,
+           "matvec_frac_of_hbm": BYTES_MATVEC_PER_DOF * eng.local_dof / t_matvec / 1e9 / peak,
+           "iteration_frac_of_hbm": BYTES_ITERATION_PER_DOF * eng.local_dof / t_iter / 1e9 / peak,
+           "peer_memory_scalars": bool(eng.uses_peer_memory)}
+    npts = args.eval_points
+    a, b = partition.split_points(npts, world)[rank]
+    full = partition.replicate_solution(eng, bounds, local)
+    eng.close()
+    gen = torch.Generator(device="cuda").manual_seed(rank)
+    cloud = torch.rand((b - a, 3), dtype=torch.float64, device="cuda", generator=gen)
+    out1 = torch.empty(b - a, dtype=torch.float64, device="cuda")
+    out3 = torch.empty((b - a, 3), dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for name, fn, buf in (("value", full.evaluate_value_device, out1), ("gradient", full.evaluate_gradient_device, out3)):
+        for _ in range(2):
+            fn(cloud.data_ptr(), buf.data_ptr(), b - a, st)
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            fn(cloud.data_ptr(), buf.data_ptr(), b - a, st)
+        e1.record()
+        torch.cuda.synchronize()
+        te = torch.tensor([e0.elapsed_time(e1) * 1e-3 / 3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        out[f"eval_{name}_points_per_second"] = npts / float(te.item())
+    # f = z + 0.1 sin 2 pi x + 0.05 cos 2 pi y is what the data describe: the solved field must follow it
+    f = cloud[:, 2] + 0.1 * torch.sin(2 * np.pi * cloud[:, 0]) + 0.05 * torch.cos(2 * np.pi * cloud[:, 1])
+    err = torch.tensor([float((out1 - f).abs().mean())], dtype=torch.float64, device="cuda")
+    dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    out["eval_points"] = npts
+    out["mean_abs_misfit_to_the_generating_field"] = float(err.item())
+    full.close()
+    return out
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -620,14 +733,30 @@ def run_ours(args):
                      "finite_fraction_rank0": float(torch.isfinite(out1).double().mean().item())}
         full.close()
 
+    # ---- N > 1: correctness of the slab solve (residual through the operator, checksums, 1-GPU solve at N <= 2)
+    check = None
+    if world > 1 and not args.no_check:
+        check = multi_gpu_check(eng, None, nsteps, step, bounds, rank, world, local, value_h, gradient_h, dist, torch)
+
     # ---- roofline of the dominant operator kernel + whole iteration, CUDA events on the engine's stream
     t_matvec = eng.time_kernel(0, reps=20)
     t_iter = eng.time_kernel(1, reps=20)
     t_rows, t_xr, t_p = eng.time_kernel(2, reps=20), eng.time_kernel(3, reps=20), eng.time_kernel(4, reps=20)
     peak, peak_src = measured_peak()
     dof_local = eng.local_dof
+    rows_local = int(eng.num_rows)
     ach = BYTES_MATVEC_PER_DOF * dof_local / t_matvec / 1e9
     ach_it = BYTES_ITERATION_PER_DOF * dof_local / t_iter / 1e9
+
+    # ---- BASELINE configs[4] on the same ranks (8 GPUs by default, --c5 forces it at other counts)
+    c5 = None
+    if world > 1 and (args.c5 or world == 8) and not args.no_c5:
+        eng.close()
+        torch.cuda.empty_cache()
+        try:
+            c5 = measure_c5(args, rank, world, local, dist, torch)
+        except Exception as exc:  # noqa: BLE001
+            c5 = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         value_ = dof_global * its / wall
@@ -654,7 +783,7 @@ def run_ours(args):
                 "matvec k_fdi_box(+zgen)+k_fdi_shell": {"us": 1e6 * t_matvec, "bytes_per_dof": 16, "gbs": 16 * dof_local / t_matvec / 1e9},
                 "k_cg_update_xr": {"us": 1e6 * t_xr, "bytes_per_dof": 56, "gbs": 56 * dof_local / t_xr / 1e9},
                 "k_cg_update_p": {"us": 1e6 * t_p, "bytes_per_dof": 32, "gbs": 32 * dof_local / t_p / 1e9},
-                "k_rows_normal": {"us": 1e6 * t_rows, "rows": int(eng.num_rows)}},
+                "k_rows_normal": {"us": 1e6 * t_rows, "rows": rows_local}},
             "e2e": {"value": dof_global * its_e2e / wall_e2e, "unit": UNIT,
                     "h2d_bytes_per_step": int(value.nbytes + gradient.nbytes),
                     "d2h_bytes_per_step": int(8 * dof_local), "ms_per_step": 1e3 * wall_e2e / max(args.steps, 1)},
@@ -663,6 +792,10 @@ def run_ours(args):
         }
         if eval_info is not None:
             line["eval"] = eval_info
+        if check is not None:
+            line["check"] = check
+        if c5 is not None:
+            line["c5"] = c5
         if world == 1 and not args.no_cpu_baseline:
             # bounded sample on the host cores: the unmodified reference when baseline/_ref travelled with the snapshot
             # (kind "reference"), else the oracle port; one batch of independent solves, one per host thread
@@ -718,6 +851,10 @@ def main():
     ap.add_argument("--eval-points", type=int, default=100_000_000)
     ap.add_argument("--no-experiments", action="store_true", help="skip the unmeasured launch-plan experiments (subprocesses)")
     ap.add_argument("--no-fault", action="store_true", help="skip the fault-frame evaluation measurement")
+    ap.add_argument("--no-check", action="store_true", help="N > 1: skip the correctness check of the slab solve")
+    ap.add_argument("--c5", action="store_true", help="N > 1: also run BASELINE configs[4] (1024^3 solve + 1e8-point evaluation)")
+    ap.add_argument("--no-c5", action="store_true", help="N = 8: skip BASELINE configs[4]")
+    ap.add_argument("--c5-n", type=int, default=1024, help="nodes per axis of the configs[4] grid")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -189,6 +189,17 @@ int lsb200_get_rhs(lsb200_handle h, double* out);
 int lsb200_get_diagonal(lsb200_handle h, double* out);
 int lsb200_get_scaling(lsb200_handle h, double* out); /* S = diag^-1/2 (ones when scaling is off) */
 
+/* 1 when the two scalar reductions of a CG iteration (p.q, r.S^2 r) go through peer-mapped mailboxes (cudaIpc, stores
+ * over NVLink) instead of ncclAllReduce; decided in lsb200_comm_init (all ranks agree).  0 on one rank. */
+int lsb200_comm_uses_peer_memory(lsb200_handle h);
+
+/* Residual of the current solution, recomputed through the operator (not the recurrence the solver carried):
+ * r = A^T W b - N c with N applied by the same kernels as inside CG (halo exchange on z slabs);
+ * *scaled_norm = sqrt(r . S^2 r) -- the quantity scipy's stopping test sees on the column-scaled system
+ * (LI/_solver_strategy.py:48-71, LI/_solver_pipeline.py:86-124) -- and *plain_norm = ||r||_2, both over ALL ranks.
+ * Collective on slab handles.  Uses the search-direction vector as scratch. */
+int lsb200_residual_norm(lsb200_handle h, double* scaled_norm, double* plain_norm);
+
 /* solved node values: DiscreteInterpolator.c (LI/_discrete_interpolator.py:1312-1318) */
 int lsb200_get_c(lsb200_handle h, double* out);
 int lsb200_set_c(lsb200_handle h, const double* c);

@@ -58,12 +58,13 @@ namespace nccl {
 typedef struct ncclComm* comm_t;
 typedef struct { char internal[128]; } unique_id;
 enum { Sum = 0 };
-enum { Float64 = 8 };
+enum { Float64 = 8, Int8 = 0 };
 static void* lib = nullptr;
 static int (*GetUniqueId)(unique_id*) = nullptr;
 static int (*CommInitRank)(comm_t*, int, unique_id, int) = nullptr;
 static int (*CommDestroy)(comm_t) = nullptr;
 static int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+static int (*AllGather)(const void*, void*, size_t, int, comm_t, cudaStream_t) = nullptr;
 static int (*Send)(const void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
 static int (*Recv)(void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
 static int (*GroupStart)() = nullptr;
@@ -80,7 +81,7 @@ static int load() {
 #define SYM(name)                                                                   \
   *(void**)(&name) = dlsym(lib, "nccl" #name);                                      \
   if (!name) return fail(LSB200_ERR_COMM, "libnccl lacks symbol nccl%s", #name);
-  SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(AllReduce) SYM(Send) SYM(Recv) SYM(GroupStart)
+  SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(AllReduce) SYM(AllGather) SYM(Send) SYM(Recv) SYM(GroupStart)
       SYM(GroupEnd) SYM(GetErrorString)
 #undef SYM
   return 0;
@@ -123,6 +124,11 @@ struct lsb200_ctx {
   bool have_c = false;
   nccl::comm_t comm = nullptr;
   int rank = 0, nranks = 1;
+  // scalar reductions over peer-mapped mailboxes (cg.cuh); null = the two ncclAllReduce calls of round 1
+  PeerMailbox* mailbox = nullptr;      // this rank's mailbox (cudaMalloc, exported by cudaIpcGetMemHandle)
+  PeerTable peer_host{};               // peers' mailboxes as mapped here
+  PeerTable* peers = nullptr;          // device copy of peer_host
+  unsigned long long solve_epoch = 0;
   int stencil_cfg = 0;
   int cz = 0;
   dim3 sgrid;
@@ -145,7 +151,7 @@ struct lsb200_ctx {
   HostPipe pipe;  // staging of the host-array entry points (hostpipe.cuh)
 };
 
-constexpr long long PIPE_CHUNK = 1 << 20;  // points per staged chunk (24 MB in, 8-48 MB out)
+constexpr long long PIPE_CHUNK = 1 << 21;  // points per staged chunk (48 MB in, 16-96 MB out)
 static int pipe_result(int rc, cudaError_t e, const char* what) {
   if (e != cudaSuccess) return fail(LSB200_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return rc;
@@ -264,10 +270,10 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
   }
 #define LSB_LAUNCH(XB, TXT, TYT, MINB, ST) LSB_LAUNCH_AT(h->stream, h->sgrid, h->cz, 0, XB, TXT, TYT, MINB, ST)
   if (h->main_cfg >= 0 && h->fused) {
-    // one launch: box tiles (y edges and z faces included) and x strips, sized by plan_fused to one even wave
+    // one launch: interior box tiles (with their z-face planes), x strips and y strips, sized by plan_fused
     const UniConsts U = make_uni_consts(w);
     const FusedPlan& pl = h->fz.pl;
-    const unsigned int ctas = (unsigned int)(pl.n_box + pl.n_strip);
+    const unsigned int ctas = (unsigned int)(pl.n_box + pl.n_xs + pl.n_ys);
     switch (h->fz.tyt) {
 #define X(TYT, ST, MINB)                                                                                          \
   case TYT: {                                                                                                     \
@@ -534,17 +540,20 @@ static int alloc_block(lsb200_ctx* h, RowBlock& rb, long long n, int k) {
   return 0;
 }
 
-static int ensure_vectors(lsb200_ctx* h) {
-  if (h->x) return 0;
-  // One zeroed guard plane in front of and behind the nzl + 4 stored planes: the gather kernels (k_fdi_shell) read
-  // the in-plane taps of the first / last stored plane without clamping -- a tap outside the grid has coefficient
-  // 0 but is still loaded, up to 2 rows + 2 nodes away.  On a single-handle grid those loads fall into the halo
-  // planes; on a z slab the first / last stored plane IS a halo plane, and they would leave the allocation.
+static int ensure_vectors(lsb200_ctx* h, const bool solution_only = false) {
+  // One zeroed guard plane in front of and behind the nzl + 4 stored planes: the gather kernels read the in-plane taps
+  // of the first / last stored plane without clamping -- a tap outside the grid has coefficient 0 but is still loaded,
+  // up to 2 rows + 2 nodes away.  On a single-handle grid those loads fall into the halo planes; on a z slab the first /
+  // last stored plane IS a halo plane, and they would leave the allocation.
+  // solution_only: a handle that only evaluates a field set by lsb200_set_c(_dev) (the replicated solution of a slab
+  // solve, a fault-frame coordinate) holds x alone -- one node vector instead of seven.
   const size_t guard = ((size_t)h->g.plane + 31) & ~(size_t)31;  // keeps the 256-byte alignment of the base
   h->guard = (long long)guard;
   const size_t bytes = sizeof(double) * ((size_t)h->g.nall + 2 * guard);
   double** v[] = {&h->x, &h->r, &h->p, &h->q, &h->rhs, &h->diag, &h->s2};
   for (double** pv : v) {
+    if (*pv) continue;
+    if (solution_only && pv != &h->x) continue;
     double* raw = nullptr;
     cudaError_t e = cudaMalloc(&raw, bytes);
     if (e != cudaSuccess) return fail(LSB200_ERR_ALLOC, "cudaMalloc of a node vector (%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
@@ -676,6 +685,10 @@ int lsb200_destroy(lsb200_handle h) {
   cudaFree(h->p1_off);
   cudaFree(h->p1_diag);
   cudaFree(h->ztab);
+  for (int r = 0; r < h->peer_host.nranks; ++r)
+    if (h->peers && r != h->rank && h->peer_host.box[r]) cudaIpcCloseMemHandle(h->peer_host.box[r]);
+  cudaFree(h->peers);
+  cudaFree(h->mailbox);
   if (h->comm) nccl::CommDestroy(h->comm);
   h->pipe.destroy();
   for (int t = 0; t < 3; ++t) {
@@ -1187,8 +1200,86 @@ int lsb200_comm_init(lsb200_handle h, const unsigned char nccl_id[128], int rank
   NCK(nccl::CommInitRank(&h->comm, nranks, id, rank));
   h->rank = rank;
   h->nranks = nranks;
+  // a slab needs HALO owned planes to feed its neighbours' halos, and the slabs must tile the grid in rank order
+  if (h->g.nzl < HALO) return fail(LSB200_ERR_ARG, "rank %d owns %d planes; a z slab needs at least %d", rank, h->g.nzl, HALO);
+  {
+    int* d_k = nullptr;
+    std::vector<int> hk(2 * (size_t)nranks);
+    const int mine[2] = {h->g.k0, h->g.k1};
+    CK(cudaMalloc(&d_k, sizeof(int) * 2 * (nranks + 1)));
+    CK(cudaMemcpyAsync(d_k + 2 * nranks, mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+    NCK(nccl::AllGather(d_k + 2 * nranks, d_k, sizeof(mine), nccl::Int8, h->comm, h->stream));
+    CK(cudaMemcpyAsync(hk.data(), d_k, sizeof(int) * 2 * nranks, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_k);
+    for (int r = 0; r < nranks; ++r) {
+      const int want = r == 0 ? 0 : hk[2 * (r - 1) + 1];
+      if (hk[2 * r] != want || (r == nranks - 1 && hk[2 * r + 1] != h->g.nz))
+        return fail(LSB200_ERR_ARG, "the slabs of the %d ranks do not tile the %d planes in rank order (rank %d owns [%d,%d))", nranks,
+                    h->g.nz, r, hk[2 * r], hk[2 * r + 1]);
+    }
+  }
+  // peer mailboxes for the two scalar reductions of an iteration; LSB200_PEER_SCALARS=0 (or any failure to map a peer,
+  // e.g. no P2P path between the devices) keeps ncclAllReduce
+  static const bool want_peers = !(getenv("LSB200_PEER_SCALARS") && atoi(getenv("LSB200_PEER_SCALARS")) == 0);
+  if (want_peers && nranks <= PEER_MAX_RANKS) {
+    bool ok = true;
+    cudaIpcMemHandle_t mine;
+    std::vector<cudaIpcMemHandle_t> all((size_t)nranks);
+    char* d_h = nullptr;
+    ok = ok && cudaMalloc(&h->mailbox, sizeof(PeerMailbox)) == cudaSuccess;
+    ok = ok && cudaMemset(h->mailbox, 0, sizeof(PeerMailbox)) == cudaSuccess;
+    ok = ok && cudaIpcGetMemHandle(&mine, h->mailbox) == cudaSuccess;
+    ok = ok && cudaMalloc(&d_h, sizeof(mine) * (nranks + 1)) == cudaSuccess;
+    // every rank takes part in the collective even when its own set-up failed (its handle is then all zeros)
+    if (!ok) memset(&mine, 0, sizeof(mine));
+    if (d_h) {
+      CK(cudaMemcpyAsync(d_h + sizeof(mine) * nranks, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+      NCK(nccl::AllGather(d_h + sizeof(mine) * nranks, d_h, sizeof(mine), nccl::Int8, h->comm, h->stream));
+      CK(cudaMemcpyAsync(all.data(), d_h, sizeof(mine) * nranks, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      cudaFree(d_h);
+    } else {
+      ok = false;
+    }
+    PeerTable pt{};
+    pt.rank = rank;
+    pt.nranks = nranks;
+    for (int r = 0; r < nranks && ok; ++r) {
+      bool zero = true;
+      for (size_t t = 0; t < sizeof(mine); ++t) zero = zero && reinterpret_cast<const char*>(&all[r])[t] == 0;
+      if (zero) { ok = false; break; }
+      if (r == rank) { pt.box[r] = h->mailbox; continue; }
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+      pt.box[r] = (PeerMailbox*)ptr;
+    }
+    // all ranks must agree: one rank on NCCL and its peers on mailboxes would wait for each other for ever
+    int* d_ok = nullptr;
+    CK(cudaMalloc(&d_ok, sizeof(int) * (nranks + 1)));
+    const int my_ok = ok ? 1 : 0;
+    std::vector<int> oks((size_t)nranks);
+    CK(cudaMemcpyAsync(d_ok + nranks, &my_ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    NCK(nccl::AllGather(d_ok + nranks, d_ok, sizeof(int), nccl::Int8, h->comm, h->stream));
+    CK(cudaMemcpyAsync(oks.data(), d_ok, sizeof(int) * nranks, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_ok);
+    for (int r = 0; r < nranks; ++r) ok = ok && oks[r] == 1;
+    if (ok) {
+      h->peer_host = pt;
+      CK(cudaMalloc(&h->peers, sizeof(PeerTable)));
+      CK(cudaMemcpy(h->peers, &pt, sizeof(PeerTable), cudaMemcpyHostToDevice));
+    } else {
+      for (int r = 0; r < nranks; ++r)
+        if (r != rank && pt.box[r]) cudaIpcCloseMemHandle(pt.box[r]);
+      cudaFree(h->mailbox);
+      h->mailbox = nullptr;
+    }
+  }
   return 0;
 }
+
+int lsb200_comm_uses_peer_memory(lsb200_handle h) { return (h && h->peers) ? 1 : 0; }
 
 // q = N p on device vectors (p must have its halo planes filled on slab handles)
 static int apply_normal_dev(lsb200_ctx* h, const double* p, double* q, int parts, int cg_mode) {
@@ -1253,7 +1344,7 @@ int lsb200_get_c(lsb200_handle h, double* out) {
 int lsb200_set_c(lsb200_handle h, const double* c) {
   if (!h || !c) return fail(LSB200_ERR_ARG, "null argument");
   CK(cudaSetDevice(h->device));
-  int rc = ensure_vectors(h);
+  int rc = ensure_vectors(h, true);
   if (rc) return rc;
   if ((rc = copy_in(h, h->x, c))) return rc;
   h->have_c = true;
@@ -1274,7 +1365,7 @@ int lsb200_get_c_dev(lsb200_handle h, double* c_dev, void* stream) {
 int lsb200_set_c_dev(lsb200_handle h, const double* c_dev, void* stream) {
   if (!h || !c_dev) return fail(LSB200_ERR_ARG, "null argument");
   CK(cudaSetDevice(h->device));
-  int rc = ensure_vectors(h);
+  int rc = ensure_vectors(h, true);
   if (rc) return rc;
   CK(cudaStreamSynchronize(h->stream));  // ensure_vectors zeroes the vectors on the handle's stream
   CK(cudaMemcpy2DAsync(owned_ptr(h, h->x), sizeof(double) * h->g.pitch, c_dev, sizeof(double) * h->g.nx, sizeof(double) * h->g.nx,
@@ -1316,19 +1407,29 @@ static int enqueue_iteration(lsb200_ctx* h) {
   }
   if ((rc = apply_normal_dev(h, h->p, h->q, 3, 1))) return rc;
   if (h->nranks > 1) {
-    k_cg_pack_pq<<<1, 1, 0, h->stream>>>(h->sc);
-    CKL();
-    h->launches++;
-    if ((rc = allreduce_scalar(h, &h->sc->pq))) return rc;
+    if (h->peers) {
+      k_cg_push_pq<<<1, 32, 0, h->stream>>>(h->sc, h->peer_host);
+      CKL();
+      h->launches++;
+    } else {
+      k_cg_pack_pq<<<1, 1, 0, h->stream>>>(h->sc);
+      CKL();
+      h->launches++;
+      if ((rc = allreduce_scalar(h, &h->sc->pq))) return rc;
+    }
   }
   k_cg_update_xr<VEC_NT><<<vec_blocks(h, n), VEC_NT, 0, h->stream>>>(n, owned_ptr(h, h->p), owned_ptr(h, h->q), owned_ptr(h, h->x),
                                                                       owned_ptr(h, h->r), s2, h->partials + 2 * MAX_PARTIALS,
-                                                                      h->counters + 2, h->sc);
+                                                                      h->counters + 2, h->sc, h->peers);
   CKL();
   h->launches++;
   if (h->nranks > 1) {
-    if ((rc = allreduce_scalar(h, &h->sc->rho_new))) return rc;
-    k_cg_scalar_step<<<1, 1, 0, h->stream>>>(h->sc);
+    if (h->peers) {
+      k_cg_pull_rho<<<1, 32, 0, h->stream>>>(h->sc, h->peer_host);
+    } else {
+      if ((rc = allreduce_scalar(h, &h->sc->rho_new))) return rc;
+      k_cg_scalar_step<<<1, 1, 0, h->stream>>>(h->sc);
+    }
     CKL();
     h->launches++;
   }
@@ -1402,6 +1503,7 @@ int lsb200_solve_cg(lsb200_handle h, double rtol, double atol, int64_t maxiter, 
     init.iter = 0;
     init.maxiter = maxit;
     init.nranks = h->nranks;
+    init.epoch = (++h->solve_epoch) << 32;
     init.info = 0;
     for (int t = 0; t < 5; ++t) init.pq_part[t] = 0.0;
     init.done = (sqrt(init.rho) < thr) ? 1 : 0;
@@ -1496,6 +1598,33 @@ int lsb200_solve_cg(lsb200_handle h, double rtol, double atol, int64_t maxiter, 
   h->have_c = true;
   if (info) *info = res;
   if (c_out) return copy_out(h, c_out, h->x);
+  return 0;
+}
+
+int lsb200_residual_norm(lsb200_handle h, double* scaled_norm, double* plain_norm) {
+  if (!h || !scaled_norm || !plain_norm) return fail(LSB200_ERR_ARG, "null argument");
+  if (!h->have_c) return fail(LSB200_ERR_STATE, "no solution on the device yet (solve or set_c first)");
+  CK(cudaSetDevice(h->device));
+  int rc = lsb200_finalize_system(h);
+  if (rc) return rc;
+  const long long n = h->g.nloc;
+  if ((rc = halo_exchange(h, h->x))) return rc;
+  if ((rc = apply_normal_dev(h, h->x, h->q, 3, 0))) return rc;
+  CgScalars* sc = h->sc;
+  const double* s2 = h->apply_scaling ? owned_ptr(h, h->s2) : nullptr;
+  k_cg_residual<VEC_NT><<<vec_blocks(h, n), VEC_NT, 0, h->stream>>>(n, owned_ptr(h, h->rhs), owned_ptr(h, h->q), owned_ptr(h, h->p), s2,
+                                                                     h->partials + 2 * MAX_PARTIALS, h->counters + 2, &sc->rho_new);
+  CKL();
+  k_cg_residual<VEC_NT><<<vec_blocks(h, n), VEC_NT, 0, h->stream>>>(n, owned_ptr(h, h->p), nullptr, nullptr, nullptr,
+                                                                     h->partials + 2 * MAX_PARTIALS, h->counters + 2, &sc->pq);
+  CKL();
+  h->launches += 2;
+  if ((rc = allreduce_scalar(h, &sc->rho_new))) return rc;
+  if ((rc = allreduce_scalar(h, &sc->pq))) return rc;
+  CK(cudaMemcpyAsync(h->sc_host, sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *scaled_norm = sqrt(h->sc_host->rho_new);
+  *plain_norm = sqrt(h->sc_host->pq);
   return 0;
 }
 
@@ -1849,7 +1978,7 @@ int lsb200_eval_lattice(lsb200_handle h, const double* transform, const double s
   const int ow = gradient ? 3 : 1;
   cudaError_t ce;
   const bool tet = F.kind == LSB200_SUPPORT_TETMESH;
-  rc = h->pipe.run(total, 4 * PIPE_CHUNK, 0, nullptr, ow * sizeof(double), out, 0, nullptr, 0,
+  rc = h->pipe.run(total, 2 * PIPE_CHUNK, 0, nullptr, ow * sizeof(double), out, 0, nullptr, 0,
                    [&](cudaStream_t st, long long o, long long m, double*, double* d0, double*, double*) -> int {
                      if (tet) k_eval_lattice<true><<<frame_blocks(h, m), 256, 0, st>>>(F, lat, o, m, gradient ? 1 : 0, d0);
                      else k_eval_lattice<false><<<frame_blocks(h, m), 256, 0, st>>>(F, lat, o, m, gradient ? 1 : 0, d0);
@@ -1888,6 +2017,7 @@ int lsb200_time_kernel(lsb200_handle h, int which, int reps, double* seconds_per
   CgScalars s;
   memset(&s, 0, sizeof(s));
   s.rho = 1.0; s.pq = 1.0; s.pq_part[0] = 1.0; s.beta = 0.5; s.thr2 = 0.0; s.maxiter = 1LL << 60; s.nranks = h->nranks;
+  s.epoch = (++h->solve_epoch) << 32;
   *h->sc_host = s;
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
@@ -1909,7 +2039,7 @@ int lsb200_time_kernel(lsb200_handle h, int which, int reps, double* seconds_per
       if (which == 3)
         k_cg_update_xr<VEC_NT><<<vec_blocks(h, n), VEC_NT, 0, h->stream>>>(n, owned_ptr(h, h->p), owned_ptr(h, h->q), owned_ptr(h, h->x),
                                                                             owned_ptr(h, h->r), s2, h->partials + 2 * MAX_PARTIALS,
-                                                                            h->counters + 2, h->sc);
+                                                                            h->counters + 2, h->sc, h->peers);
       else
         k_cg_update_p<VEC_NT><<<vec_blocks(h, n), VEC_NT, 0, h->stream>>>(n, s2, owned_ptr(h, h->r), owned_ptr(h, h->p), h->sc);
       CKL();

@@ -29,6 +29,67 @@ __device__ __forceinline__ void cg_scalar_step(CgScalars* sc, double rho_new) {
   }
 }
 
+// ---- multi-rank scalar reductions over peer-mapped memory ----------------------------------------------------------
+// Round 1 all-reduced p.q and r.S^2 r with two 8-byte ncclAllReduce calls per iteration, serial on the critical path
+// (~70 us at 2 ranks, more at 8: SCALE_r01).  Here every rank owns a small mailbox in device memory that its peers have
+// mapped (cudaIpcOpenMemHandle, lsb200_comm_init): a rank STORES its partial into slot [parity][kind][rank] of every
+// mailbox, fences, and stores the sequence number of the iteration into the matching flag; a reader spins on the flags
+// of its OWN mailbox (local memory) and sums the partials in rank order, so that every rank forms bit-identical
+// scalars and the result does not depend on arrival order.  Two parities: a rank can be at most one reduction ahead of
+// the slowest reader of the previous one (it needs that reader's partial of the current reduction to get further).
+constexpr int PEER_MAX_RANKS = 16;
+struct PeerMailbox {
+  double val[2][2][PEER_MAX_RANKS];                 // [parity][kind: 0 = p.q, 1 = rho][writer rank]
+  unsigned long long flag[2][2][PEER_MAX_RANKS];    // sequence number of the iteration the value belongs to
+};
+struct PeerTable {
+  PeerMailbox* box[PEER_MAX_RANKS];  // box[r]: rank r's mailbox as mapped into this process (box[rank] = the local one)
+  int rank, nranks;
+};
+
+__device__ __forceinline__ void peer_push(const PeerTable& pt, const int kind, const unsigned long long seq, const double v) {
+  // one lane per peer
+  const int r = threadIdx.x;
+  if (r < pt.nranks) {
+    PeerMailbox* mb = pt.box[r];
+    const int par = (int)(seq & 1ull);
+    mb->val[par][kind][pt.rank] = v;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(&mb->flag[par][kind][pt.rank]) = seq;
+  }
+}
+
+// sum of all ranks' partials of reduction (kind, seq), in rank order; every calling thread gets the value
+__device__ __forceinline__ double peer_pull(const PeerTable& pt, const int kind, const unsigned long long seq) {
+  const PeerMailbox* mb = pt.box[pt.rank];
+  const int par = (int)(seq & 1ull);
+  double s = 0.0;
+  for (int r = 0; r < pt.nranks; ++r) {
+    const volatile unsigned long long* f = &mb->flag[par][kind][r];
+    while (*f != seq) {
+    }
+    __threadfence_system();
+    s += *reinterpret_cast<const volatile double*>(&mb->val[par][kind][r]);
+  }
+  return s;
+}
+
+// after the matvec: this rank's p.q (all parts) to every peer.  <<<1, 32>>>
+__global__ void k_cg_push_pq(CgScalars* sc, const PeerTable pt) {
+  if (sc->done) return;
+  const double v = (((sc->pq_part[0] + sc->pq_part[2]) + sc->pq_part[3]) + sc->pq_part[4]) + sc->pq_part[1];
+  peer_push(pt, 0, sc->epoch + (unsigned long long)sc->iter + 1ull, v);
+}
+// after the x / r update has pushed its partial of rho: gather, advance the scalar state.  <<<1, 32>>>
+__global__ void k_cg_pull_rho(CgScalars* sc, const PeerTable pt) {
+  if (sc->done) return;
+  const double rho_new = peer_pull(pt, 1, sc->epoch + (unsigned long long)sc->iter + 1ull);
+  if (threadIdx.x == 0) {
+    sc->rho_new = rho_new;
+    cg_scalar_step(sc, rho_new);
+  }
+}
+
 // p = S^2 r + beta p   (s2 == nullptr: no scaling)
 template <int NT>
 __global__ void __launch_bounds__(NT)
@@ -62,10 +123,22 @@ template <int NT>
 __global__ void __launch_bounds__(NT)
     k_cg_update_xr(const long long n, const double* __restrict__ p, const double* __restrict__ q,
                    double* __restrict__ x, double* __restrict__ r, const double* __restrict__ s2,
-                   double* __restrict__ partials, unsigned int* __restrict__ counter, CgScalars* __restrict__ sc) {
+                   double* __restrict__ partials, unsigned int* __restrict__ counter, CgScalars* __restrict__ sc,
+                   const PeerTable* __restrict__ peers) {
   __shared__ double red[NT / 32];
+  __shared__ double s_pq;
   if (sc->done) return;
-  const double pq = sc->nranks == 1 ? (((sc->pq_part[0] + sc->pq_part[2]) + sc->pq_part[3]) + sc->pq_part[4]) + sc->pq_part[1] : sc->pq;
+  double pq;
+  if (sc->nranks == 1) {
+    pq = (((sc->pq_part[0] + sc->pq_part[2]) + sc->pq_part[3]) + sc->pq_part[4]) + sc->pq_part[1];
+  } else if (peers) {
+    // every block waits for the partials of all ranks in its own mailbox (k_cg_push_pq of each rank) and sums them
+    if (threadIdx.x == 0) s_pq = peer_pull(*peers, 0, sc->epoch + (unsigned long long)sc->iter + 1ull);
+    __syncthreads();
+    pq = s_pq;
+  } else {
+    pq = sc->pq;
+  }
   const double alpha = sc->rho / pq;
   const long long n2 = n >> 1;
   const double2* p2 = reinterpret_cast<const double2*>(p);
@@ -99,13 +172,23 @@ __global__ void __launch_bounds__(NT)
   }
   const double bsum = block_sum<NT>(acc, red);
   double total;
-  if (grid_sum_last_block<NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total)) {
+  __shared__ double s_total;
+  __shared__ int s_push;
+  const bool last = grid_sum_last_block<NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total);
+  if (threadIdx.x == 0) s_push = 0;
+  __syncthreads();
+  if (last) {
     sc->rho_new = total;
     if (sc->nranks == 1) cg_scalar_step(sc, total);
+    else if (peers) { s_total = total; s_push = 1; }
+  }
+  if (sc->nranks > 1 && peers) {
+    __syncthreads();
+    if (s_push) peer_push(*peers, 1, sc->epoch + (unsigned long long)sc->iter + 1ull, s_total);  // lanes 0..nranks-1 of the last block
   }
 }
 
-// multi-rank: scalar steps run as tiny kernels after the all-reduce
+// multi-rank, NCCL fallback (no peer mapping): scalar steps run as tiny kernels after the all-reduce
 __global__ void k_cg_pack_pq(CgScalars* sc) {
   if (sc->done) return;
   sc->pq = (((sc->pq_part[0] + sc->pq_part[2]) + sc->pq_part[3]) + sc->pq_part[4]) + sc->pq_part[1];

@@ -86,6 +86,7 @@ struct CgScalars {
   int info;
   int nranks;
   int pad;
+  unsigned long long epoch;  // solve counter << 32: makes the sequence numbers of the peer mailboxes unique across solves
 };
 
 // Dynamic shared memory of a kernel.  (LSB_EMU: tests/hostsim/cuda_emu.h runs the block-level kernels on the CPU, one

@@ -4,20 +4,26 @@
 // x/y ring).  The ring kernel -- one thread per column gathering from global memory -- is latency bound (39 us alone
 // at 256^3 for 5 % of the nodes, profiles/r02c) and cannot co-reside with the register-hungry box CTAs, so ~28 us of it
 // trailed every matvec; the z-face launch queued behind the box for the same reason.  Here every node is computed by a
-// CTA of the same launch, staged through shared memory like the box:
+// CTA of the same launch, all staged through shared memory, in three roles:
 //
-//   BOX CTAs    tile of 64 x TY nodes over the columns 4 <= i < nx-4 and ALL rows 0 <= j < ny, a chunk of cz planes.
-//               Every plane step is the register-tiled constant-coefficient update of k_fdi_box (uni_plane_fast, 20
-//               fp64 operations per node); the steps whose incoming plane lies within 5 planes of a z face use the
-//               z-general twin (zgen_plane_fast, coefficients of that plane from a 10-entry table in shared memory).
-//               The rows next to a y face (j < 3 or j >= ny-3) are exact through the ghost-cell formulation of
-//               fdi_stencil.cuh -- rows -1,-2 / ny,ny+1 of the staged tile hold the mirrored rows -- plus a fix-up
-//               (y_edge_fix) that only the warps owning such rows execute (a warp owns whole rows: no divergence).
-//   STRIP CTAs  the 4 columns next to an x face, NT rows, a chunk of planes; lanes run along y, a thread owns the 4
-//               nodes of its row.  The right strip is staged mirrored (local column c = global nx-1-c), so both sides
-//               run the same code with compile-time x coefficients (T_x end corrections, the dx border rows, C_x on
-//               ghost columns); y and z coefficients are general.  Strips are 3 % of the nodes at 256^3; their CTAs
-//               are ordinary members of the launch, sized by the planner so that the whole grid is one even wave.
+//   BOX       tile of 64 x TY nodes over the interior columns 4 <= i < nx-4 and rows 3 <= j < ny-3, a chunk of planes.
+//             Its output planes 3 <= k < nz-3 are the register-tiled constant-coefficient march of k_fdi_box
+//             (uni_plane_fast: 20 fp64 operations per node, every coefficient a launch constant, nothing else in the
+//             loop).  A chunk that owns planes next to a z face (k < 3 or k >= nz-3) first computes those <= 3 planes in
+//             GATHER form from the <= 5 planes it stages at once (z_face_block): general z coefficients per output
+//             plane, scalar shared-memory reads, few registers -- it runs once per CTA, not per plane step.
+//   X STRIP   the 4 columns next to an x face, NT rows, a chunk of planes: lanes along y, a thread owns the 4 nodes of its
+//             row.  Y STRIP: the 3 rows next to a y face over the box columns, NT columns: lanes along x, a thread owns
+//             the 3 nodes of its column.  One routine serves both (strip_cta<AXIS>): along the strip's NORMAL axis the
+//             local index c = 0 is the face (the far side is staged mirrored), so the end corrections of T, the border
+//             rows and the ghost cells of C are compile-time constants per c; along its TANGENT axis the five taps come
+//             from a per-thread table computed once (constant except next to the other faces, i.e. in the corners);
+//             z coefficients per plane from a table in shared memory.
+//
+// A strip node costs several box nodes, but strips are 5 % of a 256^3 grid (2.7 % of 512^3); their CTAs are ordinary
+// members of the launch, dispatched first, chunked short so that none of them outlasts a box CTA (plan_fused).
+// (Measured dead ends, profiles/r2b-r2d: y edges and z faces inside the box march -- inlined they push the hot loop into
+// register spills, out of line the warps that own edge rows serialise 6 calls per plane step and hold their CTA back.)
 //
 // Operator (fdi_main.cuh / fdi_stencil.cuh): q = ridge^2 p + sum_a (a_aa m_b m_c T_a + d_a B_a) p
 //   + sum_{a<b} b_ab m_c (C_a (x) C_b) p, masks m(r) = [1 <= r <= n-2]; reference: assemble_inner / assemble_borders
@@ -28,12 +34,13 @@
 namespace lsb {
 
 struct FusedPlan {
-  int tiles_x, tiles_y;   // box tiles over columns [4, nx-4) x rows [0, ny)
+  int tiles_x, tiles_y;   // box tiles over columns [4, nx-4) x rows [3, ny-3)
   int cz, chunks;         // z chunks of the box CTAs over the owned planes
   int n_box;              // tiles_x * tiles_y * chunks
-  int strips_y;           // strip CTAs per side and z chunk: ceil(ny / NT)
+  int xs_y;               // x-strip CTAs per side and z chunk: ceil(ny / NT)
+  int ys_x;               // y-strip CTAs per side and z chunk: ceil((nx - 8) / NT)
   int scz, schunks;       // z chunks of the strip CTAs
-  int n_strip;            // 2 * strips_y * schunks
+  int n_xs, n_ys;         // 2 * xs_y * schunks, 2 * ys_x * schunks
 };
 
 // z coefficients of one incoming plane kp: what it contributes to the output planes kp-2..kp+2.  l* = azz T_z + dz B_z
@@ -82,204 +89,247 @@ __device__ __forceinline__ ZFull z_uniform(const double azz) {
 
 // an incoming plane kp whose five output planes all have the constant interior z coefficients
 __device__ __forceinline__ bool z_step_uniform(const int kp, const int nz) { return kp >= 5 && kp <= nz - 6; }
-
-// index of a non-uniform plane in the 10-entry table of a box CTA: planes 0..4 and nz-5..nz-1 (nz >= 10 is not needed:
-// an entry is recomputed per plane, the two ranges may overlap)
+// index of a non-uniform plane in the table of a strip CTA: planes 0..4 -> 0..4, nz-5..nz-1 -> 5..9 (entries are
+// computed per plane, so the two ranges may overlap on grids of fewer than 10 planes)
 __device__ __forceinline__ int z_slot(const int kp, const int nz) { return kp < 5 ? kp : 5 + (kp - (nz - 5)); }
 
 // end corrections of the ghost-cell 1-D operators at index i of n (fdi_stencil.cuh header): T differs from the constant
 // 5-tap stencil by  q(0) -= p0 - p1,  q(1) += (p0 - p1)/3  (mirrored at the upper end); border rows B = d d^T / 6 on the
-// rows 1 and n-2.  pm2..pp2 are p(i-2..i+2) on ghost data.
-__device__ __forceinline__ double t_end_corr(const int i, const int n, const double pm1, const double p0, const double pp1) {
-  double c = 0.0;
-  if (i == 0) c = -(p0 - pp1);
-  if (i == 1) c = (pm1 - p0) * (1.0 / 3.0);
-  if (i == n - 1) c += -(p0 - pm1);
-  if (i == n - 2) c += (pp1 - p0) * (1.0 / 3.0);
-  return c;
-}
-__device__ __forceinline__ double b_rows(const int i, const int n, const double pm2, const double pm1, const double p0,
-                                         const double pp1, const double pp2) {
-  double c = 0.0;
+// rows 1 and n-2.  As coefficients of the taps p(i-2) .. p(i+2) on ghost data (tc: constant T plus corrections,
+// bc: border rows), computed once per thread.
+__device__ __forceinline__ void line_coefficients(const int i, const int n, double (&tc)[5], double (&bc)[5]) {
+  tc[0] = tc[4] = 1.0 / 6.0;
+  tc[1] = tc[3] = -2.0 / 3.0;
+  tc[2] = 1.0;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) bc[s] = 0.0;
+  if (i == 0) { tc[2] -= 1.0; tc[3] += 1.0; }                // -(p0 - p(+1))
+  if (i == 1) { tc[1] += 1.0 / 3.0; tc[2] -= 1.0 / 3.0; }    // (p(-1) - p0) / 3
+  if (i == n - 1) { tc[2] -= 1.0; tc[1] += 1.0; }
+  if (i == n - 2) { tc[3] += 1.0 / 3.0; tc[2] -= 1.0 / 3.0; }
   // lower border row, centred on index 1, touches 0,1,2; upper, centred on n-2, touches n-3,n-2,n-1
-  if (i == 0) c += (p0 - 2.0 * pp1 + pp2);
-  if (i == 1) c += -2.0 * (pm1 - 2.0 * p0 + pp1);
-  if (i == 2) c += (pm2 - 2.0 * pm1 + p0);
-  if (i == n - 1) c += (p0 - 2.0 * pm1 + pm2);
-  if (i == n - 2) c += -2.0 * (pp1 - 2.0 * p0 + pm1);
-  if (i == n - 3) c += (pp2 - 2.0 * pp1 + p0);
-  return c * (1.0 / 6.0);
-}
-
-// Fix-up of the box update for the output rows of this thread that lie within 3 rows of a y face.  Sc as in
-// uni_plane_fast (staged element (row j0-2, column i0-2) of the incoming plane); the uniform update has already been
-// accumulated with m_y = 1 and the constant T_y, no dy rows.  Adds (true - uniform) for those rows:
-//   dA0   = mz (-d axx X_u + ayy ycorr) + dy yb - d t0 p0 + c0 dG,   dG = -d bxz gx,  d = 1 - m_y(j)
-//   dA+-1 = -d t+-1 p0,   dA+-2 = -d t+-2 p0 + c+-2 dG
-template <int YB, int SX>
-__device__ __forceinline__ void y_edge_fix(const double* __restrict__ Sc, const UniConsts& K, const double dyw, const ZFull& Z,
-                                           const int j0, const int ny, double (&Am2)[YB][2], double (&Am1)[YB][2],
-                                           double (&A0)[YB][2], double (&Ap1)[YB][2], double (&Ap2)[YB][2]) {
-#pragma unroll
-  for (int r = 0; r < YB; ++r) {
-    const int j = j0 + r;
-    if (j >= 3 && j < ny - 3) continue;
-    if (j >= ny) continue;
-    const double* R = Sc + (r + 2) * SX;  // row j, columns i0-2 .. i0+3
-    const double d = (j == 0 || j == ny - 1) ? 1.0 : 0.0;
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const double p0 = R[2 + e];
-      const double ym2 = R[2 + e - 2 * SX], ym1 = R[2 + e - SX], yp1 = R[2 + e + SX], yp2 = R[2 + e + 2 * SX];
-      const double ycorr = t_end_corr(j, ny, ym1, p0, yp1);
-      const double yb = b_rows(j, ny, ym2, ym1, p0, yp1, yp2);
-      const double h2 = R[e] + R[4 + e];
-      const double xu = fma(1.0 / 6.0, h2, fma(-2.0 / 3.0, R[1 + e] + R[3 + e], p0));  // constant T_x on interior columns
-      const double gx = 2.0 * p0 - h2;
-      const double dG = -d * K.bxz * gx;
-      const double axx = K.cx1 * (-1.5);  // cx1 = -2 axx / 3
-      const double ayy = K.cy1 * (-1.5);
-      const double dp = d * p0;
-      A0[r][e] += Z.mz * fma(ayy, ycorr, -d * axx * xu) + dyw * yb - Z.t0 * dp + Z.c0 * dG;
-      Am1[r][e] -= Z.tm1 * dp;
-      Ap1[r][e] -= Z.tp1 * dp;
-      Am2[r][e] += fma(Z.cm2, dG, -Z.tm2 * dp);
-      Ap2[r][e] += fma(Z.cp2, dG, -Z.tp2 * dp);
-    }
-  }
+  constexpr double s6 = 1.0 / 6.0;
+  if (i == 0) { bc[2] += s6; bc[3] -= 2.0 * s6; bc[4] += s6; }
+  if (i == 1) { bc[1] -= 2.0 * s6; bc[2] += 4.0 * s6; bc[3] -= 2.0 * s6; }
+  if (i == 2) { bc[0] += s6; bc[1] -= 2.0 * s6; bc[2] += s6; }
+  if (i == n - 1) { bc[2] += s6; bc[1] -= 2.0 * s6; bc[0] += s6; }
+  if (i == n - 2) { bc[3] -= 2.0 * s6; bc[2] += 4.0 * s6; bc[1] -= 2.0 * s6; }
+  if (i == n - 3) { bc[4] += s6; bc[3] -= 2.0 * s6; bc[2] += s6; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// STRIP role: 4 columns next to an x face (side 0: columns 0..3, side 1: columns nx-1..nx-4 as local 0..3), rows
-// [y0, y0 + NT), output planes [ka, kb).  Staged plane: NT + 4 rows (ghost-mapped in y) of 6 local columns.
-constexpr int STRIP_SC = 6;  // staged local columns 0..5
+// STRIP roles.  AXIS = 0: x strip (normal axis x, W = 4 columns, tangent axis y: a thread owns a row); AXIS = 1: y strip
+// (normal axis y, W = 3 rows, tangent axis x: a thread owns a column).  side 1 is staged mirrored along the normal axis
+// (local index c <-> global n-1-c).  t0 = first tangent index of this CTA, [t_lo, t_hi) = the tangent range the strip
+// owns (x strips: every row; y strips: the box columns).  Staged plane: (NT + 4) tangent positions x (W + 2) normal
+// positions; element (tangent tt, normal c) at tt * ST_T + c * ST_C.
+template <int AXIS>
+struct StripGeom {
+  static constexpr int W = AXIS == 0 ? 4 : 3;
+  static constexpr int NC = W + 2;
+};
 
-template <int NT, int ST>
-__device__ __forceinline__ double strip_cta(const GridDesc& g, const StencilWeights& w, const double* __restrict__ ztab,
+template <int NT, int ST, int AXIS>
+__device__ __forceinline__ double strip_cta(const GridDesc& g, const StencilWeights& w, const ZFull* __restrict__ zfm,
                                             const double* __restrict__ p, double* __restrict__ q, const int side,
-                                            const int y0, const int ka, const int kb, double* __restrict__ S, const int tid) {
-  constexpr int ROWS = NT + 2 * HALO;
-  constexpr int PLANE = ROWS * STRIP_SC;
+                                            const int t0, const int t_lo, const int t_hi, const int ka, const int kb,
+                                            double* __restrict__ S, const int tid) {
+  constexpr int W = StripGeom<AXIS>::W, NC = StripGeom<AXIS>::NC;
+  constexpr int TT = NT + 2 * HALO;
+  constexpr int PLANE = TT * NC;
+  constexpr int ST_T = AXIS == 0 ? NC : 1;   // x strip: rows of NC columns; y strip: NC rows of TT columns
+  constexpr int ST_C = AXIS == 0 ? 1 : TT;
   constexpr int LD = (PLANE + NT - 1) / NT;
+  const int n_t = AXIS == 0 ? g.ny : g.nx;   // length of the tangent axis
+  const int n_n = AXIS == 0 ? g.nx : g.ny;
+  // weights seen from the strip: normal / tangent second derivatives, border rows, mixed terms with z
+  const double a_n = AXIS == 0 ? w.axx : w.ayy, a_t = AXIS == 0 ? w.ayy : w.axx;
+  const double d_n = AXIS == 0 ? w.dx : w.dy, d_t = AXIS == 0 ? w.dy : w.dx;
+  const double b_nz = AXIS == 0 ? w.bxz : w.byz, b_tz = AXIS == 0 ? w.byz : w.bxz;
+
   int off[LD];
 #pragma unroll
   for (int t = 0; t < LD; ++t) {
     const int idx = tid + t * NT;
     off[t] = -1;
     if (idx < PLANE) {
-      const int sy = idx / STRIP_SC, c = idx - sy * STRIP_SC;
-      const int gj = ghost_map(y0 - HALO + sy, g.ny);
-      const int gi = side ? g.nx - 1 - c : c;
-      if (gj >= 0) off[t] = gi + g.pitch * gj;
+      // the staged layout follows global memory: x strip (tt, c) with c fastest; y strip (c, tt) with tt fastest
+      const int tt = AXIS == 0 ? idx / NC : idx % TT;
+      const int c = AXIS == 0 ? idx % NC : idx / TT;
+      const int gt = ghost_map(t0 - HALO + tt, n_t);  // tangent index: mirrored outside the grid, -1 beyond
+      const int gn = side ? n_n - 1 - c : c;
+      if (gt >= 0) off[t] = AXIS == 0 ? gn + g.pitch * gt : gt + g.pitch * gn;
     }
   }
-  const int j = y0 + tid;
-  const bool row_ok = j < g.ny;
-  const double my = (j >= 1 && j <= g.ny - 2) ? 1.0 : 0.0;
-  double A[5][4];
+  const int jt = t0 + tid;                       // this thread's tangent index
+  const bool mine = jt >= t_lo && jt < t_hi;
+  const double mt = (jt >= 1 && jt <= n_t - 2) ? 1.0 : 0.0;
+  double tc[5], bc[5];
+  line_coefficients(jt, n_t, tc, bc);
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    tc[s] *= a_t;
+    bc[s] *= d_t;
+  }
+  double A[5][W];
 #pragma unroll
   for (int dd = 0; dd < 5; ++dd)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) A[dd][c] = 0.0;
+    for (int c = 0; c < W; ++c) A[dd][c] = 0.0;
   double dot = 0.0;
 
   const int kstart = ka - HALO, kend = ka < kb ? kb + HALO : ka - HALO;
   const double* src = p + (long long)(kstart - g.k0 + HALO) * g.plane;
-  int kstage = kstart;
+  int issued = kstart;
   auto issue_plane = [&](double* dstS) {
-    if (kstage >= 0 && kstage < g.nz) {
+    if (issued >= 0 && issued < g.nz) {
 #pragma unroll
       for (int t = 0; t < LD; ++t) {
         const int idx = tid + t * NT;
         if (idx < PLANE) {
           const bool ok = off[t] >= 0;
-          cp_async_8(dstS + idx, src + (ok ? off[t] : 0), ok);
+          cp_async_8(dstS + idx, src + (ok ? off[t] : 0), ok);  // idx IS the staged offset (see the layout above)
         }
       }
     }
     src += g.plane;
-    ++kstage;
+    ++issued;
   };
-  int issued = kstart;
 #pragma unroll
   for (int s = 0; s < ST - 3; ++s) {
-    if (issued < kend) { issue_plane(S + s * PLANE); ++issued; }
+    if (issued < kend) issue_plane(S + s * PLANE);
     cp_async_commit();
   }
   int slot = 0;
-  double* qrow = q + (long long)(ka - g.k0 + HALO) * g.plane + (long long)g.pitch * j;  // output plane ka, row j
+  long long qoff = (long long)(ka - g.k0 + HALO) * g.plane;  // output plane ka
   for (int kp = kstart; kp < kend; ++kp) {
     cp_async_wait<ST - 4>();
     __syncthreads();
     {
       const int fs = slot >= 3 ? slot - 3 : slot + ST - 3;
-      if (issued < kend) { issue_plane(S + fs * PLANE); ++issued; }
+      if (issued < kend) issue_plane(S + fs * PLANE);
       cp_async_commit();
     }
     if (kp >= 0 && kp < g.nz) {
-      const ZFull Z = z_full(g, ztab, w.azz, w.dz, kp);
-      const double* V = S + slot * PLANE + tid * STRIP_SC;  // row j-2 of this thread's window
-      double v[5][STRIP_SC];
+      const ZFull Z = zfm[z_step_uniform(kp, g.nz) ? 10 : z_slot(kp, g.nz)];
+      const double* V = S + slot * PLANE + tid * ST_T;  // tangent offset -2 of this thread's window, normal index 0
+      double v[5][NC];
 #pragma unroll
-      for (int rr = 0; rr < 5; ++rr)
+      for (int tt = 0; tt < 5; ++tt)
 #pragma unroll
-        for (int c = 0; c < STRIP_SC; c += 2) {
-          const double2 t2 = lds2(V + rr * STRIP_SC + c);
-          v[rr][c] = t2.x;
-          v[rr][c + 1] = t2.y;
-        }
+        for (int c = 0; c < NC; ++c) v[tt][c] = V[tt * ST_T + c * ST_C];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        // ghost columns: p(-1) := p(1), p(-2) := p(0)
-        auto xg = [&](const int rr, const int cc) { return cc >= 0 ? v[rr][cc] : (cc == -1 ? v[rr][1] : v[rr][0]); };
+      for (int c = 0; c < W; ++c) {
+        // ghost cells of the normal axis: p(-1) := p(1), p(-2) := p(0)
+        auto ng = [&](const int tt, const int cc) { return cc >= 0 ? v[tt][cc] : (cc == -1 ? v[tt][1] : v[tt][0]); };
         const double p0 = v[2][c];
-        const double xm1 = xg(2, c - 1), xm2 = xg(2, c - 2), xp1 = v[2][c + 1], xp2 = v[2][c + 2];
-        double X = fma(1.0 / 6.0, xm2 + xp2, fma(-2.0 / 3.0, xm1 + xp1, p0));
-        if (c == 0) X -= (v[2][0] - v[2][1]);
-        if (c == 1) X += (v[2][0] - v[2][1]) * (1.0 / 3.0);
-        const double e2 = v[2][0] - 2.0 * v[2][1] + v[2][2];
-        const double xb = (c == 0 || c == 2) ? e2 * (1.0 / 6.0) : (c == 1 ? e2 * (-2.0 / 6.0) : 0.0);
-        const double gx0 = 2.0 * v[0][c] - xg(0, c - 2) - v[0][c + 2];
-        const double gx2 = 2.0 * p0 - xm2 - xp2;
-        const double gx4 = 2.0 * v[4][c] - xg(4, c - 2) - v[4][c + 2];
-        const double XY = 2.0 * gx2 - gx0 - gx4;
-        const double ym2 = v[0][c], ym1 = v[1][c], yp1 = v[3][c], yp2 = v[4][c];
-        const double Y = fma(1.0 / 6.0, ym2 + yp2, fma(-2.0 / 3.0, ym1 + yp1, p0)) + t_end_corr(j, g.ny, ym1, p0, yp1);
-        const double yb = b_rows(j, g.ny, ym2, ym1, p0, yp1, yp2);
-        const double gy = 2.0 * p0 - (ym2 + yp2);
-        const double mx = c == 0 ? 0.0 : 1.0;
-        const double same = Z.mz * (w.axx * my * X + w.ayy * mx * Y + w.bxy * XY) + w.ridge2 * p0 + w.dx * xb + w.dy * yb;
-        const double G = w.bxz * my * gx2 + w.byz * mx * gy;
-        const double mm = mx * my;
-        // l = t + (dz B): the masks act on the azz T part only
-        A[2][c] += same + fma(Z.t0, mm * p0, (Z.l0 - Z.t0) * p0) + Z.c0 * G;
-        A[1][c] += fma(Z.tm1, mm * p0, (Z.lm1 - Z.tm1) * p0);
-        A[3][c] += fma(Z.tp1, mm * p0, (Z.lp1 - Z.tp1) * p0);
-        A[0][c] += fma(Z.tm2, mm * p0, (Z.lm2 - Z.tm2) * p0) + Z.cm2 * G;
-        A[4][c] += fma(Z.tp2, mm * p0, (Z.lp2 - Z.tp2) * p0) + Z.cp2 * G;
+        const double nm1 = ng(2, c - 1), nm2 = ng(2, c - 2), np1 = v[2][c + 1], np2 = v[2][c + 2];
+        double Nl = fma(1.0 / 6.0, nm2 + np2, fma(-2.0 / 3.0, nm1 + np1, p0));  // T along the normal axis ...
+        if (c == 0) Nl -= (v[2][0] - v[2][1]);                                   // ... with its end corrections
+        if (c == 1) Nl += (v[2][0] - v[2][1]) * (1.0 / 3.0);
+        const double e2 = v[2][0] - 2.0 * v[2][1] + v[2][2];                     // the border row next to the face
+        const double nb = (c == 0 || c == 2) ? e2 * (1.0 / 6.0) : (c == 1 ? e2 * (-2.0 / 6.0) : 0.0);
+        const double gn0 = 2.0 * v[0][c] - ng(0, c - 2) - v[0][c + 2];           // C_normal p at tangent offsets -2, 0, +2
+        const double gn2 = 2.0 * p0 - nm2 - np2;
+        const double gn4 = 2.0 * v[4][c] - ng(4, c - 2) - v[4][c + 2];
+        const double NTm = 2.0 * gn2 - gn0 - gn4;                                // (C_normal (x) C_tangent) p
+        double Tl = tc[0] * v[0][c];                                             // a_t T_tangent p
+        Tl = fma(tc[1], v[1][c], Tl); Tl = fma(tc[2], p0, Tl); Tl = fma(tc[3], v[3][c], Tl); Tl = fma(tc[4], v[4][c], Tl);
+        double tb = bc[0] * v[0][c];                                             // d_t B_tangent p
+        tb = fma(bc[1], v[1][c], tb); tb = fma(bc[2], p0, tb); tb = fma(bc[3], v[3][c], tb); tb = fma(bc[4], v[4][c], tb);
+        const double gt = 2.0 * p0 - (v[0][c] + v[4][c]);
+        const double mn = c == 0 ? 0.0 : 1.0;
+        const double same = Z.mz * (a_n * mt * Nl + mn * Tl + w.bxy * NTm) + w.ridge2 * p0 + d_n * nb + tb;
+        const double G = b_nz * mt * gn2 + b_tz * mn * gt;
+        const double pm = mn * mt * p0;
+        // l = t + dz B: the masks act on the azz T part only
+        A[2][c] += same + fma(Z.t0, pm, (Z.l0 - Z.t0) * p0) + Z.c0 * G;
+        A[1][c] += fma(Z.tm1, pm, (Z.lm1 - Z.tm1) * p0);
+        A[3][c] += fma(Z.tp1, pm, (Z.lp1 - Z.tp1) * p0);
+        A[0][c] += fma(Z.tm2, pm, (Z.lm2 - Z.tm2) * p0) + Z.cm2 * G;
+        A[4][c] += fma(Z.tp2, pm, (Z.lp2 - Z.tp2) * p0) + Z.cp2 * G;
       }
     }
     // output plane kp-2 is complete
     if (kp - HALO >= ka) {
-      if (row_ok) {
+      if (mine) {
         const int s2 = slot >= 2 ? slot - 2 : slot + ST - 2;
-        const double* P = S + s2 * PLANE + (tid + HALO) * STRIP_SC;
+        const double* P = S + s2 * PLANE + (tid + HALO) * ST_T;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int gi = side ? g.nx - 1 - c : c;
-          qrow[gi] = A[0][c];
-          dot = fma(P[c], A[0][c], dot);
+        for (int c = 0; c < W; ++c) dot = fma(P[c * ST_C], A[0][c], dot);
+        if (AXIS == 0) {
+          double* qrow = q + qoff + (long long)g.pitch * jt;
+          if ((g.pitch & 1) == 0 && (g.nx & 1) == 0) {  // the four nodes of the row are one aligned 32-byte sector
+            double2* dst = reinterpret_cast<double2*>(qrow + (side ? g.nx - 4 : 0));
+            dst[0] = side ? make_double2(A[0][3], A[0][2]) : make_double2(A[0][0], A[0][1]);
+            dst[1] = side ? make_double2(A[0][1], A[0][0]) : make_double2(A[0][2], A[0][3]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < W; ++c) qrow[side ? g.nx - 1 - c : c] = A[0][c];
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < W; ++c) q[qoff + (long long)g.pitch * (side ? g.ny - 1 - c : c) + jt] = A[0][c];  // coalesced in x
         }
       }
-      qrow += g.plane;
+      qoff += g.plane;
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < W; ++c) {
       A[0][c] = A[1][c]; A[1][c] = A[2][c]; A[2][c] = A[3][c]; A[3][c] = A[4][c]; A[4][c] = 0.0;
     }
     slot = (slot + 1 == ST) ? 0 : slot + 1;
   }
   cp_async_wait<0>();
+  return dot;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Output planes [f0, f1) next to a z face (at most 3) for the thread's 2 x YB patch of an interior tile, in gather form
+// from the planes [s0, ..) staged side by side in S (at most ST - 1 of them; plane k at slot k - s0).  In-plane
+// coefficients are the interior constants; the z coefficients of an output plane ko are row ko of the per-plane table
+// (shell_fill_z_table: T_z taps at 0..4, B_z at 5..9, C_z at 10..12, m_z at 13).  Runs once per CTA.
+template <int YB, int SX, int PLANE>
+__device__ __forceinline__ double z_face_block(const GridDesc& g, const UniConsts& K, const double* __restrict__ ztab,
+                                               const double* __restrict__ Sthr, double* __restrict__ qthr, const int f0,
+                                               const int f1, const int s0, const int nrows, const bool c0ok, const bool c1ok) {
+  // Sthr: staged element (row j0, column i0) of slot 0; qthr: q element (plane f0, row j0, column i0)
+  double dot = 0.0;
+  const double axx = K.cx1 * (-1.5), ayy = K.cy1 * (-1.5);  // cx1 = -2 axx / 3
+  for (int ko = f0; ko < f1; ++ko) {
+    const double* zr = ztab + (long long)ko * SHELL_ZSTRIDE;
+    const double mz = zr[13];
+    for (int r = 0; r < nrows; ++r) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (!(e == 0 ? c0ok : c1ok)) continue;
+        auto at = [&](const int k, const int dj, const int di) { return Sthr[(k - s0) * PLANE + (r + dj) * SX + e + di]; };
+        const double p0 = at(ko, 0, 0);
+        const double xs1 = at(ko, 0, -1) + at(ko, 0, 1), xs2 = at(ko, 0, -2) + at(ko, 0, 2);
+        const double ys1 = at(ko, -1, 0) + at(ko, 1, 0), ys2 = at(ko, -2, 0) + at(ko, 2, 0);
+        const double cs = (at(ko, -2, -2) + at(ko, -2, 2)) + (at(ko, 2, -2) + at(ko, 2, 2));
+        const double X = fma(1.0 / 6.0, xs2, fma(-2.0 / 3.0, xs1, p0));
+        const double Y = fma(1.0 / 6.0, ys2, fma(-2.0 / 3.0, ys1, p0));
+        const double XY = 4.0 * p0 - 2.0 * (xs2 + ys2) + cs;
+        double acc = mz * (axx * X + ayy * Y + K.bxy * XY) + K.ridge2 * p0;
+#pragma unroll
+        for (int s = -2; s <= 2; ++s) {
+          const int k = ko + s;
+          if (k < 0 || k >= g.nz) continue;
+          const double pk = s == 0 ? p0 : at(k, 0, 0);
+          acc = fma(fma(K.azz, zr[2 + s], K.dz * zr[7 + s]), pk, acc);
+          if (s == -2 || s == 0 || s == 2) {
+            const double xk = s == 0 ? xs2 : at(k, 0, -2) + at(k, 0, 2);
+            const double yk = s == 0 ? ys2 : at(k, -2, 0) + at(k, 2, 0);
+            const double G = K.bxz * (2.0 * pk - xk) + K.byz * (2.0 * pk - yk);
+            acc = fma(zr[11 + s / 2], G, acc);
+          }
+        }
+        qthr[(long long)(ko - f0) * g.plane + (long long)r * g.pitch + e] = acc;
+        dot = fma(p0, acc, dot);
+      }
+    }
+  }
   return dot;
 }
 
@@ -291,12 +341,11 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
                 unsigned int* __restrict__ counter, CgScalars* __restrict__ sc, const int cg_mode) {
   constexpr int YB = 4;
   using C = MainCfg<YB, TYT, ST>;
-  static_assert(ST >= 5, "ring needs planes kp-2..kp plus at least two in flight");
-  static_assert((C::NT + 2 * HALO) * STRIP_SC <= C::PLANE, "a strip plane must fit a box plane slot");
+  static_assert(ST >= 6, "ring: planes kp-2..kp plus three in flight; the z-face block stages five planes at once");
+  static_assert((C::NT + 2 * HALO) * StripGeom<0>::NC <= C::PLANE, "a strip plane must fit a box plane slot");
   LSB_DYN_SMEM(S);
   __shared__ double red[C::NT / 32];
-  __shared__ ZStep zsm[10];
-  __shared__ ZFull zfm[11];  // [10]: the constant interior coefficients
+  __shared__ ZFull zfm[11];  // strips: z coefficients of the planes next to a z face; [10]: the interior constants
 
   if (cg_mode && sc->done) return;
 
@@ -305,101 +354,111 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
   const int bid = blockIdx.x;
   double dot = 0.0;
 
-  if (bid < pl.n_strip) {
-    // ---- strip role
-    const int per_chunk = 2 * pl.strips_y;
-    const int ch = bid / per_chunk, rem = bid - ch * per_chunk;
-    const int side = rem / pl.strips_y, sy = rem - side * pl.strips_y;
-    const int ka = g.k0 + ch * pl.scz, kb = min(ka + pl.scz, g.k1);
-    dot = strip_cta<C::NT, ST>(g, w, ztab, p, q, side, sy * C::NT, ka, kb, S, tid);
-  } else {
-    // ---- box role
-    const int b = bid - pl.n_strip;
-    const int tiles = pl.tiles_x * pl.tiles_y;
-    const int ch = b / tiles, trem = b - ch * tiles;
-    const int by = trem / pl.tiles_x, bx = trem - by * pl.tiles_x;
-    const int x0 = C::X_FIRST + bx * C::TX, y0 = by * C::TY;
-    const int ka = g.k0 + ch * pl.cz, kb = min(ka + pl.cz, g.k1);
-    const int i0 = x0 + 2 * tx;
-    const int j0 = y0 + YB * ty;
-    const int nrows = max(0, min(YB, g.ny - j0));
-    const int xlim = g.nx - C::X_FIRST;
-    const bool y_edge = nrows > 0 && (j0 < 3 || j0 + YB > g.ny - 3);  // warp uniform
-
-    // Staging of one plane, row by row: warp ty copies the staged rows ty, ty + TYT, ...; a lane copies the column pair
-    // (VEC16) or the columns lane, lane + 32, lane + 64 of a row.  Addresses are affine in (row, lane): no per-thread
-    // offset table (round 1's table of 6 offsets was the first thing ptxas spilled once the edge code was added).
-    const int kstart = ka - HALO, kend = ka < kb ? kb + HALO : ka - HALO;
-    int issued = kstart;  // next plane to stage (global index)
-    auto issue_plane = [&](double* dstS) {
-      if (issued >= 0 && issued < g.nz) {
-        const double* src = p + (long long)(issued - g.k0 + HALO) * g.plane + (x0 - HALO);
-#pragma unroll
-        for (int sy = ty; sy < C::SY; sy += TYT) {
-          const int gj = ghost_map(y0 - HALO + sy, g.ny);  // rows -1,-2 / ny,ny+1 mirror the rows inside; -1: overhang
-          const double* row = src + (long long)g.pitch * max(gj, 0);
-          double* drow = dstS + sy * C::SX;
-          if (VEC16) {
-            // SX = 68 doubles = 34 pairs: every lane one pair, lanes 0 and 1 the last two
-            const bool ok = gj >= 0 && (x0 - HALO + 2 * tx) < g.nx;
-            cp_async_16(drow + 2 * tx, row + (ok ? 2 * tx : 0), ok);
-            if (tx < 2) {
-              const bool ok2 = gj >= 0 && (x0 - HALO + 64 + 2 * tx) < g.nx;
-              cp_async_16(drow + 64 + 2 * tx, row + (ok2 ? 64 + 2 * tx : 0), ok2);
-            }
-          } else {
-#pragma unroll
-            for (int c = tx; c < C::SX; c += 32) {
-              const bool ok = gj >= 0 && (x0 - HALO + c) < g.nx;
-              cp_async_8(drow + c, row + (ok ? c : 0), ok);
-            }
-          }
-        }
-      }
-      ++issued;
-    };
-    // z coefficients of the (at most ten) incoming planes next to a z face
+  if (bid < pl.n_xs + pl.n_ys) {
+    // ---- strip roles
     if (tid < 10) {
       const int k = tid < 5 ? tid : g.nz - 5 + (tid - 5);
-      ZStep Zs{};
       ZFull Zf{};
-      if (k >= 0 && k < g.nz) {
-        Zf = z_full(g, ztab, U.azz, U.dz, k);
-        Zs.mz = Zf.mz; Zs.l0 = Zf.l0; Zs.c0 = Zf.c0; Zs.lm1 = Zf.lm1; Zs.lp1 = Zf.lp1;
-        Zs.lm2 = Zf.lm2; Zs.cm2 = Zf.cm2; Zs.lp2 = Zf.lp2; Zs.cp2 = Zf.cp2;
-      }
-      // planes 0..4 fill slots 0..4, planes nz-5..nz-1 slots 5..9 (z_slot); on grids of fewer than 10 planes a plane
-      // may own two slots with the same content
-      zsm[tid] = Zs;
+      if (k >= 0 && k < g.nz) Zf = z_full(g, ztab, U.azz, U.dz, k);
       zfm[tid] = Zf;
     }
     if (tid == 10) zfm[10] = z_uniform(U.azz);
+    __syncthreads();
+    const bool ys = bid >= pl.n_xs;
+    const int b = ys ? bid - pl.n_xs : bid;
+    const int per_side = ys ? pl.ys_x : pl.xs_y;
+    const int ch = b / (2 * per_side), rem = b - ch * 2 * per_side;
+    const int side = rem / per_side, st = rem - side * per_side;
+    const int ka = g.k0 + ch * pl.scz, kb = min(ka + pl.scz, g.k1);
+    if (ys) dot = strip_cta<C::NT, ST, 1>(g, w, zfm, p, q, side, C::X_FIRST + st * C::NT, C::X_FIRST, g.nx - C::X_FIRST, ka, kb, S, tid);
+    else dot = strip_cta<C::NT, ST, 0>(g, w, zfm, p, q, side, st * C::NT, 0, g.ny, ka, kb, S, tid);
+  } else {
+    // ---- box role: interior tile, the march of k_fdi_box over the planes 3 <= k < nz-3 of its chunk
+    const int b = bid - pl.n_xs - pl.n_ys;
+    const int tiles = pl.tiles_x * pl.tiles_y;
+    const int ch = b / tiles, trem = b - ch * tiles;
+    const int by = trem / pl.tiles_x, bx = trem - by * pl.tiles_x;
+    const int x0 = C::X_FIRST + bx * C::TX, y0 = C::Y_FIRST + by * C::TY;
+    const int ka = g.k0 + ch * pl.cz, kb = min(ka + pl.cz, g.k1);
+    const int i0 = x0 + 2 * tx;
+    const int j0 = y0 + YB * ty;
+    const int nrows = max(0, min(YB, (g.ny - C::Y_FIRST) - j0));
+    const int xlim = g.nx - C::X_FIRST;
 
+    // Staging of one plane: slot idx = tid + t NT of the (SX x SY) tile (pairs of doubles when VEC16) <- the in-plane
+    // offset off[t] of its source, computed once (every staged node of an interior tile is a real node or overhang).
+    constexpr int LD = VEC16 ? C::LD16 : C::LD8;
+    constexpr int NSLOT = VEC16 ? C::PLANE / 2 : C::PLANE;
+    int off[LD];
+#pragma unroll
+    for (int t = 0; t < LD; ++t) {
+      const int idx = tid + t * C::NT;
+      off[t] = -1;
+      if (idx < NSLOT) {
+        const int e0 = VEC16 ? 2 * idx : idx;
+        const int sy = e0 / C::SX, sx = e0 - sy * C::SX;
+        const int gi = x0 - HALO + sx, gj = y0 - HALO + sy;  // >= 2, >= 1
+        if (gi < g.nx && gj < g.ny) off[t] = gi + g.pitch * gj;
+      }
+    }
+    auto stage = [&](double* dstS, const int k) {  // plane k (global index, must exist) -> dstS
+      const double* src = p + (long long)(k - g.k0 + HALO) * g.plane;
+#pragma unroll
+      for (int t = 0; t < LD; ++t) {
+        const int idx = tid + t * C::NT;
+        if (idx < NSLOT) {
+          const bool ok = off[t] >= 0;
+          if (VEC16) cp_async_16(dstS + 2 * idx, src + (ok ? off[t] : 0), ok);
+          else cp_async_8(dstS + idx, src + (ok ? off[t] : 0), ok);
+        }
+      }
+    };
+    const int my_off = (YB * ty) * C::SX + 2 * tx;
+
+    // ---- planes next to a z face owned by this chunk: gather form, once
+    const int ua = max(ka, 3), ub = min(kb, g.nz - 3);  // the uniform range [ua, ub)
+#pragma unroll 1
+    for (int face = 0; face < 2; ++face) {
+      const int f0 = face == 0 ? ka : max(ka, max(g.nz - 3, 3));
+      const int f1 = face == 0 ? min(kb, min(3, g.nz)) : kb;
+      if (f0 >= f1) continue;
+      const int s0 = max(f0 - HALO, 0), s1 = min(f1 + HALO, g.nz);  // at most 5 planes
+      for (int k = s0; k < s1; ++k) stage(S + (k - s0) * C::PLANE, k);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncthreads();
+      dot += z_face_block<YB, C::SX, C::PLANE>(g, U, ztab, S + my_off + 2 * C::SX + 2,
+                                               q + (long long)(f0 - g.k0 + HALO) * g.plane + (long long)g.pitch * j0 + i0, f0, f1,
+                                               s0, nrows, i0 < xlim, i0 + 1 < xlim);
+      __syncthreads();  // before the slots are staged again
+    }
+
+    // ---- the uniform march
     double A[5][YB][2];
 #pragma unroll
     for (int d = 0; d < 5; ++d)
 #pragma unroll
       for (int r = 0; r < YB; ++r) A[d][r][0] = A[d][r][1] = 0.0;
-
+    const int kstart = ua - HALO, kend = ua < ub ? ub + HALO : ua - HALO;
     int kp = kstart;
+    int issued = kstart;
 #pragma unroll
     for (int s = 0; s < ST - 3; ++s) {
-      if (issued < kend) issue_plane(S + s * C::PLANE);
+      if (issued < kend) { stage(S + s * C::PLANE, issued); ++issued; }
       cp_async_commit();
     }
     int slot = 0;
-    const int my_off = (YB * ty) * C::SX + 2 * tx;
-    double* qdst = q + (long long)(ka - g.k0 + HALO) * g.plane + (long long)g.pitch * j0 + i0;  // output plane ka
+    double* qdst = q + (long long)(ua - g.k0 + HALO) * g.plane + (long long)g.pitch * j0 + i0;  // output plane ua
 
     auto advance_pipeline = [&]() {
       cp_async_wait<ST - 4>();
       __syncthreads();
       const int fs = slot >= 3 ? slot - 3 : slot + ST - 3;
-      if (issued < kend) issue_plane(S + fs * C::PLANE);
+      if (issued < kend) { stage(S + fs * C::PLANE, issued); ++issued; }
       cp_async_commit();
     };
     auto store_out = [&](const double (&out)[YB][2]) {
-      if (kp - HALO < ka) return;
+      if (kp - HALO < ua) return;
       const int s2 = slot >= 2 ? slot - 2 : slot + ST - 2;
       const double* Sp = S + s2 * C::PLANE + my_off + 2 * C::SX + 2;
 #pragma unroll
@@ -430,28 +489,14 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
   {                                                                                                                 \
     if (kp >= kend) break;                                                                                          \
     advance_pipeline();                                                                                             \
-    if (kp >= 0 && kp < g.nz) {                                                                                     \
-      const double* Sc = S + slot * C::PLANE + my_off;                                                              \
-      int zs = 10;                                                                                                  \
-      if (z_step_uniform(kp, g.nz)) {                                                                               \
-        uni_plane_fast<YB, C::SX>(Sc, U, A[(PH + 0) % 5], A[(PH + 1) % 5], A[(PH + 2) % 5], A[(PH + 3) % 5],        \
-                                  A[(PH + 4) % 5]);                                                                 \
-      } else {                                                                                                      \
-        zs = z_slot(kp, g.nz);                                                                                      \
-        const ZStep Z = zsm[zs];                                                                                    \
-        zgen_plane_fast<YB, C::SX>(Sc, U, Z, A[(PH + 0) % 5], A[(PH + 1) % 5], A[(PH + 2) % 5], A[(PH + 3) % 5],    \
-                                   A[(PH + 4) % 5]);                                                                \
-      }                                                                                                             \
-      if (y_edge)                                                                                                   \
-        y_edge_fix<YB, C::SX>(Sc, U, w.dy, zfm[zs], j0, g.ny, A[(PH + 0) % 5], A[(PH + 1) % 5], A[(PH + 2) % 5],    \
+    uni_plane_fast<YB, C::SX>(S + slot * C::PLANE + my_off, U, A[(PH + 0) % 5], A[(PH + 1) % 5], A[(PH + 2) % 5],   \
                               A[(PH + 3) % 5], A[(PH + 4) % 5]);                                                    \
-    }                                                                                                               \
     store_out(A[(PH + 0) % 5]);                                                                                     \
     _Pragma("unroll") for (int r = 0; r < YB; ++r) A[(PH + 0) % 5][r][0] = A[(PH + 0) % 5][r][1] = 0.0;             \
     slot = (slot + 1 == ST) ? 0 : slot + 1;                                                                         \
     ++kp;                                                                                                           \
   }
-    if (ka < kb) {
+    if (ua < ub) {
       for (;;) {
         LSB_FUSED_STEP(0)
         LSB_FUSED_STEP(1)

@@ -145,9 +145,10 @@ struct FusedChoice {
   double cost;  // plane steps on the critical path (waves x steps per CTA), the quantity the planner minimises
 };
 
-// One candidate: box CTAs of `nch` z chunks; the strip CTAs get chunks long enough to cost about `strip_rel` of a box CTA
-// (a strip step moves a quarter of the nodes of a box step with general coefficients: measured guess, LSB200_FUSED_SCZ
-// overrides) so that they are never the last to finish.
+// One candidate: box CTAs of `nch` z chunks.  The strip CTAs get SHORT chunks: a strip plane step costs about
+// `strip_rel` box plane steps (general coefficients, one warp-step moves 128 x 4 nodes; measured, profiles/r2d) and a
+// strip CTA must not outlast a box CTA, while the z halo it re-stages (4 planes per chunk) hardly matters for 5 % of the
+// nodes.  LSB200_FUSED_SCZ overrides the strip chunk length.
 inline FusedChoice fused_candidate(const GridDesc& g, const int tyt, const int minb, const int nch, const int sm_count,
                                    const int scz_override) {
   FusedChoice c;
@@ -156,19 +157,21 @@ inline FusedChoice fused_candidate(const GridDesc& g, const int tyt, const int m
   FusedPlan& pl = c.pl;
   const int ty = 4 * tyt, nt = 32 * tyt;
   pl.tiles_x = (g.nx - 8 + 63) / 64;
-  pl.tiles_y = (g.ny + ty - 1) / ty;
+  pl.tiles_y = (g.ny - 6 + ty - 1) / ty;
   pl.cz = std::max(1, (g.nzl + nch - 1) / nch);
   pl.chunks = (g.nzl + pl.cz - 1) / pl.cz;
   pl.n_box = pl.tiles_x * pl.tiles_y * pl.chunks;
-  pl.strips_y = (g.ny + nt - 1) / nt;
-  constexpr double strip_rel = 0.6;
+  pl.xs_y = (g.ny + nt - 1) / nt;
+  pl.ys_x = (g.nx - 8 + nt - 1) / nt;
+  constexpr double strip_rel = 2.0;
   int scz = scz_override > 0 ? scz_override : (int)((pl.cz + 2 * HALO) / strip_rel) - 2 * HALO;
   scz = std::max(4, std::min(scz, g.nzl));
   pl.schunks = (g.nzl + scz - 1) / scz;
   pl.scz = (g.nzl + pl.schunks - 1) / pl.schunks;
   pl.schunks = (g.nzl + pl.scz - 1) / pl.scz;
-  pl.n_strip = 2 * pl.strips_y * pl.schunks;
-  c.ctas = (long long)pl.n_box + pl.n_strip;
+  pl.n_xs = 2 * pl.xs_y * pl.schunks;
+  pl.n_ys = 2 * pl.ys_x * pl.schunks;
+  c.ctas = (long long)pl.n_box + pl.n_xs + pl.n_ys;
   const long long slots = (long long)sm_count * minb;
   const long long waves = (c.ctas + slots - 1) / slots;
   c.cost = (double)waves * (pl.cz + 2 * HALO);

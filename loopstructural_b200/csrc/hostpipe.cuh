@@ -14,13 +14,13 @@
 namespace lsb {
 
 inline void par_memcpy(void* dst, const void* src, size_t bytes) {
-  constexpr size_t kMin = 4u << 20;
-  if (bytes < 2 * kMin) {
+  constexpr size_t kMin = 1u << 20;  // bytes per thread below which starting it costs more than it moves
+  if (bytes < 4 * kMin) {
     memcpy(dst, src, bytes);
     return;
   }
   const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-  const int nt = (int)std::min<size_t>(std::min<unsigned>(hw, 8u), bytes / kMin);
+  const int nt = (int)std::min<size_t>(std::min<unsigned>(hw, 16u), bytes / kMin);
   const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
   std::vector<std::thread> th;
   for (int t = 1; t < nt; ++t) {

@@ -243,6 +243,18 @@ class Engine:
         buf = (C.c_ubyte * 128).from_buffer_copy(nccl_id)
         nat.check(self._lib.lsb200_comm_init(self._h, buf, int(rank), int(nranks)))
 
+    @property
+    def uses_peer_memory(self) -> bool:
+        """True when the scalar reductions of CG go through peer-mapped mailboxes instead of ncclAllReduce."""
+        return bool(self._lib.lsb200_comm_uses_peer_memory(self._h))
+
+    def residual_norm(self):
+        """(sqrt(r . S^2 r), ||r||_2) of the current solution with r = A^T W b - N c recomputed through the operator;
+        collective on slab handles."""
+        a, b = C.c_double(0.0), C.c_double(0.0)
+        nat.check(self._lib.lsb200_residual_norm(self._h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
+
     @staticmethod
     def comm_unique_id() -> bytes:
         buf = (C.c_ubyte * 128)()

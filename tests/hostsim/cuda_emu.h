@@ -54,6 +54,9 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
 #define gridDim (lsb_emu::g_dim)
 #undef __shared__
 #define __shared__ static
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))
+#endif
 #undef __launch_bounds__
 #define __launch_bounds__(...)
 

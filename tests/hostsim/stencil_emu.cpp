@@ -165,7 +165,7 @@ HOSTSIM_API int emu_fdi_fused(const int* dims, const double* ew, double ridge2, 
   if (!plan_fused(g, sm_count, MAX_PARTIALS, cfg, cz_override, scz_override, &fc)) return -3;
   const UniConsts U = make_uni_consts(w);
   const bool vec16 = (g.pitch % 2) == 0;
-  const unsigned ctas = (unsigned)(fc.pl.n_box + fc.pl.n_strip);
+  const unsigned ctas = (unsigned)(fc.pl.n_box + fc.pl.n_xs + fc.pl.n_ys);
   switch (fc.tyt) {
 #define X(TYT, ST, MINB)                                                                                             \
   case TYT: {                                                                                                        \
@@ -177,7 +177,7 @@ HOSTSIM_API int emu_fdi_fused(const int* dims, const double* ew, double ridge2, 
 #undef X
     default: return -4;
   }
-  info[0] = fc.tyt; info[1] = fc.pl.cz; info[2] = fc.pl.chunks; info[3] = fc.pl.n_box; info[4] = fc.pl.scz; info[5] = fc.pl.n_strip;
+  info[0] = fc.tyt; info[1] = fc.pl.cz; info[2] = fc.pl.chunks; info[3] = fc.pl.n_box; info[4] = fc.pl.scz; info[5] = fc.pl.n_xs + fc.pl.n_ys;
   info[6] = fc.pl.tiles_x; info[7] = fc.pl.tiles_y; info[8] = 2;
   *pq_out = sc.pq_part[0];
   for (int k = 0; k < g.nzl; ++k)
