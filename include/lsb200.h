@@ -188,6 +188,10 @@ int lsb200_apply_normal(lsb200_handle h, const double* p, double* q, int parts);
 int lsb200_get_rhs(lsb200_handle h, double* out);
 int lsb200_get_diagonal(lsb200_handle h, double* out);
 int lsb200_get_scaling(lsb200_handle h, double* out); /* S = diag^-1/2 (ones when scaling is off) */
+/* Replace the right-hand side A^T W b of the normal equations by a vector of the caller (owned planes, nx*ny*nzl doubles)
+ * until the rows change again: the inner solves of the reference's ADMM solver keep the operator and change only the
+ * right-hand side (LI/loopsolver/admm_solver.py:243-316: [A; rho Q]^T [b - A m; rho (z - u - Q m)]). */
+int lsb200_set_rhs(lsb200_handle h, const double* rhs);
 
 /* 1 when the two scalar reductions of a CG iteration (p.q, r.S^2 r) go through peer-mapped mailboxes (cudaIpc, stores
  * over NVLink) instead of ncclAllReduce; decided in lsb200_comm_init (all ranks agree).  0 on one rank. */

@@ -85,6 +85,7 @@ SIGNATURES = {
     "lsb200_get_diagonal": (C.c_int, [Handle, c_double_p]),
     "lsb200_get_scaling": (C.c_int, [Handle, c_double_p]),
     "lsb200_get_c": (C.c_int, [Handle, c_double_p]),
+    "lsb200_set_rhs": (C.c_int, [Handle, c_double_p]),
     "lsb200_comm_uses_peer_memory": (C.c_int, [Handle]),
     "lsb200_residual_norm": (C.c_int, [Handle, c_double_p, c_double_p]),
     "lsb200_set_c": (C.c_int, [Handle, c_double_p]),

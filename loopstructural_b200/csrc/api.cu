@@ -3,6 +3,7 @@
 // fdi_stencil.cuh / rows.cuh / cg.cuh / eval.cuh / p1.cuh.  No CPU fallback anywhere.
 #include "../../include/lsb200.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdarg.h>
@@ -136,6 +137,11 @@ struct lsb200_ctx {
   int main_cfg = -1;
   bool fused = false;      // the single-launch plan (k_fdi_fused): default whenever the grid is large enough
   FusedChoice fz{};
+  // TMA descriptors of the two node vectors the operator is applied to (p inside CG, x for the initial residual and
+  // lsb200_residual_norm), one per box configuration (their boxes differ); tma_ok: built for this handle
+  bool tma_ok = false;
+  const double* tma_vec[2] = {nullptr, nullptr};
+  TmapArg tma_map[2];
   int main_cz = 0, shell_cz = 0;  // shell_cz = 0: chosen per launch
   int box_z0 = 0, box_z1 = 0;
   long long guard = 0;     // elements of the guard plane in front of every node vector (ensure_vectors)
@@ -245,6 +251,37 @@ static void plan_main(lsb200_ctx* h) {
                                       env_int("LSB200_FUSED_SCZ"), &h->fz);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+static bool encode_plane_tiles(const lsb200_ctx* h, const double* vec, const int box_x, const int box_y, TmapArg* out) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    encode = (encode_fn)fn;
+  }
+  const GridDesc& g = h->g;
+  static_assert(sizeof(CUtensorMap) == sizeof(TmapArg), "TmapArg carries a CUtensorMap");
+  CUtensorMap tm;
+  const cuuint64_t dims[3] = {(cuuint64_t)g.nx, (cuuint64_t)g.ny, (cuuint64_t)(g.nzl + 2 * HALO)};
+  const cuuint64_t strides[2] = {(cuuint64_t)g.pitch * sizeof(double), (cuuint64_t)g.plane * sizeof(double)};
+  const cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult rc = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(vec), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return false;
+  memcpy(out, &tm, sizeof(tm));
+  return true;
+}
+
 static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode) {
   const StencilWeights w = make_weights(h);
   const GridDesc& g = h->g;
@@ -274,18 +311,44 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
     const UniConsts U = make_uni_consts(w);
     const FusedPlan& pl = h->fz.pl;
     const unsigned int ctas = (unsigned int)(pl.n_box + pl.n_xs + pl.n_ys);
+    // TMA staging when the vector has a descriptor (built lazily for p and x; needs an even row pitch); LSB200_TMA=0
+    // keeps cp.async everywhere
+    static const bool want_tma = !(getenv("LSB200_TMA") && atoi(getenv("LSB200_TMA")) == 0);
+    int tmi = -1;
+    if (want_tma && vec16) {
+      for (int t = 0; t < 2; ++t)
+        if (h->tma_vec[t] == p) tmi = t;
+      if (tmi < 0 && (p == h->p || p == h->x)) {
+        const int t = p == h->p ? 0 : 1;
+        bool ok = false;
+        switch (h->fz.tyt) {
+#define X(TYT, ST, MINB) case TYT: ok = encode_plane_tiles(h, p, MainCfg<4, TYT, ST>::SX, MainCfg<4, TYT, ST>::SY, &h->tma_map[t]); break;
+          LSB_FUSED_CFGS(X)
+#undef X
+        }
+        if (ok) {
+          h->tma_vec[t] = p;
+          tmi = t;
+        }
+      }
+    }
+    const TmapArg no_map{};
     switch (h->fz.tyt) {
 #define X(TYT, ST, MINB)                                                                                          \
   case TYT: {                                                                                                     \
     const size_t smem = sizeof(double) * MainCfg<4, TYT, ST>::PLANE * ST;                                         \
-    if (vec16) {                                                                                                  \
-      auto kern = k_fdi_fused<TYT, ST, MINB, true>;                                                               \
+    if (vec16 && tmi >= 0) {                                                                                      \
+      auto kern = k_fdi_fused<TYT, ST, MINB, true, true>;                                                         \
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
-      kern<<<ctas, dim3(32, TYT), smem, h->stream>>>(g, U, w, pl, p, q, h->ztab, part, cnt, h->sc, cg_mode);       \
+      kern<<<ctas, dim3(32, TYT), smem, h->stream>>>(g, U, w, pl, p, q, h->ztab, part, cnt, h->sc, cg_mode, h->tma_map[tmi]); \
+    } else if (vec16) {                                                                                           \
+      auto kern = k_fdi_fused<TYT, ST, MINB, true, false>;                                                        \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
+      kern<<<ctas, dim3(32, TYT), smem, h->stream>>>(g, U, w, pl, p, q, h->ztab, part, cnt, h->sc, cg_mode, no_map); \
     } else {                                                                                                      \
-      auto kern = k_fdi_fused<TYT, ST, MINB, false>;                                                              \
+      auto kern = k_fdi_fused<TYT, ST, MINB, false, false>;                                                       \
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
-      kern<<<ctas, dim3(32, TYT), smem, h->stream>>>(g, U, w, pl, p, q, h->ztab, part, cnt, h->sc, cg_mode);       \
+      kern<<<ctas, dim3(32, TYT), smem, h->stream>>>(g, U, w, pl, p, q, h->ztab, part, cnt, h->sc, cg_mode, no_map); \
     }                                                                                                             \
   } break;
       LSB_FUSED_CFGS(X)
@@ -1318,6 +1381,13 @@ int lsb200_get_rhs(lsb200_handle h, double* out) {
   int rc = lsb200_finalize_system(h);
   if (rc) return rc;
   return copy_out(h, out, h->rhs);
+}
+int lsb200_set_rhs(lsb200_handle h, const double* rhs) {
+  if (!h || !rhs) return fail(LSB200_ERR_ARG, "null argument");
+  int rc = lsb200_finalize_system(h);  // diagonal / scaling of the rows as they are; their own rhs is replaced below
+  if (rc) return rc;
+  CK(cudaSetDevice(h->device));
+  return copy_in(h, h->rhs, rhs);
 }
 int lsb200_get_diagonal(lsb200_handle h, double* out) {
   if (!h || !out) return fail(LSB200_ERR_ARG, "null argument");

@@ -94,7 +94,7 @@ struct CgScalars {
 #ifdef LSB_EMU
 #define LSB_DYN_SMEM(name) double* name = lsb_emu::dyn_smem()
 #else
-#define LSB_DYN_SMEM(name) extern __shared__ __align__(16) double name[]
+#define LSB_DYN_SMEM(name) extern __shared__ __align__(128) double name[]  // 128 B: destination of TMA tile loads
 #endif
 
 #ifndef LSB_EMU

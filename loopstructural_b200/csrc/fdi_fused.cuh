@@ -33,9 +33,57 @@
 
 namespace lsb {
 
+// ---- TMA staging of the box tiles (cp.async.bulk.tensor, sm_90+; here sm_100a) ------------------------------------------
+// A node vector is described to the TMA unit once per handle as a 3-D tensor (x, y, stored plane) of doubles
+// (cuTensorMapEncodeTiled, csrc/api.cu); a plane of a tile with its halo is then ONE instruction of ONE thread:
+// box (SX, SY, 1) at (x0-2, y0-2, plane) -> shared memory, bytes counted on an mbarrier, columns / rows beyond the grid
+// zero-filled by the hardware.  Against the cp.async (LDGSTS) staging this removes six copy instructions, their address
+// arithmetic and the six-entry offset table from every thread of every plane step.
+struct alignas(64) TmapArg {
+  unsigned long long opaque[16];  // a CUtensorMap (128 bytes), passed as a __grid_constant__ kernel parameter
+};
+#ifndef LSB_EMU
+__device__ __forceinline__ unsigned smem_u32(const void* ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, const int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, const unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, const unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const TmapArg* tm, const int x, const int y, const int z,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+      : "memory");
+}
+#else  // the CPU emulation instantiates the cp.async path only; these are never called
+inline void mbar_init(unsigned long long*, int) {}
+inline void mbar_fence_init() {}
+inline void mbar_expect_tx(unsigned long long*, unsigned) {}
+inline void mbar_wait(unsigned long long*, unsigned) {}
+inline void tma_load_3d(void*, const TmapArg*, int, int, int, unsigned long long*) {}
+#endif
+
 struct FusedPlan {
   int tiles_x, tiles_y;   // box tiles over columns [4, nx-4) x rows [3, ny-3)
-  int cz, chunks;         // z chunks of the box CTAs over the owned planes
+  int cz, chunks;         // z chunks of the box CTAs over the owned planes: the first holds lo_len planes, the others cz
+  int lo_len;             //   (a chunk that owns a z face is shorter: it also runs z_face_block)
   int n_box;              // tiles_x * tiles_y * chunks
   int xs_y;               // x-strip CTAs per side and z chunk: ceil(ny / NT)
   int ys_x;               // y-strip CTAs per side and z chunk: ceil((nx - 8) / NT)
@@ -129,8 +177,21 @@ struct StripGeom {
   static constexpr int NC = W + 2;
 };
 
+// z coefficients of a plane step as a strip uses them: t = azz T_z (masked part), b = dz B_z (unmasked), c = C_z
+struct ZStrip {
+  double mz, t0, tm1, tp1, tm2, tp2, b0, bm1, bp1, bm2, bp2, c0, cm2, cp2;
+};
+__device__ __forceinline__ ZStrip z_strip(const ZFull& Z) {
+  ZStrip R;
+  R.mz = Z.mz;
+  R.t0 = Z.t0; R.tm1 = Z.tm1; R.tp1 = Z.tp1; R.tm2 = Z.tm2; R.tp2 = Z.tp2;
+  R.b0 = Z.l0 - Z.t0; R.bm1 = Z.lm1 - Z.tm1; R.bp1 = Z.lp1 - Z.tp1; R.bm2 = Z.lm2 - Z.tm2; R.bp2 = Z.lp2 - Z.tp2;
+  R.c0 = Z.c0; R.cm2 = Z.cm2; R.cp2 = Z.cp2;
+  return R;
+}
+
 template <int NT, int ST, int AXIS>
-__device__ __forceinline__ double strip_cta(const GridDesc& g, const StencilWeights& w, const ZFull* __restrict__ zfm,
+__device__ __forceinline__ double strip_cta(const GridDesc& g, const StencilWeights& w, const ZStrip* __restrict__ zsm,
                                             const double* __restrict__ p, double* __restrict__ q, const int side,
                                             const int t0, const int t_lo, const int t_hi, const int ka, const int kb,
                                             double* __restrict__ S, const int tid) {
@@ -166,11 +227,17 @@ __device__ __forceinline__ double strip_cta(const GridDesc& g, const StencilWeig
   const double mt = (jt >= 1 && jt <= n_t - 2) ? 1.0 : 0.0;
   double tc[5], bc[5];
   line_coefficients(jt, n_t, tc, bc);
+  // the tangent line with both families folded in: mz (a_t T_t) is applied per step, d_t B_t is not masked
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
     tc[s] *= a_t;
     bc[s] *= d_t;
   }
+  const double an_mt = a_n * mt, bnz_mt = b_nz * mt;
+  // in-plane offsets of this thread's W outputs
+  int qo[W];
+#pragma unroll
+  for (int c = 0; c < W; ++c) qo[c] = AXIS == 0 ? g.pitch * jt + (side ? g.nx - 1 - c : c) : g.pitch * (side ? g.ny - 1 - c : c) + jt;
   double A[5][W];
 #pragma unroll
   for (int dd = 0; dd < 5; ++dd)
@@ -201,7 +268,7 @@ __device__ __forceinline__ double strip_cta(const GridDesc& g, const StencilWeig
     cp_async_commit();
   }
   int slot = 0;
-  long long qoff = (long long)(ka - g.k0 + HALO) * g.plane;  // output plane ka
+  double* qpl = q + (long long)(ka - g.k0 + HALO) * g.plane;  // output plane ka
   for (int kp = kstart; kp < kend; ++kp) {
     cp_async_wait<ST - 4>();
     __syncthreads();
@@ -211,13 +278,23 @@ __device__ __forceinline__ double strip_cta(const GridDesc& g, const StencilWeig
       cp_async_commit();
     }
     if (kp >= 0 && kp < g.nz) {
-      const ZFull Z = zfm[z_step_uniform(kp, g.nz) ? 10 : z_slot(kp, g.nz)];
+      const ZStrip Z = zsm[z_step_uniform(kp, g.nz) ? 10 : z_slot(kp, g.nz)];
       const double* V = S + slot * PLANE + tid * ST_T;  // tangent offset -2 of this thread's window, normal index 0
       double v[5][NC];
 #pragma unroll
-      for (int tt = 0; tt < 5; ++tt)
+      for (int tt = 0; tt < 5; ++tt) {
+        if (AXIS == 0) {  // a row of 6 doubles, 48 bytes apart: three 16-byte loads
 #pragma unroll
-        for (int c = 0; c < NC; ++c) v[tt][c] = V[tt * ST_T + c * ST_C];
+          for (int c = 0; c < NC; c += 2) {
+            const double2 t2 = lds2(V + tt * ST_T + c);
+            v[tt][c] = t2.x;
+            v[tt][c + 1] = t2.y;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) v[tt][c] = V[tt * ST_T + c * ST_C];
+        }
+      }
 #pragma unroll
       for (int c = 0; c < W; ++c) {
         // ghost cells of the normal axis: p(-1) := p(1), p(-2) := p(0)
@@ -227,27 +304,33 @@ __device__ __forceinline__ double strip_cta(const GridDesc& g, const StencilWeig
         double Nl = fma(1.0 / 6.0, nm2 + np2, fma(-2.0 / 3.0, nm1 + np1, p0));  // T along the normal axis ...
         if (c == 0) Nl -= (v[2][0] - v[2][1]);                                   // ... with its end corrections
         if (c == 1) Nl += (v[2][0] - v[2][1]) * (1.0 / 3.0);
-        const double e2 = v[2][0] - 2.0 * v[2][1] + v[2][2];                     // the border row next to the face
-        const double nb = (c == 0 || c == 2) ? e2 * (1.0 / 6.0) : (c == 1 ? e2 * (-2.0 / 6.0) : 0.0);
         const double gn0 = 2.0 * v[0][c] - ng(0, c - 2) - v[0][c + 2];           // C_normal p at tangent offsets -2, 0, +2
         const double gn2 = 2.0 * p0 - nm2 - np2;
         const double gn4 = 2.0 * v[4][c] - ng(4, c - 2) - v[4][c + 2];
         const double NTm = 2.0 * gn2 - gn0 - gn4;                                // (C_normal (x) C_tangent) p
-        double Tl = tc[0] * v[0][c];                                             // a_t T_tangent p
-        Tl = fma(tc[1], v[1][c], Tl); Tl = fma(tc[2], p0, Tl); Tl = fma(tc[3], v[3][c], Tl); Tl = fma(tc[4], v[4][c], Tl);
-        double tb = bc[0] * v[0][c];                                             // d_t B_tangent p
+        double inplane = fma(an_mt, Nl, w.bxy * NTm);                            // the part m_z switches off
+        double rest = w.ridge2 * p0;                                             // the part it does not
+        if (c <= 2) {                                                            // the border row next to the face
+          const double e2 = v[2][0] - 2.0 * v[2][1] + v[2][2];
+          rest = fma(d_n * (c == 1 ? -2.0 / 6.0 : 1.0 / 6.0), e2, rest);
+        }
+        double G = bnz_mt * gn2;
+        double pm = 0.0;
+        if (c > 0) {  // m_normal = 1: the tangent line, the tangent-z mixed term and the z line exist
+          double Tl = tc[0] * v[0][c];
+          Tl = fma(tc[1], v[1][c], Tl); Tl = fma(tc[2], p0, Tl); Tl = fma(tc[3], v[3][c], Tl); Tl = fma(tc[4], v[4][c], Tl);
+          inplane += Tl;
+          G = fma(b_tz, 2.0 * p0 - (v[0][c] + v[4][c]), G);
+          pm = mt * p0;
+        }
+        double tb = bc[0] * v[0][c];                                             // d_t B_tangent p (zero table away from the corners)
         tb = fma(bc[1], v[1][c], tb); tb = fma(bc[2], p0, tb); tb = fma(bc[3], v[3][c], tb); tb = fma(bc[4], v[4][c], tb);
-        const double gt = 2.0 * p0 - (v[0][c] + v[4][c]);
-        const double mn = c == 0 ? 0.0 : 1.0;
-        const double same = Z.mz * (a_n * mt * Nl + mn * Tl + w.bxy * NTm) + w.ridge2 * p0 + d_n * nb + tb;
-        const double G = b_nz * mt * gn2 + b_tz * mn * gt;
-        const double pm = mn * mt * p0;
-        // l = t + dz B: the masks act on the azz T part only
-        A[2][c] += same + fma(Z.t0, pm, (Z.l0 - Z.t0) * p0) + Z.c0 * G;
-        A[1][c] += fma(Z.tm1, pm, (Z.lm1 - Z.tm1) * p0);
-        A[3][c] += fma(Z.tp1, pm, (Z.lp1 - Z.tp1) * p0);
-        A[0][c] += fma(Z.tm2, pm, (Z.lm2 - Z.tm2) * p0) + Z.cm2 * G;
-        A[4][c] += fma(Z.tp2, pm, (Z.lp2 - Z.tp2) * p0) + Z.cp2 * G;
+        rest += tb;
+        A[2][c] += fma(Z.mz, inplane, rest) + fma(Z.t0, pm, Z.b0 * p0) + Z.c0 * G;
+        A[1][c] += fma(Z.tm1, pm, Z.bm1 * p0);
+        A[3][c] += fma(Z.tp1, pm, Z.bp1 * p0);
+        A[0][c] += fma(Z.tm2, pm, Z.bm2 * p0) + Z.cm2 * G;
+        A[4][c] += fma(Z.tp2, pm, Z.bp2 * p0) + Z.cp2 * G;
       }
     }
     // output plane kp-2 is complete
@@ -257,22 +340,16 @@ __device__ __forceinline__ double strip_cta(const GridDesc& g, const StencilWeig
         const double* P = S + s2 * PLANE + (tid + HALO) * ST_T;
 #pragma unroll
         for (int c = 0; c < W; ++c) dot = fma(P[c * ST_C], A[0][c], dot);
-        if (AXIS == 0) {
-          double* qrow = q + qoff + (long long)g.pitch * jt;
-          if ((g.pitch & 1) == 0 && (g.nx & 1) == 0) {  // the four nodes of the row are one aligned 32-byte sector
-            double2* dst = reinterpret_cast<double2*>(qrow + (side ? g.nx - 4 : 0));
-            dst[0] = side ? make_double2(A[0][3], A[0][2]) : make_double2(A[0][0], A[0][1]);
-            dst[1] = side ? make_double2(A[0][1], A[0][0]) : make_double2(A[0][2], A[0][3]);
-          } else {
-#pragma unroll
-            for (int c = 0; c < W; ++c) qrow[side ? g.nx - 1 - c : c] = A[0][c];
-          }
+        if (AXIS == 0 && (g.pitch & 1) == 0 && (g.nx & 1) == 0) {  // the four nodes of a row: one aligned 32-byte sector
+          double2* dst = reinterpret_cast<double2*>(qpl + qo[side ? 3 : 0]);
+          dst[0] = side ? make_double2(A[0][3], A[0][2]) : make_double2(A[0][0], A[0][1]);
+          dst[1] = side ? make_double2(A[0][1], A[0][0]) : make_double2(A[0][2], A[0][3]);
         } else {
 #pragma unroll
-          for (int c = 0; c < W; ++c) q[qoff + (long long)g.pitch * (side ? g.ny - 1 - c : c) + jt] = A[0][c];  // coalesced in x
+          for (int c = 0; c < W; ++c) qpl[qo[c]] = A[0][c];  // y strips: coalesced along x
         }
       }
-      qoff += g.plane;
+      qpl += g.plane;
     }
 #pragma unroll
     for (int c = 0; c < W; ++c) {
@@ -334,18 +411,27 @@ __device__ __forceinline__ double z_face_block(const GridDesc& g, const UniConst
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-template <int TYT, int ST, int MINB, bool VEC16>
+#ifdef LSB_EMU
+#define LSB_GRID_CONSTANT
+#else
+#define LSB_GRID_CONSTANT __grid_constant__
+#endif
+// TMA = true: the box tiles are staged by the TMA unit (needs VEC16: an even row pitch, and `tmap` describing p);
+// the strips keep cp.async (48-byte rows).
+template <int TYT, int ST, int MINB, bool VEC16, bool TMA = false>
 __global__ void __launch_bounds__(32 * TYT, MINB)
     k_fdi_fused(const GridDesc g, const UniConsts U, const StencilWeights w, const FusedPlan pl, const double* __restrict__ p,
                 double* __restrict__ q, const double* __restrict__ ztab, double* __restrict__ partials,
-                unsigned int* __restrict__ counter, CgScalars* __restrict__ sc, const int cg_mode) {
+                unsigned int* __restrict__ counter, CgScalars* __restrict__ sc, const int cg_mode,
+                const LSB_GRID_CONSTANT TmapArg tmap) {
   constexpr int YB = 4;
   using C = MainCfg<YB, TYT, ST>;
   static_assert(ST >= 6, "ring: planes kp-2..kp plus three in flight; the z-face block stages five planes at once");
   static_assert((C::NT + 2 * HALO) * StripGeom<0>::NC <= C::PLANE, "a strip plane must fit a box plane slot");
   LSB_DYN_SMEM(S);
   __shared__ double red[C::NT / 32];
-  __shared__ ZFull zfm[11];  // strips: z coefficients of the planes next to a z face; [10]: the interior constants
+  __shared__ ZStrip zsm[11];  // strips: z coefficients of the planes next to a z face; [10]: the interior constants
+  __shared__ __align__(8) unsigned long long full[TMA ? ST : 1];  // TMA: one mbarrier per ring slot
 
   if (cg_mode && sc->done) return;
 
@@ -354,63 +440,92 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
   const int bid = blockIdx.x;
   double dot = 0.0;
 
-  if (bid < pl.n_xs + pl.n_ys) {
-    // ---- strip roles
+  if (bid >= pl.n_box) {
+    // ---- strip roles (the last block indices: they fill the CTA slots the box tiles leave free)
     if (tid < 10) {
       const int k = tid < 5 ? tid : g.nz - 5 + (tid - 5);
       ZFull Zf{};
       if (k >= 0 && k < g.nz) Zf = z_full(g, ztab, U.azz, U.dz, k);
-      zfm[tid] = Zf;
+      zsm[tid] = z_strip(Zf);
     }
-    if (tid == 10) zfm[10] = z_uniform(U.azz);
+    if (tid == 10) zsm[10] = z_strip(z_uniform(U.azz));
     __syncthreads();
-    const bool ys = bid >= pl.n_xs;
-    const int b = ys ? bid - pl.n_xs : bid;
+    const bool ys = bid >= pl.n_box + pl.n_xs;
+    const int b = bid - pl.n_box - (ys ? pl.n_xs : 0);
     const int per_side = ys ? pl.ys_x : pl.xs_y;
     const int ch = b / (2 * per_side), rem = b - ch * 2 * per_side;
     const int side = rem / per_side, st = rem - side * per_side;
     const int ka = g.k0 + ch * pl.scz, kb = min(ka + pl.scz, g.k1);
-    if (ys) dot = strip_cta<C::NT, ST, 1>(g, w, zfm, p, q, side, C::X_FIRST + st * C::NT, C::X_FIRST, g.nx - C::X_FIRST, ka, kb, S, tid);
-    else dot = strip_cta<C::NT, ST, 0>(g, w, zfm, p, q, side, st * C::NT, 0, g.ny, ka, kb, S, tid);
+    if (ys) dot = strip_cta<C::NT, ST, 1>(g, w, zsm, p, q, side, C::X_FIRST + st * C::NT, C::X_FIRST, g.nx - C::X_FIRST, ka, kb, S, tid);
+    else dot = strip_cta<C::NT, ST, 0>(g, w, zsm, p, q, side, st * C::NT, 0, g.ny, ka, kb, S, tid);
   } else {
     // ---- box role: interior tile, the march of k_fdi_box over the planes 3 <= k < nz-3 of its chunk
-    const int b = bid - pl.n_xs - pl.n_ys;
+    const int b = bid;
     const int tiles = pl.tiles_x * pl.tiles_y;
     const int ch = b / tiles, trem = b - ch * tiles;
     const int by = trem / pl.tiles_x, bx = trem - by * pl.tiles_x;
     const int x0 = C::X_FIRST + bx * C::TX, y0 = C::Y_FIRST + by * C::TY;
-    const int ka = g.k0 + ch * pl.cz, kb = min(ka + pl.cz, g.k1);
+    const int ka = ch == 0 ? g.k0 : g.k0 + pl.lo_len + (ch - 1) * pl.cz;
+    const int kb = ch == 0 ? min(g.k0 + pl.lo_len, g.k1) : min(ka + pl.cz, g.k1);
     const int i0 = x0 + 2 * tx;
     const int j0 = y0 + YB * ty;
     const int nrows = max(0, min(YB, (g.ny - C::Y_FIRST) - j0));
     const int xlim = g.nx - C::X_FIRST;
 
-    // Staging of one plane: slot idx = tid + t NT of the (SX x SY) tile (pairs of doubles when VEC16) <- the in-plane
-    // offset off[t] of its source, computed once (every staged node of an interior tile is a real node or overhang).
-    constexpr int LD = VEC16 ? C::LD16 : C::LD8;
+    // Staging of one plane.  cp.async: slot idx = tid + t NT of the (SX x SY) tile (pairs of doubles when VEC16) <- the
+    // in-plane offset off[t] of its source, computed once (every staged node of an interior tile is a real node or
+    // overhang).  TMA: one thread arms the slot's mbarrier with the byte count and issues the tile copy.
+    constexpr int LD = TMA ? 1 : (VEC16 ? C::LD16 : C::LD8);
     constexpr int NSLOT = VEC16 ? C::PLANE / 2 : C::PLANE;
+    constexpr unsigned PLANE_BYTES = C::PLANE * sizeof(double);
     int off[LD];
+    unsigned phases = 0;  // TMA: parity of the next completion of every slot's mbarrier (bit s = slot s)
+    if constexpr (TMA) {
+      off[0] = 0;
+      if (tid == 0) {
 #pragma unroll
-    for (int t = 0; t < LD; ++t) {
-      const int idx = tid + t * C::NT;
-      off[t] = -1;
-      if (idx < NSLOT) {
-        const int e0 = VEC16 ? 2 * idx : idx;
-        const int sy = e0 / C::SX, sx = e0 - sy * C::SX;
-        const int gi = x0 - HALO + sx, gj = y0 - HALO + sy;  // >= 2, >= 1
-        if (gi < g.nx && gj < g.ny) off[t] = gi + g.pitch * gj;
+        for (int s2 = 0; s2 < ST; ++s2) mbar_init(&full[s2], 1);
+        mbar_fence_init();
       }
-    }
-    auto stage = [&](double* dstS, const int k) {  // plane k (global index, must exist) -> dstS
-      const double* src = p + (long long)(k - g.k0 + HALO) * g.plane;
+      __syncthreads();
+    } else {
 #pragma unroll
       for (int t = 0; t < LD; ++t) {
         const int idx = tid + t * C::NT;
+        off[t] = -1;
         if (idx < NSLOT) {
-          const bool ok = off[t] >= 0;
-          if (VEC16) cp_async_16(dstS + 2 * idx, src + (ok ? off[t] : 0), ok);
-          else cp_async_8(dstS + idx, src + (ok ? off[t] : 0), ok);
+          const int e0 = VEC16 ? 2 * idx : idx;
+          const int sy = e0 / C::SX, sx = e0 - sy * C::SX;
+          const int gi = x0 - HALO + sx, gj = y0 - HALO + sy;  // >= 2, >= 1
+          if (gi < g.nx && gj < g.ny) off[t] = gi + g.pitch * gj;
         }
+      }
+    }
+    // plane k (global index, must exist) -> ring slot s
+    auto stage = [&](const int s, const int k) {
+      if constexpr (TMA) {
+        if (tid == 0) {
+          mbar_expect_tx(&full[s], PLANE_BYTES);
+          tma_load_3d(S + s * C::PLANE, &tmap, x0 - HALO, y0 - HALO, k - g.k0 + HALO, &full[s]);
+        }
+      } else {
+        const double* src = p + (long long)(k - g.k0 + HALO) * g.plane;
+        double* dstS = S + s * C::PLANE;
+#pragma unroll
+        for (int t = 0; t < LD; ++t) {
+          const int idx = tid + t * C::NT;
+          if (idx < NSLOT) {
+            const bool ok = off[t] >= 0;
+            if (VEC16) cp_async_16(dstS + 2 * idx, src + (ok ? off[t] : 0), ok);
+            else cp_async_8(dstS + idx, src + (ok ? off[t] : 0), ok);
+          }
+        }
+      }
+    };
+    auto wait_slot = [&](const int s) {  // TMA: until the tile of slot s has landed
+      if constexpr (TMA) {
+        mbar_wait(&full[s], (phases >> s) & 1u);
+        phases ^= 1u << s;
       }
     };
     const int my_off = (YB * ty) * C::SX + 2 * tx;
@@ -423,9 +538,13 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
       const int f1 = face == 0 ? min(kb, min(3, g.nz)) : kb;
       if (f0 >= f1) continue;
       const int s0 = max(f0 - HALO, 0), s1 = min(f1 + HALO, g.nz);  // at most 5 planes
-      for (int k = s0; k < s1; ++k) stage(S + (k - s0) * C::PLANE, k);
-      cp_async_commit();
-      cp_async_wait<0>();
+      for (int k = s0; k < s1; ++k) stage(k - s0, k);
+      if constexpr (TMA) {
+        for (int k = s0; k < s1; ++k) wait_slot(k - s0);
+      } else {
+        cp_async_commit();
+        cp_async_wait<0>();
+      }
       __syncthreads();
       dot += z_face_block<YB, C::SX, C::PLANE>(g, U, ztab, S + my_off + 2 * C::SX + 2,
                                                q + (long long)(f0 - g.k0 + HALO) * g.plane + (long long)g.pitch * j0 + i0, f0, f1,
@@ -442,20 +561,41 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
     const int kstart = ua - HALO, kend = ua < ub ? ub + HALO : ua - HALO;
     int kp = kstart;
     int issued = kstart;
+    const double* src = p + (long long)(kstart - g.k0 + HALO) * g.plane;  // cp.async: next plane to stage
+    // cp.async variant of `stage` with a running source pointer (no 64-bit multiply inside the march)
+    auto stage_next = [&](const int s) {
+      if constexpr (TMA) {
+        stage(s, issued);
+      } else {
+        double* dstS = S + s * C::PLANE;
+#pragma unroll
+        for (int t = 0; t < LD; ++t) {
+          const int idx = tid + t * C::NT;
+          if (idx < NSLOT) {
+            const bool ok = off[t] >= 0;
+            if (VEC16) cp_async_16(dstS + 2 * idx, src + (ok ? off[t] : 0), ok);
+            else cp_async_8(dstS + idx, src + (ok ? off[t] : 0), ok);
+          }
+        }
+        src += g.plane;
+      }
+      ++issued;
+    };
 #pragma unroll
     for (int s = 0; s < ST - 3; ++s) {
-      if (issued < kend) { stage(S + s * C::PLANE, issued); ++issued; }
-      cp_async_commit();
+      if (issued < kend) stage_next(s);
+      if constexpr (!TMA) cp_async_commit();
     }
     int slot = 0;
     double* qdst = q + (long long)(ua - g.k0 + HALO) * g.plane + (long long)g.pitch * j0 + i0;  // output plane ua
 
     auto advance_pipeline = [&]() {
-      cp_async_wait<ST - 4>();
-      __syncthreads();
+      if constexpr (TMA) wait_slot(slot);
+      else cp_async_wait<ST - 4>();
+      __syncthreads();  // every thread is done with plane kp-3: its slot is staged again
       const int fs = slot >= 3 ? slot - 3 : slot + ST - 3;
-      if (issued < kend) { stage(S + fs * C::PLANE, issued); ++issued; }
-      cp_async_commit();
+      if (issued < kend) stage_next(fs);
+      if constexpr (!TMA) cp_async_commit();
     };
     auto store_out = [&](const double (&out)[YB][2]) {
       if (kp - HALO < ua) return;
@@ -506,7 +646,7 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
       }
     }
 #undef LSB_FUSED_STEP
-    cp_async_wait<0>();
+    if constexpr (!TMA) cp_async_wait<0>();
   }
 
   const double bsum = block_sum<C::NT>(dot, red);

@@ -3,6 +3,9 @@
 // emulation of the same kernels), so that the plan itself is under test without a device.
 #pragma once
 #include <algorithm>
+#include <functional>
+#include <queue>
+#include <vector>
 
 #include "fdi_main.cuh"
 #include "fdi_fused.cuh"
@@ -142,15 +145,20 @@ struct FusedChoice {
   int tyt, minb;
   FusedPlan pl;
   long long ctas;
-  double cost;  // plane steps on the critical path (waves x steps per CTA), the quantity the planner minimises
+  double cost;  // estimated critical path in box plane steps, the quantity the planner minimises
 };
 
-// One candidate: box CTAs of `nch` z chunks.  The strip CTAs get SHORT chunks: a strip plane step costs about
-// `strip_rel` box plane steps (general coefficients, one warp-step moves 128 x 4 nodes; measured, profiles/r2d) and a
-// strip CTA must not outlast a box CTA, while the z halo it re-stages (4 planes per chunk) hardly matters for 5 % of the
-// nodes.  LSB200_FUSED_SCZ overrides the strip chunk length.
-inline FusedChoice fused_candidate(const GridDesc& g, const int tyt, const int minb, const int nch, const int sm_count,
-                                   const int scz_override) {
+// Cost model (units: one plane step of a box CTA with the SM fully populated; measured on a B200, profiles/r2e):
+//   box CTA      planes + 4 halo steps, + FACE_COST when the chunk owns planes next to a z face (z_face_block);
+//   x / y strip  (planes + 4) * XS_REL / YS_REL (general coefficients: 344 / 476 instructions per warp step against 242 of
+//                a TMA-staged box step, profiles/r2f).
+// The launch is simulated as the hardware runs it: CTAs in block-index order onto the first free of (SMs x CTAs per SM)
+// slots; the plan with the shortest makespan wins.
+constexpr double FUSED_FACE_COST = 12.0, FUSED_XS_REL = 1.45, FUSED_YS_REL = 2.0;
+constexpr double FUSED_CTA_COST = 4.0;  // prologue of a CTA (offset table, first planes in flight) in plane steps
+
+inline FusedChoice fused_candidate(const GridDesc& g, const int tyt, const int minb, const int nch, const int scz_in,
+                                   const int sm_count) {
   FusedChoice c;
   c.tyt = tyt;
   c.minb = minb;
@@ -158,23 +166,48 @@ inline FusedChoice fused_candidate(const GridDesc& g, const int tyt, const int m
   const int ty = 4 * tyt, nt = 32 * tyt;
   pl.tiles_x = (g.nx - 8 + 63) / 64;
   pl.tiles_y = (g.ny - 6 + ty - 1) / ty;
-  pl.cz = std::max(1, (g.nzl + nch - 1) / nch);
-  pl.chunks = (g.nzl + pl.cz - 1) / pl.cz;
+  // chunks of cz planes, the first / last shorter by FACE_COST planes when they own a z face
+  const bool lo_face = g.k0 < 3, hi_face = g.k1 > g.nz - 3;
+  const int d_lo = (lo_face && nch > 1) ? (int)FUSED_FACE_COST : 0, d_hi = (hi_face && nch > 1) ? (int)FUSED_FACE_COST : 0;
+  pl.cz = std::max(1, (g.nzl + d_lo + d_hi + nch - 1) / nch);
+  pl.lo_len = std::max(1, std::min(pl.cz - d_lo, g.nzl));
+  pl.chunks = 1 + (g.nzl > pl.lo_len ? (g.nzl - pl.lo_len + pl.cz - 1) / pl.cz : 0);
   pl.n_box = pl.tiles_x * pl.tiles_y * pl.chunks;
   pl.xs_y = (g.ny + nt - 1) / nt;
   pl.ys_x = (g.nx - 8 + nt - 1) / nt;
-  constexpr double strip_rel = 2.0;
-  int scz = scz_override > 0 ? scz_override : (int)((pl.cz + 2 * HALO) / strip_rel) - 2 * HALO;
-  scz = std::max(4, std::min(scz, g.nzl));
+  const int scz = std::max(2, std::min(scz_in, g.nzl));
   pl.schunks = (g.nzl + scz - 1) / scz;
   pl.scz = (g.nzl + pl.schunks - 1) / pl.schunks;
   pl.schunks = (g.nzl + pl.scz - 1) / pl.scz;
   pl.n_xs = 2 * pl.xs_y * pl.schunks;
   pl.n_ys = 2 * pl.ys_x * pl.schunks;
   c.ctas = (long long)pl.n_box + pl.n_xs + pl.n_ys;
+  // costs, in block-index order (the order in which the hardware hands CTAs to free slots): box tiles chunk by chunk,
+  // then x strips, then y strips
+  const int last_len = g.nzl - pl.lo_len - std::max(0, pl.chunks - 2) * pl.cz;  // planes of the last chunk (chunks >= 2)
   const long long slots = (long long)sm_count * minb;
-  const long long waves = (c.ctas + slots - 1) / slots;
-  c.cost = (double)waves * (pl.cz + 2 * HALO);
+  std::priority_queue<double, std::vector<double>, std::greater<double>> free_at;  // list scheduling on `slots` slots
+  double makespan = 0.0;
+  auto run = [&](const double cost, const long long count) {
+    for (long long i = 0; i < count; ++i) {
+      double start = 0.0;
+      if ((long long)free_at.size() >= slots) {
+        start = free_at.top();
+        free_at.pop();
+      }
+      free_at.push(start + cost);
+      makespan = std::max(makespan, start + cost);
+    }
+  };
+  for (int ch = 0; ch < pl.chunks; ++ch) {
+    const int len = ch == 0 ? pl.lo_len : (ch == pl.chunks - 1 ? last_len : pl.cz);
+    const bool lo = lo_face && ch == 0, hi = hi_face && ch == pl.chunks - 1;
+    run(FUSED_CTA_COST + len + 2 * HALO + (lo ? FUSED_FACE_COST : 0.0) + (hi ? FUSED_FACE_COST : 0.0), (long long)pl.tiles_x * pl.tiles_y);
+  }
+  run(FUSED_CTA_COST + (pl.scz + 2 * HALO) * FUSED_XS_REL, pl.n_xs);
+  run(FUSED_CTA_COST + (pl.scz + 2 * HALO) * FUSED_YS_REL, pl.n_ys);
+  // a CTA of a 96-thread configuration holds a quarter of an SM, one of 128 threads a third: scale to SM time
+  c.cost = makespan * (32.0 * tyt * minb) / 384.0;
   return c;
 }
 
@@ -185,14 +218,26 @@ inline bool plan_fused(const GridDesc& g, const int sm_count, const long long ma
   if (g.nx < 16 || g.ny < 16 || g.nz < 6 || g.nzl < 1) return false;
   bool have = false;
   FusedChoice best{};
+  // strip chunkings: every count of chunks up to 48 (chunk lengths nzl, nzl/2, ...), at least 6 planes each
+  std::vector<int> scz_list;
+  for (int n = 1; n <= 48; ++n) {
+    const int scz = (g.nzl + n - 1) / n;
+    if (scz < 6 && n > 1) break;
+    if (scz_list.empty() || scz_list.back() != scz) scz_list.push_back(scz);
+  }
 #define X(TYT, ST, MINB)                                                                                \
   if (cfg_override == 0 || cfg_override == TYT) {                                                       \
-    const int max_nch = cz_override > 0 ? 1 : std::max(1, g.nzl / 4);                                   \
+    const int max_nch = cz_override > 0 ? 1 : std::max(1, std::min(g.nzl / 8, 24));                                   \
     for (int nch = 1; nch <= max_nch && nch <= 4096; ++nch) {                                           \
       const int n = cz_override > 0 ? std::max(1, (g.nzl + cz_override - 1) / cz_override) : nch;       \
-      const FusedChoice c = fused_candidate(g, TYT, MINB, n, sm_count, scz_override);                   \
-      if (c.ctas > max_partials) break;                                                                 \
-      if (!have || c.cost < best.cost - 1e-9) { best = c; have = true; }                                \
+      bool too_many = false;                                                                            \
+      for (const int scz : scz_list) {                                                                  \
+        const FusedChoice c = fused_candidate(g, TYT, MINB, n, scz_override > 0 ? scz_override : scz, sm_count); \
+        if (c.ctas > max_partials) { too_many = true; continue; }                                       \
+        if (!have || c.cost < best.cost - 1e-9) { best = c; have = true; }                              \
+        if (scz_override > 0) break;                                                                    \
+      }                                                                                                 \
+      if (too_many && nch > 1) break;                                                                   \
     }                                                                                                   \
   }
   LSB_FUSED_CFGS(X)

@@ -275,6 +275,11 @@ class Engine:
         nat.check(self._lib.lsb200_get_rhs(self._h, nat.dptr(out)))
         return out
 
+    def set_rhs(self, rhs):
+        """Replace the right-hand side of the normal equations (valid until the rows change)."""
+        rhs = nat.as_f64(rhs, (self.local_dof,))
+        nat.check(self._lib.lsb200_set_rhs(self._h, nat.dptr(rhs)))
+
     def diagonal(self) -> np.ndarray:
         out = self._vec()
         nat.check(self._lib.lsb200_get_diagonal(self._h, nat.dptr(out)))

@@ -78,14 +78,8 @@ def _resolve_tolerances(tol, solver_kwargs):
     return rtol, atol, kw
 
 
-def _solve_on_engine(it, eng, solver, tol, solver_kwargs, skip=()) -> bool:
-    """Common tail of solve_system(solver='b200'): constraint dict -> ELL rows -> device CG -> it.c.  ``skip``: keys of
-    ``it.constraints`` that reach the engine as stencil weights instead of rows."""
-    started = perf_counter()
-    rtol, atol, kw = _resolve_tolerances(tol, solver_kwargs)
-    eng.set_options(ridge_factor=it.ridge_factor, add_ridge=it.add_ridge_regulatisation,
-                    apply_scaling=it.apply_scaling_matrix, deterministic=bool(kw.get("deterministic", False)))
-    t_asm = perf_counter()
+def _load_rows(it, eng, skip=()) -> int:
+    """Every family of ``it.constraints`` except ``skip`` (those travel as stencil weights) -> ELL rows on the device."""
     n_rows = 0
     eng.clear_rows()
     rows = {k: c for k, c in it.constraints.items() if k not in skip}
@@ -95,6 +89,93 @@ def _solve_on_engine(it, eng, solver, tol, solver_kwargs, skip=()) -> bool:
     for other, w2l, step, w, b, _stock, _pos in getattr(it, "_b200_device_rows", []):
         # frame-orthogonality families diverted by the builder patch: generated on the device from the other field
         n_rows += eng.add_field_orthogonal_rows(other, step=step, weight=w, b=b, other_world_to_local=w2l)
+    return n_rows
+
+
+def _csr_to_ell(m):
+    """Rows of a scipy sparse matrix as (vals (n,k), cols (n,k) int64), unused slots value 0 on column 0."""
+    m = m.tocsr()
+    m.sort_indices()
+    n = m.shape[0]
+    counts = np.diff(m.indptr)
+    k = int(counts.max()) if n else 0
+    vals = np.zeros((n, max(k, 1)))
+    cols = np.zeros((n, max(k, 1)), dtype=np.int64)
+    if k:
+        slot = np.arange(m.nnz) - np.repeat(m.indptr[:-1], counts)
+        rows = np.repeat(np.arange(n), counts)
+        vals[rows, slot] = m.data
+        cols[rows, slot] = m.indices
+    return vals, cols
+
+
+def _solve_admm_on_engine(it, eng, skip, stock_solve, tol, kw) -> bool:
+    """solver='admm' with solver_kwargs['linsys_solver'] in B200_SOLVERS: the outer ADMM loop is the reference's own
+    (LI/loopsolver/admm_solver.py:59-152: projections onto the bounds, dual updates, stopping test); its inner
+    least-squares solves  min || [A; rho Q] dx - [b - A m; rho (z - u - Q m)] ||  (:243-316, by default lsmr, optionally
+    Jacobi-preconditioned CG on the explicit normal equations) run on the device: the operator
+    [A; rho Q]^T [A; rho Q] = S (N + ridge^2) S + rho^2 Q^T Q is applied matrix-free -- N by the engine's stencil / row
+    kernels exactly as for solver='b200', rho Q as one more row block -- and only the right-hand side changes between
+    the (up to 200) outer iterations (lsb200_set_rhs).  The reference column-scales A but not Q (the model it iterates on
+    is y = S^-1 c); in c = S y the system reads (N + ridge^2 + Q'^T Q') c = S^-1 rhs_y with Q' = rho Q S^-1, which is what
+    the engine solves, with its own diagonal scaling inside CG."""
+    state = {"S": None, "rows_A": None, "qkey": None, "solves": 0, "iterations": 0, "rows": 0}
+    stock_scaling = it.compute_column_scaling_matrix
+
+    def capture_scaling(A):
+        S = stock_scaling(A)
+        state["S"] = np.asarray(S.diagonal(), dtype=np.float64)
+        state["rows_A"] = A.shape[0]
+        return S
+
+    def inner(system_matrix, rhs, x0=None, **ikw):
+        M = system_matrix.tocsr()
+        n_a = state["rows_A"] if state["rows_A"] is not None else M.shape[0]
+        S = state["S"] if state["S"] is not None else np.ones(M.shape[1])
+        Qs = M[n_a:]
+        key = (Qs.shape[0], Qs.nnz, float(Qs.data.sum()), float(np.abs(Qs.data).sum()), hash(Qs.indices[:256].tobytes()))
+        if key != state["qkey"]:  # first solve, rho changed, or another active set: rebuild the row blocks
+            state["rows"] = _load_rows(it, eng, skip)
+            if Qs.shape[0]:
+                Qc = Qs.copy()
+                Qc.data = Qc.data / S[Qc.indices]
+                vals, cols = _csr_to_ell(Qc)
+                eng.add_rows(vals, cols, np.zeros(Qc.shape[0]), np.ones(Qc.shape[0]), normalise=False)
+                state["rows"] += Qc.shape[0]
+            state["qkey"] = key
+        eng.set_rhs((M.T @ np.asarray(rhs, dtype=np.float64).ravel()) / S)
+        rtol = float(ikw.get("rtol", ikw.get("btol", 1e-6)))
+        atol = float(ikw["atol"]) if ("atol" in ikw and "rtol" in ikw) else 0.0
+        c, res = eng.solve_cg(rtol=rtol, atol=atol, maxiter=ikw.get("maxiter"), x0=None if x0 is None else np.asarray(x0) * S)
+        state["solves"] += 1
+        state["iterations"] += res.iterations
+        return c / S
+
+    eng.set_options(ridge_factor=it.ridge_factor, add_ridge=it.add_ridge_regulatisation, apply_scaling=it.apply_scaling_matrix)
+    kw = dict(kw)
+    kw["linsys_solver"] = inner
+    it.compute_column_scaling_matrix = capture_scaling  # instance attribute: read at call time by _preprocess_main_system
+    try:
+        ok = stock_solve(solver="admm", tol=tol, solver_kwargs=kw)
+    finally:
+        del it.compute_column_scaling_matrix
+    if ok and state["solves"] > 0:
+        eng.set_c(np.asarray(it.c, dtype=np.float64))  # the field lives on the device again: evaluation stays there
+        it.latest_solve_timing = dict(it.latest_solve_timing, inner_backend="b200", inner_solves=state["solves"],
+                                      inner_iterations=state["iterations"], matrix_rows_device=state["rows"],
+                                      b200_field_resident=True)
+    return ok
+
+
+def _solve_on_engine(it, eng, solver, tol, solver_kwargs, skip=()) -> bool:
+    """Common tail of solve_system(solver='b200'): constraint dict -> ELL rows -> device CG -> it.c.  ``skip``: keys of
+    ``it.constraints`` that reach the engine as stencil weights instead of rows."""
+    started = perf_counter()
+    rtol, atol, kw = _resolve_tolerances(tol, solver_kwargs)
+    eng.set_options(ridge_factor=it.ridge_factor, add_ridge=it.add_ridge_regulatisation,
+                    apply_scaling=it.apply_scaling_matrix, deterministic=bool(kw.get("deterministic", False)))
+    t_asm = perf_counter()
+    n_rows = _load_rows(it, eng, skip)
     assembly = perf_counter() - t_asm
     c, res = eng.solve_cg(rtol=rtol, atol=atol, maxiter=kw.get("maxiter"), x0=kw.get("x0"))
     it.c = c  # an ndarray that owns its memory: callers may keep it across solves and past the interpolator's life
@@ -187,6 +268,15 @@ class _B200Mixin:
         return self._b200_engine
 
     def solve_system(self, solver=None, tol=None, solver_kwargs=None) -> bool:
+        if solver == "admm" and (solver_kwargs or {}).get("linsys_solver") in B200_SOLVERS:
+            # inequality-constrained solve: the reference's ADMM loop with its inner solves on the device
+            if not self._b200_supported(self._b200_setup_kwargs):
+                raise ValueError(self._b200_unsupported)
+            if self._b200_divert:
+                self._b200_materialise()  # the stock pipeline assembles the explicit A for its own bookkeeping
+            eng = self._b200_get_engine()
+            skip = self._b200_set_regularisation(eng)
+            return _solve_admm_on_engine(self, eng, skip, super().solve_system, tol, solver_kwargs)
         if solver not in B200_SOLVERS:
             if self._b200_divert:
                 self._b200_materialise()
@@ -201,7 +291,8 @@ class _B200Mixin:
 
     # -- evaluation: the device holds c after a b200 solve -------------------------------------------------
     def _b200_engine_current(self):
-        if self._b200_engine is None or not self.up_to_date or self.latest_solve_timing.get("backend") != "b200":
+        t = self.latest_solve_timing
+        if self._b200_engine is None or not self.up_to_date or not (t.get("backend") == "b200" or t.get("b200_field_resident")):
             return None
         return self._b200_engine
 

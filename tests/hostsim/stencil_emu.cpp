@@ -170,8 +170,8 @@ HOSTSIM_API int emu_fdi_fused(const int* dims, const double* ew, double ridge2, 
 #define X(TYT, ST, MINB)                                                                                             \
   case TYT: {                                                                                                        \
     const size_t smem = sizeof(double) * MainCfg<4, TYT, ST>::PLANE * ST;                                            \
-    if (vec16) lsb_emu::launch(dim3(ctas), dim3(32, TYT), smem, [&] { k_fdi_fused<TYT, ST, MINB, true>(g, U, w, fc.pl, p, q, ztab.data(), partials.data(), &counter, &sc, 0); }); \
-    else lsb_emu::launch(dim3(ctas), dim3(32, TYT), smem, [&] { k_fdi_fused<TYT, ST, MINB, false>(g, U, w, fc.pl, p, q, ztab.data(), partials.data(), &counter, &sc, 0); }); \
+    if (vec16) lsb_emu::launch(dim3(ctas), dim3(32, TYT), smem, [&] { k_fdi_fused<TYT, ST, MINB, true>(g, U, w, fc.pl, p, q, ztab.data(), partials.data(), &counter, &sc, 0, TmapArg{}); }); \
+    else lsb_emu::launch(dim3(ctas), dim3(32, TYT), smem, [&] { k_fdi_fused<TYT, ST, MINB, false>(g, U, w, fc.pl, p, q, ztab.data(), partials.data(), &counter, &sc, 0, TmapArg{}); }); \
   } break;
     LSB_FUSED_CFGS(X)
 #undef X
@@ -186,6 +186,19 @@ HOSTSIM_API int emu_fdi_fused(const int* dims, const double* ew, double ridge2, 
     const bool owned = i >= guard + (size_t)HALO * g.plane && i < guard + (size_t)(HALO + g.nzl) * g.plane;
     if (!owned && qst[i] == qst[i]) return -2;
   }
+  return 0;
+}
+
+// the plan alone (no launch): info = {TYT, cz, chunks, lo_len, box CTAs, scz, x-strip CTAs, y-strip CTAs, MINB}, *cost = model cost
+HOSTSIM_API int emu_plan_fused(const int* dims, int cfg, int cz_override, int scz_override, int sm_count, int* info, double* cost) {
+  GridDesc g{};
+  g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
+  g.k0 = dims[3]; g.k1 = dims[4]; g.nzl = g.k1 - g.k0;
+  FusedChoice fc;
+  if (!plan_fused(g, sm_count, MAX_PARTIALS, cfg, cz_override, scz_override, &fc)) return -3;
+  info[0] = fc.tyt; info[1] = fc.pl.cz; info[2] = fc.pl.chunks; info[3] = fc.pl.lo_len; info[4] = fc.pl.n_box;
+  info[5] = fc.pl.scz; info[6] = fc.pl.n_xs; info[7] = fc.pl.n_ys; info[8] = fc.minb;
+  *cost = fc.cost;
   return 0;
 }
 

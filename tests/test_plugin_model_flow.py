@@ -43,6 +43,13 @@ class OracleEngine:
     def clear_rows(self):
         self.rows = []
         self.device_families = 0
+        self.rhs_override = None
+
+    def set_rhs(self, rhs):
+        self.rhs_override = np.array(rhs, dtype=float)
+
+    def set_c(self, c):
+        self.c = np.array(c, dtype=float)
 
     def add_rows(self, A, idx, b, w, normalise=True):
         assert normalise is False  # the reference has normalised them already
@@ -67,6 +74,18 @@ class OracleEngine:
             w.update(self.weights)
             fams = self.rows + self.fo.regularisation_families(self.grid, w)
         self.solve_args = dict(rtol=rtol, atol=atol)
+        if getattr(self, "rhs_override", None) is not None:
+            # lsb200_set_rhs: the operator of the rows, the right-hand side of the caller, CG from x0 in the scaled variables
+            A, b = self.fo.assemble(fams, self.grid.n_nodes)
+            A, b, S = self.fo.preprocess(A, b, ridge_factor=self.opts.get("ridge_factor", 1e-8),
+                                         apply_scaling=self.opts.get("apply_scaling", True))
+            S = np.ones(self.grid.n_nodes) if S is None else S
+            N = (A.T @ A).tocsr()
+            res = self.fo.cg(lambda v: N @ v, S * self.rhs_override, rtol=rtol, atol=atol, maxiter=maxiter,
+                             x0=None if x0 is None else np.asarray(x0) / S)
+            self.c = S * res.x
+            return self.c, SimpleNamespace(info=res.info, iterations=res.iterations, setup_seconds=0.0, solve_seconds=0.0,
+                                           residual_norm=res.residual_norm, threshold=res.threshold, kernel_launches=0)
         c, res, _ = self.fo.solve_reference_path(fams, self.grid.n_nodes, rtol=rtol, atol=atol,
                                                  ridge_factor=self.opts.get("ridge_factor", 1e-8),
                                                  apply_scaling=self.opts.get("apply_scaling", True))
@@ -496,3 +515,49 @@ def test_diverted_setup_never_touches_the_node_table(ls, monkeypatch):
         np.testing.assert_array_equal(it.constraints[k]["b"], stock.constraints[k]["b"])
         np.testing.assert_array_equal(it.constraints[k]["w"], stock.constraints[k]["w"])
     assert it.solve_system("b200")
+
+
+def _inequality_problem(ls, n=12):
+    import loop_interpolation as li
+    from loop_common.supports import StructuredGrid
+    from oracle import fdi_oracle as fo
+
+    grid, value, gradient = fo.synthetic_problem(n, 90, 15, seed=3)
+    sg = StructuredGrid(origin=grid.origin, nsteps_cells=grid.nsteps - 1, step_vector=grid.step)
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(0.1, 0.9, (25, 3))
+    f = fo.synthetic_field(pts)
+    ineq = np.column_stack([pts, f + 0.05, f + 0.3, np.ones(len(pts))])  # push the field above what the data say
+
+    def make(cls, **kw):
+        it = cls(sg)
+        it.set_value_constraints(value.copy())
+        it.set_gradient_constraints(gradient.copy())
+        it.set_value_inequality_constraints(ineq.copy())
+        it.setup_interpolator(**kw)
+        return it
+
+    return li, make, pts, f
+
+
+def test_admm_inner_solves_run_on_the_engine_and_match_the_stock_admm(ls):
+    """SURVEY 8 f rank 3: solver='admm' with linsys_solver='b200' keeps the reference's outer ADMM loop and sends every
+    inner least-squares solve to the engine (matrix-free stencil + data rows + rho Q as a row block, new right-hand side
+    per outer iteration).  With both inner solvers converged the two runs follow the same outer iterates."""
+    li, make, pts, f = _inequality_problem(ls)
+    cls = li.interpolator_map[li.InterpolatorType.FINITE_DIFFERENCE]
+    kw = {"nmajor": 25, "rtol": 1e-13}
+    stock = make(li.FiniteDifferenceInterpolator)
+    assert stock.solve_system("admm", solver_kwargs=dict(kw, linsys_solver="cg"))
+    for setup_kw in ({}, {"solver": "b200"}):  # explicit and diverted set-up
+        it = make(cls, **setup_kw)
+        n_eng = len(OracleEngine.instances)
+        assert it.solve_system("admm", solver_kwargs=dict(kw, linsys_solver="b200"))
+        t = it.latest_solve_timing
+        assert t["inner_backend"] == "b200" and t["inner_solves"] == 25 and len(OracleEngine.instances) == n_eng + 1
+        eng = OracleEngine.instances[-1]
+        assert eng.weights == {k: 1.0 for k in ("dxx", "dyy", "dzz", "dxy", "dxz", "dyz", "dx", "dy", "dz")}
+        assert len(eng.rows) == 4  # gradient, gradient_0, value and the rho Q block: no stencil family as rows
+        rng_ = float(stock.c.max() - stock.c.min())
+        assert np.linalg.norm(it.c - stock.c) / np.sqrt(stock.c.size) / rng_ <= 1e-7
+        np.testing.assert_allclose(it.evaluate_value(pts), stock.evaluate_value(pts), rtol=0, atol=1e-7 * rng_)

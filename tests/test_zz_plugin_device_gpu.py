@@ -161,3 +161,22 @@ def test_builder_flow_without_solver_at_setup_keeps_every_constraint_on_the_devi
     assert it.latest_solve_timing["matrix_rows"] == n_data  # the twelve stencil families did not travel as rows
     stock = solve(li.FiniteDifferenceInterpolator, "cg")
     assert rel_l2(it.c, stock.c) <= 1e-6
+
+
+def test_admm_inner_solves_on_the_device(ls):
+    """SURVEY 8 f rank 3: the reference's ADMM loop (inequality constraints) with every inner least-squares solve on the
+    device (solver='admm', solver_kwargs={'linsys_solver': 'b200'}); against the stock ADMM with converged CG inner solves."""
+    from test_plugin_model_flow import _inequality_problem
+
+    li, make, pts, f = _inequality_problem(ls, n=20)
+    cls = li.interpolator_map[li.InterpolatorType.FINITE_DIFFERENCE]
+    kw = {"nmajor": 25, "rtol": 1e-13}
+    stock = make(li.FiniteDifferenceInterpolator)
+    assert stock.solve_system("admm", solver_kwargs=dict(kw, linsys_solver="cg"))
+    it = make(cls, solver="b200")
+    assert it.solve_system("admm", solver_kwargs=dict(kw, linsys_solver="b200"))
+    t = it.latest_solve_timing
+    assert t["inner_backend"] == "b200" and t["inner_solves"] == 25 and t["inner_iterations"] > 25
+    assert rel_l2(it.c, stock.c) <= 1e-6
+    rng_ = float(stock.c.max() - stock.c.min())
+    np.testing.assert_allclose(it.evaluate_value(pts), stock.evaluate_value(pts), rtol=0, atol=1e-6 * rng_)
