@@ -448,10 +448,10 @@ def measure_launch_plans(local, sizes=(256, 512), timeout=150):
                             "max_rel_checksum_diff_vs_default": agree}
             except Exception as exc:  # noqa: BLE001
                 out[key] = {"error": f"{type(exc).__name__}: {exc}"}
-    # the P1 face-jump operator at BASELINE configs[2] size: generic kernel against the class-coherent interior kernel
+    # the P1 face-jump operator at BASELINE configs[2] size: shared-memory tiles (default) against the generic kernel
     script = os.path.join(os.path.dirname(script), "p1_experiment.py")
     ref = None
-    for name, env in (("p1_default_117", {}), ("p1_fast_117", {"LSB200_P1_FAST": "1"})):
+    for name, env in (("p1_tiles_117", {}), ("p1_generic_117", {"LSB200_P1_TILES": "0"})):
         try:
             e = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local)), **env)
             res = subprocess.run([sys.executable, script, "117"], capture_output=True, text=True, timeout=timeout, env=e)

@@ -353,6 +353,11 @@ int lsb200_host_free(void* p);
  * fused r.S^2 r reduction, 4 = p update */
 int lsb200_time_kernel(lsb200_handle h, int which, int reps, double* seconds_per_launch);
 
+/* one launch of the regularisation operator with the per-CTA trace on: out[3 b .. 3 b + 2] = {start ns, end ns, SM id}
+ * of CTA b in block-index order (the single-launch plans only: k_fdi_fused, k_p1_tiles); *n_ctas = CTAs of the launch.
+ * Shows which role of a launch (box chunk, z-face chunk, strip; tile, boundary) ends last. */
+int lsb200_debug_cta_trace(lsb200_handle h, int64_t max_ctas, uint64_t* out, int64_t* n_ctas);
+
 #ifdef __cplusplus
 }
 #endif

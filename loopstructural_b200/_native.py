@@ -112,6 +112,7 @@ SIGNATURES = {
     "lsb200_host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     "lsb200_host_free": (C.c_int, [C.c_void_p]),
     "lsb200_time_kernel": (C.c_int, [Handle, C.c_int, C.c_int, c_double_p]),
+    "lsb200_debug_cta_trace": (C.c_int, [Handle, C.c_int64, C.POINTER(C.c_uint64), c_int64_p]),
 }
 
 _lib = None

@@ -108,6 +108,10 @@ struct lsb200_ctx {
   int* p1_off = nullptr;       //   tap offsets
   double* p1_diag = nullptr;   //   and centre taps
   int p1_m[3] = {0, 0, 0};
+  bool p1_tiles = false;       // k_p1_tiles plan (meshes with an interior), else k_p1_normal everywhere
+  int p1_tile_cfg = 0;
+  P1TilePlan p1_plan{};
+  P1ClassTaps p1_cls{};
   double ridge = 1e-8;
   int add_ridge = 1, apply_scaling = 1, deterministic = 0;
   cudaStream_t stream = nullptr;
@@ -494,21 +498,27 @@ static int launch_regularisation(lsb200_ctx* h, const double* p, double* q, int 
   const long long n = (long long)h->g.nx * h->g.ny * h->g.nzl;
   const int nb = (int)std::max<long long>(1, std::min<long long>((n + VEC_NT - 1) / VEC_NT, (long long)h->sm_count * 16));
   const double w2 = h->p1_w * h->p1_w, ridge2 = h->add_ridge ? h->ridge * h->ridge : 0.0;
-  // LSB200_P1_FAST=1: interior nodes by the class-coherent kernel (table rows in registers), the rest by the generic
-  // one; off by default until it has been measured
-  static const bool fast = getenv("LSB200_P1_FAST") && atoi(getenv("LSB200_P1_FAST")) == 1;
-  P1InteriorPlan pl;
-  if (fast && p1_plan_interior(h->g, h->p1_m, 128, MAX_PARTIALS, &pl)) {
-    k_p1_normal_interior<128><<<dim3(pl.gx, pl.gy, pl.gz), 128, 0, h->stream>>>(h->g, tb, w2, ridge2, pl.jchunk, pl.kchunk, p, q,
-                                                                              h->partials, h->counters + 0, h->sc, cg_mode);
+  if (h->p1_tiles) {
+    // one launch: boundary-role CTAs first, then the shared-memory tiles of the interior (csrc/p1.cuh)
+    const P1TilePlan& pl = h->p1_plan;
+    const unsigned int ctas = (unsigned int)(pl.n_bnd_cta + pl.tiles_x * pl.tiles_y * pl.tiles_z);
+    switch (h->p1_tile_cfg) {
+#define X(ID, TY, TZ, NW)                                                                                   \
+  case ID: {                                                                                                \
+    auto kern = k_p1_tiles<TY, TZ, NW>;                                                                     \
+    const size_t smem = sizeof(double) * P1TileGeom<TY, TZ>::ELEMS;                                         \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                     \
+    kern<<<ctas, 32 * NW, smem, h->stream>>>(h->g, tb, h->p1_cls, pl, w2, ridge2, p, q, h->partials, h->counters + 0, h->sc, \
+                                             cg_mode);                                                      \
+  } break;
+      LSB_P1_TILE_CFGS(X)
+#undef X
+    }
     CKL();
-    k_p1_normal<VEC_NT, true><<<nb, VEC_NT, 0, h->stream>>>(h->g, tb, w2, ridge2, p, q, h->partials + 3 * (size_t)MAX_PARTIALS,
-                                                            h->counters + 3, h->sc, cg_mode);
-    CKL();
-    h->launches += 2;
+    h->launches++;
     return 0;
   }
-  k_p1_normal<VEC_NT, false><<<nb, VEC_NT, 0, h->stream>>>(h->g, tb, w2, ridge2, p, q, h->partials, h->counters + 0, h->sc, cg_mode);
+  k_p1_normal<VEC_NT><<<nb, VEC_NT, 0, h->stream>>>(h->g, tb, w2, ridge2, p, q, h->partials, h->counters + 0, h->sc, cg_mode);
   CKL();
   h->launches++;
   return 0;
@@ -812,6 +822,21 @@ int lsb200_set_p1_tables(lsb200_handle h, const int64_t m[3], const double* tabl
   CK(cudaMemcpy(h->p1_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->p1_diag, diag.data(), sizeof(double) * diag.size(), cudaMemcpyHostToDevice));
   for (int a = 0; a < 3; ++a) h->p1_m[a] = (int)m[a];
+  // tile plan of the interior (LSB200_P1_TILES=0: the generic kernel everywhere; LSB200_P1_TILE_CFG: tile shape)
+  static const bool want_tiles = !(getenv("LSB200_P1_TILES") && atoi(getenv("LSB200_P1_TILES")) == 0);
+  static const int tile_cfg = getenv("LSB200_P1_TILE_CFG") ? atoi(getenv("LSB200_P1_TILE_CFG")) : 0;
+  h->p1_tiles = false;
+  if (want_tiles) {
+    switch (tile_cfg) {
+#define X(ID, TY, TZ, NW)                                                                                          \
+  case ID:                                                                                                         \
+    h->p1_tiles = p1_plan_tiles(h->g, h->p1_m, table, TY, TZ, 32 * NW, MAX_PARTIALS, &h->p1_plan, &h->p1_cls);     \
+    h->p1_tile_cfg = ID;                                                                                           \
+    break;
+      LSB_P1_TILE_CFGS(X)
+#undef X
+    }
+  }
   h->finalized = false;
   return 0;
 }
@@ -2078,6 +2103,41 @@ int lsb200_host_free(void* p) {
   return 0;
 }
 
+// Diagnostics: one launch of the regularisation operator (q = N p on the handle's own vectors) with the per-CTA trace
+// switched on; out[3 b .. 3 b + 2] = {start ns, end ns, SM id} of CTA b (csrc/common.cuh, g_cta_trace).
+int lsb200_debug_cta_trace(lsb200_handle h, int64_t max_ctas, uint64_t* out, int64_t* n_ctas) {
+  if (!h || !out || !n_ctas || max_ctas < 1) return fail(LSB200_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(h->device));
+  int rc = lsb200_finalize_system(h);
+  if (rc) return rc;
+  long long ctas = 0;
+  if (h->kind == LSB200_SUPPORT_GRID) {
+    if (!(h->main_cfg >= 0 && h->fused)) return fail(LSB200_ERR_STATE, "the per-CTA trace needs the fused stencil plan");
+    ctas = (long long)h->fz.pl.n_box + h->fz.pl.n_xs + h->fz.pl.n_ys;
+  } else {
+    if (!h->p1_tiles) return fail(LSB200_ERR_STATE, "the per-CTA trace needs the tiled P1 plan");
+    ctas = (long long)h->p1_plan.n_bnd_cta + (long long)h->p1_plan.tiles_x * h->p1_plan.tiles_y * h->p1_plan.tiles_z;
+  }
+  if (ctas > max_ctas) return fail(LSB200_ERR_ARG, "the launch has %lld CTAs, the buffer holds %lld", ctas, (long long)max_ctas);
+  unsigned long long* buf = nullptr;
+  CK(cudaMalloc(&buf, sizeof(unsigned long long) * 3 * (size_t)ctas));
+  CK(cudaMemset(buf, 0, sizeof(unsigned long long) * 3 * (size_t)ctas));
+  CK(cudaMemcpyAsync(h->p, h->rhs, sizeof(double) * (size_t)h->g.nall, cudaMemcpyDeviceToDevice, h->stream));
+  for (int rep = 0; rep < 3 && rc == 0; ++rep) rc = launch_regularisation(h, h->p, h->q, 0);  // warm
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpyToSymbol(g_cta_trace, &buf, sizeof(buf)));
+  if (rc == 0) rc = launch_regularisation(h, h->p, h->q, 0);
+  const cudaError_t se = cudaStreamSynchronize(h->stream);
+  unsigned long long* none = nullptr;
+  cudaMemcpyToSymbol(g_cta_trace, &none, sizeof(none));
+  if (rc == 0 && se == cudaSuccess) cudaMemcpy(out, buf, sizeof(unsigned long long) * 3 * (size_t)ctas, cudaMemcpyDeviceToHost);
+  cudaFree(buf);
+  h->have_c = false;
+  if (se != cudaSuccess) return fail(LSB200_ERR_CUDA, "trace launch: %s", cudaGetErrorString(se));
+  *n_ctas = ctas;
+  return rc;
+}
+
 int lsb200_time_kernel(lsb200_handle h, int which, int reps, double* seconds_per_launch) {
   if (!h || !seconds_per_launch || reps < 1) return fail(LSB200_ERR_ARG, "bad argument");
   CK(cudaSetDevice(h->device));
@@ -2099,7 +2159,8 @@ int lsb200_time_kernel(lsb200_handle h, int which, int reps, double* seconds_per
   float total_ms = 0.f;
   for (int rep = -3; rep < reps; ++rep) {
     if (rep == 0) CK(cudaEventRecord(e0, h->stream));
-    CK(cudaMemcpyAsync(h->sc, h->sc_host, sizeof(CgScalars), cudaMemcpyHostToDevice, h->stream));
+    // the whole iteration advances the scalars: reset them every time; a single kernel does not
+    if (which == 1 || rep == -3) CK(cudaMemcpyAsync(h->sc, h->sc_host, sizeof(CgScalars), cudaMemcpyHostToDevice, h->stream));
     if (which == 0) rc = launch_regularisation(h, h->p, h->q, 1);
     else if (which == 1) rc = enqueue_iteration(h);
     else if (which == 2) rc = launch_rows(h, h->p, h->q, 1);

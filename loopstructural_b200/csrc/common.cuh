@@ -97,6 +97,13 @@ struct CgScalars {
 #define LSB_DYN_SMEM(name) extern __shared__ __align__(128) double name[]  // 128 B: destination of TMA tile loads
 #endif
 
+// a kernel parameter the device code reads in place (constant bank): TMA descriptors, coefficient tables
+#ifdef LSB_EMU
+#define LSB_GRID_CONSTANT
+#else
+#define LSB_GRID_CONSTANT __grid_constant__
+#endif
+
 #ifndef LSB_EMU
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -133,6 +140,32 @@ inline double block_sum(double v, double* /*red*/) {
   __syncthreads();
   return s;
 }
+#endif
+
+// Diagnostics (lsb200_debug_cta_trace): when set, thread 0 of every CTA of an instrumented kernel records
+// {start ns, end ns, SM id} at [3 * block index].  Null in normal operation: one uniform load per CTA.
+#ifndef LSB_EMU
+__device__ unsigned long long* g_cta_trace = nullptr;
+__device__ __forceinline__ unsigned long long trace_begin() {
+  unsigned long long t = 0;
+  if (g_cta_trace) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_end(const unsigned long long t0, const unsigned int bid) {
+  unsigned long long* tr = g_cta_trace;
+  if (tr) {
+    unsigned long long t1;
+    unsigned int sm;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+    tr[3 * (size_t)bid] = t0;
+    tr[3 * (size_t)bid + 1] = t1;
+    tr[3 * (size_t)bid + 2] = sm;
+  }
+}
+#else
+inline unsigned long long trace_begin() { return 0; }
+inline void trace_end(unsigned long long, unsigned int) {}
 #endif
 
 // "last block done" reduction of per-block partials in a fixed order.  Returns true in

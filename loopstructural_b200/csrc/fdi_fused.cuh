@@ -411,11 +411,6 @@ __device__ __forceinline__ double z_face_block(const GridDesc& g, const UniConst
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-#ifdef LSB_EMU
-#define LSB_GRID_CONSTANT
-#else
-#define LSB_GRID_CONSTANT __grid_constant__
-#endif
 // TMA = true: the box tiles are staged by the TMA unit (needs VEC16: an even row pitch, and `tmap` describing p);
 // the strips keep cp.async (48-byte rows).
 template <int TYT, int ST, int MINB, bool VEC16, bool TMA = false>
@@ -439,6 +434,7 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
   const int tid = tx + 32 * ty;
   const int bid = blockIdx.x;
   double dot = 0.0;
+  const unsigned long long t_begin = tid == 0 ? trace_begin() : 0ull;
 
   if (bid >= pl.n_box) {
     // ---- strip roles (the last block indices: they fill the CTA slots the box tiles leave free)
@@ -650,6 +646,7 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
   }
 
   const double bsum = block_sum<C::NT>(dot, red);
+  if (tid == 0) trace_end(t_begin, blockIdx.x);
   double total;
   if (grid_sum_last_block<C::NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total)) sc->pq_part[0] = total;
 }

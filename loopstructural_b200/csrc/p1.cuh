@@ -15,7 +15,12 @@
 #pragma once
 #include <vector>
 
+#include <string.h>
+
+#include <algorithm>
+
 #include "common.cuh"
+#include "fdi_stencil.cuh"
 #include "rows.cuh"
 
 namespace lsb {
@@ -72,12 +77,33 @@ __device__ __forceinline__ int p1_row(const GridDesc& g, const P1Tables& tb, int
 // a node whose class is one of the eight interior ones on every axis (p1_rep: 2 + parity): 2 <= i <= nc - 2, on a
 // mesh with more cells than the small mesh of the table (nc > m)
 __device__ __forceinline__ bool p1_interior_axis(int i, int nc, int m) { return nc != m && i >= 2 && i <= nc - 2; }
-__device__ __forceinline__ bool p1_interior(const GridDesc& g, const P1Tables& tb, int i, int j, int k) {
-  return p1_interior_axis(i, g.nx - 1, tb.m[0]) && p1_interior_axis(j, g.ny - 1, tb.m[1]) && p1_interior_axis(k, g.nz - 1, tb.m[2]);
+
+// The generic form of a node: (coefficient, offset) lists and p gathered from global memory.  One thread per node in
+// k_p1_normal (meshes too small to have an interior: an axis of <= 6 cells) and in the boundary role of k_p1_tiles.
+__device__ __forceinline__ double p1_node_generic(const GridDesc& g, const P1Tables& tb, const double w2, const double ridge2,
+                                                  const double* __restrict__ p, double* __restrict__ q, const int i, const int j,
+                                                  const int kl) {
+  const int row = p1_row(g, tb, i, j, g.k0 + kl);  // the class of a node depends on its GLOBAL plane
+  const double* __restrict__ C = tb.coef + (long long)row * P1_TAPS;
+  const int* __restrict__ O = tb.off + (long long)row * P1_TAPS;
+  const double* pb = p + ((long long)(kl + HALO) * g.plane + (long long)j * g.pitch + i);
+  // a non-zero coefficient implies that the neighbour exists (same cell pattern as the representative);
+  // padding entries have coefficient 0 and offset 0
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+  for (int e = 0; e < P1_TAPS; e += 4) {
+    a0 = fma(__ldg(C + e), pb[__ldg(O + e)], a0);
+    a1 = fma(__ldg(C + e + 1), pb[__ldg(O + e + 1)], a1);
+    a2 = fma(__ldg(C + e + 2), pb[__ldg(O + e + 2)], a2);
+    a3 = fma(__ldg(C + e + 3), pb[__ldg(O + e + 3)], a3);
+  }
+  const double p0 = pb[0];
+  const double v = fma(w2, (a0 + a1) + (a2 + a3), ridge2 * p0);
+  q[pb - p] = v;
+  return p0 * v;
 }
 
-// BOUNDARY_ONLY = true: the companion of k_p1_normal_interior -- only the nodes that kernel leaves out, p.q into pq_part[2]
-template <int NT, bool BOUNDARY_ONLY = false>
+template <int NT>
 __global__ void __launch_bounds__(NT)
     k_p1_normal(const GridDesc g, const P1Tables tb, const double w2, const double ridge2, const double* __restrict__ p,
                 double* __restrict__ q, double* __restrict__ partials, unsigned int* __restrict__ counter,
@@ -89,122 +115,212 @@ __global__ void __launch_bounds__(NT)
   for (long long t = blockIdx.x * (long long)NT + threadIdx.x; t < n; t += (long long)gridDim.x * NT) {
     const int i = (int)(t % g.nx);
     const long long r = t / g.nx;
-    const int j = (int)(r % g.ny), kl = (int)(r / g.ny);
-    if (BOUNDARY_ONLY && p1_interior(g, tb, i, j, g.k0 + kl)) continue;
-    const int row = p1_row(g, tb, i, j, g.k0 + kl);  // the class of a node depends on its GLOBAL plane
-    const double* __restrict__ C = tb.coef + (long long)row * P1_TAPS;
-    const int* __restrict__ O = tb.off + (long long)row * P1_TAPS;
-    const double* pb = p + ((long long)(kl + HALO) * g.plane + (long long)j * g.pitch + i);
-    // a non-zero coefficient implies that the neighbour exists (same cell pattern as the representative);
-    // padding entries have coefficient 0 and offset 0
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-    for (int e = 0; e < P1_TAPS; e += 4) {
-      a0 = fma(__ldg(C + e), pb[__ldg(O + e)], a0);
-      a1 = fma(__ldg(C + e + 1), pb[__ldg(O + e + 1)], a1);
-      a2 = fma(__ldg(C + e + 2), pb[__ldg(O + e + 2)], a2);
-      a3 = fma(__ldg(C + e + 3), pb[__ldg(O + e + 3)], a3);
-    }
-    const double p0 = pb[0];
-    const double v = fma(w2, (a0 + a1) + (a2 + a3), ridge2 * p0);
-    q[pb - p] = v;
-    dot = fma(p0, v, dot);
+    dot += p1_node_generic(g, tb, w2, ridge2, p, q, i, (int)(r % g.ny), (int)(r / g.ny));
   }
   const double bsum = block_sum<NT>(dot, red);
   double total;
-  if (grid_sum_last_block<NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total)) sc->pq_part[BOUNDARY_ONLY ? 2 : 0] = total;
+  if (grid_sum_last_block<NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total)) sc->pq_part[0] = total;
 }
 
-// The interior nodes of the same operator (LSB200_P1_FAST=1, beside k_p1_normal<NT, true> for the rest).  In
-// k_p1_normal every node costs 36 x (coefficient + offset + p) = 108 loads, two thirds of them table reads that
-// depend only on the node's CLASS, and on the interior there are just eight classes (the parities of i, j, k).  Here a
-// thread keeps i fixed and walks j and k in steps of two, so its class is constant: the 36 (coefficient, offset) pairs
-// are loaded into registers once per parity pair and a node costs its 36 gathers of p.  Thread x <-> consecutive i
-// (coalesced rows); blockIdx.y / .z: chunks of j / of the owned planes.
-template <int NT>
-__global__ void __launch_bounds__(NT)
-    k_p1_normal_interior(const GridDesc g, const P1Tables tb, const double w2, const double ridge2, const int jchunk,
-                         const int kchunk, const double* __restrict__ p, double* __restrict__ q,
-                         double* __restrict__ partials, unsigned int* __restrict__ counter, CgScalars* __restrict__ sc,
-                         const int cg_mode) {
-  __shared__ double red[NT / 32];
-  if (cg_mode && sc->done) return;
-  const int ncx = g.nx - 1, ncy = g.ny - 1, ncz = g.nz - 1;
-  const int i = 2 + blockIdx.x * NT + threadIdx.x;
-  // interior ranges of j and of the owned planes (global k), cut into this block's chunks
-  const int j0 = 2 + blockIdx.y * jchunk, j1 = min(j0 + jchunk, ncy - 1);
-  const int kfirst = max(g.k0, 2), klast = min(g.k1, ncz - 1);  // [kfirst, klast)
-  const int k0 = kfirst + blockIdx.z * kchunk, k1 = min(k0 + kchunk, klast);
-  double dot = 0.0;
-  if (i <= ncx - 2) {
-    const int rx = 2 + ((i - 2) & 1);
-#pragma unroll 1
-    for (int par = 0; par < 4; ++par) {
-      const int pj = par & 1, pk = par >> 1;
-      // first j / k of the chunk with (j - 2) & 1 == pj, (k - 2) & 1 == pk
-      const int ja = j0 + (((j0 - 2) & 1) == pj ? 0 : 1), ka = k0 + (((k0 - 2) & 1) == pk ? 0 : 1);
-      if (ja >= j1 || ka >= k1) continue;
-      const int row = ((2 + pk) * (tb.m[1] + 1) + (2 + pj)) * (tb.m[0] + 1) + rx;
-      double C[P1_TAPS];
-      int O[P1_TAPS];
-#pragma unroll
-      for (int e = 0; e < P1_TAPS; ++e) {
-        C[e] = __ldg(tb.coef + (long long)row * P1_TAPS + e);
-        O[e] = __ldg(tb.off + (long long)row * P1_TAPS + e);
-      }
-      for (int k = ka; k < k1; k += 2) {
-        const double* pr = p + ((long long)(k - g.k0 + HALO) * g.plane + i);
-        for (int j = ja; j < j1; j += 2) {
-          const double* pb = pr + (long long)j * g.pitch;
-          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-          for (int e = 0; e < P1_TAPS; e += 4) {
-            a0 = fma(C[e], pb[O[e]], a0);
-            a1 = fma(C[e + 1], pb[O[e + 1]], a1);
-            a2 = fma(C[e + 2], pb[O[e + 2]], a2);
-            a3 = fma(C[e + 3], pb[O[e + 3]], a3);
-          }
-          const double p0 = pb[0];
-          const double v = fma(w2, (a0 + a1) + (a2 + a3), ridge2 * p0);
-          q[pb - p] = v;
-          dot = fma(p0, v, dot);
-        }
-      }
-    }
-  }
-  const double bsum = block_sum<NT>(dot, red);
-  const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
-  const unsigned int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-  double total;
-  if (grid_sum_last_block<NT>(bsum, partials, counter, nblocks, bid, red, &total)) sc->pq_part[0] = total;
-}
-
-// launch shape of k_p1_normal_interior for a handle (host); returns false when there is no interior to speak of (a
-// small-mesh axis, or no owned interior plane): k_p1_normal then does everything
-struct P1InteriorPlan {
-  int gx, gy, gz, jchunk, kchunk;
+// ---- k_p1_tiles: the same operator from shared-memory tiles, one launch -----------------------------------------------
+// k_p1_normal spends 108 loads per node (36 coefficients, 36 offsets, 36 values of p), two thirds of them table reads
+// that depend only on the node's CLASS; it is gather-latency bound (66 us for 1.64 M nodes, 0.06 of the HBM roofline,
+// profiles/r01p).  On the interior (2 <= i <= n-3 on every axis) there are eight classes, the parities of (i, j, k):
+//   * a CTA stages a tile of p (64 x TY x TZ nodes + 2 halo nodes per side) in shared memory, DE-INTERLEAVED along x
+//     (even columns first, then odd), so that 32 nodes of equal x parity are 32 consecutive doubles;
+//   * a warp computes a row of 32 same-class nodes at a time.  The class is a compile-time constant of the unrolled
+//     code, so coefficients and shared-memory offsets are constant-bank operands (P1ClassTaps, a kernel parameter):
+//     a tap is one LDS + one DFMA, no table load and no per-thread register array;
+//   * nodes whose parity sum is even belong to corner tets only: 15 taps against 33 (checked on the host when the plan
+//     is made, p1_plan_tiles), their loops are 16 long.
+// The boundary nodes (a shell two nodes thick, 10 % of config 3) are enumerated compactly and computed in the generic form
+// by the first CTAs of the same launch (dispatched first: they are latency bound and overlap the tile CTAs).
+constexpr int P1_TAPS_EVEN = 16;
+struct P1ClassTaps {
+  double coef[8][P1_TAPS];  // class = pi + 2 pj + 4 pk; zero padded
+  int soff[8][P1_TAPS];     // BYTE offset of the tap in the de-interleaved tile, from (row base + lane)
+  int centre[2];            // byte offset of the node itself, by pi
 };
-inline bool p1_plan_interior(const GridDesc& g, const int m[3], const int NT, const long long max_blocks, P1InteriorPlan* out) {
+struct P1TilePlan {
+  int tiles_x, tiles_y, tiles_z;
+  int z_base;          // global plane of the tile lattice's first layer (even)
+  int kfirst, klast;   // owned interior planes [kfirst, klast)
+  int n_bnd_cta;       // CTAs [0, n_bnd_cta) take the boundary role
+  long long nbz, nby, nbx;  // boundary nodes: whole planes / the 4 boundary rows of interior planes / the 4 boundary columns
+};
+// X(ID, TY, TZ, warps per CTA): tiles of 64 x TY x TZ nodes
+#define LSB_P1_TILE_CFGS(X) \
+  X(0, 8, 8, 8)             \
+  X(1, 8, 4, 8)             \
+  X(2, 4, 4, 4)
+template <int TY, int TZ>
+struct P1TileGeom {
+  static constexpr int TX = 64, HX = TX / 2 + HALO, SY = TY + 2 * HALO, SZ = TZ + 2 * HALO;
+  static constexpr int ELEMS = 2 * HX * SY * SZ;
+};
+
+// host: tile plan and class tables of a handle for tiles of 64 x ty x tz nodes, or false when the mesh has no interior
+// (an axis that is its own small mesh) or a class needs more taps than its loop holds -- k_p1_normal does everything then
+inline bool p1_plan_tiles(const GridDesc& g, const int m[3], const double* table, const int ty, const int tz, const int nt,
+                          const long long max_blocks, P1TilePlan* out, P1ClassTaps* T) {
   const int nc[3] = {g.nx - 1, g.ny - 1, g.nz - 1};
   for (int a = 0; a < 3; ++a)
-    if (nc[a] == m[a] || nc[a] < 4) return false;
-  const int ni = nc[0] - 3, nj = nc[1] - 3;
-  const int kfirst = g.k0 > 2 ? g.k0 : 2, klast = g.k1 < nc[2] - 1 ? g.k1 : nc[2] - 1;
-  const int nk = klast - kfirst;
-  if (ni < 1 || nj < 1 || nk < 1) return false;
-  P1InteriorPlan pl;
-  pl.jchunk = 8;
-  pl.kchunk = 4;
-  pl.gx = (ni + NT - 1) / NT;
-  for (;;) {
-    pl.gy = (nj + pl.jchunk - 1) / pl.jchunk;
-    pl.gz = (nk + pl.kchunk - 1) / pl.kchunk;
-    if ((long long)pl.gx * pl.gy * pl.gz <= max_blocks) break;
-    pl.jchunk *= 2;
-    pl.kchunk *= 2;
+    if (nc[a] == m[a] || nc[a] < 6) return false;
+  P1TilePlan pl;
+  pl.kfirst = std::min(std::max(g.k0, 2), g.k1);
+  pl.klast = std::max(pl.kfirst, std::min(g.k1, g.nz - 2));
+  pl.z_base = pl.kfirst & ~1;
+  pl.tiles_x = (g.nx - 4 + 63) / 64;
+  pl.tiles_y = (g.ny - 4 + ty - 1) / ty;
+  pl.tiles_z = pl.klast > pl.kfirst ? (pl.klast - pl.z_base + tz - 1) / tz : 0;
+  const long long nzi = pl.klast - pl.kfirst;
+  pl.nbz = (long long)(g.nzl - nzi) * g.nx * g.ny;
+  pl.nby = nzi * 4 * g.nx;
+  pl.nbx = nzi * 4 * (g.ny - 4);
+  const long long nb = pl.nbz + pl.nby + pl.nbx;
+  pl.n_bnd_cta = (int)((nb + 2 * nt - 1) / (2 * nt));  // two nodes per thread
+  if ((long long)pl.tiles_x * pl.tiles_y * pl.tiles_z + pl.n_bnd_cta > max_blocks) return false;
+  const int HX = 32 + HALO, SY = ty + 2 * HALO;
+  memset(T, 0, sizeof(*T));
+  for (int cls = 0; cls < 8; ++cls) {
+    const int pi = cls & 1, pj = (cls >> 1) & 1, pk = cls >> 2;
+    const size_t row = ((size_t)(2 + pk) * (m[1] + 1) + (2 + pj)) * (m[0] + 1) + 2 + pi;
+    const int budget = ((pi + pj + pk) & 1) ? P1_TAPS : P1_TAPS_EVEN;
+    int cnt = 0;
+    for (int t = 0; t < 125; ++t) {
+      const double c = table[row * 125 + t];
+      if (!(c == c)) return false;
+      if (c == 0.0) continue;
+      if (cnt == budget) return false;
+      const int dz = t / 25 - 2, dy = (t / 5) % 5 - 2, dx = t % 5 - 2;
+      T->coef[cls][cnt] = c;
+      T->soff[cls][cnt] = 8 * ((((dz + 2) * SY + (dy + 2)) * 2 + ((pi + dx) & 1)) * HX + ((pi + 2 + dx) >> 1));
+      ++cnt;
+    }
   }
+  for (int pi = 0; pi < 2; ++pi) T->centre[pi] = 8 * (((2 * SY + 2) * 2 + pi) * HX + 1);
   *out = pl;
   return true;
+}
+
+// boundary node t of the plan's enumeration -> (i, j, local plane)
+__device__ __forceinline__ void p1_boundary_node(const GridDesc& g, const P1TilePlan& pl, long long t, int* i, int* j, int* kl) {
+  if (t < pl.nbz) {
+    const long long per = (long long)g.nx * g.ny;
+    const int lp = (int)(t / per);
+    const int r = (int)(t - lp * per);
+    const int nlo = pl.kfirst - g.k0;  // boundary planes below the interior ones
+    *kl = lp < nlo ? lp : (pl.klast - g.k0) + (lp - nlo);
+    *j = r / g.nx;
+    *i = r - *j * g.nx;
+    return;
+  }
+  t -= pl.nbz;
+  if (t < pl.nby) {
+    const int per = 4 * g.nx;
+    const int kz = (int)(t / per);
+    const int r = (int)(t - (long long)kz * per);
+    const int jr = r / g.nx;
+    *kl = pl.kfirst - g.k0 + kz;
+    *j = jr < 2 ? jr : g.ny - 4 + jr;
+    *i = r - jr * g.nx;
+    return;
+  }
+  t -= pl.nby;
+  const int per = 4 * (g.ny - 4);
+  const int kz = (int)(t / per);
+  const int r = (int)(t - (long long)kz * per);
+  const int ic = r & 3;
+  *kl = pl.kfirst - g.k0 + kz;
+  *j = 2 + (r >> 2);
+  *i = ic < 2 ? ic : g.nx - 4 + ic;
+}
+
+// one row of 32 same-class nodes: NTAP taps, every coefficient and offset a constant-bank operand
+__device__ __forceinline__ double p1_at(const double* __restrict__ Sb, const int byte_off) {
+  return *reinterpret_cast<const double*>(reinterpret_cast<const char*>(Sb) + byte_off);
+}
+template <int CLS, int NTAP>
+__device__ __forceinline__ double p1_row_taps(const P1ClassTaps& T, const double* __restrict__ Sb) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+  for (int e = 0; e < NTAP; e += 4) {
+    a0 = fma(T.coef[CLS][e], p1_at(Sb, T.soff[CLS][e]), a0);
+    a1 = fma(T.coef[CLS][e + 1], p1_at(Sb, T.soff[CLS][e + 1]), a1);
+    a2 = fma(T.coef[CLS][e + 2], p1_at(Sb, T.soff[CLS][e + 2]), a2);
+    a3 = fma(T.coef[CLS][e + 3], p1_at(Sb, T.soff[CLS][e + 3]), a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
+template <int TY, int TZ, int NW>
+__global__ void __launch_bounds__(32 * NW)
+    k_p1_tiles(const GridDesc g, const P1Tables tb, const LSB_GRID_CONSTANT P1ClassTaps T, const P1TilePlan pl, const double w2,
+               const double ridge2, const double* __restrict__ p, double* __restrict__ q, double* __restrict__ partials,
+               unsigned int* __restrict__ counter, CgScalars* __restrict__ sc, const int cg_mode) {
+  using G = P1TileGeom<TY, TZ>;
+  constexpr int NT = 32 * NW, HX = G::HX, SY = G::SY;
+  static_assert(TY % 2 == 0 && TZ % 2 == 0, "tiles start on even rows / planes: the class of a row is a compile-time constant");
+  LSB_DYN_SMEM(S);
+  __shared__ double red[NT / 32];
+  if (cg_mode && sc->done) return;
+  const int tid = threadIdx.x;
+  double dot = 0.0;
+  const unsigned long long t_begin = tid == 0 ? trace_begin() : 0ull;
+  if ((int)blockIdx.x < pl.n_bnd_cta) {
+    // ---- boundary role
+    const long long nb = pl.nbz + pl.nby + pl.nbx;
+    for (long long t = (long long)blockIdx.x * NT + tid; t < nb; t += (long long)pl.n_bnd_cta * NT) {
+      int i, j, kl;
+      p1_boundary_node(g, pl, t, &i, &j, &kl);
+      dot += p1_node_generic(g, tb, w2, ridge2, p, q, i, j, kl);
+    }
+  } else {
+    // ---- tile role
+    const int b = (int)blockIdx.x - pl.n_bnd_cta;
+    const int txy = pl.tiles_x * pl.tiles_y;
+    const int bz = b / txy, brem = b - bz * txy;
+    const int by = brem / pl.tiles_x, bx = brem - by * pl.tiles_x;
+    const int x0 = 2 + 64 * bx, y0 = 2 + TY * by, z0 = pl.z_base + TZ * bz;  // first output node of the tile
+    // stage the nodes (x0-2 .., y0-2 .., z0-2 ..): consecutive threads read consecutive x
+    for (int idx = tid; idx < G::ELEMS; idx += NT) {
+      const int sx = idx % (2 * HX), r = idx / (2 * HX);
+      const int sy = r % SY, sz = r / SY;
+      const int gi = x0 - HALO + sx, gj = y0 - HALO + sy, gk = z0 - HALO + sz;
+      const bool ok = gi < g.nx && gj < g.ny && gk >= 0 && gk < g.nz && gk >= g.k0 - HALO && gk < g.k1 + HALO;
+      const double* src = p + ((long long)(gk - g.k0 + HALO) * g.plane + (long long)gj * g.pitch + gi);
+      cp_async_8(S + ((sz * SY + sy) * 2 + (sx & 1)) * HX + (sx >> 1), ok ? src : p, ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int ROWS = (TY / 2) * (TZ / 2);  // rows of one class in a tile
+    for (int r = warp; r < ROWS; r += NW) {
+      const int ya = 2 * (r % (TY / 2)), za = 2 * (r / (TY / 2));
+#define LSB_P1_CLASS(CLS)                                                                                           \
+  {                                                                                                                 \
+    constexpr int pi = (CLS) & 1, pj = ((CLS) >> 1) & 1, pk = (CLS) >> 2;                                           \
+    const int y = ya + pj, z = za + pk;                                                                             \
+    const int i = x0 + 2 * lane + pi, j = y0 + y, k = z0 + z;                                                       \
+    const double* Sb = S + (z * SY + y) * 2 * HX + lane;                                                            \
+    const double acc = p1_row_taps<CLS, ((pi + pj + pk) & 1) ? P1_TAPS : P1_TAPS_EVEN>(T, Sb);                      \
+    const double p0 = p1_at(Sb, T.centre[pi]);                                                                             \
+    const double v = fma(w2, acc, ridge2 * p0);                                                                     \
+    if (i <= g.nx - 3 && j <= g.ny - 3 && k >= pl.kfirst && k < pl.klast) {                                         \
+      q[(long long)(k - g.k0 + HALO) * g.plane + (long long)j * g.pitch + i] = v;                                   \
+      dot = fma(p0, v, dot);                                                                                        \
+    }                                                                                                               \
+  }
+      LSB_P1_CLASS(0) LSB_P1_CLASS(1) LSB_P1_CLASS(2) LSB_P1_CLASS(3)
+      LSB_P1_CLASS(4) LSB_P1_CLASS(5) LSB_P1_CLASS(6) LSB_P1_CLASS(7)
+#undef LSB_P1_CLASS
+    }
+  }
+  const double bsum = block_sum<NT>(dot, red);
+  if (tid == 0) trace_end(t_begin, blockIdx.x);
+  double total;
+  if (grid_sum_last_block<NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total)) sc->pq_part[0] = total;
 }
 
 // diag(R^T R) w^2 + ridge^2 (for the column scaling, LI/_discrete_interpolator.py:815-833)

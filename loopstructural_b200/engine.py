@@ -392,6 +392,13 @@ class Engine:
                                                 int(gradient), nat.dptr(out)))
         return out
 
+    def cta_trace(self, max_ctas: int = 1 << 18) -> np.ndarray:
+        """(n_ctas, 3) uint64: start ns, end ns, SM id of every CTA of one launch of the regularisation operator."""
+        out = np.zeros((max_ctas, 3), dtype=np.uint64)
+        n = C.c_int64(0)
+        nat.check(self._lib.lsb200_debug_cta_trace(self._h, max_ctas, out.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(n)))
+        return out[: n.value]
+
     def time_kernel(self, which: int, reps: int = 20) -> float:
         out = C.c_double(0.0)
         nat.check(self._lib.lsb200_time_kernel(self._h, int(which), int(reps), C.byref(out)))

@@ -1,7 +1,7 @@
 """P1 / TetMesh face-jump operator at BASELINE configs[2] size (117^3 cells = 8,008,065 tets), timed in a process of its
-own (LSB200_P1_FAST is read once per process).  Prints one JSON line like scripts/matvec_experiment.py.
+own (LSB200_P1_TILES / LSB200_P1_TILE_CFG are read once per process).  Prints one JSON line like scripts/matvec_experiment.py.
 
-    LSB200_P1_FAST=1 python scripts/p1_experiment.py 117
+    LSB200_P1_TILE_CFG=1 python scripts/p1_experiment.py 117
 """
 import json
 import os

@@ -57,10 +57,10 @@ GridDesc make_grid(const int* dims, const double* origin, const double* step) {
 extern "C" {
 
 // q = (w2 R^T R + ridge2 I) p on the owned planes and diag of the same; dims = {nx, ny, nz, k0, k1}
-// fast != 0: the LSB200_P1_FAST plan of launch_regularisation (k_p1_normal_interior + k_p1_normal<.., true>); returns 1
-// then if the interior kernel was used, 0 if the plan fell back to the generic kernel
+// tiles != 0: the k_p1_tiles plan of launch_regularisation with tile configuration tiles - 1 (LSB_P1_TILE_CFGS); returns 1
+// then if the tile kernel was used, 0 if the plan fell back to the generic kernel (no interior)
 HOSTSIM_API int emu_p1_normal(const int* dims, const double* step, const long long* m, const double* table, double w2,
-                              double ridge2, int fast, const double* p_global, double* q_owned, double* diag_owned, double* pq_out) {
+                              double ridge2, int tiles, const double* p_global, double* q_owned, double* diag_owned, double* pq_out) {
   const double origin[3] = {0.0, 0.0, 0.0};
   const GridDesc g = make_grid(dims, origin, step);
   std::vector<double> coef, dg;
@@ -82,31 +82,37 @@ HOSTSIM_API int emu_p1_normal(const int* dims, const double* step, const long lo
   constexpr int NT = 256;
   const long long n = (long long)g.nx * g.ny * g.nzl;
   const int nb = (int)std::max<long long>(1, std::min<long long>((n + NT - 1) / NT, 5));
-  std::vector<double> partials2((size_t)MAX_PARTIALS, 0.0);
-  unsigned int counter2 = 0;
-  int used_fast = 0;
-  P1InteriorPlan pl;
+  int used_tiles = 0;
+  P1TilePlan pl;
+  P1ClassTaps cls;
   const int mi[3] = {(int)m[0], (int)m[1], (int)m[2]};
-  if (fast && p1_plan_interior(g, mi, 128, MAX_PARTIALS, &pl)) {
-    used_fast = 1;
-    lsb_emu::launch(dim3(pl.gx, pl.gy, pl.gz), dim3(128), 0, [&] {
-      k_p1_normal_interior<128>(g, tb, w2, ridge2, pl.jchunk, pl.kchunk, p, q, partials.data(), &counter, &sc, 0);
-    });
-    lsb_emu::launch(dim3(nb), dim3(NT), 0, [&] { k_p1_normal<NT, true>(g, tb, w2, ridge2, p, q, partials2.data(), &counter2, &sc, 0); });
-  } else {
-    lsb_emu::launch(dim3(nb), dim3(NT), 0, [&] { k_p1_normal<NT, false>(g, tb, w2, ridge2, p, q, partials.data(), &counter, &sc, 0); });
+  switch (tiles - 1) {
+#define X(ID, TY, TZ, NW)                                                                                                \
+  case ID:                                                                                                               \
+    if (p1_plan_tiles(g, mi, table, TY, TZ, 32 * NW, MAX_PARTIALS, &pl, &cls)) {                                         \
+      used_tiles = 1;                                                                                                    \
+      lsb_emu::launch(dim3(pl.n_bnd_cta + pl.tiles_x * pl.tiles_y * pl.tiles_z), dim3(32 * NW),                          \
+                      sizeof(double) * P1TileGeom<TY, TZ>::ELEMS, [&] {                                                   \
+                        k_p1_tiles<TY, TZ, NW>(g, tb, cls, pl, w2, ridge2, p, q, partials.data(), &counter, &sc, 0);     \
+                      });                                                                                                \
+    }                                                                                                                    \
+    break;
+    LSB_P1_TILE_CFGS(X)
+#undef X
   }
+  if (!used_tiles)
+    lsb_emu::launch(dim3(nb), dim3(NT), 0, [&] { k_p1_normal<NT>(g, tb, w2, ridge2, p, q, partials.data(), &counter, &sc, 0); });
   lsb_emu::launch(dim3(nb), dim3(NT), 0, [&] { k_p1_diag(g, tb, w2, ridge2, d); });
   for (int k = 0; k < g.nzl; ++k) {
     memcpy(q_owned + (size_t)k * g.plane, q + (size_t)(k + HALO) * g.plane, sizeof(double) * g.plane);
     memcpy(diag_owned + (size_t)k * g.plane, d + (size_t)(k + HALO) * g.plane, sizeof(double) * g.plane);
   }
-  *pq_out = sc.pq_part[0] + sc.pq_part[2];
+  *pq_out = sc.pq_part[0];
   for (size_t i = 0; i < qst.size(); ++i) {
     const bool owned = i >= guard + (size_t)HALO * g.plane && i < guard + (size_t)(HALO + g.nzl) * g.plane;
     if (!owned && (qst[i] == qst[i] || dst[i] != 0.0)) return -2;
   }
-  return used_fast;
+  return used_tiles;
 }
 
 // k_p1_point_rows on a slab: rows as (n_out, 4) values, GLOBAL node ids (-1 = empty row), b, w^2; returns rows kept

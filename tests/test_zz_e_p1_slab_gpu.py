@@ -55,17 +55,17 @@ def test_face_jump_operator_and_rows_on_slab_handles(cells, step, world):
         e.close()
 
 
-def test_p1_device_tests_under_the_fast_plan():
-    """LSB200_P1_FAST=1 (k_p1_normal_interior + boundary-only k_p1_normal; read once per process): the P1 device tests
-    again in a process of their own."""
+def test_p1_device_tests_under_the_generic_plan():
+    """LSB200_P1_TILES=0 (k_p1_normal for every node, the kernel the tiled plan falls back to on meshes without an
+    interior; read once per process): the P1 device tests again in a process of their own."""
     import os
     import subprocess
     import sys
 
-    if os.environ.get("LSB200_P1_FAST") == "1":
-        pytest.skip("already inside the fast-plan run")
+    if os.environ.get("LSB200_P1_TILES") == "0":
+        pytest.skip("already inside the generic-plan run")
     here = os.path.dirname(os.path.abspath(__file__))
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_p1_gpu.py"), os.path.join(here, "test_zz_e_p1_slab_gpu.py"),
                           "-q", "-m", "gpu", "-x"], capture_output=True, text=True, timeout=1500,
-                         env=dict(os.environ, LSB200_P1_FAST="1"), cwd=os.path.dirname(here))
+                         env=dict(os.environ, LSB200_P1_TILES="0"), cwd=os.path.dirname(here))
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
