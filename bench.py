@@ -28,10 +28,20 @@ sys.path.insert(0, ROOT)
 METRIC = "fdi_cg_node_updates_per_second"
 UNIT = "dof-iter/s"
 BYTES_MATVEC_PER_DOF = 16.0      # read p, write q
-# dram__bytes_read.sum + dram__bytes_write.sum of one 256^3 matvec from ncu --set full (profiles/r02c_matvec_full_details.csv:
-# 138.3 + 75.3 MB for the uniform k_fdi_box, 10.5 + 0.0 MB for its z-general launch, 21.4 + 0.1 MB for k_fdi_shell; the
-# writes that are still in L2 when a kernel ends are not counted by ncu)
-TRAFFIC_MATVEC_256 = (138.34 + 75.32 + 10.49 + 0.0 + 21.43 + 0.06) * 1e6
+
+
+def measured_traffic(kernel, nsteps):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of `kernel` on a grid of `nsteps` nodes, from the committed
+    ncu --set full capture (profiles/kernel_traffic.json, written from the ncu report of the same kernel and grid; a number
+    taken under the profiler, so it is never measured inside a timed run).  None when no capture of this grid exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as fh:
+            rec = json.load(fh).get(f"{kernel}@{'x'.join(str(int(v)) for v in nsteps)}")
+        return None if rec is None else float(rec["dram_bytes_read"]) + float(rec["dram_bytes_write"])
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 BYTES_ITERATION_PER_DOF = 104.0  # matvec 16 + x/r update 48 (+8 scaling vector) + p update 24 (+8 scaling vector)
 
 
@@ -330,6 +340,7 @@ def measure_eval(eng, local, npts=20_000_000, npts_host=10_000_000):
     dt = time.perf_counter() - t0
     res["value_points_per_second_host_arrays"] = npts_host / dt
     res["host_arrays"] = {"points": npts_host, "seconds": dt, "gbs_over_pcie": 32.0 * npts_host / dt / 1e9}
+    eng.evaluate_gradient(host)  # sizes the (three times larger) output staging
     t0 = time.perf_counter()
     eng.evaluate_gradient(host)
     res["gradient_points_per_second_host_arrays"] = npts_host / (time.perf_counter() - t0)
@@ -417,19 +428,19 @@ def measure_fault(local, n_nodes=128, npts=10_000_000, steps=10, cpu_points=100_
 
 
 def measure_launch_plans(local, sizes=(256, 512), timeout=150):
-    """The matvec under the launch-plan switches that are built but have not been measured yet,
-    each in a process of its own (scripts/matvec_experiment.py): fused ring (LSB200_RING=1 / 2) and shell-first launch
-    order, beside the default plan.  Reports times and whether q = N p agrees with the default plan's."""
+    """The matvec at 256^3 and 512^3 under the switches of the single-launch plan, each in a process of its own
+    (scripts/matvec_experiment.py): cp.async instead of TMA staging, the 96-thread tile shape, the small-grid kernel
+    everywhere -- beside the default plan.  Reports times and whether q = N p agrees with the default plan's."""
     import subprocess
 
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "matvec_experiment.py")
-    plans = {"default": {}, "shell_first": {"LSB200_SHELL_FIRST": "1"}, "ring": {"LSB200_RING": "1"},
-             "ring_staggered": {"LSB200_RING": "2"}}
+    plans = {"default": {}, "cp_async": {"LSB200_TMA": "0"}, "tiles_64x12": {"LSB200_FUSED_CFG": "3"},
+             "k_fdi_normal": {"LSB200_STENCIL_MAIN": "-1"}}
     out = {}
     for n in sizes:
         ref = None
         for name, env in plans.items():
-            if n > 256 and name == "shell_first":
+            if n > 256 and name == "k_fdi_normal":
                 continue
             key = f"{name}_{n}"
             try:
@@ -771,16 +782,16 @@ def run_ours(args):
                        "dof": dof_global},
             "solve_seconds": dev_s / max(args.steps, 1), "cg_iterations": iters_per_solve,
             "cg_iterations_per_second": its / dev_s if dev_s > 0 else None,
-            "roofline": {"bound": "hbm", "kernel": "FDI regularisation normal matvec = k_fdi_box (uniform) + k_fdi_box (z faces) + k_fdi_shell "
-                                                   "(x/y ring): one logical launch on three streams",
+            "roofline": {"bound": "hbm", "kernel": "FDI regularisation normal matvec = k_fdi_fused: interior box tiles (TMA-staged plane ring), "
+                                                   "z-face planes and x/y strips in one launch",
                          "achieved": ach,
-                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": TRAFFIC_MATVEC_256 if n == 256 and world == 1 else None,
+                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": measured_traffic("k_fdi_fused", (n, n, nz // world)) if world == 1 else None,
                          "seconds_per_launch": t_matvec, "bytes_per_dof": BYTES_MATVEC_PER_DOF},
             "roofline_iteration": {"bound": "hbm", "achieved": ach_it, "peak": peak, "unit": "GB/s",
                                    "frac": ach_it / peak, "seconds_per_iteration": t_iter,
                                    "bytes_per_dof": BYTES_ITERATION_PER_DOF},
             "kernels": {  # every kernel of the iteration, CUDA events around 20 back-to-back launches each
-                "matvec k_fdi_box(+zgen)+k_fdi_shell": {"us": 1e6 * t_matvec, "bytes_per_dof": 16, "gbs": 16 * dof_local / t_matvec / 1e9},
+                "matvec k_fdi_fused": {"us": 1e6 * t_matvec, "bytes_per_dof": 16, "gbs": 16 * dof_local / t_matvec / 1e9},
                 "k_cg_update_xr": {"us": 1e6 * t_xr, "bytes_per_dof": 56, "gbs": 56 * dof_local / t_xr / 1e9},
                 "k_cg_update_p": {"us": 1e6 * t_p, "bytes_per_dof": 32, "gbs": 32 * dof_local / t_p / 1e9},
                 "k_rows_normal": {"us": 1e6 * t_rows, "rows": rows_local}},

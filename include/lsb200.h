@@ -335,11 +335,6 @@ int lsb200_eval_lattice(lsb200_handle h, const double* transform, const double s
 int lsb200_eval_lattice_dev(lsb200_handle h, const double* transform, const double start[3], const double stop[3],
                             const int64_t n[3], int order_f, int gradient, double* out_dev, void* stream);
 
-/* Introspection (no device needed): the output planes of the three launches of the tiled FDI operator for a
- * handle owning the planes [k0,k1) of nz: out = {A0,A1, B0,B1, U0,U1}, A/B = z-general ranges next to the z faces,
- * U = uniform range; see plan_z_ranges in csrc/api.cu. */
-int lsb200_plan_z_ranges(int nz, int k0, int k1, int cz, int zface, int out[6]);
-
 /* Page-locked host memory for result buffers (c of a large grid is 134 MB - 1 GB: a pageable destination halves
  * the device->host rate and pays its page faults inside every solve). */
 int lsb200_host_alloc(int64_t bytes, void** out);

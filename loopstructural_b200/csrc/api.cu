@@ -134,27 +134,22 @@ struct lsb200_ctx {
   PeerTable peer_host{};               // peers' mailboxes as mapped here
   PeerTable* peers = nullptr;          // device copy of peer_host
   unsigned long long solve_epoch = 0;
-  int stencil_cfg = 0;
-  int cz = 0;
+  int cz = 0;              // k_fdi_normal (grids too small for box tiles): z chunk and grid
   dim3 sgrid;
-  // main (register-tiled) kernel + y-shell launch of k_fdi_normal; main_cfg < 0: k_fdi_normal everywhere
-  int main_cfg = -1;
-  bool fused = false;      // the single-launch plan (k_fdi_fused): default whenever the grid is large enough
+  bool fused = false;      // the single-launch plan (k_fdi_fused): whenever the grid is large enough
   FusedChoice fz{};
   // TMA descriptors of the two node vectors the operator is applied to (p inside CG, x for the initial residual and
   // lsb200_residual_norm), one per box configuration (their boxes differ); tma_ok: built for this handle
   bool tma_ok = false;
+  bool want_tma = true;    // LSB200_TMA=0 (read when the handle is planned): cp.async staging everywhere
   const double* tma_vec[2] = {nullptr, nullptr};
   TmapArg tma_map[2];
-  int main_cz = 0, shell_cz = 0;  // shell_cz = 0: chosen per launch
-  int box_z0 = 0, box_z1 = 0;
   long long guard = 0;     // elements of the guard plane in front of every node vector (ensure_vectors)
-  double* ztab = nullptr;  // per-plane z coefficients of k_fdi_shell (nz * SHELL_ZSTRIDE)
-  dim3 main_grid;
-  // the shell launches run on side streams, overlapped with the box kernel (fork/join by events)
+  double* ztab = nullptr;  // per-plane z coefficients of the planes next to a z face (nz * SHELL_ZSTRIDE)
+  // side[1]: the halo exchange of a slab handle runs beside the interior part of the p update (fork/join by events)
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
-  bool overlap_shells = true;
+  bool overlap_shells = true;  // LSB200_OVERLAP=0: the exchange on the main stream
   int sm_count = 148;
   long long launches = 0;
   double setup_seconds = 0.0;
@@ -226,33 +221,24 @@ static void plan_stencil(lsb200_ctx* h, int ctas_per_sm) {
 }
 
 static void plan_main(lsb200_ctx* h) {
-  const char* env = getenv("LSB200_STENCIL_MAIN");
-  int cfg = env ? atoi(env) : 4;
-  h->main_cfg = -1;
+  // the single-launch plan of a grid large enough to have interior box tiles; LSB200_STENCIL_MAIN=-1 keeps k_fdi_normal
+  // everywhere (comparison measurements)
+  h->fused = false;
   const GridDesc& g = h->g;
-  if (cfg < 0 || h->kind != LSB200_SUPPORT_GRID) return;
-  const char* czenv = getenv("LSB200_STENCIL_CZ");
-  const int czo = (czenv && atoi(czenv) > 0) ? atoi(czenv) : 0;
-  BoxTiles bt;
-  if (!plan_box_tiles(g, cfg, czo, h->sm_count, MAX_PARTIALS, &bt)) return;  // no box: k_fdi_normal everywhere
-  cfg = bt.cfg;
-  h->box_z0 = g.k0;
-  h->box_z1 = g.k1;
-  h->main_cz = bt.cz;
-  h->main_grid = dim3(bt.tiles_x, bt.tiles_y, bt.chunks);
-  { const char* e = getenv("LSB200_SHELL_CZ"); h->shell_cz = (e && atoi(e) > 0) ? atoi(e) : 0; }
+  if (h->kind != LSB200_SUPPORT_GRID) return;
+  if (getenv("LSB200_STENCIL_MAIN") && atoi(getenv("LSB200_STENCIL_MAIN")) < 0) return;
+  auto env_int = [](const char* name) { const char* e = getenv(name); return (e && atoi(e) > 0) ? atoi(e) : 0; };
+  if (!plan_fused(g, h->sm_count, MAX_PARTIALS, env_int("LSB200_FUSED_CFG"), env_int("LSB200_FUSED_CZ"), env_int("LSB200_FUSED_SCZ"),
+                  &h->fz))
+    return;  // no box: k_fdi_normal everywhere
   if (!h->ztab) {
     std::vector<double> zt((size_t)g.nz * SHELL_ZSTRIDE);
     shell_fill_z_table(g.nz, zt.data());
     if (cudaMalloc(&h->ztab, sizeof(double) * zt.size()) != cudaSuccess) return;
     if (cudaMemcpy(h->ztab, zt.data(), sizeof(double) * zt.size(), cudaMemcpyHostToDevice) != cudaSuccess) return;
   }
-  h->main_cfg = cfg;
-  // the single-launch plan; LSB200_FUSED=0 keeps the three-launch plan of round 1 (for comparison measurements)
-  static const bool want_fused = !(getenv("LSB200_FUSED") && atoi(getenv("LSB200_FUSED")) == 0);
-  auto env_int = [](const char* name) { const char* e = getenv(name); return (e && atoi(e) > 0) ? atoi(e) : 0; };
-  h->fused = want_fused && plan_fused(g, h->sm_count, MAX_PARTIALS, env_int("LSB200_FUSED_CFG"), env_int("LSB200_FUSED_CZ"),
-                                      env_int("LSB200_FUSED_SCZ"), &h->fz);
+  h->want_tma = !(getenv("LSB200_TMA") && atoi(getenv("LSB200_TMA")) == 0);
+  h->fused = true;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
@@ -310,14 +296,14 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
     h->launches++;                                                                                               \
   }
 #define LSB_LAUNCH(XB, TXT, TYT, MINB, ST) LSB_LAUNCH_AT(h->stream, h->sgrid, h->cz, 0, XB, TXT, TYT, MINB, ST)
-  if (h->main_cfg >= 0 && h->fused) {
+  if (h->fused) {
     // one launch: interior box tiles (with their z-face planes), x strips and y strips, sized by plan_fused
     const UniConsts U = make_uni_consts(w);
     const FusedPlan& pl = h->fz.pl;
     const unsigned int ctas = (unsigned int)(pl.n_box + pl.n_xs + pl.n_ys);
     // TMA staging when the vector has a descriptor (built lazily for p and x; needs an even row pitch); LSB200_TMA=0
     // keeps cp.async everywhere
-    static const bool want_tma = !(getenv("LSB200_TMA") && atoi(getenv("LSB200_TMA")) == 0);
+    const bool want_tma = h->want_tma;
     int tmi = -1;
     if (want_tma && vec16) {
       for (int t = 0; t < 2; ++t)
@@ -363,125 +349,14 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
     h->launches++;
     return 0;
   }
-  if (h->main_cfg >= 0) {
-    const bool ov = h->overlap_shells;
-    // fork: the shell launches read p and write rows / columns / planes the box kernel never touches
-    if (ov) {
-      CK(cudaEventRecord(h->ev_fork, h->stream));
-      CK(cudaStreamWaitEvent(h->side[0], h->ev_fork, 0));
-    }
-    // Launch order decides which kernel's CTAs reach the SMs first.  Default: box first (the gather shell then only
-    // finds room on the SMs the box leaves one slot short, profiles/r01r).  LSB200_SHELL_FIRST=1 enqueues the
-    // latency-bound shell first so that the box fills in around it -- an experiment for the next GPU session, off by
-    // default because it has not been measured.
-    static const bool shell_first = getenv("LSB200_SHELL_FIRST") && atoi(getenv("LSB200_SHELL_FIRST")) == 1;
-    // LSB200_RING=1: the ring columns are computed by the box CTAs themselves (k_fdi_box<..., RING>), no shell launch
-    // (LSB200_RING=2: the same with the ring phase of every other CTA in front of its box work, see fdi_main.cuh)
-    static const int ring_mode = getenv("LSB200_RING") ? atoi(getenv("LSB200_RING")) : 0;
-    const bool ring = ring_mode == 1 || ring_mode == 2;
-    ShellBox sb;
-    const long long shell_ctas = make_shell_box(g, h->shell_cz, 128, &sb);
-    sb.ring_stagger = ring_mode == 2 ? 1 : 0;
-    auto launch_box = [&]() -> int {
-    {
-        const UniConsts U = make_uni_consts(w);
-        const int cz = h->main_cz;
-        // output planes of the z-general launch (next to the z faces this handle owns) and of the uniform launch
-        static const int zface = (getenv("LSB200_ZFACE") && atoi(getenv("LSB200_ZFACE")) >= 3) ? atoi(getenv("LSB200_ZFACE")) : 8;
-        int zr[6];
-        plan_z_ranges(g.nz, g.k0, g.k1, cz, zface, zr);
-        const int za0 = zr[0], za1 = zr[1], zb0 = zr[2], zb1 = zr[3], ulo = zr[4], uhi = zr[5];
-        const bool zfirst = za1 > za0, zlast = zb1 > zb0;
-        const int nuni = (uhi - ulo + cz - 1) / cz;
-        const bool have_z = zfirst || zlast;
-        if (have_z && ov) CK(cudaStreamWaitEvent(h->side[2], h->ev_fork, 0));
-        cudaStream_t zs = (have_z && ov) ? h->side[2] : h->stream;
-        double* zpart = h->partials + 4 * (size_t)MAX_PARTIALS;
-        unsigned int* zcnt = h->counters + 4;
-        const dim3 ugrid(h->main_grid.x, h->main_grid.y, nuni), zgrid(h->main_grid.x, h->main_grid.y, (zb1 > zb0) ? 2 : 1);
-        switch (h->main_cfg) {
-#define LSB_BOX_LAUNCH(YB, TYT, ST, MINB, V16, RING)                                                                 \
-  {                                                                                                               \
-    auto ku = k_fdi_box<YB, TYT, ST, MINB, V16, false, RING>;                                                     \
-    auto kz = k_fdi_box<YB, TYT, ST, MINB, V16, true, RING>;                                                      \
-    cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                             \
-    cudaFuncSetAttribute(kz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                             \
-    if (ugrid.z > 0) ku<<<ugrid, dim3(32, TYT), smem, h->stream>>>(g, U, p, q, cz, ulo, uhi, 0, 0, h->ztab, part, cnt, h->sc, cg_mode, w, sb); \
-    if (have_z) kz<<<zgrid, dim3(32, TYT), smem, zs>>>(g, U, p, q, cz, za0, za1, zb0, zb1, h->ztab, zpart, zcnt, h->sc, cg_mode, w, sb);      \
-  }
-#define X(ID, YB, TYT, ST, MINB)                                                                                  \
-  case ID: {                                                                                                      \
-    const size_t smem = sizeof(double) * MainCfg<YB, TYT, ST>::PLANE * ST;                                        \
-    if (vec16 && ring) LSB_BOX_LAUNCH(YB, TYT, ST, MINB, true, true)                                              \
-    else if (vec16) LSB_BOX_LAUNCH(YB, TYT, ST, MINB, true, false)                                                \
-    else if (ring) LSB_BOX_LAUNCH(YB, TYT, ST, MINB, false, true)                                                 \
-    else LSB_BOX_LAUNCH(YB, TYT, ST, MINB, false, false)                                                          \
-  } break;
-          LSB_BOX_CFGS(X)
-#undef X
-#undef LSB_BOX_LAUNCH
-        }
-        CKL();
-        h->launches += (ugrid.z > 0 ? 1 : 0) + (have_z ? 1 : 0);
-        if (ugrid.z == 0) CK(cudaMemsetAsync(&h->sc->pq_part[0], 0, sizeof(double), h->stream));
-        if (!have_z) CK(cudaMemsetAsync(&h->sc->pq_part[3], 0, sizeof(double), h->stream));
-        if (have_z && ov) {
-          CK(cudaEventRecord(h->ev_join[2], h->side[2]));
-          CK(cudaStreamWaitEvent(h->stream, h->ev_join[2], 0));
-        }
-      }
-      return 0;
-    };
-    auto launch_shell = [&]() -> int {
-    // everything outside the box: one gather launch on a side stream, overlapped with the box kernel
-      // (LSB200_SHELL=0 leaves it out: profiling of the box kernel alone, results are then incomplete)
-      static const bool with_shell = !(getenv("LSB200_SHELL") && atoi(getenv("LSB200_SHELL")) == 0);
-      if (ring) {
-        CK(cudaMemsetAsync(&h->sc->pq_part[2], 0, sizeof(double), h->stream));
-      } else if (with_shell) {
-        constexpr int SNT = 128;
-        const long long nb = shell_ctas;
-        if (nb > MAX_PARTIALS) return fail(LSB200_ERR_ARG, "shell launch needs %lld CTAs (limit %d)", nb, MAX_PARTIALS);
-        if (nb > 0)
-          k_fdi_shell<SNT><<<(int)nb, SNT, 0, ov ? h->side[0] : h->stream>>>(g, w, sb, h->ztab, p, q,
-                                                                            h->partials + 3 * (size_t)MAX_PARTIALS,
-                                                                            h->counters + 3, h->sc, cg_mode);
-        CKL();
-        h->launches++;
-      }
-      return 0;
-    };
-    if (shell_first) {
-      if (int rc = launch_shell()) return rc;
-      if (int rc = launch_box()) return rc;
-    } else {
-      if (int rc = launch_box()) return rc;
-      if (int rc = launch_shell()) return rc;
-    }
-    if (ov) {
-      CK(cudaEventRecord(h->ev_join[0], h->side[0]));
-      CK(cudaStreamWaitEvent(h->stream, h->ev_join[0], 0));
-    }
-    return 0;
-  }
-  switch (h->stencil_cfg) {
-    case 5: LSB_LAUNCH(2, 32, 8, 1, 4); break;
-    case 6: LSB_LAUNCH(1, 32, 8, 3, 4); break;
-    default: LSB_LAUNCH(2, 32, 8, 2, 4);
-  }
+  LSB_LAUNCH(2, 32, 8, 2, 4);
 #undef LSB_LAUNCH
 #undef LSB_LAUNCH_AT
   return 0;
 }
 
 static void plan(lsb200_ctx* h) {
-  const char* env = getenv("LSB200_STENCIL_CFG");
-  h->stencil_cfg = env ? atoi(env) : 0;
-  switch (h->stencil_cfg) {
-    case 5: plan_stencil<2, 32, 8>(h, 1); break;
-    case 6: plan_stencil<1, 32, 8>(h, 3); break;
-    default: h->stencil_cfg = 0; plan_stencil<2, 32, 8>(h, 2);
-  }
+  plan_stencil<2, 32, 8>(h, 2);  // k_fdi_normal: small grids
   const char* cz = getenv("LSB200_STENCIL_CZ");
   if (cz && atoi(cz) > 0) {
     h->cz = atoi(cz);
@@ -499,7 +374,7 @@ static int launch_regularisation(lsb200_ctx* h, const double* p, double* q, int 
   const int nb = (int)std::max<long long>(1, std::min<long long>((n + VEC_NT - 1) / VEC_NT, (long long)h->sm_count * 16));
   const double w2 = h->p1_w * h->p1_w, ridge2 = h->add_ridge ? h->ridge * h->ridge : 0.0;
   if (h->p1_tiles) {
-    // one launch: boundary-role CTAs first, then the shared-memory tiles of the interior (csrc/p1.cuh)
+    // one launch: shared-memory tiles of the interior, every CTA with its share of the boundary nodes (csrc/p1.cuh)
     const P1TilePlan& pl = h->p1_plan;
     const unsigned int ctas = (unsigned int)(pl.n_bnd_cta + pl.tiles_x * pl.tiles_y * pl.tiles_z);
     switch (h->p1_tile_cfg) {
@@ -823,8 +698,8 @@ int lsb200_set_p1_tables(lsb200_handle h, const int64_t m[3], const double* tabl
   CK(cudaMemcpy(h->p1_diag, diag.data(), sizeof(double) * diag.size(), cudaMemcpyHostToDevice));
   for (int a = 0; a < 3; ++a) h->p1_m[a] = (int)m[a];
   // tile plan of the interior (LSB200_P1_TILES=0: the generic kernel everywhere; LSB200_P1_TILE_CFG: tile shape)
-  static const bool want_tiles = !(getenv("LSB200_P1_TILES") && atoi(getenv("LSB200_P1_TILES")) == 0);
-  static const int tile_cfg = getenv("LSB200_P1_TILE_CFG") ? atoi(getenv("LSB200_P1_TILE_CFG")) : 0;
+  const bool want_tiles = !(getenv("LSB200_P1_TILES") && atoi(getenv("LSB200_P1_TILES")) == 0);
+  const int tile_cfg = getenv("LSB200_P1_TILE_CFG") ? atoi(getenv("LSB200_P1_TILE_CFG")) : 1;
   h->p1_tiles = false;
   if (want_tiles) {
     switch (tile_cfg) {
@@ -2084,12 +1959,6 @@ int lsb200_eval_lattice(lsb200_handle h, const double* transform, const double s
   return pipe_result(rc, ce, "staged lattice evaluation");
 }
 
-int lsb200_plan_z_ranges(int nz, int k0, int k1, int cz, int zface, int out[6]) {
-  if (!out || nz < 1 || k0 < 0 || k1 > nz || k1 <= k0 || cz < 1) return fail(LSB200_ERR_ARG, "bad argument");
-  plan_z_ranges(nz, k0, k1, cz, zface, out);
-  return 0;
-}
-
 int lsb200_host_alloc(int64_t bytes, void** out) {
   if (!out || bytes <= 0) return fail(LSB200_ERR_ARG, "bad argument");
   *out = nullptr;
@@ -2112,7 +1981,7 @@ int lsb200_debug_cta_trace(lsb200_handle h, int64_t max_ctas, uint64_t* out, int
   if (rc) return rc;
   long long ctas = 0;
   if (h->kind == LSB200_SUPPORT_GRID) {
-    if (!(h->main_cfg >= 0 && h->fused)) return fail(LSB200_ERR_STATE, "the per-CTA trace needs the fused stencil plan");
+    if (!h->fused) return fail(LSB200_ERR_STATE, "the per-CTA trace needs the fused stencil plan");
     ctas = (long long)h->fz.pl.n_box + h->fz.pl.n_xs + h->fz.pl.n_ys;
   } else {
     if (!h->p1_tiles) return fail(LSB200_ERR_STATE, "the per-CTA trace needs the tiled P1 plan");

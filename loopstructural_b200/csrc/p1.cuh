@@ -133,8 +133,10 @@ __global__ void __launch_bounds__(NT)
 //     a tap is one LDS + one DFMA, no table load and no per-thread register array;
 //   * nodes whose parity sum is even belong to corner tets only: 15 taps against 33 (checked on the host when the plan
 //     is made, p1_plan_tiles), their loops are 16 long.
-// The boundary nodes (a shell two nodes thick, 10 % of config 3) are enumerated compactly and computed in the generic form
-// by the first CTAs of the same launch (dispatched first: they are latency bound and overlap the tile CTAs).
+// The boundary nodes (a shell two nodes thick, 10 % of config 3) are enumerated compactly and computed in the generic form,
+// an equal share by every CTA between issuing the copies of its tile and waiting for them: the gathers of the one hide
+// the latency of the other.  (CTAs of their own for the boundary held every CTA slot for the first 9 us of a 38 us launch:
+// they need no shared memory but are launched with the tile's, profiles/r2j.)
 constexpr int P1_TAPS_EVEN = 16;
 struct P1ClassTaps {
   double coef[8][P1_TAPS];  // class = pi + 2 pj + 4 pk; zero padded
@@ -145,7 +147,7 @@ struct P1TilePlan {
   int tiles_x, tiles_y, tiles_z;
   int z_base;          // global plane of the tile lattice's first layer (even)
   int kfirst, klast;   // owned interior planes [kfirst, klast)
-  int n_bnd_cta;       // CTAs [0, n_bnd_cta) take the boundary role
+  int n_bnd_cta;       // CTAs beyond the tiles that only take a share of the boundary (slabs without interior planes)
   long long nbz, nby, nbx;  // boundary nodes: whole planes / the 4 boundary rows of interior planes / the 4 boundary columns
 };
 // X(ID, TY, TZ, warps per CTA): tiles of 64 x TY x TZ nodes
@@ -178,7 +180,8 @@ inline bool p1_plan_tiles(const GridDesc& g, const int m[3], const double* table
   pl.nby = nzi * 4 * g.nx;
   pl.nbx = nzi * 4 * (g.ny - 4);
   const long long nb = pl.nbz + pl.nby + pl.nbx;
-  pl.n_bnd_cta = (int)((nb + 2 * nt - 1) / (2 * nt));  // two nodes per thread
+  const long long n_tiles = (long long)pl.tiles_x * pl.tiles_y * pl.tiles_z;
+  pl.n_bnd_cta = n_tiles * 2 * nt >= nb ? 0 : (int)((nb - n_tiles * 2 * nt + 2 * nt - 1) / (2 * nt));  // <= two nodes per thread
   if ((long long)pl.tiles_x * pl.tiles_y * pl.tiles_z + pl.n_bnd_cta > max_blocks) return false;
   const int HX = 32 + HALO, SY = ty + 2 * HALO;
   memset(T, 0, sizeof(*T));
@@ -267,21 +270,15 @@ __global__ void __launch_bounds__(32 * NW)
   const int tid = threadIdx.x;
   double dot = 0.0;
   const unsigned long long t_begin = tid == 0 ? trace_begin() : 0ull;
-  if ((int)blockIdx.x < pl.n_bnd_cta) {
-    // ---- boundary role
-    const long long nb = pl.nbz + pl.nby + pl.nbx;
-    for (long long t = (long long)blockIdx.x * NT + tid; t < nb; t += (long long)pl.n_bnd_cta * NT) {
-      int i, j, kl;
-      p1_boundary_node(g, pl, t, &i, &j, &kl);
-      dot += p1_node_generic(g, tb, w2, ridge2, p, q, i, j, kl);
-    }
-  } else {
-    // ---- tile role
-    const int b = (int)blockIdx.x - pl.n_bnd_cta;
+  const int n_tiles = pl.tiles_x * pl.tiles_y * pl.tiles_z;
+  const bool has_tile = (int)blockIdx.x < n_tiles;
+  int x0 = 0, y0 = 0, z0 = 0;
+  if (has_tile) {
+    const int b = (int)blockIdx.x;
     const int txy = pl.tiles_x * pl.tiles_y;
     const int bz = b / txy, brem = b - bz * txy;
     const int by = brem / pl.tiles_x, bx = brem - by * pl.tiles_x;
-    const int x0 = 2 + 64 * bx, y0 = 2 + TY * by, z0 = pl.z_base + TZ * bz;  // first output node of the tile
+    x0 = 2 + 64 * bx; y0 = 2 + TY * by; z0 = pl.z_base + TZ * bz;  // first output node of the tile
     // stage the nodes (x0-2 .., y0-2 .., z0-2 ..): consecutive threads read consecutive x
     for (int idx = tid; idx < G::ELEMS; idx += NT) {
       const int sx = idx % (2 * HX), r = idx / (2 * HX);
@@ -292,6 +289,17 @@ __global__ void __launch_bounds__(32 * NW)
       cp_async_8(S + ((sz * SY + sy) * 2 + (sx & 1)) * HX + (sx >> 1), ok ? src : p, ok);
     }
     cp_async_commit();
+  }
+  {
+    // ---- this CTA's share of the boundary nodes, while the tile is on its way
+    const long long nb = pl.nbz + pl.nby + pl.nbx;
+    for (long long t = (long long)blockIdx.x * NT + tid; t < nb; t += (long long)gridDim.x * NT) {
+      int i, j, kl;
+      p1_boundary_node(g, pl, t, &i, &j, &kl);
+      dot += p1_node_generic(g, tb, w2, ridge2, p, q, i, j, kl);
+    }
+  }
+  if (has_tile) {
     cp_async_wait<0>();
     __syncthreads();
     const int lane = tid & 31, warp = tid >> 5;
@@ -305,7 +313,7 @@ __global__ void __launch_bounds__(32 * NW)
     const int i = x0 + 2 * lane + pi, j = y0 + y, k = z0 + z;                                                       \
     const double* Sb = S + (z * SY + y) * 2 * HX + lane;                                                            \
     const double acc = p1_row_taps<CLS, ((pi + pj + pk) & 1) ? P1_TAPS : P1_TAPS_EVEN>(T, Sb);                      \
-    const double p0 = p1_at(Sb, T.centre[pi]);                                                                             \
+    const double p0 = p1_at(Sb, T.centre[pi]);                                                                      \
     const double v = fma(w2, acc, ridge2 * p0);                                                                     \
     if (i <= g.nx - 3 && j <= g.ny - 3 && k >= pl.kfirst && k < pl.klast) {                                         \
       q[(long long)(k - g.k0 + HALO) * g.plane + (long long)j * g.pitch + i] = v;                                   \

@@ -1,9 +1,9 @@
-"""One configuration of the FDI matvec, timed in a process of its own (the launch-plan switches LSB200_RING /
-LSB200_SHELL_FIRST / LSB200_STENCIL_MAIN are read once per process).  Prints one JSON line:
+"""One configuration of the FDI matvec, timed in a process of its own (launch-plan switches: LSB200_TMA, LSB200_FUSED_CFG,
+LSB200_FUSED_CZ, LSB200_FUSED_SCZ, LSB200_STENCIL_MAIN).  Prints one JSON line:
 matvec and whole-iteration time (CUDA events on the engine's stream, lsb200_time_kernel) and two checksums of
 q = N p for a fixed p, so that the caller can compare the numerics of the configurations with each other.
 
-    LSB200_RING=1 python scripts/matvec_experiment.py 256
+    LSB200_TMA=0 python scripts/matvec_experiment.py 256
 """
 import json
 import os

@@ -1,8 +1,8 @@
-// TEST INFRASTRUCTURE ONLY: runs the three launches of the tiled FDI regularisation operator (k_fdi_box uniform,
-// k_fdi_box<ZGEN>, k_fdi_shell -- loopstructural_b200/csrc/fdi_main.cuh, unmodified) and the single-kernel form
-// (k_fdi_normal) on the CPU through tests/hostsim/cuda_emu.h, with the launch plan of csrc/fdi_plan.cuh that
-// csrc/api.cu's launch_stencil uses, for ONE handle: a full grid or a z slab [k0,k1) whose halo planes are filled
-// from the global vector as the NCCL halo exchange would.  tests/test_stencil_emu.py compares it with the oracle.
+// TEST INFRASTRUCTURE ONLY: runs the FDI regularisation operator -- the single launch k_fdi_fused
+// (loopstructural_b200/csrc/fdi_fused.cuh, unmodified, with the launch plan of csrc/fdi_plan.cuh that csrc/api.cu's
+// launch_stencil uses) and the small-grid kernel k_fdi_normal -- on the CPU through tests/hostsim/cuda_emu.h, for ONE
+// handle: a full grid or a z slab [k0,k1) whose halo planes are filled from the global vector as the NCCL halo exchange
+// would.  tests/test_stencil_emu.py compares it with the oracle.
 //
 //   g++ -O1 -std=c++20 -pthread -mfma -DLSB_EMU -I/usr/local/cuda/include -fPIC -fvisibility=hidden -Wl,-Bsymbolic -shared \
 //       -o tests/hostsim/libstencil_emu.so tests/hostsim/stencil_emu.cpp
@@ -32,10 +32,10 @@ extern "C" {
 
 // dims = {nx, ny, nz, k0, k1}; ew = the nine effective row weights (LSB200_W_* order: mixed terms as given to
 // lsb200_set_regularisation, i.e. already divided by 4 ... see weights_from); p_global: nx*ny*nz; q_owned: nx*ny*(k1-k0).
-// cfg >= 0: box + shell launches (as LSB200_STENCIL_MAIN), cfg < 0: k_fdi_normal.  info[0..5] = z ranges, info[6] = cz,
-// info[7] = CTAs launched, info[8] = 1 if the box plan was used.  pq_out = p.q over the owned planes as the kernels sum it.
-HOSTSIM_API int emu_fdi_matvec(const int* dims, const double* ew, double ridge2, int cfg, int cz_override, int zface, int shell_cz, int ring,
-                   const double* p_global, double* q_owned, double* pq_out, int* info) {
+// k_fdi_normal everywhere (grids too small for box tiles, LSB200_STENCIL_MAIN=-1).  info[6] = cz, info[7] = CTAs launched.
+// pq_out = p.q over the owned planes as the kernel sums it.
+HOSTSIM_API int emu_fdi_normal(const int* dims, const double* ew, double ridge2, int cz_override, const double* p_global,
+                               double* q_owned, double* pq_out, int* info) {
   GridDesc g{};
   g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
   g.k0 = dims[3]; g.k1 = dims[4]; g.nzl = g.k1 - g.k0;
@@ -60,56 +60,8 @@ HOSTSIM_API int emu_fdi_matvec(const int* dims, const double* ew, double ridge2,
   CgScalars sc{};
   const bool vec16 = (g.pitch % 2) == 0;
   int ctas = 0;
-  BoxTiles bt{};
-  const bool box = cfg >= 0 && plan_box_tiles(g, cfg, cz_override, 148, MAX_PARTIALS, &bt);
   for (int i = 0; i < 9; ++i) info[i] = 0;
-  if (box) {
-    const UniConsts U = make_uni_consts(w);
-    int zr[6];
-    plan_z_ranges(g.nz, g.k0, g.k1, bt.cz, zface, zr);
-    const int za0 = zr[0], za1 = zr[1], zb0 = zr[2], zb1 = zr[3], ulo = zr[4], uhi = zr[5];
-    const int nuni = (uhi - ulo + bt.cz - 1) / bt.cz;
-    const bool have_z = za1 > za0 || zb1 > zb0;
-    const dim3 ugrid(bt.tiles_x, bt.tiles_y, nuni), zgrid(bt.tiles_x, bt.tiles_y, (zb1 > zb0) ? 2 : 1);
-    double* part = partials.data();
-    double* zpart = partials.data() + 4 * (size_t)MAX_PARTIALS;
-    const int cz = bt.cz;
-    constexpr int SNT = 128;
-    ShellBox sb;
-    const long long nb = make_shell_box(g, shell_cz, SNT, &sb);
-    sb.ring_stagger = ring == 2 ? 1 : 0;
-    switch (bt.cfg) {  // the dispatch of launch_stencil, launches through the emulator
-#define EMU_BOX_LAUNCH(YB, TYT, ST, MINB, V16, RING)                                                                  \
-  {                                                                                                                  \
-    if (ugrid.z > 0) lsb_emu::launch(ugrid, dim3(32, TYT), smem, [&] { k_fdi_box<YB, TYT, ST, MINB, V16, false, RING>(g, U, p, q, cz, ulo, uhi, 0, 0, ztab.data(), part, counters + 0, &sc, 0, w, sb); }); \
-    if (have_z) lsb_emu::launch(zgrid, dim3(32, TYT), smem, [&] { k_fdi_box<YB, TYT, ST, MINB, V16, true, RING>(g, U, p, q, cz, za0, za1, zb0, zb1, ztab.data(), zpart, counters + 4, &sc, 0, w, sb); }); \
-  }
-#define X(ID, YB, TYT, ST, MINB)                                                                                     \
-  case ID: {                                                                                                         \
-    const size_t smem = sizeof(double) * MainCfg<YB, TYT, ST>::PLANE * ST;                                           \
-    if (vec16 && ring) EMU_BOX_LAUNCH(YB, TYT, ST, MINB, true, true)                                                 \
-    else if (vec16) EMU_BOX_LAUNCH(YB, TYT, ST, MINB, true, false)                                                   \
-    else if (ring) EMU_BOX_LAUNCH(YB, TYT, ST, MINB, false, true)                                                    \
-    else EMU_BOX_LAUNCH(YB, TYT, ST, MINB, false, false)                                                             \
-  } break;
-      LSB_BOX_CFGS(X)
-#undef X
-    }
-    ctas += (ugrid.z > 0 ? ugrid.x * ugrid.y * ugrid.z : 0) + (have_z ? zgrid.x * zgrid.y * zgrid.z : 0);
-    if (ugrid.z == 0) sc.pq_part[0] = 0.0;
-    if (!have_z) sc.pq_part[3] = 0.0;
-    if (nb > MAX_PARTIALS) return -1;
-    if (ring) sc.pq_part[2] = 0.0;  // as launch_stencil: no shell launch
-    else if (nb > 0)
-      lsb_emu::launch(dim3((unsigned)nb), dim3(SNT), 0, [&] {
-        k_fdi_shell<SNT>(g, w, sb, ztab.data(), p, q, partials.data() + 3 * (size_t)MAX_PARTIALS, counters + 3, &sc, 0);
-      });
-    if (!ring) ctas += (int)nb;
-    for (int i = 0; i < 6; ++i) info[i] = zr[i];
-    info[6] = cz;
-    info[8] = 1;
-    *pq_out = sc.pq_part[0] + sc.pq_part[2] + sc.pq_part[3];
-  } else {
+  {
     // k_fdi_normal everywhere: plan_stencil<2,32,8>(h, 2) of csrc/api.cu with one z chunk per 16 planes
     using C = StencilCfg<2, 32, 8, 4>;
     const int tiles_x = (g.nx + C::TX - 1) / C::TX, tiles_y = (g.ny + C::TY - 1) / C::TY;

@@ -21,11 +21,9 @@ def _built():
 
 # ---------------------------------------------------------------- K1: regularisation operator
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "fdi_operator_*.npz"))))
-@pytest.mark.parametrize("cfg", ["0", "5", "6"])
-def test_stencil_operator_matches_reference_gram(path, cfg, monkeypatch):
+def test_stencil_operator_matches_reference_gram(path):
     """R^T R p at EVERY dof incl. the boundary shell == the explicit Gram matrix of the reference
     (the bar of LIT/test_fdi_matrix_free_regularisation.py:468-493, 1e-10)."""
-    monkeypatch.setenv("LSB200_STENCIL_CFG", cfg)
     z = np.load(path)
     grid = fo.Grid(z["nodes"], np.zeros(3), np.ones(3))
     w = H.weights_of(z)
@@ -63,14 +61,21 @@ def test_stencil_operator_matches_oracle_two_pass(nodes, cz, monkeypatch):
 
 
 @pytest.mark.parametrize("nodes", [(70, 37, 45), (129, 20, 66), (64, 64, 40), (16, 16, 5), (200, 100, 9), (66, 70, 130), (8, 16, 3)])
-@pytest.mark.parametrize("main", ["-1", "0", "1", "2", "4"])
+@pytest.mark.parametrize("main", ["normal", "fused", "fused3", "fused4", "fused-cp.async", "fused3-cp.async"])
 @pytest.mark.parametrize("cz", ["0", "7"])
 def test_main_stencil_kernel_configs(nodes, main, cz, monkeypatch):
-    """Every configuration of the register-tiled main kernel (+ y-shell launch) against the oracle's masked
-    two-pass form, on ragged grids and odd z-chunking; main=-1 is k_fdi_normal everywhere."""
-    monkeypatch.setenv("LSB200_STENCIL_MAIN", main)
+    """Every configuration of the single-launch operator (k_fdi_fused: both tile shapes, TMA and cp.async staging)
+    against the oracle's masked two-pass form, on ragged grids and odd z-chunking; "normal" is k_fdi_normal everywhere."""
+    if main == "normal":
+        monkeypatch.setenv("LSB200_STENCIL_MAIN", "-1")
+    if "3" in main or "4" in main:
+        monkeypatch.setenv("LSB200_FUSED_CFG", "3" if "3" in main else "4")
+    if "cp.async" in main:
+        monkeypatch.setenv("LSB200_TMA", "0")
     if cz != "0":
         monkeypatch.setenv("LSB200_STENCIL_CZ", cz)
+        monkeypatch.setenv("LSB200_FUSED_CZ", cz)
+        monkeypatch.setenv("LSB200_FUSED_SCZ", "9")
     rng = np.random.default_rng(sum(nodes) + 1)
     grid = fo.Grid(np.array(nodes), np.zeros(3), np.ones(3))
     w = dict(dxx=1.3, dyy=0.8, dzz=1.1, dxy=2.0, dyz=0.5, dxz=1.5, dx=0.7, dy=1.9, dz=1.2)

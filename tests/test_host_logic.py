@@ -75,41 +75,6 @@ def test_p1_stencil_table_reproduces_the_explicit_gram(ncells, step):
                 assert np.abs(row - N[i + n[0] * (j + n[1] * k)]).max() <= 1e-13
 
 
-def test_z_ranges_of_the_box_launches_partition_every_slab():
-    """plan_z_ranges (csrc/api.cu, through lsb200_plan_z_ranges): for every slab of every partition the z-general
-    ranges A, B and the uniform range U are disjoint, cover the owned planes, keep the planes next to a z face out of
-    U, stay short enough for the kernel's per-CTA coefficient table, and A is non-empty whenever B is."""
-    import ctypes as C
-
-    from loopstructural_b200 import _native as nat
-    from loopstructural_b200 import build as lsbuild
-    from loopstructural_b200 import partition
-
-    lsbuild.build()
-    lib = nat.load()
-    out = (C.c_int * 6)()
-    for nz in (6, 7, 9, 16, 24, 66, 128, 256, 1024, 2048):
-        for nranks in (1, 2, 3, 4, 8):
-            if nz < 2 * nranks:
-                continue
-            for cz in (3, 5, 8, 43, 103, 156):
-                for zface in (3, 8, 16):
-                    for k0, k1 in partition.slab_bounds(nz, nranks):
-                        assert lib.lsb200_plan_z_ranges(nz, k0, k1, cz, zface, out) == 0
-                        a0, a1, b0, b1, u0, u1 = list(out)
-                        planes = []
-                        for lo, hi in ((a0, a1), (u0, u1), (b0, b1)):
-                            if hi > lo:
-                                planes += list(range(lo, hi))
-                        assert sorted(planes) == list(range(k0, k1)), (nz, nranks, cz, zface, k0, k1, list(out))
-                        assert all(3 <= k <= nz - 4 for k in range(u0, u1))
-                        assert a1 - a0 <= 156 and b1 - b0 <= 156
-                        assert (a1 > a0) or not (b1 > b0)
-                        if a1 > a0 and b1 > b0:
-                            assert a1 <= b0
-    assert lib.lsb200_plan_z_ranges(10, 5, 3, 4, 8, out) != 0
-
-
 def test_mirror_drops_a_whole_family_that_holds_a_nan_like_the_reference(monkeypatch):
     """add_constraints_to_least_squares returns without adding anything when A, B or the indices of a family contain a
     NaN (LI/_discrete_interpolator.py:355-359) -- a NaN value constraint inside the support silences ALL value
