@@ -754,6 +754,7 @@ def run_ours(args):
     t_iter = eng.time_kernel(1, reps=20)
     t_rows, t_xr, t_p = eng.time_kernel(2, reps=20), eng.time_kernel(3, reps=20), eng.time_kernel(4, reps=20)
     peak, peak_src = measured_peak()
+    plan_text = eng.describe_plan()
     dof_local = eng.local_dof
     rows_local = int(eng.num_rows)
     ach = BYTES_MATVEC_PER_DOF * dof_local / t_matvec / 1e9
@@ -778,7 +779,7 @@ def run_ours(args):
             "config": {"workload": f"synthetic FDI foliation {n}x{n}x{nz} nodes, {n_value} value + {n_gradient} gradient "
                                    f"constraints, default weights, ridge 1e-8, column scaling, cg rtol 1e-5 (configs[1]"
                                    f"{' x N z-slabs' if world > 1 else ''})",
-                       "parallelism": f"z-slabs x{world}", "l2": "node vectors (134 MB each) exceed the 126 MB L2",
+                       "parallelism": f"z-slabs x{world}", "launch_plan": plan_text, "l2": "node vectors (134 MB each) exceed the 126 MB L2",
                        "dof": dof_global},
             "solve_seconds": dev_s / max(args.steps, 1), "cg_iterations": iters_per_solve,
             "cg_iterations_per_second": its / dev_s if dev_s > 0 else None,

@@ -348,6 +348,10 @@ int lsb200_host_free(void* p);
  * fused r.S^2 r reduction, 4 = p update */
 int lsb200_time_kernel(lsb200_handle h, int which, int reps, double* seconds_per_launch);
 
+/* the launch plan of the regularisation operator as text (tile shape, chunks, CTAs; after lsb200_finalize_system the
+ * plan chosen by timing the planner's candidates on this handle) */
+int lsb200_describe_plan(lsb200_handle h, char* out, int64_t capacity);
+
 /* one launch of the regularisation operator with the per-CTA trace on: out[3 b .. 3 b + 2] = {start ns, end ns, SM id}
  * of CTA b in block-index order (the single-launch plans only: k_fdi_fused, k_p1_tiles); *n_ctas = CTAs of the launch.
  * Shows which role of a launch (box chunk, z-face chunk, strip; tile, boundary) ends last. */

@@ -111,6 +111,7 @@ SIGNATURES = {
     "lsb200_host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     "lsb200_host_free": (C.c_int, [C.c_void_p]),
     "lsb200_time_kernel": (C.c_int, [Handle, C.c_int, C.c_int, c_double_p]),
+    "lsb200_describe_plan": (C.c_int, [Handle, C.c_char_p, C.c_int64]),
     "lsb200_debug_cta_trace": (C.c_int, [Handle, C.c_int64, C.POINTER(C.c_uint64), c_int64_p]),
 }
 
@@ -122,12 +123,13 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("LSB200_LIBRARY", LIB_PATH)  # another build of the same ABI (A/B measurements)
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m loopstructural_b200.build` "
+            f"{path} is missing: build it with `python -m loopstructural_b200.build` "
             "(the engine has no CPU fallback)"
         )
-    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res

@@ -137,6 +137,8 @@ struct lsb200_ctx {
   int cz = 0;              // k_fdi_normal (grids too small for box tiles): z chunk and grid
   dim3 sgrid;
   bool fused = false;      // the single-launch plan (k_fdi_fused): whenever the grid is large enough
+  bool tuned = false;      // the plan has been chosen among the planner's candidates by timing them (tune_fused)
+  bool plan_forced = false;  // an environment switch fixed the plan: no tuning
   FusedChoice fz{};
   // TMA descriptors of the two node vectors the operator is applied to (p inside CG, x for the initial residual and
   // lsb200_residual_norm), one per box configuration (their boxes differ); tma_ok: built for this handle
@@ -228,6 +230,10 @@ static void plan_main(lsb200_ctx* h) {
   if (h->kind != LSB200_SUPPORT_GRID) return;
   if (getenv("LSB200_STENCIL_MAIN") && atoi(getenv("LSB200_STENCIL_MAIN")) < 0) return;
   auto env_int = [](const char* name) { const char* e = getenv(name); return (e && atoi(e) > 0) ? atoi(e) : 0; };
+  if (const char* e = getenv("LSB200_FUSED_MODEL")) sscanf(e, "%lf,%lf,%lf", &FUSED_FACE_COST, &FUSED_XS_REL, &FUSED_YS_REL);
+  h->plan_forced = getenv("LSB200_FUSED_MODEL") || env_int("LSB200_FUSED_CFG") || env_int("LSB200_FUSED_CZ") || env_int("LSB200_FUSED_SCZ") ||
+                   (getenv("LSB200_AUTOTUNE") && atoi(getenv("LSB200_AUTOTUNE")) == 0);
+  h->tuned = false;
   if (!plan_fused(g, h->sm_count, MAX_PARTIALS, env_int("LSB200_FUSED_CFG"), env_int("LSB200_FUSED_CZ"), env_int("LSB200_FUSED_SCZ"),
                   &h->fz))
     return;  // no box: k_fdi_normal everywhere
@@ -1071,6 +1077,70 @@ static int build_transposes(lsb200_ctx* h) {
   return 0;
 }
 
+// The planner's cost model (csrc/fdi_plan.cuh) ranks plans well on one grid and badly on the next: at 512^3 the plan it
+// prefers with strips costed at 1.0 / 1.4 box steps runs in 409 us against 489 us for its default, at 256^3 the same
+// constants lose 76 us against 72 (profiles/r2q).  So the model only proposes: the plans it picks under a handful of
+// constant sets are each launched a few times on the handle's own vectors (q = N p, both scratch before a solve) and the
+// fastest stays.  Once per handle, a few ms; skipped in deterministic mode (the plan fixes the order of the p.q sums)
+// and whenever an environment switch pins the plan.
+static int tune_fused(lsb200_ctx* h) {
+  static const double models[][3] = {{12, 1.45, 2.0}, {24, 1.45, 2.0}, {24, 1.8, 2.4}, {24, 1.0, 1.4}, {12, 1.0, 1.4}, {24, 0.7, 1.0}};
+  const double keep[3] = {FUSED_FACE_COST, FUSED_XS_REL, FUSED_YS_REL};
+  std::vector<FusedChoice> cands;
+  for (const auto& m : models) {
+    FUSED_FACE_COST = m[0]; FUSED_XS_REL = m[1]; FUSED_YS_REL = m[2];
+    FusedChoice c;
+    if (!plan_fused(h->g, h->sm_count, MAX_PARTIALS, 0, 0, 0, &c)) continue;
+    bool seen = false;
+    for (const FusedChoice& o : cands) seen = seen || (o.tyt == c.tyt && memcmp(&o.pl, &c.pl, sizeof(FusedPlan)) == 0);
+    if (!seen) cands.push_back(c);
+  }
+  FUSED_FACE_COST = keep[0]; FUSED_XS_REL = keep[1]; FUSED_YS_REL = keep[2];
+  // ... and the neighbours of the default plan: one chunk fewer to two more, strips shorter and longer
+  {
+    const FusedChoice base = h->fz;
+    const int minb = base.minb;
+    for (int dn = -1; dn <= 2 && cands.size() < 20; ++dn)
+      for (const double fs : {1.0, 0.7, 1.4, 2.0}) {
+        const int nch = base.pl.chunks + dn, scz = std::max(6, (int)(base.pl.scz * fs + 0.5));
+        if (nch < 1 || nch > std::max(1, h->g.nzl / 8)) continue;
+        const FusedChoice c = fused_candidate(h->g, base.tyt, minb, nch, scz, h->sm_count);
+        if (c.ctas > MAX_PARTIALS) continue;
+        bool seen = false;
+        for (const FusedChoice& o : cands) seen = seen || (o.tyt == c.tyt && memcmp(&o.pl, &c.pl, sizeof(FusedPlan)) == 0);
+        if (!seen) cands.push_back(c);
+      }
+  }
+  h->tuned = true;
+  if (cands.size() < 2) return 0;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaMemsetAsync(h->p, 0, sizeof(double) * (size_t)h->g.nall, h->stream));
+  const FusedChoice first = h->fz;
+  float best_ms = 0.f;
+  int best = -1, rc = 0;
+  for (size_t i = 0; i < cands.size() && rc == 0; ++i) {
+    h->fz = cands[i];
+    h->tma_vec[0] = h->tma_vec[1] = nullptr;  // the TMA box follows the tile shape
+    for (int rep = -1; rep < 3 && rc == 0; ++rep) {
+      if (rep == 0) CK(cudaEventRecord(e0, h->stream));
+      rc = launch_stencil(h, h->p, h->q, 0);
+    }
+    if (rc) break;
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (best < 0 || ms < best_ms) { best = (int)i; best_ms = ms; }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  h->fz = (rc == 0 && best >= 0) ? cands[best] : first;
+  h->tma_vec[0] = h->tma_vec[1] = nullptr;
+  return rc;
+}
+
 int lsb200_finalize_system(lsb200_handle h) {
   if (!h) return fail(LSB200_ERR_ARG, "null handle");
   if (h->finalized) return 0;
@@ -1081,6 +1151,7 @@ int lsb200_finalize_system(lsb200_handle h) {
   CK(cudaEventRecord(e0, h->stream));
   int rc = ensure_vectors(h);
   if (rc) return rc;
+  if (h->kind == LSB200_SUPPORT_GRID && h->fused && !h->tuned && !h->plan_forced && !h->deterministic && (rc = tune_fused(h))) return rc;
   rc = merge_blocks(h);
   if (rc) return rc;
   for (RowBlock& rb : h->blocks)
@@ -1969,6 +2040,28 @@ int lsb200_host_alloc(int64_t bytes, void** out) {
 }
 int lsb200_host_free(void* p) {
   if (p) cudaFreeHost(p);
+  return 0;
+}
+
+// Diagnostics: the launch plan of the regularisation operator as text (after lsb200_finalize_system: the tuned plan)
+int lsb200_describe_plan(lsb200_handle h, char* out, int64_t capacity) {
+  if (!h || !out || capacity < 1) return fail(LSB200_ERR_ARG, "bad argument");
+  if (h->kind == LSB200_SUPPORT_GRID && h->fused) {
+    const FusedPlan& pl = h->fz.pl;
+    snprintf(out, (size_t)capacity,
+             "k_fdi_fused: tiles 64x%d (%d x %d), %d box chunks of %d planes (first %d), %d box CTAs, strips of %d planes "
+             "(%d x-strip + %d y-strip CTAs), %d CTAs per SM, %s staging, %s",
+             4 * h->fz.tyt, pl.tiles_x, pl.tiles_y, pl.chunks, pl.cz, pl.lo_len, pl.n_box, pl.scz, pl.n_xs, pl.n_ys, h->fz.minb,
+             (h->want_tma && h->g.pitch % 2 == 0) ? "TMA" : "cp.async", h->tuned ? "chosen by timing" : "planner default");
+  } else if (h->kind == LSB200_SUPPORT_GRID) {
+    snprintf(out, (size_t)capacity, "k_fdi_normal: grid %u x %u x %u, z chunks of %d planes", h->sgrid.x, h->sgrid.y, h->sgrid.z, h->cz);
+  } else if (h->p1_tiles) {
+    const P1TilePlan& pl = h->p1_plan;
+    snprintf(out, (size_t)capacity, "k_p1_tiles: tile configuration %d, %d x %d x %d tiles, %d boundary-only CTAs", h->p1_tile_cfg,
+             pl.tiles_x, pl.tiles_y, pl.tiles_z, pl.n_bnd_cta);
+  } else {
+    snprintf(out, (size_t)capacity, "k_p1_normal: one thread per node");
+  }
   return 0;
 }
 

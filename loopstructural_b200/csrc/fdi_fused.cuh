@@ -452,8 +452,13 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
     const int ch = b / (2 * per_side), rem = b - ch * 2 * per_side;
     const int side = rem / per_side, st = rem - side * per_side;
     const int ka = g.k0 + ch * pl.scz, kb = min(ka + pl.scz, g.k1);
-    if (ys) dot = strip_cta<C::NT, ST, 1>(g, w, zsm, p, q, side, C::X_FIRST + st * C::NT, C::X_FIRST, g.nx - C::X_FIRST, ka, kb, S, tid);
-    else dot = strip_cta<C::NT, ST, 0>(g, w, zsm, p, q, side, st * C::NT, 0, g.ny, ka, kb, S, tid);
+    // a strip plane is small (NT + 4 rows of 6 doubles): the same shared memory holds a ring of STS of them, STS - 3 in
+    // flight.  A strip row is 48 bytes of a 2 KB grid row, its copies are bound by DRAM latency, not bandwidth; with the 3
+    // planes in flight of the box ring a strip step took 1.4 us (profiles/r2j_cta_trace_256.txt)
+    constexpr int STS = (ST * C::PLANE) / ((C::NT + 2 * HALO) * StripGeom<0>::NC) < 12 ? (ST * C::PLANE) / ((C::NT + 2 * HALO) * StripGeom<0>::NC) : 12;
+    static_assert(STS >= ST, "the strip ring is at least as deep as the box ring");
+    if (ys) dot = strip_cta<C::NT, STS, 1>(g, w, zsm, p, q, side, C::X_FIRST + st * C::NT, C::X_FIRST, g.nx - C::X_FIRST, ka, kb, S, tid);
+    else dot = strip_cta<C::NT, STS, 0>(g, w, zsm, p, q, side, st * C::NT, 0, g.ny, ka, kb, S, tid);
   } else {
     // ---- box role: interior tile, the march of k_fdi_box over the planes 3 <= k < nz-3 of its chunk
     const int b = bid;

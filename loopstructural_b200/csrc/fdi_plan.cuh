@@ -44,15 +44,17 @@ struct FusedChoice {
   double cost;  // estimated critical path in box plane steps, the quantity the planner minimises
 };
 
-// Cost model (units: one plane step of a box CTA with the SM fully populated), calibrated on the per-CTA timeline of a
-// 256^3 launch on a B200 (lsb200_debug_cta_trace, profiles/r2j_cta_trace_256.txt: box CTA 1.03 us per step, strip CTA
-// 0.32 us per step, a z-face chunk of 35 planes as long as an interior chunk of 47):
+// Cost model (units: one plane step of a box CTA with the SM fully populated; measured on a B200 with the per-CTA
+// timeline of a launch, lsb200_debug_cta_trace, profiles/r2j_cta_trace_256.txt -- 320 box CTAs of 44-56 planes, then 80
+// strip CTAs of 26 planes):
 //   box CTA      planes + 4 halo steps, + FACE_COST when the chunk owns planes next to a z face (z_face_block);
-//   x / y strip  (planes + 4) * XS_REL / YS_REL (a strip step moves 4 x NT or 3 x NT nodes against the 64 x 4 TYT of a box
-//                step and is not bound by shared-memory bandwidth).
+//   x / y strip  (planes + 4) * XS_REL / YS_REL: a strip step is 1.4 us against the 1.0 us of a box step although it moves
+//                a quarter of the nodes (general coefficients, 8-byte copies: 344 / 476 instructions per warp step against
+//                242 of a TMA-staged box step).  A "recalibration" to 0.35 / 0.45 from a misread timeline made every
+//                256^3 matvec 117 us instead of 71 (profiles/r2o_cost_model.jsonl): strips are short and many on purpose.
 // The launch is simulated as the hardware runs it: CTAs in block-index order onto the first free of (SMs x CTAs per SM)
-// slots; the plan with the shortest makespan wins.
-constexpr double FUSED_FACE_COST = 16.0, FUSED_XS_REL = 0.35, FUSED_YS_REL = 0.45;
+// slots; the plan with the shortest makespan wins.  LSB200_FUSED_MODEL=face,xs,ys overrides the three constants.
+static double FUSED_FACE_COST = 12.0, FUSED_XS_REL = 1.45, FUSED_YS_REL = 2.0;
 constexpr double FUSED_CTA_COST = 4.0;  // prologue of a CTA (offset table, first planes in flight) in plane steps
 
 inline FusedChoice fused_candidate(const GridDesc& g, const int tyt, const int minb, const int nch, const int scz_in,

@@ -392,6 +392,12 @@ class Engine:
                                                 int(gradient), nat.dptr(out)))
         return out
 
+    def describe_plan(self) -> str:
+        """Launch plan of the regularisation operator (after finalize(): the one chosen by timing the candidates)."""
+        buf = C.create_string_buffer(512)
+        nat.check(self._lib.lsb200_describe_plan(self._h, buf, 512))
+        return buf.value.decode()
+
     def cta_trace(self, max_ctas: int = 1 << 18) -> np.ndarray:
         """(n_ctas, 3) uint64: start ns, end ns, SM id of every CTA of one launch of the regularisation operator."""
         out = np.zeros((max_ctas, 3), dtype=np.uint64)

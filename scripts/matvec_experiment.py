@@ -30,6 +30,7 @@ def main():
            "matvec_us": 1e6 * e.time_kernel(0, 20), "iteration_us": 1e6 * e.time_kernel(1, 20),
            "q_dot_probe": float(q @ probe), "q_norm": float(np.linalg.norm(q)), "p_dot_q": float(p @ q)}
     out["matvec_gbs"] = 16.0 * e.local_dof / out["matvec_us"] / 1e3
+    out["plan"] = e.describe_plan()
     e.close()
     print(json.dumps(out))
 

@@ -16,5 +16,5 @@ for name, slab in (("end rank", (0, planes)), ("middle rank", (planes, 2 * plane
     e.finalize()
     dof = e.local_dof
     tm, ti = e.time_kernel(0, 10), e.time_kernel(1, 10)
-    print(f"{n}x{n} x planes {slab} ({name}): matvec {tm*1e6:.1f} us = {16*dof/tm/1e9:.0f} GB/s, iteration {ti*1e6:.1f} us = {104*dof/ti/1e9:.0f} GB/s")
+    print(f"{n}x{n} x planes {slab} ({name}): matvec {tm*1e6:.1f} us = {16*dof/tm/1e9:.0f} GB/s, iteration {ti*1e6:.1f} us = {104*dof/ti/1e9:.0f} GB/s; {e.describe_plan()}")
     e.close()

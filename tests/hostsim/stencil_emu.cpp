@@ -141,6 +141,8 @@ HOSTSIM_API int emu_fdi_fused(const int* dims, const double* ew, double ridge2, 
   return 0;
 }
 
+HOSTSIM_API void emu_set_fused_model(double face, double xs, double ys) { FUSED_FACE_COST = face; FUSED_XS_REL = xs; FUSED_YS_REL = ys; }
+
 // the plan alone (no launch): info = {TYT, cz, chunks, lo_len, box CTAs, scz, x-strip CTAs, y-strip CTAs, MINB}, *cost = model cost
 HOSTSIM_API int emu_plan_fused(const int* dims, int cfg, int cz_override, int scz_override, int sm_count, int* info, double* cost) {
   GridDesc g{};
