@@ -348,6 +348,69 @@ def measure_eval(eng, local, npts=20_000_000, npts_host=10_000_000):
     return res
 
 
+def measure_other_configs(local):
+    """The other single-GPU BASELINE configurations on the driver's clock, each solved twice (the second solve is reported):
+    configs[0] -- the README quickstart (Claudius 'strati', nelements=1e5 -> 175,780 nodes) through the unmodified
+    reference's GeologicalModel with plugin.install() and solver='b200' (needs baseline/_ref on the box);
+    configs[2] -- P1 on 117^3 cells = 8,008,065 tets with 1e5 normal + 1e5 tangent + 100 value points through the
+    reference-shaped mirror class.  Small systems: the iteration is launch-latency bound, not HBM bound."""
+    out = {}
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    try:
+        import fullsize_inputs as fi
+        from loopstructural_b200.interpolators import B200P1Interpolator, Support
+
+        nc = 117
+        value, normal, tangent = fi.c3_points()
+        it = B200P1Interpolator(Support(np.zeros(3), [nc] * 3, np.full(3, 1.0 / nc)), device=local)
+        it.set_value_constraints(value)
+        it.set_normal_constraints(normal)
+        it.set_tangent_constraints(tangent)
+        for _ in range(2):
+            t0 = time.perf_counter()
+            it.setup_interpolator(cgw=0.1)
+            ok = it.solve_system("b200")
+            wall = time.perf_counter() - t0
+        t = it.latest_solve_timing
+        out["configs2_p1_8M_tets"] = {"tets": 5 * nc ** 3, "nodes": (nc + 1) ** 3, "ok": bool(ok), "iterations": int(t["iterations"]),
+                                      "solve_seconds": t["solve_seconds"], "setup_and_solve_wall_seconds": wall,
+                                      "us_per_iteration": 1e6 * t["solve_seconds"] / max(int(t["iterations"]), 1),
+                                      "reference": "1619 iterations, 120 s CG + 3 min set-up (SURVEY.md section 6)"}
+        it.close()
+    except Exception as exc:  # noqa: BLE001
+        out["configs2_p1_8M_tets"] = {"error": f"{type(exc).__name__}: {exc}"}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import refenv
+
+        refenv.activate()
+        import LoopStructural as ls
+        from LoopStructural.datasets import load_claudius
+
+        import loopstructural_b200.plugin as b200
+
+        b200.install()
+        data, bb = load_claudius()
+        for _ in range(2):
+            model = ls.GeologicalModel(bb[0, :], bb[1, :])
+            model.data = data
+            t0 = time.perf_counter()
+            model.create_and_add_foliation("strati", nelements=1e5, solver="b200")
+            model.update()
+            wall = time.perf_counter() - t0
+        it = model["strati"].interpolator
+        t = it.latest_solve_timing
+        out["configs0_claudius_1e5"] = {"nodes": int(np.prod(it.support.nsteps)), "backend": t.get("backend"),
+                                        "iterations": int(t["iterations"]), "solve_seconds": t["solve_seconds"],
+                                        "model_update_wall_seconds": wall,
+                                        "us_per_iteration": 1e6 * t["solve_seconds"] / max(int(t["iterations"]), 1),
+                                        "reference": "2015 iterations, 18.6 s (SURVEY.md section 6)"}
+        b200.uninstall()
+    except Exception as exc:  # noqa: BLE001
+        out["configs0_claudius_1e5"] = {"error": f"{type(exc).__name__}: {exc}"}
+    return out
+
+
 def measure_fault(local, n_nodes=128, npts=10_000_000, steps=10, cpu_points=100_000):
     """Fault-frame evaluation (SURVEY.md section 8 f rank 1; FaultSegment.apply_to_points,
     LS/modelling/features/fault/_fault_segment.py:315-423): three synthetic 128^3 fields, a device-resident uniform
@@ -829,6 +892,11 @@ def run_ours(args):
                 line["fault"] = measure_fault(local)
             except Exception as exc:  # noqa: BLE001
                 line["fault"] = {"error": f"{type(exc).__name__}: {exc}"}
+        if world == 1 and not args.no_other_configs:
+            try:
+                line["other_configs"] = measure_other_configs(local)
+            except Exception as exc:  # noqa: BLE001
+                line["other_configs"] = {"error": f"{type(exc).__name__}: {exc}"}
         if world == 1 and not args.no_experiments:
             # processes of their own, after this one has released the device memory it no longer needs
             try:
@@ -863,6 +931,7 @@ def main():
     ap.add_argument("--eval-points", type=int, default=100_000_000)
     ap.add_argument("--no-experiments", action="store_true", help="skip the unmeasured launch-plan experiments (subprocesses)")
     ap.add_argument("--no-fault", action="store_true", help="skip the fault-frame evaluation measurement")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip BASELINE configs[0] and configs[2] (small-system solves)")
     ap.add_argument("--no-check", action="store_true", help="N > 1: skip the correctness check of the slab solve")
     ap.add_argument("--c5", action="store_true", help="N > 1: also run BASELINE configs[4] (1024^3 solve + 1e8-point evaluation)")
     ap.add_argument("--no-c5", action="store_true", help="N = 8: skip BASELINE configs[4]")

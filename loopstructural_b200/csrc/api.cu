@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "cg.cuh"
+#include "cg_small.cuh"
 #include "common.cuh"
 #include "eval.cuh"
 #include "fdi_stencil.cuh"
@@ -137,6 +138,11 @@ struct lsb200_ctx {
   int cz = 0;              // k_fdi_normal (grids too small for box tiles): z chunk and grid
   dim3 sgrid;
   bool fused = false;      // the single-launch plan (k_fdi_fused): whenever the grid is large enough
+  // small systems: the CG loop as one persistent launch per batch of iterations (csrc/cg_small.cuh)
+  bool small_ok = false;
+  unsigned int* small_bar = nullptr;
+  double* small_slots = nullptr;
+  int small_grid = 0;
   bool tuned = false;      // the plan has been chosen among the planner's candidates by timing them (tune_fused)
   bool plan_forced = false;  // an environment switch fixed the plan: no tuning
   FusedChoice fz{};
@@ -289,7 +295,7 @@ static int launch_stencil(lsb200_ctx* h, const double* p, double* q, int cg_mode
     const size_t smem = sizeof(double) * StencilCfg<XB, TXT, TYT, ST>::PLANE * ST;                               \
     double* part_ = h->partials + (size_t)(SLOT) * MAX_PARTIALS;                                                 \
     unsigned int* cnt_ = h->counters + (SLOT);                                                                   \
-    if (vec16) {                                                                                                 \
+    if (vec16 && g.nx % 2 == 0) { /* pairs must not straddle the last column: its partner would be row padding */ \
       auto kern = k_fdi_normal<XB, TXT, TYT, MINB, ST, true>;                                                    \
       if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
       kern<<<GRID, dim3(TXT, TYT), smem, STREAM>>>(g, w, p, q, CZ, part_, cnt_, h->sc, cg_mode);                  \
@@ -557,7 +563,7 @@ static int create_common(int kind, const int64_t nsteps[3], const double origin[
   int ndev = lsb200_device_count();
   if (ndev <= 0) return fail(LSB200_ERR_CUDA, "no CUDA device available (this engine has no CPU fallback)");
   if (device < 0 || device >= ndev) return fail(LSB200_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
-  const long long plane = (long long)nsteps[0] * nsteps[1];
+  const long long plane = (long long)((nsteps[0] + 1) & ~1LL) * nsteps[1];
   if (plane * (k1 - k0 + 2 * HALO) >= 2147483647LL)
     return fail(LSB200_ERR_ARG, "local slab has %lld node slots; the limit per handle is 2^31-1 (use more z-slabs)", plane * (k1 - k0 + 2 * HALO));
   CK(cudaSetDevice(device));
@@ -567,7 +573,7 @@ static int create_common(int kind, const int64_t nsteps[3], const double origin[
   GridDesc& g = h->g;
   g.nx = (int)nsteps[0]; g.ny = (int)nsteps[1]; g.nz = (int)nsteps[2];
   g.k0 = (int)k0; g.k1 = (int)k1; g.nzl = (int)(k1 - k0);
-  g.pitch = g.nx;
+  g.pitch = (g.nx + 1) & ~1;  // even: 16-byte copies and the TMA descriptors need rows that start on 16 bytes
   g.plane = (long long)g.pitch * g.ny;
   g.nloc = g.plane * g.nzl;
   g.nall = g.plane * (g.nzl + 2 * HALO);
@@ -635,6 +641,8 @@ int lsb200_destroy(lsb200_handle h) {
   cudaFree(h->partials);
   cudaFree(h->counters);
   cudaFree(h->status);
+  cudaFree(h->small_bar);
+  cudaFree(h->small_slots);
   cudaFree(h->p1_table);
   cudaFree(h->p1_off);
   cudaFree(h->p1_diag);
@@ -1083,6 +1091,9 @@ static int build_transposes(lsb200_ctx* h) {
 // constant sets are each launched a few times on the handle's own vectors (q = N p, both scratch before a solve) and the
 // fastest stays.  Once per handle, a few ms; skipped in deterministic mode (the plan fixes the order of the p.q sums)
 // and whenever an environment switch pins the plan.
+static void plan_small(lsb200_ctx* h);
+static int launch_small(lsb200_ctx* h, int iters);
+
 static int tune_fused(lsb200_ctx* h) {
   static const double models[][3] = {{12, 1.45, 2.0}, {24, 1.45, 2.0}, {24, 1.8, 2.4}, {24, 1.0, 1.4}, {12, 1.0, 1.4}, {24, 0.7, 1.0}};
   const double keep[3] = {FUSED_FACE_COST, FUSED_XS_REL, FUSED_YS_REL};
@@ -1100,16 +1111,28 @@ static int tune_fused(lsb200_ctx* h) {
   {
     const FusedChoice base = h->fz;
     const int minb = base.minb;
-    for (int dn = -1; dn <= 2 && cands.size() < 20; ++dn)
-      for (const double fs : {1.0, 0.7, 1.4, 2.0}) {
-        const int nch = base.pl.chunks + dn, scz = std::max(6, (int)(base.pl.scz * fs + 0.5));
-        if (nch < 1 || nch > std::max(1, h->g.nzl / 8)) continue;
+    // (a grid whose plan leaves CTA slots empty is bound by the latency of a march, not by bandwidth: chunks down to
+    // 2 planes, twice and four times as many as the model likes)
+    const long long slots = (long long)h->sm_count * minb;
+    const bool small = base.ctas < slots;
+    std::vector<std::pair<int, double>> var;
+    for (int dn = -1; dn <= 2; ++dn)
+      for (const double fs : {1.0, 0.7, 1.4, 2.0}) var.push_back({base.pl.chunks + dn, fs});
+    if (small)
+      for (const int mul : {2, 4, 8})
+        for (const double fs : {1.0, 0.5, 0.25}) var.push_back({base.pl.chunks * mul, fs});
+    for (const auto& v : var) {
+      if (cands.size() >= 28) break;
+      {
+        const int nch = v.first, scz = std::max(small ? 3 : 6, (int)(base.pl.scz * v.second + 0.5));
+        if (nch < 1 || nch > std::max(1, h->g.nzl / (small ? 2 : 8))) continue;
         const FusedChoice c = fused_candidate(h->g, base.tyt, minb, nch, scz, h->sm_count);
         if (c.ctas > MAX_PARTIALS) continue;
         bool seen = false;
         for (const FusedChoice& o : cands) seen = seen || (o.tyt == c.tyt && memcmp(&o.pl, &c.pl, sizeof(FusedPlan)) == 0);
         if (!seen) cands.push_back(c);
       }
+    }
   }
   h->tuned = true;
   if (cands.size() < 2) return 0;
@@ -1208,6 +1231,7 @@ int lsb200_finalize_system(lsb200_handle h) {
   h->setup_seconds = ms * 1e-3;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  plan_small(h);
   h->finalized = true;
   return 0;
 }
@@ -1417,6 +1441,112 @@ int lsb200_set_c_dev(lsb200_handle h, const double* c_dev, void* stream) {
 }
 
 // one CG iteration enqueued on the stream (no host synchronisation)
+// ---- small systems: `iters` CG iterations in one persistent cooperative launch (csrc/cg_small.cuh) -----------------------
+constexpr long long SMALL_MAX_NODES = 3000000;  // above: an iteration is bandwidth bound and the four launches stream better
+static TmapArg* small_tmap(lsb200_ctx* h) {     // descriptor of p for the plan's tile shape (as launch_stencil builds it)
+  for (int t = 0; t < 2; ++t)
+    if (h->tma_vec[t] == h->p) return &h->tma_map[t];
+  bool ok = false;
+  switch (h->fz.tyt) {
+#define X(TYT, ST, MINB) case TYT: ok = encode_plane_tiles(h, h->p, MainCfg<4, TYT, ST>::SX, MainCfg<4, TYT, ST>::SY, &h->tma_map[0]); break;
+    LSB_FUSED_CFGS(X)
+#undef X
+  }
+  if (!ok) return nullptr;
+  h->tma_vec[0] = h->p;
+  return &h->tma_map[0];
+}
+
+static int small_grid_of(lsb200_ctx* h, const void* kern, int threads, size_t smem, long long useful) {
+  int per_sm = 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    return 0;
+  }
+  long long grid = (long long)per_sm * h->sm_count;
+  grid = std::min<long long>(grid, SMALL_MAX_CTAS);
+  grid = std::min<long long>(grid, std::max<long long>(useful, h->sm_count));
+  return (int)grid;
+}
+
+// can this handle run the persistent loop, and with how many CTAs (called at the end of finalize)
+static void plan_small(lsb200_ctx* h) {
+  h->small_ok = false;
+  const char* e = getenv("LSB200_PERSIST");
+  const int want = e ? atoi(e) : -1;  // 0: never, 1: whenever possible, default: systems of <= SMALL_MAX_NODES nodes
+  if (want == 0 || h->nranks > 1 || h->deterministic || h->blocks.size() > (size_t)SMALL_MAX_BLOCKS) return;
+  if (want != 1 && h->g.nloc > SMALL_MAX_NODES) return;
+  int coop = 0;
+  if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device) != cudaSuccess || !coop) return;
+  const long long per_cta_nodes = 4096;
+  const long long by_nodes = (h->g.nloc + per_cta_nodes - 1) / per_cta_nodes;
+  int grid = 0;
+  if (h->kind == LSB200_SUPPORT_GRID) {
+    if (!h->fused || !h->want_tma || h->g.pitch % 2 != 0 || !small_tmap(h)) return;
+    const long long nvb = (long long)h->fz.pl.n_box + h->fz.pl.n_xs + h->fz.pl.n_ys;
+    switch (h->fz.tyt) {
+#define X(TYT, ST, MINB) \
+  case TYT: grid = small_grid_of(h, (const void*)k_cg_small_fdi<TYT, ST, MINB>, 32 * TYT, sizeof(double) * MainCfg<4, TYT, ST>::PLANE * ST, std::max(nvb, by_nodes)); break;
+      LSB_FUSED_CFGS(X)
+#undef X
+    }
+  } else {
+    if (!h->p1_tiles || h->p1_tile_cfg != 1) return;
+    const long long nvb = (long long)h->p1_plan.n_bnd_cta + (long long)h->p1_plan.tiles_x * h->p1_plan.tiles_y * h->p1_plan.tiles_z;
+    grid = small_grid_of(h, (const void*)k_cg_small_p1<8, 4, 8>, 256, sizeof(double) * P1TileGeom<8, 4>::ELEMS, std::max(nvb, by_nodes));
+  }
+  if (grid < 1) return;
+  if (!h->small_bar) {
+    if (cudaMalloc(&h->small_bar, 2 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(h->small_bar, 0, 2 * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc(&h->small_slots, sizeof(double) * 2 * SMALL_MAX_CTAS) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+  }
+  h->small_grid = grid;
+  h->small_ok = true;
+}
+
+static int launch_small(lsb200_ctx* h, int iters) {
+  SmallCgArgs a{};
+  a.n = h->g.nloc;
+  a.x = owned_ptr(h, h->x); a.r = owned_ptr(h, h->r); a.p = owned_ptr(h, h->p); a.q = owned_ptr(h, h->q);
+  a.s2 = h->apply_scaling ? owned_ptr(h, h->s2) : nullptr;
+  a.p_all = h->p; a.q_all = h->q;
+  a.nblocks = 0;
+  for (const RowBlock& rb : h->blocks)
+    if (rb.n > 0) a.blocks[a.nblocks++] = rb;
+  a.iters = iters;
+  a.bar = h->small_bar;
+  a.slots = h->small_slots;
+  a.sc = h->sc;
+  if (h->kind == LSB200_SUPPORT_GRID) {
+    SmallFdi f{h->g, make_uni_consts(make_weights(h)), make_weights(h), h->fz.pl, h->ztab};
+    TmapArg* tm = small_tmap(h);
+    if (!tm) return fail(LSB200_ERR_STATE, "no TMA descriptor for the persistent CG loop");
+    void* args[] = {&a, &f, tm};
+    switch (h->fz.tyt) {
+#define X(TYT, ST, MINB)                                                                                                   \
+  case TYT:                                                                                                                \
+    CK(cudaLaunchCooperativeKernel((void*)k_cg_small_fdi<TYT, ST, MINB>, dim3(h->small_grid), dim3(32, TYT), args,          \
+                                   sizeof(double) * MainCfg<4, TYT, ST>::PLANE * ST, h->stream));                          \
+    break;
+      LSB_FUSED_CFGS(X)
+#undef X
+      default: return fail(LSB200_ERR_STATE, "no persistent CG kernel for tile shape %d", h->fz.tyt);
+    }
+  } else {
+    const P1Tables tb{{h->p1_m[0], h->p1_m[1], h->p1_m[2]}, h->p1_table, h->p1_off, h->p1_diag};
+    SmallP1 f{h->g, tb, h->p1_plan, h->p1_w * h->p1_w, h->add_ridge ? h->ridge * h->ridge : 0.0};
+    void* args[] = {&a, &f, &h->p1_cls};
+    CK(cudaLaunchCooperativeKernel((void*)k_cg_small_p1<8, 4, 8>, dim3(h->small_grid), dim3(256), args,
+                                   sizeof(double) * P1TileGeom<8, 4>::ELEMS, h->stream));
+  }
+  h->launches++;
+  return 0;
+}
+
 static int enqueue_iteration(lsb200_ctx* h) {
   const long long n = h->g.nloc;
   const double* s2 = h->apply_scaling ? owned_ptr(h, h->s2) : nullptr;
@@ -1574,7 +1704,9 @@ int lsb200_solve_cg(lsb200_handle h, double rtol, double atol, int64_t maxiter, 
     long long launches_per_batch = 0;
     while (!done) {
       const long long todo = std::min<long long>(batch, maxit - enq);
-      if (want_graph && !graph_tried && enq >= batch && todo == batch) {
+      if (h->small_ok) {
+        if ((rc = launch_small(h, (int)todo))) return rc;
+      } else if (want_graph && !graph_tried && enq >= batch && todo == batch) {
         graph_tried = true;
         const long long l0 = h->launches;
         if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
@@ -1591,7 +1723,9 @@ int lsb200_solve_cg(lsb200_handle h, double rtol, double atol, int64_t maxiter, 
         launches_per_batch = h->launches - l0;
         h->launches = l0;  // nothing ran during the capture
       }
-      if (gexec && todo == batch) {
+      if (h->small_ok) {
+        // enqueued above
+      } else if (gexec && todo == batch) {
         CK(cudaGraphLaunch(gexec, h->stream));
         h->launches += launches_per_batch;
       } else {
@@ -2117,8 +2251,23 @@ int lsb200_time_kernel(lsb200_handle h, int which, int reps, double* seconds_per
   // p = rhs so that the vectors hold representative data
   CK(cudaMemcpyAsync(h->p, h->rhs, sizeof(double) * (size_t)h->g.nall, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemcpyAsync(h->r, h->rhs, sizeof(double) * (size_t)h->g.nall, cudaMemcpyDeviceToDevice, h->stream));
-  // three warm-up launches, then `reps` launches back to back between two events, as inside the CG loop
   float total_ms = 0.f;
+  if (which == 1 && h->small_ok) {
+    // small systems: the iterations of one persistent launch (csrc/cg_small.cuh), as lsb200_solve_cg enqueues them
+    CK(cudaMemcpyAsync(h->sc, h->sc_host, sizeof(CgScalars), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = launch_small(h, 3))) return rc;
+    CK(cudaEventRecord(e0, h->stream));
+    if ((rc = launch_small(h, reps))) return rc;
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&total_ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *seconds_per_launch = total_ms * 1e-3 / reps;
+    h->have_c = false;
+    return 0;
+  }
+  // three warm-up launches, then `reps` launches back to back between two events, as inside the CG loop
   for (int rep = -3; rep < reps; ++rep) {
     if (rep == 0) CK(cudaEventRecord(e0, h->stream));
     // the whole iteration advances the scalars: reset them every time; a single kernel does not
@@ -2129,10 +2278,10 @@ int lsb200_time_kernel(lsb200_handle h, int which, int reps, double* seconds_per
     else if (which == 3 || which == 4) {
       const long long n = h->g.nloc;
       const double* s2 = h->apply_scaling ? owned_ptr(h, h->s2) : nullptr;
-      if (which == 3)
+      if (which == 3)  // alone, without the peers' pushes it would wait for: p.q from the scalar block (peers = null)
         k_cg_update_xr<VEC_NT><<<vec_blocks(h, n), VEC_NT, 0, h->stream>>>(n, owned_ptr(h, h->p), owned_ptr(h, h->q), owned_ptr(h, h->x),
                                                                             owned_ptr(h, h->r), s2, h->partials + 2 * MAX_PARTIALS,
-                                                                            h->counters + 2, h->sc, h->peers);
+                                                                            h->counters + 2, h->sc, nullptr);
       else
         k_cg_update_p<VEC_NT><<<vec_blocks(h, n), VEC_NT, 0, h->stream>>>(n, s2, owned_ptr(h, h->r), owned_ptr(h, h->p), h->sc);
       CKL();

@@ -66,7 +66,8 @@ __device__ __forceinline__ double peer_pull(const PeerTable& pt, const int kind,
   double s = 0.0;
   for (int r = 0; r < pt.nranks; ++r) {
     const volatile unsigned long long* f = &mb->flag[par][kind][r];
-    while (*f != seq) {
+    // bounded: a peer that died must not hang this GPU (the sum is then wrong and the solve fails its residual check)
+    for (long long spin = 0; *f != seq && spin < (1ll << 31); ++spin) {
     }
     __threadfence_system();
     s += *reinterpret_cast<const volatile double*>(&mb->val[par][kind][r]);

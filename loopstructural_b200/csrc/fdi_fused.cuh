@@ -411,31 +411,37 @@ __device__ __forceinline__ double z_face_block(const GridDesc& g, const UniConst
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// TMA = true: the box tiles are staged by the TMA unit (needs VEC16: an even row pitch, and `tmap` describing p);
-// the strips keep cp.async (48-byte rows).
-template <int TYT, int ST, int MINB, bool VEC16, bool TMA = false>
-__global__ void __launch_bounds__(32 * TYT, MINB)
-    k_fdi_fused(const GridDesc g, const UniConsts U, const StencilWeights w, const FusedPlan pl, const double* __restrict__ p,
-                double* __restrict__ q, const double* __restrict__ ztab, double* __restrict__ partials,
-                unsigned int* __restrict__ counter, CgScalars* __restrict__ sc, const int cg_mode,
-                const LSB_GRID_CONSTANT TmapArg tmap) {
+// The work of CTA `bid` of the plan: its part of q = N p, and (return value) this thread's share of p.q.  A device
+// function so that the launch-per-matvec kernel below and the persistent CG kernel of small systems (csrc/cg_small.cuh,
+// which walks the plan's CTAs in a loop) run the same code.  `phases`: TMA only, the parities of the ring's mbarriers,
+// which live as long as the real CTA (initialised when `first`).
+template <int TYT, int ST, bool VEC16, bool TMA>
+__device__ __forceinline__ double fused_cta(const GridDesc& g, const UniConsts& U, const StencilWeights& w, const FusedPlan& pl,
+                                            const double* __restrict__ p, double* __restrict__ q, const double* __restrict__ ztab,
+                                            const TmapArg* tmap_ptr, const int bid, const bool first, unsigned& phases) {
   constexpr int YB = 4;
   using C = MainCfg<YB, TYT, ST>;
   static_assert(ST >= 6, "ring: planes kp-2..kp plus three in flight; the z-face block stages five planes at once");
   static_assert((C::NT + 2 * HALO) * StripGeom<0>::NC <= C::PLANE, "a strip plane must fit a box plane slot");
   LSB_DYN_SMEM(S);
-  __shared__ double red[C::NT / 32];
   __shared__ ZStrip zsm[11];  // strips: z coefficients of the planes next to a z face; [10]: the interior constants
   __shared__ __align__(8) unsigned long long full[TMA ? ST : 1];  // TMA: one mbarrier per ring slot
 
-  if (cg_mode && sc->done) return;
-
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int tid = tx + 32 * ty;
-  const int bid = blockIdx.x;
   double dot = 0.0;
-  const unsigned long long t_begin = tid == 0 ? trace_begin() : 0ull;
 
+  if constexpr (TMA) {
+    if (first) {
+      if (tid == 0) {
+#pragma unroll
+        for (int s2 = 0; s2 < ST; ++s2) mbar_init(&full[s2], 1);
+        mbar_fence_init();
+      }
+      phases = 0;
+      __syncthreads();
+    }
+  }
   if (bid >= pl.n_box) {
     // ---- strip roles (the last block indices: they fill the CTA slots the box tiles leave free)
     if (tid < 10) {
@@ -480,15 +486,8 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
     constexpr int NSLOT = VEC16 ? C::PLANE / 2 : C::PLANE;
     constexpr unsigned PLANE_BYTES = C::PLANE * sizeof(double);
     int off[LD];
-    unsigned phases = 0;  // TMA: parity of the next completion of every slot's mbarrier (bit s = slot s)
     if constexpr (TMA) {
       off[0] = 0;
-      if (tid == 0) {
-#pragma unroll
-        for (int s2 = 0; s2 < ST; ++s2) mbar_init(&full[s2], 1);
-        mbar_fence_init();
-      }
-      __syncthreads();
     } else {
 #pragma unroll
       for (int t = 0; t < LD; ++t) {
@@ -507,7 +506,7 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
       if constexpr (TMA) {
         if (tid == 0) {
           mbar_expect_tx(&full[s], PLANE_BYTES);
-          tma_load_3d(S + s * C::PLANE, &tmap, x0 - HALO, y0 - HALO, k - g.k0 + HALO, &full[s]);
+          tma_load_3d(S + s * C::PLANE, tmap_ptr, x0 - HALO, y0 - HALO, k - g.k0 + HALO, &full[s]);
         }
       } else {
         const double* src = p + (long long)(k - g.k0 + HALO) * g.plane;
@@ -606,12 +605,10 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
       for (int r = 0; r < YB; ++r) {
         if (r < nrows) {
           const double2 pv = lds2(Sp + r * C::SX);
-          if (VEC16) {
-            if (i0 < xlim) {
-              *reinterpret_cast<double2*>(qdst + (long long)r * g.pitch) = make_double2(out[r][0], out[r][1]);
-              dot = fma(pv.x, out[r][0], dot);
-              dot = fma(pv.y, out[r][1], dot);
-            }
+          if (VEC16 && i0 + 1 < xlim) {  // (an odd last column of the box range -- odd nx -- is stored alone below)
+            *reinterpret_cast<double2*>(qdst + (long long)r * g.pitch) = make_double2(out[r][0], out[r][1]);
+            dot = fma(pv.x, out[r][0], dot);
+            dot = fma(pv.y, out[r][1], dot);
           } else {
             if (i0 < xlim) {
               qdst[(long long)r * g.pitch] = out[r][0];
@@ -649,11 +646,28 @@ __global__ void __launch_bounds__(32 * TYT, MINB)
 #undef LSB_FUSED_STEP
     if constexpr (!TMA) cp_async_wait<0>();
   }
+  return dot;
+}
 
-  const double bsum = block_sum<C::NT>(dot, red);
+// TMA = true: the box tiles are staged by the TMA unit (needs VEC16: an even row pitch, and `tmap` describing p);
+// the strips keep cp.async (48-byte rows).
+template <int TYT, int ST, int MINB, bool VEC16, bool TMA = false>
+__global__ void __launch_bounds__(32 * TYT, MINB)
+    k_fdi_fused(const GridDesc g, const UniConsts U, const StencilWeights w, const FusedPlan pl, const double* __restrict__ p,
+                double* __restrict__ q, const double* __restrict__ ztab, double* __restrict__ partials,
+                unsigned int* __restrict__ counter, CgScalars* __restrict__ sc, const int cg_mode,
+                const LSB_GRID_CONSTANT TmapArg tmap) {
+  constexpr int NT = 32 * TYT;
+  __shared__ double red[NT / 32];
+  if (cg_mode && sc->done) return;
+  const int tid = threadIdx.x + 32 * threadIdx.y;
+  const unsigned long long t_begin = tid == 0 ? trace_begin() : 0ull;
+  unsigned phases = 0;
+  const double dot = fused_cta<TYT, ST, VEC16, TMA>(g, U, w, pl, p, q, ztab, &tmap, (int)blockIdx.x, true, phases);
+  const double bsum = block_sum<NT>(dot, red);
   if (tid == 0) trace_end(t_begin, blockIdx.x);
   double total;
-  if (grid_sum_last_block<C::NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total)) sc->pq_part[0] = total;
+  if (grid_sum_last_block<NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total)) sc->pq_part[0] = total;
 }
 
 }  // namespace lsb

@@ -256,25 +256,23 @@ __device__ __forceinline__ double p1_row_taps(const P1ClassTaps& T, const double
   return (a0 + a1) + (a2 + a3);
 }
 
+// The work of CTA `vb` of `nvb` (tiles first, then the boundary-only CTAs): its tile and its share of the boundary nodes;
+// returns this thread's share of p.q.  Shared by k_p1_tiles and the persistent CG kernel of small systems (cg_small.cuh).
 template <int TY, int TZ, int NW>
-__global__ void __launch_bounds__(32 * NW)
-    k_p1_tiles(const GridDesc g, const P1Tables tb, const LSB_GRID_CONSTANT P1ClassTaps T, const P1TilePlan pl, const double w2,
-               const double ridge2, const double* __restrict__ p, double* __restrict__ q, double* __restrict__ partials,
-               unsigned int* __restrict__ counter, CgScalars* __restrict__ sc, const int cg_mode) {
+__device__ __forceinline__ double p1_tiles_cta(const GridDesc& g, const P1Tables& tb, const P1ClassTaps& T, const P1TilePlan& pl,
+                                               const double w2, const double ridge2, const double* __restrict__ p,
+                                               double* __restrict__ q, const int vb, const int nvb) {
   using G = P1TileGeom<TY, TZ>;
   constexpr int NT = 32 * NW, HX = G::HX, SY = G::SY;
   static_assert(TY % 2 == 0 && TZ % 2 == 0, "tiles start on even rows / planes: the class of a row is a compile-time constant");
   LSB_DYN_SMEM(S);
-  __shared__ double red[NT / 32];
-  if (cg_mode && sc->done) return;
   const int tid = threadIdx.x;
   double dot = 0.0;
-  const unsigned long long t_begin = tid == 0 ? trace_begin() : 0ull;
   const int n_tiles = pl.tiles_x * pl.tiles_y * pl.tiles_z;
-  const bool has_tile = (int)blockIdx.x < n_tiles;
+  const bool has_tile = vb < n_tiles;
   int x0 = 0, y0 = 0, z0 = 0;
   if (has_tile) {
-    const int b = (int)blockIdx.x;
+    const int b = vb;
     const int txy = pl.tiles_x * pl.tiles_y;
     const int bz = b / txy, brem = b - bz * txy;
     const int by = brem / pl.tiles_x, bx = brem - by * pl.tiles_x;
@@ -293,7 +291,7 @@ __global__ void __launch_bounds__(32 * NW)
   {
     // ---- this CTA's share of the boundary nodes, while the tile is on its way
     const long long nb = pl.nbz + pl.nby + pl.nbx;
-    for (long long t = (long long)blockIdx.x * NT + tid; t < nb; t += (long long)gridDim.x * NT) {
+    for (long long t = (long long)vb * NT + tid; t < nb; t += (long long)nvb * NT) {
       int i, j, kl;
       p1_boundary_node(g, pl, t, &i, &j, &kl);
       dot += p1_node_generic(g, tb, w2, ridge2, p, q, i, j, kl);
@@ -325,6 +323,20 @@ __global__ void __launch_bounds__(32 * NW)
 #undef LSB_P1_CLASS
     }
   }
+  return dot;
+}
+
+template <int TY, int TZ, int NW>
+__global__ void __launch_bounds__(32 * NW)
+    k_p1_tiles(const GridDesc g, const P1Tables tb, const LSB_GRID_CONSTANT P1ClassTaps T, const P1TilePlan pl, const double w2,
+               const double ridge2, const double* __restrict__ p, double* __restrict__ q, double* __restrict__ partials,
+               unsigned int* __restrict__ counter, CgScalars* __restrict__ sc, const int cg_mode) {
+  constexpr int NT = 32 * NW;
+  __shared__ double red[NT / 32];
+  if (cg_mode && sc->done) return;
+  const int tid = threadIdx.x;
+  const unsigned long long t_begin = tid == 0 ? trace_begin() : 0ull;
+  const double dot = p1_tiles_cta<TY, TZ, NW>(g, tb, T, pl, w2, ridge2, p, q, (int)blockIdx.x, (int)gridDim.x);
   const double bsum = block_sum<NT>(dot, red);
   if (tid == 0) trace_end(t_begin, blockIdx.x);
   double total;

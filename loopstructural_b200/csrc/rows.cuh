@@ -44,18 +44,15 @@ __device__ __forceinline__ void red_add(double* addr, double v) {
 // form a segment, the per-column products a_j t are summed over the segment with shuffles, and the segment's first lane
 // issues ONE non-returning add per column -- the warp-aggregated scatter.  p . q part: sum_r t_r (a_r . p) over owned
 // columns, fixed-order block / grid reduction.
+// rows [vb NT, ...) in steps of nvb NT, one row per thread (tid in [0, NT)); returns this thread's share of p . q
 template <int NT, int K>
-__global__ void __launch_bounds__(NT)
-    k_rows_normal(const GridDesc g, const RowBlock rb, const double* __restrict__ p, double* __restrict__ q,
-                  double* __restrict__ partials, unsigned int* __restrict__ counter, CgScalars* __restrict__ sc,
-                  const int cg_mode, const int first) {
-  __shared__ double red[NT / 32];
-  if (cg_mode && sc->done) return;
+__device__ __forceinline__ double rows_normal_cta(const GridDesc& g, const RowBlock& rb, const double* __restrict__ p,
+                                                  double* __restrict__ q, const int tid, const int vb, const int nvb) {
   double dot = 0.0;
-  const unsigned lane = threadIdx.x & 31u;
-  const long long stride = (long long)gridDim.x * NT;
-  for (long long base = blockIdx.x * (long long)NT; base < rb.n; base += stride) {  // block-uniform trip count
-    const long long r = base + threadIdx.x;
+  const unsigned lane = (unsigned)tid & 31u;
+  const long long stride = (long long)nvb * NT;
+  for (long long base = vb * (long long)NT; base < rb.n; base += stride) {  // block-uniform trip count
+    const long long r = base + tid;
     const bool active = r < rb.n;
     int c[K];
     double a[K];
@@ -96,6 +93,17 @@ __global__ void __launch_bounds__(NT)
       if (!same && c[j] >= 0 && v != 0.0 && owned(g, c[j])) red_add(q + c[j], v);
     }
   }
+  return dot;
+}
+
+template <int NT, int K>
+__global__ void __launch_bounds__(NT)
+    k_rows_normal(const GridDesc g, const RowBlock rb, const double* __restrict__ p, double* __restrict__ q,
+                  double* __restrict__ partials, unsigned int* __restrict__ counter, CgScalars* __restrict__ sc,
+                  const int cg_mode, const int first) {
+  __shared__ double red[NT / 32];
+  if (cg_mode && sc->done) return;
+  const double dot = rows_normal_cta<NT, K>(g, rb, p, q, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
   const double bsum = block_sum<NT>(dot, red);
   double total;
   if (grid_sum_last_block<NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total)) {
@@ -105,14 +113,10 @@ __global__ void __launch_bounds__(NT)
 
 // generic width (blocks wider than 16): one thread per row, one non-returning add per entry
 template <int NT>
-__global__ void __launch_bounds__(NT)
-    k_rows_normal_wide(const GridDesc g, const RowBlock rb, const double* __restrict__ p, double* __restrict__ q,
-                       double* __restrict__ partials, unsigned int* __restrict__ counter, CgScalars* __restrict__ sc,
-                       const int cg_mode, const int first) {
-  __shared__ double red[NT / 32];
-  if (cg_mode && sc->done) return;
+__device__ __forceinline__ double rows_normal_wide_cta(const GridDesc& g, const RowBlock& rb, const double* __restrict__ p,
+                                                       double* __restrict__ q, const int tid, const int vb, const int nvb) {
   double dot = 0.0;
-  for (long long r = blockIdx.x * (long long)NT + threadIdx.x; r < rb.n; r += (long long)gridDim.x * NT) {
+  for (long long r = vb * (long long)NT + tid; r < rb.n; r += (long long)nvb * NT) {
     double t = 0.0, town = 0.0;
     for (int j = 0; j < rb.k; ++j) {
       const int c = rb.cols[j * rb.n + r];
@@ -131,6 +135,17 @@ __global__ void __launch_bounds__(NT)
       }
     }
   }
+  return dot;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+    k_rows_normal_wide(const GridDesc g, const RowBlock rb, const double* __restrict__ p, double* __restrict__ q,
+                       double* __restrict__ partials, unsigned int* __restrict__ counter, CgScalars* __restrict__ sc,
+                       const int cg_mode, const int first) {
+  __shared__ double red[NT / 32];
+  if (cg_mode && sc->done) return;
+  const double dot = rows_normal_wide_cta<NT>(g, rb, p, q, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
   const double bsum = block_sum<NT>(dot, red);
   double total;
   if (grid_sum_last_block<NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total)) {

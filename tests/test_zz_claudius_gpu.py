@@ -13,7 +13,12 @@ import golden_helpers as H
 pytestmark = pytest.mark.gpu
 
 
-def test_claudius_quickstart_solve_and_evaluation():
+def test_claudius_quickstart_solve_and_evaluation(monkeypatch):
+    # The reference's last residual is 0.988 of the stopping threshold: which iterate a correct CG run stops at is decided
+    # by rounding, i.e. by the order of the p.q partial sums, i.e. by the launch plan.  The plan is normally chosen by timing
+    # (not repeatable from run to run); this comparison at the DEFAULT tolerance pins the planner's default plan.  The
+    # rtol 1e-10 comparison below does not depend on it.
+    monkeypatch.setenv("LSB200_AUTOTUNE", "0")
     from loopstructural_b200 import build
     from loopstructural_b200.interpolators import B200FiniteDifferenceInterpolator, Support
 
