@@ -134,6 +134,12 @@ struct lsb200_ctx {
   PeerMailbox* mailbox = nullptr;      // this rank's mailbox (cudaMalloc, exported by cudaIpcGetMemHandle)
   PeerTable peer_host{};               // peers' mailboxes as mapped here
   PeerTable* peers = nullptr;          // device copy of peer_host
+  // halo planes of p over peer memory (cg.cuh): the neighbours' p vectors as mapped here ([0] below, [1] above) and the
+  // position of the halo planes this rank fills in them; null = ncclSend / ncclRecv
+  std::vector<int> slab_k;             // [k0, k1) of every rank
+  double* nb_p_raw[2] = {nullptr, nullptr};
+  double* nb_halo[2] = {nullptr, nullptr};
+  bool peer_halo = false;
   unsigned long long solve_epoch = 0;
   int cz = 0;              // k_fdi_normal (grids too small for box tiles): z chunk and grid
   dim3 sgrid;
@@ -649,6 +655,8 @@ int lsb200_destroy(lsb200_handle h) {
   cudaFree(h->ztab);
   for (int r = 0; r < h->peer_host.nranks; ++r)
     if (h->peers && r != h->rank && h->peer_host.box[r]) cudaIpcCloseMemHandle(h->peer_host.box[r]);
+  for (int side = 0; side < 2; ++side)
+    if (h->nb_p_raw[side]) cudaIpcCloseMemHandle(h->nb_p_raw[side]);
   cudaFree(h->peers);
   cudaFree(h->mailbox);
   if (h->comm) nccl::CommDestroy(h->comm);
@@ -1270,6 +1278,7 @@ int lsb200_comm_init(lsb200_handle h, const unsigned char nccl_id[128], int rank
     CK(cudaMemcpyAsync(hk.data(), d_k, sizeof(int) * 2 * nranks, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(d_k);
+    h->slab_k = hk;
     for (int r = 0; r < nranks; ++r) {
       const int want = r == 0 ? 0 : hk[2 * (r - 1) + 1];
       if (hk[2 * r] != want || (r == nranks - 1 && hk[2 * r + 1] != h->g.nz))
@@ -1327,6 +1336,51 @@ int lsb200_comm_init(lsb200_handle h, const unsigned char nccl_id[128], int rank
       h->peer_host = pt;
       CK(cudaMalloc(&h->peers, sizeof(PeerTable)));
       CK(cudaMemcpy(h->peers, &pt, sizeof(PeerTable), cudaMemcpyHostToDevice));
+      // the neighbours' p vectors, for the halo planes (LSB200_PEER_HALO=0 keeps ncclSend / ncclRecv).  Collective: every
+      // rank allocates its vectors now and shares the handle of p; all must succeed or none uses it.
+      static const bool want_halo = !(getenv("LSB200_PEER_HALO") && atoi(getenv("LSB200_PEER_HALO")) == 0);
+      bool hok = want_halo && h->g.nzl >= 3 * HALO && h->g.plane % 2 == 0 && ensure_vectors(h) == 0;
+      cudaIpcMemHandle_t pm;
+      memset(&pm, 0, sizeof(pm));
+      hok = hok && cudaIpcGetMemHandle(&pm, h->p - h->guard) == cudaSuccess;
+      if (!hok) memset(&pm, 0, sizeof(pm));
+      std::vector<cudaIpcMemHandle_t> pall((size_t)nranks);
+      char* d_p = nullptr;
+      CK(cudaMalloc(&d_p, sizeof(pm) * (nranks + 1)));
+      CK(cudaMemcpyAsync(d_p + sizeof(pm) * nranks, &pm, sizeof(pm), cudaMemcpyHostToDevice, h->stream));
+      NCK(nccl::AllGather(d_p + sizeof(pm) * nranks, d_p, sizeof(pm), nccl::Int8, h->comm, h->stream));
+      CK(cudaMemcpyAsync(pall.data(), d_p, sizeof(pm) * nranks, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      cudaFree(d_p);
+      for (int r = 0; r < nranks; ++r) {
+        bool zero = true;
+        for (size_t t = 0; t < sizeof(pm); ++t) zero = zero && reinterpret_cast<const char*>(&pall[r])[t] == 0;
+        hok = hok && !zero;
+      }
+      if (hok) {
+        for (int side = 0; side < 2 && hok; ++side) {
+          const int nb = side == 0 ? rank - 1 : rank + 1;
+          if (nb < 0 || nb >= nranks) continue;
+          void* ptr = nullptr;
+          if (cudaIpcOpenMemHandle(&ptr, pall[nb], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); hok = false; break; }
+          h->nb_p_raw[side] = (double*)ptr;
+          // same plane size on every rank -> same guard; the rank below receives its UPPER halo planes (stored planes
+          // nzl' + 2, nzl' + 3), the rank above its LOWER ones (stored planes 0, 1)
+          const long long nb_nzl = h->slab_k[2 * nb + 1] - h->slab_k[2 * nb];
+          h->nb_halo[side] = (double*)ptr + h->guard + (side == 0 ? (nb_nzl + HALO) * h->g.plane : 0);
+        }
+      }
+      int* d_ok2 = nullptr;
+      CK(cudaMalloc(&d_ok2, sizeof(int) * (nranks + 1)));
+      const int my_ok2 = hok ? 1 : 0;
+      std::vector<int> oks2((size_t)nranks);
+      CK(cudaMemcpyAsync(d_ok2 + nranks, &my_ok2, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      NCK(nccl::AllGather(d_ok2 + nranks, d_ok2, sizeof(int), nccl::Int8, h->comm, h->stream));
+      CK(cudaMemcpyAsync(oks2.data(), d_ok2, sizeof(int) * nranks, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      cudaFree(d_ok2);
+      for (int r = 0; r < nranks; ++r) hok = hok && oks2[r] == 1;
+      h->peer_halo = hok;
     } else {
       for (int r = 0; r < nranks; ++r)
         if (r != rank && pt.box[r]) cudaIpcCloseMemHandle(pt.box[r]);
@@ -1560,16 +1614,33 @@ static int enqueue_iteration(lsb200_ctx* h) {
                                                                           owned_ptr(h, h->p) + off, h->sc);
       h->launches++;
     };
-    upd(0, edge);
-    upd(n - edge, edge);
-    CKL();
-    CK(cudaEventRecord(h->ev_fork, h->stream));
-    CK(cudaStreamWaitEvent(h->side[1], h->ev_fork, 0));
-    if ((rc = halo_exchange(h, h->p, h->side[1]))) return rc;
-    CK(cudaEventRecord(h->ev_join[1], h->side[1]));
-    upd(edge, n - 2 * edge);
-    CKL();
-    CK(cudaStreamWaitEvent(h->stream, h->ev_join[1], 0));
+    if (h->peer_halo) {
+      // the edge planes go straight into the neighbours' halo planes (cg.cuh), the wait sits in front of the matvec
+      auto upd_edge = [&](long long off, int side) {
+        if (!h->nb_halo[side]) { upd(off, edge); return; }
+        k_cg_update_p_edge<VEC_NT><<<vec_blocks(h, edge), VEC_NT, 0, h->stream>>>(
+            edge, s2 ? s2 + off : nullptr, owned_ptr(h, h->r) + off, owned_ptr(h, h->p) + off, h->nb_halo[side],
+            h->peer_host.box[side == 0 ? h->rank - 1 : h->rank + 1], side == 0 ? 1 : 0, h->counters + 5 + side, h->sc);
+        h->launches++;
+      };
+      upd_edge(0, 0);         // my lowest planes are the upper halo of the rank below: it receives them "from above"
+      upd_edge(n - edge, 1);  // my highest planes are the lower halo of the rank above: "from below"
+      upd(edge, n - 2 * edge);
+      k_cg_halo_wait<<<1, 32, 0, h->stream>>>(h->sc, h->mailbox, h->rank > 0 ? 1 : 0, h->rank < h->nranks - 1 ? 1 : 0);
+      CKL();
+      h->launches++;
+    } else {
+      upd(0, edge);
+      upd(n - edge, edge);
+      CKL();
+      CK(cudaEventRecord(h->ev_fork, h->stream));
+      CK(cudaStreamWaitEvent(h->side[1], h->ev_fork, 0));
+      if ((rc = halo_exchange(h, h->p, h->side[1]))) return rc;
+      CK(cudaEventRecord(h->ev_join[1], h->side[1]));
+      upd(edge, n - 2 * edge);
+      CKL();
+      CK(cudaStreamWaitEvent(h->stream, h->ev_join[1], 0));
+    }
   } else {
     k_cg_update_p<VEC_NT><<<vec_blocks(h, n), VEC_NT, 0, h->stream>>>(n, s2, owned_ptr(h, h->r), owned_ptr(h, h->p), h->sc);
     CKL();

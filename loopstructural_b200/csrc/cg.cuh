@@ -41,6 +41,7 @@ constexpr int PEER_MAX_RANKS = 16;
 struct PeerMailbox {
   double val[2][2][PEER_MAX_RANKS];                 // [parity][kind: 0 = p.q, 1 = rho][writer rank]
   unsigned long long flag[2][2][PEER_MAX_RANKS];    // sequence number of the iteration the value belongs to
+  unsigned long long halo[2][2];                    // [parity][0: from the rank below, 1: from the rank above]: the halo planes of p of that iteration have landed
 };
 struct PeerTable {
   PeerMailbox* box[PEER_MAX_RANKS];  // box[r]: rank r's mailbox as mapped into this process (box[rank] = the local one)
@@ -117,6 +118,62 @@ __global__ void __launch_bounds__(NT)
     const long long i = n - 1;
     p[i] = (s2 ? s2[i] * r[i] : r[i]) + beta * p[i];
   }
+}
+
+// ---- halo planes of p over peer memory ------------------------------------------------------------------------------
+// Round 1 (and this round's first half) shipped the two edge planes of p with ncclSend / ncclRecv on a side stream "while
+// the interior planes are updated" -- but the NCCL kernel needs CTA slots the interior update (a grid that fills every
+// SM) does not give up, so the exchange ran AFTER it: +80 us per iteration at 2 ranks (profiles/r2y_bench_2gpu.json).
+// Here the kernel that updates an edge of p stores every value twice, into its own vector and into the halo planes of the
+// neighbour (that rank's p, mapped through cudaIpc), and the last of its CTAs raises a flag in the neighbour's mailbox;
+// the neighbour waits for its two flags in a one-warp kernel in front of its matvec.  No launch of a communication library
+// inside the iteration.  A rank may overwrite a neighbour's halo planes as soon as it has this iteration's scalars: every
+// rank pushed its part of rho after its own matvec had read them.
+template <int NT>
+__global__ void __launch_bounds__(NT)
+    k_cg_update_p_edge(const long long n, const double* __restrict__ s2, const double* __restrict__ r, double* __restrict__ p,
+                       double* __restrict__ nb_halo, PeerMailbox* __restrict__ nb_box, const int from, unsigned int* __restrict__ counter,
+                       const CgScalars* __restrict__ sc) {
+  if (sc->done) return;
+  const double beta = sc->beta;
+  const long long n2 = n >> 1;  // n = HALO * plane, plane even: the caller checks
+  const double2* r2 = reinterpret_cast<const double2*>(r);
+  const double2* s22 = reinterpret_cast<const double2*>(s2);
+  double2* p2 = reinterpret_cast<double2*>(p);
+  double2* h2 = reinterpret_cast<double2*>(nb_halo);
+  for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < n2; i += (long long)gridDim.x * NT) {
+    double2 rv = r2[i], pv = p2[i];
+    if (s2) {
+      const double2 sv = s22[i];
+      rv.x *= sv.x;
+      rv.y *= sv.y;
+    }
+    pv.x = rv.x + beta * pv.x;
+    pv.y = rv.y + beta * pv.y;
+    p2[i] = pv;
+    h2[i] = pv;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicInc(counter, gridDim.x - 1);
+    if (t == gridDim.x - 1) {  // every CTA's stores are out: tell the neighbour
+      __threadfence_system();
+      const unsigned long long seq = sc->epoch + (unsigned long long)sc->iter + 1ull;
+      *reinterpret_cast<volatile unsigned long long*>(&nb_box->halo[(int)(seq & 1ull)][from]) = seq;
+    }
+  }
+}
+
+// in front of the matvec: until the neighbours' halo planes of this iteration have landed.  <<<1, 32>>>
+__global__ void k_cg_halo_wait(const CgScalars* sc, const PeerMailbox* mine, const int has_lo, const int has_hi) {
+  if (sc->done || threadIdx.x > 1) return;
+  if ((threadIdx.x == 0 && !has_lo) || (threadIdx.x == 1 && !has_hi)) return;
+  const unsigned long long seq = sc->epoch + (unsigned long long)sc->iter + 1ull;
+  const volatile unsigned long long* f = &mine->halo[(int)(seq & 1ull)][threadIdx.x];
+  for (long long spin = 0; *f != seq && spin < (1ll << 31); ++spin) {
+  }
+  __threadfence_system();
 }
 
 // x += alpha p ; r -= alpha q ; rho_new = r . S^2 r

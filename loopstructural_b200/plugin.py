@@ -712,6 +712,36 @@ def _make_scalar_field(stock):
     return scalar_field
 
 
+def _make_gradient_norm_scalar_field(stock):
+    def gradient_norm_scalar_field(self, bounding_box=None):
+        """BaseFeature.gradient_norm_scalar_field (LS/modelling/features/_base_geological_feature.py:390-426): the node
+        values are |grad f| on BoundingBox.regular_grid(local=False, order='F') -- the world gradient on that lattice from
+        lsb200_eval_lattice (coordinates generated in the kernel, gradients rotated back to world axes there) when the
+        feature is a plain one solved by the engine; the stock method otherwise."""
+        src = None
+        if type(self).__name__ == "GeologicalFeature" and len(getattr(self, "regions", [])) == 0:
+            src = _solved_grid_field(self, kinds=("grid", "tetmesh"))
+        if src is None:
+            return stock(self, bounding_box)
+        from LoopStructural.geometry import StructuredGrid
+
+        if bounding_box is None:
+            if self.model is None:
+                raise ValueError("Must specify bounding box")
+            bounding_box = self.model.bounding_box
+        grid = StructuredGrid(origin=bounding_box.origin, step_vector=bounding_box.step_vector, nsteps=bounding_box.nsteps,
+                              name=self.name)
+        eng, w2l = src
+        g = eng.evaluate_lattice(np.asarray(bounding_box.origin, dtype=float), np.asarray(bounding_box.maximum, dtype=float),
+                                 np.asarray(bounding_box.nsteps), order="F", gradient=True, world_to_local=w2l)
+        grid.properties[self.name] = np.linalg.norm(g, axis=1)
+        centres = bounding_box.reproject(bounding_box.cell_centres(order="F"))
+        grid.cell_properties[self.name] = np.linalg.norm(self.evaluate_gradient(centres), axis=1)
+        return grid
+
+    return gradient_norm_scalar_field
+
+
 def _fault_chain_of(feature):
     """(frames, profiles, displacements, steps) of the faults that cut ``feature`` when every one of them can run on the
     engine, else None."""
@@ -783,8 +813,10 @@ def _install_feature_patch():
     if "feature_stock" not in _installed:
         _installed["feature_stock"] = (BaseFeature, BaseFeature.scalar_field)
         _installed["apply_faults_stock"] = BaseFeature._apply_faults
+        _installed["gradient_norm_stock"] = BaseFeature.gradient_norm_scalar_field
     cls, stock = _installed["feature_stock"]
     cls.scalar_field = _make_scalar_field(stock)
+    cls.gradient_norm_scalar_field = _make_gradient_norm_scalar_field(_installed["gradient_norm_stock"])
     cls._apply_faults = _make_apply_faults(_installed["apply_faults_stock"])
     try:
         from LoopStructural.modelling.features._geological_feature import GeologicalFeature
@@ -847,6 +879,7 @@ def uninstall():
         cls, stock = _installed["feature_stock"]
         cls.scalar_field = stock
         cls._apply_faults = _installed["apply_faults_stock"]
+        cls.gradient_norm_scalar_field = _installed["gradient_norm_stock"]
     if "evaluate_value_stock" in _installed:
         gcls, gstock = _installed["evaluate_value_stock"]
         gcls.evaluate_value = gstock

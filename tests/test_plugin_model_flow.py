@@ -166,6 +166,8 @@ def test_foliation_through_the_model_with_the_b200_solver_matches_the_stock_solv
     c_b200 = np.array(it.c)
     field = model["strati"].scalar_field()  # regular-grid export: node values from the lattice entry point
     assert eng.lattice_calls == 1
+    gnorm = model["strati"].gradient_norm_scalar_field()  # |grad f| on the same lattice: the gradient variant of the entry point
+    assert eng.lattice_calls == 2
 
     from loopstructural_b200 import plugin
 
@@ -181,6 +183,11 @@ def test_foliation_through_the_model_with_the_b200_solver_matches_the_stock_solv
     assert type(stock["strati"]).scalar_field.__qualname__ == "BaseFeature.scalar_field"
     for got, ref in ((field.properties, stock_field.properties), (field.cell_properties, stock_field.cell_properties)):
         np.testing.assert_allclose(np.asarray(got["strati"], float), np.asarray(ref["strati"], float), rtol=0, atol=1e-9 * rng_,
+                                   equal_nan=True)
+    stock_gnorm = stock["strati"].gradient_norm_scalar_field()
+    assert type(stock["strati"]).gradient_norm_scalar_field.__qualname__ == "BaseFeature.gradient_norm_scalar_field"
+    for got, ref in ((gnorm.properties, stock_gnorm.properties), (gnorm.cell_properties, stock_gnorm.cell_properties)):
+        np.testing.assert_allclose(np.asarray(got["strati"], float), np.asarray(ref["strati"], float), rtol=0, atol=1e-11,
                                    equal_nan=True)
 
 
