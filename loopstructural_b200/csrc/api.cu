@@ -900,7 +900,6 @@ int lsb200_add_field_orthogonal_rows(lsb200_handle h, lsb200_handle other, const
                                      int64_t element_step, double weight, double b, int64_t* n_rows_out) {
   if (!h) return fail(LSB200_ERR_ARG, "null handle");
   if (n_rows_out) *n_rows_out = 0;
-  if (h->kind != LSB200_SUPPORT_GRID) return fail(LSB200_ERR_STATE, "field-orthogonality rows need a grid handle");
   if (element_step < 1) return fail(LSB200_ERR_ARG, "element_step must be >= 1");
   if (other == h) return fail(LSB200_ERR_ARG, "a field cannot be made orthogonal to itself");
   FrameField F;
@@ -908,6 +907,39 @@ int lsb200_add_field_orthogonal_rows(lsb200_handle h, lsb200_handle other, const
   if (rc) return rc;
   if (other->device != h->device) return fail(LSB200_ERR_ARG, "the two handles live on different devices");
   CK(cudaSetDevice(h->device));
+  if (h->kind == LSB200_SUPPORT_TETMESH) {
+    // P1 twin: barycentres of the tets e = 0, step, 2 step, ... and the other field's normalised gradient there, made on
+    // the device (k_p1_barycentre_vectors), then the tangent family of k_p1_point_rows (weight w * tet volume)
+    const long long n_el = 5LL * (h->g.nx - 1) * (h->g.ny - 1) * (h->g.nz - 1);
+    const long long n = (n_el + element_step - 1) / element_step;
+    if (n == 0) return 0;
+    double* dd = nullptr;
+    CK(cudaMallocAsync(&dd, sizeof(double) * 7 * n, h->stream));
+    CK(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * 4, h->stream));
+    RowBlock rb{};
+    rc = alloc_block(h, rb, n, 4);
+    if (rc) return rc;
+    const int nb = (int)std::min<long long>((n + 127) / 128, 4096);
+    if (F.kind == LSB200_SUPPORT_TETMESH) k_p1_barycentre_vectors<true><<<nb, 128, 0, h->stream>>>(h->g, F, (long long)element_step, n, b, dd, h->status);
+    else k_p1_barycentre_vectors<false><<<nb, 128, 0, h->stream>>>(h->g, F, (long long)element_step, n, b, dd, h->status);
+    CKL();
+    k_p1_point_rows<<<nb, 128, 0, h->stream>>>(h->g, LSB200_ROWS_TANGENT, n, dd, 7, weight, rb, 0, h->status);
+    CKL();
+    h->launches += 2;
+    unsigned long long st[3];
+    CK(cudaMemcpyAsync(st, h->status, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    pool_free(h, dd);
+    if (st[2]) {  // a NaN among the vectors: add_constraints_to_least_squares drops the WHOLE family (LI/_discrete_interpolator.py:357-359)
+      free_block(h, rb);
+      return 0;
+    }
+    if (n_rows_out) *n_rows_out = (int64_t)st[0];
+    h->rows_kept += (long long)st[0];
+    h->pending.push_back(rb);
+    h->finalized = false;
+    return 0;
+  }
   const long long n_el = (long long)(h->g.nx - 1) * (h->g.ny - 1) * (h->g.nz - 1);
   const long long n = (n_el + element_step - 1) / element_step;  // element_idx[::step]
   if (n == 0) return 0;
@@ -922,9 +954,13 @@ int lsb200_add_field_orthogonal_rows(lsb200_handle h, lsb200_handle other, const
     k_fdi_field_orthogonal_rows<false><<<nb, 128, 0, h->stream>>>(h->g, F, (long long)element_step, n, weight, b, rb, 0, h->status);
   CKL();
   h->launches++;
-  unsigned long long st[2];
+  unsigned long long st[3];
   CK(cudaMemcpyAsync(st, h->status, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (st[2]) {  // a NaN gradient (outside a tet-mesh source): the reference drops the whole family
+    free_block(h, rb);
+    return 0;
+  }
   if (n_rows_out) *n_rows_out = (int64_t)st[0];
   h->rows_kept += (long long)st[0];
   h->pending.push_back(rb);
@@ -1650,7 +1686,7 @@ static int enqueue_iteration(lsb200_ctx* h) {
   if ((rc = apply_normal_dev(h, h->p, h->q, 3, 1))) return rc;
   if (h->nranks > 1) {
     if (h->peers) {
-      k_cg_push_pq<<<1, 32, 0, h->stream>>>(h->sc, h->peer_host);
+      k_cg_sync_pq<<<1, 32, 0, h->stream>>>(h->sc, h->peer_host);
       CKL();
       h->launches++;
     } else {

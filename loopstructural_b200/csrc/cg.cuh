@@ -60,32 +60,41 @@ __device__ __forceinline__ void peer_push(const PeerTable& pt, const int kind, c
   }
 }
 
-// sum of all ranks' partials of reduction (kind, seq), in rank order; every calling thread gets the value
-__device__ __forceinline__ double peer_pull(const PeerTable& pt, const int kind, const unsigned long long seq) {
+// sum of all ranks' partials of reduction (kind, seq), in rank order; ONE WARP calls it (lane r waits for rank r's flag, so
+// the waits overlap; one system-scope fence for the warp), every lane gets the value.  (The first version polled the ranks
+// one after the other from thread 0 of EVERY block of the x / r update: 1184 blocks x 8 ranks x a system-scope fence per
+// iteration -- at 8 ranks a real solve ran at 502 us per iteration against 316 us of kernels, profiles/r2aa.)
+__device__ __forceinline__ double peer_pull_warp(const PeerTable& pt, const int kind, const unsigned long long seq) {
   const PeerMailbox* mb = pt.box[pt.rank];
   const int par = (int)(seq & 1ull);
-  double s = 0.0;
-  for (int r = 0; r < pt.nranks; ++r) {
-    const volatile unsigned long long* f = &mb->flag[par][kind][r];
+  const int lane = threadIdx.x & 31;
+  if (lane < pt.nranks) {
+    const volatile unsigned long long* f = &mb->flag[par][kind][lane];
     // bounded: a peer that died must not hang this GPU (the sum is then wrong and the solve fails its residual check)
     for (long long spin = 0; *f != seq && spin < (1ll << 31); ++spin) {
     }
-    __threadfence_system();
-    s += *reinterpret_cast<const volatile double*>(&mb->val[par][kind][r]);
   }
+  __syncwarp();
+  __threadfence_system();
+  const double v = lane < pt.nranks ? *reinterpret_cast<const volatile double*>(&mb->val[par][kind][lane]) : 0.0;
+  double s = 0.0;
+  for (int r = 0; r < pt.nranks; ++r) s += __shfl_sync(0xffffffffu, v, r);  // rank order: the same bits on every rank
   return s;
 }
 
-// after the matvec: this rank's p.q (all parts) to every peer.  <<<1, 32>>>
-__global__ void k_cg_push_pq(CgScalars* sc, const PeerTable pt) {
+// after the matvec: this rank's p.q (all parts) to every peer, then everybody's into sc->pq.  <<<1, 32>>>
+__global__ void k_cg_sync_pq(CgScalars* sc, const PeerTable pt) {
   if (sc->done) return;
+  const unsigned long long seq = sc->epoch + (unsigned long long)sc->iter + 1ull;
   const double v = (((sc->pq_part[0] + sc->pq_part[2]) + sc->pq_part[3]) + sc->pq_part[4]) + sc->pq_part[1];
-  peer_push(pt, 0, sc->epoch + (unsigned long long)sc->iter + 1ull, v);
+  peer_push(pt, 0, seq, v);
+  const double pq = peer_pull_warp(pt, 0, seq);
+  if (threadIdx.x == 0) sc->pq = pq;
 }
 // after the x / r update has pushed its partial of rho: gather, advance the scalar state.  <<<1, 32>>>
 __global__ void k_cg_pull_rho(CgScalars* sc, const PeerTable pt) {
   if (sc->done) return;
-  const double rho_new = peer_pull(pt, 1, sc->epoch + (unsigned long long)sc->iter + 1ull);
+  const double rho_new = peer_pull_warp(pt, 1, sc->epoch + (unsigned long long)sc->iter + 1ull);
   if (threadIdx.x == 0) {
     sc->rho_new = rho_new;
     cg_scalar_step(sc, rho_new);
@@ -153,9 +162,9 @@ __global__ void __launch_bounds__(NT)
     p2[i] = pv;
     h2[i] = pv;
   }
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();  // cumulative: the CTA's stores, ordered before this thread by the barrier, are out
     const unsigned int t = atomicInc(counter, gridDim.x - 1);
     if (t == gridDim.x - 1) {  // every CTA's stores are out: tell the neighbour
       __threadfence_system();
@@ -184,18 +193,12 @@ __global__ void __launch_bounds__(NT)
                    double* __restrict__ partials, unsigned int* __restrict__ counter, CgScalars* __restrict__ sc,
                    const PeerTable* __restrict__ peers) {
   __shared__ double red[NT / 32];
-  __shared__ double s_pq;
   if (sc->done) return;
   double pq;
   if (sc->nranks == 1) {
     pq = (((sc->pq_part[0] + sc->pq_part[2]) + sc->pq_part[3]) + sc->pq_part[4]) + sc->pq_part[1];
-  } else if (peers) {
-    // every block waits for the partials of all ranks in its own mailbox (k_cg_push_pq of each rank) and sums them
-    if (threadIdx.x == 0) s_pq = peer_pull(*peers, 0, sc->epoch + (unsigned long long)sc->iter + 1ull);
-    __syncthreads();
-    pq = s_pq;
   } else {
-    pq = sc->pq;
+    pq = sc->pq;  // k_cg_sync_pq (peer mailboxes) or ncclAllReduce put the sum of all ranks there
   }
   const double alpha = sc->rho / pq;
   const long long n2 = n >> 1;

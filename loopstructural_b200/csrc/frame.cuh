@@ -327,13 +327,59 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// The P1 / TetMesh twin: install_gradient_constraint hands TetMesh.barycentre[::estep] (mean of the four vertices,
+// LC/supports/_3d_structured_tetra.py:106-118) and the other feature's normalised gradient there to
+// P1Interpolator.add_gradient_orthogonal_constraints (LI/_p1interpolator.py:248-296), which is the tangent family of
+// k_p1_point_rows (v_hat . grad phi = b, weight w * tet volume).  This kernel makes that family's input on the device --
+// row r: x,y,z of the barycentre of tet r * estep, the normalised gradient of `other` there, b -- and k_p1_point_rows
+// turns it into rows; nothing of size N crosses the bus.
+template <bool TET>
+LSB_HD void p1_barycentre_vector(const GridDesc& g, const FrameField& other, const long long e, const double bval, double* d) {
+  const int ncx = g.nx - 1, ncy = g.ny - 1;
+  const long long cell_id = e / 5;
+  const int local = (int)(e - 5 * cell_id);
+  const int cell[3] = {(int)(cell_id % ncx), (int)((cell_id / ncx) % ncy), (int)(cell_id / ((long long)ncx * ncy))};
+  const bool even = ((cell[0] + cell[1] + cell[2]) & 1) == 0;
+  double x[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int corner = tet_corner(even, local, s);
+    const int off[3] = {corner & 1, (corner >> 1) & 1, (corner >> 2) & 1};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) x[a] = rn_add(x[a], rn_add(g.origin[a], rn_mul(g.step[a], (double)(cell[a] + off[a]))));
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) x[a] = x[a] / 4.0;
+  double v[3];
+  frame_field_at<TET>(other, x, v);
+  const double n1 = sqrt(rn_add(rn_add(rn_mul(v[0], v[0]), rn_mul(v[1], v[1])), rn_mul(v[2], v[2])));
+  if (n1 > 0.0) { v[0] /= n1; v[1] /= n1; v[2] /= n1; }
+  d[0] = x[0]; d[1] = x[1]; d[2] = x[2];
+  d[3] = v[0]; d[4] = v[1]; d[5] = v[2];
+  d[6] = bval;
+}
+
+template <bool TET>
+__global__ void __launch_bounds__(128)
+    k_p1_barycentre_vectors(const GridDesc g, const FrameField other, const long long estep, const long long n_rows,
+                            const double bval, double* __restrict__ data, unsigned long long* __restrict__ status) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x) {
+    double* d = data + 7 * r;
+    p1_barycentre_vector<TET>(g, other, r * estep, bval, d);
+    if (d[3] != d[3] || d[4] != d[4] || d[5] != d[5]) atomicAdd(status + 2, 1ull);  // outside a tet-mesh source: see the caller
+  }
+}
+
 template <bool TET>
 __global__ void __launch_bounds__(128)
     k_fdi_field_orthogonal_rows(const GridDesc g, const FrameField other, const long long estep, const long long n_rows,
                                 const double weight, const double bval, const RowBlock rb, const long long row0,
                                 unsigned long long* __restrict__ status) {
-  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x)
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x) {
     if (field_orthogonal_row_store<TET>(g, other, estep, weight, bval, rb, row0, r)) atomicAdd(status, 1ull);
+    const double a0 = rb.vals[row0 + r];
+    if (a0 != a0) atomicAdd(status + 2, 1ull);  // NaN gradient of the other field (outside a tet-mesh source)
+  }
 }
 
 // the three values (n,3) and, when grad_out != nullptr, the gradient (n,3) of field `gfield`: one pass over xyz

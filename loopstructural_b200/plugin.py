@@ -615,8 +615,8 @@ def _make_fault_methods(stock_apply, stock_displacement):
 
 def _solved_grid_field(feature, kinds=("grid",), allow_faults=False):
     """(engine, world_to_local) of a plain interpolated feature solved by the engine on one of ``kinds``, else None.
-    (Orthogonality rows take grid sources only: outside a tet mesh the gradient is NaN and the reference then drops the
-    WHOLE family, LI/_discrete_interpolator.py:357-359 -- left to the stock method.)"""
+    (Outside a tet mesh the gradient is NaN and the reference then drops the WHOLE orthogonality family,
+    LI/_discrete_interpolator.py:357-359: lsb200_add_field_orthogonal_rows does the same.)"""
     if type(feature).__name__ != "GeologicalFeature":
         return None
     if not allow_faults and getattr(feature, "faults_enabled", True) and len(getattr(feature, "faults", [])) > 0:
@@ -635,10 +635,10 @@ def _make_install_gradient_constraint(stock):
     def install_gradient_constraint(self):
         """GeologicalFeatureBuilder.install_gradient_constraint
         (LS/modelling/features/builders/_geological_feature_builder.py:293-318): families whose source feature was
-        solved by the grid engine are recorded and generated on the device at solve time
+        solved by the engine (grid or tet mesh; the target may be either, too) are recorded and generated on the device at solve time
         (lsb200_add_field_orthogonal_rows); the others go through the stock method."""
         it = self.interpolator
-        if not (getattr(it, "_b200_divert", False) and hasattr(it, "_b200_stencil")):
+        if not (getattr(it, "_b200_divert", False) and hasattr(it, "_b200_device_rows")):
             return stock(self)
         rest = {}
 
@@ -656,7 +656,7 @@ def _make_install_gradient_constraint(stock):
             feature, w, _region, step, b = g
             if w == 0:
                 continue
-            src = _solved_grid_field(feature)
+            src = _solved_grid_field(feature, kinds=("grid", "tetmesh"))
             if src is None:
                 rest[key] = g
             else:

@@ -214,7 +214,29 @@ def field_orthogonal_rows(grid: fo.Grid, other: FrameField, element_step: int, w
     norm = np.linalg.norm(vec, axis=1)
     vec[norm > 0] /= norm[norm > 0, None]
     sel = np.arange(n_el)[::element_step]
+    if np.isnan(vec[sel]).any():  # a tet-mesh source, barycentre outside it: the reference drops the whole family
+        return None
     return fo.orthogonal_rows(grid, bary[sel], vec[sel], w=w, b=b, name=name)
+
+
+def p1_field_orthogonal_rows(grid: fo.Grid, other: FrameField, element_step: int, w: float, b: float = 0.0,
+                             name: str = "orthogonal"):
+    """The same builder step for a P1 interpolator on a TetMesh: TetMesh.barycentre (mean of the four vertices,
+    LC/supports/_3d_structured_tetra.py:106-118) of every `element_step`-th tet and the other feature's normalised gradient
+    there -> P1Interpolator.add_gradient_orthogonal_constraints (LI/_p1interpolator.py:248-296; weight w * tet volume).
+    Returns None when a selected vector holds a NaN (a barycentre outside a tet-mesh source): the reference then drops the
+    whole family (LI/_discrete_interpolator.py:357-359)."""
+    from . import p1_oracle as po
+
+    el = po.elements(grid)
+    bary = np.sum(po.node_xyz(grid, el), axis=1) / 4.0
+    vec = other.gradient(bary)
+    norm = np.linalg.norm(vec, axis=1)
+    vec[norm > 0] /= norm[norm > 0, None]
+    sel = np.arange(el.shape[0])[::element_step]
+    if np.isnan(vec[sel]).any():
+        return None
+    return po.orthogonal_rows(grid, bary[sel], vec[sel], w=w, b=b, name=name)
 
 
 # ---------------------------------------------------------------------------------------------------------------

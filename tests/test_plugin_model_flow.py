@@ -58,10 +58,13 @@ class OracleEngine:
     def add_field_orthogonal_rows(self, other, step=10, weight=1.0, b=0.0, other_world_to_local=None):
         from oracle import fault_oracle as fa
 
-        fam = fa.field_orthogonal_rows(self.grid, fa.FrameField(other.grid, other.c, other_world_to_local), step, weight, b,
-                                       name=f"device_orthogonal{len(self.rows)}")
-        self.rows.append(fam)
+        src = fa.FrameField(other.grid, other.c, other_world_to_local, other.kind)
+        make = fa.p1_field_orthogonal_rows if self.kind == "tetmesh" else fa.field_orthogonal_rows
+        fam = make(self.grid, src, step, weight, b, name=f"device_orthogonal{len(self.rows)}")
         self.device_families = getattr(self, "device_families", 0) + 1
+        if fam is None:  # NaN gradient outside a tet-mesh source: the whole family is dropped, as in the reference
+            return 0
+        self.rows.append(fam)
         return fam.A.shape[0]
 
     def solve_cg(self, rtol=1e-5, atol=0.0, maxiter=None, x0=None, want_c=True, out=None):
@@ -309,6 +312,39 @@ def test_fault_frame_and_faulted_foliation_through_the_model(ls, monkeypatch):
     s_ref = stock.evaluate_feature_value("strati", pts)
     np.testing.assert_array_equal(np.isnan(strati), np.isnan(s_ref))
     np.testing.assert_allclose(strati, s_ref, rtol=0, atol=1e-6 * float(np.nanmax(s_ref) - np.nanmin(s_ref)), equal_nan=True)
+
+
+def test_p1_fault_frame_orthogonality_rows_come_from_the_device(ls):
+    """A fault frame on tet meshes (interpolatortype='PLI', data shifted to a zero origin so that the barycentres stay inside
+    the other coordinates' meshes): the '<feature>_orthogonal' families of coordinates 1 and 2 are generated by the engine
+    (the P1 twin of lsb200_add_field_orthogonal_rows) and the solved frame matches the stock build."""
+    from LoopStructural.datasets import load_intrusion
+    from loopstructural_b200 import plugin
+
+    def build(**kw):
+        data, bb = load_intrusion()
+        data = data.copy()
+        data[["X", "Y", "Z"]] -= bb[0]
+        bb = bb - bb[0]
+        model = ls.GeologicalModel(bb[0, :], bb[1, :])
+        model.data = data
+        model.create_and_add_fault("fault", 500, nelements=2000, interpolatortype="PLI", buffer=0.3, **kw)
+        model.update()
+        return model
+
+    fault = build(solver="b200")["fault"]
+    for i in range(3):
+        it = fault[i].interpolator
+        assert type(it).__name__ == "B200P1Interpolator" and it.latest_solve_timing["backend"] == "b200"
+    assert [getattr(fault[i].interpolator._b200_engine, "device_families", 0) for i in range(3)] == [0, 2, 1]
+    assert not any("orthogonal" in k for i in range(3) for k in fault[i].interpolator.constraints)
+    c_frame = [np.array(fault[i].interpolator.c) for i in range(3)]
+    plugin.uninstall()
+    sf = build()["fault"]
+    assert any("orthogonal" in k for k in sf[1].interpolator.constraints)
+    for i in range(3):
+        cs = np.asarray(sf[i].interpolator.c)
+        assert np.linalg.norm(c_frame[i] - cs) / np.sqrt(cs.size) / float(cs.max() - cs.min()) <= 1e-6
 
 
 def _fold_model(ls, **kw):

@@ -193,6 +193,48 @@ def test_field_orthogonal_rows_match_the_reference(tag):
         eo.close()
 
 
+@pytest.mark.parametrize("tag", ["p1_world", "p1_zero_origin"])
+def test_p1_field_orthogonal_rows_match_the_reference(tag):
+    """The P1 / TetMesh twin of the entry point (target and source on tet meshes, a fault frame built with
+    interpolatortype='PLI', tests/golden/orth_p1_*.npz): rows through the normal operator and the right-hand side as the
+    reference's; with the dataset's own origin every barycentre is outside the source mesh, the gradient is NaN and the
+    whole family is dropped -- by the reference and by the entry point."""
+    from loopstructural_b200 import Engine, build
+    from loopstructural_b200 import engine as en
+
+    build.build()
+    z = np.load(os.path.join(GOLDEN, f"orth_{tag}.npz"))
+    rng = np.random.default_rng(3)
+    for key in z["families"]:
+        key = str(key)
+        ti, oj = int(key[1]), int(key[4])
+        grid = fo.Grid.from_cells(z[f"f{ti}_ncells"], z[f"f{ti}_origin"], z[f"f{ti}_step"])
+        ogrid = fo.Grid.from_cells(z[f"f{oj}_ncells"], z[f"f{oj}_origin"], z[f"f{oj}_step"])
+        other = fa.FrameField(ogrid, z[f"f{oj}_c"], z[f"f{oj}_w2l"], "tetmesh")
+        step, w = int(z[f"{key}/step"]), float(z[f"{key}/weight"])
+        B = 0.37
+        fam = fa.p1_field_orthogonal_rows(grid, other, step, w, B)
+        eo = Engine(ogrid.nsteps, ogrid.origin, ogrid.step, kind="tetmesh")
+        eo.set_c(other.c)
+        e = Engine(grid.nsteps, grid.origin, grid.step, kind="tetmesh")
+        e.set_p1_regularisation(0.0)
+        kept = e.add_field_orthogonal_rows(eo, step=step, weight=w, b=B, other_world_to_local=other.world_to_local)
+        if f"{key}/dropped" in z.files:
+            assert fam is None and kept == 0 and e.num_rows == 0
+        else:
+            m_or = fam.matrix(grid.n_nodes)
+            assert kept == m_or.shape[0] == int(z[f"{key}/shape"][0]) == e.num_rows
+            e.finalize()
+            p = rng.normal(size=grid.n_nodes)
+            q = e.apply_normal(p, parts=en.PART_ROWS)
+            q_ref = m_or.T @ (fam.w**2 * (m_or @ p))
+            np.testing.assert_allclose(q, q_ref, rtol=0, atol=1e-12 * max(np.abs(q_ref).max(), 1e-300))
+            rhs_rows = m_or.T @ (fam.w**2 * fam.b)
+            np.testing.assert_allclose(e.rhs(), rhs_rows, rtol=0, atol=1e-12 * max(np.abs(rhs_rows).max(), 1e-300))
+        e.close()
+        eo.close()
+
+
 def test_lattice_export_matches_the_reference_and_the_oracle():
     """lsb200_eval_lattice against BaseFeature.scalar_field of the unmodified reference (lattice_claudius.npz), then
     lattices that reach outside the support, single-point axes, both flattening orders and the device-pointer entry."""
