@@ -846,6 +846,9 @@ def run_ours(args):
                        "dof": dof_global},
             "solve_seconds": dev_s / max(args.steps, 1), "cg_iterations": iters_per_solve,
             "cg_iterations_per_second": its / dev_s if dev_s > 0 else None,
+            # the iteration as the timed solves ran it (at N > 1 with the ranks really waiting for each other; roofline_iteration
+            # below is lsb200_time_kernel's back-to-back figure, in which no rank waits)
+            "solve_us_per_iteration": 1e6 * dev_s / its if its else None,
             "roofline": {"bound": "hbm", "kernel": "FDI regularisation normal matvec = k_fdi_fused: interior box tiles (TMA-staged plane ring), "
                                                    "z-face planes and x/y strips in one launch",
                          "achieved": ach,

@@ -277,18 +277,19 @@ __device__ __forceinline__ double p1_tiles_cta(const GridDesc& g, const P1Tables
     const int bz = b / txy, brem = b - bz * txy;
     const int by = brem / pl.tiles_x, bx = brem - by * pl.tiles_x;
     x0 = 2 + 64 * bx; y0 = 2 + TY * by; z0 = pl.z_base + TZ * bz;  // first output node of the tile
-    // stage the nodes (x0-2 .., y0-2 .., z0-2 ..): a warp per staged row (the row's address arithmetic once, not per
-    // element: the element-wise form spent 45 % of the kernel's instructions here), lanes along x
-    for (int row = tid >> 5; row < SY * G::SZ; row += NW) {
-      const int sz = row / SY, sy = row - sz * SY;
-      const int gj = y0 - HALO + sy, gk = z0 - HALO + sz;
+    // stage the nodes (x0-2 .., y0-2 .., z0-2 ..): a thread per pair of x-neighbours (one address computation for two
+    // copies; consecutive threads read consecutive pairs), the even one into the first half of the staged row, the odd one
+    // into the second.  (A warp per row with the lanes along x was tried: 46 us against 41, profiles/r2ac.)
+    for (int idx = tid; idx < G::ELEMS / 2; idx += NT) {
+      const int hx = idx % HX, r = idx / HX;
+      const int sy = r % SY, sz = r / SY;
+      const int gi = x0 - HALO + 2 * hx, gj = y0 - HALO + sy, gk = z0 - HALO + sz;
       const bool rowok = gj < g.ny && gk >= 0 && gk < g.nz && gk >= g.k0 - HALO && gk < g.k1 + HALO;
-      const double* src = p + ((long long)(gk - g.k0 + HALO) * g.plane + (long long)gj * g.pitch + (x0 - HALO));
-      double* dst = S + row * 2 * HX;
-      for (int sx = tid & 31; sx < 2 * HX; sx += 32) {
-        const bool ok = rowok && x0 - HALO + sx < g.nx;
-        cp_async_8(dst + (sx & 1) * HX + (sx >> 1), ok ? src + sx : p, ok);
-      }
+      const double* src = p + ((long long)(gk - g.k0 + HALO) * g.plane + (long long)gj * g.pitch + gi);
+      double* dst = S + r * 2 * HX + hx;
+      const bool ok0 = rowok && gi < g.nx, ok1 = rowok && gi + 1 < g.nx;
+      cp_async_8(dst, ok0 ? src : p, ok0);
+      cp_async_8(dst + HX, ok1 ? src + 1 : p, ok1);
     }
     cp_async_commit();
   }
