@@ -32,7 +32,9 @@ inline UniConsts make_uni_consts(const StencilWeights& w) {
 }
 
 // ---- the single-launch plan (k_fdi_fused, csrc/fdi_fused.cuh) ------------------------------------------------------
-// X(TYT warps per CTA, ST ring planes, MINB CTAs per SM): tiles of 64 x 4 TYT nodes
+// X(TYT warps per CTA, ST ring planes, MINB CTAs per SM): tiles of 64 x 4 TYT nodes.  (64 x 8 tiles with 5 CTAs per SM,
+// X(2, 6, 5), were measured: no faster at 256^3 (69.2 us), slower at 512^3 and on slabs, and the 20 % extra staging
+// traffic costs the vector kernels of the iteration their L2, profiles/r2ae_tiles_64x8.jsonl)
 #define LSB_FUSED_CFGS(X) \
   X(4, 6, 3)              \
   X(3, 6, 4)

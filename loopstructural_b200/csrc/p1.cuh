@@ -277,19 +277,16 @@ __device__ __forceinline__ double p1_tiles_cta(const GridDesc& g, const P1Tables
     const int bz = b / txy, brem = b - bz * txy;
     const int by = brem / pl.tiles_x, bx = brem - by * pl.tiles_x;
     x0 = 2 + 64 * bx; y0 = 2 + TY * by; z0 = pl.z_base + TZ * bz;  // first output node of the tile
-    // stage the nodes (x0-2 .., y0-2 .., z0-2 ..): a thread per pair of x-neighbours (one address computation for two
-    // copies; consecutive threads read consecutive pairs), the even one into the first half of the staged row, the odd one
-    // into the second.  (A warp per row with the lanes along x was tried: 46 us against 41, profiles/r2ac.)
-    for (int idx = tid; idx < G::ELEMS / 2; idx += NT) {
-      const int hx = idx % HX, r = idx / HX;
+    // stage the nodes (x0-2 .., y0-2 .., z0-2 ..): consecutive threads read consecutive x.  (A warp per staged row and a
+    // thread per pair of x-neighbours were both tried to save address arithmetic: 46 and 44 us against 41, profiles/r2ac,
+    // r2_final_p1_tiles.jsonl.)
+    for (int idx = tid; idx < G::ELEMS; idx += NT) {
+      const int sx = idx % (2 * HX), r = idx / (2 * HX);
       const int sy = r % SY, sz = r / SY;
-      const int gi = x0 - HALO + 2 * hx, gj = y0 - HALO + sy, gk = z0 - HALO + sz;
-      const bool rowok = gj < g.ny && gk >= 0 && gk < g.nz && gk >= g.k0 - HALO && gk < g.k1 + HALO;
+      const int gi = x0 - HALO + sx, gj = y0 - HALO + sy, gk = z0 - HALO + sz;
+      const bool ok = gi < g.nx && gj < g.ny && gk >= 0 && gk < g.nz && gk >= g.k0 - HALO && gk < g.k1 + HALO;
       const double* src = p + ((long long)(gk - g.k0 + HALO) * g.plane + (long long)gj * g.pitch + gi);
-      double* dst = S + r * 2 * HX + hx;
-      const bool ok0 = rowok && gi < g.nx, ok1 = rowok && gi + 1 < g.nx;
-      cp_async_8(dst, ok0 ? src : p, ok0);
-      cp_async_8(dst + HX, ok1 ? src + 1 : p, ok1);
+      cp_async_8(S + ((sz * SY + sy) * 2 + (sx & 1)) * HX + (sx >> 1), ok ? src : p, ok);
     }
     cp_async_commit();
   }

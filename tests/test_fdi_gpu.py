@@ -68,8 +68,9 @@ def test_main_stencil_kernel_configs(nodes, main, cz, monkeypatch):
     against the oracle's masked two-pass form, on ragged grids and odd z-chunking; "normal" is k_fdi_normal everywhere."""
     if main == "normal":
         monkeypatch.setenv("LSB200_STENCIL_MAIN", "-1")
-    if "3" in main or "4" in main:
-        monkeypatch.setenv("LSB200_FUSED_CFG", "3" if "3" in main else "4")
+    for tyt in "34":
+        if tyt in main:
+            monkeypatch.setenv("LSB200_FUSED_CFG", tyt)
     if "cp.async" in main:
         monkeypatch.setenv("LSB200_TMA", "0")
     if cz != "0":
