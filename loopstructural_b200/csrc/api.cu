@@ -149,6 +149,10 @@ struct lsb200_ctx {
   unsigned int* small_bar = nullptr;
   double* small_slots = nullptr;
   int small_grid = 0;
+  // the CUDA graph of one batch of iterations, kept from solve to solve: lsb200_finalize_system drops it (row blocks,
+  // weights and the launch plan are kernel arguments by value)
+  cudaGraphExec_t cg_graph = nullptr;
+  long long cg_graph_launches = 0;
   bool tuned = false;      // the plan has been chosen among the planner's candidates by timing them (tune_fused)
   bool plan_forced = false;  // an environment switch fixed the plan: no tuning
   FusedChoice fz{};
@@ -647,6 +651,7 @@ int lsb200_destroy(lsb200_handle h) {
   cudaFree(h->partials);
   cudaFree(h->counters);
   cudaFree(h->status);
+  if (h->cg_graph) cudaGraphExecDestroy(h->cg_graph);
   cudaFree(h->small_bar);
   cudaFree(h->small_slots);
   cudaFree(h->p1_table);
@@ -1227,6 +1232,10 @@ int lsb200_finalize_system(lsb200_handle h) {
   if (!h) return fail(LSB200_ERR_ARG, "null handle");
   if (h->finalized) return 0;
   CK(cudaSetDevice(h->device));
+  if (h->cg_graph) {
+    cudaGraphExecDestroy(h->cg_graph);
+    h->cg_graph = nullptr;
+  }
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
@@ -1821,9 +1830,9 @@ int lsb200_solve_cg(lsb200_handle h, double rtol, double atol, int64_t maxiter, 
     // Claudius-size grid).  LSB200_GRAPH=0 keeps plain launches.
     static const bool want_graph = !(getenv("LSB200_GRAPH") && atoi(getenv("LSB200_GRAPH")) == 0);
     cudaGraph_t graph = nullptr;
-    cudaGraphExec_t gexec = nullptr;
-    bool graph_tried = false;
-    long long launches_per_batch = 0;
+    cudaGraphExec_t gexec = want_graph ? h->cg_graph : nullptr;  // a previous solve of the same system left its graph
+    bool graph_tried = gexec != nullptr;
+    long long launches_per_batch = h->cg_graph_launches;
     while (!done) {
       const long long todo = std::min<long long>(batch, maxit - enq);
       if (h->small_ok) {
@@ -1872,7 +1881,10 @@ int lsb200_solve_cg(lsb200_handle h, double rtol, double atol, int64_t maxiter, 
       slot ^= 1;
     }
     CK(cudaStreamSynchronize(h->stream));
-    if (gexec) cudaGraphExecDestroy(gexec);
+    if (gexec && gexec != h->cg_graph) {
+      h->cg_graph = gexec;
+      h->cg_graph_launches = launches_per_batch;
+    }
     if (graph) cudaGraphDestroy(graph);
     cudaEventDestroy(ev[0]);
     cudaEventDestroy(ev[1]);
