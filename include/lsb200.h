@@ -335,6 +335,21 @@ int lsb200_eval_lattice(lsb200_handle h, const double* transform, const double s
 int lsb200_eval_lattice_dev(lsb200_handle h, const double* transform, const double start[3], const double stop[3],
                             const int64_t n[3], int order_f, int gradient, double* out_dev, void* stream);
 
+/* ---- isosurface of a lattice volume (SURVEY.md 8 f rank 4) --------------- */
+/* What LoopIsosurfacer.fit (LoopStructural/utils/_surface.py:66-186, behind BaseFeature.surfaces,
+ * LoopStructural/modelling/features/_base_geological_feature.py:317-357) asks of
+ * skimage.measure.marching_cubes(volume, level, spacing=..., mask=~isnan(volume)): vertices (index coordinates times
+ * spacing), triangles, vertex normals (towards decreasing values).  volume: dims[0] x dims[1] x dims[2] samples in C order
+ * (host); NaN samples are masked out.  The triangulation is marching tetrahedra on the lattice (six Kuhn tetrahedra per
+ * cell, one vertex per crossed lattice edge, watertight), not scikit-image's Lewiner cubes: same level set of the same
+ * samples, more triangles.  Two steps: the first returns the counts and an object that holds the result on the device,
+ * the second copies into caller-owned arrays (vertices, normals: 3 doubles per vertex; triangles: 3 int32 each). */
+typedef struct lsb200_iso_result* lsb200_iso;
+int lsb200_isosurface(int device, const int64_t dims[3], const double* volume, double level, const double spacing[3],
+                      lsb200_iso* out, int64_t* n_vertices, int64_t* n_triangles);
+int lsb200_isosurface_fetch(lsb200_iso iso, double* vertices, int32_t* triangles, double* normals);
+int lsb200_isosurface_free(lsb200_iso iso);
+
 /* Page-locked host memory for result buffers (c of a large grid is 134 MB - 1 GB: a pageable destination halves
  * the device->host rate and pays its page faults inside every solve). */
 int lsb200_host_alloc(int64_t bytes, void** out);

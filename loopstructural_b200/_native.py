@@ -108,6 +108,9 @@ SIGNATURES = {
     "lsb200_add_field_orthogonal_rows": (C.c_int, [Handle, Handle, c_double_p, C.c_int64, C.c_double, C.c_double, c_int64_p]),
     "lsb200_eval_lattice": (C.c_int, [Handle, c_double_p, c_double_p, c_double_p, c_int64_p, C.c_int, C.c_int, c_double_p]),
     "lsb200_eval_lattice_dev": (C.c_int, [Handle, c_double_p, c_double_p, c_double_p, c_int64_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "lsb200_isosurface": (C.c_int, [C.c_int, c_int64_p, c_double_p, C.c_double, c_double_p, C.POINTER(C.c_void_p), c_int64_p, c_int64_p]),
+    "lsb200_isosurface_fetch": (C.c_int, [C.c_void_p, c_double_p, C.POINTER(C.c_int32), c_double_p]),
+    "lsb200_isosurface_free": (C.c_int, [C.c_void_p]),
     "lsb200_host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     "lsb200_host_free": (C.c_int, [C.c_void_p]),
     "lsb200_time_kernel": (C.c_int, [Handle, C.c_int, C.c_int, c_double_p]),

@@ -26,6 +26,7 @@
 #include "fdi_plan.cuh"
 #include "frame.cuh"
 #include "hostpipe.cuh"
+#include "iso.cuh"
 #include "p1.cuh"
 #include "rows.cuh"
 
@@ -2296,6 +2297,112 @@ int lsb200_eval_lattice(lsb200_handle h, const double* transform, const double s
                      return 0;
                    }, &ce);
   return pipe_result(rc, ce, "staged lattice evaluation");
+}
+
+// ------------------------------------------------------------------ isosurface of a lattice volume (iso.cuh)
+struct lsb200_iso_result {
+  int device = 0;
+  long long nv = 0, nt = 0;
+  double* verts = nullptr;
+  double* normals = nullptr;
+  int* tris = nullptr;
+};
+
+int lsb200_isosurface(int device, const int64_t dims[3], const double* volume, double level, const double spacing[3],
+                      lsb200_iso* out, int64_t* n_vertices, int64_t* n_triangles) {
+  if (!dims || !volume || !spacing || !out || !n_vertices || !n_triangles) return fail(LSB200_ERR_ARG, "null argument");
+  *out = nullptr;
+  *n_vertices = *n_triangles = 0;
+  if (dims[0] < 2 || dims[1] < 2 || dims[2] < 2) return fail(LSB200_ERR_ARG, "an isosurface needs at least 2 samples per axis");
+  const long long n = (long long)dims[0] * dims[1] * dims[2];
+  if (7 * n >= 2147483647LL) return fail(LSB200_ERR_ARG, "volume of %lld samples: the limit is 306 million", n);
+  if (!(level == level)) return fail(LSB200_ERR_ARG, "NaN level");
+  int ndev = lsb200_device_count();
+  if (ndev <= 0) return fail(LSB200_ERR_CUDA, "no CUDA device available (the engine has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(LSB200_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+  CK(cudaSetDevice(device));
+  IsoGrid g{dims[0], dims[1], dims[2], {spacing[0], spacing[1], spacing[2]}, level};
+  const long long ne = 7 * n, nc = (long long)(dims[0] - 1) * (dims[1] - 1) * (dims[2] - 1);
+  cudaStream_t st = nullptr;
+  double* dv = nullptr;
+  int *flag = nullptr, *id = nullptr, *count = nullptr, *first = nullptr;
+  void* tmp = nullptr;
+  lsb200_iso_result* res = new lsb200_iso_result();
+  res->device = device;
+  auto cleanup = [&]() {
+    cudaFree(dv); cudaFree(flag); cudaFree(id); cudaFree(count); cudaFree(first); cudaFree(tmp);
+    if (st) cudaStreamDestroy(st);
+  };
+  auto bail = [&](cudaError_t e, const char* what) {
+    cleanup();
+    cudaFree(res->verts); cudaFree(res->normals); cudaFree(res->tris);
+    delete res;
+    return fail(e == cudaErrorMemoryAllocation ? LSB200_ERR_ALLOC : LSB200_ERR_CUDA, "isosurface: %s: %s", what, cudaGetErrorString(e));
+  };
+#define ICK(x, what) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return bail(e_, what); } while (0)
+  ICK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "stream");
+  ICK(cudaMalloc(&dv, sizeof(double) * n), "volume");
+  ICK(cudaMalloc(&flag, sizeof(int) * (ne + 1)), "edge flags");
+  ICK(cudaMalloc(&id, sizeof(int) * (ne + 1)), "edge ids");
+  ICK(cudaMalloc(&count, sizeof(int) * (nc + 1)), "cell counts");
+  ICK(cudaMalloc(&first, sizeof(int) * (nc + 1)), "cell offsets");
+  ICK(cudaMemcpyAsync(dv, volume, sizeof(double) * n, cudaMemcpyHostToDevice, st), "upload");
+  ICK(cudaMemsetAsync(flag + ne, 0, sizeof(int), st), "flags");
+  ICK(cudaMemsetAsync(count + nc, 0, sizeof(int), st), "counts");
+  const int nbe = (int)std::min<long long>((ne + 255) / 256, 1 << 20), nbc = (int)std::min<long long>((nc + 255) / 256, 1 << 20);
+  k_iso_edge_flags<<<nbe, 256, 0, st>>>(g, dv, flag);
+  k_iso_cell_counts<<<nbc, 256, 0, st>>>(g, dv, count);
+  ICK(cudaGetLastError(), "launch");
+  size_t need1 = 0, need2 = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need1, flag, id, (int)(ne + 1), st);
+  cub::DeviceScan::ExclusiveSum(nullptr, need2, count, first, (int)(nc + 1), st);
+  ICK(cudaMalloc(&tmp, std::max(need1, need2)), "scan scratch");
+  size_t have = std::max(need1, need2);
+  ICK(cub::DeviceScan::ExclusiveSum(tmp, have, flag, id, (int)(ne + 1), st), "scan");
+  have = std::max(need1, need2);
+  ICK(cub::DeviceScan::ExclusiveSum(tmp, have, count, first, (int)(nc + 1), st), "scan");
+  int totals[2] = {0, 0};
+  ICK(cudaMemcpyAsync(&totals[0], id + ne, sizeof(int), cudaMemcpyDeviceToHost, st), "totals");
+  ICK(cudaMemcpyAsync(&totals[1], first + nc, sizeof(int), cudaMemcpyDeviceToHost, st), "totals");
+  ICK(cudaStreamSynchronize(st), "sync");
+  res->nv = totals[0];
+  res->nt = totals[1];
+  if (res->nv > 0) {
+    ICK(cudaMalloc(&res->verts, sizeof(double) * 3 * res->nv), "vertices");
+    ICK(cudaMalloc(&res->normals, sizeof(double) * 3 * res->nv), "normals");
+    k_iso_vertices<<<nbe, 256, 0, st>>>(g, dv, flag, id, res->verts, res->normals);
+  }
+  if (res->nt > 0) {
+    ICK(cudaMalloc(&res->tris, sizeof(int) * 3 * res->nt), "triangles");
+    k_iso_triangles<<<nbc, 256, 0, st>>>(g, dv, id, first, res->tris);
+  }
+  ICK(cudaGetLastError(), "launch");
+  ICK(cudaStreamSynchronize(st), "sync");
+#undef ICK
+  cleanup();
+  *out = res;
+  *n_vertices = res->nv;
+  *n_triangles = res->nt;
+  return 0;
+}
+
+int lsb200_isosurface_fetch(lsb200_iso iso, double* vertices, int32_t* triangles, double* normals) {
+  if (!iso) return fail(LSB200_ERR_ARG, "null isosurface");
+  CK(cudaSetDevice(iso->device));
+  if (vertices && iso->nv) CK(cudaMemcpy(vertices, iso->verts, sizeof(double) * 3 * iso->nv, cudaMemcpyDeviceToHost));
+  if (normals && iso->nv) CK(cudaMemcpy(normals, iso->normals, sizeof(double) * 3 * iso->nv, cudaMemcpyDeviceToHost));
+  if (triangles && iso->nt) CK(cudaMemcpy(triangles, iso->tris, sizeof(int) * 3 * iso->nt, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int lsb200_isosurface_free(lsb200_iso iso) {
+  if (!iso) return 0;
+  cudaSetDevice(iso->device);
+  cudaFree(iso->verts);
+  cudaFree(iso->normals);
+  cudaFree(iso->tris);
+  delete iso;
+  return 0;
 }
 
 int lsb200_host_alloc(int64_t bytes, void** out) {

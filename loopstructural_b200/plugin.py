@@ -828,6 +828,26 @@ def _install_feature_patch():
     gcls.evaluate_value = _make_evaluate_value(gstock)
 
 
+def _install_isosurface_patch():
+    """LoopIsosurfacer.fit (LoopStructural/utils/_surface.py:139-147) calls the module-level name ``marching_cubes``
+    (skimage.measure.marching_cubes): it is pointed at the device isosurface (loopstructural_b200.isosurface), which takes
+    the same arguments and returns the same four arrays.  BaseFeature.surfaces then runs: evaluate_value on the regular
+    grid (device, through the patched evaluate_value) -> device isosurface -> Surface objects."""
+    try:
+        import LoopStructural.utils._surface as mod
+    except Exception:
+        return
+    from .isosurface import marching_tetrahedra
+
+    if "marching_cubes_stock" not in _installed:
+        _installed["marching_cubes_stock"] = (mod, mod.marching_cubes)
+
+    def marching_cubes(volume, level=None, *, spacing=(1.0, 1.0, 1.0), mask=None, **kwargs):
+        return marching_tetrahedra(volume, level, spacing=spacing, mask=mask)
+
+    mod.marching_cubes = marching_cubes
+
+
 def _install_fault_patch():
     """Patch FaultSegment when LoopStructural itself is importable (the interpolation package alone is enough for
     everything else in this module)."""
@@ -860,6 +880,7 @@ def install():
     _install_fault_patch()
     _install_builder_patch()
     _install_feature_patch()
+    _install_isosurface_patch()
     return {"FDI": _installed["fdi"], "P1": _installed["p1"], "DFI": _installed["dfi"]}
 
 
@@ -883,3 +904,6 @@ def uninstall():
     if "evaluate_value_stock" in _installed:
         gcls, gstock = _installed["evaluate_value_stock"]
         gcls.evaluate_value = gstock
+    if "marching_cubes_stock" in _installed:
+        mod, stock = _installed["marching_cubes_stock"]
+        mod.marching_cubes = stock
