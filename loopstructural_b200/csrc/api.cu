@@ -28,6 +28,7 @@
 #include "hostpipe.cuh"
 #include "iso.cuh"
 #include "p1.cuh"
+#include "p1_march.cuh"
 #include "rows.cuh"
 
 using namespace lsb;
@@ -114,6 +115,12 @@ struct lsb200_ctx {
   int p1_tile_cfg = 0;
   P1TilePlan p1_plan{};
   P1ClassTaps p1_cls{};
+  int p1_march = 0;            // configuration of the k_p1_march plan (LSB_P1_MARCH_CFGS), 0: not used
+  int p1_march_nw = 0;         // its marching and boundary warps per CTA
+  int p1_march_nb = 0;
+  int p1_march_minb = 1;       // CTAs of it that fit an SM
+  P1MarchPlan p1_mplan{};
+  P1MarchTaps p1_mtaps{};
   double ridge = 1e-8;
   int add_ridge = 1, apply_scaling = 1, deterministic = 0;
   cudaStream_t stream = nullptr;
@@ -396,6 +403,26 @@ static int launch_regularisation(lsb200_ctx* h, const double* p, double* q, int 
   const long long n = (long long)h->g.nx * h->g.ny * h->g.nzl;
   const int nb = (int)std::max<long long>(1, std::min<long long>((n + VEC_NT - 1) / VEC_NT, (long long)h->sm_count * 16));
   const double w2 = h->p1_w * h->p1_w, ridge2 = h->add_ridge ? h->ridge * h->ridge : 0.0;
+  if (h->p1_march) {
+    // one launch: the interior by z-marching register tiles, every CTA with its share of the boundary nodes (csrc/p1_march.cuh)
+    const P1MarchPlan& pl = h->p1_mplan;
+    const unsigned int ctas = (unsigned int)(pl.n_cta + pl.b.n_bnd_cta);
+    switch (h->p1_march) {
+#define X(ID, NW, NB, MINB)                                                                                 \
+  case ID: {                                                                                                \
+    auto kern = k_p1_march<NW, NB, MINB>;                                                                   \
+    const size_t smem = sizeof(double) * P1MarchCfg<NW, NB>::PLANE * P1MarchCfg<NW, NB>::ST;                \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                     \
+    kern<<<ctas, 32 * (NW + NB), smem, h->stream>>>(h->g, tb, h->p1_mtaps, pl, w2, ridge2, p, q, h->partials, h->counters + 0, h->sc, \
+                                             cg_mode);                                                      \
+  } break;
+      LSB_P1_MARCH_CFGS(X)
+#undef X
+    }
+    CKL();
+    h->launches++;
+    return 0;
+  }
   if (h->p1_tiles) {
     // one launch: shared-memory tiles of the interior, every CTA with its share of the boundary nodes (csrc/p1.cuh)
     const P1TilePlan& pl = h->p1_plan;
@@ -737,6 +764,50 @@ int lsb200_set_p1_tables(lsb200_handle h, const int64_t m[3], const double* tabl
     h->p1_tile_cfg = ID;                                                                                           \
     break;
       LSB_P1_TILE_CFGS(X)
+#undef X
+    }
+  }
+  // the z-marching form of the interior (LSB200_P1_MARCH = configuration of LSB_P1_MARCH_CFGS, 0: off; LSB200_P1_MARCH_CZ: planes per chunk)
+  h->p1_march = 0;
+  const int march = getenv("LSB200_P1_MARCH") ? atoi(getenv("LSB200_P1_MARCH")) : LSB_P1_MARCH_DEFAULT;
+  const int march_cz = getenv("LSB200_P1_MARCH_CZ") ? atoi(getenv("LSB200_P1_MARCH_CZ")) : 0;
+  if (want_tiles && h->p1_tiles) {
+    switch (march) {
+#define X(ID, NW, NB, MINB)                                                                                          \
+  case ID: {                                                                                                         \
+    int per_sm = 0;                                                                                                  \
+    const size_t smem = sizeof(double) * P1MarchCfg<NW, NB>::PLANE * P1MarchCfg<NW, NB>::ST;                         \
+    cudaFuncSetAttribute(k_p1_march<NW, NB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_p1_march<NW, NB, MINB>, 32 * (NW + NB), smem) != cudaSuccess || per_sm < 1) { \
+      cudaGetLastError();                                                                                            \
+      break;                                                                                                         \
+    }                                                                                                                \
+    {                                                                                                                \
+      /* the persistent CG loop walks the same plan: one wave there too */                                          \
+      int per_sm_loop = 0;                                                                                           \
+      cudaFuncSetAttribute(k_cg_small_p1m<NW, NB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_loop, k_cg_small_p1m<NW, NB, MINB>, 32 * (NW + NB), smem) == cudaSuccess && \
+          per_sm_loop >= 1)                                                                                          \
+        per_sm = std::min(per_sm, per_sm_loop);                                                                      \
+      else                                                                                                           \
+        cudaGetLastError();                                                                                          \
+    }                                                                                                                \
+    if (p1_plan_march<NW, NB>(h->g, h->p1_m, table, h->sm_count, per_sm, MAX_PARTIALS, march_cz, &h->p1_mplan, &h->p1_mtaps)) { \
+      h->p1_march = ID;                                                                                              \
+      if (getenv("LSB200_P1_MARCH_SKIP") && atoi(getenv("LSB200_P1_MARCH_SKIP")) == 1) { /* timing only: no boundary */  \
+        h->p1_mplan.b.nbz = h->p1_mplan.b.nby = h->p1_mplan.b.nbx = 0;                                               \
+        h->p1_mplan.b.n_bnd_cta = 0;                                                                                 \
+      }                                                                                                              \
+      if (getenv("LSB200_P1_MARCH_SKIP") && atoi(getenv("LSB200_P1_MARCH_SKIP")) == 2) { /* timing only: no tiles */     \
+        h->p1_mplan.b.n_bnd_cta += h->p1_mplan.n_cta;                                                                \
+        h->p1_mplan.n_cta = 0;                                                                                       \
+      }                                                                                                              \
+      h->p1_march_nw = NW;                                                                                           \
+      h->p1_march_nb = NB;                                                                                           \
+      h->p1_march_minb = per_sm;                                                                                     \
+    }                                                                                                                \
+  } break;
+      LSB_P1_MARCH_CFGS(X)
 #undef X
     }
   }
@@ -1607,9 +1678,22 @@ static void plan_small(lsb200_ctx* h) {
 #undef X
     }
   } else {
-    if (!h->p1_tiles || h->p1_tile_cfg != 1) return;
-    const long long nvb = (long long)h->p1_plan.n_bnd_cta + (long long)h->p1_plan.tiles_x * h->p1_plan.tiles_y * h->p1_plan.tiles_z;
-    grid = small_grid_of(h, (const void*)k_cg_small_p1<8, 4, 8>, 256, sizeof(double) * P1TileGeom<8, 4>::ELEMS, std::max(nvb, by_nodes));
+    if (h->p1_march) {
+      const long long nvb = (long long)h->p1_mplan.n_cta + h->p1_mplan.b.n_bnd_cta;
+      switch (h->p1_march) {
+#define X(ID, NW, NB, MINB)                                                                                              \
+  case ID:                                                                                                               \
+    grid = small_grid_of(h, (const void*)k_cg_small_p1m<NW, NB, MINB>, 32 * (NW + NB),                                   \
+                         sizeof(double) * P1MarchCfg<NW, NB>::PLANE * P1MarchCfg<NW, NB>::ST, std::max(nvb, by_nodes));  \
+    break;
+        LSB_P1_MARCH_CFGS(X)
+#undef X
+      }
+    } else {
+      if (!h->p1_tiles || h->p1_tile_cfg != 1) return;
+      const long long nvb = (long long)h->p1_plan.n_bnd_cta + (long long)h->p1_plan.tiles_x * h->p1_plan.tiles_y * h->p1_plan.tiles_z;
+      grid = small_grid_of(h, (const void*)k_cg_small_p1<8, 4, 8>, 256, sizeof(double) * P1TileGeom<8, 4>::ELEMS, std::max(nvb, by_nodes));
+    }
   }
   if (grid < 1) return;
   if (!h->small_bar) {
@@ -1653,10 +1737,24 @@ static int launch_small(lsb200_ctx* h, int iters) {
     }
   } else {
     const P1Tables tb{{h->p1_m[0], h->p1_m[1], h->p1_m[2]}, h->p1_table, h->p1_off, h->p1_diag};
-    SmallP1 f{h->g, tb, h->p1_plan, h->p1_w * h->p1_w, h->add_ridge ? h->ridge * h->ridge : 0.0};
-    void* args[] = {&a, &f, &h->p1_cls};
-    CK(cudaLaunchCooperativeKernel((void*)k_cg_small_p1<8, 4, 8>, dim3(h->small_grid), dim3(256), args,
-                                   sizeof(double) * P1TileGeom<8, 4>::ELEMS, h->stream));
+    if (h->p1_march) {
+      SmallP1M f{h->g, tb, h->p1_mplan, h->p1_w * h->p1_w, h->add_ridge ? h->ridge * h->ridge : 0.0};
+      void* args[] = {&a, &f, &h->p1_mtaps};
+      switch (h->p1_march) {
+#define X(ID, NW, NB, MINB)                                                                                              \
+  case ID:                                                                                                               \
+    CK(cudaLaunchCooperativeKernel((void*)k_cg_small_p1m<NW, NB, MINB>, dim3(h->small_grid), dim3(32 * (NW + NB)), args,  \
+                                   sizeof(double) * P1MarchCfg<NW, NB>::PLANE * P1MarchCfg<NW, NB>::ST, h->stream));     \
+    break;
+        LSB_P1_MARCH_CFGS(X)
+#undef X
+      }
+    } else {
+      SmallP1 f{h->g, tb, h->p1_plan, h->p1_w * h->p1_w, h->add_ridge ? h->ridge * h->ridge : 0.0};
+      void* args[] = {&a, &f, &h->p1_cls};
+      CK(cudaLaunchCooperativeKernel((void*)k_cg_small_p1<8, 4, 8>, dim3(h->small_grid), dim3(256), args,
+                                     sizeof(double) * P1TileGeom<8, 4>::ELEMS, h->stream));
+    }
   }
   h->launches++;
   return 0;
@@ -2430,6 +2528,10 @@ int lsb200_describe_plan(lsb200_handle h, char* out, int64_t capacity) {
              (h->want_tma && h->g.pitch % 2 == 0) ? "TMA" : "cp.async", h->tuned ? "chosen by timing" : "planner default");
   } else if (h->kind == LSB200_SUPPORT_GRID) {
     snprintf(out, (size_t)capacity, "k_fdi_normal: grid %u x %u x %u, z chunks of %d planes", h->sgrid.x, h->sgrid.y, h->sgrid.z, h->cz);
+  } else if (h->p1_march) {
+    const P1MarchPlan& pl = h->p1_mplan;
+    snprintf(out, (size_t)capacity, "k_p1_march: tiles 64x%d (%d x %d), %d + %d warps, %d z chunks of %d planes, %d CTAs (+%d boundary-only), %d CTAs per SM",
+             2 * h->p1_march_nw, pl.tiles_x, pl.tiles_y, h->p1_march_nw, h->p1_march_nb, pl.chunks, pl.cz, pl.n_cta, pl.b.n_bnd_cta, h->p1_march_minb);
   } else if (h->p1_tiles) {
     const P1TilePlan& pl = h->p1_plan;
     snprintf(out, (size_t)capacity, "k_p1_tiles: tile configuration %d, %d x %d x %d tiles, %d boundary-only CTAs", h->p1_tile_cfg,
@@ -2453,7 +2555,8 @@ int lsb200_debug_cta_trace(lsb200_handle h, int64_t max_ctas, uint64_t* out, int
     ctas = (long long)h->fz.pl.n_box + h->fz.pl.n_xs + h->fz.pl.n_ys;
   } else {
     if (!h->p1_tiles) return fail(LSB200_ERR_STATE, "the per-CTA trace needs the tiled P1 plan");
-    ctas = (long long)h->p1_plan.n_bnd_cta + (long long)h->p1_plan.tiles_x * h->p1_plan.tiles_y * h->p1_plan.tiles_z;
+    ctas = h->p1_march ? (long long)h->p1_mplan.n_cta + h->p1_mplan.b.n_bnd_cta
+                       : (long long)h->p1_plan.n_bnd_cta + (long long)h->p1_plan.tiles_x * h->p1_plan.tiles_y * h->p1_plan.tiles_z;
   }
   if (ctas > max_ctas) return fail(LSB200_ERR_ARG, "the launch has %lld CTAs, the buffer holds %lld", ctas, (long long)max_ctas);
   unsigned long long* buf = nullptr;

@@ -15,6 +15,7 @@
 #include "cg.cuh"
 #include "fdi_fused.cuh"
 #include "p1.cuh"
+#include "p1_march.cuh"
 #include "rows.cuh"
 
 namespace lsb {
@@ -86,6 +87,13 @@ struct SmallP1 {
   GridDesc g;
   P1Tables tb;
   P1TilePlan pl;
+  double w2, ridge2;
+};
+
+struct SmallP1M {
+  GridDesc g;
+  P1Tables tb;
+  P1MarchPlan pl;
   double w2, ridge2;
 };
 
@@ -240,6 +248,23 @@ __global__ void __launch_bounds__(32 * NW)
     for (int vb = (int)blockIdx.x; vb < nvb; vb += (int)gridDim.x) {
       dot += p1_tiles_cta<TY, TZ, NW>(f.g, f.tb, T, f.pl, f.w2, f.ridge2, a.p_all, a.q_all, vb, nvb);
       __syncthreads();  // the tile's shared memory is free for the next one
+    }
+    return dot;
+  });
+}
+
+template <int NW, int NB, int MINB>
+__global__ void __launch_bounds__(32 * (NW + NB), MINB)
+    k_cg_small_p1m(const SmallCgArgs a, const SmallP1M f, const LSB_GRID_CONSTANT P1MarchTaps T) {
+  constexpr int NT = 32 * (NW + NB);
+  __shared__ double red[NT / 32];
+  const int tid = threadIdx.x;
+  const int nvb = f.pl.n_cta + f.pl.b.n_bnd_cta;
+  small_cg_loop<NT>(a, f.g, tid, red, [&]() {
+    double dot = 0.0;
+    for (int vb = (int)blockIdx.x; vb < nvb; vb += (int)gridDim.x) {
+      dot += p1_march_cta<NW, NB>(f.g, f.tb, T, f.pl, f.w2, f.ridge2, a.p_all, a.q_all, vb, nvb);
+      __syncthreads();  // the ring is free for the next chunk
     }
     return dot;
   });

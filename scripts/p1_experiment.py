@@ -26,7 +26,7 @@ def main():
     probe = np.cos(np.arange(q.size) * 0.37)
     out = {"cells": nc, "env": {k: v for k, v in os.environ.items() if k.startswith("LSB200_")},
            "matvec_us": 1e6 * e.time_kernel(0, 20), "iteration_us": 1e6 * e.time_kernel(1, 20),
-           "q_dot_probe": float(q @ probe), "q_norm": float(np.linalg.norm(q)), "p_dot_q": float(p @ q)}
+           "plan": e.describe_plan(), "q_dot_probe": float(q @ probe), "q_norm": float(np.linalg.norm(q)), "p_dot_q": float(p @ q)}
     out["matvec_gbs"] = 16.0 * e.local_dof / out["matvec_us"] / 1e3
     e.close()
     print(json.dumps(out))

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <barrier>
 #include <cmath>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -18,6 +19,15 @@ inline thread_local uint3 t_idx;
 inline uint3 b_idx;
 inline dim3 b_dim, g_dim;
 inline std::barrier<>* cta_barrier = nullptr;
+inline std::barrier<>* named_barrier[16] = {};  // bar.sync id, count: created by the first thread that arrives
+inline std::mutex named_mutex;
+inline void named_sync(int id, int count) {
+  {
+    std::lock_guard<std::mutex> l(named_mutex);
+    if (!named_barrier[id]) named_barrier[id] = new std::barrier<>((std::ptrdiff_t)count);
+  }
+  named_barrier[id]->arrive_and_wait();
+}
 inline std::vector<double> dyn;
 inline double* dyn_smem() { return dyn.data(); }
 
@@ -44,6 +54,10 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
                 cta_barrier->arrive_and_drop();  // a thread that leaves the kernel no longer takes part in barriers
               });
         for (auto& t : th) t.join();
+        for (auto& nb : named_barrier) {
+          delete nb;
+          nb = nullptr;
+        }
       }
 }
 }  // namespace lsb_emu

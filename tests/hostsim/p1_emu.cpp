@@ -35,16 +35,17 @@ inline unsigned long long atomicExch(unsigned long long* a, unsigned long long v
 inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
 
 #include "../../loopstructural_b200/csrc/p1.cuh"
+#include "../../loopstructural_b200/csrc/p1_march.cuh"
 
 using namespace lsb;
 
 namespace {
 constexpr int MAX_PARTIALS = 1 << 18;
-GridDesc make_grid(const int* dims, const double* origin, const double* step) {
+GridDesc make_grid(const int* dims, const double* origin, const double* step, const bool even_pitch = false) {
   GridDesc g{};
   g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
   g.k0 = dims[3]; g.k1 = dims[4]; g.nzl = g.k1 - g.k0;
-  g.pitch = g.nx;
+  g.pitch = even_pitch ? (g.nx + 1) & ~1 : g.nx;  // the library pads rows to an even length (api.cu: lsb200_create)
   g.plane = (long long)g.pitch * g.ny;
   g.nloc = g.plane * g.nzl;
   g.nall = g.plane * (g.nzl + 2 * HALO);
@@ -58,11 +59,13 @@ extern "C" {
 
 // q = (w2 R^T R + ridge2 I) p on the owned planes and diag of the same; dims = {nx, ny, nz, k0, k1}
 // tiles != 0: the k_p1_tiles plan of launch_regularisation with tile configuration tiles - 1 (LSB_P1_TILE_CFGS); returns 1
-// then if the tile kernel was used, 0 if the plan fell back to the generic kernel (no interior)
+// then if the tile kernel was used, 0 if the plan fell back to the generic kernel (no interior).  tiles = 10 + ID of
+// LSB_P1_MARCH_CFGS: k_p1_march, cz = z planes per chunk (0: the plan's own choice).  p_global, q_owned, diag_owned are dense
+// (nx * ny per plane); the emulated device arrays have the library's even row pitch.
 HOSTSIM_API int emu_p1_normal(const int* dims, const double* step, const long long* m, const double* table, double w2,
-                              double ridge2, int tiles, const double* p_global, double* q_owned, double* diag_owned, double* pq_out) {
+                              double ridge2, int tiles, int cz, const double* p_global, double* q_owned, double* diag_owned, double* pq_out) {
   const double origin[3] = {0.0, 0.0, 0.0};
-  const GridDesc g = make_grid(dims, origin, step);
+  const GridDesc g = make_grid(dims, origin, step, true);
   std::vector<double> coef, dg;
   std::vector<int> off;
   size_t bad = 0;
@@ -75,7 +78,8 @@ HOSTSIM_API int emu_p1_normal(const int* dims, const double* step, const long lo
   double* d = dst.data() + guard;
   for (int k = g.k0 - HALO; k < g.k1 + HALO; ++k)
     if (k >= 0 && k < g.nz)
-      memcpy(p + (size_t)(k - g.k0 + HALO) * g.plane, p_global + (size_t)k * g.plane, sizeof(double) * g.plane);
+      for (int j = 0; j < g.ny; ++j)
+        memcpy(p + (size_t)(k - g.k0 + HALO) * g.plane + (size_t)j * g.pitch, p_global + ((size_t)k * g.ny + j) * g.nx, sizeof(double) * g.nx);
   std::vector<double> partials((size_t)MAX_PARTIALS, 0.0);
   unsigned int counter = 0;
   CgScalars sc{};
@@ -99,18 +103,33 @@ HOSTSIM_API int emu_p1_normal(const int* dims, const double* step, const long lo
     break;
     LSB_P1_TILE_CFGS(X)
 #undef X
+#define M(ID, NW, NB, MINB)                                                                                              \
+  case 9 + ID: {                                                                                                         \
+    using MC = P1MarchCfg<NW, NB>;                                                                                       \
+    P1MarchPlan mp;                                                                                                      \
+    P1MarchTaps mt;                                                                                                      \
+    if (p1_plan_march<NW, NB>(g, mi, table, 3, 2, MAX_PARTIALS, cz, &mp, &mt)) {                                         \
+      used_tiles = 1;                                                                                                    \
+      lsb_emu::launch(dim3(mp.n_cta + mp.b.n_bnd_cta), dim3(MC::NT), sizeof(double) * MC::PLANE * MC::ST,                \
+                      [&] { k_p1_march<NW, NB, MINB>(g, tb, mt, mp, w2, ridge2, p, q, partials.data(), &counter, &sc, 0); }); \
+    }                                                                                                                    \
+  } break;
+    LSB_P1_MARCH_CFGS(M)
+#undef M
   }
   if (!used_tiles)
     lsb_emu::launch(dim3(nb), dim3(NT), 0, [&] { k_p1_normal<NT>(g, tb, w2, ridge2, p, q, partials.data(), &counter, &sc, 0); });
   lsb_emu::launch(dim3(nb), dim3(NT), 0, [&] { k_p1_diag(g, tb, w2, ridge2, d); });
-  for (int k = 0; k < g.nzl; ++k) {
-    memcpy(q_owned + (size_t)k * g.plane, q + (size_t)(k + HALO) * g.plane, sizeof(double) * g.plane);
-    memcpy(diag_owned + (size_t)k * g.plane, d + (size_t)(k + HALO) * g.plane, sizeof(double) * g.plane);
-  }
+  for (int k = 0; k < g.nzl; ++k)
+    for (int j = 0; j < g.ny; ++j) {
+      memcpy(q_owned + ((size_t)k * g.ny + j) * g.nx, q + (size_t)(k + HALO) * g.plane + (size_t)j * g.pitch, sizeof(double) * g.nx);
+      memcpy(diag_owned + ((size_t)k * g.ny + j) * g.nx, d + (size_t)(k + HALO) * g.plane + (size_t)j * g.pitch, sizeof(double) * g.nx);
+    }
   *pq_out = sc.pq_part[0];
   for (size_t i = 0; i < qst.size(); ++i) {
     const bool owned = i >= guard + (size_t)HALO * g.plane && i < guard + (size_t)(HALO + g.nzl) * g.plane;
-    if (!owned && (qst[i] == qst[i] || dst[i] != 0.0)) return -2;
+    const bool padding = owned && (int)((i - guard) % (size_t)g.pitch) >= g.nx;
+    if ((!owned || padding) && (qst[i] == qst[i] || dst[i] != 0.0)) return -2;
   }
   return used_tiles;
 }

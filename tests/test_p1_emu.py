@@ -39,7 +39,7 @@ def _bounds(nz, world):
     return partition.slab_bounds(nz, world) if world > 1 else [(0, nz)]
 
 
-@pytest.mark.parametrize("tiles", [0, 1, 2, 3])
+@pytest.mark.parametrize("tiles", [0, 1, 2, 3, (11, 0), (11, 3), (12, 0), (12, 5), (13, 4)])
 @pytest.mark.parametrize("cells,step,world", [((5, 4, 6), (1.0, 1.0, 1.0), 1), ((7, 8, 9), (1.0, 0.7, 1.3), 2),
                                                ((8, 7, 11), (0.9, 1.1, 1.0), 3), ((9, 6, 10), (1.0, 1.0, 2.0), 5),
                                                ((20, 13, 15), (1.0, 1.2, 0.8), 2), ((12, 6, 17), (1.0, 1.0, 1.0), 3),
@@ -48,6 +48,7 @@ def test_face_jump_operator_on_every_slab_matches_the_explicit_rows(emu, cells, 
     """tiles > 0: the k_p1_tiles plan with tile configuration tiles - 1 (interior nodes from de-interleaved shared-memory
     tiles with the eight class tables as constant-bank operands, boundary nodes in the generic form by the first CTAs of
     the same launch); meshes with an axis of <= 6 cells have no interior classes and fall back to k_p1_normal."""
+    tiles, cz = tiles if isinstance(tiles, tuple) else (tiles, 0)
     grid = fo.Grid.from_cells(np.array(cells), np.zeros(3), np.array(step))
     fam = po.face_rows(grid, 1.0)
     R = fam.matrix(grid.n_nodes)
@@ -69,7 +70,7 @@ def test_face_jump_operator_on_every_slab_matches_the_explicit_rows(emu, cells, 
         q, d = np.empty(plane * (k1 - k0)), np.empty(plane * (k1 - k0))
         pq = C.c_double(0.0)
         rc = emu.emu_p1_normal(dims, stp.ctypes.data_as(dp), m.ctypes.data_as(llp), table.ctypes.data_as(dp), C.c_double(w2),
-                               C.c_double(ridge2), tiles, p.ctypes.data_as(dp), q.ctypes.data_as(dp), d.ctypes.data_as(dp), C.byref(pq))
+                               C.c_double(ridge2), tiles, cz, p.ctypes.data_as(dp), q.ctypes.data_as(dp), d.ctypes.data_as(dp), C.byref(pq))
         assert rc >= 0, f"slab {k0, k1}: rc {rc} (-2 = written outside the owned planes)"
         assert rc == (1 if tiles and min(cells) > 6 else 0), (rc, cells, (k0, k1))
         sl = slice(k0 * plane, k1 * plane)
