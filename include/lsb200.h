@@ -55,7 +55,12 @@ enum {
   LSB200_ROWS_VALUE = 0,    /* data (n,5): x y z value w        -> 1 row / point  */
   LSB200_ROWS_GRADIENT = 1, /* data (n,7): x y z gx gy gz w     -> 2 rows / point */
   LSB200_ROWS_NORMAL = 2,   /* data (n,7): x y z nx ny nz w     -> 3 rows / point */
-  LSB200_ROWS_TANGENT = 3   /* data (n,7): x y z tx ty tz b     -> 1 row / point  */
+  LSB200_ROWS_TANGENT = 3,  /* data (n,7): x y z tx ty tz b     -> 1 row / point  */
+  /* tet meshes only: v . grad(phi) = b on the tetrahedron that holds the point (its barycentre, for the callers this
+   * exists for); unlike a tangent row v is taken as given and the weight is not multiplied by the element volume.  The
+   * fold orientation / fold axis / fold normalisation rows of DiscreteFoldInterpolator.add_fold_constraints
+   * (LI/_discrete_fold_interpolator.py:116-190): vol (v . eg) x = vol b, L2-normalised like every row. */
+  LSB200_ROWS_ELEMENT_VECTOR = 4 /* data (n,7): x y z vx vy vz b -> 1 row / point */
 };
 
 /* support kinds */
@@ -132,6 +137,17 @@ int lsb200_add_rows(lsb200_handle h, int64_t n_rows, int k, const double* vals, 
  * n_rows_out (may be NULL) receives the number of rows created. */
 int lsb200_add_point_rows(lsb200_handle h, int kind, int64_t n, const double* data, int ncols,
                           double weight, int64_t* n_rows_out);
+
+/* Direction-weighted face-jump rows of a tet mesh: v_f . (grad phi_a - grad phi_b) = 0 for n pairs of face-adjacent
+ * tetrahedra, P1Interpolator.minimise_edge_jumps with a vector per shared face (LI/_p1interpolator.py:115-166) -- what
+ * DiscreteInterpolator.add_directional_regularisation (LI/_discrete_interpolator.py:413-451) and the 'fold regularisation
+ * n' families of DiscreteFoldInterpolator.add_fold_constraints (LI/_discrete_fold_interpolator.py:204-242) put into the
+ * system.  nodes_a, nodes_b are (n,4) row-major GLOBAL node ids of the two tetrahedra (support.elements[tri]), vectors
+ * (n,3) the direction at the shared face; 8 listed entries per row, L2-normalised over them as the reference does before
+ * its duplicate merge, right-hand side 0, weight the family weight.  Rows holding a NaN are dropped (the reference drops
+ * the whole family then: the caller checks).  n_rows_out (may be NULL) receives the number of rows kept. */
+int lsb200_add_face_vector_rows(lsb200_handle h, int64_t n, const int64_t* nodes_a, const int64_t* nodes_b,
+                                const double* vectors, double weight, int64_t* n_rows_out);
 
 /* Interface rows N(x_i) - N(x_j) = 0 for n point pairs (FDI.add_interface_constraints,
  * LI/_finite_difference_interpolator.py:297-340): 16 listed entries per row, weight ipw.  The pairing per

@@ -794,14 +794,6 @@ int lsb200_set_p1_tables(lsb200_handle h, const int64_t m[3], const double* tabl
     }                                                                                                                \
     if (p1_plan_march<NW, NB>(h->g, h->p1_m, table, h->sm_count, per_sm, MAX_PARTIALS, march_cz, &h->p1_mplan, &h->p1_mtaps)) { \
       h->p1_march = ID;                                                                                              \
-      if (getenv("LSB200_P1_MARCH_SKIP") && atoi(getenv("LSB200_P1_MARCH_SKIP")) == 1) { /* timing only: no boundary */  \
-        h->p1_mplan.b.nbz = h->p1_mplan.b.nby = h->p1_mplan.b.nbx = 0;                                               \
-        h->p1_mplan.b.n_bnd_cta = 0;                                                                                 \
-      }                                                                                                              \
-      if (getenv("LSB200_P1_MARCH_SKIP") && atoi(getenv("LSB200_P1_MARCH_SKIP")) == 2) { /* timing only: no tiles */     \
-        h->p1_mplan.b.n_bnd_cta += h->p1_mplan.n_cta;                                                                \
-        h->p1_mplan.n_cta = 0;                                                                                       \
-      }                                                                                                              \
       h->p1_march_nw = NW;                                                                                           \
       h->p1_march_nb = NB;                                                                                           \
       h->p1_march_minb = per_sm;                                                                                     \
@@ -894,7 +886,9 @@ int lsb200_add_point_rows(lsb200_handle h, int kind, int64_t n, const double* da
   if (n_rows_out) *n_rows_out = 0;
   if (n < 0) return fail(LSB200_ERR_ARG, "negative point count");
   const int need = kind == LSB200_ROWS_VALUE ? 5 : 7;
-  if (kind < LSB200_ROWS_VALUE || kind > LSB200_ROWS_TANGENT) return fail(LSB200_ERR_ARG, "unknown row kind %d", kind);
+  if (kind < LSB200_ROWS_VALUE || kind > LSB200_ROWS_ELEMENT_VECTOR) return fail(LSB200_ERR_ARG, "unknown row kind %d", kind);
+  if (kind == LSB200_ROWS_ELEMENT_VECTOR && h->kind != LSB200_SUPPORT_TETMESH)
+    return fail(LSB200_ERR_STATE, "element-vector rows need a tet-mesh handle");
   if (ncols < need) return fail(LSB200_ERR_ARG, "row kind %d needs %d data columns, got %d", kind, need, ncols);
   if (n == 0) return 0;
   if (!data) return fail(LSB200_ERR_ARG, "null data");
@@ -926,6 +920,70 @@ int lsb200_add_point_rows(lsb200_handle h, int kind, int64_t n, const double* da
   CK(cudaMemcpyAsync(st, h->status, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   pool_free(h, dd);
+  if (n_rows_out) *n_rows_out = (int64_t)st[0];
+  h->rows_kept += (long long)st[0];
+  h->pending.push_back(rb);
+  h->finalized = false;
+  return 0;
+}
+
+int lsb200_add_face_vector_rows(lsb200_handle h, int64_t n, const int64_t* nodes_a, const int64_t* nodes_b,
+                                const double* vectors, double weight, int64_t* n_rows_out) {
+  if (!h) return fail(LSB200_ERR_ARG, "null handle");
+  if (n_rows_out) *n_rows_out = 0;
+  if (n < 0) return fail(LSB200_ERR_ARG, "negative face count");
+  if (h->kind != LSB200_SUPPORT_TETMESH) return fail(LSB200_ERR_STATE, "face-vector rows need a tet-mesh handle");
+  if (n == 0) return 0;
+  if (!nodes_a || !nodes_b || !vectors) return fail(LSB200_ERR_ARG, "null face arrays");
+  CK(cudaSetDevice(h->device));
+  long long *da = nullptr, *dbn = nullptr, *dc = nullptr;
+  double *dvec = nullptr, *dv = nullptr, *db = nullptr, *dw = nullptr;
+  RowBlock rb{};
+  auto release = [&]() { pool_free(h, da); pool_free(h, dbn); pool_free(h, dc); pool_free(h, dvec); pool_free(h, dv); pool_free(h, db); pool_free(h, dw); };
+  auto stage = [&]() -> int {
+    CK(cudaMallocAsync(&da, sizeof(long long) * 4 * n, h->stream));
+    CK(cudaMallocAsync(&dbn, sizeof(long long) * 4 * n, h->stream));
+    CK(cudaMallocAsync(&dvec, sizeof(double) * 3 * n, h->stream));
+    CK(cudaMallocAsync(&dv, sizeof(double) * 8 * n, h->stream));
+    CK(cudaMallocAsync(&dc, sizeof(long long) * 8 * n, h->stream));
+    CK(cudaMallocAsync(&db, sizeof(double) * n, h->stream));
+    CK(cudaMallocAsync(&dw, sizeof(double) * n, h->stream));
+    CK(cudaMemcpyAsync(da, nodes_a, sizeof(long long) * 4 * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dbn, nodes_b, sizeof(long long) * 4 * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dvec, vectors, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * 4, h->stream));
+    const int nb = (int)std::min<long long>((n + 255) / 256, 4096);
+    k_p1_face_vector_vals<<<nb, 256, 0, h->stream>>>(h->g, n, da, dbn, dvec, weight, dv, dc, db, dw);
+    CKL();
+    int rc = alloc_block(h, rb, n, width_class(8));
+    if (rc) return rc;
+    CK(cudaMemsetAsync(rb.cols, 0xff, sizeof(int) * rb.n * rb.k, h->stream));
+    CK(cudaMemsetAsync(rb.vals, 0, sizeof(double) * rb.n * rb.k, h->stream));
+    k_rows_ingest<<<nb, 256, 0, h->stream>>>(h->g, n, 8, dv, dc, db, dw, 1, rb, 0, h->status);
+    CKL();
+    h->launches += 2;
+    return 0;
+  };
+  unsigned long long st[4] = {0, 0, 0, 0};
+  int rc = stage();
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(st, h->status, sizeof(st), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) rc = fail(LSB200_ERR_CUDA, "face-vector rows failed: %s", cudaGetErrorString(e));
+  }
+  release();
+  if (rc) {
+    free_block(h, rb);
+    return rc;
+  }
+  if (st[2]) {
+    free_block(h, rb);
+    return fail(LSB200_ERR_ARG, "node id %lld outside [0,%lld)", (long long)st[3], (long long)h->g.nx * h->g.ny * h->g.nz);
+  }
+  if (st[1]) {
+    free_block(h, rb);
+    return fail(LSB200_ERR_ARG, "a face touching the owned planes [%d,%d) has a node outside the halo planes", h->g.k0, h->g.k1);
+  }
   if (n_rows_out) *n_rows_out = (int64_t)st[0];
   h->rows_kept += (long long)st[0];
   h->pending.push_back(rb);

@@ -492,7 +492,8 @@ LSB_HD double tet_gradients(const double v[4][3], double G[3][4]) {
 
 // K4: P1 rows from constraint points (LI/_p1interpolator.py:73-113,248-296).  value: the 4 barycentrics, b = value,
 // w = cpw (the per-point weight column is not used); normal: three rows grad phi[d,:] with b = n_d, w = npw;
-// tangent / orthogonal: v_hat . grad phi = b, w = tpw * tet volume.  Rows are L2-normalised; mult rows per point at
+// tangent / orthogonal: v_hat . grad phi = b, w = tpw * tet volume; element vector (fold rows): v . grad phi = b, w as given.
+// Rows are L2-normalised; mult rows per point at
 // row0 + 3*point + d for normals (the reference flattens the (n,3,4) block point-major), else row0 + point.
 __global__ void k_p1_point_rows(const GridDesc g, const int kind, const long long n, const double* __restrict__ data,
                                 const int ncols, const double weight, RowBlock rb, const long long row0,
@@ -502,7 +503,7 @@ __global__ void k_p1_point_rows(const GridDesc g, const int kind, const long lon
     const double x[3] = {d[0], d[1], d[2]};
     const TetLoc L = locate_tet(g, x);
     bool ok = L.inside;
-    const int used = kind == LSB200_ROWS_VALUE ? 4 : (kind == LSB200_ROWS_TANGENT ? 7 : 6);
+    const int used = kind == LSB200_ROWS_VALUE ? 4 : (kind == LSB200_ROWS_TANGENT || kind == LSB200_ROWS_ELEMENT_VECTOR ? 7 : 6);
     for (int c = 0; c < used; ++c) ok = ok && (d[c] == d[c]);
     // slab: keep the row when its cell touches an owned plane (as k_fdi_point_rows does)
     ok = ok && (L.cz + 1 >= g.k0) && (L.cz < g.k1);
@@ -524,6 +525,12 @@ __global__ void k_p1_point_rows(const GridDesc g, const int kind, const long lon
             for (int c = 0; c < 4; ++c) A[a][c] = G[a][c];
             bb[a] = d[3 + a];
           }
+        } else if (kind == LSB200_ROWS_ELEMENT_VECTOR) {
+          // fold rows (LI/_discrete_fold_interpolator.py:116-190): the volume factor of A and B cancels in the row
+          // normalisation, the weight is the caller's
+#pragma unroll
+          for (int c = 0; c < 4; ++c) A[0][c] = d[3] * G[0][c] + d[4] * G[1][c] + d[5] * G[2][c];
+          bb[0] = d[6];
         } else {
           const double len = sqrt(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
           double vv[3] = {d[3], d[4], d[5]};
@@ -551,6 +558,46 @@ __global__ void k_p1_point_rows(const GridDesc g, const int kind, const long lon
       }
       rb.b[ro] = good ? (len > 0.0 ? bb[m] / len : bb[m]) : 0.0;
       rb.w2[ro] = good ? ww * ww : 0.0;
+    }
+  }
+}
+
+// Direction-weighted face-jump rows, P1Interpolator.minimise_edge_jumps with a vector per shared face
+// (LI/_p1interpolator.py:115-166; the 'fold regularisation n' families of DiscreteFoldInterpolator, and every
+// DirectionalRegularisation term of a P1 interpolator): v . (grad phi_a - grad phi_b) = 0 over the 4 + 4 listed nodes of the
+// two tetrahedra (global node ids; the three shared nodes appear twice, as in the reference before its coo -> csc merge).
+// Writes the (n, 8) values and column ids, b = 0 and w = weight: what k_rows_ingest then normalises and stores.
+__global__ void k_p1_face_vector_vals(const GridDesc g, const long long n, const long long* __restrict__ nodes_a,
+                                      const long long* __restrict__ nodes_b, const double* __restrict__ vec,
+                                      const double weight, double* __restrict__ vals, long long* __restrict__ cols,
+                                      double* __restrict__ b, double* __restrict__ w) {
+  const long long nxny = (long long)g.nx * g.ny, ntot = nxny * g.nz;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    const double v[3] = {vec[3 * r], vec[3 * r + 1], vec[3 * r + 2]};
+    b[r] = 0.0;
+    w[r] = weight;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const long long* nd = (side ? nodes_b : nodes_a) + 4 * r;
+      double X[4][3], G[3][4];
+      bool ok = true;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const long long id = nd[c];
+        ok = ok && id >= 0 && id < ntot;
+        const long long kz = id / nxny, rem = id - kz * nxny;
+        const long long jy = rem / g.nx, ix = rem - jy * g.nx;
+        X[c][0] = g.origin[0] + g.step[0] * (double)ix;
+        X[c][1] = g.origin[1] + g.step[1] * (double)jy;
+        X[c][2] = g.origin[2] + g.step[2] * (double)kz;
+        cols[8 * r + 4 * side + c] = id;  // an id outside the mesh is reported by k_rows_ingest
+      }
+      if (ok) tet_gradients(X, G);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double a = ok ? v[0] * G[0][c] + v[1] * G[1][c] + v[2] * G[2][c] : 0.0;
+        vals[8 * r + 4 * side + c] = side ? -a : a;
+      }
     }
   }
 }

@@ -30,13 +30,16 @@ struct P1MarchPlan {
   int n_cta;               // tiles_x * tiles_y * chunks
 };
 
-// X(ID, marching warps, boundary warps, CTAs per SM the kernel is compiled for); LSB200_P1_MARCH = ID (0: k_p1_tiles instead)
+// X(ID, marching warps, boundary warps, CTAs per SM the kernel is compiled for); LSB200_P1_MARCH = ID (0: k_p1_tiles instead).
+// Measured on config 3 (118^3 nodes, profiles/r2ak_p1_march.txt), operator / CG iteration of the persistent loop in us:
+// k_p1_tiles 41.1 / 58.3; 1: 27.5 / 54.3; 3: 25.2 / 48.0.  (Patches of 2 x 1 columns, twice the marching warps with half
+// the accumulators each, were no faster: 28.4 / 49.2 -- the march is not short of warps.)
 #define LSB_P1_MARCH_CFGS(X) \
   X(1, 4, 0, 3)              \
   X(2, 4, 2, 2)              \
   X(3, 4, 4, 2)              \
   X(4, 4, 2, 3)
-#define LSB_P1_MARCH_DEFAULT 2
+#define LSB_P1_MARCH_DEFAULT 3
 constexpr int P1M_BND_PER_THREAD = 6;  // boundary nodes a thread may be given before the plan adds boundary-only CTAs
 template <int NW, int NB = 0>
 struct P1MarchCfg {
@@ -74,16 +77,21 @@ inline bool p1_plan_march(const GridDesc& g, const int m[3], const double* table
   // chunks: as many as fit the CTA slots at once (a second wave would double the launch), at least 8 planes per chunk
   // (each chunk re-stages 4 halo planes)
   const long long tiles = (long long)pl.tiles_x * pl.tiles_y, slots = (long long)sm_count * ctas_per_sm;
+  const long long nb = pl.b.nbz + pl.b.nby + pl.b.nbx;
+  const long long per_cta = (long long)C::NT * P1M_BND_PER_THREAD;
   int chunks = (int)std::max<long long>(1, slots / tiles);
   chunks = std::max(1, std::min(chunks, std::max(1, planes / 8)));
   if (cz_override > 0) chunks = std::max(1, (planes + cz_override - 1) / cz_override);
-  pl.cz = planes > 0 ? (planes + chunks - 1) / chunks : 1;
-  pl.chunks = planes > 0 ? (planes + pl.cz - 1) / pl.cz : 0;
-  pl.n_cta = (int)(tiles * pl.chunks);
-  // boundary-only CTAs when the tiles are too few to carry the boundary shares (slabs without interior planes)
-  const long long nb = pl.b.nbz + pl.b.nby + pl.b.nbx;
-  const long long carried = (long long)pl.n_cta * C::NBT * P1M_BND_PER_THREAD, per_cta = (long long)C::NT * P1M_BND_PER_THREAD;
-  pl.b.n_bnd_cta = carried >= nb ? 0 : (int)((nb - carried + per_cta - 1) / per_cta);
+  for (;; --chunks) {
+    pl.cz = planes > 0 ? (planes + chunks - 1) / chunks : 1;
+    pl.chunks = planes > 0 ? (planes + pl.cz - 1) / pl.cz : 0;
+    pl.n_cta = (int)(tiles * pl.chunks);
+    // boundary-only CTAs when the tiles are too few to carry the boundary shares (always: slabs without interior planes)
+    const long long carried = (long long)pl.n_cta * C::NBT * P1M_BND_PER_THREAD;
+    pl.b.n_bnd_cta = carried >= nb ? 0 : (int)((nb - carried + per_cta - 1) / per_cta);
+    // they too belong to the first wave: fewer, longer chunks until they fit (or nothing is left to give)
+    if (cz_override > 0 || chunks <= 1 || (long long)pl.n_cta + pl.b.n_bnd_cta <= slots) break;
+  }
   if ((long long)pl.n_cta + pl.b.n_bnd_cta > max_blocks) return false;
   memset(T, 0, sizeof(*T));
   for (int cls = 0; cls < 8; ++cls) {

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _native as nat
 
-ROWS_VALUE, ROWS_GRADIENT, ROWS_NORMAL, ROWS_TANGENT = 0, 1, 2, 3
+ROWS_VALUE, ROWS_GRADIENT, ROWS_NORMAL, ROWS_TANGENT, ROWS_ELEMENT_VECTOR = 0, 1, 2, 3, 4
 PART_REGULARISATION, PART_ROWS, PART_RIDGE = 1, 2, 4
 
 # FDI weight defaults, LI/_finite_difference_interpolator.py:102-119
@@ -212,6 +212,20 @@ class Engine:
         out = C.c_int64(0)
         nat.check(self._lib.lsb200_add_pair_rows(self._h, xi.shape[0], nat.dptr(xi), nat.dptr(xj), float(weight),
                                                  C.byref(out)))
+        return int(out.value)
+
+    def add_face_vector_rows(self, nodes_a, nodes_b, vectors, weight: float) -> int:
+        """P1Interpolator.minimise_edge_jumps with a vector per shared face (LI/_p1interpolator.py:115-166): one row
+        v . (grad phi_a - grad phi_b) = 0 per pair of face-adjacent tetrahedra, given by their (n,4) global node ids."""
+        a = np.ascontiguousarray(nodes_a, dtype=np.int64)
+        b = np.ascontiguousarray(nodes_b, dtype=np.int64)
+        v = nat.as_f64(vectors)
+        if a.ndim != 2 or a.shape[1] != 4 or b.shape != a.shape or v.shape != (a.shape[0], 3):
+            raise ValueError("nodes_a, nodes_b must be (n,4) and vectors (n,3)")
+        out = C.c_int64(0)
+        nat.check(self._lib.lsb200_add_face_vector_rows(self._h, a.shape[0], a.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                        b.ctypes.data_as(C.POINTER(C.c_int64)), nat.dptr(v), float(weight),
+                                                        C.byref(out)))
         return int(out.value)
 
     def add_field_orthogonal_rows(self, other: "Engine", step: int = 10, weight: float = 1.0, b: float = 0.0,

@@ -89,6 +89,14 @@ def _load_rows(it, eng, skip=()) -> int:
     for other, w2l, step, w, b, _stock, _pos in getattr(it, "_b200_device_rows", []):
         # frame-orthogonality families diverted by the builder patch: generated on the device from the other field
         n_rows += eng.add_field_orthogonal_rows(other, step=step, weight=w, b=b, other_world_to_local=w2l)
+    for fam in getattr(it, "_b200_generated", []):
+        # fold rows and direction-weighted face rows: generated on the device from points / faces and their vectors
+        if fam["type"] == "element":
+            n_rows += eng.add_point_rows(fam["kind"], fam["data"], fam["weight"])
+        else:
+            el = np.asarray(it.support.elements)
+            rel = np.asarray(it.support.shared_element_relationships)
+            n_rows += eng.add_face_vector_rows(el[rel[:, 0]], el[rel[:, 1]], fam["vectors"], fam["weight"])
     return n_rows
 
 
@@ -210,11 +218,15 @@ class _B200Mixin:
         # (other engine, its world_to_local, element step, weight, b, stock, position) per diverted orthogonality
         # family; stock() assembles the same family on the host (used when a stock solver is asked for after all)
         self._b200_device_rows = []
+        # families generated on the device from host vectors (fold rows, direction-weighted face rows): dicts with
+        # type 'element' (kind, data (n,7), weight) or 'face' (vectors (n_faces,3), weight), name, pos, stock
+        self._b200_generated = []
 
     def setup_interpolator(self, **kwargs):
         self._b200_setup_kwargs = dict(kwargs)
         self._b200_reg, self._b200_reg_ops, self._b200_explicit = {}, {}, {}
         self._b200_device_rows = []
+        self._b200_generated = []
         self._b200_divert = (self._b200_supported(kwargs) and kwargs.get("solver") in B200_SOLVERS
                              and not kwargs.get("use_regularisation_weight_scale", False))
         return super().setup_interpolator(**kwargs)
@@ -241,6 +253,7 @@ class _B200Mixin:
         self.regularisation_scale = np.ones(self.dof)
         todo = [(pos, lambda n=name, p=payload: self._b200_assemble_recorded(n, p)) for name, (pos, payload) in self._b200_reg_ops.items()]
         todo += [(entry[6], entry[5]) for entry in self._b200_device_rows]
+        todo += [(fam["pos"], fam["stock"]) for fam in self._b200_generated]
         placed = []
         for pos, run in todo:
             before = set(self.constraints)
@@ -253,7 +266,7 @@ class _B200Mixin:
             order[pos + shift:pos + shift] = keys
             shift += len(keys)
         self.constraints = {k: self.constraints[k] for k in order}
-        self._b200_reg, self._b200_reg_ops, self._b200_device_rows = {}, {}, []
+        self._b200_reg, self._b200_reg_ops, self._b200_device_rows, self._b200_generated = {}, {}, [], []
 
     def _b200_get_engine(self):
         """One engine per interpolator, kept across solves (7 node vectors of device memory)."""
@@ -501,6 +514,23 @@ def _make_tet_class(base, name, doc):
                 self._b200_reg["cgw"] = float(w)
                 self._b200_record("cgw", w)
                 return
+            if (self._b200_divert and vector_func is None and vector is not None and np.ndim(w) == 0
+                    and self._b200_supported(self._b200_setup_kwargs)
+                    and not self._b200_setup_kwargs.get("use_regularisation_weight_scale", False)):
+                # a direction per shared face (add_directional_regularisation, the fold regularisation families): the rows
+                # v . (grad phi_T1 - grad phi_T2) = 0 are generated on the device from the two tetrahedra of a face.  A
+                # vector of any other length is ignored by the reference (LI/_p1interpolator.py:130-131) and a NaN drops
+                # the family (LI/_discrete_interpolator.py:357-359): both stay with the stock method.
+                vec = np.asarray(vector, dtype=np.float64)
+                cells = [int(v) - 1 for v in self.support.nsteps]
+                n_faces = 10 * cells[0] * cells[1] * cells[2] - 2 * (cells[0] * cells[1] + cells[1] * cells[2] + cells[2] * cells[0])
+                if vec.shape == (n_faces, 3) and not np.isnan(vec).any():
+                    stock = super().minimise_edge_jumps
+                    self._b200_generated.append(dict(
+                        type="face", vectors=vec, weight=float(w), name=name, pos=len(self.constraints),
+                        stock=lambda: stock(w=w, vector_func=None, vector=vector, name=name)))
+                    self.up_to_date = False
+                    return
             before = set(self.constraints)
             out = super().minimise_edge_jumps(w=w, vector_func=vector_func, vector=vector, name=name)
             new = set(self.constraints) - before
@@ -548,12 +578,102 @@ def _make_dfi_class():
     """DiscreteFoldInterpolator (LI/_discrete_fold_interpolator.py:21-242; every folded foliation / folded fold frame is
     built with it, LoopStructural/modelling/core/_model_feature_factory.py:248-250) on the same engine path as P1: its
     fold orientation / axis / normalisation rows and its direction-weighted face rows ('fold regularisation n',
-    minimise_edge_jumps with a vector_func) stay explicit families and reach the device through lsb200_add_rows; a
-    plain 'edge jump' family, when the builder asks for one, is applied matrix-free like P1's."""
+    minimise_edge_jumps with a vector per shared face) are generated on the device from the fold vectors the reference's
+    FoldEvent computes on the host; a plain 'edge jump' family, when the builder asks for one, is applied matrix-free
+    like P1's."""
+    import inspect
+
+    from loop_common.math import rng  # the module-level generator the reference shuffles the elements with
     from loop_interpolation._discrete_fold_interpolator import DiscreteFoldInterpolator
 
-    return _make_tet_class(DiscreteFoldInterpolator, "B200DiscreteFoldInterpolator",
+    from . import engine as en
+
+    base = _make_tet_class(DiscreteFoldInterpolator, "B200DiscreteFoldInterpolator",
                            "DiscreteFoldInterpolator whose ``solver='b200'`` runs on the GPU engine.")
+    stock_sig = inspect.signature(DiscreteFoldInterpolator.add_fold_constraints)
+
+    class B200DFI(base):
+        def add_fold_constraints(self, *args, **kwargs):
+            """DiscreteFoldInterpolator.add_fold_constraints (LI/_discrete_fold_interpolator.py:66-242) for a diverted
+            set-up: the same elements (the reference's generator is shuffled exactly as the stock method shuffles it), the
+            same fold vectors (FoldEvent.get_deformed_orientation, host code of the reference), but no element-gradient
+            table, no einsum and no sparse matrix on the host: a family is its barycentres, vectors and target, and its
+            rows are generated on the device at solve time (LSB200_ROWS_ELEMENT_VECTOR); the three direction-weighted
+            face families go through minimise_edge_jumps above (lsb200_add_face_vector_rows)."""
+            a = stock_sig.bind(self, *args, **kwargs)
+            a.apply_defaults()
+            a = a.arguments
+            if not self._b200_divert or "dgz_alignment" not in a:
+                return super().add_fold_constraints(*args, **kwargs)
+            from loop_interpolation._fold_norm_alignment import resolve_fold_norm_target
+
+            sup, step, mask_fn = self.support, a["step"], a["mask_fn"]
+            bary = np.asarray(sup.barycentre, dtype=np.float64)
+            deformed, axis, dgz = self.fold.get_deformed_orientation(bary)
+            element_idx = np.arange(sup.n_elements)
+            rng.shuffle(element_idx)
+            weight = np.ones(sup.n_elements, dtype=float)
+            if mask_fn is not None:
+                weight[mask_fn(bary)] = 0
+            for name, w, vec in (("fold orientation", a["fold_orientation"], deformed), ("fold axis", a["fold_axis_w"], axis),
+                                 ("fold normalisation", a["fold_normalisation"], dgz)):
+                if w is None:
+                    continue
+                rng.shuffle(element_idx)
+                sel = element_idx[::step].copy()
+                target = 0.0
+                if name == "fold normalisation":
+                    target = w * resolve_fold_norm_target(
+                        fold=self.fold, normal_constraints=self.get_norm_constraints(), fold_norm=a["fold_norm"],
+                        dgz_alignment=a["dgz_alignment"], logger=_fold_logger(), default_fold_norm=-1.0)
+                self._b200_add_element_family(name, sel, np.asarray(vec, dtype=np.float64), float(w), float(target), weight, bary)
+            reg = a["fold_regularisation"]
+            if reg is not None:
+                # add_directional_regularisation (LI/_discrete_interpolator.py:413-451) with the three providers of the stock
+                # method (normal, deformed orientation, axis at the shared-face centres), one fold evaluation instead of three
+                pts = np.asarray(self.get_regularisation_sample_points(), dtype=float)
+                d_f, a_f, n_f = self.fold.get_deformed_orientation(pts)
+                for i, vec in enumerate((n_f, d_f, a_f)):
+                    if reg[i] == 0:
+                        continue
+                    vec = np.asarray(vec, dtype=float)
+                    if mask_fn is not None:
+                        vec = vec.copy()
+                        vec[mask_fn(pts)] = 0.0
+                    if vec.shape != pts.shape:
+                        continue
+                    self._add_directional_regularisation(reg[i], vec, name=f"fold regularisation {i + 1}")
+
+        def _b200_add_element_family(self, name, sel, vec, w, target, weight, bary):
+            v = vec[sel]
+            sup = self.support
+
+            def stock():
+                # the same family on the host (a stock solver was asked for after all): vol (v . eg) x = vol target
+                eg = sup.get_element_gradients(sel)
+                idc = sup.get_elements()[sel]
+                nodes = sup.nodes[idc]
+                vol = np.abs(np.linalg.det(nodes[:, 1:, :] - nodes[:, 0, None, :])) / 6
+                self.add_constraints_to_least_squares(np.einsum("ij,ijk->ik", v, eg) * vol[:, None], np.ones(len(sel)) * target * vol,
+                                                      idc, w=weight[sel] * w, name=name)
+
+            if np.isnan(v).any() or not np.isfinite(target):
+                return stock()  # the reference drops such a family with a warning (LI/_discrete_interpolator.py:357-359)
+            keep = weight[sel] > 0
+            data = np.column_stack([bary[sel][keep], v[keep], np.full(int(keep.sum()), target)])
+            self._b200_generated.append(dict(type="element", kind=en.ROWS_ELEMENT_VECTOR, data=data, weight=w, name=name,
+                                             pos=len(self.constraints), stock=stock))
+            self.up_to_date = False
+
+    B200DFI.__name__ = B200DFI.__qualname__ = "B200DiscreteFoldInterpolator"
+    B200DFI.__doc__ = base.__doc__
+    return B200DFI
+
+
+def _fold_logger():
+    import logging
+
+    return logging.getLogger("loop_interpolation._discrete_fold_interpolator")
 
 
 # -- fault frames: FaultSegment.apply_to_points / evaluate_displacement on the device -------------------------------

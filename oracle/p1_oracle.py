@@ -9,7 +9,11 @@ Restates, with explicit arrays and brute-force topology:
     gradient-orthogonal / tangent rows with w * tet volume (:248-296), face gradient-jump regularisation
     minimise_edge_jumps (:115-166) over every interior shared face;
   row normalisation of add_constraints_to_least_squares (LI/_discrete_interpolator.py:361-366).
-Pinned against tests/golden/p1_*.npz, which tests/golden/make_golden_p1.py wrote from the unmodified reference.
+  DiscreteFoldInterpolator.add_fold_constraints (LI/_discrete_fold_interpolator.py:116-242): one row vol (v . eg) = vol b
+    per selected tetrahedron (element_vector_rows) and direction-weighted face-jump rows (face_vector_rows:
+    minimise_edge_jumps with a vector per shared face, LI/_p1interpolator.py:115-166).
+Pinned against tests/golden/p1_*.npz and fold_rows_*.npz, which tests/golden/make_golden_p1.py / make_golden_fold.py
+wrote from the unmodified reference.
 """
 from __future__ import annotations
 
@@ -144,6 +148,29 @@ def orthogonal_rows(grid: Grid, xyz: np.ndarray, vectors: np.ndarray, w: float =
     g = tet_gradients(v[ins])
     A = np.einsum("ij,ijk->ik", vec[ins], g)
     return make_family(name, A, np.zeros(int(ins.sum())) + b, ids[ins], w * tet_volume(v[ins]))
+
+
+def element_vector_rows(grid: Grid, xyz: np.ndarray, vectors: np.ndarray, w: float = 1.0, b: float = 0.0,
+                        name: str = "fold orientation"):
+    """LI/_discrete_fold_interpolator.py:116-190 for the tetrahedra that hold ``xyz`` (their barycentres in the reference):
+    A = vol (v . eg), B = vol b, weight w -- neither is v normalised nor the weight scaled by the volume."""
+    if xyz.shape[0] == 0:
+        return None
+    _c, ids, v, _t, ins = locate(grid, xyz[:, :3])
+    vol = tet_volume(v[ins])
+    A = np.einsum("ij,ijk->ik", np.asarray(vectors, float)[ins], tet_gradients(v[ins])) * vol[:, None]
+    return make_family(name, A, (np.zeros(int(ins.sum())) + b) * vol, ids[ins], w)
+
+
+def face_vector_rows(grid: Grid, nodes_a: np.ndarray, nodes_b: np.ndarray, vectors: np.ndarray, w: float,
+                     name: str = "directional edge jump"):
+    """minimise_edge_jumps with ``vector`` (LI/_p1interpolator.py:115-166): v . (grad phi_a - grad phi_b) = 0 over the 4 + 4
+    listed nodes of two face-adjacent tetrahedra given by their global node ids."""
+    g1 = tet_gradients(node_xyz(grid, np.asarray(nodes_a)))
+    g2 = tet_gradients(node_xyz(grid, np.asarray(nodes_b)))
+    v = np.asarray(vectors, float)
+    A = np.hstack([np.einsum("ij,ijk->ik", v, g1), -np.einsum("ij,ijk->ik", v, g2)])
+    return make_family(name, A, np.zeros(A.shape[0]), np.hstack([nodes_a, nodes_b]), w)
 
 
 def evaluate_value(grid: Grid, pts: np.ndarray, cvec: np.ndarray) -> np.ndarray:

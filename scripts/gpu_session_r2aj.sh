@@ -22,3 +22,9 @@ for l in open('gpurun_out/r2aj_p1_march.txt'):
     print(d['env'].get('LSB200_P1_MARCH'), d['env'].get('LSB200_P1_MARCH_CZ'), round(d['matvec_us'], 2), round(d['iteration_us'], 2), d['q_dot_probe'], d['p_dot_q'], d['plan'][12:130])
 PY
 cat gpurun_out/r2aj_trace.txt
+# one ncu capture of the default configuration (source-level stall reasons)
+timeout 200 ncu --set full --import-source on --clock-control none -k regex:k_p1_march -s 5 -c 1 -o gpurun_out/r2aj_p1_march python scripts/p1_experiment.py 117 > gpurun_out/r2aj_ncu.log 2>&1
+ncu -i gpurun_out/r2aj_p1_march.ncu-rep --page details --csv > gpurun_out/r2aj_ncu_details.csv 2>/dev/null
+ncu -i gpurun_out/r2aj_p1_march.ncu-rep --page source --csv > gpurun_out/r2aj_ncu_source.csv 2>/dev/null
+ls -la gpurun_out/r2aj_* | head
+rm -f gpurun_out/r2aj_p1_march.ncu-rep

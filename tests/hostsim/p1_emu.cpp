@@ -159,4 +159,31 @@ HOSTSIM_API long long emu_p1_point_rows(const int* dims, const double* origin, c
   return (long long)status[0];
 }
 
+// lsb200_add_face_vector_rows on a slab: k_p1_face_vector_vals then k_rows_ingest; rows as (n, 8) values, GLOBAL node ids
+// (-1 = row not kept by this slab), b, w^2; returns rows kept (or -1: a node id outside the mesh / outside the halo planes)
+HOSTSIM_API long long emu_p1_face_vector_rows(const int* dims, const double* origin, const double* step, long long n,
+                                              const long long* nodes_a, const long long* nodes_b, const double* vec, double weight,
+                                              double* vals, long long* cols, double* b, double* w2) {
+  const GridDesc g = make_grid(dims, origin, step);
+  std::vector<double> tv((size_t)n * 8), tb((size_t)n), tw((size_t)n), v((size_t)n * 8), bb((size_t)n), ww((size_t)n);
+  std::vector<long long> tc((size_t)n * 8);
+  std::vector<int> cc((size_t)n * 8);
+  lsb_emu::launch(dim3(2), dim3(64), 0, [&] { k_p1_face_vector_vals(g, n, nodes_a, nodes_b, vec, weight, tv.data(), tc.data(), tb.data(), tw.data()); });
+  RowBlock rb{};
+  rb.n = n; rb.k = 8; rb.vals = v.data(); rb.cols = cc.data(); rb.b = bb.data(); rb.w2 = ww.data();
+  unsigned long long status[4] = {0, 0, 0, 0};
+  lsb_emu::launch(dim3(2), dim3(64), 0, [&] { k_rows_ingest(g, n, 8, tv.data(), tc.data(), tb.data(), tw.data(), 1, rb, 0, status); });
+  if (status[1] || status[2]) return -1;
+  for (long long r = 0; r < n; ++r) {
+    for (int k = 0; k < 8; ++k) {
+      vals[r * 8 + k] = v[(size_t)k * n + r];
+      const int lc = cc[(size_t)k * n + r];
+      cols[r * 8 + k] = lc < 0 ? -1 : (long long)lc + (long long)(g.k0 - HALO) * g.plane;
+    }
+    b[r] = bb[r];
+    w2[r] = ww[r];
+  }
+  return (long long)status[0];
+}
+
 }  // extern "C"

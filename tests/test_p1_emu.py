@@ -98,8 +98,11 @@ def test_point_rows_on_every_slab_match_the_oracle(emu, world):
     vec = np.column_stack([xyz, rng.normal(size=(n, 3)), np.zeros(n)])
     nx, ny, nz = (int(v) for v in grid.nsteps)
     org, stp = np.ascontiguousarray(grid.origin), np.ascontiguousarray(grid.step)
+    fold = vec.copy()
+    fold[:, 6] = 0.7
     cases = ((0, value, 5, po.value_rows(grid, value, 1.0), 1), (2, vec, 7, po.normal_rows(grid, vec, 1.0), 3),
-             (3, vec, 7, po.orthogonal_rows(grid, vec[:, :3], vec[:, 3:6], 1.0), 1))
+             (3, vec, 7, po.orthogonal_rows(grid, vec[:, :3], vec[:, 3:6], 1.0), 1),
+             (4, fold, 7, po.element_vector_rows(grid, fold[:, :3], fold[:, 3:6], 1.0, 0.7), 1))
     for kind, data, ncols, fam, mult in cases:
         data = np.ascontiguousarray(data)
         M_ref = fam.matrix(grid.n_nodes)
@@ -130,3 +133,43 @@ def test_point_rows_on_every_slab_match_the_oracle(emu, world):
             np.testing.assert_allclose(w2[sel], fam.w[ref_sel] ** 2, rtol=1e-12, atol=0)
             seen |= live
         assert np.array_equal(seen, np.repeat(ins, mult))
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_face_vector_rows_on_every_slab_match_the_oracle(emu, world):
+    """k_p1_face_vector_vals + k_rows_ingest (lsb200_add_face_vector_rows): direction-weighted face-jump rows from the
+    node ids of the two tetrahedra of a shared face; a rank keeps the rows with a node in its planes."""
+    from scipy import sparse
+
+    cells = (4, 3, 7)
+    grid = fo.Grid.from_cells(np.array(cells), np.array([0.5, -1.0, 2.0]), np.array([1.0, 0.8, 1.25]))
+    plain = po.face_rows(grid, 1.0)          # every interior face once: its index array lists the two tetrahedra
+    na, nb = np.ascontiguousarray(plain.idx[:, :4]), np.ascontiguousarray(plain.idx[:, 4:])
+    n = na.shape[0]
+    rng = np.random.default_rng(9)
+    vec = np.ascontiguousarray(rng.normal(size=(n, 3)))
+    fam = po.face_vector_rows(grid, na, nb, vec, 0.3)
+    M_ref = fam.matrix(grid.n_nodes)
+    nx, ny, nz = (int(v) for v in grid.nsteps)
+    org, stp = np.ascontiguousarray(grid.origin), np.ascontiguousarray(grid.step)
+    plane = nx * ny
+    kz = np.hstack([na, nb]) // plane
+    seen = np.zeros(n, dtype=bool)
+    for k0, k1 in _bounds(nz, world):
+        dims = (C.c_int * 5)(nx, ny, nz, k0, k1)
+        vals, cols = np.empty((n, 8)), np.empty((n, 8), dtype=np.int64)
+        b, w2 = np.empty(n), np.empty(n)
+        kept = emu.emu_p1_face_vector_rows(dims, org.ctypes.data_as(dp), stp.ctypes.data_as(dp), C.c_longlong(n),
+                                           na.ctypes.data_as(llp), nb.ctypes.data_as(llp), vec.ctypes.data_as(dp), C.c_double(0.3),
+                                           vals.ctypes.data_as(dp), cols.ctypes.data_as(llp), b.ctypes.data_as(dp), w2.ctypes.data_as(dp))
+        touches = np.any((kz >= k0) & (kz < k1), axis=1)
+        assert kept == int(touches.sum())
+        assert np.array_equal(cols[:, 0] >= 0, touches)
+        sel = np.flatnonzero(touches)
+        M = sparse.coo_matrix((vals[sel].ravel(), (np.repeat(np.arange(sel.size), 8), cols[sel].ravel())),
+                              shape=(sel.size, grid.n_nodes)).tocsr()
+        assert abs(M - M_ref[sel]).max() <= 1e-12
+        assert not np.any(b[sel])
+        np.testing.assert_allclose(w2[sel], 0.09, rtol=1e-12)
+        seen |= touches
+    assert seen.all()

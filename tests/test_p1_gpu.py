@@ -108,6 +108,58 @@ def test_point_rows_match_reference(tag):
     e.close()
 
 
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_fold_rows_match_reference(tag):
+    """The fold rows of DiscreteFoldInterpolator.add_fold_constraints (LI/_discrete_fold_interpolator.py:116-242) generated
+    on the device -- one row per selected tetrahedron from its barycentre and the fold vector there
+    (LSB200_ROWS_ELEMENT_VECTOR), direction-weighted face-jump rows from the two tetrahedra of a face and the vector at
+    its centre (lsb200_add_face_vector_rows) -- against the families of the unmodified reference
+    (tests/golden/fold_rows_*.npz)."""
+    from loopstructural_b200 import engine as en
+
+    z = np.load(os.path.join(GOLDEN, f"fold_rows_{tag}.npz"))
+    grid = fo.Grid.from_cells(z["ncells"], z["origin"], z["step"])
+    w = H.weights_of(z, "w_keys", "w_vals")
+    p = np.random.default_rng(3).standard_normal(grid.n_nodes)
+
+    def check(e, name, nrows):
+        m, b, rw = H.ref_family(z, name)
+        assert nrows == m.shape[0], name
+        q_ref = m.T @ (rw * rw * (m @ p))
+        rhs_ref = m.T @ (rw * rw * b)
+        assert np.abs(e.apply_normal(p, parts=2) - q_ref).max() <= 1e-11 * np.abs(q_ref).max(), name
+        assert np.abs(e.rhs() - rhs_ref).max() <= 1e-11 * max(np.abs(rhs_ref).max(), 1.0), name
+        e.close()
+
+    for name, vec, wkey, bkey in (("fold orientation", "deformed_orientation", "fold_orientation", None),
+                                  ("fold axis", "fold_axis", "fold_axis_w", None),
+                                  ("fold normalisation", "dgz", "fold_normalisation", "fold_norm")):
+        if name not in z["names"]:
+            continue
+        sel = z[f"{name}/elements"]
+        target = w[bkey] * w[wkey] if bkey else 0.0
+        data = np.column_stack([z["barycentre"][sel], z[vec][sel], np.full(len(sel), target)])
+        e = _engine(grid, 0.0, add_ridge=False, apply_scaling=False)
+        check(e, name, e.add_point_rows(en.ROWS_ELEMENT_VECTOR, data, w[wkey]))
+    if "fold regularisation 1" in z["names"]:
+        for i, weight in enumerate(z["fold_regularisation"], start=1):
+            e = _engine(grid, 0.0, add_ridge=False, apply_scaling=False)
+            check(e, f"fold regularisation {i}",
+                  e.add_face_vector_rows(z["face_nodes_a"], z["face_nodes_b"], z[f"face_vectors_{i}"], float(weight)))
+
+
+def test_element_vector_rows_are_refused_on_a_grid_handle():
+    from loopstructural_b200 import Engine, engine as en
+    from loopstructural_b200._native import Lsb200Error
+
+    e = Engine([6, 6, 6], np.zeros(3), np.ones(3))
+    with pytest.raises(Lsb200Error):
+        e.add_point_rows(en.ROWS_ELEMENT_VECTOR, np.zeros((1, 7)) + 0.5, 1.0)
+    with pytest.raises(Lsb200Error):
+        e.add_face_vector_rows(np.zeros((1, 4), dtype=np.int64), np.zeros((1, 4), dtype=np.int64), np.ones((1, 3)), 1.0)
+    e.close()
+
+
 # ---------------------------------------------------------------- solve + K8: evaluation
 @pytest.mark.parametrize("tag", ["unit12", "aniso", "unit16_tight"])
 def test_solve_and_evaluation_match_reference(tag):

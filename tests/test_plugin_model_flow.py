@@ -55,6 +55,29 @@ class OracleEngine:
         assert normalise is False  # the reference has normalised them already
         self.rows.append(self.fo.Family(f"rows{len(self.rows)}", np.array(A, float), np.array(idx), np.array(b, float), np.array(w, float)))
 
+    def add_point_rows(self, kind, data, weight):
+        from oracle import p1_oracle as po
+
+        assert self.kind == "tetmesh" and kind == 4  # LSB200_ROWS_ELEMENT_VECTOR: the only point rows the plug-in generates
+        data = np.asarray(data, float)
+        if data.shape[0] == 0:
+            return 0
+        b = data[:, 6]
+        assert np.all(b == b[0])
+        fam = po.element_vector_rows(self.grid, data[:, :3], data[:, 3:6], float(weight), float(b[0]), name=f"device_element{len(self.rows)}")
+        self.device_families = getattr(self, "device_families", 0) + 1
+        self.rows.append(fam)
+        return fam.A.shape[0]
+
+    def add_face_vector_rows(self, nodes_a, nodes_b, vectors, weight):
+        from oracle import p1_oracle as po
+
+        assert self.kind == "tetmesh"
+        fam = po.face_vector_rows(self.grid, np.asarray(nodes_a), np.asarray(nodes_b), vectors, float(weight), name=f"device_face{len(self.rows)}")
+        self.device_families = getattr(self, "device_families", 0) + 1
+        self.rows.append(fam)
+        return fam.A.shape[0]
+
     def add_field_orthogonal_rows(self, other, step=10, weight=1.0, b=0.0, other_world_to_local=None):
         from oracle import fault_oracle as fa
 
@@ -366,29 +389,40 @@ def _fold_model(ls, **kw):
 
 def test_refolded_model_through_the_b200_solver_matches_the_stock_solver(ls):
     """BASELINE configs[3], fold half (load_laurent2016 style): a fold frame (FDI), a folded fold frame and a folded
-    foliation (DiscreteFoldInterpolator on a TetMesh: fold orientation / axis / normalisation rows and direction-weighted
-    face rows as explicit families) all solved with solver='b200'."""
+    foliation (DiscreteFoldInterpolator on a TetMesh) all solved with solver='b200'; the fold orientation / axis /
+    normalisation rows and the three direction-weighted face families never exist on the host: the engine generates them
+    from barycentres / faces and the fold vectors (here the oracle stand-in does, with oracle/p1_oracle.py)."""
     from loopstructural_b200 import plugin
 
     model, bb = _fold_model(ls, solver="b200")
     it0 = model["s0"].interpolator
     assert type(it0).__name__ == "B200DiscreteFoldInterpolator" and it0.latest_solve_timing["backend"] == "b200"
-    assert {"fold orientation", "fold axis", "fold normalisation", "fold regularisation 1"} <= set(it0.constraints)
+    fold_names = ["fold orientation", "fold axis", "fold normalisation", "fold regularisation 1", "fold regularisation 2",
+                  "fold regularisation 3"]
+    assert not set(fold_names) & set(it0.constraints)
+    assert [f["name"] for f in it0._b200_generated] == fold_names
+    assert [f["type"] for f in it0._b200_generated] == ["element"] * 3 + ["face"] * 3
     assert model["s1"][0].interpolator.latest_solve_timing["backend"] == "b200"   # DFI coordinate of the folded frame
     assert model["s2"][0].interpolator.latest_solve_timing["backend"] == "b200"   # FDI
     # Every stage against the stock solver ON THE SAME SYSTEM: the fold rows of s1 / s0 are functions of the previous
     # field (rotation angles fitted to its gradient) and the systems take thousands of CG iterations, so two separately
     # built models drift apart by far more than any solver difference -- the reference against itself under a one-ulp
-    # change of s2 does the same.  Nothing of a fold interpolator is diverted here (cgw = 0: no plain edge-jump family),
-    # so its constraint dict is the whole system and the stock solve_system can run on it directly.
+    # change of s2 does the same.  Asking for a stock solver materialises the recorded families on the host (the same
+    # elements, the same vectors) at the places the stock set-up would have put them.
     for it in (model["s1"][0].interpolator, it0):
         assert it._b200_reg == {} and it.interpolation_weights["cgw"] == 0.0
+        # (s1: the fold vectors of four families hold NaNs, the reference drops such a family and so does the plug-in)
+        generated = [f["name"] for f in it._b200_generated]
+        assert len(generated) >= 2 and set(generated) <= set(fold_names) and not set(generated) & set(it.constraints)
+        # the rows generated from barycentres / faces equal the host rows to rounding, not bit for bit, and these systems
+        # take thousands of iterations: compared where CG has converged, not at the model's default tolerance
+        tight = {"rtol": 1e-13, "atol": 0.0, "maxiter": 200000}
+        assert it.solve_system("b200", solver_kwargs=tight) and it.latest_solve_timing["backend"] == "b200"
         c_b200 = np.array(it.c)
-        tol = it.interpolation_weights.get("tol")
-        it._b200_divert = False  # keep the assembled families: the mixin would otherwise redo the (shuffled) set-up
-        assert it.solve_system("cg", tol=tol) is True and it.latest_solve_timing["backend"] == "python"
+        assert it.solve_system("cg", solver_kwargs=tight) is True and it.latest_solve_timing["backend"] == "python"
+        assert it._b200_generated == [] and list(it.constraints)[-len(generated):] == generated
         rng_ = float(it.c.max() - it.c.min())
-        assert np.linalg.norm(c_b200 - it.c) / np.sqrt(it.c.size) / rng_ <= 1e-9
+        assert np.linalg.norm(c_b200 - it.c) / np.sqrt(it.c.size) / rng_ <= 1e-10
     c_frame = np.array(model["s2"][0].interpolator.c)
 
     plugin.uninstall()
@@ -397,6 +431,44 @@ def test_refolded_model_through_the_b200_solver_matches_the_stock_solver(ls):
     assert type(its).__name__ == "DiscreteFoldInterpolator" and its.latest_solve_timing["backend"] == "python"
     cs2 = np.asarray(stock["s2"][0].interpolator.c)
     assert np.linalg.norm(c_frame - cs2) / np.sqrt(cs2.size) / float(cs2.max() - cs2.min()) <= 1e-9  # the unfolded frame
+
+
+def test_p1_directional_regularisation_rows_come_from_the_device(ls):
+    """P1Interpolator.setup_interpolator(directional_regularisation=...) (LI/_p1interpolator.py:198-229,
+    LI/_discrete_interpolator.py:413-451): the direction-weighted face-jump family is recorded with its vectors at the
+    shared-face centres and generated by the engine; a vector field holding a NaN stays with the stock method, which
+    drops the family; a stock solver afterwards sees the stock family."""
+    import loop_interpolation as li
+    from loop_common.supports import TetMesh
+
+    mesh = TetMesh(origin=np.zeros(3), nsteps_cells=np.array([6, 5, 7]), step_vector=np.array([1.0, 1.2, 0.9]))
+    rng = np.random.default_rng(11)
+    pts = rng.uniform(0.3, 4.5, (60, 3))
+    value = np.column_stack([pts, np.sin(pts[:, 0]) + 0.3 * pts[:, 2], np.ones(60)])
+
+    def direction(x):
+        x = np.asarray(x, float)
+        return np.column_stack([np.cos(0.4 * x[:, 1]), 0.3 + 0.1 * x[:, 0], np.sin(0.5 * x[:, 2]) + 1.2])
+
+    def with_nan(x):
+        v = direction(x)
+        v[3, 1] = np.nan
+        return v
+
+    terms = [{"weight": 0.4, "direction": direction, "name": "along"}, {"weight": 0.2, "direction": with_nan, "name": "broken"}]
+    it = li.interpolator_map[li.InterpolatorType.PIECEWISE_LINEAR](mesh)
+    assert type(it).__name__ == "B200P1Interpolator"
+    it.set_value_constraints(value.copy())
+    it.setup_interpolator(solver="b200", regularisation=0.05, directional_regularisation=terms)
+    assert [(f["type"], f["name"]) for f in it._b200_generated] == [("face", "along")]
+    assert "along" not in it.constraints and "broken" not in it.constraints and it._b200_reg == {"cgw": 0.05}
+    tight = {"rtol": 1e-13, "atol": 0.0}
+    assert it.solve_system("b200", solver_kwargs=tight) and it.latest_solve_timing["backend"] == "b200"
+    assert it._b200_engine.device_families == 1
+    c_b200 = np.array(it.c)
+    assert it.solve_system("cg", solver_kwargs=tight) and it.latest_solve_timing["backend"] == "python"
+    assert list(it.constraints)[:2] == ["edge jump", "along"] and it._b200_generated == []
+    assert np.linalg.norm(c_b200 - it.c) / np.sqrt(it.c.size) / float(it.c.max() - it.c.min()) <= 1e-10
 
 
 def test_two_faults_are_applied_as_one_chain(ls, monkeypatch):

@@ -114,7 +114,7 @@ def test_fault_frame_and_faulted_foliation_on_the_device(ls):
 
 def test_refolded_model_on_the_device(ls):
     """BASELINE configs[3], fold half (load_laurent2016): fold frame (FDI), folded fold frame and folded foliation
-    (DiscreteFoldInterpolator on a TetMesh, fold rows as explicit families) with solver='b200'; every stage against the
+    (DiscreteFoldInterpolator on a TetMesh, fold rows generated on the device) with solver='b200'; every stage against the
     stock solver ON THE SAME SYSTEM (see tests/test_plugin_model_flow.py for why)."""
     from test_plugin_model_flow import _fold_model
 
@@ -123,14 +123,19 @@ def test_refolded_model_on_the_device(ls):
     assert type(it0).__name__ == "B200DiscreteFoldInterpolator" and it0.latest_solve_timing["backend"] == "b200"
     assert model["s2"][0].interpolator.latest_solve_timing["backend"] == "b200"
     for it in (model["s1"][0].interpolator, it0):
-        c_b200 = np.array(it.c)
+        # the fold rows exist on the device only: generated there from barycentres / faces and the fold vectors
+        generated = [f["name"] for f in it._b200_generated]
+        assert len(generated) >= 2 and not set(generated) & set(it.constraints)
+        c_default = np.array(it.c)
         tol = it.interpolation_weights.get("tol")
-        assert it.solve_system("cg", tol=tol) is True and it.latest_solve_timing["backend"] == "python"
-        assert rel_l2(c_b200, it.c) <= 3e-5  # default tolerance on systems of thousands of iterations
-        assert it.solve_system("b200", solver_kwargs={"rtol": 1e-11, "atol": 0.0})
+        assert it.solve_system("b200", solver_kwargs={"rtol": 1e-11, "atol": 0.0}) and it.latest_solve_timing["backend"] == "b200"
         c_tight = np.array(it.c)
-        assert it.solve_system("cg", solver_kwargs={"rtol": 1e-11, "atol": 0.0})
+        # a stock solver materialises the same families on the host (the same elements, the same vectors)
+        assert it.solve_system("cg", solver_kwargs={"rtol": 1e-11, "atol": 0.0}) and it.latest_solve_timing["backend"] == "python"
+        assert it._b200_generated == [] and set(generated) <= set(it.constraints)
         assert rel_l2(c_tight, it.c) <= 1e-6
+        assert it.solve_system("cg", tol=tol) is True
+        assert rel_l2(c_default, it.c) <= 3e-5  # default tolerance on systems of thousands of iterations
 
 
 def test_builder_flow_without_solver_at_setup_keeps_every_constraint_on_the_device(ls):
