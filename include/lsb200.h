@@ -149,6 +149,14 @@ int lsb200_add_point_rows(lsb200_handle h, int kind, int64_t n, const double* da
 int lsb200_add_face_vector_rows(lsb200_handle h, int64_t n, const int64_t* nodes_a, const int64_t* nodes_b,
                                 const double* vectors, double weight, int64_t* n_rows_out);
 
+/* Directional regularisation of a grid, FiniteDifferenceInterpolator.minimise_directional_gradient_change
+ * (LI/_finite_difference_interpolator.py:1207-1340; reached through setup_interpolator(directional_regularisation=...),
+ * LI/_discrete_interpolator.py:413-451): the six second-derivative masks at every node interior on all axes as rows
+ * weighted by weight * (vx^2, vy^2, vz^2, 2 vx vy, 2 vx vz, 2 vy vz) of the direction at the node.  vectors is the
+ * (nx*ny*nz, 3) row-major direction field in GLOBAL node order (support.nodes order); a slab handle reads the planes it
+ * needs.  Rows of weight 0 (or NaN) are dropped as in the reference.  n_rows_out (may be NULL): rows kept. */
+int lsb200_add_directional_rows(lsb200_handle h, const double* vectors, double weight, int64_t* n_rows_out);
+
 /* Interface rows N(x_i) - N(x_j) = 0 for n point pairs (FDI.add_interface_constraints,
  * LI/_finite_difference_interpolator.py:297-340): 16 listed entries per row, weight ipw.  The pairing per
  * interface id (all / star / chain, :271-295) is done by the caller; pairs with a point outside the grid are

@@ -73,6 +73,7 @@ SIGNATURES = {
     "lsb200_add_rows": (C.c_int, [Handle, C.c_int64, C.c_int, c_double_p, c_int64_p, c_double_p, c_double_p, C.c_int]),
     "lsb200_add_point_rows": (C.c_int, [Handle, C.c_int, C.c_int64, c_double_p, C.c_int, C.c_double, c_int64_p]),
     "lsb200_add_pair_rows": (C.c_int, [Handle, C.c_int64, c_double_p, c_double_p, C.c_double, c_int64_p]),
+    "lsb200_add_directional_rows": (C.c_int, [Handle, c_double_p, C.c_double, c_int64_p]),
     "lsb200_add_face_vector_rows": (C.c_int, [Handle, C.c_int64, c_int64_p, c_int64_p, c_double_p, C.c_double, c_int64_p]),
     "lsb200_clear_rows": (C.c_int, [Handle]),
     "lsb200_num_rows": (C.c_int64, [Handle]),

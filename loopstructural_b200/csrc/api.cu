@@ -991,6 +991,40 @@ int lsb200_add_face_vector_rows(lsb200_handle h, int64_t n, const int64_t* nodes
   return 0;
 }
 
+int lsb200_add_directional_rows(lsb200_handle h, const double* vectors, double weight, int64_t* n_rows_out) {
+  if (!h) return fail(LSB200_ERR_ARG, "null handle");
+  if (n_rows_out) *n_rows_out = 0;
+  if (h->kind != LSB200_SUPPORT_GRID) return fail(LSB200_ERR_STATE, "directional stencil rows need a grid handle");
+  if (!vectors) return fail(LSB200_ERR_ARG, "null vectors");
+  const GridDesc& g = h->g;
+  const int ka = std::max(1, g.k0 - 1), kb = std::min(g.nz - 1, g.k1 + 1);
+  if (g.nx < 3 || g.ny < 3 || kb <= ka) return 0;  // no node is interior on all axes
+  CK(cudaSetDevice(h->device));
+  const long long per_plane = (long long)g.nx * g.ny;
+  const long long ncent = (long long)(g.nx - 2) * (g.ny - 2) * (kb - ka);
+  double* dv = nullptr;
+  const size_t bytes = sizeof(double) * 3 * (size_t)per_plane * (size_t)(kb - ka);
+  CK(cudaMallocAsync(&dv, bytes, h->stream));
+  CK(cudaMemcpyAsync(dv, vectors + 3 * per_plane * ka, bytes, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * 4, h->stream));
+  RowBlock rb{};
+  int rc = alloc_block(h, rb, 6 * ncent, 4);
+  if (rc) return rc;
+  const int nb = (int)std::min<long long>((ncent + 255) / 256, 8192);
+  k_fdi_directional_rows<<<nb, 256, 0, h->stream>>>(g, ka, kb, dv, weight, rb, h->status);
+  CKL();
+  h->launches++;
+  unsigned long long st[2];
+  CK(cudaMemcpyAsync(st, h->status, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  pool_free(h, dv);
+  if (n_rows_out) *n_rows_out = (int64_t)st[0];
+  h->rows_kept += (long long)st[0];
+  h->pending.push_back(rb);
+  h->finalized = false;
+  return 0;
+}
+
 int lsb200_add_pair_rows(lsb200_handle h, int64_t n, const double* xyz_i, const double* xyz_j, double weight,
                          int64_t* n_rows_out) {
   if (!h) return fail(LSB200_ERR_ARG, "null handle");
@@ -1687,6 +1721,10 @@ int lsb200_set_c_dev(lsb200_handle h, const double* c_dev, void* stream) {
 // one CG iteration enqueued on the stream (no host synchronisation)
 // ---- small systems: `iters` CG iterations in one persistent cooperative launch (csrc/cg_small.cuh) -----------------------
 constexpr long long SMALL_MAX_NODES = 3000000;  // above: an iteration is bandwidth bound and the four launches stream better
+// tet meshes: the marching operator fills an SM with 2 CTAs of 8 warps, too few threads for the loop's streaming phases --
+// config 3 (1.64 M nodes): 66.0 us per iteration in the loop, 60.3 launch by launch (profiles/r2am_c3.txt); the loop's
+// 8 us of barriers against 16 us of launch gaps put the crossover near 0.9 M nodes
+constexpr long long SMALL_MAX_NODES_P1 = 800000;
 static TmapArg* small_tmap(lsb200_ctx* h) {     // descriptor of p for the plan's tile shape (as launch_stencil builds it)
   for (int t = 0; t < 2; ++t)
     if (h->tma_vec[t] == h->p) return &h->tma_map[t];
@@ -1720,7 +1758,7 @@ static void plan_small(lsb200_ctx* h) {
   const char* e = getenv("LSB200_PERSIST");
   const int want = e ? atoi(e) : -1;  // 0: never, 1: whenever possible, default: systems of <= SMALL_MAX_NODES nodes
   if (want == 0 || h->nranks > 1 || h->deterministic || h->blocks.size() > (size_t)SMALL_MAX_BLOCKS) return;
-  if (want != 1 && h->g.nloc > SMALL_MAX_NODES) return;
+  if (want != 1 && h->g.nloc > (h->kind == LSB200_SUPPORT_GRID || !h->p1_march ? SMALL_MAX_NODES : SMALL_MAX_NODES_P1)) return;
   int coop = 0;
   if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device) != cudaSuccess || !coop) return;
   const long long per_cta_nodes = 4096;

@@ -362,6 +362,59 @@ __device__ __forceinline__ void strike_dip(const double nrm[3], double strike[3]
   }
 }
 
+// Directional regularisation of a grid, FiniteDifferenceInterpolator.minimise_directional_gradient_change
+// (LI/_finite_difference_interpolator.py:1207-1340): at every node interior on all axes the six second-derivative masks
+// (LI/_operator.py:29-35) as rows of their own, weighted by the components of the direction v at the node --
+// vx^2 fxx + vy^2 fyy + vz^2 fzz + 2 vx vy fxy + 2 vx vz fxz + 2 vy vz fyz = 0 -- each row L2-normalised like every row
+// (dxx: (1,-2,1)/sqrt 6; the mixed masks: four entries of +-1/2), b = 0, w = weight * component; rows whose weight is 0 or
+// NaN are dead (the reference drops them, :1325-1329) and are cut off when the block is compacted at finalize.
+// Centres: planes [ka, kb) = the interior planes whose stencil touches an owned plane; vec holds the (node, 3) vectors
+// of the planes from ka on; row of (op, centre c) = op * ncent + c.
+__global__ void k_fdi_directional_rows(const GridDesc g, const int ka, const int kb, const double* __restrict__ vec,
+                                       const double weight, RowBlock rb, unsigned long long* __restrict__ status) {
+  const int mx = g.nx - 2, my = g.ny - 2;
+  const long long ncent = (long long)mx * my * (kb - ka);
+  const double c3 = 1.0 / sqrt(6.0), c3m = -2.0 / sqrt(6.0);
+  unsigned long long kept = 0;
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ncent; c += (long long)gridDim.x * blockDim.x) {
+    const int i = 1 + (int)(c % mx);
+    const long long rr = c / mx;
+    const int j = 1 + (int)(rr % my), k = ka + (int)(rr / my);
+    const long long vn = ((long long)(k - ka) * g.ny + j) * g.nx + i;
+    const double vx = vec[3 * vn], vy = vec[3 * vn + 1], vz = vec[3 * vn + 2];
+    const int centre = (int)((long long)(k - g.k0 + HALO) * g.plane + (long long)j * g.pitch + i);
+    const int sx = 1, sy = g.pitch, sz = (int)g.plane;
+    const double comp[6] = {vx * vx, vy * vy, vz * vz, 2.0 * vx * vy, 2.0 * vx * vz, 2.0 * vy * vz};
+    const int sa[6] = {sx, sy, sz, sx, sx, sy}, sb[6] = {0, 0, 0, sy, sz, sz};
+#pragma unroll
+    for (int op = 0; op < 6; ++op) {
+      const long long ro = (long long)op * ncent + c;
+      const double rw = weight * comp[op];
+      const bool live = fabs(rw) > 0.0;  // false for NaN
+      if (op < 3) {
+        rb.cols[0 * rb.n + ro] = centre - sa[op]; rb.vals[0 * rb.n + ro] = c3;
+        rb.cols[1 * rb.n + ro] = centre;          rb.vals[1 * rb.n + ro] = c3m;
+        rb.cols[2 * rb.n + ro] = centre + sa[op]; rb.vals[2 * rb.n + ro] = c3;
+        rb.cols[3 * rb.n + ro] = -1;              rb.vals[3 * rb.n + ro] = 0.0;
+      } else {
+        // mask value at (a, b) offsets: -(-1,-1), +(+1,-1), +(-1,+1), -(+1,+1) (Operator.Dxy_mask and its axis swaps)
+        rb.cols[0 * rb.n + ro] = centre - sa[op] - sb[op]; rb.vals[0 * rb.n + ro] = -0.5;
+        rb.cols[1 * rb.n + ro] = centre + sa[op] - sb[op]; rb.vals[1 * rb.n + ro] = 0.5;
+        rb.cols[2 * rb.n + ro] = centre - sa[op] + sb[op]; rb.vals[2 * rb.n + ro] = 0.5;
+        rb.cols[3 * rb.n + ro] = centre + sa[op] + sb[op]; rb.vals[3 * rb.n + ro] = -0.5;
+      }
+      for (int e = 4; e < rb.k; ++e) {
+        rb.cols[e * rb.n + ro] = -1;
+        rb.vals[e * rb.n + ro] = 0.0;
+      }
+      rb.b[ro] = 0.0;
+      rb.w2[ro] = live ? rw * rw : 0.0;
+      kept += live ? 1ull : 0ull;
+    }
+  }
+  if (kept) atomicAdd(status, kept);
+}
+
 // One thread per constraint point; writes `mult` rows per point into rb at row0 + m*n + point.
 // Points outside the support (or on a slab: in cells that touch no owned plane) become empty rows.
 __global__ void k_fdi_point_rows(const GridDesc g, const int kind, const long long n, const double* __restrict__ data,

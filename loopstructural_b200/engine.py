@@ -214,6 +214,16 @@ class Engine:
                                                  C.byref(out)))
         return int(out.value)
 
+    def add_directional_rows(self, vectors, weight: float) -> int:
+        """FDI.minimise_directional_gradient_change (LI/_finite_difference_interpolator.py:1207-1340): ``vectors`` is the
+        (n_nodes, 3) direction field in the support's node order."""
+        v = nat.as_f64(vectors)
+        if v.shape != (int(np.prod(self.nsteps)), 3):
+            raise ValueError(f"vectors must be ({int(np.prod(self.nsteps))}, 3), got {v.shape}")
+        out = C.c_int64(0)
+        nat.check(self._lib.lsb200_add_directional_rows(self._h, nat.dptr(v), float(weight), C.byref(out)))
+        return int(out.value)
+
     def add_face_vector_rows(self, nodes_a, nodes_b, vectors, weight: float) -> int:
         """P1Interpolator.minimise_edge_jumps with a vector per shared face (LI/_p1interpolator.py:115-166): one row
         v . (grad phi_a - grad phi_b) = 0 per pair of face-adjacent tetrahedra, given by their (n,4) global node ids."""

@@ -93,6 +93,8 @@ def _load_rows(it, eng, skip=()) -> int:
         # fold rows and direction-weighted face rows: generated on the device from points / faces and their vectors
         if fam["type"] == "element":
             n_rows += eng.add_point_rows(fam["kind"], fam["data"], fam["weight"])
+        elif fam["type"] == "directional":
+            n_rows += eng.add_directional_rows(fam["vectors"], fam["weight"])
         else:
             el = np.asarray(it.support.elements)
             rel = np.asarray(it.support.shared_element_relationships)
@@ -449,6 +451,23 @@ def _make_fdi_class():
             for d in range(dim):
                 self.add_constraints_to_least_squares(T[:, d, :], pts[inside, dim + d], corners, w=weights, name=f"norm_{d}")
             self.up_to_date = False
+
+        def minimise_directional_gradient_change(self, w, vector, name="directional regularisation"):
+            """FDI.minimise_directional_gradient_change (LI/_finite_difference_interpolator.py:1207-1340) for a diverted
+            set-up: six families of one row per interior node (index tables, tiled masks, six sparse matrices on the
+            host) become one record -- the direction field -- and the rows are generated on the device
+            (lsb200_add_directional_rows)."""
+            vec = None if vector is None else np.asarray(vector)
+            if (self._b200_divert and vec is not None and vec.ndim == 2 and vec.shape == (self.support.n_nodes, 3)
+                    and np.ndim(w) == 0 and self._b200_supported(self._b200_setup_kwargs)
+                    and not self.use_regularisation_weight_scale):
+                stock = super().minimise_directional_gradient_change
+                self._b200_generated.append(dict(type="directional", vectors=np.ascontiguousarray(vec, dtype=np.float64),
+                                                 weight=float(w), name=name, pos=len(self.constraints),
+                                                 stock=lambda: stock(w, vector, name=name)))
+                self.up_to_date = False
+                return
+            return super().minimise_directional_gradient_change(w, vector, name=name)
 
         def _b200_assemble_recorded(self, name, payload):
             if name == "borders":

@@ -382,6 +382,35 @@ def regularisation_families(grid: Grid, weights: dict | None = None) -> list[Fam
     return fams
 
 
+def directional_families(grid: Grid, vectors: np.ndarray, w: float, name: str = "directional regularisation") -> list[Family]:
+    """minimise_directional_gradient_change, LI/_finite_difference_interpolator.py:1207-1340 (StructuredGrid path): the six
+    second-derivative masks at the nodes interior on all axes, row weights w * (vx^2, vy^2, vz^2, 2 vx vy, 2 vx vz, 2 vy vz)
+    of the direction at the centre node, rows of weight 0 dropped (:1325-1329)."""
+    nx, ny, nz = (int(v) for v in grid.nsteps)
+    vectors = np.asarray(vectors, dtype=float)
+
+    def interior(i, j, k):
+        return (i > 0) & (i < nx - 1) & (j > 0) & (j < ny - 1) & (k > 0) & (k < nz - 1)
+
+    i, j, k = _node_ijk(grid, interior)
+    centre = i + nx * j + nx * ny * k
+    vx, vy, vz = vectors[centre, 0], vectors[centre, 1], vectors[centre, 2]
+    comp = {"dxx": vx ** 2, "dyy": vy ** 2, "dzz": vz ** 2, "dxy": 2.0 * vx * vy, "dxz": 2.0 * vx * vz, "dyz": 2.0 * vy * vz}
+    fams = []
+    for key in ("dxx", "dyy", "dzz", "dxy", "dxz", "dyz"):
+        taps, coefs = STENCILS[key]
+        full = stencil_family(grid, f"{name}_{key}", taps, coefs, 1.0, interior)
+        if full is None:
+            continue
+        row_w = w * comp[key]
+        with np.errstate(invalid="ignore"):
+            nz_ = np.abs(row_w) > 0.0
+        if not np.any(nz_):
+            continue
+        fams.append(Family(full.name, full.A[nz_], full.idx[nz_], full.b[nz_], row_w[nz_]))
+    return fams
+
+
 # --------------------------------------------------------------------------
 # system assembly, preprocessing, CG
 # --------------------------------------------------------------------------

@@ -186,4 +186,35 @@ HOSTSIM_API long long emu_p1_face_vector_rows(const int* dims, const double* ori
   return (long long)status[0];
 }
 
+// lsb200_add_directional_rows on a slab (a GRID handle: the row kernels are shared): rows as (6 * ncent, 4) values, GLOBAL
+// node ids (-1 = empty slot), w^2 (0 = dead row); vec_global is the (nx*ny*nz, 3) field; returns rows kept
+HOSTSIM_API long long emu_fdi_directional_rows(const int* dims, const double* origin, const double* step, const double* vec_global,
+                                               double weight, double* vals, long long* cols, double* w2) {
+  const GridDesc g = make_grid(dims, origin, step, true);
+  const int ka = std::max(1, g.k0 - 1), kb = std::min(g.nz - 1, g.k1 + 1);
+  if (g.nx < 3 || g.ny < 3 || kb <= ka) return 0;
+  const long long ncent = (long long)(g.nx - 2) * (g.ny - 2) * (kb - ka), nr = 6 * ncent;
+  std::vector<double> v((size_t)nr * 4), bb((size_t)nr), ww((size_t)nr);
+  std::vector<int> cc((size_t)nr * 4);
+  RowBlock rb{};
+  rb.n = nr; rb.k = 4; rb.vals = v.data(); rb.cols = cc.data(); rb.b = bb.data(); rb.w2 = ww.data();
+  unsigned long long status[4] = {0, 0, 0, 0};
+  lsb_emu::launch(dim3(3), dim3(64), 0, [&] {
+    k_fdi_directional_rows(g, ka, kb, vec_global + 3 * (long long)g.nx * g.ny * ka, weight, rb, status);
+  });
+  for (long long r = 0; r < nr; ++r) {
+    for (int k = 0; k < 4; ++k) {
+      vals[r * 4 + k] = v[(size_t)k * nr + r];
+      const int lc = cc[(size_t)k * nr + r];
+      if (lc < 0) { cols[r * 4 + k] = -1; continue; }
+      // storage index (even row pitch) -> global node id
+      const long long kl = lc / g.plane, rem = lc - kl * g.plane;
+      const long long j = rem / g.pitch, i = rem - j * g.pitch;
+      cols[r * 4 + k] = ((kl + g.k0 - HALO) * g.ny + j) * g.nx + i;
+    }
+    w2[r] = ww[r];
+  }
+  return (long long)status[0];
+}
+
 }  // extern "C"

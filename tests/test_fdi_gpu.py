@@ -450,3 +450,29 @@ def test_deterministic_mode_with_interface_and_generic_rows():
         e.close()
     for a, b in zip(*out):
         assert np.abs(a - b).max() <= 1e-12 * max(np.abs(b).max(), 1.0)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_directional_regularisation_rows_match_reference(tag):
+    """lsb200_add_directional_rows (k_fdi_directional_rows) against the families of the unmodified reference's
+    minimise_directional_gradient_change (tests/golden/fdi_directional_*.npz): row count after the zero-weight filter and
+    the normal operator of the six families together."""
+    import golden_helpers as H
+    from loopstructural_b200 import Engine
+
+    z = np.load(os.path.join(H.GOLDEN, f"fdi_directional_{tag}.npz"))
+    grid = fo.Grid.from_cells(z["ncells"], z["origin"], z["step"])
+    e = Engine(grid.nsteps, grid.origin, grid.step)
+    e.set_regularisation({k: 0.0 for k in ("dxx", "dyy", "dzz", "dxy", "dxz", "dyz", "dx", "dy", "dz")})
+    e.set_options(add_ridge=False, apply_scaling=False)
+    kept = e.add_directional_rows(z["vectors"], float(z["w"]))
+    p = np.random.default_rng(3).standard_normal(grid.n_nodes)
+    q_ref, rows = np.zeros(grid.n_nodes), 0
+    for name in z["names"]:
+        m, _b, w = H.ref_family(z, str(name))
+        q_ref += m.T @ (w * w * (m @ p))
+        rows += m.shape[0]
+    assert kept == rows
+    assert np.abs(e.apply_normal(p, parts=2) - q_ref).max() <= 1e-11 * np.abs(q_ref).max()
+    assert not np.any(e.rhs())
+    e.close()

@@ -9,6 +9,7 @@ import scipy.sparse.linalg as spla
 from scipy import sparse
 
 from oracle import fdi_oracle as fo
+import golden_helpers as H
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -165,3 +166,22 @@ def test_claudius_quickstart_matches_reference():
     np.testing.assert_array_equal(np.isnan(v), np.isnan(z["value_at"]))
     np.testing.assert_allclose(v, z["value_at"], rtol=0, atol=1e-9, equal_nan=True)
     np.testing.assert_allclose(fo.evaluate_gradient(grid, z["query"], z["c"]), z["gradient_at"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_directional_regularisation_families_match_reference(tag):
+    """fdi_oracle.directional_families against FDI.minimise_directional_gradient_change of the unmodified reference
+    (tests/golden/fdi_directional_*.npz): the same rows survive the zero-weight filter, the same normal equations."""
+    z = np.load(os.path.join(GOLDEN, f"fdi_directional_{tag}.npz"))
+    grid = fo.Grid.from_cells(z["ncells"], z["origin"], z["step"])
+    fams = {f.name: f for f in fo.directional_families(grid, z["vectors"], float(z["w"]), name="fold regularisation 1")}
+    assert set(fams) == set(str(n) for n in z["names"]) and len(fams) == 6
+    p = np.random.default_rng(8).standard_normal(grid.n_nodes)
+    for name, fam in fams.items():
+        m, b, w = H.ref_family(z, name)
+        assert fam.A.shape[0] == m.shape[0], name
+        M = fam.matrix(grid.n_nodes)
+        ref = m.T @ (w * w * (m @ p))
+        got = M.T @ (fam.w * fam.w * (M @ p))
+        assert np.abs(ref - got).max() <= 1e-12 * np.abs(ref).max(), name
+        assert not np.any(b)

@@ -173,3 +173,45 @@ def test_face_vector_rows_on_every_slab_match_the_oracle(emu, world):
         np.testing.assert_allclose(w2[sel], 0.09, rtol=1e-12)
         seen |= touches
     assert seen.all()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_directional_stencil_rows_on_every_slab_match_the_oracle(emu, world):
+    """k_fdi_directional_rows (lsb200_add_directional_rows; odd nx: the storage has an even row pitch): per slab the live
+    rows are the oracle's rows whose stencil touches an owned plane, with the same weights."""
+    from scipy import sparse
+
+    cells = (6, 5, 8)
+    grid = fo.Grid.from_cells(np.array(cells), np.array([0.5, -1.0, 2.0]), np.array([1.0, 0.8, 1.25]))
+    nx, ny, nz = (int(v) for v in grid.nsteps)
+    rng = np.random.default_rng(12)
+    vec = rng.normal(size=(grid.n_nodes, 3))
+    vec[rng.random(grid.n_nodes) < 0.2, 0] = 0.0
+    vec[nx * ny * 3: nx * ny * 4] = 0.0
+    vec[7] = np.nan
+    vec = np.ascontiguousarray(vec)
+    fams = fo.directional_families(grid, vec, 0.7)
+    ref = sparse.vstack([f.matrix(grid.n_nodes).multiply(f.w[:, None]) for f in fams]).tocsr()
+    p = rng.standard_normal(grid.n_nodes)
+    q_ref = ref.T @ (ref @ p)
+    org, stp = np.ascontiguousarray(grid.origin), np.ascontiguousarray(grid.step)
+    q = np.zeros(grid.n_nodes)
+    for k0, k1 in _bounds(nz, world):
+        ka, kb = max(1, k0 - 1), min(nz - 1, k1 + 1)
+        nr = 6 * (nx - 2) * (ny - 2) * (kb - ka)
+        dims = (C.c_int * 5)(nx, ny, nz, k0, k1)
+        vals, cols, w2 = np.empty((nr, 4)), np.empty((nr, 4), dtype=np.int64), np.empty(nr)
+        kept = emu.emu_fdi_directional_rows(dims, org.ctypes.data_as(dp), stp.ctypes.data_as(dp), vec.ctypes.data_as(dp),
+                                            C.c_double(0.7), vals.ctypes.data_as(dp), cols.ctypes.data_as(llp), w2.ctypes.data_as(dp))
+        live = w2 > 0
+        assert kept == int(live.sum())
+        cc = np.where(cols < 0, 0, cols)
+        vv = np.where(cols < 0, 0.0, vals)
+        M = sparse.coo_matrix((vv[live].ravel(), (np.repeat(np.arange(int(live.sum())), 4), cc[live].ravel())),
+                              shape=(int(live.sum()), grid.n_nodes)).tocsr()
+        part = M.T @ (w2[live] * (M @ p))
+        own = slice(k0 * nx * ny, k1 * nx * ny)
+        q[own] = part[own]  # a rank applies its rows to the planes it owns
+        if world == 1:
+            assert kept == ref.shape[0]
+    assert np.abs(q - q_ref).max() <= 1e-12 * np.abs(q_ref).max()

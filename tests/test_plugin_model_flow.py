@@ -69,6 +69,13 @@ class OracleEngine:
         self.rows.append(fam)
         return fam.A.shape[0]
 
+    def add_directional_rows(self, vectors, weight):
+        assert self.kind == "grid"
+        fams = self.fo.directional_families(self.grid, vectors, float(weight), name=f"device_directional{len(self.rows)}")
+        self.device_families = getattr(self, "device_families", 0) + 1
+        self.rows.extend(fams)
+        return sum(f.A.shape[0] for f in fams)
+
     def add_face_vector_rows(self, nodes_a, nodes_b, vectors, weight):
         from oracle import p1_oracle as po
 
@@ -468,6 +475,39 @@ def test_p1_directional_regularisation_rows_come_from_the_device(ls):
     c_b200 = np.array(it.c)
     assert it.solve_system("cg", solver_kwargs=tight) and it.latest_solve_timing["backend"] == "python"
     assert list(it.constraints)[:2] == ["edge jump", "along"] and it._b200_generated == []
+    assert np.linalg.norm(c_b200 - it.c) / np.sqrt(it.c.size) / float(it.c.max() - it.c.min()) <= 1e-10
+
+
+def test_fdi_directional_regularisation_rows_come_from_the_device(ls):
+    """FiniteDifferenceInterpolator.setup_interpolator(directional_regularisation=...): the six direction-weighted
+    second-derivative families (LI/_finite_difference_interpolator.py:1207-1340) are one record of the direction field,
+    generated by the engine; a stock solver afterwards sees the six stock families."""
+    import loop_interpolation as li
+    from loop_common.supports import StructuredGrid
+
+    sg = StructuredGrid(origin=np.zeros(3), nsteps_cells=np.array([7, 6, 8]), step_vector=np.array([1.0, 1.2, 0.9]))
+    rng = np.random.default_rng(13)
+    pts = rng.uniform(0.3, 5.5, (80, 3))
+    value = np.column_stack([pts, np.sin(pts[:, 0]) + 0.3 * pts[:, 2], np.ones(80)])
+
+    def direction(x):
+        x = np.asarray(x, float)
+        v = np.column_stack([np.cos(0.4 * x[:, 1]), 0.3 + 0.1 * x[:, 0], np.sin(0.5 * x[:, 2]) + 1.2])
+        v[x[:, 0] > 4.0, 2] = 0.0
+        return v
+
+    it = li.interpolator_map[li.InterpolatorType.FINITE_DIFFERENCE](sg)
+    assert type(it).__name__ == "B200FiniteDifferenceInterpolator"
+    it.set_value_constraints(value.copy())
+    it.setup_interpolator(solver="b200", regularisation=0.3, directional_regularisation=[{"weight": 0.8, "direction": direction, "name": "along"}])
+    assert [(f["type"], f["name"]) for f in it._b200_generated] == [("directional", "along")]
+    assert not any(k.startswith("along") for k in it.constraints)
+    tight = {"rtol": 1e-13, "atol": 0.0}
+    assert it.solve_system("b200", solver_kwargs=tight) and it.latest_solve_timing["backend"] == "b200"
+    assert it._b200_engine.device_families == 1
+    c_b200 = np.array(it.c)
+    assert it.solve_system("cg", solver_kwargs=tight) and it.latest_solve_timing["backend"] == "python"
+    assert sorted(k for k in it.constraints if k.startswith("along")) == sorted(f"along_{op}" for op in ("dxx", "dyy", "dzz", "dxy", "dxz", "dyz"))
     assert np.linalg.norm(c_b200 - it.c) / np.sqrt(it.c.size) / float(it.c.max() - it.c.min()) <= 1e-10
 
 
