@@ -288,6 +288,18 @@ class B200FiniteDifferenceInterpolator(_B200DiscreteInterpolator):
         self.up_to_date = False
         return n
 
+    def minimise_directional_gradient_change(self, w, vector, name="directional regularisation"):
+        """FDI.minimise_directional_gradient_change (LI/_finite_difference_interpolator.py:1207-1340): the six
+        direction-weighted second-derivative families from the (n_nodes, 3) direction field at the nodes; a field of
+        another shape is skipped with the reference's warning semantics (returns 0)."""
+        vector = None if vector is None else np.asarray(vector, dtype=np.float64)
+        if vector is None or vector.ndim != 2 or vector.shape != (int(np.prod(self.engine.nsteps)), 3):
+            return 0
+        n = self.engine.add_directional_rows(vector, float(w))
+        self.row_counts[name] = self.row_counts.get(name, 0) + n
+        self.up_to_date = False
+        return n
+
 
 class B200P1Interpolator(_B200DiscreteInterpolator):
     """P1Interpolator on a TetMesh (LI/_p1interpolator.py:23-113)."""
