@@ -121,6 +121,8 @@ struct lsb200_ctx {
   int p1_march_minb = 1;       // CTAs of it that fit an SM
   P1MarchPlan p1_mplan{};
   P1MarchTaps p1_mtaps{};
+  bool p1_split = false;       // launches outside the persistent loop: k_p1_march<4, 0, 3> marching only (p1_splan), the
+  P1MarchPlan p1_splan{};      // boundary shell by k_p1_boundary on a side stream
   double ridge = 1e-8;
   int add_ridge = 1, apply_scaling = 1, deterministic = 0;
   cudaStream_t stream = nullptr;
@@ -403,6 +405,26 @@ static int launch_regularisation(lsb200_ctx* h, const double* p, double* q, int 
   const long long n = (long long)h->g.nx * h->g.ny * h->g.nzl;
   const int nb = (int)std::max<long long>(1, std::min<long long>((n + VEC_NT - 1) / VEC_NT, (long long)h->sm_count * 16));
   const double w2 = h->p1_w * h->p1_w, ridge2 = h->add_ridge ? h->ridge * h->ridge : 0.0;
+  if (h->p1_split) {
+    // two launches side by side: the march of the interior, the boundary shell at full occupancy on a side stream
+    const P1MarchPlan& pl = h->p1_splan;
+    auto kern = k_p1_march<4, 0, 3>;
+    const size_t smem = sizeof(double) * P1MarchCfg<4, 0>::PLANE * P1MarchCfg<4, 0>::ST;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    CK(cudaStreamWaitEvent(h->side[0], h->ev_fork, 0));
+    kern<<<(unsigned int)pl.n_cta, 128, smem, h->stream>>>(h->g, tb, h->p1_mtaps, pl, w2, ridge2, p, q, h->partials, h->counters + 0, h->sc, cg_mode);
+    CKL();
+    const long long nbn = pl.b.nbz + pl.b.nby + pl.b.nbx;
+    const int nbb = (int)std::max<long long>(1, std::min<long long>((nbn + 255) / 256, (long long)h->sm_count * 4));
+    k_p1_boundary<256><<<nbb, 256, 0, h->side[0]>>>(h->g, tb, pl.b, w2, ridge2, p, q, h->partials + (size_t)3 * MAX_PARTIALS,
+                                                    h->counters + 3, h->sc, cg_mode);
+    CKL();
+    CK(cudaEventRecord(h->ev_join[0], h->side[0]));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_join[0], 0));
+    h->launches += 2;
+    return 0;
+  }
   if (h->p1_march) {
     // one launch: the interior by z-marching register tiles, every CTA with its share of the boundary nodes (csrc/p1_march.cuh)
     const P1MarchPlan& pl = h->p1_mplan;
@@ -801,6 +823,21 @@ int lsb200_set_p1_tables(lsb200_handle h, const int64_t m[3], const double* tabl
   } break;
       LSB_P1_MARCH_CFGS(X)
 #undef X
+    }
+  }
+  // outside the persistent loop: the march and the boundary shell as two launches side by side (LSB200_P1_SPLIT=0: one)
+  h->p1_split = false;
+  if (h->p1_march && !(getenv("LSB200_P1_SPLIT") && atoi(getenv("LSB200_P1_SPLIT")) == 0)) {
+    int per_sm = 0;
+    const size_t smem = sizeof(double) * P1MarchCfg<4, 0>::PLANE * P1MarchCfg<4, 0>::ST;
+    cudaFuncSetAttribute(k_p1_march<4, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_p1_march<4, 0, 3>, 128, smem) == cudaSuccess && per_sm >= 1) {
+      // two marching CTAs per SM: the third CTA's registers are the boundary kernel's
+      P1MarchTaps same;
+      h->p1_split = p1_plan_march<4, 0>(h->g, h->p1_m, table, h->sm_count, std::min(per_sm, 2), MAX_PARTIALS, march_cz, &h->p1_splan,
+                                        &same, true) && h->p1_splan.n_cta > 0;  // (a slab without interior planes: one launch)
+    } else {
+      cudaGetLastError();
     }
   }
   h->finalized = false;
@@ -2624,6 +2661,10 @@ int lsb200_describe_plan(lsb200_handle h, char* out, int64_t capacity) {
              (h->want_tma && h->g.pitch % 2 == 0) ? "TMA" : "cp.async", h->tuned ? "chosen by timing" : "planner default");
   } else if (h->kind == LSB200_SUPPORT_GRID) {
     snprintf(out, (size_t)capacity, "k_fdi_normal: grid %u x %u x %u, z chunks of %d planes", h->sgrid.x, h->sgrid.y, h->sgrid.z, h->cz);
+  } else if (h->p1_split && !h->small_ok) {
+    const P1MarchPlan& pl = h->p1_splan;
+    snprintf(out, (size_t)capacity, "k_p1_march: tiles 64x8 (%d x %d), 4 warps, %d z chunks of %d planes, %d CTAs, beside k_p1_boundary (%lld nodes) on a side stream",
+             pl.tiles_x, pl.tiles_y, pl.chunks, pl.cz, pl.n_cta, (long long)(pl.b.nbz + pl.b.nby + pl.b.nbx));
   } else if (h->p1_march) {
     const P1MarchPlan& pl = h->p1_mplan;
     snprintf(out, (size_t)capacity, "k_p1_march: tiles 64x%d (%d x %d), %d + %d warps, %d z chunks of %d planes, %d CTAs (+%d boundary-only), %d CTAs per SM",
@@ -2651,7 +2692,8 @@ int lsb200_debug_cta_trace(lsb200_handle h, int64_t max_ctas, uint64_t* out, int
     ctas = (long long)h->fz.pl.n_box + h->fz.pl.n_xs + h->fz.pl.n_ys;
   } else {
     if (!h->p1_tiles) return fail(LSB200_ERR_STATE, "the per-CTA trace needs the tiled P1 plan");
-    ctas = h->p1_march ? (long long)h->p1_mplan.n_cta + h->p1_mplan.b.n_bnd_cta
+    ctas = h->p1_split ? (long long)h->p1_splan.n_cta
+           : h->p1_march ? (long long)h->p1_mplan.n_cta + h->p1_mplan.b.n_bnd_cta
                        : (long long)h->p1_plan.n_bnd_cta + (long long)h->p1_plan.tiles_x * h->p1_plan.tiles_y * h->p1_plan.tiles_z;
   }
   if (ctas > max_ctas) return fail(LSB200_ERR_ARG, "the launch has %lld CTAs, the buffer holds %lld", ctas, (long long)max_ctas);

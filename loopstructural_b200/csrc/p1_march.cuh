@@ -28,6 +28,7 @@ struct P1MarchPlan {
   int tiles_x, tiles_y;    // tiles of 64 x TY interior nodes
   int cz, chunks;          // z chunks of the owned interior planes [kfirst, klast)
   int n_cta;               // tiles_x * tiles_y * chunks
+  int split;               // the boundary nodes are another launch's (k_p1_boundary): the CTAs of this plan only march
 };
 
 // X(ID, marching warps, boundary warps, CTAs per SM the kernel is compiled for); LSB200_P1_MARCH = ID (0: k_p1_tiles instead).
@@ -62,7 +63,8 @@ __device__ __forceinline__ void p1m_named_sync(const int count) {
 // host: plan and coefficients, or false (no interior, an entry of the table outside the baked pattern, too many CTAs)
 template <int NW, int NB>
 inline bool p1_plan_march(const GridDesc& g, const int m[3], const double* table, const int sm_count, const int ctas_per_sm,
-                          const long long max_blocks, const int cz_override, P1MarchPlan* out, P1MarchTaps* T) {
+                          const long long max_blocks, const int cz_override, P1MarchPlan* out, P1MarchTaps* T,
+                          const bool split = false) {
   using C = P1MarchCfg<NW, NB>;
   const int nc[3] = {g.nx - 1, g.ny - 1, g.nz - 1};
   for (int a = 0; a < 3; ++a)
@@ -88,10 +90,11 @@ inline bool p1_plan_march(const GridDesc& g, const int m[3], const double* table
     pl.n_cta = (int)(tiles * pl.chunks);
     // boundary-only CTAs when the tiles are too few to carry the boundary shares (always: slabs without interior planes)
     const long long carried = (long long)pl.n_cta * C::NBT * P1M_BND_PER_THREAD;
-    pl.b.n_bnd_cta = carried >= nb ? 0 : (int)((nb - carried + per_cta - 1) / per_cta);
+    pl.b.n_bnd_cta = (carried >= nb || split) ? 0 : (int)((nb - carried + per_cta - 1) / per_cta);
     // they too belong to the first wave: fewer, longer chunks until they fit (or nothing is left to give)
     if (cz_override > 0 || chunks <= 1 || (long long)pl.n_cta + pl.b.n_bnd_cta <= slots) break;
   }
+  pl.split = split ? 1 : 0;
   if ((long long)pl.n_cta + pl.b.n_bnd_cta > max_blocks) return false;
   memset(T, 0, sizeof(*T));
   for (int cls = 0; cls < 8; ++cls) {
@@ -171,7 +174,7 @@ __device__ __forceinline__ double p1_march_cta(const GridDesc& g, const P1Tables
       cp_async_commit();
     }
   }
-  if (!has_tile || NB == 0 || tid >= NT) {
+  if (!pl.split && (!has_tile || NB == 0 || tid >= NT)) {
     // ---- a share of the boundary nodes: the boundary warps of a tile CTA (NB = 0: its marching threads, while their
     // first planes are on their way), every thread of a boundary-only CTA
     const long long nb = pl.b.nbz + pl.b.nby + pl.b.nbx;
@@ -288,6 +291,27 @@ __global__ void __launch_bounds__(32 * (NW + NB), MINB)
   if (tid == 0) trace_end(t_begin, blockIdx.x);
   double total;
   if (grid_sum_last_block<NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total)) sc->pq_part[0] = total;
+}
+
+// The boundary shell of a split plan: one thread per node at full occupancy (no shared memory, ~40 registers), launched on
+// a side stream beside k_p1_march, whose CTAs leave a third of an SM's registers free; its share of p.q goes to pq_part[2].
+template <int NT>
+__global__ void __launch_bounds__(NT)
+    k_p1_boundary(const GridDesc g, const P1Tables tb, const P1TilePlan b, const double w2, const double ridge2,
+                  const double* __restrict__ p, double* __restrict__ q, double* __restrict__ partials,
+                  unsigned int* __restrict__ counter, CgScalars* __restrict__ sc, const int cg_mode) {
+  __shared__ double red[NT / 32];
+  if (cg_mode && sc->done) return;
+  const long long nb = b.nbz + b.nby + b.nbx;
+  double dot = 0.0;
+  for (long long t = blockIdx.x * (long long)NT + threadIdx.x; t < nb; t += (long long)gridDim.x * NT) {
+    int i, j, kl;
+    p1_boundary_node(g, b, t, &i, &j, &kl);
+    dot += p1_node_generic(g, tb, w2, ridge2, p, q, i, j, kl);
+  }
+  const double bsum = block_sum<NT>(dot, red);
+  double total;
+  if (grid_sum_last_block<NT>(bsum, partials, counter, gridDim.x, blockIdx.x, red, &total)) sc->pq_part[2] = total;
 }
 
 }  // namespace lsb

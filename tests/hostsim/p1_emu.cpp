@@ -115,6 +115,22 @@ HOSTSIM_API int emu_p1_normal(const int* dims, const double* step, const long lo
     }                                                                                                                    \
   } break;
     LSB_P1_MARCH_CFGS(M)
+    case 19: {  // tiles = 20: the split plan -- k_p1_march<4, 0, 3> marching only, then k_p1_boundary
+      using MC = P1MarchCfg<4, 0>;
+      P1MarchPlan mp;
+      P1MarchTaps mt;
+      if (p1_plan_march<4, 0>(g, mi, table, 3, 2, MAX_PARTIALS, cz, &mp, &mt, true)) {
+        used_tiles = 1;
+        CgScalars sc2{};
+        unsigned int counter2 = 0;
+        std::vector<double> partials2((size_t)MAX_PARTIALS, 0.0);
+        if (mp.n_cta > 0)
+          lsb_emu::launch(dim3(mp.n_cta), dim3(MC::NT), sizeof(double) * MC::PLANE * MC::ST,
+                          [&] { k_p1_march<4, 0, 3>(g, tb, mt, mp, w2, ridge2, p, q, partials.data(), &counter, &sc, 0); });
+        lsb_emu::launch(dim3(3), dim3(64), 0, [&] { k_p1_boundary<64>(g, tb, mp.b, w2, ridge2, p, q, partials2.data(), &counter2, &sc2, 0); });
+        sc.pq_part[0] += sc2.pq_part[2];
+      }
+    } break;
 #undef M
   }
   if (!used_tiles)

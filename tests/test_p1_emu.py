@@ -39,7 +39,7 @@ def _bounds(nz, world):
     return partition.slab_bounds(nz, world) if world > 1 else [(0, nz)]
 
 
-@pytest.mark.parametrize("tiles", [0, 1, 2, 3, (11, 0), (11, 3), (12, 0), (12, 5), (13, 4)])
+@pytest.mark.parametrize("tiles", [0, 1, 2, 3, (11, 0), (11, 3), (12, 0), (12, 5), (13, 4), (20, 0), (20, 3)])
 @pytest.mark.parametrize("cells,step,world", [((5, 4, 6), (1.0, 1.0, 1.0), 1), ((7, 8, 9), (1.0, 0.7, 1.3), 2),
                                                ((8, 7, 11), (0.9, 1.1, 1.0), 3), ((9, 6, 10), (1.0, 1.0, 2.0), 5),
                                                ((20, 13, 15), (1.0, 1.2, 0.8), 2), ((12, 6, 17), (1.0, 1.0, 1.0), 3),
