@@ -395,6 +395,10 @@ int lsb200_describe_plan(lsb200_handle h, char* out, int64_t capacity);
  * of CTA b in block-index order (the single-launch plans only: k_fdi_fused, k_p1_tiles); *n_ctas = CTAs of the launch.
  * Shows which role of a launch (box chunk, z-face chunk, strip; tile, boundary) ends last. */
 int lsb200_debug_cta_trace(lsb200_handle h, int64_t max_ctas, uint64_t* out, int64_t* n_ctas);
+/* Diagnostics of the persistent CG loop of small systems (csrc/cg_small.cuh): mean microseconds per iteration that CTA 0
+ * spends in each of the eight phases -- p update, barrier, operator, barrier, data rows, barrier + p.q, x / r update,
+ * barrier + rho -- over `iters` iterations.  LSB200_ERR_STATE when the handle iterates launch by launch. */
+int lsb200_debug_small_phases(lsb200_handle h, int iters, double* out_us);
 
 #ifdef __cplusplus
 }

@@ -117,6 +117,7 @@ SIGNATURES = {
     "lsb200_host_free": (C.c_int, [C.c_void_p]),
     "lsb200_time_kernel": (C.c_int, [Handle, C.c_int, C.c_int, c_double_p]),
     "lsb200_describe_plan": (C.c_int, [Handle, C.c_char_p, C.c_int64]),
+    "lsb200_debug_small_phases": (C.c_int, [Handle, C.c_int, c_double_p]),
     "lsb200_debug_cta_trace": (C.c_int, [Handle, C.c_int64, C.POINTER(C.c_uint64), c_int64_p]),
 }
 

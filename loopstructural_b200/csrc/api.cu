@@ -1830,7 +1830,7 @@ static void plan_small(lsb200_ctx* h) {
   }
   if (grid < 1) return;
   if (!h->small_bar) {
-    if (cudaMalloc(&h->small_bar, 2 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(h->small_bar, 0, 2 * sizeof(unsigned int)) != cudaSuccess ||
+    if (cudaMalloc(&h->small_bar, 64 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(h->small_bar, 0, 64 * sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc(&h->small_slots, sizeof(double) * 2 * SMALL_MAX_CTAS) != cudaSuccess) {
       cudaGetLastError();
       return;
@@ -1851,6 +1851,7 @@ static int launch_small(lsb200_ctx* h, int iters) {
     if (rb.n > 0) a.blocks[a.nblocks++] = rb;
   a.iters = iters;
   a.bar = h->small_bar;
+  CK(cudaMemsetAsync(h->small_bar, 0, sizeof(unsigned int), h->stream));  // the arrival counter of the launch's barriers
   a.slots = h->small_slots;
   a.sc = h->sc;
   if (h->kind == LSB200_SUPPORT_GRID) {
@@ -2713,6 +2714,40 @@ int lsb200_debug_cta_trace(lsb200_handle h, int64_t max_ctas, uint64_t* out, int
   h->have_c = false;
   if (se != cudaSuccess) return fail(LSB200_ERR_CUDA, "trace launch: %s", cudaGetErrorString(se));
   *n_ctas = ctas;
+  return rc;
+}
+
+// Diagnostics: `iters` iterations of the persistent CG loop with CTA 0's phase clock switched on; out_us[0..7] = mean
+// microseconds per iteration CTA 0 spent in: p update, barrier, operator, barrier, data rows, barrier + p.q, x/r update,
+// barrier + rho (a barrier's figure includes the wait for the slowest CTA of the phase before it).
+int lsb200_debug_small_phases(lsb200_handle h, int iters, double* out_us) {
+  if (!h || !out_us || iters < 1) return fail(LSB200_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(h->device));
+  int rc = lsb200_finalize_system(h);
+  if (rc) return rc;
+  if (!h->small_ok) return fail(LSB200_ERR_STATE, "the handle does not use the persistent CG loop");
+  CgScalars s{};
+  s.rho = 1.0; s.pq = 1.0; s.pq_part[0] = 1.0; s.beta = 0.5; s.thr2 = 0.0; s.maxiter = 1LL << 60; s.nranks = h->nranks;
+  *h->sc_host = s;
+  CK(cudaMemcpyAsync(h->p, h->rhs, sizeof(double) * (size_t)h->g.nall, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->r, h->rhs, sizeof(double) * (size_t)h->g.nall, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->sc, h->sc_host, sizeof(CgScalars), cudaMemcpyHostToDevice, h->stream));
+  if ((rc = launch_small(h, 3))) return rc;  // warm
+  unsigned long long* buf = nullptr;
+  CK(cudaMalloc(&buf, sizeof(unsigned long long) * 8));
+  CK(cudaMemset(buf, 0, sizeof(unsigned long long) * 8));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpyToSymbol(g_cta_trace, &buf, sizeof(buf)));
+  rc = launch_small(h, iters);
+  const cudaError_t se = cudaStreamSynchronize(h->stream);
+  unsigned long long* none = nullptr;
+  cudaMemcpyToSymbol(g_cta_trace, &none, sizeof(none));
+  unsigned long long ns[8] = {0};
+  if (rc == 0 && se == cudaSuccess) cudaMemcpy(ns, buf, sizeof(ns), cudaMemcpyDeviceToHost);
+  cudaFree(buf);
+  h->have_c = false;
+  if (se != cudaSuccess) return fail(LSB200_ERR_CUDA, "phase trace launch: %s", cudaGetErrorString(se));
+  for (int k = 0; k < 8; ++k) out_us[k] = 1e-3 * (double)ns[k] / iters;
   return rc;
 }
 

@@ -35,24 +35,29 @@ struct SmallCgArgs {
   RowBlock blocks[SMALL_MAX_BLOCKS];
   int nblocks;
   int iters;                   // iterations of this launch
-  unsigned int* bar;           // [0] arrivals, [1] generation (zero between launches)
+  unsigned int* bar;           // [0] arrivals of all barriers of this launch (zeroed by the host in front of it)
   double* slots;               // 2 * SMALL_MAX_CTAS partial sums
   CgScalars* sc;
 };
 
-// sense-reversing grid barrier; `gen` is the generation this CTA expects to leave (kept in a register by every thread)
+// grid barrier on ONE monotonic counter (zero at launch): a CTA adds its arrival and polls the same word until the
+// arrivals of barrier number `gen` are complete -- one atomic round trip and one poll, where a counter that is reset plus
+// a generation flag costs the last arriver a second round trip before anybody can leave.  `gen`: barriers passed so far,
+// kept in a register by every thread.  The poll is bounded: a CTA that never arrives traps the launch instead of hanging it.
+__device__ __forceinline__ unsigned int small_poll(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void small_barrier(unsigned int* bar, const unsigned int nctas, unsigned int& gen, const int tid) {
   __syncthreads();
   if (tid == 0) {
+    const unsigned int target = (gen + 1u) * nctas;
     __threadfence();
-    const unsigned int arrived = atomicAdd(&bar[0], 1u);
-    if (arrived == nctas - 1) {
-      bar[0] = 0u;
-      __threadfence();
-      atomicExch(&bar[1], gen + 1u);
-    } else {
-      while (*reinterpret_cast<volatile unsigned int*>(&bar[1]) == gen) {
-      }
+    atomicAdd(&bar[0], 1u);
+    unsigned int spins = 0;
+    while (small_poll(&bar[0]) < target) {
+      if (++spins > (1u << 25)) __trap();
     }
     __threadfence();
   }
@@ -108,7 +113,19 @@ __device__ __forceinline__ void small_cg_loop(const SmallCgArgs& a, const GridDe
   const long long maxiter = sc->maxiter;
   int done = sc->done, info = sc->info;
   double rho_new = sc->rho_new, pq = sc->pq;
-  unsigned int gen = *reinterpret_cast<volatile unsigned int*>(&a.bar[1]);
+  unsigned int gen = 0;  // the host zeroes the counter in front of every launch
+  // diagnostics (lsb200_debug_small_phases): CTA 0 adds up how long it spends in each phase and at each barrier
+  unsigned long long* tr = (cta == 0 && tid == 0) ? g_cta_trace : nullptr;
+  unsigned long long t_prev = 0;
+  if (tr) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_prev));
+  auto mark = [&](const int k) {
+    if (tr) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      tr[k] += t - t_prev;
+      t_prev = t;
+    }
+  };
   // every CTA has read the state before CTA 0 may publish a new one: the first barrier below orders that
   const long long n2 = a.n >> 1;
   for (int it = 0; it < a.iters && !done; ++it) {
@@ -133,10 +150,14 @@ __device__ __forceinline__ void small_cg_loop(const SmallCgArgs& a, const GridDe
         a.p[i] = (a.s2 ? a.s2[i] * a.r[i] : a.r[i]) + beta * a.p[i];
       }
     }
+    mark(0);
     small_barrier(a.bar, nctas, gen, tid);
+    mark(1);
     // ---- q = N_reg p, this CTA's share of the operator's launch plan; then the data rows on top of it
     double dot = reg();
+    mark(2);
     small_barrier(a.bar, nctas, gen, tid);
+    mark(3);
     for (int b = 0; b < a.nblocks; ++b) {
       const RowBlock& rb = a.blocks[b];
       switch (rb.k) {
@@ -150,8 +171,10 @@ __device__ __forceinline__ void small_cg_loop(const SmallCgArgs& a, const GridDe
       const double bsum = block_sum<NT>(dot, red);
       if (tid == 0) a.slots[cta] = bsum;
     }
+    mark(4);
     small_barrier(a.bar, nctas, gen, tid);
     pq = small_sum<NT>(a.slots, nctas, tid, red);
+    mark(5);
     // ---- x += alpha p ; r -= alpha q ; rho_new = r . S^2 r
     const double alpha = rho / pq;
     double acc = 0.0;
@@ -189,8 +212,10 @@ __device__ __forceinline__ void small_cg_loop(const SmallCgArgs& a, const GridDe
       const double bsum = block_sum<NT>(acc, red);
       if (tid == 0) a.slots[SMALL_MAX_CTAS + cta] = bsum;
     }
+    mark(6);
     small_barrier(a.bar, nctas, gen, tid);
     rho_new = small_sum<NT>(a.slots + SMALL_MAX_CTAS, nctas, tid, red);
+    mark(7);
     // ---- scalar step (cg_scalar_step, on the local copy)
     beta = rho_new / rho;
     rho = rho_new;

@@ -422,6 +422,13 @@ class Engine:
         nat.check(self._lib.lsb200_describe_plan(self._h, buf, 512))
         return buf.value.decode()
 
+    def small_phases(self, iters: int = 64) -> dict:
+        """Mean microseconds per iteration of the persistent CG loop by phase, as CTA 0 sees them (diagnostics)."""
+        out = np.zeros(8)
+        nat.check(self._lib.lsb200_debug_small_phases(self._h, int(iters), nat.dptr(out)))
+        names = ("p_update", "barrier_p", "operator", "barrier_q", "rows", "barrier_pq", "xr_update", "barrier_rho")
+        return {k: float(v) for k, v in zip(names, out)}
+
     def cta_trace(self, max_ctas: int = 1 << 18) -> np.ndarray:
         """(n_ctas, 3) uint64: start ns, end ns, SM id of every CTA of one launch of the regularisation operator."""
         out = np.zeros((max_ctas, 3), dtype=np.uint64)

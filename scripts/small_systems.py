@@ -26,6 +26,10 @@ def run(name, e, add):
            "us_per_iteration_solve": 1e6 * res.solve_seconds / max(int(res.iterations), 1),
            "iteration_us": 1e6 * e.time_kernel(1, 64), "matvec_us": 1e6 * e.time_kernel(0, 20), "launches": int(res.kernel_launches),
            "checksum": float(np.dot(c, np.cos(np.arange(c.size) * 0.37))), "plan": e.describe_plan()}
+    try:
+        out["phases_us"] = {k: round(v, 2) for k, v in e.small_phases(64).items()}
+    except Exception:
+        pass  # launch-by-launch iteration
     print(json.dumps(out), flush=True)
     e.close()
 
