@@ -511,6 +511,76 @@ def test_fdi_directional_regularisation_rows_come_from_the_device(ls):
     assert np.linalg.norm(c_b200 - it.c) / np.sqrt(it.c.size) / float(it.c.max() - it.c.min()) <= 1e-10
 
 
+class _AnalyticFold:
+    """Stands in for FoldEvent: three smooth vector fields (deformed orientation, fold axis, fold normal)."""
+
+    def get_deformed_orientation(self, points):
+        x = np.asarray(points, float)
+        f = lambda a, b, c: np.column_stack([np.sin(a * x[:, 1]) + 0.3, np.cos(b * x[:, 2]) - 0.2 * x[:, 0], 0.5 + np.sin(c * x[:, 0])])  # noqa: E731
+        return f(0.4, 0.7, 0.9), f(0.8, 0.3, 0.5), f(0.6, 0.5, 0.7)
+
+
+@pytest.mark.parametrize("case", ["masked", "no_axis_step3", "nan_in_a_vector"])
+def test_fold_constraints_of_a_bare_fold_interpolator(ls, case):
+    """DiscreteFoldInterpolator.add_fold_constraints through the plug-in without a model around it: a mask function
+    (masked elements carry weight 0 in the reference and are left out here; masked faces get a zero vector), a family
+    switched off and another element step, a fold vector holding a NaN (the reference drops that family, the plug-in hands it
+    to the stock method which does) -- each against the stock class on the same generator state."""
+    import loop_interpolation as li
+    from loop_common.math import rng
+    from loop_common.supports import TetMesh
+
+    from loopstructural_b200 import plugin
+
+    fold = _AnalyticFold()
+    if case == "nan_in_a_vector":
+        base = fold.get_deformed_orientation
+
+        def with_nan(points):
+            d, a, n = base(points)
+            a = a.copy()
+            a[::3, 2] = np.nan
+            return d, a, n
+        fold.get_deformed_orientation = with_nan
+    kw = dict(fold_orientation=4.0, fold_axis_w=3.0, fold_normalisation=1.5, fold_norm=0.8, fold_regularisation=[0.2, 0.05, 0.03])
+    if case == "masked":
+        kw["mask_fn"] = lambda x: np.asarray(x)[:, 0] > 3.0
+    if case == "no_axis_step3":
+        kw.update(fold_axis_w=None, step=3)
+    pts = np.random.default_rng(21).uniform(0.3, 4.5, (50, 3))
+    value = np.column_stack([pts, 0.4 * pts[:, 0] + np.cos(pts[:, 1]), np.ones(50)])
+    tight = {"rtol": 1e-13, "atol": 0.0}
+
+    def solve(solver):
+        mesh = TetMesh(origin=np.zeros(3), nsteps_cells=np.array([6, 5, 6]), step_vector=np.array([1.0, 1.1, 0.9]))
+        it = li.interpolator_map[li.InterpolatorType.DISCRETE_FOLD](mesh, fold)
+        it.set_value_constraints(value.copy())
+        rng.bit_generator.state = np.random.default_rng(77).bit_generator.state
+        it.setup_interpolator(solver=solver, regularisation=0.05, fold_weights=dict(kw)) if solver else \
+            it.setup_interpolator(regularisation=0.05, fold_weights=dict(kw))
+        state_after = rng.bit_generator.state["state"]["state"]
+        assert it.solve_system(solver or "cg", solver_kwargs=tight)
+        return it, state_after
+
+    it, state_b200 = solve("b200")
+    assert type(it).__name__ == "B200DiscreteFoldInterpolator" and it.latest_solve_timing["backend"] == "b200"
+    names = [f["name"] for f in it._b200_generated]
+    if case == "nan_in_a_vector":
+        assert "fold axis" not in names and "fold axis" not in it.constraints and "fold regularisation 3" not in names
+        assert names == ["fold orientation", "fold normalisation", "fold regularisation 1", "fold regularisation 2"]
+    elif case == "no_axis_step3":
+        assert names == ["fold orientation", "fold normalisation", "fold regularisation 1", "fold regularisation 2", "fold regularisation 3"]
+        assert it._b200_generated[0]["data"].shape[0] == -(-it.support.n_elements // 3)
+    else:
+        assert len(names) == 6 and it._b200_generated[0]["data"].shape[0] < -(-it.support.n_elements // 2)
+    c_b200 = np.array(it.c)
+    plugin.uninstall()
+    stock, state_stock = solve(None)
+    assert type(stock).__name__ == "DiscreteFoldInterpolator"
+    assert state_b200 == state_stock  # the generator was advanced exactly as the stock method advances it
+    assert np.linalg.norm(c_b200 - stock.c) / np.sqrt(stock.c.size) / float(stock.c.max() - stock.c.min()) <= 1e-9
+
+
 def test_two_faults_are_applied_as_one_chain(ls, monkeypatch):
     """A feature cut by two faults: BaseFeature._apply_faults hands both frames to lsb200_fault_displace_chain in one
     call (here an oracle stand-in composing the two displacements) and the model's answers equal the stock solver's."""
