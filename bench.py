@@ -408,6 +408,82 @@ def measure_other_configs(local):
         b200.uninstall()
     except Exception as exc:  # noqa: BLE001
         out["configs0_claudius_1e5"] = {"error": f"{type(exc).__name__}: {exc}"}
+    out["configs3_fault_and_fold_models"] = measure_config3()
+    return out
+
+
+def measure_config3(nelements_fault=1e5, nelements_fold=2e4):
+    """configs[3]: a fault network model and a refolded fold-frame model through the unmodified reference's GeologicalModel
+    with plugin.install() and solver='b200' -- load_intrusion: a fault frame (three coupled FDI solves, the orthogonality
+    rows of coordinates 1 and 2 generated on the device) and a foliation faulted by it (its data un-faulted through
+    lsb200_fault_displace); load_laurent2016: a fold frame (FDI), a folded fold frame and a folded foliation
+    (DiscreteFoldInterpolator on tet meshes, fold rows and direction-weighted face rows generated on the device).  Built
+    twice, the second build is reported: wall time of create + update, and per solved interpolator its class, backend,
+    iterations and solve seconds.  Needs baseline/_ref on the box."""
+    out = {}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import refenv
+
+        refenv.activate()
+        import LoopStructural as ls
+        from LoopStructural.datasets import load_intrusion, load_laurent2016
+
+        import loopstructural_b200.plugin as b200
+
+        def solved(model, names):
+            rows = []
+            for name in names:
+                feat = model[name]
+                parts = [feat[i] for i in range(3)] if hasattr(feat, "__getitem__") and type(feat).__name__ != "GeologicalFeature" else [feat]
+                for k, part in enumerate(parts):
+                    it = getattr(part, "interpolator", None)
+                    t = getattr(it, "latest_solve_timing", None) or {}
+                    rows.append({"feature": f"{name}[{k}]" if len(parts) > 1 else name, "class": type(it).__name__,
+                                 "nodes": int(getattr(it, "dof", 0)), "backend": t.get("backend"), "iterations": int(t.get("iterations", 0)),
+                                 "solve_seconds": float(t.get("solve_seconds", 0.0)),
+                                 "rows_generated_on_device": len(getattr(it, "_b200_generated", [])) + len(getattr(it, "_b200_device_rows", []))})
+            return rows
+
+        def on_device(feats):
+            # (a frame coordinate without data of its own is a zero-iteration stock solve: nothing to run anywhere)
+            return all(f["backend"] == "b200" for f in feats if f["class"] != "NoneType" and f["iterations"] > 0)
+
+        b200.install()
+        try:
+            data, bb = load_intrusion()
+            for _ in range(2):
+                model = ls.GeologicalModel(bb[0, :], bb[1, :])
+                model.data = data
+                t0 = time.perf_counter()
+                model.create_and_add_fault("fault", 500, nelements=nelements_fault, interpolatortype="FDI", buffer=0.3, solver="b200")
+                model.create_and_add_foliation("strati", nelements=nelements_fault, interpolatortype="FDI", solver="b200")
+                model.update()
+                wall = time.perf_counter() - t0
+            feats = solved(model, ["fault", "strati"])
+            out["load_intrusion_faulted"] = {"nelements": nelements_fault, "build_wall_seconds": wall, "features": feats,
+                                             "solve_seconds_total": sum(f["solve_seconds"] for f in feats),
+                                             "all_on_device": on_device(feats)}
+            data, bb = load_laurent2016()
+            for _ in range(2):
+                model = ls.GeologicalModel(bb[0, :], bb[1, :])
+                model.data = data
+                t0 = time.perf_counter()
+                s2 = model.create_and_add_fold_frame("s2", nelements=nelements_fold, buffer=0.3, solver="b200")
+                s1 = model.create_and_add_folded_fold_frame("s1", fold_frame=s2, limb_wl=4, av_fold_axis=True, nelements=nelements_fold,
+                                                            buffer=0.3, solver="b200")
+                model.create_and_add_folded_foliation("s0", fold_frame=s1, limb_wl=1.0, av_fold_axis=True, nelements=nelements_fold,
+                                                      buffer=0.3, solver="b200")
+                model.update()
+                wall = time.perf_counter() - t0
+            feats = solved(model, ["s2", "s1", "s0"])
+            out["load_laurent2016_refolded"] = {"nelements": nelements_fold, "build_wall_seconds": wall, "features": feats,
+                                                "solve_seconds_total": sum(f["solve_seconds"] for f in feats),
+                                                "all_on_device": on_device(feats)}
+        finally:
+            b200.uninstall()
+    except Exception as exc:  # noqa: BLE001
+        out["error"] = f"{type(exc).__name__}: {exc}"
     return out
 
 

@@ -76,20 +76,25 @@ inline bool p1_plan_march(const GridDesc& g, const int m[3], const double* table
   pl.tiles_x = (g.nx - 4 + C::TX - 1) / C::TX;
   pl.tiles_y = (g.ny - 4 + C::TY - 1) / C::TY;
   const int planes = pl.b.klast - pl.b.kfirst;
-  // chunks: as many as fit the CTA slots at once (a second wave would double the launch), at least 8 planes per chunk
-  // (each chunk re-stages 4 halo planes)
+  // chunks: as many as fit the CTA slots at once (a second wave would double the launch), at least 4 planes per chunk
+  // (each chunk re-stages 4 halo planes; small meshes leave most slots empty and are bound by the length of a march)
   const long long tiles = (long long)pl.tiles_x * pl.tiles_y, slots = (long long)sm_count * ctas_per_sm;
   const long long nb = pl.b.nbz + pl.b.nby + pl.b.nbx;
-  const long long per_cta = (long long)C::NT * P1M_BND_PER_THREAD;
   int chunks = (int)std::max<long long>(1, slots / tiles);
-  chunks = std::max(1, std::min(chunks, std::max(1, planes / 8)));
+  chunks = std::max(1, std::min(chunks, std::max(1, planes / 4)));
   if (cz_override > 0) chunks = std::max(1, (planes + cz_override - 1) / cz_override);
   for (;; --chunks) {
     pl.cz = planes > 0 ? (planes + chunks - 1) / chunks : 1;
     pl.chunks = planes > 0 ? (planes + pl.cz - 1) / pl.cz : 0;
     pl.n_cta = (int)(tiles * pl.chunks);
-    // boundary-only CTAs when the tiles are too few to carry the boundary shares (always: slabs without interior planes)
-    const long long carried = (long long)pl.n_cta * C::NBT * P1M_BND_PER_THREAD;
+    // the boundary shell: spread over the boundary threads of the tile CTAs and boundary-only CTAs in the slots the
+    // tiles leave free, as few nodes per thread as that allows (a thread walks its nodes one after the other, each a
+    // chain of three dependent loads), at most P1M_BND_PER_THREAD before more CTAs than slots are launched
+    const long long free_slots = std::max<long long>(0, slots - pl.n_cta);
+    const long long threads = (long long)pl.n_cta * C::NBT + free_slots * C::NT;
+    long long per = threads > 0 ? (nb + threads - 1) / threads : P1M_BND_PER_THREAD;
+    per = std::max<long long>(1, std::min<long long>(per, P1M_BND_PER_THREAD));
+    const long long carried = (long long)pl.n_cta * C::NBT * per, per_cta = (long long)C::NT * per;
     pl.b.n_bnd_cta = (carried >= nb || split) ? 0 : (int)((nb - carried + per_cta - 1) / per_cta);
     // they too belong to the first wave: fewer, longer chunks until they fit (or nothing is left to give)
     if (cz_override > 0 || chunks <= 1 || (long long)pl.n_cta + pl.b.n_bnd_cta <= slots) break;
