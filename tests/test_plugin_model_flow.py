@@ -520,7 +520,7 @@ class _AnalyticFold:
         return f(0.4, 0.7, 0.9), f(0.8, 0.3, 0.5), f(0.6, 0.5, 0.7)
 
 
-@pytest.mark.parametrize("case", ["masked", "no_axis_step3", "nan_in_a_vector"])
+@pytest.mark.parametrize("case", ["masked", "no_axis_step3", "nan_in_a_vector", "norm_sign_corrected"])
 def test_fold_constraints_of_a_bare_fold_interpolator(ls, case):
     """DiscreteFoldInterpolator.add_fold_constraints through the plug-in without a model around it: a mask function
     (masked elements carry weight 0 in the reference and are left out here; masked faces get a zero vector), a family
@@ -547,6 +547,8 @@ def test_fold_constraints_of_a_bare_fold_interpolator(ls, case):
         kw["mask_fn"] = lambda x: np.asarray(x)[:, 0] > 3.0
     if case == "no_axis_step3":
         kw.update(fold_axis_w=None, step=3)
+    if case == "norm_sign_corrected":
+        kw.update(dgz_alignment="correct")  # resolve_fold_norm_target flips the target when dgz opposes the normals
     pts = np.random.default_rng(21).uniform(0.3, 4.5, (50, 3))
     value = np.column_stack([pts, 0.4 * pts[:, 0] + np.cos(pts[:, 1]), np.ones(50)])
     tight = {"rtol": 1e-13, "atol": 0.0}
@@ -555,6 +557,9 @@ def test_fold_constraints_of_a_bare_fold_interpolator(ls, case):
         mesh = TetMesh(origin=np.zeros(3), nsteps_cells=np.array([6, 5, 6]), step_vector=np.array([1.0, 1.1, 0.9]))
         it = li.interpolator_map[li.InterpolatorType.DISCRETE_FOLD](mesh, fold)
         it.set_value_constraints(value.copy())
+        if case == "norm_sign_corrected":
+            npts = pts[:20]
+            it.set_normal_constraints(np.column_stack([npts, -fold.get_deformed_orientation(npts)[2], np.ones(20)]))
         rng.bit_generator.state = np.random.default_rng(77).bit_generator.state
         it.setup_interpolator(solver=solver, regularisation=0.05, fold_weights=dict(kw)) if solver else \
             it.setup_interpolator(regularisation=0.05, fold_weights=dict(kw))
@@ -571,6 +576,9 @@ def test_fold_constraints_of_a_bare_fold_interpolator(ls, case):
     elif case == "no_axis_step3":
         assert names == ["fold orientation", "fold normalisation", "fold regularisation 1", "fold regularisation 2", "fold regularisation 3"]
         assert it._b200_generated[0]["data"].shape[0] == -(-it.support.n_elements // 3)
+    elif case == "norm_sign_corrected":
+        fam = [f for f in it._b200_generated if f["name"] == "fold normalisation"][0]
+        assert np.all(fam["data"][:, 6] == -0.8 * 1.5)  # target = -fold_norm (corrected) * fold_normalisation
     else:
         assert len(names) == 6 and it._b200_generated[0]["data"].shape[0] < -(-it.support.n_elements // 2)
     c_b200 = np.array(it.c)
