@@ -41,7 +41,7 @@ struct P1MarchPlan {
   X(3, 4, 4, 2)              \
   X(4, 4, 2, 3)
 #define LSB_P1_MARCH_DEFAULT 3
-constexpr int P1M_BND_PER_THREAD = 6;  // boundary nodes a thread may be given before the plan adds boundary-only CTAs
+constexpr int P1M_BND_PER_THREAD = 6;  // boundary nodes per thread the plan accepts before it launches more CTAs than slots
 template <int NW, int NB = 0>
 struct P1MarchCfg {
   static constexpr int NM = 32 * NW;               // marching threads
