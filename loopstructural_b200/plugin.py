@@ -235,6 +235,11 @@ class _B200Mixin:
 
     def reset(self):
         super().reset()
+        if hasattr(self, "_b200_generated"):
+            # the stock reset empties self.constraints (LI/_discrete_interpolator.py:300-314): what a diverted set-up recorded
+            # instead of assembling goes with it
+            self._b200_reg, self._b200_reg_ops, self._b200_explicit = {}, {}, {}
+            self._b200_device_rows, self._b200_generated = [], []
         if getattr(self, "_b200_divert", False):
             # DiscreteInterpolator.reset allocates np.ones(dof) (LI/_discrete_interpolator.py:313); only the explicit
             # stencil assembly with use_regularisation_weight_scale reads it, and that case is never diverted

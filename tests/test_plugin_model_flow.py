@@ -469,6 +469,10 @@ def test_p1_directional_regularisation_rows_come_from_the_device(ls):
     it.setup_interpolator(solver="b200", regularisation=0.05, directional_regularisation=terms)
     assert [(f["type"], f["name"]) for f in it._b200_generated] == [("face", "along")]
     assert "along" not in it.constraints and "broken" not in it.constraints and it._b200_reg == {"cgw": 0.05}
+    it.reset()  # the stock reset empties the constraint dict: the recorded families go with it
+    assert it._b200_generated == [] and it._b200_reg == {} and not it.constraints
+    it.setup_interpolator(solver="b200", regularisation=0.05, directional_regularisation=terms)
+    assert [(f["type"], f["name"]) for f in it._b200_generated] == [("face", "along")]
     tight = {"rtol": 1e-13, "atol": 0.0}
     assert it.solve_system("b200", solver_kwargs=tight) and it.latest_solve_timing["backend"] == "b200"
     assert it._b200_engine.device_families == 1
