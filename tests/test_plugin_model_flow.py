@@ -593,6 +593,40 @@ def test_fold_constraints_of_a_bare_fold_interpolator(ls, case):
     assert np.linalg.norm(c_b200 - stock.c) / np.sqrt(stock.c.size) / float(stock.c.max() - stock.c.min()) <= 1e-9
 
 
+@pytest.mark.parametrize("case", ["weight_scale", "custom_operators"])
+def test_set_ups_the_engine_cannot_apply_matrix_free_are_solved_from_explicit_rows(ls, case):
+    """use_regularisation_weight_scale=True (per-node weights on the stencil rows, LI/_finite_difference_interpolator.py:643-692)
+    and a caller-supplied operators= dict: nothing is diverted, the reference assembles its families, and solver='b200'
+    solves exactly that system from explicit rows (families that ARE default masks with one weight still go matrix-free)."""
+    import loop_interpolation as li
+    from loop_common.supports import StructuredGrid
+    from loop_interpolation._operator import Operator
+
+    from loopstructural_b200 import plugin
+    from oracle import fdi_oracle as fo
+
+    grid, value, gradient = fo.synthetic_problem(12, 200, 30, seed=3)
+    sg = StructuredGrid(origin=grid.origin, nsteps_cells=grid.nsteps - 1, step_vector=grid.step)
+    kw = dict(use_regularisation_weight_scale=True) if case == "weight_scale" else \
+        dict(operators={"laplacian": (Operator.Lapacian.astype(float), 0.7), "dxx": (Operator.Dxx_mask, 0.4)})
+    tight = {"rtol": 1e-12, "atol": 0.0}
+
+    def run(cls, solver):
+        it = cls(sg)
+        it.set_value_constraints(value.copy())
+        it.set_normal_constraints(gradient.copy())
+        it.setup_interpolator(**(dict(kw, solver=solver) if solver == "b200" else kw))
+        assert it.solve_system(solver, solver_kwargs=tight)
+        return it
+
+    a = run(li.interpolator_map[li.InterpolatorType.FINITE_DIFFERENCE], "b200")
+    assert type(a).__name__ == "B200FiniteDifferenceInterpolator" and a.latest_solve_timing["backend"] == "b200"
+    assert a._b200_generated == [] and ("laplacian" in a.constraints or case == "weight_scale")
+    b = run(plugin._installed["stock"][li.InterpolatorType.FINITE_DIFFERENCE], "cg")
+    assert b.latest_solve_timing["backend"] == "python"
+    assert np.abs(a.c - b.c).max() <= 1e-9 * np.abs(b.c).max()
+
+
 def test_two_faults_are_applied_as_one_chain(ls, monkeypatch):
     """A feature cut by two faults: BaseFeature._apply_faults hands both frames to lsb200_fault_displace_chain in one
     call (here an oracle stand-in composing the two displacements) and the model's answers equal the stock solver's."""
